@@ -1,0 +1,174 @@
+/* include/krepp_b200.h -- C ABI of the B200-native krepp query path (`krepp dist` / `krepp place`).
+ *
+ * This is the drop-in boundary.  The reference (bo1929/krepp v0.8.3) has no plugin/FFI layer; its seam for this path
+ * is the C++ class IBatch (src/query.hpp:46-97) sitting on Index (src/index.hpp:11-42).  Each entry point below names
+ * the reference interface it replaces (file:line relative to the reference tree).  Plain pointers and sizes only; no
+ * C++ or torch types cross this boundary; no exceptions cross it (status codes + krepp_last_error()).
+ *
+ * Threading: an index handle is immutable after open and may be shared; a batch handle ("slot") owns one CUDA stream
+ * and its buffers and must be driven by one host thread at a time.  Several slots on one index pipeline H2D / kernels
+ * / D2H.  There is NO CPU fallback: every call that needs the GPU fails with KREPP_ERR_CUDA when none is usable.
+ */
+#ifndef KREPP_B200_H
+#define KREPP_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KREPP_ABI_VERSION 1
+#define KREPP_MAX_TH 16 /* k-h <= 16 positions survive in the 32-bit residual encoding (src/lshf.cpp:39-54) */
+
+enum {
+  KREPP_OK = 0,
+  KREPP_ERR_ARG = 1,      /* invalid argument / configuration (src/krepp.hpp:192-204 validate_configuration_*) */
+  KREPP_ERR_IO = 2,       /* index directory or file unreadable / malformed (src/index.cpp:51-158 error_exit paths) */
+  KREPP_ERR_CUDA = 3,     /* no usable device, launch or copy failure */
+  KREPP_ERR_CAPACITY = 4, /* a batch exceeded the slot's declared capacity */
+  KREPP_ERR_UNSUPPORTED = 5
+};
+
+typedef struct krepp_index krepp_index_t;
+typedef struct krepp_batch krepp_batch_t;
+
+/* -------------------------------------------------------------------------------------------------- index */
+
+typedef struct {
+  uint32_t k, w, h, m, r, frac;    /* metadata-* (src/krepp.cpp:18-29) */
+  uint32_t nrows;                  /* rows of the flat table = entries of inc-* (src/table.cpp:71-73) */
+  uint64_t nkmers;                 /* entries of cmer-* (src/table.cpp:67-69) */
+  uint32_t nnodes;                 /* tree nodes; se runs 1..nnodes, 0 is the null sentinel (src/phytree.hpp:53) */
+  uint32_t nleaves;
+  uint32_t nsubsets;               /* colour ids in crecord-* (src/record.cpp:203-211) */
+  uint32_t root_se;
+  uint64_t mask_hash_bp;           /* LSHF::mask_hash_bp (src/lshf.cpp:47-50) */
+  uint64_t mask_drop_lr;           /* LSHF::mask_drop_lr (src/lshf.cpp:39-46) */
+  uint64_t device_bytes;           /* HBM held by the index image */
+  double mean_bucket, size_biased_bucket; /* occupancy statistics used to pick the scan group width */
+} krepp_index_info_t;
+
+/* Replaces TargetIndex::load_index (src/krepp.cpp:66-108) + Index::load_partial_tree/_index + make_rho_partial
+ * (src/index.cpp:29-158,188-201) + FlatHT::load (src/table.cpp:65-75) + CRecord::load (src/record.cpp:203-211) +
+ * Tree::load (src/phytree.cpp:394-404): reads the on-disk index written by `krepp index` unchanged and uploads the
+ * flat image to `device`.  Round-1 scope: one partial suffix per directory, with a backbone tree file. */
+#define KREPP_DEVICE_NONE (-1) /* parse + validate only (metadata, tree, names); batches cannot be created on it */
+int krepp_index_open(const char* index_dir, int device, krepp_index_t** out);
+void krepp_index_close(krepp_index_t* ix);
+int krepp_index_info(const krepp_index_t* ix, krepp_index_info_t* out);
+/* Node::get_name(return_na) (src/phytree.hpp:133-144): label, else to_string(se-1) or "NA".  Pointer valid until the
+ * next call from the same thread. */
+const char* krepp_index_node_name(const krepp_index_t* ix, uint32_t se, int return_na);
+/* Flattened phytree arrays, each of length nnodes+1 and indexed by se (src/phytree.hpp:95-131,156): parent se (0 for
+ * the root), number of children, leaf flag, branch length (NaN when absent).  Any output pointer may be NULL. */
+int krepp_index_tree(const krepp_index_t* ix, uint32_t* parent, uint32_t* nchildren, uint8_t* is_leaf, double* blen);
+/* Tree::stream_nwk_jplace (src/phytree.cpp:47-64): edge-numbered Newick, std::fixed precision 5.  Returns the number
+ * of bytes needed (excluding NUL); writes at most cap bytes including the NUL. */
+size_t krepp_index_jplace_tree(const krepp_index_t* ix, char* buf, size_t cap);
+
+/* -------------------------------------------------------------------------------------------------- parameters */
+
+/* The IBatch constructor arguments (src/query.hpp:49-57, src/query.cpp:8-38) plus the CLI's `tabular` switch. */
+typedef struct {
+  uint32_t hdist_th;  /* --hdist-th [4] */
+  double chisq;       /* --chisq [2.706] */
+  double dist_max;    /* --dist-max [NaN = unset] */
+  uint32_t tau;       /* --tau [2] */
+  int32_t no_filter;  /* dist default 1 (src/krepp.cpp:637-642), place default 0 (:614-617) */
+  int32_t multi;      /* [1] */
+  int32_t summarize;  /* [0] */
+  int32_t place;      /* 0: IBatch::estimate_distances (src/query.cpp:141-156); 1: place_sequences (:198-216) */
+} krepp_params_t;
+
+void krepp_params_default(krepp_params_t* p, int place);
+
+/* -------------------------------------------------------------------------------------------------- results */
+
+/* One (read, strand, leaf) Hamming histogram = one Minfo of IMers::leaf_to_minfo (src/query.hpp:43,213-226). */
+typedef struct {
+  uint32_t read;        /* index of the read inside the batch */
+  uint32_t leaf_se;     /* Node::se of the reference genome */
+  uint32_t strand;      /* 0 forward, 1 reverse complement */
+  uint32_t match_count; /* Minfo::match_count */
+  uint32_t hdist_min;   /* Minfo::hdist_min */
+  uint32_t flags;       /* KREPP_REC_* */
+  double rho;           /* CRecord::se_to_rho after make_rho_partial */
+  double d_llh, v_llh;  /* Minfo::optimize_likelihood (src/query.cpp:426-433); DBL_MAX / NaN when not solved */
+  double chisq;         /* Minfo::likelihood_ratio vs the closest (src/query.cpp:420-424); NaN when not computed */
+} krepp_record_t;
+#define KREPP_REC_SOLVED 1u   /* passed the hdist_filt gate of summarize_matches (src/query.cpp:106,119) */
+#define KREPP_REC_SELECTED 2u /* is the entry of IBatch::node_to_minfo for its leaf (src/query.cpp:114,127-137) */
+#define KREPP_REC_CLOSEST 4u  /* is IBatch::mi_closest (src/query.cpp:110-113,123-126) */
+
+/* One candidate placement = one PP_JPLACE_FIELDS row (src/query.hpp:202-204, src/query.cpp:284-310). */
+typedef struct {
+  uint32_t read, se;                               /* edge_num = se-1 (src/phytree.hpp:156) */
+  double pendant, distal, loglik, lwr, d_llh, chisq;
+} krepp_placement_t;
+
+typedef struct {
+  uint32_t onmers;        /* IBatch::onmers: valid k-mer windows (src/query.cpp:66) */
+  uint32_t wn[2];         /* IBatch::wnmers_or / wnmers_rc: eligible lookups per strand (src/query.cpp:85,90) */
+  uint32_t hdist_filt[2]; /* IMers::hdist_filt per strand before the 2x+1 of summarize_matches (0xffffffff: none) */
+  uint32_t rec_begin, rec_count;     /* this read's records[]: forward leaves by ascending se, then reverse */
+  uint32_t place_begin, place_count; /* this read's placements[] by ascending se */
+  int32_t closest;                   /* index into records[] of mi_closest, -1 when node_to_minfo is empty */
+} krepp_read_summary_t;
+
+typedef struct {
+  uint32_t n_reads;
+  uint32_t hist_stride;               /* hdist_th + 1 */
+  uint64_t n_records, n_placements;
+  const krepp_read_summary_t* reads;  /* [n_reads] */
+  const krepp_record_t* records;      /* [n_records] */
+  const uint32_t* hist;               /* [n_records * hist_stride]: Minfo::hdisthist_v */
+  const krepp_placement_t* placements;/* [n_placements] */
+  float gpu_ms;                       /* device time of this batch (CUDA events on the slot's stream) */
+  uint32_t gpu_launches;              /* kernels launched for this batch */
+} krepp_results_t;
+
+/* -------------------------------------------------------------------------------------------------- batches */
+
+/* Replaces the IBatch constructor (src/query.cpp:8-38).  max_reads / max_bases size the slot's pinned and device
+ * buffers once; a larger submit returns KREPP_ERR_CAPACITY. */
+int krepp_batch_create(krepp_index_t* ix, const krepp_params_t* p, uint32_t max_reads, uint64_t max_bases,
+                       krepp_batch_t** out);
+void krepp_batch_destroy(krepp_batch_t* b);
+
+/* Replaces IBatch::estimate_distances / place_sequences up to (not including) text formatting (src/query.cpp:141-156,
+ * 198-216): `bases` holds the reads' ASCII characters back to back, read i is bases[offsets[i] .. offsets[i+1]).
+ * HOST buffers; the call stages them through the slot's pinned memory, enqueues H2D, all kernels and D2H on the slot's
+ * stream and returns without waiting.  The caller may reuse `bases`/`offsets` as soon as the call returns. */
+int krepp_batch_submit(krepp_batch_t* b, const char* bases, const uint64_t* offsets, uint32_t n_reads);
+
+/* The slot's own pinned input buffers (max_bases + 64 bytes, max_reads + 1 offsets).  A producer that parses reads
+ * straight into them and then passes the same pointers to krepp_batch_submit skips the staging copy. */
+int krepp_batch_host_buffers(krepp_batch_t* b, char** bases, uint64_t** offsets);
+
+/* Same work with inputs already resident in HBM (device pointers on the index's device); nothing is copied in.  Used
+ * to measure kernel-side throughput and by callers that produce reads on the device. */
+int krepp_batch_submit_device(krepp_batch_t* b, const char* d_bases, const uint64_t* d_offsets, uint32_t n_reads,
+                              uint64_t n_bases);
+
+/* Waits for the slot's stream and exposes the results (library-owned pinned host memory, valid until the next submit
+ * on this slot).  Replaces reading IBatch::node_to_minfo / get_summary() (src/query.hpp:64,95). */
+int krepp_batch_wait(krepp_batch_t* b, krepp_results_t* out);
+
+/* Parity taps (SURVEY.md section 8b "dump_stage").  stage 1: every eligible lookup of the last submitted batch as
+ * 4 x u32 {read, strand<<31|pos, rix, enc32}, unordered (src/query.cpp:82-91 arguments of add_matching_mer).
+ * Must be enabled before submit with krepp_batch_enable_tap.  Returns the number of items through *n. */
+int krepp_batch_enable_tap(krepp_batch_t* b, int stage, uint64_t capacity_items);
+int krepp_batch_read_tap(krepp_batch_t* b, int stage, uint32_t* out, uint64_t cap_items, uint64_t* n);
+
+/* Roofline accounting of the last waited batch: algorithmic bytes = sum over reads of
+ * len + sum over eligible lookups (16 + 8*|bucket|) + 64 * records, computed on the device while matching. */
+int krepp_batch_algorithmic_bytes(krepp_batch_t* b, uint64_t* bytes, uint64_t* lookups, uint64_t* entries_scanned);
+
+const char* krepp_last_error(void);
+int krepp_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

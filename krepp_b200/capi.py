@@ -1,0 +1,262 @@
+"""ctypes binding of include/krepp_b200.h, shaped like the reference's seam:
+
+    reference (C++)                                     here
+    ------------------------------------------------    ---------------------------------------------
+    Index(dir); load_partial_*; make_rho_partial        Index(dir, device)
+    IBatch(index, qs, hdist_th, chisq, dist_max, tau,   IBatch(index, reads, hdist_th=4, chisq=2.706, dist_max=nan,
+           no_filter, multi, summarize)                        tau=2, no_filter=True, multi=True, summarize=False)
+    IBatch::estimate_distances(stream)                  IBatch.estimate_distances() -> TSV text (src/query.cpp:141-196)
+    IBatch::node_to_minfo / Minfo fields                IBatch.results()  (numpy views of the C result structs)
+
+Everything is computed by libkrepp_b200.so on the GPU; if the library or a device is missing the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "csrc")
+_LIB = os.path.join(_HERE, "_build", "libkrepp_b200.so")
+
+
+class KreppError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"[krepp_b200 error {code}] {msg}")
+        self.code = code
+
+
+class Params(C.Structure):
+    _fields_ = [("hdist_th", C.c_uint32), ("chisq", C.c_double), ("dist_max", C.c_double), ("tau", C.c_uint32),
+                ("no_filter", C.c_int32), ("multi", C.c_int32), ("summarize", C.c_int32), ("place", C.c_int32)]
+
+
+class IndexInfo(C.Structure):
+    _fields_ = [("k", C.c_uint32), ("w", C.c_uint32), ("h", C.c_uint32), ("m", C.c_uint32), ("r", C.c_uint32),
+                ("frac", C.c_uint32), ("nrows", C.c_uint32), ("nkmers", C.c_uint64), ("nnodes", C.c_uint32),
+                ("nleaves", C.c_uint32), ("nsubsets", C.c_uint32), ("root_se", C.c_uint32), ("mask_hash_bp", C.c_uint64),
+                ("mask_drop_lr", C.c_uint64), ("device_bytes", C.c_uint64), ("mean_bucket", C.c_double),
+                ("size_biased_bucket", C.c_double)]
+
+
+class Results(C.Structure):
+    _fields_ = [("n_reads", C.c_uint32), ("hist_stride", C.c_uint32), ("n_records", C.c_uint64), ("n_placements", C.c_uint64),
+                ("reads", C.c_void_p), ("records", C.c_void_p), ("hist", C.c_void_p), ("placements", C.c_void_p),
+                ("gpu_ms", C.c_float), ("gpu_launches", C.c_uint32)]
+
+
+RECORD_DTYPE = np.dtype([("read", "<u4"), ("leaf_se", "<u4"), ("strand", "<u4"), ("match_count", "<u4"), ("hdist_min", "<u4"),
+                         ("flags", "<u4"), ("rho", "<f8"), ("d_llh", "<f8"), ("v_llh", "<f8"), ("chisq", "<f8")])
+READ_DTYPE = np.dtype([("onmers", "<u4"), ("wn", "<u4", (2,)), ("hdist_filt", "<u4", (2,)), ("rec_begin", "<u4"),
+                       ("rec_count", "<u4"), ("place_begin", "<u4"), ("place_count", "<u4"), ("closest", "<i4")])
+PLACEMENT_DTYPE = np.dtype([("read", "<u4"), ("se", "<u4"), ("pendant", "<f8"), ("distal", "<f8"), ("loglik", "<f8"),
+                            ("lwr", "<f8"), ("d_llh", "<f8"), ("chisq", "<f8")])
+REC_SOLVED, REC_SELECTED, REC_CLOSEST = 1, 2, 4
+
+
+def library_path() -> str:
+    return _LIB
+
+
+def build_library(verbose: bool = False) -> str:
+    """Compiles csrc/ for sm_100a with nvcc (cross-compiles without a GPU)."""
+    subprocess.run(["make", "-C", _CSRC] + ([] if verbose else ["-s"]), check=True)
+    return _LIB
+
+
+_lib = None
+
+
+def load_library():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB):
+        raise KreppError(3, f"{_LIB} is missing: build it with krepp_b200.build_library() / make -C krepp_b200/csrc "
+                            "(there is no CPU fallback)")
+    L = C.CDLL(_LIB)
+    L.krepp_last_error.restype = C.c_char_p
+    L.krepp_index_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+    L.krepp_index_close.argtypes = [C.c_void_p]
+    L.krepp_index_info.argtypes = [C.c_void_p, C.POINTER(IndexInfo)]
+    L.krepp_index_node_name.restype = C.c_char_p
+    L.krepp_index_node_name.argtypes = [C.c_void_p, C.c_uint32, C.c_int]
+    L.krepp_index_tree.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.krepp_index_jplace_tree.restype = C.c_size_t
+    L.krepp_index_jplace_tree.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+    L.krepp_params_default.argtypes = [C.POINTER(Params), C.c_int]
+    L.krepp_batch_create.argtypes = [C.c_void_p, C.POINTER(Params), C.c_uint32, C.c_uint64, C.POINTER(C.c_void_p)]
+    L.krepp_batch_destroy.argtypes = [C.c_void_p]
+    L.krepp_batch_host_buffers.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    L.krepp_batch_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+    L.krepp_batch_submit_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64]
+    L.krepp_batch_wait.argtypes = [C.c_void_p, C.POINTER(Results)]
+    L.krepp_batch_enable_tap.argtypes = [C.c_void_p, C.c_int, C.c_uint64]
+    L.krepp_batch_read_tap.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.krepp_batch_algorithmic_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    _lib = L
+    return L
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise KreppError(rc, load_library().krepp_last_error().decode())
+
+
+def _view(ptr, dtype, n):
+    if not ptr or n == 0:
+        return np.zeros(0, dtype=dtype)
+    buf = (C.c_char * (dtype.itemsize * n)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype, count=n)
+
+
+class Index:
+    """Index image resident on one GPU (replaces Index + TargetIndex::load_index, src/krepp.cpp:66-108)."""
+
+    def __init__(self, index_dir: str, device: int = 0):
+        L = load_library()
+        self._h = C.c_void_p()
+        _check(L.krepp_index_open(os.fsencode(index_dir), device, C.byref(self._h)))
+        self.info = IndexInfo()
+        _check(L.krepp_index_info(self._h, C.byref(self.info)))
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().krepp_index_close(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def node_name(self, se: int, return_na: bool = False) -> str:
+        return load_library().krepp_index_node_name(self._h, se, int(return_na)).decode()
+
+    def tree(self):
+        n = self.info.nnodes + 1
+        parent, nch = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+        leaf, blen = np.zeros(n, np.uint8), np.zeros(n, np.float64)
+        _check(load_library().krepp_index_tree(self._h, parent.ctypes.data, nch.ctypes.data, leaf.ctypes.data, blen.ctypes.data))
+        return dict(parent=parent, nchildren=nch, is_leaf=leaf, blen=blen)
+
+    def jplace_tree(self) -> str:
+        L = load_library()
+        n = L.krepp_index_jplace_tree(self._h, None, 0)
+        buf = C.create_string_buffer(n + 1)
+        L.krepp_index_jplace_tree(self._h, buf, n + 1)
+        return buf.value.decode()
+
+
+def pack_reads(reads) -> tuple[np.ndarray, np.ndarray]:
+    """reads: (n, L) uint8 matrix, or a list of bytes.  Returns (bases uint8[total], offsets uint64[n+1])."""
+    if isinstance(reads, np.ndarray) and reads.ndim == 2:
+        n, ln = reads.shape
+        return np.ascontiguousarray(reads).reshape(-1), (np.arange(n + 1, dtype=np.uint64) * np.uint64(ln))
+    lens = np.fromiter((len(r) for r in reads), dtype=np.uint64, count=len(reads))
+    offs = np.zeros(len(reads) + 1, dtype=np.uint64)
+    np.cumsum(lens, out=offs[1:])
+    return np.frombuffer(b"".join(reads), dtype=np.uint8), offs
+
+
+class IBatch:
+    """One batch of reads on one slot; mirrors IBatch (src/query.hpp:46-97)."""
+
+    def __init__(self, index: Index, reads, names=None, hdist_th: int = 4, chisq: float = 2.706, dist_max: float = math.nan,
+                 tau: int = 2, no_filter: bool = True, multi: bool = True, summarize: bool = False, place: bool = False,
+                 capacity: tuple[int, int] | None = None):
+        L = load_library()
+        self.index = index
+        self.names = names
+        self.params = Params(hdist_th, chisq, dist_max, tau, int(no_filter), int(multi), int(summarize), int(place))
+        self.bases, self.offsets = pack_reads(reads)
+        self.n_reads = len(self.offsets) - 1
+        cap_reads, cap_bases = capacity or (max(self.n_reads, 1), max(int(self.offsets[-1]), 1))
+        self._h = C.c_void_p()
+        rc = L.krepp_batch_create(index._h, C.byref(self.params), cap_reads, cap_bases, C.byref(self._h))
+        if rc:
+            msg = L.krepp_last_error().decode()
+            if self._h:
+                L.krepp_batch_destroy(self._h)
+                self._h = None
+            raise KreppError(rc, msg)
+        self._res = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().krepp_batch_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    # -- raw pipeline -------------------------------------------------------------------------------------------
+    def enable_tap(self, capacity_items: int):
+        _check(load_library().krepp_batch_enable_tap(self._h, 1, capacity_items))
+
+    def submit(self):
+        _check(load_library().krepp_batch_submit(self._h, self.bases.ctypes.data, self.offsets.ctypes.data, self.n_reads))
+
+    def submit_device(self, d_bases_ptr: int, d_offsets_ptr: int, n_reads: int, n_bases: int):
+        _check(load_library().krepp_batch_submit_device(self._h, d_bases_ptr, d_offsets_ptr, n_reads, n_bases))
+
+    def wait(self) -> dict:
+        r = Results()
+        _check(load_library().krepp_batch_wait(self._h, C.byref(r)))
+        nrec = int(r.n_records)
+        self._res = dict(
+            reads=_view(r.reads, READ_DTYPE, r.n_reads), records=_view(r.records, RECORD_DTYPE, nrec),
+            hist=_view(r.hist, np.dtype("<u4"), nrec * r.hist_stride).reshape(nrec, r.hist_stride),
+            placements=_view(r.placements, PLACEMENT_DTYPE, int(r.n_placements)), gpu_ms=float(r.gpu_ms),
+            gpu_launches=int(r.gpu_launches))
+        return self._res
+
+    def results(self) -> dict:
+        if self._res is None:
+            self.submit()
+            self.wait()
+        return self._res
+
+    def read_tap(self) -> np.ndarray:
+        L = load_library()
+        n = C.c_uint64()
+        _check(L.krepp_batch_read_tap(self._h, 1, None, 0, C.byref(n)))
+        out = np.zeros((n.value, 4), dtype=np.uint32)
+        if n.value:
+            _check(L.krepp_batch_read_tap(self._h, 1, out.ctypes.data, n.value, C.byref(n)))
+        return out
+
+    def algorithmic_bytes(self) -> dict:
+        b, l, e = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        _check(load_library().krepp_batch_algorithmic_bytes(self._h, C.byref(b), C.byref(l), C.byref(e)))
+        return dict(bytes=b.value, lookups=l.value, entries=e.value)
+
+    # -- reference-shaped entry points ------------------------------------------------------------------------------
+    def estimate_distances(self) -> str:
+        """TSV body of `krepp dist` for this batch: report_distances (src/query.cpp:158-196), precision 5, reads in
+        input order and references by ascending se (the reference's own order is unspecified)."""
+        res = self.results()
+        p = self.params
+        has_max = not math.isnan(p.dist_max)
+        out = []
+        recs, reads = res["records"], res["reads"]
+        for i in range(self.n_reads):
+            name = self.names[i] if self.names is not None else f"r{i}"
+            s = reads[i]
+            rr = recs[s["rec_begin"]:s["rec_begin"] + s["rec_count"]]
+            sel = rr[(rr["flags"] & REC_SELECTED) != 0]
+            if len(sel) == 0 or (has_max and recs[s["closest"]]["d_llh"] > p.dist_max):
+                out.append(f"{name}\tNA\tNaN\n")
+                continue
+            if p.multi:
+                for r in sorted(sel, key=lambda r: r["leaf_se"]):
+                    if not p.no_filter and not (r["chisq"] < p.chisq):
+                        continue
+                    if has_max and not (r["d_llh"] < p.dist_max):
+                        continue
+                    out.append(f"{name}\t{self.index.node_name(int(r['leaf_se']))}\t{r['d_llh']:.5f}\n")
+            else:
+                r = recs[s["closest"]]
+                out.append(f"{name}\t{self.index.node_name(int(r['leaf_se']))}\t{r['d_llh']:.5f}\n")
+        return "".join(out)

@@ -1,0 +1,464 @@
+// api.cu -- the C ABI declared in include/krepp_b200.h: index image upload, batch slots (one CUDA stream each),
+// submit / wait, parity taps.  No CPU fallback exists: every compute entry point needs a CUDA device.
+#include "../../include/krepp_b200.h"
+
+#include "device.cuh"
+#include "index_image.hpp"
+#include "solve.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+using namespace krepp;
+
+namespace {
+
+thread_local std::string g_err;
+thread_local std::string g_name;
+
+int fail(int code, const char* fmt, ...)
+{
+  char b[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(b, sizeof b, fmt, ap);
+  va_end(ap);
+  g_err = b;
+  return code;
+}
+
+#define CU(expr)                                                                                                 \
+  do {                                                                                                           \
+    cudaError_t e__ = (expr);                                                                                    \
+    if (e__ != cudaSuccess) return fail(KREPP_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__));      \
+  } while (0)
+
+template <class T>
+cudaError_t upload(const std::vector<T>& v, const T** out, std::vector<void*>& allocs, uint64_t& bytes, size_t pad = 0)
+{
+  void* p = nullptr;
+  const size_t n = (v.size() + pad) * sizeof(T);
+  cudaError_t e = cudaMalloc(&p, n ? n : sizeof(T));
+  if (e != cudaSuccess) return e;
+  allocs.push_back(p);
+  bytes += n;
+  if (pad) { e = cudaMemset(p, 0, n); if (e != cudaSuccess) return e; }
+  if (!v.empty()) e = cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+  *out = static_cast<const T*>(p);
+  return e;
+}
+
+// AoS assembly of the public result structs on the device (one D2H copy each, no host-side gather).
+__global__ void __launch_bounds__(128) finalize_kernel(const SolveArgs a, krepp_record_t* out_rec, krepp_read_summary_t* out_read,
+                                                        const uint32_t* wn)
+{
+  const uint32_t n = a.counters[0] < a.n_records ? a.counters[0] : a.n_records;
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  for (uint32_t i = tid; i < n; i += nth) {
+    krepp_record_t r;
+    const uint32_t slot = a.rec_slot[i];
+    r.read = a.rec_read[i]; r.leaf_se = slot & 0x7FFFFFFFu; r.strand = slot >> 31;
+    r.match_count = a.rec_match[i]; r.hdist_min = a.rec_hdmin[i]; r.flags = a.rec_flags[i];
+    r.rho = a.rho[r.leaf_se]; r.d_llh = a.rec_d[i]; r.v_llh = a.rec_v[i]; r.chisq = a.rec_chisq[i];
+    out_rec[i] = r;
+  }
+  for (uint32_t i = tid; i < a.n_reads; i += nth) {
+    krepp_read_summary_t s;
+    s.onmers = a.onmers[i]; s.wn[0] = wn[2 * i]; s.wn[1] = wn[2 * i + 1];
+    s.hdist_filt[0] = a.hdfilt[2 * i]; s.hdist_filt[1] = a.hdfilt[2 * i + 1];
+    s.rec_begin = a.rec_begin[i]; s.rec_count = a.rec_count[i]; s.place_begin = 0; s.place_count = 0;
+    s.closest = a.closest[i];
+    out_read[i] = s;
+  }
+}
+
+} // namespace
+
+struct krepp_index {
+  HostIndex host;
+  DevIndex dev{};
+  int device = 0, sms = 0, resident_warps = 0;
+  uint64_t device_bytes = 0;
+  std::vector<void*> allocs;
+};
+
+struct krepp_batch {
+  krepp_index* ix = nullptr;
+  krepp_params_t p{};
+  LlhTables tab{};
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  uint32_t max_reads = 0, rec_cap = 0, n_reads = 0, launches = 0;
+  uint64_t max_bases = 0, n_bases = 0;
+  bool submitted = false, device_input = false;
+  const char* in_bases = nullptr;       // device pointers used by the last submit
+  const uint64_t* in_offsets = nullptr;
+  // pinned host staging + device inputs
+  char* h_bases = nullptr; uint64_t* h_offsets = nullptr;
+  char* d_bases = nullptr; uint64_t* d_offsets = nullptr;
+  // device state
+  uint32_t *d_onmers = nullptr, *d_wn = nullptr, *d_hdfilt = nullptr, *d_rec_begin = nullptr, *d_rec_count = nullptr;
+  int32_t* d_closest = nullptr;
+  uint32_t *d_rec_read = nullptr, *d_rec_slot = nullptr, *d_rec_hist = nullptr, *d_rec_flags = nullptr, *d_rec_match = nullptr, *d_rec_hdmin = nullptr;
+  double *d_rec_d = nullptr, *d_rec_v = nullptr, *d_rec_chisq = nullptr;
+  uint32_t* d_counters = nullptr; unsigned long long* d_stats = nullptr;
+  uint32_t *d_acc = nullptr, *d_bitmap = nullptr, *d_marker = nullptr, *d_stack = nullptr;
+  uint32_t stack_cap = 0;
+  krepp_record_t* d_out_rec = nullptr; krepp_read_summary_t* d_out_read = nullptr;
+  // pinned host results
+  krepp_record_t* h_rec = nullptr; krepp_read_summary_t* h_read = nullptr; uint32_t* h_hist = nullptr;
+  uint32_t* h_counters = nullptr; unsigned long long* h_stats = nullptr;
+  // tap
+  uint4* d_tap = nullptr; unsigned long long* d_tap_count = nullptr; unsigned long long tap_cap = 0;
+};
+
+extern "C" {
+
+const char* krepp_last_error(void) { return g_err.c_str(); }
+int krepp_abi_version(void) { return KREPP_ABI_VERSION; }
+
+void krepp_params_default(krepp_params_t* p, int place)
+{
+  if (!p) return;
+  p->hdist_th = 4; p->chisq = 2.706; p->dist_max = std::numeric_limits<double>::quiet_NaN(); p->tau = 2;
+  p->no_filter = place ? 0 : 1; p->multi = 1; p->summarize = 0; p->place = place ? 1 : 0;
+}
+
+int krepp_index_open(const char* index_dir, int device, krepp_index_t** out)
+{
+  if (!index_dir || !out) return fail(KREPP_ERR_ARG, "krepp_index_open: null argument");
+  *out = nullptr;
+  int ndev = 0;
+  if (device != KREPP_DEVICE_NONE) {
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(KREPP_ERR_CUDA, "no CUDA device is available (the krepp_b200 query path has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(KREPP_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
+  }
+  auto* ix = new krepp_index;
+  std::string err = ix->host.load(index_dir);
+  if (!err.empty()) { delete ix; return fail(KREPP_ERR_IO, "%s", err.c_str()); }
+  const HostIndex& h = ix->host;
+  if (device == KREPP_DEVICE_NONE) { ix->device = device; *out = ix; return KREPP_OK; } // metadata / tree only, no queries
+  if (h.m > (uint32_t)kMaxResidues) { const uint32_t m = h.m; delete ix; return fail(KREPP_ERR_UNSUPPORTED, "m = %u exceeds the %d residues supported on the device", m, kMaxResidues); }
+  if (h.hash_runs.size() > (size_t)kMaxRuns || h.drop_runs.size() > (size_t)kMaxRuns) { delete ix; return fail(KREPP_ERR_UNSUPPORTED, "hash mask has too many runs"); }
+  ix->device = device;
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ix->sms, cudaDevAttrMultiProcessorCount, device);
+  DevIndex& d = ix->dev;
+  std::vector<uint2> tmp2;
+  // the image: cmer and pse are uploaded verbatim (8-byte pairs), inc padded by one entry
+  if (e == cudaSuccess) e = upload(h.cmer, reinterpret_cast<const uint64_t**>(&d.cmer), ix->allocs, ix->device_bytes, 4);
+  if (e == cudaSuccess) e = upload(h.inc, &d.inc, ix->allocs, ix->device_bytes, 1);
+  if (e == cudaSuccess) e = upload(h.pse, reinterpret_cast<const uint64_t**>(&d.pse), ix->allocs, ix->device_bytes);
+  if (e == cudaSuccess) e = upload(h.kind, &d.kind, ix->allocs, ix->device_bytes);
+  if (e == cudaSuccess) e = upload(h.rho, &d.rho, ix->allocs, ix->device_bytes);
+  if (e == cudaSuccess) e = upload(h.tree.leaf_rank, &d.leaf_rank, ix->allocs, ix->device_bytes);
+  if (e == cudaSuccess) e = upload(h.tree.leaf_se, &d.leaf_se, ix->allocs, ix->device_bytes);
+  if (e == cudaSuccess) e = upload(h.tree.parent, &d.parent, ix->allocs, ix->device_bytes);
+  if (e == cudaSuccess) e = upload(h.tree.nchildren, &d.nchildren, ix->allocs, ix->device_bytes);
+  if (e == cudaSuccess) e = upload(h.tree.blen, &d.blen, ix->allocs, ix->device_bytes);
+  if (e != cudaSuccess) {
+    for (void* p : ix->allocs) cudaFree(p);
+    delete ix;
+    return fail(KREPP_ERR_CUDA, "uploading the index image failed: %s", cudaGetErrorString(e));
+  }
+  d.nkmers = h.nkmers; d.nrows = h.nrows; d.nsubsets = h.nsubsets; d.nnodes = h.tree.nnodes; d.nleaves = h.tree.nleaves;
+  d.k = h.k; d.h = h.h; d.m = h.m;
+  d.m_shift = (h.m & (h.m - 1)) == 0 ? (uint32_t)__builtin_ctz(h.m) : 0xFFFFFFFFu;
+  d.n_hash_runs = (uint32_t)h.hash_runs.size(); d.n_drop_runs = (uint32_t)h.drop_runs.size();
+  for (size_t i = 0; i < h.hash_runs.size(); ++i) d.hash_runs[i] = {h.hash_runs[i].src, (uint32_t)((1ull << h.hash_runs[i].width) - 1), h.hash_runs[i].dst};
+  for (size_t i = 0; i < h.drop_runs.size(); ++i) d.drop_runs[i] = {h.drop_runs[i].src, (uint32_t)((1ull << h.drop_runs[i].width) - 1), h.drop_runs[i].dst};
+  for (uint32_t i = 0; i < (uint32_t)kMaxResidues; ++i) d.res_numer[i] = i < h.m ? h.res_numer[i] : 0;
+  d.local_expand = h.max_expand_depth + 2 <= 32 ? 1u : 0u;
+  ix->resident_warps = match_resident_warps(device);
+  *out = ix;
+  return KREPP_OK;
+}
+
+void krepp_index_close(krepp_index_t* ix)
+{
+  if (!ix) return;
+  if (ix->device != KREPP_DEVICE_NONE) cudaSetDevice(ix->device);
+  for (void* p : ix->allocs) cudaFree(p);
+  delete ix;
+}
+
+int krepp_index_info(const krepp_index_t* ix, krepp_index_info_t* o)
+{
+  if (!ix || !o) return fail(KREPP_ERR_ARG, "krepp_index_info: null argument");
+  const HostIndex& h = ix->host;
+  o->k = h.k; o->w = h.w; o->h = h.h; o->m = h.m; o->r = h.r; o->frac = h.frac; o->nrows = h.nrows; o->nkmers = h.nkmers;
+  o->nnodes = h.tree.nnodes; o->nleaves = h.tree.nleaves; o->nsubsets = h.nsubsets; o->root_se = h.tree.root;
+  o->mask_hash_bp = h.mask_hash_bp; o->mask_drop_lr = h.mask_drop_lr; o->device_bytes = ix->device_bytes;
+  o->mean_bucket = h.mean_bucket; o->size_biased_bucket = h.size_biased_bucket;
+  return KREPP_OK;
+}
+
+const char* krepp_index_node_name(const krepp_index_t* ix, uint32_t se, int return_na)
+{
+  if (!ix) return "";
+  g_name = ix->host.tree.node_name(se, return_na != 0);
+  return g_name.c_str();
+}
+
+int krepp_index_tree(const krepp_index_t* ix, uint32_t* parent, uint32_t* nchildren, uint8_t* is_leaf, double* blen)
+{
+  if (!ix) return fail(KREPP_ERR_ARG, "krepp_index_tree: null index");
+  const HostTree& t = ix->host.tree;
+  const size_t n = t.nnodes + 1;
+  if (parent) std::memcpy(parent, t.parent.data(), n * 4);
+  if (nchildren) std::memcpy(nchildren, t.nchildren.data(), n * 4);
+  if (is_leaf) std::memcpy(is_leaf, t.is_leaf.data(), n);
+  if (blen) std::memcpy(blen, t.blen.data(), n * 8);
+  return KREPP_OK;
+}
+
+size_t krepp_index_jplace_tree(const krepp_index_t* ix, char* buf, size_t cap)
+{
+  if (!ix) return 0;
+  const std::string s = ix->host.tree.jplace_newick();
+  if (buf && cap) { const size_t n = std::min(cap - 1, s.size()); std::memcpy(buf, s.data(), n); buf[n] = 0; }
+  return s.size();
+}
+
+// ------------------------------------------------------------------------------------------------ batches
+
+static void free_records(krepp_batch* b)
+{
+  for (void* p : {(void*)b->d_rec_read, (void*)b->d_rec_slot, (void*)b->d_rec_hist, (void*)b->d_rec_flags, (void*)b->d_rec_match,
+                  (void*)b->d_rec_hdmin, (void*)b->d_rec_d, (void*)b->d_rec_v, (void*)b->d_rec_chisq, (void*)b->d_out_rec})
+    if (p) cudaFree(p);
+  if (b->h_rec) cudaFreeHost(b->h_rec);
+  if (b->h_hist) cudaFreeHost(b->h_hist);
+  b->d_rec_read = b->d_rec_slot = b->d_rec_hist = b->d_rec_flags = b->d_rec_match = b->d_rec_hdmin = nullptr;
+  b->d_rec_d = b->d_rec_v = b->d_rec_chisq = nullptr; b->d_out_rec = nullptr; b->h_rec = nullptr; b->h_hist = nullptr;
+}
+
+static int alloc_records(krepp_batch* b, uint32_t cap)
+{
+  free_records(b);
+  const size_t stride = b->p.hdist_th + 1;
+  b->rec_cap = cap;
+  CU(cudaMalloc(&b->d_rec_read, 4ull * cap)); CU(cudaMalloc(&b->d_rec_slot, 4ull * cap)); CU(cudaMalloc(&b->d_rec_hist, 4ull * cap * stride));
+  CU(cudaMalloc(&b->d_rec_flags, 4ull * cap)); CU(cudaMalloc(&b->d_rec_match, 4ull * cap)); CU(cudaMalloc(&b->d_rec_hdmin, 4ull * cap));
+  CU(cudaMalloc(&b->d_rec_d, 8ull * cap)); CU(cudaMalloc(&b->d_rec_v, 8ull * cap)); CU(cudaMalloc(&b->d_rec_chisq, 8ull * cap));
+  CU(cudaMalloc(&b->d_out_rec, sizeof(krepp_record_t) * (size_t)cap));
+  CU(cudaMallocHost(&b->h_rec, sizeof(krepp_record_t) * (size_t)cap));
+  CU(cudaMallocHost(&b->h_hist, 4ull * cap * stride));
+  return KREPP_OK;
+}
+
+int krepp_batch_create(krepp_index_t* ix, const krepp_params_t* p, uint32_t max_reads, uint64_t max_bases, krepp_batch_t** out)
+{
+  if (!ix || !p || !out || !max_reads) return fail(KREPP_ERR_ARG, "krepp_batch_create: bad argument");
+  *out = nullptr;
+  if (p->hdist_th > (uint32_t)kMaxTh) return fail(KREPP_ERR_ARG, "--hdist-th %u exceeds %d", p->hdist_th, kMaxTh);
+  if (p->place && p->hdist_th < p->tau) return fail(KREPP_ERR_ARG, "The threshold tau must be less than HD threshold --hdist-th!");
+  if (p->place) return fail(KREPP_ERR_UNSUPPORTED, "placement is not wired into the batch pipeline yet");
+  if (ix->device == KREPP_DEVICE_NONE) return fail(KREPP_ERR_CUDA, "this index handle was opened without a device (KREPP_DEVICE_NONE); queries need a GPU");
+  if (cudaSetDevice(ix->device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice(%d) failed", ix->device);
+  auto* b = new krepp_batch;
+  *out = b; // destroyed by the caller on failure
+  b->ix = ix; b->p = *p; b->max_reads = max_reads; b->max_bases = max_bases;
+  const HostIndex& h = ix->host;
+  { // HDistHistLLH tables (ref src/hdhistllh.hpp:51-69), exact integer arithmetic then converted
+    uint64_t ck[33] = {0}, vc = 1;
+    ck[0] = 1;
+    for (uint32_t i = 0; i < h.k; ++i) ck[i + 1] = (ck[i] * (h.k - i)) / (i + 1);
+    for (uint32_t i = 0; i <= h.k; ++i) b->tab.ck[i] = (double)ck[i];
+    b->tab.hnk[0] = 0;
+    const uint32_t nh = h.k - h.h;
+    for (uint32_t i = 1; i <= p->hdist_th; ++i) { vc = (vc * (nh - i + 1)) / i; b->tab.hnk[i] = (double)(ck[i] - vc); }
+  }
+  CU(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+  CU(cudaEventCreate(&b->ev0)); CU(cudaEventCreate(&b->ev1));
+  CU(cudaMallocHost(&b->h_bases, max_bases + 64)); CU(cudaMallocHost(&b->h_offsets, 8ull * (max_reads + 1)));
+  CU(cudaMalloc(&b->d_bases, max_bases + 64)); CU(cudaMalloc(&b->d_offsets, 8ull * (max_reads + 1)));
+  CU(cudaMalloc(&b->d_onmers, 4ull * max_reads)); CU(cudaMalloc(&b->d_wn, 8ull * max_reads)); CU(cudaMalloc(&b->d_hdfilt, 8ull * max_reads));
+  CU(cudaMalloc(&b->d_rec_begin, 4ull * max_reads)); CU(cudaMalloc(&b->d_rec_count, 4ull * max_reads)); CU(cudaMalloc(&b->d_closest, 4ull * max_reads));
+  CU(cudaMalloc(&b->d_counters, 16)); CU(cudaMalloc(&b->d_stats, 32));
+  CU(cudaMallocHost(&b->h_counters, 16)); CU(cudaMallocHost(&b->h_stats, 32));
+  CU(cudaMalloc(&b->d_out_read, sizeof(krepp_read_summary_t) * (size_t)max_reads));
+  CU(cudaMallocHost(&b->h_read, sizeof(krepp_read_summary_t) * (size_t)max_reads));
+  // per-warp scratch
+  const size_t warps = (size_t)ix->resident_warps, nslots = 2ull * h.tree.nleaves, stride = p->hdist_th + 1;
+  const size_t nbm = (nslots + 31) / 32;
+  b->stack_cap = 32 * (h.max_expand_depth + 2) + 64;
+  CU(cudaMalloc(&b->d_acc, 4 * warps * nslots * stride)); CU(cudaMemset(b->d_acc, 0, 4 * warps * nslots * stride));
+  CU(cudaMalloc(&b->d_bitmap, 4 * warps * nbm)); CU(cudaMemset(b->d_bitmap, 0, 4 * warps * nbm));
+  CU(cudaMalloc(&b->d_marker, 4 * warps * h.tree.nleaves)); CU(cudaMemset(b->d_marker, 0xFF, 4 * warps * h.tree.nleaves));
+  CU(cudaMalloc(&b->d_stack, 4 * warps * b->stack_cap));
+  const uint64_t want = std::max<uint64_t>(4ull * max_reads, 4096);
+  if (int rc = alloc_records(b, (uint32_t)std::min<uint64_t>(want, 0x7FFFFFFFull))) return rc;
+  return KREPP_OK;
+}
+
+void krepp_batch_destroy(krepp_batch_t* b)
+{
+  if (!b) return;
+  cudaSetDevice(b->ix->device);
+  if (b->stream) cudaStreamSynchronize(b->stream);
+  free_records(b);
+  for (void* p : {(void*)b->d_bases, (void*)b->d_offsets, (void*)b->d_onmers, (void*)b->d_wn, (void*)b->d_hdfilt, (void*)b->d_rec_begin,
+                  (void*)b->d_rec_count, (void*)b->d_closest, (void*)b->d_counters, (void*)b->d_stats, (void*)b->d_acc, (void*)b->d_bitmap,
+                  (void*)b->d_marker, (void*)b->d_stack, (void*)b->d_out_read, (void*)b->d_tap, (void*)b->d_tap_count})
+    if (p) cudaFree(p);
+  for (void* p : {(void*)b->h_bases, (void*)b->h_offsets, (void*)b->h_read, (void*)b->h_counters, (void*)b->h_stats})
+    if (p) cudaFreeHost(p);
+  if (b->ev0) cudaEventDestroy(b->ev0);
+  if (b->ev1) cudaEventDestroy(b->ev1);
+  if (b->stream) cudaStreamDestroy(b->stream);
+  delete b;
+}
+
+// Enqueues all kernels of one batch on the slot's stream (inputs already on the device).
+static int enqueue(krepp_batch* b)
+{
+  krepp_index* ix = b->ix;
+  const HostIndex& h = ix->host;
+  cudaStream_t s = b->stream;
+  CU(cudaMemsetAsync(b->d_counters, 0, 16, s));
+  CU(cudaMemsetAsync(b->d_stats, 0, 32, s));
+  if (b->d_tap_count) CU(cudaMemsetAsync(b->d_tap_count, 0, 8, s));
+  MatchArgs m{};
+  m.bases = b->in_bases; m.offsets = b->in_offsets; m.n_bases = b->n_bases; m.n_reads = b->n_reads; m.th = b->p.hdist_th;
+  m.onmers = b->d_onmers; m.wn = b->d_wn; m.hdfilt = b->d_hdfilt; m.rec_begin = b->d_rec_begin; m.rec_count = b->d_rec_count;
+  m.rec_read = b->d_rec_read; m.rec_slot = b->d_rec_slot; m.rec_hist = b->d_rec_hist; m.rec_cap = b->rec_cap; m.counters = b->d_counters;
+  m.acc = b->d_acc; m.bitmap = b->d_bitmap; m.marker = b->d_marker; m.stack = b->d_stack; m.stack_cap = b->stack_cap; m.stats = b->d_stats;
+  m.tap = b->d_tap; m.tap_count = b->d_tap_count; m.tap_cap = b->tap_cap;
+  CU(launch_match(ix->dev, m, ix->resident_warps, b->d_tap != nullptr, s));
+  SolveArgs sa{};
+  sa.n_reads = b->n_reads; sa.th = b->p.hdist_th; sa.k = h.k; sa.h = h.h; sa.n_records = b->rec_cap; sa.counters = b->d_counters;
+  sa.onmers = b->d_onmers; sa.hdfilt = b->d_hdfilt; sa.rec_begin = b->d_rec_begin; sa.rec_count = b->d_rec_count;
+  sa.rec_read = b->d_rec_read; sa.rec_slot = b->d_rec_slot; sa.rec_hist = b->d_rec_hist; sa.rho = ix->dev.rho;
+  sa.rec_d = b->d_rec_d; sa.rec_v = b->d_rec_v; sa.rec_chisq = b->d_rec_chisq; sa.rec_flags = b->d_rec_flags; sa.rec_match = b->d_rec_match;
+  sa.rec_hdmin = b->d_rec_hdmin; sa.closest = b->d_closest;
+  sa.want_chisq = (!b->p.no_filter || b->p.summarize || b->p.place) ? 1 : 0;
+  CU(launch_solve(sa, b->tab, ix->sms, s));
+  finalize_kernel<<<ix->sms * 4, 128, 0, s>>>(sa, b->d_out_rec, b->d_out_read, b->d_wn);
+  CU(cudaGetLastError());
+  b->launches = 4 + (sa.want_chisq ? 1 : 0);
+  CU(cudaMemcpyAsync(b->h_counters, b->d_counters, 16, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(b->h_stats, b->d_stats, 32, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(b->h_read, b->d_out_read, sizeof(krepp_read_summary_t) * (size_t)b->n_reads, cudaMemcpyDeviceToHost, s));
+  return KREPP_OK;
+}
+
+int krepp_batch_host_buffers(krepp_batch_t* b, char** bases, uint64_t** offsets)
+{
+  if (!b) return fail(KREPP_ERR_ARG, "null batch");
+  if (bases) *bases = b->h_bases;
+  if (offsets) *offsets = b->h_offsets;
+  return KREPP_OK;
+}
+
+int krepp_batch_submit(krepp_batch_t* b, const char* bases, const uint64_t* offsets, uint32_t n_reads)
+{
+  if (!b || !bases || !offsets) return fail(KREPP_ERR_ARG, "krepp_batch_submit: null argument");
+  if (n_reads > b->max_reads) return fail(KREPP_ERR_CAPACITY, "batch of %u reads exceeds the slot capacity of %u", n_reads, b->max_reads);
+  const uint64_t nb = n_reads ? offsets[n_reads] - offsets[0] : 0;
+  if (nb > b->max_bases) return fail(KREPP_ERR_CAPACITY, "batch of %llu bases exceeds the slot capacity of %llu", (unsigned long long)nb, (unsigned long long)b->max_bases);
+  if (cudaSetDevice(b->ix->device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice failed");
+  CU(cudaStreamSynchronize(b->stream)); // the previous batch of this slot must be finished before its buffers are reused
+  if (bases != b->h_bases) std::memcpy(b->h_bases, bases + offsets[0], nb);
+  if (offsets != b->h_offsets || offsets[0] != 0) {
+    const uint64_t o0 = offsets[0];
+    for (uint32_t i = 0; i <= n_reads; ++i) b->h_offsets[i] = offsets[i] - o0;
+  }
+  b->n_reads = n_reads; b->n_bases = nb; b->device_input = false;
+  b->in_bases = b->d_bases; b->in_offsets = b->d_offsets;
+  CU(cudaEventRecord(b->ev0, b->stream));
+  CU(cudaMemcpyAsync(b->d_bases, b->h_bases, nb, cudaMemcpyHostToDevice, b->stream));
+  CU(cudaMemcpyAsync(b->d_offsets, b->h_offsets, 8ull * (n_reads + 1), cudaMemcpyHostToDevice, b->stream));
+  if (int rc = enqueue(b)) return rc;
+  b->submitted = true;
+  return KREPP_OK;
+}
+
+int krepp_batch_submit_device(krepp_batch_t* b, const char* d_bases, const uint64_t* d_offsets, uint32_t n_reads, uint64_t n_bases)
+{
+  if (!b || !d_bases || !d_offsets) return fail(KREPP_ERR_ARG, "krepp_batch_submit_device: null argument");
+  if (n_reads > b->max_reads) return fail(KREPP_ERR_CAPACITY, "batch of %u reads exceeds the slot capacity of %u", n_reads, b->max_reads);
+  if (reinterpret_cast<uintptr_t>(d_bases) & 15) return fail(KREPP_ERR_ARG, "device bases pointer must be 16-byte aligned");
+  if (cudaSetDevice(b->ix->device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice failed");
+  CU(cudaStreamSynchronize(b->stream));
+  b->n_reads = n_reads; b->n_bases = n_bases; b->device_input = true;
+  b->in_bases = d_bases; b->in_offsets = d_offsets;
+  CU(cudaEventRecord(b->ev0, b->stream));
+  if (int rc = enqueue(b)) return rc;
+  b->submitted = true;
+  return KREPP_OK;
+}
+
+int krepp_batch_wait(krepp_batch_t* b, krepp_results_t* out)
+{
+  if (!b || !out) return fail(KREPP_ERR_ARG, "krepp_batch_wait: null argument");
+  if (!b->submitted) return fail(KREPP_ERR_ARG, "krepp_batch_wait: nothing was submitted on this slot");
+  if (cudaSetDevice(b->ix->device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice failed");
+  for (int attempt = 0;; ++attempt) {
+    CU(cudaStreamSynchronize(b->stream));
+    if (b->h_counters[2] & kErrStackOverflow) return fail(KREPP_ERR_CAPACITY, "colour expansion stack overflow on the device");
+    if (!(b->h_counters[2] & kErrRecOverflow)) break;
+    // the record buffer was too small: grow it to what the kernel asked for and run the batch again
+    if (attempt >= 4) return fail(KREPP_ERR_CAPACITY, "record buffer overflow persists");
+    const uint64_t want = std::max<uint64_t>(2ull * b->h_counters[0], 2ull * b->rec_cap);
+    if (want > 0x7FFFFFFFull) return fail(KREPP_ERR_CAPACITY, "batch produces too many records; submit fewer reads per batch");
+    if (int rc = alloc_records(b, (uint32_t)want)) return rc;
+    if (int rc = enqueue(b)) return rc;
+  }
+  const uint32_t nrec = b->h_counters[0];
+  const size_t stride = b->p.hdist_th + 1;
+  if (nrec) {
+    CU(cudaMemcpyAsync(b->h_rec, b->d_out_rec, sizeof(krepp_record_t) * (size_t)nrec, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaMemcpyAsync(b->h_hist, b->d_rec_hist, 4ull * nrec * stride, cudaMemcpyDeviceToHost, b->stream));
+  }
+  CU(cudaEventRecord(b->ev1, b->stream));
+  CU(cudaStreamSynchronize(b->stream));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, b->ev0, b->ev1));
+  out->n_reads = b->n_reads; out->hist_stride = (uint32_t)stride; out->n_records = nrec; out->n_placements = 0;
+  out->reads = b->h_read; out->records = b->h_rec; out->hist = b->h_hist; out->placements = nullptr;
+  out->gpu_ms = ms; out->gpu_launches = b->launches;
+  return KREPP_OK;
+}
+
+int krepp_batch_enable_tap(krepp_batch_t* b, int stage, uint64_t capacity_items)
+{
+  if (!b || stage != 1 || !capacity_items) return fail(KREPP_ERR_ARG, "krepp_batch_enable_tap: bad argument");
+  if (cudaSetDevice(b->ix->device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice failed");
+  CU(cudaStreamSynchronize(b->stream));
+  if (b->d_tap) { cudaFree(b->d_tap); b->d_tap = nullptr; }
+  if (!b->d_tap_count) CU(cudaMalloc(&b->d_tap_count, 8));
+  CU(cudaMalloc(&b->d_tap, sizeof(uint4) * capacity_items));
+  b->tap_cap = capacity_items;
+  return KREPP_OK;
+}
+
+int krepp_batch_read_tap(krepp_batch_t* b, int stage, uint32_t* out, uint64_t cap_items, uint64_t* n)
+{
+  if (!b || stage != 1 || !n || !b->d_tap) return fail(KREPP_ERR_ARG, "krepp_batch_read_tap: bad argument or tap not enabled");
+  if (cudaSetDevice(b->ix->device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice failed");
+  CU(cudaStreamSynchronize(b->stream));
+  unsigned long long cnt = 0;
+  CU(cudaMemcpy(&cnt, b->d_tap_count, 8, cudaMemcpyDeviceToHost));
+  *n = cnt;
+  const uint64_t take = std::min<uint64_t>(std::min<uint64_t>(cnt, b->tap_cap), cap_items);
+  if (out && take) CU(cudaMemcpy(out, b->d_tap, sizeof(uint4) * take, cudaMemcpyDeviceToHost));
+  return KREPP_OK;
+}
+
+int krepp_batch_algorithmic_bytes(krepp_batch_t* b, uint64_t* bytes, uint64_t* lookups, uint64_t* entries)
+{
+  if (!b) return fail(KREPP_ERR_ARG, "null batch");
+  if (bytes) *bytes = b->h_stats[0];
+  if (lookups) *lookups = b->h_stats[1];
+  if (entries) *entries = b->h_stats[2];
+  return KREPP_OK;
+}
+
+} // extern "C"

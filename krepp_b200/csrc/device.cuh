@@ -1,0 +1,82 @@
+// Device-side data model shared by the kernels and the C-ABI layer.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace krepp {
+
+constexpr int kMaxRuns = 18;      // a pext mask over k <= 32 two-bit groups has at most 17 runs
+constexpr int kMaxResidues = 64;  // m (modulo of the LSH partition, ref src/krepp.hpp:40) supported on device
+constexpr int kMaxTh = 16;
+
+struct DevRun { uint32_t src, mask, dst; };
+
+// Flat index image resident in HBM (see index_image.hpp for the on-disk format it mirrors).
+struct DevIndex {
+  const uint2* cmer;        // nkmers x (enc32, se)               ref FlatHT::cmer_v  src/table.hpp:143
+  const uint64_t* inc;      // nrows cumulative bucket ends        ref FlatHT::inc_v   src/table.hpp:142
+  const uint2* pse;         // nsubsets x (first, second)          ref CRecord::se_to_pse src/record.hpp:103
+  const uint8_t* kind;      // nsubsets: 0 drop, 1 leaf, 2 expand  ref src/query.cpp:373-386
+  const double* rho;        // by se, scaled                        ref CRecord::se_to_rho src/record.hpp:104
+  const uint32_t* leaf_rank;// by se
+  const uint32_t* leaf_se;  // by rank
+  const uint32_t* parent;   // by se (0 for root)                  ref Node::parent
+  const uint32_t* nchildren;// by se
+  const double* blen;       // by se
+  uint64_t nkmers;
+  uint32_t nrows, nsubsets, nnodes, nleaves;
+  uint32_t k, h, m, m_shift; // m_shift = log2(m) when m is a power of two, else 0xffffffff
+  uint32_t n_hash_runs, n_drop_runs;
+  uint32_t local_expand;    // 1 when the deepest colour DAG fits the lane-private expansion stack
+  DevRun hash_runs[kMaxRuns], drop_runs[kMaxRuns];
+  int32_t res_numer[kMaxResidues];
+};
+
+// Per-slot buffers for one batch.
+struct MatchArgs {
+  const char* bases;          // concatenated ASCII reads
+  const uint64_t* offsets;    // n_reads + 1
+  uint64_t n_bases;           // bytes readable at `bases`
+  uint32_t n_reads, th;
+  // per-read outputs
+  uint32_t* onmers;           // [n]
+  uint32_t* wn;               // [2n]
+  uint32_t* hdfilt;           // [2n]
+  uint32_t* rec_begin;        // [n]
+  uint32_t* rec_count;        // [n]
+  // record outputs (SoA)
+  uint32_t* rec_read;         // [cap]
+  uint32_t* rec_slot;         // [cap]  strand<<31 | leaf_se
+  uint32_t* rec_hist;         // [cap * (th+1)]
+  uint32_t rec_cap;
+  uint32_t* counters;         // [0] records reserved, [1] next read to claim, [2] error flags
+  // per-warp scratch in HBM (sized by the host from the resident warp count)
+  uint32_t* acc;              // [warps][2*nleaves*(th+1)] Hamming histograms being accumulated
+  uint32_t* bitmap;           // [warps][ceil(2*nleaves/32)] touched (strand, leaf) slots
+  uint32_t* marker;           // [warps][nleaves] per-lookup min-hd markers (0xffffffff at rest)
+  uint32_t* stack;            // [warps][stack_cap] colour expansion stack
+  uint32_t stack_cap;
+  unsigned long long* stats;  // [0] algorithmic bytes, [1] lookups, [2] entries scanned
+  // parity tap (stage 1)
+  uint4* tap;
+  unsigned long long* tap_count;
+  unsigned long long tap_cap;
+};
+
+constexpr uint32_t kErrRecOverflow = 1u, kErrStackOverflow = 2u;
+
+struct SolveArgs {
+  uint32_t n_reads, th, k, h;
+  uint32_t n_records;                // filled from counters[0] on the device when 0xffffffff
+  const uint32_t* counters;
+  const uint32_t* onmers; const uint32_t* hdfilt;
+  const uint32_t* rec_begin; const uint32_t* rec_count;
+  const uint32_t* rec_read; const uint32_t* rec_slot; const uint32_t* rec_hist;
+  const double* rho;                 // by se
+  // outputs
+  double* rec_d; double* rec_v; double* rec_chisq; uint32_t* rec_flags; uint32_t* rec_match; uint32_t* rec_hdmin;
+  int32_t* closest;                  // [n_reads] record index or -1
+  int want_chisq;
+};
+
+} // namespace krepp

@@ -1,0 +1,371 @@
+// Host loader for the on-disk krepp index; see index_image.hpp for the format and reference citations.
+#include "index_image.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <dirent.h>
+#include <fstream>
+#include <limits>
+#include <sstream>
+
+namespace krepp {
+
+// ------------------------------------------------------------------------------------------------ Newick
+
+namespace {
+
+// Splits Newick text into label/length strings and the four structural characters.  The observable conventions of
+// the reference tokenizer (ref src/phytree.cpp:84-148) are kept: one trailing newline is ignored, the text must end in
+// ';', quotes (' or ") protect structural characters and a doubled quote is a literal ', [...] comments are only
+// recognised (and dropped) inside quotes, and a label string -- possibly empty -- is emitted in front of every ')',
+// ':' and ',' unless the preceding character is '('.
+struct NewickScanner {
+  std::vector<std::string> items;
+  std::string error;
+
+  bool run(std::string text)
+  {
+    if (text.empty()) { error = "Given Newick tree seems to be empty?!?."; return false; }
+    if (text.back() == '\n') text.pop_back();
+    if (text.empty() || text.back() != ';') { error = "Given Newick tree ends with a character other than ';'."; return false; }
+    std::string pending;
+    bool in_quote = false, prev_was_quote = false, in_comment = false;
+    const size_t n = text.size();
+    for (size_t i = 0; i < n; ++i) {
+      const char c = text[i];
+      if (in_comment) { if (c == ']') in_comment = false; continue; }
+      const bool is_quote = (c == '\'' || c == '"');
+      if (is_quote && prev_was_quote) { in_quote = false; pending += '\''; continue; }
+      prev_was_quote = is_quote;
+      if (is_quote) { in_quote = !in_quote; continue; }
+      if (in_quote) {
+        if (c == '[') in_comment = true; else pending += c;
+        continue;
+      }
+      switch (c) {
+        case '(': items.emplace_back(1, c); break;
+        case ')': case ':': case ',':
+          if (i == 0 || text[i - 1] != '(') { items.push_back(pending); pending.clear(); }
+          items.emplace_back(1, c);
+          break;
+        case '[': case ']':
+          error = "Given Newick tree contains an unquoted label or length with '[' or ']'."; return false;
+        case ';':
+          if (i + 1 == n) { i = n; break; }
+          error = (i + 1 < n && text[i + 1] == '\n') ? "Given Newick file may contain multiple trees, encountered unexpected ';'."
+                                                     : "Given Newick tree contains an unquoted label or length with ';'.";
+          return false;
+        default:
+          if ((c == ' ' || c == '\n') && !pending.empty()) {
+            error = "Given Newick tree contains an unquoted label or length with ' ' or newline."; return false;
+          }
+          pending += c;
+      }
+    }
+    if (!pending.empty()) items.push_back(pending);
+    return true;
+  }
+};
+
+struct TreeBuilder {
+  const std::vector<std::string>& it;
+  size_t at = 0;
+  HostTree& t;
+  std::string error;
+  // temporary per-node storage in creation order; se is handed out when a node closes (post-order)
+  struct Tmp { uint32_t se = 0, parent_tmp = 0xffffffffu, nch = 0, card = 0; bool leaf = true; double blen = 0; std::string name; std::vector<uint32_t> kids; };
+  std::vector<Tmp> tmp;
+  uint32_t next_se = 0;
+
+  TreeBuilder(const std::vector<std::string>& items, HostTree& tree) : it(items), t(tree) {}
+  bool is(const char* s) const { return at < it.size() && it[at] == s; }
+
+  void label_and_length(Tmp& nd)
+  { // optional label then optional ":length" (ref src/phytree.cpp:175-187,192-203)
+    nd.name.clear();
+    nd.blen = std::numeric_limits<double>::quiet_NaN();
+    if (at >= it.size()) return; // unlabeled root: nothing left to read
+    if (!is(",")) {
+      if (!is(":")) { nd.name = it[at]; ++at; }
+      if (is(":")) { nd.blen = (at + 1 < it.size()) ? std::atof(it[at + 1].c_str()) : 0.0; at += 2; }
+    }
+  }
+
+  uint32_t subtree()
+  {
+    const uint32_t id = (uint32_t)tmp.size();
+    tmp.emplace_back();
+    if (!error.empty() || at >= it.size()) return id;
+    if (is("(")) {
+      do {
+        ++at;
+        const uint32_t ch = subtree();
+        tmp[ch].parent_tmp = id;
+        tmp[id].kids.push_back(ch);
+        tmp[id].card += tmp[ch].card;
+        tmp[id].leaf = false;
+      } while (is(","));
+      if (tmp[id].kids.size() == 1) { error = "A node has a single child in the backbone tree! Please suppress unifurcations."; return id; }
+      tmp[id].se = ++next_se;
+      if (is(")")) { ++at; if (is(")")) return id; } // unlabeled, length-less last child keeps blen = 0 (ref :171-174)
+      label_and_length(tmp[id]);
+    } else {
+      label_and_length(tmp[id]);
+      tmp[id].leaf = true;
+      tmp[id].card = 1;
+      tmp[id].se = ++next_se;
+    }
+    return id;
+  }
+};
+
+std::string fixed5(double v)
+{
+  char b[64];
+  snprintf(b, sizeof b, "%.5f", v);
+  return b;
+}
+
+} // namespace
+
+std::string HostTree::parse(const std::string& newick)
+{
+  NewickScanner sc;
+  if (!sc.run(newick)) return sc.error;
+  TreeBuilder tb(sc.items, *this);
+  const uint32_t root_tmp = tb.subtree();
+  if (!tb.error.empty()) return tb.error;
+  nnodes = tb.next_se;
+  const size_t N = nnodes + 1;
+  parent.assign(N, 0); nchildren.assign(N, 0); card.assign(N, 0); first_child.assign(N, 0); next_sibling.assign(N, 0);
+  is_leaf.assign(N, 0); blen.assign(N, std::numeric_limits<double>::quiet_NaN()); name.assign(N, "");
+  leaf_rank.assign(N, 0xffffffffu); leaf_se.clear();
+  for (const auto& nd : tb.tmp) {
+    if (!nd.se) continue;
+    parent[nd.se] = nd.parent_tmp == 0xffffffffu ? 0 : tb.tmp[nd.parent_tmp].se;
+    nchildren[nd.se] = (uint32_t)nd.kids.size();
+    card[nd.se] = nd.card; is_leaf[nd.se] = nd.leaf; blen[nd.se] = nd.blen; name[nd.se] = nd.name;
+    for (size_t i = 0; i < nd.kids.size(); ++i) {
+      const uint32_t c = tb.tmp[nd.kids[i]].se;
+      if (i == 0) first_child[nd.se] = c;
+      if (i + 1 < nd.kids.size()) next_sibling[c] = tb.tmp[nd.kids[i + 1]].se;
+    }
+  }
+  root = tb.tmp[root_tmp].se;
+  for (uint32_t se = 1; se <= nnodes; ++se)
+    if (is_leaf[se]) { leaf_rank[se] = (uint32_t)leaf_se.size(); leaf_se.push_back(se); }
+  nleaves = (uint32_t)leaf_se.size();
+  return "";
+}
+
+std::string HostTree::node_name(uint32_t se, bool return_na) const
+{
+  if (se == 0 || se > nnodes) return "";
+  if (!name[se].empty()) return name[se];
+  return return_na ? std::string("NA") : std::to_string(se - 1);
+}
+
+std::string HostTree::jplace_newick() const
+{
+  // iterative emission of "(" children ")" name[:blen]{se-1}, ";" after the root (ref src/phytree.cpp:47-64)
+  std::string out;
+  struct Frame { uint32_t se; uint32_t next; bool opened; };
+  std::vector<Frame> st;
+  st.push_back({root, 0, false});
+  while (!st.empty()) {
+    Frame& f = st.back();
+    if (!is_leaf[f.se] && !f.opened) { out += '('; f.opened = true; f.next = first_child[f.se]; }
+    if (!is_leaf[f.se] && f.next) {
+      const uint32_t c = f.next;
+      if (c != first_child[f.se]) out += ',';
+      f.next = next_sibling[c];
+      st.push_back({c, 0, false});
+      continue;
+    }
+    if (!is_leaf[f.se]) out += ')';
+    out += name[f.se];
+    if (!std::isnan(blen[f.se])) { out += ':'; out += fixed5(blen[f.se]); }
+    out += '{'; out += std::to_string(f.se - 1); out += '}';
+    if (f.se == root) out += ';';
+    st.pop_back();
+  }
+  return out;
+}
+
+// ------------------------------------------------------------------------------------------------ index files
+
+namespace {
+
+bool slurp(const std::string& path, std::string& out)
+{
+  std::ifstream f(path, std::ios::binary);
+  if (!f.is_open()) return false;
+  std::ostringstream ss;
+  ss << f.rdbuf();
+  out = ss.str();
+  return true;
+}
+
+std::vector<BitRun> runs_of(uint64_t mask)
+{ // decomposes a pext mask into contiguous runs: pext(x, mask) == OR over runs of ((x >> src) & ones(width)) << dst
+  std::vector<BitRun> v;
+  uint8_t dst = 0;
+  for (int b = 0; b < 64;) {
+    if (!((mask >> b) & 1)) { ++b; continue; }
+    int e = b;
+    while (e < 64 && ((mask >> e) & 1)) ++e;
+    v.push_back({(uint8_t)b, (uint8_t)(e - b), dst});
+    dst = (uint8_t)(dst + (e - b));
+    b = e;
+  }
+  return v;
+}
+
+} // namespace
+
+std::string HostIndex::load(const std::string& dir)
+{
+  // group files by suffix the way TargetIndex::load_index does (ref src/krepp.cpp:72-91)
+  std::vector<std::string> suffixes;
+  DIR* d = opendir(dir.c_str());
+  if (!d) return "Failed to open " + dir;
+  while (dirent* e = readdir(d)) {
+    std::string fn = e->d_name;
+    if (fn.rfind("metadata-", 0) == 0 && fn.find('.') == std::string::npos) suffixes.push_back(fn.substr(8));
+  }
+  closedir(d);
+  if (suffixes.empty()) return "There is no partial index in " + dir;
+  if (suffixes.size() > 1)
+    return "directories holding several partial libraries are not supported by the GPU path yet (found " +
+           std::to_string(suffixes.size()) + " suffixes)";
+  const std::string sfx = suffixes[0];
+  std::string buf;
+
+  // ---- metadata
+  if (!slurp(dir + "/metadata" + sfx, buf)) return "Failed to open " + dir + "/metadata" + sfx;
+  if (buf.size() < 16) return "Failed to read the metadata of a partial skecth!";
+  const unsigned char* md = reinterpret_cast<const unsigned char*>(buf.data());
+  k = md[0]; w = md[1]; h = md[2];
+  std::memcpy(&m, md + 3, 4); std::memcpy(&r, md + 7, 4); frac = md[11]; std::memcpy(&nrows, md + 12, 4);
+  if (k == 0 || k > 32 || h == 0 || h >= k || k - h > 16 || m == 0 || buf.size() < 16 + (size_t)k) return "Failed to read the metadata of a partial skecth!";
+  ppos.assign(md + 16, md + 16 + h);
+  npos.assign(md + 16 + h, md + 16 + k);
+  // masks (ref src/lshf.cpp:39-52)
+  mask_hash_bp = mask_drop_lr = mask_drop_bp = 0;
+  for (uint8_t p : npos) { if (p >= k) return "Failed to read the metadata of a partial skecth!"; mask_drop_lr += 0x0000000100000001ull << p; mask_drop_bp += 3ull << (2 * p); }
+  for (uint32_t i = 0; i < 16 - (k - h); ++i) mask_drop_lr += 1ull << (i + k);
+  for (uint8_t p : ppos) { if (p >= k) return "Failed to read the metadata of a partial skecth!"; mask_hash_bp += 3ull << (2 * p); }
+  if ((mask_hash_bp & mask_drop_bp) || __builtin_popcountll(mask_hash_bp | mask_drop_bp) != 2 * (int)k) return "Failed to read the metadata of a partial skecth!";
+  hash_runs = runs_of(mask_hash_bp);
+  drop_runs = runs_of(mask_drop_bp);
+  res_numer.assign(m, 0);
+  if (frac) { for (uint32_t i = 0; i <= r && i < m; ++i) res_numer[i] = (int32_t)(r + 1); }
+  else if (r < m) res_numer[r] = 1;
+
+  // ---- tree
+  if (!slurp(dir + "/tree" + sfx, buf)) return "Failed to open " + dir + "/tree" + sfx + " (indexes without a backbone tree are not supported by the GPU path yet)";
+  if (std::string err = tree.parse(buf); !err.empty()) return err;
+
+  // ---- cmer / inc
+  {
+    std::ifstream f(dir + "/cmer" + sfx, std::ios::binary);
+    if (!f.is_open()) return "Failed to open " + dir + "/cmer" + sfx;
+    f.read(reinterpret_cast<char*>(&nkmers), 8);
+    if (!f.good()) return "Failed to read the k-mer vector of a partial index!";
+    cmer.resize(nkmers);
+    f.read(reinterpret_cast<char*>(cmer.data()), (std::streamsize)(nkmers * 8));
+    if (!f.good() && nkmers) return "Failed to read the k-mer vector of a partial index!";
+  }
+  {
+    std::ifstream f(dir + "/inc" + sfx, std::ios::binary);
+    if (!f.is_open()) return "Failed to open " + dir + "/inc" + sfx;
+    uint32_t nr = 0;
+    f.read(reinterpret_cast<char*>(&nr), 4);
+    if (!f.good()) return "Failed to read the offset array of a partial index!";
+    nrows = nr;
+    inc.resize(nrows);
+    f.read(reinterpret_cast<char*>(inc.data()), (std::streamsize)((uint64_t)nrows * 8));
+    if (!f.good() && nrows) return "Failed to read the offset array of a partial index!";
+    uint64_t prev = 0;
+    double s1 = 0, s2 = 0;
+    for (uint64_t v : inc) {
+      if (v < prev || v > nkmers) return "Failed to read the offset array of a partial index!";
+      const double len = (double)(v - prev);
+      s1 += len; s2 += len * len; prev = v;
+    }
+    mean_bucket = nrows ? s1 / nrows : 0;
+    size_biased_bucket = s1 > 0 ? s2 / s1 : 0;
+  }
+  // every rix the hash can produce must address a row below nrows (ref src/krepp.cpp:5-16 set_nrows)
+  {
+    const uint64_t hash_size = 1ull << (2 * h);
+    uint64_t need = 0;
+    for (uint32_t res = 0; res < m; ++res) {
+      if (!res_numer[res] || res >= hash_size) continue;
+      const uint64_t max_rix = (hash_size - 1 - res) / m * m + res;
+      const uint64_t off = res_numer[res] > 1 ? (max_rix / m) * res_numer[res] + res : max_rix / m;
+      need = std::max(need, off + 1);
+    }
+    if (need > nrows) return "Failed to read the offset array of a partial index!";
+  }
+
+  // ---- crecord
+  if (!slurp(dir + "/crecord" + sfx, buf)) return "Failed to open " + dir + "/crecord" + sfx;
+  if (buf.size() < 8) return "Failed to read the color array of a partial index!";
+  std::memcpy(&cr_nnodes, buf.data(), 4); std::memcpy(&nsubsets, buf.data() + 4, 4);
+  if (buf.size() < 8 + 8ull * nsubsets + 8ull * cr_nnodes) return "Failed to read the color array of a partial index!";
+  pse.resize(nsubsets);
+  std::memcpy(pse.data(), buf.data() + 8, 8ull * nsubsets);
+  rho.resize(cr_nnodes);
+  std::memcpy(rho.data(), buf.data() + 8 + 8ull * nsubsets, 8ull * cr_nnodes);
+  if (cr_nnodes != tree.nnodes + 1 || nsubsets < cr_nnodes) return "The colour record does not match the backbone tree of the index!";
+  // make_rho_partial: rho *= (#residues present)/m (ref src/index.cpp:188-201, src/record.cpp:304-309)
+  {
+    uint32_t present = 0;
+    for (uint32_t res = 0; res < m; ++res) present += res_numer[res] != 0;
+    const double ratio_m = (double)present / (double)m;
+    for (double& x : rho) x *= ratio_m;
+  }
+  // classify colour ids the way add_matching_mer walks them (ref src/query.cpp:369-387)
+  kind.assign(nsubsets, 2);
+  kind[0] = 0;
+  for (uint32_t se = 1; se <= tree.nnodes; ++se) kind[se] = tree.is_leaf[se] ? 1 : 2;
+  for (uint64_t e : cmer) if ((uint32_t)(e >> 32) >= nsubsets) return "Failed to read the k-mer vector of a partial index!";
+  // expansion depth / leaf count per colour (iterative post-order over the DAG; also rejects cycles)
+  {
+    std::vector<uint32_t> depth(nsubsets, 0), leaves(nsubsets, 0);
+    std::vector<uint8_t> state(nsubsets, 0); // 0 new, 1 open, 2 done
+    std::vector<uint32_t> st;
+    for (uint32_t s0 = 0; s0 < nsubsets; ++s0) {
+      if (state[s0]) continue;
+      st.push_back(s0);
+      while (!st.empty()) {
+        const uint32_t se = st.back();
+        if (kind[se] != 2) { state[se] = 2; depth[se] = 0; leaves[se] = kind[se] == 1; st.pop_back(); continue; }
+        const uint32_t a = (uint32_t)pse[se], b = (uint32_t)(pse[se] >> 32);
+        if (a >= nsubsets || b >= nsubsets) return "The colour record of the index is corrupt (child id out of range)!";
+        if (state[se] == 0) {
+          state[se] = 1;
+          bool pushed = false;
+          for (uint32_t c : {a, b}) {
+            if (state[c] == 1) return "The colour record of the index is corrupt (cycle)!";
+            if (state[c] == 0) { st.push_back(c); pushed = true; }
+          }
+          if (pushed) continue;
+        }
+        state[se] = 2;
+        depth[se] = 1 + std::max(depth[a], depth[b]);
+        leaves[se] = leaves[a] + leaves[b];
+        st.pop_back();
+      }
+    }
+    max_expand_depth = *std::max_element(depth.begin(), depth.end());
+    max_colour_leaves = *std::max_element(leaves.begin(), leaves.end());
+  }
+  return "";
+}
+
+} // namespace krepp

@@ -1,0 +1,55 @@
+// Host-side image of an on-disk krepp index (the files written by `krepp index`), flattened for upload to HBM.
+//
+// Format (little-endian, packed, one suffix "-m{m}r{r}-{frac|no_frac}" per partial index):
+//   metadata-*  u8 k, u8 w, u8 h, u32 m, u32 r, u8 frac, u32 nrows, u8 ppos[h] (descending), u8 npos[k-h] (ascending)
+//               (ref src/krepp.cpp:18-29, src/index.cpp:58-72)
+//   cmer-*      u64 nkmers, nkmers x {u32 enc, u32 se}                      (ref src/table.cpp:65-70)
+//   inc-*       u32 nrows, nrows x u64 cumulative bucket end               (ref src/table.cpp:71-74)
+//   crecord-*   u32 nnodes, u32 nsubsets, nsubsets x {u32,u32}, nnodes x f64 rho   (ref src/record.cpp:203-211)
+//   tree-*      Newick text                                                 (ref src/phytree.cpp:394-404)
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace krepp {
+
+struct BitRun { uint8_t src, width, dst; }; // ((x >> src) & ((1<<width)-1)) << dst
+
+struct HostTree {
+  uint32_t nnodes = 0, root = 0, nleaves = 0;
+  std::vector<uint32_t> parent, nchildren, card, first_child, next_sibling; // [nnodes+1], by se
+  std::vector<uint8_t> is_leaf;
+  std::vector<double> blen;              // NaN when absent
+  std::vector<std::string> name;         // "" when unlabeled
+  std::vector<uint32_t> leaf_rank;       // se -> 0-based rank among leaves by ascending se (0xffffffff for non-leaves)
+  std::vector<uint32_t> leaf_se;         // rank -> se
+  // Parses Newick text with the reference's conventions (ref src/phytree.cpp:84-215): post-order, 1-based se.
+  // Returns an empty string on success, else the error message.
+  std::string parse(const std::string& newick);
+  std::string node_name(uint32_t se, bool return_na) const; // ref src/phytree.hpp:133-144
+  std::string jplace_newick() const;                         // ref src/phytree.cpp:47-64
+};
+
+struct HostIndex {
+  uint32_t k = 0, w = 0, h = 0, m = 0, r = 0, frac = 0, nrows = 0;
+  uint64_t nkmers = 0;
+  std::vector<uint8_t> ppos, npos;
+  uint64_t mask_hash_bp = 0, mask_drop_lr = 0, mask_drop_bp = 0;
+  std::vector<BitRun> hash_runs, drop_runs;   // pext plans over the 2-bit (bp) k-mer word
+  std::vector<int32_t> res_numer;             // [m]: 0 = residue absent, else numerator (ref src/index.cpp:144-157)
+  std::vector<uint64_t> cmer;                 // nkmers x (enc | se<<32)
+  std::vector<uint64_t> inc;                  // nrows
+  uint32_t cr_nnodes = 0, nsubsets = 0;
+  std::vector<uint64_t> pse;                  // nsubsets x (first | second<<32)
+  std::vector<double> rho;                    // cr_nnodes, already scaled by make_rho_partial (ref src/index.cpp:188-201)
+  std::vector<uint8_t> kind;                  // [nsubsets]: 0 drop (null node), 1 leaf, 2 expand through pse
+  uint32_t max_expand_depth = 0;              // deepest colour DAG expansion (bounds the device stack)
+  uint32_t max_colour_leaves = 0;
+  double mean_bucket = 0, size_biased_bucket = 0;
+  HostTree tree;
+  // Returns "" on success, else an error message (the reference's wording where it has one).
+  std::string load(const std::string& dir);
+};
+
+} // namespace krepp

@@ -1,0 +1,17 @@
+// Declarations shared between the kernels' translation units and the C-ABI layer.
+#pragma once
+#include "device.cuh"
+
+namespace krepp {
+
+// Binomial tables of optimize::HDistHistLLH (ref src/hdhistllh.hpp:51-69), exact in double (values < 2^53).
+struct LlhTables {
+  double ck[33];          // C(k, x), x = 0..k
+  double hnk[kMaxTh + 1]; // C(k, x) - C(k-h, x) for 1 <= x <= th, and 0 for x = 0
+};
+
+int match_resident_warps(int device);
+cudaError_t launch_match(const DevIndex& ix, const MatchArgs& a, int resident_warps, bool tap, cudaStream_t stream);
+cudaError_t launch_solve(const SolveArgs& a, const LlhTables& tab, int sms, cudaStream_t stream);
+
+} // namespace krepp

@@ -1,0 +1,129 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the oracle on the same inputs.
+
+Integer stages (k-mers/lookups, bucket ids, matched sets, Hamming histograms, filters, selections) must be bit-exact;
+d_llh / v_llh / chisq within 1e-5 relative (north_star).  Needs oracle/_ref/toy (the reference-built toy index).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import conftest
+from conftest import TOY_DIR, needs_ref
+
+pytestmark = [pytest.mark.gpu]
+
+
+@pytest.fixture(scope="module")
+def env():
+    import krepp_b200
+    import oracle_lib as O
+    idx = os.path.join(TOY_DIR, "index_toy")
+    return dict(dir=idx, oracle=O.OracleIndex(idx), gpu=krepp_b200.Index(idx, 0))
+
+
+def fastq_reads(path):
+    with open(path, "rb") as f:
+        lines = f.read().split(b"\n")
+    return [lines[i][1:].split()[0].decode() for i in range(0, len(lines) - 1, 4)], [lines[i] for i in range(1, len(lines), 4)]
+
+
+@needs_ref
+def test_toy_query_all_stages(env):
+    from gpu_common import run_and_compare
+    names, reads = fastq_reads(os.path.join(TOY_DIR, "query_toy.fq"))
+    st = run_and_compare(env["dir"], reads, env["oracle"], env["gpu"])
+    assert st["reads"] == 100 and st["solves"] > 100
+    print(st)
+
+
+@needs_ref
+def test_synthetic_20k_all_stages(env):
+    import synth
+    from gpu_common import run_and_compare
+    seq, offs = synth.load_packed(os.path.join(TOY_DIR, "genomes.npz"))
+    reads = [r.tobytes() for r in synth.sample_reads(seq, offs, 20000, seed=1)]
+    st = run_and_compare(env["dir"], reads, env["oracle"], env["gpu"])
+    print(st)
+    assert st["bitexact_d"] >= 0.99 * st["solves"]
+
+
+@needs_ref
+def test_edge_cases(env):
+    """Empty / shorter-than-k / exactly-k reads, N runs, lower case, non-ACGT bytes, long and ragged reads."""
+    import synth
+    from gpu_common import run_and_compare
+    seq, offs = synth.load_packed(os.path.join(TOY_DIR, "genomes.npz"))
+    rng = np.random.default_rng(5)
+    base = [r.tobytes() for r in synth.sample_reads(seq, offs, 64, read_len=300, max_sub=0.05, seed=3)]
+    reads = [b"", b"A", base[0][:26], base[0][:27], base[1][:28], b"N" * 150, base[2][:100].lower(),
+             base[3][:60] + b"N" + base[3][61:150], base[4][:30] + b"NNNNN" + base[4][35:200], b"ACGT" * 40, b"A" * 200,
+             base[5][:149] + b"*", bytes([200]) + base[6][:150], base[7][:150].replace(b"A", b"R")]
+    for ln in (127, 128, 129, 154, 155, 156, 255, 256, 257, 283, 300):
+        reads.append(base[8 + (ln % 7)][:ln])
+    long_src = synth.sample_reads(seq, offs, 4, read_len=5000, max_sub=0.02, seed=9)
+    reads += [long_src[0].tobytes(), long_src[1].tobytes()[:1000], long_src[2].tobytes()[:3333]]
+    for _ in range(40):
+        ln = int(rng.integers(1, 400))
+        r = bytearray(base[int(rng.integers(0, 64))][:ln])
+        for _ in range(int(rng.integers(0, 4))):
+            r[int(rng.integers(0, len(r)))] = ord("N")
+        reads.append(bytes(r))
+    st = run_and_compare(env["dir"], reads, env["oracle"], env["gpu"])
+    print(st)
+
+
+@needs_ref
+@pytest.mark.parametrize("th", [0, 2, 7])
+def test_other_thresholds(env, th):
+    import synth
+    from gpu_common import run_and_compare
+    seq, offs = synth.load_packed(os.path.join(TOY_DIR, "genomes.npz"))
+    reads = [r.tobytes() for r in synth.sample_reads(seq, offs, 1500, seed=11 + th)]
+    run_and_compare(env["dir"], reads, env["oracle"], env["gpu"], check_lookups=False, hdist_th=th)
+
+
+@needs_ref
+def test_dist_filter_chisq(env):
+    import synth
+    from gpu_common import run_and_compare
+    seq, offs = synth.load_packed(os.path.join(TOY_DIR, "genomes.npz"))
+    reads = [r.tobytes() for r in synth.sample_reads(seq, offs, 3000, seed=21)]
+    run_and_compare(env["dir"], reads, env["oracle"], env["gpu"], check_lookups=False, no_filter=False)
+
+
+@needs_ref
+def test_tsv_matches_reference_cli(env):
+    """`krepp dist` body of the reference binary itself vs the GPU path's TSV, compared as sorted line sets."""
+    import subprocess
+    import krepp_b200
+    names, reads = fastq_reads(os.path.join(TOY_DIR, "query_toy.fq"))
+    ref = subprocess.run([os.path.join(conftest.REF_DIR, "krepp"), "dist", "-i", env["dir"], "-q", os.path.join(TOY_DIR, "query_toy.fq")],
+                         capture_output=True, text=True, check=True).stdout.splitlines()[2:]
+    b = krepp_b200.IBatch(env["gpu"], reads, names=names)
+    got = b.estimate_distances().splitlines()
+    assert sorted(got) == sorted(ref)
+
+
+@needs_ref
+def test_device_resident_input_and_idempotence(env):
+    """submit_device on HBM-resident reads gives the same records as the host path; resubmitting a slot is idempotent."""
+    import torch
+    import krepp_b200
+    import synth
+    seq, offs = synth.load_packed(os.path.join(TOY_DIR, "genomes.npz"))
+    m = synth.sample_reads(seq, offs, 5000, seed=33)
+    b = krepp_b200.IBatch(env["gpu"], m)
+    b.submit(); r1 = b.wait()
+    key1 = (r1["reads"].copy(), np.sort(r1["records"].copy(), order=["read", "strand", "leaf_se"]))
+    d_b = torch.from_numpy(b.bases.copy()).cuda()
+    d_o = torch.from_numpy(b.offsets.astype(np.int64)).cuda()
+    for _ in range(2):
+        b.submit_device(d_b.data_ptr(), d_o.data_ptr(), b.n_reads, int(b.offsets[-1]))
+        r2 = b.wait()
+        rec2 = np.sort(r2["records"].copy(), order=["read", "strand", "leaf_se"])
+        for f in ("leaf_se", "strand", "match_count", "hdist_min", "flags"):
+            assert np.array_equal(key1[1][f], rec2[f]), f
+        assert np.array_equal(key1[1]["d_llh"], rec2["d_llh"])
+        for f in ("onmers", "wn", "hdist_filt", "rec_count"):
+            assert np.array_equal(key1[0][f], r2["reads"][f]), f
