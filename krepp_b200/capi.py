@@ -46,7 +46,7 @@ class IndexInfo(C.Structure):
 class Results(C.Structure):
     _fields_ = [("n_reads", C.c_uint32), ("hist_stride", C.c_uint32), ("n_records", C.c_uint64), ("n_placements", C.c_uint64),
                 ("reads", C.c_void_p), ("records", C.c_void_p), ("hist", C.c_void_p), ("placements", C.c_void_p),
-                ("gpu_ms", C.c_float), ("gpu_launches", C.c_uint32)]
+                ("gpu_ms", C.c_float), ("match_ms", C.c_float), ("gpu_launches", C.c_uint32)]
 
 
 RECORD_DTYPE = np.dtype([("read", "<u4"), ("leaf_se", "<u4"), ("strand", "<u4"), ("match_count", "<u4"), ("hdist_min", "<u4"),
@@ -195,6 +195,18 @@ class IBatch:
     def enable_tap(self, capacity_items: int):
         _check(load_library().krepp_batch_enable_tap(self._h, 1, capacity_items))
 
+    def pin_inputs(self):
+        """Moves this batch's reads into the slot's own pinned host buffers (krepp_batch_host_buffers) so that submit()
+        copies host->device straight from pinned memory, without the staging memcpy."""
+        pb, po = C.c_void_p(), C.c_void_p()
+        _check(load_library().krepp_batch_host_buffers(self._h, C.byref(pb), C.byref(po)))
+        nb = int(self.offsets[-1])
+        hb = np.frombuffer((C.c_char * max(nb, 1)).from_address(pb.value), dtype=np.uint8, count=nb)
+        ho = np.frombuffer((C.c_char * (8 * (self.n_reads + 1))).from_address(po.value), dtype=np.uint64, count=self.n_reads + 1)
+        hb[:] = self.bases[:nb]
+        ho[:] = self.offsets - self.offsets[0]
+        self.bases, self.offsets = hb, ho
+
     def submit(self):
         _check(load_library().krepp_batch_submit(self._h, self.bases.ctypes.data, self.offsets.ctypes.data, self.n_reads))
 
@@ -208,7 +220,7 @@ class IBatch:
         self._res = dict(
             reads=_view(r.reads, READ_DTYPE, r.n_reads), records=_view(r.records, RECORD_DTYPE, nrec),
             hist=_view(r.hist, np.dtype("<u4"), nrec * r.hist_stride).reshape(nrec, r.hist_stride),
-            placements=_view(r.placements, PLACEMENT_DTYPE, int(r.n_placements)), gpu_ms=float(r.gpu_ms),
+            placements=_view(r.placements, PLACEMENT_DTYPE, int(r.n_placements)), gpu_ms=float(r.gpu_ms), match_ms=float(r.match_ms),
             gpu_launches=int(r.gpu_launches))
         return self._res
 

@@ -93,7 +93,7 @@ struct krepp_batch {
   krepp_params_t p{};
   LlhTables tab{};
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm0 = nullptr, evm1 = nullptr;
   uint32_t max_reads = 0, rec_cap = 0, n_reads = 0, launches = 0;
   uint64_t max_bases = 0, n_bases = 0;
   bool submitted = false, device_input = false;
@@ -276,7 +276,7 @@ int krepp_batch_create(krepp_index_t* ix, const krepp_params_t* p, uint32_t max_
     for (uint32_t i = 1; i <= p->hdist_th; ++i) { vc = (vc * (nh - i + 1)) / i; b->tab.hnk[i] = (double)(ck[i] - vc); }
   }
   CU(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
-  CU(cudaEventCreate(&b->ev0)); CU(cudaEventCreate(&b->ev1));
+  CU(cudaEventCreate(&b->ev0)); CU(cudaEventCreate(&b->ev1)); CU(cudaEventCreate(&b->evm0)); CU(cudaEventCreate(&b->evm1));
   CU(cudaMallocHost(&b->h_bases, max_bases + 64)); CU(cudaMallocHost(&b->h_offsets, 8ull * (max_reads + 1)));
   CU(cudaMalloc(&b->d_bases, max_bases + 64)); CU(cudaMalloc(&b->d_offsets, 8ull * (max_reads + 1)));
   CU(cudaMalloc(&b->d_onmers, 4ull * max_reads)); CU(cudaMalloc(&b->d_wn, 8ull * max_reads)); CU(cudaMalloc(&b->d_hdfilt, 8ull * max_reads));
@@ -312,6 +312,8 @@ void krepp_batch_destroy(krepp_batch_t* b)
     if (p) cudaFreeHost(p);
   if (b->ev0) cudaEventDestroy(b->ev0);
   if (b->ev1) cudaEventDestroy(b->ev1);
+  if (b->evm0) cudaEventDestroy(b->evm0);
+  if (b->evm1) cudaEventDestroy(b->evm1);
   if (b->stream) cudaStreamDestroy(b->stream);
   delete b;
 }
@@ -331,7 +333,9 @@ static int enqueue(krepp_batch* b)
   m.rec_read = b->d_rec_read; m.rec_slot = b->d_rec_slot; m.rec_hist = b->d_rec_hist; m.rec_cap = b->rec_cap; m.counters = b->d_counters;
   m.acc = b->d_acc; m.bitmap = b->d_bitmap; m.marker = b->d_marker; m.stack = b->d_stack; m.stack_cap = b->stack_cap; m.stats = b->d_stats;
   m.tap = b->d_tap; m.tap_count = b->d_tap_count; m.tap_cap = b->tap_cap;
+  CU(cudaEventRecord(b->evm0, s));
   CU(launch_match(ix->dev, m, ix->resident_warps, b->d_tap != nullptr, s));
+  CU(cudaEventRecord(b->evm1, s));
   SolveArgs sa{};
   sa.n_reads = b->n_reads; sa.th = b->p.hdist_th; sa.k = h.k; sa.h = h.h; sa.n_records = b->rec_cap; sa.counters = b->d_counters;
   sa.onmers = b->d_onmers; sa.hdfilt = b->d_hdfilt; sa.rec_begin = b->d_rec_begin; sa.rec_count = b->d_rec_count;
@@ -423,7 +427,9 @@ int krepp_batch_wait(krepp_batch_t* b, krepp_results_t* out)
   CU(cudaEventElapsedTime(&ms, b->ev0, b->ev1));
   out->n_reads = b->n_reads; out->hist_stride = (uint32_t)stride; out->n_records = nrec; out->n_placements = 0;
   out->reads = b->h_read; out->records = b->h_rec; out->hist = b->h_hist; out->placements = nullptr;
-  out->gpu_ms = ms; out->gpu_launches = b->launches;
+  float mms = 0;
+  CU(cudaEventElapsedTime(&mms, b->evm0, b->evm1));
+  out->gpu_ms = ms; out->match_ms = mms; out->gpu_launches = b->launches;
   return KREPP_OK;
 }
 
