@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -54,6 +55,37 @@ cudaError_t upload(const std::vector<T>& v, const T** out, std::vector<void*>& a
   return e;
 }
 
+// Byte-indexed tables for the two software pexts (see match.cu lut_pext).  Position p (0 = last base of the k-mer) sits at
+// bits 2p, 2p+1 of the k-mer word.  Forward strand: a base at a hash position contributes its code to rix at the rank of
+// that position among ppos (ascending, pext order; ref src/lshf.cpp:47-50,62); a base at a kept position contributes
+// bit0 / bit1 of its code to bits r and 16+r of q, r its rank among npos (ref src/lshf.cpp:39-46,64-69).  Reverse
+// strand: the same forward base, complemented, is the base at position k-1-p of the reverse complement
+// (ref src/common.hpp:177-186).
+static std::vector<uint64_t> build_lut(const HostIndex& h)
+{
+  std::vector<int> hrank(32, -1), nrank(32, -1);
+  { std::vector<uint8_t> pp = h.ppos, np = h.npos; std::sort(pp.begin(), pp.end()); std::sort(np.begin(), np.end());
+    for (size_t i = 0; i < pp.size(); ++i) hrank[pp[i]] = (int)i;
+    for (size_t i = 0; i < np.size(); ++i) nrank[np[i]] = (int)i; }
+  const uint32_t nch = (2 * h.k + 7) / 8; // bytes of the k-mer word that can be non-zero
+  std::vector<uint64_t> lut(2 * nch * 256, 0);
+  for (uint32_t strand = 0; strand < 2; ++strand)
+    for (uint32_t c = 0; c < nch; ++c)
+      for (uint32_t v = 0; v < 256; ++v) {
+        uint64_t rix = 0, q = 0;
+        for (uint32_t s = 0; s < 4; ++s) {
+          const uint32_t p = 4 * c + s;
+          if (p >= h.k) continue;
+          uint32_t code = (v >> (2 * s)) & 3, pos = p;
+          if (strand) { code = 3 - code; pos = h.k - 1 - p; }
+          if (hrank[pos] >= 0) rix |= (uint64_t)code << (2 * hrank[pos]);
+          if (nrank[pos] >= 0) q |= (uint64_t)(code & 1) << nrank[pos] | (uint64_t)(code >> 1) << (16 + nrank[pos]);
+        }
+        lut[(strand * nch + c) * 256 + v] = rix | (q << 32);
+      }
+  return lut;
+}
+
 // AoS assembly of the public result structs on the device (one D2H copy each, no host-side gather).
 __global__ void __launch_bounds__(128) finalize_kernel(const SolveArgs a, krepp_record_t* out_rec, krepp_read_summary_t* out_read,
                                                         const uint32_t* wn)
@@ -83,7 +115,7 @@ __global__ void __launch_bounds__(128) finalize_kernel(const SolveArgs a, krepp_
 struct krepp_index {
   HostIndex host;
   DevIndex dev{};
-  int device = 0, sms = 0, resident_warps = 0;
+  int device = 0, sms = 0, resident_warps = 0, group = 4;
   uint64_t device_bytes = 0;
   std::vector<void*> allocs;
 };
@@ -145,7 +177,7 @@ int krepp_index_open(const char* index_dir, int device, krepp_index_t** out)
   const HostIndex& h = ix->host;
   if (device == KREPP_DEVICE_NONE) { ix->device = device; *out = ix; return KREPP_OK; } // metadata / tree only, no queries
   if (h.m > (uint32_t)kMaxResidues) { const uint32_t m = h.m; delete ix; return fail(KREPP_ERR_UNSUPPORTED, "m = %u exceeds the %d residues supported on the device", m, kMaxResidues); }
-  if (h.hash_runs.size() > (size_t)kMaxRuns || h.drop_runs.size() > (size_t)kMaxRuns) { delete ix; return fail(KREPP_ERR_UNSUPPORTED, "hash mask has too many runs"); }
+  if (h.inc32.empty() && h.nrows) { delete ix; return fail(KREPP_ERR_UNSUPPORTED, "indexes with 2^32 or more k-mers are not supported by the GPU path yet"); }
   ix->device = device;
   cudaError_t e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ix->sms, cudaDevAttrMultiProcessorCount, device);
@@ -153,7 +185,7 @@ int krepp_index_open(const char* index_dir, int device, krepp_index_t** out)
   std::vector<uint2> tmp2;
   // the image: cmer and pse are uploaded verbatim (8-byte pairs), inc padded by one entry
   if (e == cudaSuccess) e = upload(h.cmer, reinterpret_cast<const uint64_t**>(&d.cmer), ix->allocs, ix->device_bytes, 4);
-  if (e == cudaSuccess) e = upload(h.inc, &d.inc, ix->allocs, ix->device_bytes, 1);
+  if (e == cudaSuccess) e = upload(h.inc32, &d.inc32, ix->allocs, ix->device_bytes, 1);
   if (e == cudaSuccess) e = upload(h.pse, reinterpret_cast<const uint64_t**>(&d.pse), ix->allocs, ix->device_bytes);
   if (e == cudaSuccess) e = upload(h.kind, &d.kind, ix->allocs, ix->device_bytes);
   if (e == cudaSuccess) e = upload(h.rho, &d.rho, ix->allocs, ix->device_bytes);
@@ -162,6 +194,7 @@ int krepp_index_open(const char* index_dir, int device, krepp_index_t** out)
   if (e == cudaSuccess) e = upload(h.tree.parent, &d.parent, ix->allocs, ix->device_bytes);
   if (e == cudaSuccess) e = upload(h.tree.nchildren, &d.nchildren, ix->allocs, ix->device_bytes);
   if (e == cudaSuccess) e = upload(h.tree.blen, &d.blen, ix->allocs, ix->device_bytes);
+  if (e == cudaSuccess) e = upload(build_lut(h), &d.lut, ix->allocs, ix->device_bytes);
   if (e != cudaSuccess) {
     for (void* p : ix->allocs) cudaFree(p);
     delete ix;
@@ -170,12 +203,16 @@ int krepp_index_open(const char* index_dir, int device, krepp_index_t** out)
   d.nkmers = h.nkmers; d.nrows = h.nrows; d.nsubsets = h.nsubsets; d.nnodes = h.tree.nnodes; d.nleaves = h.tree.nleaves;
   d.k = h.k; d.h = h.h; d.m = h.m;
   d.m_shift = (h.m & (h.m - 1)) == 0 ? (uint32_t)__builtin_ctz(h.m) : 0xFFFFFFFFu;
-  d.n_hash_runs = (uint32_t)h.hash_runs.size(); d.n_drop_runs = (uint32_t)h.drop_runs.size();
-  for (size_t i = 0; i < h.hash_runs.size(); ++i) d.hash_runs[i] = {h.hash_runs[i].src, (uint32_t)((1ull << h.hash_runs[i].width) - 1), h.hash_runs[i].dst};
-  for (size_t i = 0; i < h.drop_runs.size(); ++i) d.drop_runs[i] = {h.drop_runs[i].src, (uint32_t)((1ull << h.drop_runs[i].width) - 1), h.drop_runs[i].dst};
   for (uint32_t i = 0; i < (uint32_t)kMaxResidues; ++i) d.res_numer[i] = i < h.m ? h.res_numer[i] : 0;
   d.local_expand = h.max_expand_depth + 2 <= 32 ? 1u : 0u;
-  ix->resident_warps = match_resident_warps(device);
+  ix->resident_warps = match_resident_warps(device, h.k);
+  { // scan group width: lanes that cooperate on one bucket (see match.cu phase B)
+    const double nonempty = h.mean_bucket > 0 ? h.size_biased_bucket : 0; // entries seen by a lookup that lands on a k-mer
+    int g = 1;
+    while (g < 32 && 2.0 * g < std::max(h.mean_bucket, nonempty * 0.5)) g *= 2;
+    if (const char* env = getenv("KREPP_GROUP")) { const int v = atoi(env); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) g = v; }
+    ix->group = g;
+  }
   *out = ix;
   return KREPP_OK;
 }
@@ -334,7 +371,7 @@ static int enqueue(krepp_batch* b)
   m.acc = b->d_acc; m.bitmap = b->d_bitmap; m.marker = b->d_marker; m.stack = b->d_stack; m.stack_cap = b->stack_cap; m.stats = b->d_stats;
   m.tap = b->d_tap; m.tap_count = b->d_tap_count; m.tap_cap = b->tap_cap;
   CU(cudaEventRecord(b->evm0, s));
-  CU(launch_match(ix->dev, m, ix->resident_warps, b->d_tap != nullptr, s));
+  CU(launch_match(ix->dev, m, ix->resident_warps, ix->group, b->d_tap != nullptr, s));
   CU(cudaEventRecord(b->evm1, s));
   SolveArgs sa{};
   sa.n_reads = b->n_reads; sa.th = b->p.hdist_th; sa.k = h.k; sa.h = h.h; sa.n_records = b->rec_cap; sa.counters = b->d_counters;

@@ -9,12 +9,13 @@ constexpr int kMaxRuns = 18;      // a pext mask over k <= 32 two-bit groups has
 constexpr int kMaxResidues = 64;  // m (modulo of the LSH partition, ref src/krepp.hpp:40) supported on device
 constexpr int kMaxTh = 16;
 
-struct DevRun { uint32_t src, mask, dst; };
+constexpr int kLutChunks = 8;     // bytes of the 64-bit k-mer word
 
 // Flat index image resident in HBM (see index_image.hpp for the on-disk format it mirrors).
 struct DevIndex {
   const uint2* cmer;        // nkmers x (enc32, se)               ref FlatHT::cmer_v  src/table.hpp:143
-  const uint64_t* inc;      // nrows cumulative bucket ends        ref FlatHT::inc_v   src/table.hpp:142
+  const uint32_t* inc32;    // nrows cumulative bucket ends, narrowed to 32 bits (nkmers < 2^32)
+                            //                                     ref FlatHT::inc_v   src/table.hpp:142
   const uint2* pse;         // nsubsets x (first, second)          ref CRecord::se_to_pse src/record.hpp:103
   const uint8_t* kind;      // nsubsets: 0 drop, 1 leaf, 2 expand  ref src/query.cpp:373-386
   const double* rho;        // by se, scaled                        ref CRecord::se_to_rho src/record.hpp:104
@@ -26,9 +27,8 @@ struct DevIndex {
   uint64_t nkmers;
   uint32_t nrows, nsubsets, nnodes, nleaves;
   uint32_t k, h, m, m_shift; // m_shift = log2(m) when m is a power of two, else 0xffffffff
-  uint32_t n_hash_runs, n_drop_runs;
   uint32_t local_expand;    // 1 when the deepest colour DAG fits the lane-private expansion stack
-  DevRun hash_runs[kMaxRuns], drop_runs[kMaxRuns];
+  const uint64_t* lut;      // [2 strands][8 bytes][256]: rix part | q part << 32 (see match.cu lut_pext)
   int32_t res_numer[kMaxResidues];
 };
 

@@ -296,6 +296,7 @@ std::string HostIndex::load(const std::string& dir)
       const double len = (double)(v - prev);
       s1 += len; s2 += len * len; prev = v;
     }
+    if (nkmers < (1ull << 32)) { inc32.resize(nrows); for (size_t i = 0; i < inc.size(); ++i) inc32[i] = (uint32_t)inc[i]; }
     mean_bucket = nrows ? s1 / nrows : 0;
     size_biased_bucket = s1 > 0 ? s2 / s1 : 0;
   }

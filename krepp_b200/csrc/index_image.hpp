@@ -40,6 +40,7 @@ struct HostIndex {
   std::vector<int32_t> res_numer;             // [m]: 0 = residue absent, else numerator (ref src/index.cpp:144-157)
   std::vector<uint64_t> cmer;                 // nkmers x (enc | se<<32)
   std::vector<uint64_t> inc;                  // nrows
+  std::vector<uint32_t> inc32;                // nrows, present when nkmers < 2^32 (what the device scans with)
   uint32_t cr_nnodes = 0, nsubsets = 0;
   std::vector<uint64_t> pse;                  // nsubsets x (first | second<<32)
   std::vector<double> rho;                    // cr_nnodes, already scaled by make_rho_partial (ref src/index.cpp:188-201)

@@ -1,15 +1,19 @@
 // match.cu -- K1..K3 of the query path fused into one persistent kernel (sm_100a).
 //
-// One warp owns one read at a time (reads are claimed from a global counter, so ragged lengths balance):
-//   1. 128-bit loads of the read's ASCII bases -> 2-bit codes + validity bits, packed MSB-first in shared memory
-//      (ref src/common.cpp:10-18 seq_nt4_table, src/common.hpp:225-243 compute/update_encoding).
-//   2. every lane extracts k-mer windows from the packed stream, forms the reverse complement
-//      (ref src/common.hpp:177-186), the LSH bucket id rix = pext(bp, mask_hash_bp) (ref src/lshf.cpp:62) and the 32-bit
-//      residual q = pext(lr, mask_drop_lr) (ref src/lshf.cpp:64-69), eligibility + row offset (ref src/index.hpp:27,
-//      src/index.cpp:160-168) for both strands (ref src/query.cpp:82-91).
-//   3. the bucket [inc[off-1], inc[off]) of the flat table is scanned with XOR/OR/popc (ref src/common.hpp:175,
-//      src/query.cpp:361-368); hits expand their colour through the se->(se,se) DAG to leaves on the device
-//      (ref src/query.cpp:369-387) and bump the per-(strand, leaf) Hamming histogram (ref src/query.hpp:153-176).
+// One warp owns one read at a time (reads are claimed from a global counter, so ragged lengths balance) and walks it
+// in tiles of 128 k-mer windows:
+//   A0. 128-bit loads of the tile's ASCII bases -> 2-bit codes + validity bits, packed MSB-first in shared memory
+//       (ref src/common.cpp:10-18 seq_nt4_table, src/common.hpp:225-243 compute/update_encoding).
+//   A1. every lane extracts 4 windows from the packed stream, forms the reverse complement (ref src/common.hpp:177-186)
+//       and the LSH bucket id rix = pext(bp, mask_hash_bp) (ref src/lshf.cpp:62) for both strands (ref
+//       src/query.cpp:82-91); eligible lookups (ref src/index.hpp:27) are compacted into a shared-memory list.
+//   A2. the compacted list is completed with all lanes busy: residual q = pext(lr, mask_drop_lr) (ref src/lshf.cpp:64-69)
+//       and the bucket range [inc[off-1], inc[off]) (ref src/index.cpp:160-168, src/table.hpp:121-136); all range loads
+//       of a tile are in flight together; empty buckets are dropped from the list.
+//   B.  groups of G lanes (G chosen by the host from the index's bucket occupancy) pull lookups from the list and scan
+//       their buckets G entries per step with XOR/OR/popc (ref src/common.hpp:175, src/query.cpp:361-368); consecutive
+//       lanes read consecutive 8-byte entries.  Hits expand their colour through the se->(se,se) DAG to leaves on the
+//       device (ref src/query.cpp:369-387) and bump the per-(strand, leaf) Hamming histogram (ref src/query.hpp:153-176).
 //
 // The reference's Minfo::update_match keeps, per (strand, leaf, position), the MINIMUM Hamming distance over all
 // matching entries.  All entries that can match one (read, strand, position) live in one bucket, so that minimum is
@@ -26,11 +30,20 @@ constexpr int kWarpsPerCta = 8;
 constexpr int kTileWindows = 128;              // windows handled per tile: 4 per lane
 constexpr int kTileWords = 12;                 // 16 bases per 32-bit word -> 192 bases >= 128 + 32 - 1
 constexpr int kLocalStack = 32;
+constexpr uint32_t kClaim = 4;                // reads claimed per atomic on the global work counter
+constexpr int kMaxLookups = 2 * kTileWindows;  // both strands
 
 struct WarpSmem {
+  uint32_t lk_a[kMaxLookups];  // A1: row offset | strand<<31; A2: first entry of the bucket
+  uint32_t lk_l[kMaxLookups];  // A2: bucket length | strand<<31
+  uint32_t lk_q[kMaxLookups];  // residual encoding q of the query k-mer
   uint32_t code[kTileWords + 1];
   uint32_t valid[kTileWords / 2 + 1];
+  uint32_t cursor;
 };
+// LUT layout: [strand][byte of the k-mer word][byte value] -> rix part | q part << 32; 7 bytes cover k <= 28
+__host__ __device__ inline uint32_t lut_chunks(uint32_t k) { return (2 * k + 7) / 8; }
+__host__ __device__ inline size_t smem_bytes(uint32_t k) { return 2 * lut_chunks(k) * 256 * sizeof(uint64_t) + kWarpsPerCta * sizeof(WarpSmem); }
 
 __device__ __forceinline__ void encode4(uint32_t u, uint32_t& code8, uint32_t& valid4)
 {
@@ -43,28 +56,23 @@ __device__ __forceinline__ void encode4(uint32_t u, uint32_t& code8, uint32_t& v
   valid4 = ((vm & 0x01010101u) * 0x08040201u) >> 24;      // first char -> bit 3
 }
 
-__device__ __forceinline__ uint32_t pext_runs(uint64_t x, const DevRun* runs, uint32_t n)
+// Both software pexts of one k-mer word, for one strand, by table lookup: the 2k-bit word is cut into bytes (4 bases
+// each); every byte value maps to its pre-positioned contribution to rix = pext(bp, mask_hash_bp) (low 32 bits) and to
+// q = pext(lr, mask_drop_lr) (high 32 bits, already in the bit-plane form the index stores).  The reverse strand uses a
+// second table indexed by the SAME forward bytes (a base at position p lands, complemented, at position k-1-p of the
+// reverse complement), so no reverse-complement word is ever formed.  Tables are built by the host from the index's
+// ppos/npos (api.cu build_lut) and copied to shared memory once per CTA.
+__device__ __forceinline__ uint64_t lut_pext(const uint64_t* lut, uint32_t lo, uint32_t hi, bool wide)
 {
-  uint32_t r = 0;
-  for (uint32_t i = 0; i < n; ++i) r |= ((uint32_t)(x >> runs[i].src) & runs[i].mask) << runs[i].dst;
+  uint64_t r = lut[lo & 0xFF];
+  r |= lut[256 + ((lo >> 8) & 0xFF)];
+  r |= lut[512 + ((lo >> 16) & 0xFF)];
+  r |= lut[768 + (lo >> 24)];
+  r |= lut[1024 + (hi & 0xFF)];
+  r |= lut[1280 + ((hi >> 8) & 0xFF)];
+  r |= lut[1536 + ((hi >> 16) & 0xFF)];
+  if (wide) r |= lut[1792 + (hi >> 24)]; // only k > 28 reaches the eighth byte
   return r;
-}
-
-__device__ __forceinline__ uint32_t even_bits16(uint32_t t)
-{
-  t &= 0x55555555u;
-  t = (t | (t >> 1)) & 0x33333333u;
-  t = (t | (t >> 2)) & 0x0F0F0F0Fu;
-  t = (t | (t >> 4)) & 0x00FF00FFu;
-  t = (t | (t >> 8)) & 0x0000FFFFu;
-  return t;
-}
-
-__device__ __forceinline__ uint64_t revcomp(uint64_t bp, uint32_t k)
-{
-  uint64_t y = __brevll(bp);
-  y = ((y >> 1) & 0x5555555555555555ull) | ((y & 0x5555555555555555ull) << 1);
-  return (~y) >> (64 - 2 * k);
 }
 
 struct WarpCtx {
@@ -135,14 +143,14 @@ __device__ void expand_coop(const DevIndex& ix, const WarpCtx& w, uint32_t se, u
 
 // Careful path for one lookup with several hit entries (or a colour too deep for the private stack): the whole warp
 // rescans the bucket, marks per-leaf minima, then commits them.
-__device__ void careful_lookup(const DevIndex& ix, const WarpCtx& w, uint64_t begin, uint32_t len, uint32_t q, uint32_t strand, uint32_t th)
+__device__ void careful_lookup(const DevIndex& ix, const WarpCtx& w, uint32_t begin, uint32_t len, uint32_t q, uint32_t strand, uint32_t th)
 {
   const uint32_t lane = threadIdx.x & 31;
   for (int pass = 1; pass <= 2; ++pass) {
     for (uint32_t base = 0; base < len; base += 32) {
       uint32_t se = 0, hd = 0xFFFFFFFFu;
       if (base + lane < len) {
-        const uint2 e = ix.cmer[begin + base + lane];
+        const uint2 e = ix.cmer[(size_t)begin + base + lane];
         const uint32_t z = e.x ^ q;
         hd = __popc((z | (z >> 16)) & 0xFFFFu);
         se = e.y;
@@ -158,15 +166,25 @@ __device__ void careful_lookup(const DevIndex& ix, const WarpCtx& w, uint64_t be
   }
 }
 
-template <bool TAP>
+template <int G, bool TAP>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) match_kernel(const DevIndex ix, const MatchArgs a)
 {
-  __shared__ WarpSmem smem[kWarpsPerCta];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const uint32_t nchunks = lut_chunks(ix.k), lut_strand = nchunks * 256;
+  uint64_t* lut = reinterpret_cast<uint64_t*>(smem_raw);
+  WarpSmem* smem = reinterpret_cast<WarpSmem*>(smem_raw + 2 * lut_strand * sizeof(uint64_t));
+  for (uint32_t i = threadIdx.x; i < 2 * lut_strand; i += blockDim.x) lut[i] = ix.lut[i];
+  __syncthreads();
+  const bool wide = nchunks > 7;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t gwarp = blockIdx.x * kWarpsPerCta + warp;
   WarpSmem& sm = smem[warp];
   const uint32_t k = ix.k, th = a.th, stride = th + 1, nleaves = ix.nleaves;
   const uint32_t nslots = 2 * nleaves, nbm = (nslots + 31) >> 5;
+  const uint32_t lt_mask = (1u << lane) - 1;
+  constexpr uint32_t NG = 32 / G;
+  const uint32_t gl = lane & (G - 1), gbase = lane & ~(uint32_t)(G - 1), gid = lane / G;
+  const uint32_t gmask = (G == 32) ? 0xFFFFFFFFu : (((1u << G) - 1u) << gbase);
 
   WarpCtx w;
   w.acc = a.acc + (size_t)gwarp * nslots * stride;
@@ -177,18 +195,22 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) match_kernel(const DevIndex
 
   unsigned long long st_bytes = 0, st_lookups = 0, st_entries = 0;
 
+  uint32_t claim = 0, claim_end = 0;
   for (;;) {
-    uint32_t read = 0;
-    if (lane == 0) read = atomicAdd(a.counters + 1, 1u);
-    read = __shfl_sync(0xFFFFFFFFu, read, 0);
-    if (read >= a.n_reads) break;
+    if (claim == claim_end) { // claim the next kClaim reads for this warp
+      if (lane == 0) claim = atomicAdd(a.counters + 1, kClaim);
+      claim = __shfl_sync(0xFFFFFFFFu, claim, 0);
+      claim_end = min(claim + kClaim, a.n_reads);
+      if (claim >= a.n_reads) break;
+    }
+    const uint32_t read = claim++;
     const uint64_t off = a.offsets[read];
     const uint64_t len = a.offsets[read + 1] - off;
     uint32_t onmers = 0, wn0 = 0, wn1 = 0, filt0 = 0xFFFFFFFFu, filt1 = 0xFFFFFFFFu;
     st_bytes += (lane == 0) ? len : 0;
 
     for (uint64_t t0 = 0; t0 + k <= len; t0 += kTileWindows) {
-      // ---- 1. load + encode the tile's bases: [t0, t0 + kTileWindows + k - 1) clipped to the read
+      // ---- A0. load + encode the tile's bases: [t0, t0 + kTileWindows + k - 1) clipped to the read
       const uint64_t rem = len - t0;                                  // bases available from t0
       const uint32_t nb = (uint32_t)min((uint64_t)(kTileWindows + k - 1), rem);
       const char* p0 = a.bases + off + t0;
@@ -214,22 +236,23 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) match_kernel(const DevIndex
       }
       // align the stream to the tile start: word t covers tile bases 16t .. 16t+15
       const uint32_t cn = __shfl_down_sync(0xFFFFFFFFu, cw, 1), vn = __shfl_down_sync(0xFFFFFFFFu, vw, 1);
-      uint32_t cwa = __funnelshift_l(cn, cw, 2 * sh);
+      const uint32_t cwa = __funnelshift_l(cn, cw, 2 * sh);
       uint32_t vwa = (((vw << 16) | vn) << sh) >> 16;
-      // clip validity to the bases that belong to this read
-      {
-        const int first = 16 * (int)lane;
-        const int keep = (int)nb - first;             // number of leading bases of this word inside the read
+      { // clip validity to the bases that belong to this read
+        const int keep = (int)nb - 16 * (int)lane;    // number of leading bases of this word inside the read
         if (keep <= 0) vwa = 0; else if (keep < 16) vwa &= 0xFFFFu << (16 - keep);
       }
       const uint32_t vhi = __shfl_sync(0xFFFFFFFFu, vwa, (2 * lane) & 31), vlo = __shfl_sync(0xFFFFFFFFu, vwa, (2 * lane + 1) & 31);
       __syncwarp();
       if (lane <= kTileWords) sm.code[lane] = cwa;
       if (lane <= kTileWords / 2) sm.valid[lane] = (vhi << 16) | vlo;
+      if (lane == 0) sm.cursor = 0;
       __syncwarp();
 
-      // ---- 2 + 3. windows -> lookups -> bucket scans
+      // ---- A1. windows -> k-mer words -> bucket ids; eligible lookups compacted into the list
       const uint32_t nwin = (uint32_t)min((uint64_t)kTileWindows, rem - k + 1);
+      uint32_t nl = 0;
+#pragma unroll
       for (uint32_t j = 0; j < kTileWindows / 32; ++j) {
         const uint32_t p = lane + 32 * j;
         bool valid = false;
@@ -244,58 +267,170 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) match_kernel(const DevIndex
           bp = x >> (64 - 2 * k);
         }
         onmers += valid;
-        // per strand: hash, eligibility, bucket scan
-        uint32_t n_hit[2] = {0, 0}, hit_se[2] = {0, 0}, hit_hd[2] = {0, 0}, lk_len[2] = {0, 0}, lk_q[2] = {0, 0};
-        uint64_t lk_begin[2] = {0, 0};
 #pragma unroll
         for (uint32_t strand = 0; strand < 2; ++strand) {
-          if (!valid) continue;
-          const uint64_t e = strand ? revcomp(bp, k) : bp;
-          const uint32_t rix = pext_runs(e, ix.hash_runs, ix.n_hash_runs);
+          const uint64_t rq = lut_pext(lut + strand * lut_strand, (uint32_t)bp, (uint32_t)(bp >> 32), wide);
+          const uint32_t rix = (uint32_t)rq, q = (uint32_t)(rq >> 32);
           uint32_t quo, res;
           if (ix.m_shift != 0xFFFFFFFFu) { quo = rix >> ix.m_shift; res = rix & (ix.m - 1); }
           else { quo = rix / ix.m; res = rix - quo * ix.m; }
           const int32_t numer = ix.res_numer[res];
-          if (numer == 0) continue;
+          const bool elig = valid && numer != 0;
           const uint32_t offset = numer > 1 ? quo * (uint32_t)numer + res : quo;
-          const uint32_t qbp = pext_runs(e, ix.drop_runs, ix.n_drop_runs);
-          const uint32_t q = even_bits16(qbp) | (even_bits16(qbp >> 1) << 16);
-          if (strand) ++wn1; else ++wn0;
-          const uint64_t begin = offset ? ix.inc[offset - 1] : 0ull;
-          const uint64_t end = ix.inc[offset];
-          const uint32_t blen = (uint32_t)(end - begin);
-          if (TAP) {
-            const unsigned long long at = atomicAdd(a.tap_count, 1ull);
-            const uint32_t pos = strand ? (uint32_t)(len - (t0 + p) - k) : (uint32_t)(t0 + p);
-            if (at < a.tap_cap) a.tap[at] = make_uint4(read, strand << 31 | pos, rix, q);
+          const uint32_t em = __ballot_sync(0xFFFFFFFFu, elig);
+          if (elig) {
+            const uint32_t idx = nl + __popc(em & lt_mask);
+            sm.lk_a[idx] = offset | (strand << 31);
+            sm.lk_q[idx] = q;
+            if (strand) ++wn1; else ++wn0;
+            if (TAP) {
+              const unsigned long long at = atomicAdd(a.tap_count, 1ull);
+              const uint32_t pos = strand ? (uint32_t)(len - (t0 + p) - k) : (uint32_t)(t0 + p);
+              if (at < a.tap_cap) a.tap[at] = make_uint4(read, strand << 31 | pos, rix, q);
+            }
           }
-          st_lookups += 1; st_entries += blen; st_bytes += 16 + 8ull * blen;
-          uint32_t cnt = 0, fse = 0, fhd = 0, mn = 0xFFFFFFFFu;
-          for (uint32_t i = 0; i < blen; ++i) {
-            const uint2 ent = __ldg(&ix.cmer[begin + i]);
-            const uint32_t z = ent.x ^ q;
-            const uint32_t hd = __popc((z | (z >> 16)) & 0xFFFFu);
-            if (hd <= th) { if (!cnt) { fse = ent.y; fhd = hd; } ++cnt; mn = min(mn, hd); }
-          }
-          if (strand) filt1 = min(filt1, mn); else filt0 = min(filt0, mn);
-          n_hit[strand] = cnt; hit_se[strand] = fse; hit_hd[strand] = fhd; lk_len[strand] = blen; lk_q[strand] = q; lk_begin[strand] = begin;
+          nl += __popc(em);
         }
-        // commit hits
+      }
+      __syncwarp();
+
+      // ---- A2. bucket ranges [inc[off-1], inc[off]) with all loads of the tile in flight; empty buckets are dropped
+      //          (in-place compaction: writes trail reads)
+      uint32_t nout = 0;
+      for (uint32_t base = 0; base < nl; base += 128) {
+        uint32_t qv[4], bg[4], en[4], sb[4];
 #pragma unroll
-        for (uint32_t strand = 0; strand < 2; ++strand) {
-          bool careful = n_hit[strand] > 1;
-          if (n_hit[strand] == 1) {
-            const uint32_t kd = ix.kind[hit_se[strand]];
-            if (kd == 1) commit(w, strand, ix.leaf_rank[hit_se[strand]], hit_hd[strand]);
-            else if (kd == 2) { if (ix.local_expand) expand_local(ix, w, hit_se[strand], strand, hit_hd[strand]); else careful = true; }
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t i = base + 32 * u + lane;
+          qv[u] = 0; bg[u] = 0; en[u] = 0; sb[u] = 0;
+          if (i < nl) {
+            const uint32_t ob = sm.lk_a[i], offset = ob & 0x7FFFFFFFu;
+            qv[u] = sm.lk_q[i];
+            bg[u] = offset ? __ldg(&ix.inc32[offset - 1]) : 0u;
+            en[u] = __ldg(&ix.inc32[offset]);
+            sb[u] = ob & 0x80000000u;
           }
-          uint32_t need = __ballot_sync(0xFFFFFFFFu, careful);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t i = base + 32 * u + lane;
+          const uint32_t blen = en[u] - bg[u];
+          if (i < nl) { st_lookups += 1; st_entries += blen; }
+          const bool keep = i < nl && blen != 0;
+          const uint32_t km = __ballot_sync(0xFFFFFFFFu, keep);
+          if (keep) {
+            const uint32_t o = nout + __popc(km & lt_mask);
+            sm.lk_a[o] = bg[u]; sm.lk_l[o] = blen | sb[u]; sm.lk_q[o] = qv[u];
+          }
+          nout += __popc(km);
+        }
+        __syncwarp();
+      }
+
+      // ---- B. bucket scans.
+      if (G == 1) {
+        // Small buckets: every lane pulls whole lookups from the list and scans its bucket two entries (one 128-bit
+        // load) per step.  No warp-collective sits in this loop; lanes leave it independently.
+        constexpr uint32_t kCareful = 0x40000000u;
+        uint32_t idx = 0, cq = 0, cs = 0, e = 0, lo = 0, hi = 0, cnt = 0, fse = 0, fhd = 0;
+        bool have = false;
+        for (;;) {
+          if (!have) {
+            idx = atomicAdd(&sm.cursor, 1u);
+            if (idx >= nout) break;
+            const uint32_t l = sm.lk_l[idx];
+            lo = sm.lk_a[idx]; hi = lo + (l & 0x3FFFFFFFu); cs = l >> 31; cq = sm.lk_q[idx];
+            e = lo & ~1u; cnt = 0; have = true;
+          }
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(ix.cmer + e));
+          const uint32_t z0 = v.x ^ cq, z1 = v.z ^ cq;
+          const uint32_t h0 = __popc((z0 | (z0 >> 16)) & 0xFFFFu), h1 = __popc((z1 | (z1 >> 16)) & 0xFFFFu);
+          if (h0 <= th && e >= lo) {
+            if (!cnt) { fse = v.y; fhd = h0; }
+            ++cnt;
+            if (cs) filt1 = min(filt1, h0); else filt0 = min(filt0, h0);
+          }
+          if (h1 <= th && e + 1 < hi) {
+            if (!cnt) { fse = v.w; fhd = h1; }
+            ++cnt;
+            if (cs) filt1 = min(filt1, h1); else filt0 = min(filt0, h1);
+          }
+          e += 2;
+          if (e >= hi) {
+            have = false;
+            if (cnt == 1) { // exactly one hit entry: no other entry can lower a leaf's distance
+              const uint32_t kd = ix.kind[fse];
+              if (kd == 1) commit(w, cs, ix.leaf_rank[fse], fhd);
+              else if (kd == 2) { if (ix.local_expand) expand_local(ix, w, fse, cs, fhd); else cnt = 2; }
+            }
+            if (cnt > 1) sm.lk_l[idx] |= kCareful; // several hit entries: handled by the whole warp below
+          }
+        }
+        __syncwarp();
+        for (uint32_t base = 0; base < nout; base += 32) {
+          const uint32_t l = (base + lane < nout) ? sm.lk_l[base + lane] : 0u;
+          uint32_t need = __ballot_sync(0xFFFFFFFFu, (l & kCareful) != 0);
           while (need) {
             const int src = __ffs(need) - 1;
             need &= need - 1;
-            const uint64_t b = __shfl_sync(0xFFFFFFFFu, lk_begin[strand], src);
-            const uint32_t l = __shfl_sync(0xFFFFFFFFu, lk_len[strand], src), qq = __shfl_sync(0xFFFFFFFFu, lk_q[strand], src);
-            careful_lookup(ix, w, b, l, qq, strand, th);
+            const uint32_t ll = sm.lk_l[base + src];
+            careful_lookup(ix, w, sm.lk_a[base + src], ll & 0x3FFFFFFFu, sm.lk_q[base + src], ll >> 31, th);
+          }
+        }
+      } else {
+        // Larger buckets: groups of G lanes walk the list (group g takes lookups g, g+NG, ...) and scan G consecutive
+        // entries per step, so that a group reads one contiguous run of 8*G bytes.
+        uint32_t idx = gid, cb = 0, cl = 0, cq = 0, cs = 0, pos = 0, cnt = 0, fse = 0, fhd = 0;
+        bool have = false;
+        for (;;) {
+          if (!have && idx < nout) {
+            cb = sm.lk_a[idx]; cq = sm.lk_q[idx];
+            const uint32_t l = sm.lk_l[idx];
+            cl = l & 0x7FFFFFFFu; cs = l >> 31;
+            idx += NG; have = true; pos = 0; cnt = 0;
+          }
+          if (!__any_sync(0xFFFFFFFFu, have)) break;
+          bool careful = false;
+          if (have) {
+            const uint32_t e = pos + gl;
+            if (e < cl) {
+              const uint2 ent = __ldg(&ix.cmer[(size_t)cb + e]);
+              const uint32_t z = ent.x ^ cq;
+              const uint32_t hd = __popc((z | (z >> 16)) & 0xFFFFu);
+              if (hd <= th) {
+                if (!cnt) { fse = ent.y; fhd = hd; }
+                ++cnt;
+                if (cs) filt1 = min(filt1, hd); else filt0 = min(filt0, hd);
+              }
+            }
+            pos += G;
+            if (pos >= cl) { // this lookup is finished (uniform inside the group)
+              have = false;
+              if (__any_sync(gmask, cnt != 0)) {
+                uint32_t total = cnt;
+#pragma unroll
+                for (int o = G / 2; o; o >>= 1) total += __shfl_xor_sync(gmask, total, o);
+                uint32_t flag = total > 1;
+                if (total == 1 && cnt == 1) { // exactly one hit entry: no other entry can lower a leaf's distance
+                  const uint32_t kd = ix.kind[fse];
+                  if (kd == 1) commit(w, cs, ix.leaf_rank[fse], fhd);
+                  else if (kd == 2) { if (ix.local_expand) expand_local(ix, w, fse, cs, fhd); else flag = 1; }
+                }
+#pragma unroll
+                for (int o = G / 2; o; o >>= 1) flag |= __shfl_xor_sync(gmask, flag, o);
+                careful = flag != 0;
+              }
+            }
+          }
+          // several hit entries in one bucket: the warp handles those lookups together, one after the other
+          uint32_t need = __ballot_sync(0xFFFFFFFFu, careful && gl == 0);
+          while (need) {
+            const int src = __ffs(need) - 1;
+            need &= need - 1;
+            const uint32_t b = __shfl_sync(0xFFFFFFFFu, cb, src), l = __shfl_sync(0xFFFFFFFFu, cl, src);
+            const uint32_t qq = __shfl_sync(0xFFFFFFFFu, cq, src), ss = __shfl_sync(0xFFFFFFFFu, cs, src);
+            careful_lookup(ix, w, b, l, qq, ss, th);
           }
         }
       }
@@ -360,26 +495,48 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) match_kernel(const DevIndex
     st_lookups += __shfl_xor_sync(0xFFFFFFFFu, st_lookups, o);
     st_entries += __shfl_xor_sync(0xFFFFFFFFu, st_entries, o);
   }
-  if (lane == 0) { atomicAdd(a.stats, st_bytes); atomicAdd(a.stats + 1, st_lookups); atomicAdd(a.stats + 2, st_entries); }
+  if (lane == 0) { atomicAdd(a.stats, st_bytes + 16ull * st_lookups + 8ull * st_entries); atomicAdd(a.stats + 1, st_lookups); atomicAdd(a.stats + 2, st_entries); }
 }
 
 // ------------------------------------------------------------------------------------------------ host launchers
 
-int match_resident_warps(int device)
+template <int G, bool TAP>
+static cudaError_t prepare()
+{
+  return cudaFuncSetAttribute(match_kernel<G, TAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(32));
+}
+
+int match_resident_warps(int device, uint32_t k)
 {
   int sms = 0, per_sm = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, match_kernel<false>, kWarpsPerCta * 32, 0);
+  prepare<4, false>();
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, match_kernel<4, false>, kWarpsPerCta * 32, smem_bytes(k));
   if (per_sm < 1) per_sm = 1;
   return sms * per_sm * kWarpsPerCta;
 }
 
-cudaError_t launch_match(const DevIndex& ix, const MatchArgs& a, int resident_warps, bool tap, cudaStream_t stream)
+template <int G>
+static cudaError_t launch_g(const DevIndex& ix, const MatchArgs& a, int grid, bool tap, cudaStream_t stream)
+{
+  cudaError_t e = tap ? prepare<G, true>() : prepare<G, false>();
+  if (e != cudaSuccess) return e;
+  if (tap) match_kernel<G, true><<<grid, kWarpsPerCta * 32, smem_bytes(ix.k), stream>>>(ix, a);
+  else match_kernel<G, false><<<grid, kWarpsPerCta * 32, smem_bytes(ix.k), stream>>>(ix, a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_match(const DevIndex& ix, const MatchArgs& a, int resident_warps, int group, bool tap, cudaStream_t stream)
 {
   const int grid = resident_warps / kWarpsPerCta;
-  if (tap) match_kernel<true><<<grid, kWarpsPerCta * 32, 0, stream>>>(ix, a);
-  else match_kernel<false><<<grid, kWarpsPerCta * 32, 0, stream>>>(ix, a);
-  return cudaGetLastError();
+  switch (group) {
+    case 1: return launch_g<1>(ix, a, grid, tap, stream);
+    case 2: return launch_g<2>(ix, a, grid, tap, stream);
+    case 4: return launch_g<4>(ix, a, grid, tap, stream);
+    case 8: return launch_g<8>(ix, a, grid, tap, stream);
+    case 16: return launch_g<16>(ix, a, grid, tap, stream);
+    default: return launch_g<32>(ix, a, grid, tap, stream);
+  }
 }
 
 } // namespace krepp
