@@ -272,3 +272,28 @@ class IBatch:
                 r = recs[s["closest"]]
                 out.append(f"{name}\t{self.index.node_name(int(r['leaf_se']))}\t{r['d_llh']:.5f}\n")
         return "".join(out)
+
+    def place_sequences(self, tabular: bool = False) -> str:
+        """Placement rows of this batch the way IBatch::place_sequences / report_placement frame them
+        (src/query.cpp:198-333): jplace "placements" entries (PP_JPLACE_FIELDS, src/query.hpp:202-204) joined by ",\n",
+        or the tab-separated rows of --tabular (PP_TABULAR_FIELDS, :206).  Reads in input order, edges by ascending se."""
+        res = self.results()
+        out = []
+        pl, reads = res["placements"], res["reads"]
+        for i in range(self.n_reads):
+            s = reads[i]
+            if s["place_count"] == 0:
+                continue
+            name = self.names[i] if self.names is not None else f"r{i}"
+            rows = pl[s["place_begin"]:s["place_begin"] + s["place_count"]]
+            if tabular:
+                for r in rows:
+                    out.append(f"{name}\t{self.index.node_name(int(r['se']), True)}\t{int(r['se']) - 1}\t{r['lwr']:.5f}\t{r['d_llh']:.5f}\n")
+                continue
+            f = [f"[{int(r['se']) - 1}, {r['pendant']:.5f}, {r['distal']:.5f}, {r['loglik']:.5f}, {r['lwr']:.5f}, {r['d_llh']:.5f}]" for r in rows]
+            head = f'\t\t\t{{"n" : ["{name}"], "p" : ['
+            if len(res["records"][s["rec_begin"]:s["rec_begin"] + s["rec_count"]][(res["records"][s["rec_begin"]:s["rec_begin"] + s["rec_count"]]["flags"] & REC_SELECTED) != 0]) == 1:
+                out.append(head + f[0] + "]}")  # single-candidate shortcut (src/query.cpp:231-241)
+            else:
+                out.append(head + ",".join("\n\t\t\t\t" + x for x in f) + "]\n\t\t\t}")
+        return "".join(out) if tabular else ",\n".join(out)

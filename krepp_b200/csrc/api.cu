@@ -61,34 +61,35 @@ cudaError_t upload(const std::vector<T>& v, const T** out, std::vector<void*>& a
 // bit0 / bit1 of its code to bits r and 16+r of q, r its rank among npos (ref src/lshf.cpp:39-46,64-69).  Reverse
 // strand: the same forward base, complemented, is the base at position k-1-p of the reverse complement
 // (ref src/common.hpp:177-186).
-static std::vector<uint64_t> build_lut(const HostIndex& h)
+static std::vector<uint4> build_lut(const HostIndex& h)
 {
   std::vector<int> hrank(32, -1), nrank(32, -1);
   { std::vector<uint8_t> pp = h.ppos, np = h.npos; std::sort(pp.begin(), pp.end()); std::sort(np.begin(), np.end());
     for (size_t i = 0; i < pp.size(); ++i) hrank[pp[i]] = (int)i;
     for (size_t i = 0; i < np.size(); ++i) nrank[np[i]] = (int)i; }
   const uint32_t nch = (2 * h.k + 7) / 8; // bytes of the k-mer word that can be non-zero
-  std::vector<uint64_t> lut(2 * nch * 256, 0);
+  std::vector<uint4> lut(nch * 256, make_uint4(0, 0, 0, 0));
   for (uint32_t strand = 0; strand < 2; ++strand)
     for (uint32_t c = 0; c < nch; ++c)
       for (uint32_t v = 0; v < 256; ++v) {
-        uint64_t rix = 0, q = 0;
+        uint32_t rix = 0, q = 0;
         for (uint32_t s = 0; s < 4; ++s) {
           const uint32_t p = 4 * c + s;
           if (p >= h.k) continue;
           uint32_t code = (v >> (2 * s)) & 3, pos = p;
           if (strand) { code = 3 - code; pos = h.k - 1 - p; }
-          if (hrank[pos] >= 0) rix |= (uint64_t)code << (2 * hrank[pos]);
-          if (nrank[pos] >= 0) q |= (uint64_t)(code & 1) << nrank[pos] | (uint64_t)(code >> 1) << (16 + nrank[pos]);
+          if (hrank[pos] >= 0) rix |= code << (2 * hrank[pos]);
+          if (nrank[pos] >= 0) q |= (code & 1) << nrank[pos] | (code >> 1) << (16 + nrank[pos]);
         }
-        lut[(strand * nch + c) * 256 + v] = rix | (q << 32);
+        uint4& t = lut[c * 256 + v];
+        if (strand) { t.z = rix; t.w = q; } else { t.x = rix; t.y = q; }
       }
   return lut;
 }
 
 // AoS assembly of the public result structs on the device (one D2H copy each, no host-side gather).
 __global__ void __launch_bounds__(128) finalize_kernel(const SolveArgs a, krepp_record_t* out_rec, krepp_read_summary_t* out_read,
-                                                        const uint32_t* wn)
+                                                        const uint32_t* wn, const uint32_t* place_begin, const uint32_t* place_count)
 {
   const uint32_t n = a.counters[0] < a.n_records ? a.counters[0] : a.n_records;
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
@@ -104,7 +105,8 @@ __global__ void __launch_bounds__(128) finalize_kernel(const SolveArgs a, krepp_
     krepp_read_summary_t s;
     s.onmers = a.onmers[i]; s.wn[0] = wn[2 * i]; s.wn[1] = wn[2 * i + 1];
     s.hdist_filt[0] = a.hdfilt[2 * i]; s.hdist_filt[1] = a.hdfilt[2 * i + 1];
-    s.rec_begin = a.rec_begin[i]; s.rec_count = a.rec_count[i]; s.place_begin = 0; s.place_count = 0;
+    s.rec_begin = a.rec_begin[i]; s.rec_count = a.rec_count[i];
+    s.place_begin = place_begin ? place_begin[i] : 0; s.place_count = place_count ? place_count[i] : 0;
     s.closest = a.closest[i];
     out_read[i] = s;
   }
@@ -146,6 +148,11 @@ struct krepp_batch {
   // pinned host results
   krepp_record_t* h_rec = nullptr; krepp_read_summary_t* h_read = nullptr; uint32_t* h_hist = nullptr;
   uint32_t* h_counters = nullptr; unsigned long long* h_stats = nullptr;
+  // placement (K5)
+  uint32_t place_cap = 0, place_warps = 0;
+  uint32_t *d_place_begin = nullptr, *d_place_count = nullptr, *d_node_bitmap = nullptr, *d_node_list = nullptr, *d_node_cand = nullptr;
+  double *d_node_d = nullptr, *d_node_v = nullptr, *d_node_chisq = nullptr;
+  krepp_placement_t *d_place = nullptr, *h_place = nullptr;
   // tap
   uint4* d_tap = nullptr; unsigned long long* d_tap_count = nullptr; unsigned long long tap_cap = 0;
 };
@@ -195,6 +202,7 @@ int krepp_index_open(const char* index_dir, int device, krepp_index_t** out)
   if (e == cudaSuccess) e = upload(h.tree.nchildren, &d.nchildren, ix->allocs, ix->device_bytes);
   if (e == cudaSuccess) e = upload(h.tree.blen, &d.blen, ix->allocs, ix->device_bytes);
   if (e == cudaSuccess) e = upload(build_lut(h), &d.lut, ix->allocs, ix->device_bytes);
+  if (e == cudaSuccess) e = upload(h.tree.subtree, &d.subtree, ix->allocs, ix->device_bytes);
   if (e != cudaSuccess) {
     for (void* p : ix->allocs) cudaFree(p);
     delete ix;
@@ -276,6 +284,17 @@ static void free_records(krepp_batch* b)
   b->d_rec_d = b->d_rec_v = b->d_rec_chisq = nullptr; b->d_out_rec = nullptr; b->h_rec = nullptr; b->h_hist = nullptr;
 }
 
+static int alloc_placements(krepp_batch* b, uint32_t cap)
+{
+  if (b->d_place) cudaFree(b->d_place);
+  if (b->h_place) cudaFreeHost(b->h_place);
+  b->d_place = nullptr; b->h_place = nullptr;
+  b->place_cap = cap;
+  CU(cudaMalloc(&b->d_place, sizeof(krepp_placement_t) * (size_t)cap));
+  CU(cudaMallocHost(&b->h_place, sizeof(krepp_placement_t) * (size_t)cap));
+  return KREPP_OK;
+}
+
 static int alloc_records(krepp_batch* b, uint32_t cap)
 {
   free_records(b);
@@ -296,7 +315,6 @@ int krepp_batch_create(krepp_index_t* ix, const krepp_params_t* p, uint32_t max_
   *out = nullptr;
   if (p->hdist_th > (uint32_t)kMaxTh) return fail(KREPP_ERR_ARG, "--hdist-th %u exceeds %d", p->hdist_th, kMaxTh);
   if (p->place && p->hdist_th < p->tau) return fail(KREPP_ERR_ARG, "The threshold tau must be less than HD threshold --hdist-th!");
-  if (p->place) return fail(KREPP_ERR_UNSUPPORTED, "placement is not wired into the batch pipeline yet");
   if (ix->device == KREPP_DEVICE_NONE) return fail(KREPP_ERR_CUDA, "this index handle was opened without a device (KREPP_DEVICE_NONE); queries need a GPU");
   if (cudaSetDevice(ix->device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice(%d) failed", ix->device);
   auto* b = new krepp_batch;
@@ -332,6 +350,16 @@ int krepp_batch_create(krepp_index_t* ix, const krepp_params_t* p, uint32_t max_
   CU(cudaMalloc(&b->d_stack, 4 * warps * b->stack_cap));
   const uint64_t want = std::max<uint64_t>(4ull * max_reads, 4096);
   if (int rc = alloc_records(b, (uint32_t)std::min<uint64_t>(want, 0x7FFFFFFFull))) return rc;
+  if (p->place) {
+    const size_t nn = h.tree.nnodes, nbm_nodes = (nn + 32) / 32;
+    b->place_warps = (uint32_t)ix->sms * 4u * (uint32_t)kPlaceWarpsPerCta;
+    const size_t pw = b->place_warps;
+    CU(cudaMalloc(&b->d_place_begin, 4ull * max_reads)); CU(cudaMalloc(&b->d_place_count, 4ull * max_reads));
+    CU(cudaMalloc(&b->d_node_bitmap, 4 * pw * nbm_nodes)); CU(cudaMemset(b->d_node_bitmap, 0, 4 * pw * nbm_nodes));
+    CU(cudaMalloc(&b->d_node_list, 4 * pw * nn)); CU(cudaMalloc(&b->d_node_cand, 4 * pw * nn));
+    CU(cudaMalloc(&b->d_node_d, 8 * pw * nn)); CU(cudaMalloc(&b->d_node_v, 8 * pw * nn)); CU(cudaMalloc(&b->d_node_chisq, 8 * pw * nn));
+    if (int rc = alloc_placements(b, (uint32_t)std::min<uint64_t>(std::max<uint64_t>(8ull * max_reads, 4096), 0x7FFFFFFFull))) return rc;
+  }
   return KREPP_OK;
 }
 
@@ -343,9 +371,11 @@ void krepp_batch_destroy(krepp_batch_t* b)
   free_records(b);
   for (void* p : {(void*)b->d_bases, (void*)b->d_offsets, (void*)b->d_onmers, (void*)b->d_wn, (void*)b->d_hdfilt, (void*)b->d_rec_begin,
                   (void*)b->d_rec_count, (void*)b->d_closest, (void*)b->d_counters, (void*)b->d_stats, (void*)b->d_acc, (void*)b->d_bitmap,
-                  (void*)b->d_marker, (void*)b->d_stack, (void*)b->d_out_read, (void*)b->d_tap, (void*)b->d_tap_count})
+                  (void*)b->d_marker, (void*)b->d_stack, (void*)b->d_out_read, (void*)b->d_tap, (void*)b->d_tap_count, (void*)b->d_place_begin,
+                  (void*)b->d_place_count, (void*)b->d_node_bitmap, (void*)b->d_node_list, (void*)b->d_node_cand, (void*)b->d_node_d, (void*)b->d_node_v,
+                  (void*)b->d_node_chisq, (void*)b->d_place})
     if (p) cudaFree(p);
-  for (void* p : {(void*)b->h_bases, (void*)b->h_offsets, (void*)b->h_read, (void*)b->h_counters, (void*)b->h_stats})
+  for (void* p : {(void*)b->h_bases, (void*)b->h_offsets, (void*)b->h_read, (void*)b->h_counters, (void*)b->h_stats, (void*)b->h_place})
     if (p) cudaFreeHost(p);
   if (b->ev0) cudaEventDestroy(b->ev0);
   if (b->ev1) cudaEventDestroy(b->ev1);
@@ -381,9 +411,20 @@ static int enqueue(krepp_batch* b)
   sa.rec_hdmin = b->d_rec_hdmin; sa.closest = b->d_closest;
   sa.want_chisq = (!b->p.no_filter || b->p.summarize || b->p.place) ? 1 : 0;
   CU(launch_solve(sa, b->tab, ix->sms, s));
-  finalize_kernel<<<ix->sms * 4, 128, 0, s>>>(sa, b->d_out_rec, b->d_out_read, b->d_wn);
-  CU(cudaGetLastError());
   b->launches = 4 + (sa.want_chisq ? 1 : 0);
+  if (b->p.place) {
+    PlaceArgs pa{};
+    pa.s = sa; pa.offsets = b->in_offsets; pa.tau = b->p.tau; pa.no_filter = b->p.no_filter; pa.chisq_value = b->p.chisq;
+    pa.parent = ix->dev.parent; pa.nchildren = ix->dev.nchildren; pa.subtree = ix->dev.subtree; pa.blen = ix->dev.blen; pa.leaf_rank = ix->dev.leaf_rank;
+    pa.nnodes = h.tree.nnodes;
+    pa.node_bitmap = b->d_node_bitmap; pa.node_list = b->d_node_list; pa.node_d = b->d_node_d; pa.node_v = b->d_node_v; pa.node_chisq = b->d_node_chisq;
+    pa.node_cand = b->d_node_cand; pa.placements = b->d_place; pa.place_cap = b->place_cap; pa.counters = b->d_counters;
+    pa.place_begin = b->d_place_begin; pa.place_count = b->d_place_count;
+    CU(launch_place(pa, b->tab, (int)(b->place_warps / kPlaceWarpsPerCta), s));
+    b->launches += 1;
+  }
+  finalize_kernel<<<ix->sms * 4, 128, 0, s>>>(sa, b->d_out_rec, b->d_out_read, b->d_wn, b->d_place_begin, b->d_place_count);
+  CU(cudaGetLastError());
   CU(cudaMemcpyAsync(b->h_counters, b->d_counters, 16, cudaMemcpyDeviceToHost, s));
   CU(cudaMemcpyAsync(b->h_stats, b->d_stats, 32, cudaMemcpyDeviceToHost, s));
   CU(cudaMemcpyAsync(b->h_read, b->d_out_read, sizeof(krepp_read_summary_t) * (size_t)b->n_reads, cudaMemcpyDeviceToHost, s));
@@ -444,12 +485,19 @@ int krepp_batch_wait(krepp_batch_t* b, krepp_results_t* out)
   for (int attempt = 0;; ++attempt) {
     CU(cudaStreamSynchronize(b->stream));
     if (b->h_counters[2] & kErrStackOverflow) return fail(KREPP_ERR_CAPACITY, "colour expansion stack overflow on the device");
-    if (!(b->h_counters[2] & kErrRecOverflow)) break;
-    // the record buffer was too small: grow it to what the kernel asked for and run the batch again
-    if (attempt >= 4) return fail(KREPP_ERR_CAPACITY, "record buffer overflow persists");
-    const uint64_t want = std::max<uint64_t>(2ull * b->h_counters[0], 2ull * b->rec_cap);
-    if (want > 0x7FFFFFFFull) return fail(KREPP_ERR_CAPACITY, "batch produces too many records; submit fewer reads per batch");
-    if (int rc = alloc_records(b, (uint32_t)want)) return rc;
+    if (!(b->h_counters[2] & (kErrRecOverflow | kErrPlaceOverflow))) break;
+    // a result buffer was too small: grow it to what the kernels asked for and run the batch again
+    if (attempt >= 4) return fail(KREPP_ERR_CAPACITY, "result buffer overflow persists");
+    if (b->h_counters[2] & kErrRecOverflow) {
+      const uint64_t want = std::max<uint64_t>(2ull * b->h_counters[0], 2ull * b->rec_cap);
+      if (want > 0x7FFFFFFFull) return fail(KREPP_ERR_CAPACITY, "batch produces too many records; submit fewer reads per batch");
+      if (int rc = alloc_records(b, (uint32_t)want)) return rc;
+    }
+    if (b->h_counters[2] & kErrPlaceOverflow) {
+      const uint64_t want = std::max<uint64_t>(2ull * b->h_counters[3], 2ull * b->place_cap);
+      if (want > 0x7FFFFFFFull) return fail(KREPP_ERR_CAPACITY, "batch produces too many placements; submit fewer reads per batch");
+      if (int rc = alloc_placements(b, (uint32_t)want)) return rc;
+    }
     if (int rc = enqueue(b)) return rc;
   }
   const uint32_t nrec = b->h_counters[0];
@@ -458,12 +506,14 @@ int krepp_batch_wait(krepp_batch_t* b, krepp_results_t* out)
     CU(cudaMemcpyAsync(b->h_rec, b->d_out_rec, sizeof(krepp_record_t) * (size_t)nrec, cudaMemcpyDeviceToHost, b->stream));
     CU(cudaMemcpyAsync(b->h_hist, b->d_rec_hist, 4ull * nrec * stride, cudaMemcpyDeviceToHost, b->stream));
   }
+  const uint32_t nplace = b->p.place ? b->h_counters[3] : 0;
+  if (nplace) CU(cudaMemcpyAsync(b->h_place, b->d_place, sizeof(krepp_placement_t) * (size_t)nplace, cudaMemcpyDeviceToHost, b->stream));
   CU(cudaEventRecord(b->ev1, b->stream));
   CU(cudaStreamSynchronize(b->stream));
   float ms = 0;
   CU(cudaEventElapsedTime(&ms, b->ev0, b->ev1));
-  out->n_reads = b->n_reads; out->hist_stride = (uint32_t)stride; out->n_records = nrec; out->n_placements = 0;
-  out->reads = b->h_read; out->records = b->h_rec; out->hist = b->h_hist; out->placements = nullptr;
+  out->n_reads = b->n_reads; out->hist_stride = (uint32_t)stride; out->n_records = nrec; out->n_placements = nplace;
+  out->reads = b->h_read; out->records = b->h_rec; out->hist = b->h_hist; out->placements = nplace ? b->h_place : nullptr;
   float mms = 0;
   CU(cudaEventElapsedTime(&mms, b->evm0, b->evm1));
   out->gpu_ms = ms; out->match_ms = mms; out->gpu_launches = b->launches;

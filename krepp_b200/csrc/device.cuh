@@ -24,11 +24,12 @@ struct DevIndex {
   const uint32_t* parent;   // by se (0 for root)                  ref Node::parent
   const uint32_t* nchildren;// by se
   const double* blen;       // by se
+  const uint32_t* subtree;  // by se: number of nodes in the subtree rooted there (post-order => se range (se-subtree, se])
   uint64_t nkmers;
   uint32_t nrows, nsubsets, nnodes, nleaves;
   uint32_t k, h, m, m_shift; // m_shift = log2(m) when m is a power of two, else 0xffffffff
   uint32_t local_expand;    // 1 when the deepest colour DAG fits the lane-private expansion stack
-  const uint64_t* lut;      // [2 strands][8 bytes][256]: rix part | q part << 32 (see match.cu lut_pext)
+  const uint4* lut;         // [bytes of the k-mer word][256]: {rix fwd, q fwd, rix rc, q rc} parts (match.cu lut_pext)
   int32_t res_numer[kMaxResidues];
 };
 
@@ -63,7 +64,7 @@ struct MatchArgs {
   unsigned long long tap_cap;
 };
 
-constexpr uint32_t kErrRecOverflow = 1u, kErrStackOverflow = 2u;
+constexpr uint32_t kErrRecOverflow = 1u, kErrStackOverflow = 2u, kErrPlaceOverflow = 4u;
 
 struct SolveArgs {
   uint32_t n_reads, th, k, h;
@@ -77,6 +78,25 @@ struct SolveArgs {
   double* rec_d; double* rec_v; double* rec_chisq; uint32_t* rec_flags; uint32_t* rec_match; uint32_t* rec_hdmin;
   int32_t* closest;                  // [n_reads] record index or -1
   int want_chisq;
+};
+
+// K5 (placement) arguments: everything K4 produced plus the flattened phytree.
+struct PlaceArgs {
+  SolveArgs s;
+  const uint64_t* offsets;     // read offsets (enmers = len - k + 1, ref src/query.cpp:345-349)
+  uint32_t tau; int no_filter; double chisq_value;
+  // flattened tree (by se)
+  const uint32_t* parent; const uint32_t* nchildren; const uint32_t* subtree; const double* blen; const uint32_t* leaf_rank;
+  uint32_t nnodes;
+  // per-warp scratch
+  uint32_t* node_bitmap;       // [warps][ceil((nnodes+1)/32)]
+  uint32_t* node_list;         // [warps][nnodes]
+  double* node_d; double* node_v; double* node_chisq; uint32_t* node_cand;  // [warps][nnodes]
+  // outputs
+  void* placements;            // krepp_placement_t[place_cap]
+  uint32_t place_cap;
+  uint32_t* counters;          // [3] placements reserved, [2] error flags
+  uint32_t* place_begin; uint32_t* place_count;  // [n_reads]
 };
 
 } // namespace krepp

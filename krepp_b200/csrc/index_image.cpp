@@ -158,6 +158,8 @@ std::string HostTree::parse(const std::string& newick)
   for (uint32_t se = 1; se <= nnodes; ++se)
     if (is_leaf[se]) { leaf_rank[se] = (uint32_t)leaf_se.size(); leaf_se.push_back(se); }
   nleaves = (uint32_t)leaf_se.size();
+  subtree.assign(N, 1); subtree[0] = 0;
+  for (uint32_t se = 1; se <= nnodes; ++se) if (parent[se]) subtree[parent[se]] += subtree[se]; // children precede parents
   return "";
 }
 

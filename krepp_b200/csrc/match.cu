@@ -41,9 +41,9 @@ struct WarpSmem {
   uint32_t valid[kTileWords / 2 + 1];
   uint32_t cursor;
 };
-// LUT layout: [strand][byte of the k-mer word][byte value] -> rix part | q part << 32; 7 bytes cover k <= 28
+// LUT layout: [byte of the k-mer word][byte value] -> {rix fwd, q fwd, rix rc, q rc} parts; 7 bytes cover k <= 28
 __host__ __device__ inline uint32_t lut_chunks(uint32_t k) { return (2 * k + 7) / 8; }
-__host__ __device__ inline size_t smem_bytes(uint32_t k) { return 2 * lut_chunks(k) * 256 * sizeof(uint64_t) + kWarpsPerCta * sizeof(WarpSmem); }
+__host__ __device__ inline size_t smem_bytes(uint32_t k) { return lut_chunks(k) * 256 * sizeof(uint4) + kWarpsPerCta * sizeof(WarpSmem); }
 
 __device__ __forceinline__ void encode4(uint32_t u, uint32_t& code8, uint32_t& valid4)
 {
@@ -56,22 +56,25 @@ __device__ __forceinline__ void encode4(uint32_t u, uint32_t& code8, uint32_t& v
   valid4 = ((vm & 0x01010101u) * 0x08040201u) >> 24;      // first char -> bit 3
 }
 
-// Both software pexts of one k-mer word, for one strand, by table lookup: the 2k-bit word is cut into bytes (4 bases
-// each); every byte value maps to its pre-positioned contribution to rix = pext(bp, mask_hash_bp) (low 32 bits) and to
-// q = pext(lr, mask_drop_lr) (high 32 bits, already in the bit-plane form the index stores).  The reverse strand uses a
-// second table indexed by the SAME forward bytes (a base at position p lands, complemented, at position k-1-p of the
-// reverse complement), so no reverse-complement word is ever formed.  Tables are built by the host from the index's
-// ppos/npos (api.cu build_lut) and copied to shared memory once per CTA.
-__device__ __forceinline__ uint64_t lut_pext(const uint64_t* lut, uint32_t lo, uint32_t hi, bool wide)
+// Both software pexts of one k-mer word, for BOTH strands, by table lookup: the 2k-bit word is cut into bytes (4 bases
+// each); every byte value maps to its pre-positioned contribution to rix = pext(bp, mask_hash_bp) and to
+// q = pext(lr, mask_drop_lr) (already in the bit-plane form the index stores) of the forward k-mer (.x, .y) and of its
+// reverse complement (.z, .w): a base at position p lands, complemented, at position k-1-p of the reverse complement,
+// so the reverse strand is indexed by the SAME forward bytes and no reverse-complement word is ever formed.  Tables
+// are built by the host from the index's ppos/npos (api.cu build_lut) and copied to shared memory once per CTA.
+__device__ __forceinline__ uint4 lut_pext(const uint4* lut, uint32_t lo, uint32_t hi, bool wide)
 {
-  uint64_t r = lut[lo & 0xFF];
-  r |= lut[256 + ((lo >> 8) & 0xFF)];
-  r |= lut[512 + ((lo >> 16) & 0xFF)];
-  r |= lut[768 + (lo >> 24)];
-  r |= lut[1024 + (hi & 0xFF)];
-  r |= lut[1280 + ((hi >> 8) & 0xFF)];
-  r |= lut[1536 + ((hi >> 16) & 0xFF)];
-  if (wide) r |= lut[1792 + (hi >> 24)]; // only k > 28 reaches the eighth byte
+  uint4 r = lut[lo & 0xFF];
+  uint4 t;
+#define KREPP_LUT_OR(expr) t = lut[expr]; r.x |= t.x; r.y |= t.y; r.z |= t.z; r.w |= t.w;
+  KREPP_LUT_OR(256 + ((lo >> 8) & 0xFF))
+  KREPP_LUT_OR(512 + ((lo >> 16) & 0xFF))
+  KREPP_LUT_OR(768 + (lo >> 24))
+  KREPP_LUT_OR(1024 + (hi & 0xFF))
+  KREPP_LUT_OR(1280 + ((hi >> 8) & 0xFF))
+  KREPP_LUT_OR(1536 + ((hi >> 16) & 0xFF))
+  if (wide) { KREPP_LUT_OR(1792 + (hi >> 24)) } // only k > 28 reaches the eighth byte
+#undef KREPP_LUT_OR
   return r;
 }
 
@@ -170,10 +173,10 @@ template <int G, bool TAP>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) match_kernel(const DevIndex ix, const MatchArgs a)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const uint32_t nchunks = lut_chunks(ix.k), lut_strand = nchunks * 256;
-  uint64_t* lut = reinterpret_cast<uint64_t*>(smem_raw);
-  WarpSmem* smem = reinterpret_cast<WarpSmem*>(smem_raw + 2 * lut_strand * sizeof(uint64_t));
-  for (uint32_t i = threadIdx.x; i < 2 * lut_strand; i += blockDim.x) lut[i] = ix.lut[i];
+  const uint32_t nchunks = lut_chunks(ix.k);
+  uint4* lut = reinterpret_cast<uint4*>(smem_raw);
+  WarpSmem* smem = reinterpret_cast<WarpSmem*>(smem_raw + nchunks * 256 * sizeof(uint4));
+  for (uint32_t i = threadIdx.x; i < nchunks * 256; i += blockDim.x) lut[i] = ix.lut[i];
   __syncthreads();
   const bool wide = nchunks > 7;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -267,10 +270,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) match_kernel(const DevIndex
           bp = x >> (64 - 2 * k);
         }
         onmers += valid;
+        const uint4 rq = lut_pext(lut, (uint32_t)bp, (uint32_t)(bp >> 32), wide);
 #pragma unroll
         for (uint32_t strand = 0; strand < 2; ++strand) {
-          const uint64_t rq = lut_pext(lut + strand * lut_strand, (uint32_t)bp, (uint32_t)(bp >> 32), wide);
-          const uint32_t rix = (uint32_t)rq, q = (uint32_t)(rq >> 32);
+          const uint32_t rix = strand ? rq.z : rq.x, q = strand ? rq.w : rq.y;
           uint32_t quo, res;
           if (ix.m_shift != 0xFFFFFFFFu) { quo = rix >> ix.m_shift; res = rix & (ix.m - 1); }
           else { quo = rix / ix.m; res = rix - quo * ix.m; }
@@ -344,19 +347,17 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) match_kernel(const DevIndex
             e = lo & ~1u; cnt = 0; have = true;
           }
           const uint4 v = __ldg(reinterpret_cast<const uint4*>(ix.cmer + e));
-          const uint32_t z0 = v.x ^ cq, z1 = v.z ^ cq;
-          const uint32_t h0 = __popc((z0 | (z0 >> 16)) & 0xFFFFu), h1 = __popc((z1 | (z1 >> 16)) & 0xFFFFu);
-          if (h0 <= th && e >= lo) {
-            if (!cnt) { fse = v.y; fhd = h0; }
-            ++cnt;
-            if (cs) filt1 = min(filt1, h0); else filt0 = min(filt0, h0);
-          }
-          if (h1 <= th && e + 1 < hi) {
-            if (!cnt) { fse = v.w; fhd = h1; }
-            ++cnt;
-            if (cs) filt1 = min(filt1, h1); else filt0 = min(filt0, h1);
-          }
-          e += 2;
+          const uint4 u = __ldg(reinterpret_cast<const uint4*>(ix.cmer + ((e + 2 < hi) ? e + 2 : e)));
+#define KREPP_SCAN1(enc, sev, ok)                                                           \
+          { const uint32_t z = (enc) ^ cq; const uint32_t hd = __popc((z | (z >> 16)) & 0xFFFFu); \
+            if (hd <= th && (ok)) { if (!cnt) { fse = (sev); fhd = hd; } ++cnt;            \
+              if (cs) filt1 = min(filt1, hd); else filt0 = min(filt0, hd); } }
+          KREPP_SCAN1(v.x, v.y, e >= lo)
+          KREPP_SCAN1(v.z, v.w, e + 1 < hi)
+          KREPP_SCAN1(u.x, u.y, e + 2 < hi)
+          KREPP_SCAN1(u.z, u.w, e + 3 < hi)
+#undef KREPP_SCAN1
+          e += 4;
           if (e >= hi) {
             have = false;
             if (cnt == 1) { // exactly one hit entry: no other entry can lower a leaf's distance

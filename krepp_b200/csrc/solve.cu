@@ -11,6 +11,7 @@
 //                ref external/boost/libs/math/include/boost/math/tools/minima.hpp:23-138, called at src/query.cpp:430
 //   gate/merge : IBatch::summarize_matches                   ref src/query.cpp:96-139
 //   chisq      : Minfo::likelihood_ratio                     ref src/query.cpp:420-424
+#include "../../include/krepp_b200.h"
 #include "device.cuh"
 #include "solve.cuh"
 
@@ -179,6 +180,166 @@ __global__ void __launch_bounds__(128) chisq_kernel(const SolveArgs a, const Llh
     Objective f{&tab, mc, (double)a.onmers[read] - (double)a.rec_match[cl], a.rho[a.rec_slot[cl] & 0x7FFFFFFFu], a.k, a.th};
     a.rec_chisq[i] = 2 * (f(a.rec_d[i]) - a.rec_v[cl]);
   }
+}
+
+// ------------------------------------------------------------------------------------------------ K5: placement
+//
+// One warp per read; restates IBatch::report_placement (ref src/query.cpp:218-333, multi mode) over the flattened tree:
+//   * skip unless the closest reference has more than one match at Hamming distance <= tau (when filtering, :220)
+//   * one selected reference  -> that leaf, lwr = 1, chisq = 0 (:231-241)
+//   * otherwise every selected leaf is pushed to all its ancestors with weight prod 1/eff_nchildren (Minfo::add,
+//     ref src/query.hpp:139-152; denominators formed by successive division as at src/query.cpp:250-259), in ascending
+//     leaf order; internal nodes are re-solved (:273-275); a node is a candidate when its chisq against the closest
+//     is below the threshold and it is not the root (:276-279); lwr = exp(-chisq/2) / sum (:284-296).
+// Visiting order is fixed to ascending se.  In post-order numbering the subtree of node g
+// is the contiguous range (g - subtree[g], g], which makes "is leaf l below g" two comparisons.
+__device__ __forceinline__ double jukes_cantor(double d) { return -0.75 * log(1 - 4.0 / 3.0 * d); }
+
+__global__ void __launch_bounds__(128) place_kernel(const PlaceArgs a, const LlhTables tab)
+{
+  const SolveArgs& s = a.s;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t stride = s.th + 1, nbm = (a.nnodes + 32) >> 5;
+  uint32_t* bm = a.node_bitmap + (size_t)gwarp * nbm;
+  uint32_t* list = a.node_list + (size_t)gwarp * a.nnodes;
+  double* nd_d = a.node_d + (size_t)gwarp * a.nnodes;
+  double* nd_v = a.node_v + (size_t)gwarp * a.nnodes;
+  double* nd_c = a.node_chisq + (size_t)gwarp * a.nnodes;
+  uint32_t* nd_k = a.node_cand + (size_t)gwarp * a.nnodes;
+  krepp_placement_t* out = static_cast<krepp_placement_t*>(a.placements);
+
+  for (uint32_t r = gwarp; r < s.n_reads; r += nwarps) {
+    const uint32_t b = s.rec_begin[r], n = s.rec_count[r];
+    const int32_t cl = s.closest[r];
+    uint32_t pbegin = 0, pcount = 0;
+    if (cl >= 0) {
+      // number of selected references; records are forward leaves by ascending se, then reverse leaves by ascending se
+      uint32_t nsel = 0, nf = 0;
+      for (uint32_t i = lane; i < n; i += 32) { nsel += (s.rec_flags[b + i] >> 1) & 1u; nf += !(s.rec_slot[b + i] >> 31); }
+      for (int o = 16; o; o >>= 1) { nsel += __shfl_xor_sync(0xFFFFFFFFu, nsel, o); nf += __shfl_xor_sync(0xFFFFFFFFu, nf, o); }
+      double leq_cl = 0; // Minfo::get_leq_tau of the closest (ref src/query.hpp:189-196)
+      for (uint32_t x = 0; x <= a.tau && x < stride; ++x) leq_cl += (double)s.rec_hist[(size_t)cl * stride + x];
+      const uint32_t cl_se = s.rec_slot[cl] & 0x7FFFFFFFu;
+      double mc_cl[kMaxTh + 1];
+      for (uint32_t x = 0; x < stride; ++x) mc_cl[x] = (double)s.rec_hist[(size_t)cl * stride + x];
+      const Objective f_cl{&tab, mc_cl, (double)s.onmers[r] - (double)s.rec_match[cl], s.rho[cl_se], s.k, s.th};
+      const double v_cl = s.rec_v[cl];
+      if (a.no_filter || leq_cl > 1.0) {
+        if (nsel == 1) {
+          if (lane == 0) {
+            pbegin = atomicAdd(a.counters + 3, 1u); pcount = 1;
+            if (pbegin < a.place_cap) {
+              const double bl = a.blen[cl_se], mid = isnan(bl) ? 0.0 : bl / 2.0, d = s.rec_d[cl];
+              krepp_placement_t p; p.read = r; p.se = cl_se; p.pendant = jukes_cantor(d) - mid; p.distal = mid; p.loglik = -v_cl;
+              p.lwr = 1; p.d_llh = d; p.chisq = 0;
+              out[pbegin] = p;
+            } else atomicOr(a.counters + 2, kErrPlaceOverflow);
+          }
+        } else {
+          // 1. mark every selected leaf and all its ancestors
+          for (uint32_t i = lane; i < n; i += 32) {
+            if (!(s.rec_flags[b + i] & 2u)) continue;
+            uint32_t node = s.rec_slot[b + i] & 0x7FFFFFFFu;
+            while (node) {
+              const uint32_t bit = 1u << (node & 31);
+              if (atomicOr(&bm[node >> 5], bit) & bit) break;
+              node = a.parent[node];
+            }
+          }
+          __syncwarp();
+          // 2. ascending list of marked nodes
+          uint32_t cnt = 0;
+          for (uint32_t wb = 0; wb < nbm; wb += 32) {
+            uint32_t bits = (wb + lane < nbm) ? __ldcg(&bm[wb + lane]) : 0u;
+            const uint32_t c = __popc(bits);
+            uint32_t incl = c;
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += t; }
+            uint32_t at = cnt + incl - c;
+            cnt += __shfl_sync(0xFFFFFFFFu, incl, 31);
+            if (wb + lane < nbm && bits) bm[wb + lane] = 0;
+            while (bits) { const uint32_t q = __ffs(bits) - 1; bits &= bits - 1; list[at++] = (wb + lane) * 32 + q; }
+          }
+          __syncwarp();
+          // 3. one lane per marked node: accumulate, solve, test
+          const uint32_t enmers = (uint32_t)(a.offsets[r + 1] - a.offsets[r]) - s.k + 1;
+          for (uint32_t j = lane; j < cnt; j += 32) {
+            const uint32_t g = __ldcg(&list[j]);
+            double d = DBL_MAX, v = nan(""), chisq = nan(""), leq = 0;
+            if (a.leaf_rank[g] != 0xFFFFFFFFu) { // a selected leaf: its own record
+              uint32_t rec = 0xFFFFFFFFu;
+              for (uint32_t i = 0; i < n; ++i) if ((s.rec_flags[b + i] & 2u) && (s.rec_slot[b + i] & 0x7FFFFFFFu) == g) rec = b + i;
+              d = s.rec_d[rec]; v = s.rec_v[rec];
+              for (uint32_t x = 0; x <= a.tau && x < stride; ++x) leq += (double)s.rec_hist[(size_t)rec * stride + x];
+            } else {
+              double mc[kMaxTh + 1];
+              for (uint32_t x = 0; x < stride; ++x) mc[x] = 0;
+              double nmers = 0, mismatch = 0, match = 0, rho = 0;
+              const uint32_t lo = g - a.subtree[g]; // leaves below g have lo < se <= g
+              uint32_t i = b, jx = b + nf;
+              const uint32_t ie = b + nf, je = b + n;
+              while (i < ie || jx < je) { // selected records by ascending leaf se (merge of the two strands' runs)
+                const uint32_t si = i < ie ? (s.rec_slot[i] & 0x7FFFFFFFu) : 0xFFFFFFFFu, sj = jx < je ? (s.rec_slot[jx] & 0x7FFFFFFFu) : 0xFFFFFFFFu;
+                uint32_t rec, se;
+                if (si <= sj) { rec = i; se = si; ++i; if (si == sj) { if (!(s.rec_flags[rec] & 2u)) rec = jx; ++jx; } }
+                else { rec = jx; se = sj; ++jx; }
+                if (!(s.rec_flags[rec] & 2u) || !(se > lo && se <= g)) continue;
+                double denom = 1.0;
+                for (uint32_t node = a.parent[se];; node = a.parent[node]) { denom /= (double)a.nchildren[node]; if (node == g) break; }
+                const double m = (double)s.rec_match[rec];
+                mismatch = nmers != 0 ? mismatch : (double)enmers;      // Minfo::add (ref src/query.hpp:139-152)
+                match += m * denom;
+                mismatch -= m * denom;
+                for (uint32_t x = 0; x < stride; ++x) mc[x] = mc[x] + (double)s.rec_hist[(size_t)rec * stride + x] * denom;
+                nmers = fmax(nmers, (double)enmers);
+                rho = fmax(rho, s.rho[se]);
+              }
+              for (uint32_t x = 0; x <= a.tau && x < stride; ++x) leq += mc[x];
+              if (a.no_filter || leq > 1.0) {
+                Objective f{&tab, mc, mismatch, rho, s.k, s.th};
+                brent_minimum(f, d, v);
+              }
+            }
+            uint32_t cand = 0;
+            if (a.nchildren[g] != 1 && (a.no_filter || leq > 1.0)) {
+              chisq = 2 * (f_cl(d) - v_cl);
+              cand = (chisq < a.chisq_value) && a.parent[g] != 0;
+            }
+            nd_d[j] = d; nd_v[j] = v; nd_c[j] = chisq; nd_k[j] = cand;
+          }
+          __syncwarp();
+          // 4. candidates in ascending se: lwr = exp(-chisq/2) / total
+          if (lane == 0) {
+            double total = 0;
+            uint32_t nc = 0;
+            for (uint32_t j = 0; j < cnt; ++j) if (__ldcg(&nd_k[j])) { total = total + exp(-__ldcg(&nd_c[j]) / 2); ++nc; }
+            if (nc) {
+              pbegin = atomicAdd(a.counters + 3, nc); pcount = nc;
+              if ((uint64_t)pbegin + nc <= a.place_cap) {
+                uint32_t at = pbegin;
+                for (uint32_t j = 0; j < cnt; ++j) {
+                  if (!__ldcg(&nd_k[j])) continue;
+                  const uint32_t g = __ldcg(&list[j]);
+                  const double bl = a.blen[g], mid = isnan(bl) ? 0.0 : bl / 2.0, d = __ldcg(&nd_d[j]), c = __ldcg(&nd_c[j]);
+                  krepp_placement_t p; p.read = r; p.se = g; p.pendant = jukes_cantor(d) - mid; p.distal = mid; p.loglik = -__ldcg(&nd_v[j]);
+                  p.lwr = exp(-c / 2) / total; p.d_llh = d; p.chisq = c;
+                  out[at++] = p;
+                }
+              } else { atomicOr(a.counters + 2, kErrPlaceOverflow); pcount = 0; }
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+    if (lane == 0) { a.place_begin[r] = pbegin; a.place_count[r] = pcount; }
+  }
+}
+
+cudaError_t launch_place(const PlaceArgs& a, const LlhTables& tab, int grid, cudaStream_t stream)
+{
+  place_kernel<<<grid, 128, 0, stream>>>(a, tab);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_solve(const SolveArgs& a, const LlhTables& tab, int sms, cudaStream_t stream)

@@ -13,5 +13,7 @@ struct LlhTables {
 int match_resident_warps(int device, uint32_t k);
 cudaError_t launch_match(const DevIndex& ix, const MatchArgs& a, int resident_warps, int group, bool tap, cudaStream_t stream);
 cudaError_t launch_solve(const SolveArgs& a, const LlhTables& tab, int sms, cudaStream_t stream);
+constexpr int kPlaceWarpsPerCta = 4;
+cudaError_t launch_place(const PlaceArgs& a, const LlhTables& tab, int grid, cudaStream_t stream);
 
 } // namespace krepp

@@ -42,9 +42,12 @@ def gpu_stage_dicts(batch: "krepp_b200.IBatch", res: dict, tap: np.ndarray | Non
                 sel.append(dict(leaf_se=int(r["leaf_se"]), strand=int(r["strand"]), is_closest=int(bool(r["flags"] & 4)),
                                 d=float(r["d_llh"]), v=float(r["v_llh"]), chisq=float(r["chisq"])))
         sel.sort(key=lambda e: e["leaf_se"])
+        pb, pn = int(s["place_begin"]), int(s["place_count"])
+        place = [dict(se=int(q["se"]), edge=int(q["se"]) - 1, d=float(q["d_llh"]), v=-float(q["loglik"]), chisq=float(q["chisq"]),
+                      lwr=float(q["lwr"]), pendant=float(q["pendant"]), distal=float(q["distal"])) for q in res["placements"][pb:pb + pn]]
         out.append(dict(onmers=int(s["onmers"]), wn=(int(s["wn"][0]), int(s["wn"][1])),
                         hdist_filt=(int(s["hdist_filt"][0]), int(s["hdist_filt"][1])), lookups=lookups.get(i, []),
-                        minfo=minfo, sel=sel))
+                        minfo=minfo, sel=sel, place=place))
     return out
 
 
@@ -75,6 +78,21 @@ def compare_read(i: int, g: dict, o: dict, check_lookups: bool, check_chisq: boo
             assert rel_close(a["chisq"], b["chisq"], 1e-5) or abs(a["chisq"] - b["chisq"]) < 1e-9, (i, "chisq", a, b)
 
 
+def compare_place(i: int, g: dict, o: dict, stats: dict):
+    """Candidate edges must be the same set; d / loglik / lwr / pendant within REL_TOL (chisq and lwr are differences /
+    exponentials of likelihoods, so they get an absolute floor as well)."""
+    ge, oe = [p["se"] for p in g["place"]], [p["se"] for p in o["place"]]
+    assert ge == oe, (i, "place edges", ge, oe)
+    for a, b in zip(g["place"], o["place"]):
+        stats["placements"] += 1
+        assert rel_close(a["d"], b["d"]), (i, "place d", a, b)
+        assert rel_close(a["v"], b["v"]), (i, "place loglik", a, b)
+        assert rel_close(a["lwr"], b["lwr"]) or abs(a["lwr"] - b["lwr"]) < 1e-9, (i, "place lwr", a, b)
+        assert rel_close(a["pendant"], b["pendant"]) or abs(a["pendant"] - b["pendant"]) < 1e-9, (i, "pendant", a, b)
+        assert a["distal"] == b["distal"], (i, "distal", a, b)
+        assert rel_close(a["chisq"], b["chisq"]) or abs(a["chisq"] - b["chisq"]) < 1e-7, (i, "place chisq", a, b)
+
+
 def run_and_compare(index_dir: str, reads: list[bytes], oracle: "O.OracleIndex", gindex: "krepp_b200.Index",
                     check_lookups: bool = True, **params) -> dict:
     th = params.get("hdist_th", 4)
@@ -85,10 +103,15 @@ def run_and_compare(index_dir: str, reads: list[bytes], oracle: "O.OracleIndex",
     res = batch.wait()
     tap = batch.read_tap() if check_lookups else None
     g = gpu_stage_dicts(batch, res, tap)
-    p = O.default_params(hdist_th=th, want_lookups=int(check_lookups), no_filter=int(params.get("no_filter", True)))
-    stats = dict(solves=0, bitexact_d=0, max_rel_d=0.0, reads=len(reads), records=len(res["records"]))
+    place = bool(params.get("place", False))
+    p = O.default_params(hdist_th=th, want_lookups=int(check_lookups), no_filter=int(params.get("no_filter", True)),
+                         want_place=int(place), tau=params.get("tau", 2), chisq=params.get("chisq", 2.706))
+    stats = dict(solves=0, bitexact_d=0, max_rel_d=0.0, reads=len(reads), records=len(res["records"]), placements=0)
     for i, s in enumerate(reads):
-        compare_read(i, g[i], oracle.query(s, p), check_lookups, not params.get("no_filter", True), stats)
+        o = oracle.query(s, p)
+        compare_read(i, g[i], o, check_lookups, place or not params.get("no_filter", True), stats)
+        if place:
+            compare_place(i, g[i], o, stats)
     stats["alg"] = batch.algorithmic_bytes()
     batch.close()
     return stats

@@ -94,6 +94,21 @@ def test_dist_filter_chisq(env):
 
 
 @needs_ref
+@pytest.mark.parametrize("kw", [dict(no_filter=False), dict(no_filter=True), dict(no_filter=False, tau=3, chisq=3.841)])
+def test_place_all_stages(env, kw):
+    """krepp place: candidate edges identical to the oracle's (same deterministic tie rule), likelihoods / LWR / pendant
+    lengths within 1e-5."""
+    import synth
+    from gpu_common import run_and_compare
+    seq, offs = synth.load_packed(os.path.join(TOY_DIR, "genomes.npz"))
+    names, reads = fastq_reads(os.path.join(TOY_DIR, "query_toy.fq"))
+    reads = reads + [r.tobytes() for r in synth.sample_reads(seq, offs, 6000, seed=77)]
+    st = run_and_compare(env["dir"], reads, env["oracle"], env["gpu"], check_lookups=False, place=True, **kw)
+    print(st)
+    assert st["placements"] > 1000
+
+
+@needs_ref
 def test_tsv_matches_reference_cli(env):
     """`krepp dist` body of the reference binary itself vs the GPU path's TSV, compared as sorted line sets."""
     import subprocess
