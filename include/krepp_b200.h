@@ -124,7 +124,7 @@ typedef struct {
   const krepp_record_t* records;      /* [n_records] */
   const uint32_t* hist;               /* [n_records * hist_stride]: Minfo::hdisthist_v */
   const krepp_placement_t* placements;/* [n_placements] */
-  float gpu_ms;                       /* device time of this batch incl. copies (CUDA events on the slot's stream) */
+  float gpu_ms;                       /* device time of all kernels of this batch, copies excluded (CUDA events on the slot's stream) */
   float match_ms;                     /* device time of the match kernel alone (same stream, CUDA events) */
   uint32_t gpu_launches;              /* kernels launched for this batch */
 } krepp_results_t;

@@ -214,10 +214,12 @@ int krepp_index_open(const char* index_dir, int device, krepp_index_t** out)
   for (uint32_t i = 0; i < (uint32_t)kMaxResidues; ++i) d.res_numer[i] = i < h.m ? h.res_numer[i] : 0;
   d.local_expand = h.max_expand_depth + 2 <= 32 ? 1u : 0u;
   ix->resident_warps = match_resident_warps(device, h.k);
-  { // scan group width: lanes that cooperate on one bucket (see match.cu phase B)
-    const double nonempty = h.mean_bucket > 0 ? h.size_biased_bucket : 0; // entries seen by a lookup that lands on a k-mer
+  { // scan group width (match.cu phase B).  Small buckets: every lane scans whole buckets on its own with 128-bit
+    // loads (G = 1).  Once a typical hit bucket spans several 128-byte lines, G lanes share one bucket so that a group
+    // reads one contiguous run per step.
+    const double sb = h.size_biased_bucket; // entries in the bucket an indexed k-mer lands in
     int g = 1;
-    while (g < 32 && 2.0 * g < std::max(h.mean_bucket, nonempty * 0.5)) g *= 2;
+    if (sb > 24.0) { g = 4; while (g < 32 && 4.0 * g < sb) g *= 2; }
     if (const char* env = getenv("KREPP_GROUP")) { const int v = atoi(env); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) g = v; }
     ix->group = g;
   }
@@ -425,6 +427,7 @@ static int enqueue(krepp_batch* b)
   }
   finalize_kernel<<<ix->sms * 4, 128, 0, s>>>(sa, b->d_out_rec, b->d_out_read, b->d_wn, b->d_place_begin, b->d_place_count);
   CU(cudaGetLastError());
+  CU(cudaEventRecord(b->ev1, s)); // kernels only: [ev0, ev1] excludes the host<->device copies on both sides
   CU(cudaMemcpyAsync(b->h_counters, b->d_counters, 16, cudaMemcpyDeviceToHost, s));
   CU(cudaMemcpyAsync(b->h_stats, b->d_stats, 32, cudaMemcpyDeviceToHost, s));
   CU(cudaMemcpyAsync(b->h_read, b->d_out_read, sizeof(krepp_read_summary_t) * (size_t)b->n_reads, cudaMemcpyDeviceToHost, s));
@@ -454,9 +457,9 @@ int krepp_batch_submit(krepp_batch_t* b, const char* bases, const uint64_t* offs
   }
   b->n_reads = n_reads; b->n_bases = nb; b->device_input = false;
   b->in_bases = b->d_bases; b->in_offsets = b->d_offsets;
-  CU(cudaEventRecord(b->ev0, b->stream));
   CU(cudaMemcpyAsync(b->d_bases, b->h_bases, nb, cudaMemcpyHostToDevice, b->stream));
   CU(cudaMemcpyAsync(b->d_offsets, b->h_offsets, 8ull * (n_reads + 1), cudaMemcpyHostToDevice, b->stream));
+  CU(cudaEventRecord(b->ev0, b->stream));
   if (int rc = enqueue(b)) return rc;
   b->submitted = true;
   return KREPP_OK;
@@ -508,7 +511,6 @@ int krepp_batch_wait(krepp_batch_t* b, krepp_results_t* out)
   }
   const uint32_t nplace = b->p.place ? b->h_counters[3] : 0;
   if (nplace) CU(cudaMemcpyAsync(b->h_place, b->d_place, sizeof(krepp_placement_t) * (size_t)nplace, cudaMemcpyDeviceToHost, b->stream));
-  CU(cudaEventRecord(b->ev1, b->stream));
   CU(cudaStreamSynchronize(b->stream));
   float ms = 0;
   CU(cudaEventElapsedTime(&ms, b->ev0, b->ev1));

@@ -28,6 +28,32 @@ def fastq_reads(path):
     return [lines[i][1:].split()[0].decode() for i in range(0, len(lines) - 1, 4)], [lines[i] for i in range(1, len(lines), 4)]
 
 
+def test_golden_small_index_k21_h7():
+    """The committed golden fixture (reference-built index with k=21 w=25 h=7, reads incl. edge cases): the CUDA path
+    against the oracle on every stage, dist and place.  Needs nothing from oracle/_ref."""
+    import krepp_b200
+    import oracle_lib as O
+    from gpu_common import run_and_compare
+    small = os.path.join(conftest.GOLDEN_DIR, "small")
+    names, reads = fastq_reads(os.path.join(small, "reads.fq"))
+    o, g = O.OracleIndex(os.path.join(small, "index")), krepp_b200.Index(os.path.join(small, "index"), 0)
+    st = run_and_compare(small, reads, o, g)
+    assert st["reads"] == 236 and st["solves"] > 500
+    st = run_and_compare(small, reads, o, g, check_lookups=False, place=True, no_filter=False)
+    assert st["placements"] == 408  # the reference's own count for this fixture (ref_dump 'P' lines)
+    b = krepp_b200.IBatch(g, reads, names=names)
+    with open(os.path.join(small, "ref_dist.tsv")) as f:
+        assert sorted(b.estimate_distances().splitlines()) == sorted(f.read().splitlines())
+    for grp in ("1", "4", "32"):   # every scan strategy gives the same integers
+        os.environ["KREPP_GROUP"] = grp
+        try:
+            g2 = krepp_b200.Index(os.path.join(small, "index"), 0)
+            run_and_compare(small, reads, o, g2, check_lookups=False)
+            g2.close()
+        finally:
+            del os.environ["KREPP_GROUP"]
+
+
 @needs_ref
 def test_toy_query_all_stages(env):
     from gpu_common import run_and_compare

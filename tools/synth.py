@@ -112,7 +112,9 @@ def random_genomes(n_genomes: int, length: int, seed: int = 7, depth_blen: float
         return "(" + ",".join(parts) + ")"
 
     root = rng.integers(0, 4, size=length).astype(np.uint8)
-    nwk = grow(root, n_genomes) + ";"
+    # the reference's Newick reader indexes past its token vector for a root without label AND length
+    # (src/phytree.cpp:171-187), so the root always gets both
+    nwk = grow(root, n_genomes) + "root:0.0;"
     return names, seqs, nwk
 
 
