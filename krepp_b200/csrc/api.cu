@@ -67,7 +67,7 @@ static std::vector<uint4> build_lut(const HostIndex& h)
   { std::vector<uint8_t> pp = h.ppos, np = h.npos; std::sort(pp.begin(), pp.end()); std::sort(np.begin(), np.end());
     for (size_t i = 0; i < pp.size(); ++i) hrank[pp[i]] = (int)i;
     for (size_t i = 0; i < np.size(); ++i) nrank[np[i]] = (int)i; }
-  const uint32_t nch = (2 * h.k + 7) / 8; // bytes of the k-mer word that can be non-zero
+  const uint32_t nch = std::max<uint32_t>(7, (2 * h.k + 7) / 8); // bytes of the k-mer word (match.cu lut_chunks: never fewer than seven tables)
   std::vector<uint4> lut(nch * 256, make_uint4(0, 0, 0, 0));
   for (uint32_t strand = 0; strand < 2; ++strand)
     for (uint32_t c = 0; c < nch; ++c)

@@ -42,7 +42,8 @@ struct WarpSmem {
   uint32_t cursor;
 };
 // LUT layout: [byte of the k-mer word][byte value] -> {rix fwd, q fwd, rix rc, q rc} parts; 7 bytes cover k <= 28
-__host__ __device__ inline uint32_t lut_chunks(uint32_t k) { return (2 * k + 7) / 8; }
+// lut_pext always reads the first seven byte tables, so at least seven are staged (all-zero past the k-mer's last byte)
+__host__ __device__ inline uint32_t lut_chunks(uint32_t k) { const uint32_t n = (2 * k + 7) / 8; return n < 7 ? 7 : n; }
 __host__ __device__ inline size_t smem_bytes(uint32_t k) { return lut_chunks(k) * 256 * sizeof(uint4) + kWarpsPerCta * sizeof(WarpSmem); }
 
 __device__ __forceinline__ void encode4(uint32_t u, uint32_t& code8, uint32_t& valid4)
