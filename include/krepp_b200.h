@@ -166,6 +166,50 @@ int krepp_batch_read_tap(krepp_batch_t* b, int stage, uint32_t* out, uint64_t ca
  * len + sum over eligible lookups (16 + 8*|bucket|) + 64 * records, computed on the device while matching. */
 int krepp_batch_algorithmic_bytes(krepp_batch_t* b, uint64_t* bytes, uint64_t* lookups, uint64_t* entries_scanned);
 
+/* -------------------------------------------------------------------------------------------------- host I/O layer
+ * The steps immediately either side of the GPU path.  Pure host code: usable
+ * without a device (the index handle may have been opened with KREPP_DEVICE_NONE). */
+
+typedef struct krepp_reader krepp_reader_t;
+
+/* Replaces the QSeq constructor (src/rqseq.cpp:161-178): opens a FASTA/FASTQ file, plain or gzip (zlib gzopen). */
+int krepp_reader_open(const char* path, krepp_reader_t** out);
+void krepp_reader_close(krepp_reader_t* r);
+/* Replaces QSeq::read_next_batch (src/rqseq.cpp:180-197) over kseq_read (src/kseq.h:177-216) with the same record
+ * framing: a record starts at '>' or '@'; the name is the header up to the first whitespace; sequence characters are
+ * all printable non-space bytes up to the next '>', '@' or '+'; after '+' the rest of that line is skipped and as many
+ * quality characters as there were bases are consumed; a truncated quality string ends the input.  Reads are appended
+ * back to back into `bases` (offsets[0] = 0 ... offsets[n]) and names, NUL-terminated, into `names`
+ * (name_offsets[i] = start of name i).  The batch ends when max_reads, max_bases or max_name_bytes would be exceeded
+ * (the record that did not fit opens the next batch) or at end of input (*eof = 1).  A single record larger than
+ * max_bases returns KREPP_ERR_CAPACITY. */
+int krepp_reader_next(krepp_reader_t* r, char* bases, uint64_t max_bases, uint64_t* offsets, uint32_t max_reads,
+                      char* names, uint64_t max_name_bytes, uint64_t* name_offsets, uint32_t* n_reads, int* eof);
+
+/* All formatters append to `buf` (capacity `cap`) and return the number of bytes the complete text needs; when that
+ * exceeds cap nothing useful was written and the caller retries with a larger buffer.  Doubles are printed like the
+ * reference's streams: std::fixed, precision 5 (src/query.cpp:152-153, src/krepp.cpp:351-352). */
+
+/* header_dreport / header_preport / begin_jplace (src/krepp.cpp:311-319,396-408,426-432). */
+size_t krepp_format_header(const krepp_index_t* ix, const krepp_params_t* p, int tabular, const char* invocation,
+                           char* buf, size_t cap);
+/* IBatch::report_distances for every read of a batch (src/query.cpp:158-196): reads in input order, references by
+ * ascending se.  With p->summarize the rows are not written; the per-node weights are added to wcount[nnodes+1]
+ * instead (src/query.cpp:160-171) and 0 is returned. */
+size_t krepp_format_dist(const krepp_index_t* ix, const krepp_params_t* p, const krepp_results_t* res,
+                         const char* names, const uint64_t* name_offsets, double* wcount, char* buf, size_t cap);
+/* IBatch::place_sequences / report_placement text for a batch (src/query.cpp:198-333): jplace "placements" entries
+ * (PP_JPLACE_FIELDS, src/query.hpp:202-204) or --tabular rows (PP_TABULAR_FIELDS, :206); --no-multi picks the
+ * candidate with the largest clade, then the smallest distance (src/query.cpp:311-330).  *has_previous carries the
+ * "a placement was already written" state across batches (src/krepp.cpp:476-481).  With p->summarize weights go to
+ * wcount (src/query.cpp:232,298,323). */
+size_t krepp_format_place(const krepp_index_t* ix, const krepp_params_t* p, const krepp_results_t* res,
+                          const char* names, const uint64_t* name_offsets, int tabular, int* has_previous, double* wcount,
+                          char* buf, size_t cap);
+/* Tail of the output: the --summarize table (src/krepp.cpp:385-392,492-497) or end_jplace (src/krepp.cpp:410-424). */
+size_t krepp_format_footer(const krepp_index_t* ix, const krepp_params_t* p, int tabular, const double* wcount,
+                           uint64_t total_queries, const char* invocation, char* buf, size_t cap);
+
 const char* krepp_last_error(void);
 int krepp_abi_version(void);
 

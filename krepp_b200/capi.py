@@ -98,6 +98,17 @@ def load_library():
     L.krepp_batch_enable_tap.argtypes = [C.c_void_p, C.c_int, C.c_uint64]
     L.krepp_batch_read_tap.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.krepp_batch_algorithmic_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.krepp_reader_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    L.krepp_reader_close.argtypes = [C.c_void_p]
+    L.krepp_reader_next.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p,
+                                    C.POINTER(C.c_uint32), C.POINTER(C.c_int)]
+    for f in ("krepp_format_header", "krepp_format_dist", "krepp_format_place", "krepp_format_footer"):
+        getattr(L, f).restype = C.c_size_t
+    L.krepp_format_header.argtypes = [C.c_void_p, C.POINTER(Params), C.c_int, C.c_char_p, C.c_void_p, C.c_size_t]
+    L.krepp_format_dist.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Results), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    L.krepp_format_place.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Results), C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int),
+                                     C.c_void_p, C.c_void_p, C.c_size_t]
+    L.krepp_format_footer.argtypes = [C.c_void_p, C.POINTER(Params), C.c_int, C.c_void_p, C.c_uint64, C.c_char_p, C.c_void_p, C.c_size_t]
     _lib = L
     return L
 
@@ -297,3 +308,111 @@ class IBatch:
             else:
                 out.append(head + ",".join("\n\t\t\t\t" + x for x in f) + "]\n\t\t\t}")
         return "".join(out) if tabular else ",\n".join(out)
+
+
+# ---- host I/O layer (krepp_reader_* / krepp_format_*): pure host code, usable with Index(dir, device=-1) ------------------
+
+class Reader:
+    """FASTA/FASTQ batch reader with kseq framing (replaces QSeq, src/rqseq.cpp:161-197)."""
+
+    def __init__(self, path: str):
+        self._h = C.c_void_p()
+        _check(load_library().krepp_reader_open(os.fsencode(path), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().krepp_reader_close(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def next_batch(self, max_reads: int = 1 << 16, max_bases: int = 1 << 24, max_name_bytes: int | None = None):
+        """Returns (names, reads, eof) for the next batch; reads are bytes objects."""
+        max_name_bytes = max_name_bytes or 64 * max_reads
+        bases = np.empty(max(max_bases, 1), np.uint8)
+        offs = np.empty(max_reads + 1, np.uint64)
+        names = np.empty(max(max_name_bytes, 1), np.uint8)
+        noffs = np.empty(max(max_reads, 1), np.uint64)
+        n, eof = C.c_uint32(), C.c_int()
+        _check(load_library().krepp_reader_next(self._h, bases.ctypes.data, max_bases, offs.ctypes.data, max_reads, names.ctypes.data,
+                                                max_name_bytes, noffs.ctypes.data, C.byref(n), C.byref(eof)))
+        nb = names.tobytes()
+        out_names = [nb[int(noffs[i]):nb.index(b"\0", int(noffs[i]))].decode() for i in range(n.value)]
+        out_reads = [bases[int(offs[i]):int(offs[i + 1])].tobytes() for i in range(n.value)]
+        return out_names, out_reads, bool(eof.value)
+
+    def read_all(self, **kw):
+        names, reads = [], []
+        while True:
+            a, b, eof = self.next_batch(**kw)
+            names += a
+            reads += b
+            if eof:
+                return names, reads
+
+
+def pack_names(names) -> tuple[np.ndarray, np.ndarray]:
+    blob = b"".join(n.encode() + b"\0" for n in names)
+    offs = np.zeros(max(len(names), 1), np.uint64)
+    at = 0
+    for i, n in enumerate(names):
+        offs[i] = at
+        at += len(n.encode()) + 1
+    return np.frombuffer(blob + b"\0", dtype=np.uint8).copy(), offs
+
+
+def results_struct(reads: np.ndarray, records: np.ndarray, hist: np.ndarray, placements: np.ndarray | None = None) -> Results:
+    """A krepp_results_t over caller-owned numpy arrays (kept alive by the caller)."""
+    r = Results()
+    r.n_reads, r.hist_stride = len(reads), hist.shape[1] if hist.ndim == 2 else 0
+    r.n_records, r.n_placements = len(records), 0 if placements is None else len(placements)
+    r.reads, r.records, r.hist = reads.ctypes.data, records.ctypes.data, hist.ctypes.data
+    r.placements = placements.ctypes.data if placements is not None and len(placements) else None
+    return r
+
+
+def _format(call) -> str:
+    cap = 1 << 16
+    while True:
+        buf = C.create_string_buffer(cap)
+        n = call(buf, cap)
+        if n <= cap:
+            return buf.raw[:n].decode()
+        cap = n + 16
+
+
+def format_header(index: Index, params: Params, tabular: bool = False, invocation: str = "") -> str:
+    L = load_library()
+    return _format(lambda b, c: L.krepp_format_header(index._h, C.byref(params), int(tabular), invocation.encode(), b, c))
+
+
+def format_dist(index: Index, params: Params, res: Results, names, wcount: np.ndarray | None = None) -> str:
+    L = load_library()
+    nb, no = pack_names(names)
+    w = wcount.ctypes.data if wcount is not None else None
+    if wcount is not None:  # accumulate exactly once
+        L.krepp_format_dist(index._h, C.byref(params), C.byref(res), nb.ctypes.data, no.ctypes.data, w, None, 0)
+        return ""
+    return _format(lambda b, c: L.krepp_format_dist(index._h, C.byref(params), C.byref(res), nb.ctypes.data, no.ctypes.data, None, b, c))
+
+
+def format_place(index: Index, params: Params, res: Results, names, tabular: bool = False, wcount: np.ndarray | None = None) -> str:
+    L = load_library()
+    nb, no = pack_names(names)
+    if wcount is not None:
+        prev = C.c_int(0)
+        L.krepp_format_place(index._h, C.byref(params), C.byref(res), nb.ctypes.data, no.ctypes.data, int(tabular), C.byref(prev),
+                             wcount.ctypes.data, None, 0)
+        return ""
+
+    def call(b, c):
+        prev = C.c_int(0)
+        return L.krepp_format_place(index._h, C.byref(params), C.byref(res), nb.ctypes.data, no.ctypes.data, int(tabular), C.byref(prev), None, b, c)
+    return _format(call)
+
+
+def format_footer(index: Index, params: Params, tabular: bool = False, wcount: np.ndarray | None = None, total_queries: int = 0,
+                  invocation: str = "") -> str:
+    L = load_library()
+    w = wcount.ctypes.data if wcount is not None else None
+    return _format(lambda b, c: L.krepp_format_footer(index._h, C.byref(params), int(tabular), w, total_queries, invocation.encode(), b, c))

@@ -3,6 +3,7 @@
 #include "../../include/krepp_b200.h"
 
 #include "device.cuh"
+#include "handles.hpp"
 #include "index_image.hpp"
 #include "solve.cuh"
 
@@ -114,13 +115,18 @@ __global__ void __launch_bounds__(128) finalize_kernel(const SolveArgs a, krepp_
 
 } // namespace
 
-struct krepp_index {
-  HostIndex host;
-  DevIndex dev{};
-  int device = 0, sms = 0, resident_warps = 0, group = 4;
-  uint64_t device_bytes = 0;
-  std::vector<void*> allocs;
-};
+namespace krepp {
+int set_error(int code, const char* fmt, ...)
+{
+  char b[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(b, sizeof b, fmt, ap);
+  va_end(ap);
+  g_err = b;
+  return code;
+}
+} // namespace krepp
 
 struct krepp_batch {
   krepp_index* ix = nullptr;

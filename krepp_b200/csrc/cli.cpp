@@ -1,0 +1,293 @@
+// cli.cpp -- `krepp_b200 dist|place`: the reference's command line for the query path (ref src/krepp.cpp:593-716,738-763)
+// over the C ABI of include/krepp_b200.h.  Same flags, defaults and validation as `krepp dist` / `krepp place`, same
+// output framing; reads are reported in input order (the reference's order is unspecified).
+//
+// Pipeline: one producer thread parses FASTA/FASTQ straight into the pinned buffers of the next free batch slot and
+// submits it (H2D + kernels + D2H are asynchronous on the slot's stream); one consumer thread waits for slots in
+// submission order, formats them with --num-threads workers and writes the text.  Slots are spread round-robin over the
+// GPUs given by --num-gpus / --devices (index replicated per GPU, no data-path collective: SURVEY.md section 8e mode A).
+#include "../../include/krepp_b200.h"
+
+#include <chrono>
+#include <cmath>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <deque>
+#include <limits>
+#include <mutex>
+#include <string>
+#include <sys/stat.h>
+#include <thread>
+#include <vector>
+
+namespace {
+
+[[noreturn]] void error_exit(const std::string& msg)
+{ // ref src/common.cpp:20-24
+  fprintf(stderr, "[ERROR] %s\n", msg.c_str());
+  exit(EXIT_FAILURE);
+}
+
+struct Options {
+  std::string sub, query, index_dir, output_path, nwk_path, lineage_path;
+  uint32_t hdist_th = 4, tau = 2, num_threads = 1, seed = 0;
+  double chisq = 2.706, dist_max = std::numeric_limits<double>::quiet_NaN();
+  bool multi = true, filter = false, summarize = false, tabular = false, verbose = false;
+  // additions of this implementation
+  std::vector<int> devices;
+  uint32_t batch_reads = 1u << 18, slots_per_gpu = 3;
+  uint64_t batch_bases = 64ull << 20;
+};
+
+const char* kUsage =
+  "krepp_b200: B200-native query path of krepp (k-mer-based distance estimation & phylogenetic placement).\n"
+  "Usage: krepp_b200 [--num-threads N] [--seed S] [--verbose] {dist|place} -i INDEX_DIR -q QUERY [options]\n"
+  "  common:  -q,--query PATH   -i,--index-dir DIR   -o,--output-path PATH   --hdist-th N [4]   --chisq X [2.706]\n"
+  "           --summarize/--no-summarize [false]\n"
+  "  dist:    --dist-max X   --multi/--no-multi [true]   --filter/--no-filter [false]\n"
+  "  place:   --tau N [2]   --multi/--no-multi [true]   --filter/--no-filter [true]   --tabular/--no-tabular [false]\n"
+  "           -t,--nwk-file / -l,--lineage-file (not supported by the GPU path yet)\n"
+  "  GPU:     --num-gpus N [1] | --devices 0,1,..   --batch-reads N [262144]   --batch-bases N [67108864]   --slots N [3]\n";
+
+bool exists(const std::string& p, bool dir)
+{
+  struct stat st;
+  if (stat(p.c_str(), &st) != 0) return false;
+  return dir ? S_ISDIR(st.st_mode) : S_ISREG(st.st_mode);
+}
+
+Options parse(int argc, char** argv)
+{
+  Options o;
+  bool filter_set = false;
+  int num_gpus = 0;
+  std::vector<std::string> a(argv + 1, argv + argc);
+  auto need = [&](size_t& i, const std::string& name) -> std::string {
+    const size_t eq = a[i].find('=');
+    if (a[i].rfind("--", 0) == 0 && eq != std::string::npos) return a[i].substr(eq + 1);
+    if (i + 1 >= a.size()) error_exit("Option " + name + " requires an argument.");
+    return a[++i];
+  };
+  for (size_t i = 0; i < a.size(); ++i) {
+    std::string k = a[i];
+    if (k.rfind("--", 0) == 0 && k.find('=') != std::string::npos) k = k.substr(0, k.find('='));
+    if (k == "dist" || k == "place") { if (!o.sub.empty()) error_exit("Only one subcommand may be given."); o.sub = k; }
+    else if (k == "index" || k == "inspect" || k == "sketch" || k == "seek") error_exit("Subcommand '" + k + "' is not part of the GPU query path; use the reference krepp binary for it.");
+    else if (k == "--help") { fputs(kUsage, stdout); exit(0); }
+    else if (k == "--verbose") o.verbose = true;
+    else if (k == "--no-verbose") o.verbose = false;
+    else if (k == "--seed") o.seed = (uint32_t)strtoul(need(i, k).c_str(), nullptr, 10);
+    else if (k == "--num-threads") o.num_threads = (uint32_t)strtoul(need(i, k).c_str(), nullptr, 10);
+    else if (k == "-q" || k == "--query") o.query = need(i, k);
+    else if (k == "-i" || k == "--index-dir") o.index_dir = need(i, k);
+    else if (k == "-o" || k == "--output-path") o.output_path = need(i, k);
+    else if (k == "--hdist-th") { const std::string v = need(i, k); if (v.empty() || v[0] == '-') error_exit("--hdist-th: Number less than 0"); o.hdist_th = (uint32_t)strtoul(v.c_str(), nullptr, 10); }
+    else if (k == "--chisq") { o.chisq = atof(need(i, k).c_str()); if (!(o.chisq > 0)) error_exit("--chisq: Number less or equal to 0"); }
+    else if (k == "--summarize") o.summarize = true;
+    else if (k == "--no-summarize") o.summarize = false;
+    else if (k == "--dist-max") { o.dist_max = atof(need(i, k).c_str()); if (!(o.dist_max >= 1e-8 && o.dist_max <= 0.33)) error_exit("--dist-max: Value not in range [1e-08 - 0.33]"); }
+    else if (k == "--multi") o.multi = true;
+    else if (k == "--no-multi") o.multi = false;
+    else if (k == "--filter") { o.filter = true; filter_set = true; }
+    else if (k == "--no-filter") { o.filter = false; filter_set = true; }
+    else if (k == "--tau") { const std::string v = need(i, k); if (v.empty() || v[0] == '-') error_exit("--tau: Number less than 0"); o.tau = (uint32_t)strtoul(v.c_str(), nullptr, 10); }
+    else if (k == "--tabular") o.tabular = true;
+    else if (k == "--no-tabular") o.tabular = false;
+    else if (k == "-t" || k == "--nwk-file") o.nwk_path = need(i, k);
+    else if (k == "-l" || k == "--lineage-file") o.lineage_path = need(i, k);
+    else if (k == "--num-gpus") num_gpus = atoi(need(i, k).c_str());
+    else if (k == "--devices") { const std::string v = need(i, k); size_t p = 0; while (p < v.size()) { o.devices.push_back(atoi(v.c_str() + p)); p = v.find(',', p); if (p == std::string::npos) break; ++p; } }
+    else if (k == "--batch-reads") o.batch_reads = (uint32_t)strtoul(need(i, k).c_str(), nullptr, 10);
+    else if (k == "--batch-bases") o.batch_bases = strtoull(need(i, k).c_str(), nullptr, 10);
+    else if (k == "--slots") o.slots_per_gpu = (uint32_t)strtoul(need(i, k).c_str(), nullptr, 10);
+    else error_exit("The following argument was not expected: " + a[i]);
+  }
+  if (o.sub.empty()) { fputs(kUsage, stderr); error_exit("A subcommand is required"); }
+  if (o.query.empty()) error_exit("--query is required");
+  if (o.index_dir.empty()) error_exit("--index-dir is required");
+  if (!exists(o.query, false)) error_exit("--query: File does not exist: " + o.query);
+  if (!exists(o.index_dir, true)) error_exit("--index-dir: Directory does not exist: " + o.index_dir);
+  if (o.sub == "place" && !filter_set) o.filter = true; // ref src/krepp.cpp:614
+  if (o.sub == "dist" && (o.tabular || !o.nwk_path.empty() || !o.lineage_path.empty())) error_exit("The following argument was not expected for dist");
+  if (!o.nwk_path.empty() || !o.lineage_path.empty()) error_exit("-t/--nwk-file and -l/--lineage-file are not supported by the GPU path yet (placement uses the index's backbone tree)");
+  if (o.devices.empty()) for (int d = 0; d < (num_gpus > 0 ? num_gpus : 1); ++d) o.devices.push_back(d);
+  if (!o.num_threads) o.num_threads = 1;
+  if (!o.batch_reads || !o.batch_bases || !o.slots_per_gpu) error_exit("--batch-reads, --batch-bases and --slots must be positive");
+  return o;
+}
+
+struct Slot {
+  krepp_batch_t* batch = nullptr;
+  char* bases = nullptr;
+  uint64_t* offsets = nullptr;
+  std::vector<char> names;
+  std::vector<uint64_t> name_off;
+  uint32_t n = 0;
+  int gpu = 0; // index into devices
+};
+
+template <class T>
+class Channel {
+public:
+  void push(T v) { { std::lock_guard<std::mutex> l(m_); q_.push_back(v); } cv_.notify_one(); }
+  bool pop(T& v)
+  {
+    std::unique_lock<std::mutex> l(m_);
+    cv_.wait(l, [&] { return !q_.empty() || closed_; });
+    if (q_.empty()) return false;
+    v = q_.front();
+    q_.pop_front();
+    return true;
+  }
+  void close() { { std::lock_guard<std::mutex> l(m_); closed_ = true; } cv_.notify_all(); }
+
+private:
+  std::mutex m_;
+  std::condition_variable cv_;
+  std::deque<T> q_;
+  bool closed_ = false;
+};
+
+void check(int rc) { if (rc != KREPP_OK) error_exit(krepp_last_error()); }
+
+} // namespace
+
+int main(int argc, char** argv)
+{
+  fprintf(stderr, "krepp_b200 version: v0.8.3+b200\n");
+  const Options o = parse(argc, argv);
+  std::string invocation;
+  for (int i = 0; i < argc; ++i) invocation += std::string(argv[i]) + (i + 1 < argc ? " " : "");
+  const auto tstart = std::chrono::system_clock::now();
+  { std::time_t t = std::chrono::system_clock::to_time_t(tstart); fprintf(stderr, "Invocation: %s\n%s", invocation.c_str(), std::ctime(&t)); }
+
+  const bool place = o.sub == "place";
+  krepp_params_t p;
+  krepp_params_default(&p, place ? 1 : 0);
+  p.hdist_th = o.hdist_th; p.chisq = o.chisq; p.dist_max = o.dist_max; p.tau = o.tau;
+  p.no_filter = o.filter ? 0 : 1; p.multi = o.multi ? 1 : 0; p.summarize = o.summarize ? 1 : 0;
+  if (place && o.hdist_th < o.tau) { // ref src/krepp.hpp:192-199
+    fprintf(stderr, "The threshold tau must be less than HD threshold --hdist-th!\n");
+    error_exit("Invalid configuration!");
+  }
+
+  fprintf(stderr, place ? "Loading the index and the backbone tree...\n" : "Loading the index and initializing...\n");
+  std::vector<krepp_index_t*> index(o.devices.size(), nullptr);
+  { // one replica of the index image per GPU, uploaded concurrently
+    std::vector<std::thread> th;
+    std::vector<std::string> err(o.devices.size());
+    for (size_t g = 0; g < o.devices.size(); ++g)
+      th.emplace_back([&, g] { if (krepp_index_open(o.index_dir.c_str(), o.devices[g], &index[g]) != KREPP_OK) err[g] = krepp_last_error(); });
+    for (auto& t : th) t.join();
+    for (auto& e : err) if (!e.empty()) error_exit(e);
+  }
+  krepp_index_info_t info;
+  check(krepp_index_info(index[0], &info));
+
+  FILE* out = stdout;
+  if (!o.output_path.empty()) { out = fopen(o.output_path.c_str(), "wb"); if (!out) error_exit("Failed to open the output file at " + o.output_path); }
+  std::vector<char> obuf(8 << 20);
+  setvbuf(out, obuf.data(), _IOFBF, obuf.size());
+
+  std::vector<Slot> slots(o.devices.size() * o.slots_per_gpu);
+  Channel<Slot*> free_q, busy_q;
+  for (size_t i = 0; i < slots.size(); ++i) {
+    Slot& s = slots[i];
+    s.gpu = (int)(i % o.devices.size());
+    check(krepp_batch_create(index[s.gpu], &p, o.batch_reads, o.batch_bases, &s.batch));
+    check(krepp_batch_host_buffers(s.batch, &s.bases, &s.offsets));
+    s.names.resize(64ull * o.batch_reads);
+    s.name_off.resize(o.batch_reads);
+    free_q.push(&s);
+  }
+
+  fprintf(stderr, place ? "Placing given sequences on the backbone tree...\n" : "Estimating distances between given sequences and references...\n");
+  const auto tquery = std::chrono::system_clock::now();
+  std::vector<char> text(1 << 20);
+  auto emit = [&](size_t n) { if (n && fwrite(text.data(), 1, n, out) != n) error_exit("Failed to write the output"); };
+  { // header / begin_jplace
+    size_t n = krepp_format_header(index[0], &p, o.tabular, invocation.c_str(), text.data(), text.size());
+    if (n > text.size()) { text.resize(n); n = krepp_format_header(index[0], &p, o.tabular, invocation.c_str(), text.data(), text.size()); }
+    emit(n);
+  }
+
+  uint64_t total_queries = 0;
+  std::vector<double> wcount(info.nnodes + 1, 0.0);
+
+  std::thread consumer([&] {
+    int has_previous = 0;
+    const uint32_t T = o.num_threads;
+    std::vector<std::vector<char>> part(T, std::vector<char>(1 << 20));
+    std::vector<size_t> part_len(T, 0);
+    std::vector<std::vector<double>> part_w(T);
+    Slot* s = nullptr;
+    while (busy_q.pop(s)) {
+      krepp_results_t res;
+      check(krepp_batch_wait(s->batch, &res));
+      // split the batch's reads over T workers; every worker formats its range into its own buffer
+      auto work = [&](uint32_t t) {
+        const uint32_t lo = (uint32_t)((uint64_t)res.n_reads * t / T), hi = (uint32_t)((uint64_t)res.n_reads * (t + 1) / T);
+        krepp_results_t sub = res;
+        sub.reads = res.reads + lo;
+        sub.n_reads = hi - lo;
+        double* w = nullptr;
+        if (p.summarize) { part_w[t].assign(info.nnodes + 1, 0.0); w = part_w[t].data(); }
+        for (;;) {
+          int prev = 0;
+          const size_t n = place ? krepp_format_place(index[0], &p, &sub, s->names.data(), s->name_off.data() + lo, o.tabular, &prev, w, part[t].data(), part[t].size())
+                                 : krepp_format_dist(index[0], &p, &sub, s->names.data(), s->name_off.data() + lo, w, part[t].data(), part[t].size());
+          if (n <= part[t].size()) { part_len[t] = n; break; }
+          part[t].resize(n + n / 4);
+          if (w) part_w[t].assign(info.nnodes + 1, 0.0);
+        }
+      };
+      if (T == 1) work(0);
+      else { std::vector<std::thread> th; for (uint32_t t = 0; t < T; ++t) th.emplace_back(work, t); for (auto& x : th) x.join(); }
+      const bool jplace = place && !o.tabular && !p.summarize;
+      for (uint32_t t = 0; t < T; ++t) {
+        if (p.summarize) { for (uint32_t se = 0; se <= info.nnodes; ++se) wcount[se] += part_w[t][se]; continue; }
+        if (!part_len[t]) continue;
+        if (jplace && has_previous) fwrite(",\n", 1, 2, out); // ref src/krepp.cpp:476-481
+        if (fwrite(part[t].data(), 1, part_len[t], out) != part_len[t]) error_exit("Failed to write the output");
+        has_previous = 1;
+      }
+      free_q.push(s);
+    }
+  });
+
+  krepp_reader_t* reader = nullptr;
+  check(krepp_reader_open(o.query.c_str(), &reader));
+  for (;;) {
+    Slot* s = nullptr;
+    free_q.pop(s);
+    int eof = 0;
+    check(krepp_reader_next(reader, s->bases, o.batch_bases, s->offsets, o.batch_reads, s->names.data(), s->names.size(), s->name_off.data(), &s->n, &eof));
+    if (s->n) {
+      total_queries += s->n;
+      check(krepp_batch_submit(s->batch, s->bases, s->offsets, s->n));
+      busy_q.push(s);
+    } else free_q.push(s);
+    if (eof) break;
+  }
+  krepp_reader_close(reader);
+  busy_q.close();
+  consumer.join();
+
+  { // --summarize table / end_jplace
+    size_t n = krepp_format_footer(index[0], &p, o.tabular, wcount.data(), total_queries, invocation.c_str(), text.data(), text.size());
+    if (n > text.size()) { text.resize(n); n = krepp_format_footer(index[0], &p, o.tabular, wcount.data(), total_queries, invocation.c_str(), text.data(), text.size()); }
+    emit(n);
+  }
+  fflush(out);
+  if (out != stdout) fclose(out);
+  const std::chrono::duration<float> es = std::chrono::system_clock::now() - tquery;
+  fprintf(stderr, place ? "Done placing queries, elapsed: %g sec\n" : "Done estimating distances, elapsed: %g sec\n", es.count());
+  fprintf(stderr, "Total number of sequences queried: %llu\n", (unsigned long long)total_queries);
+  for (Slot& s : slots) krepp_batch_destroy(s.batch);
+  for (krepp_index_t* ix : index) krepp_index_close(ix);
+  { std::time_t t = std::chrono::system_clock::to_time_t(std::chrono::system_clock::now()); fprintf(stderr, "%s", std::ctime(&t)); }
+  return 0;
+}

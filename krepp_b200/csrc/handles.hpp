@@ -1,0 +1,19 @@
+// The opaque index handle of include/krepp_b200.h, shared by the GPU layer (api.cu) and the host I/O layer (host_io.cpp).
+#pragma once
+#include "device.cuh"
+#include "index_image.hpp"
+
+#include <vector>
+
+struct krepp_index {
+  krepp::HostIndex host;
+  krepp::DevIndex dev{};
+  int device = 0, sms = 0, resident_warps = 0, group = 4;
+  uint64_t device_bytes = 0;
+  std::vector<void*> allocs;
+};
+
+namespace krepp {
+// sets the thread-local krepp_last_error() text and returns `code`
+int set_error(int code, const char* fmt, ...);
+}

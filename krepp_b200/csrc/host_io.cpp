@@ -1,0 +1,430 @@
+// host_io.cpp -- the host steps either side of the GPU path, behind the same C ABI (include/krepp_b200.h):
+//   * FASTA/FASTQ batch reader with the record framing of kseq_read (ref src/kseq.h:177-216) as driven by
+//     QSeq::read_next_batch (ref src/rqseq.cpp:180-197), parsing straight into a batch slot's pinned buffers;
+//   * text formatting of the result structs: report_distances (ref src/query.cpp:158-196), report_placement
+//     (ref src/query.cpp:218-333, text and --no-multi / --summarize selection only; all arithmetic is done on the GPU),
+//     headers and jplace framing (ref src/krepp.cpp:311-319,396-432).
+// Pure host code; nothing here touches the device.
+#include "../../include/krepp_b200.h"
+
+#include "handles.hpp"
+
+#include <zlib.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace krepp;
+
+#define KREPP_VERSION_STRING "v0.8.3+b200"
+
+// ------------------------------------------------------------------------------------------------ reader
+
+namespace {
+
+// byte classes inside a sequence block (ref src/kseq.h:193-201): 0 dropped (not isgraph), 1 sequence character,
+// 2 '>' or '@' (next header), 3 '+' (quality block follows)
+struct ByteClass {
+  uint8_t seq[256];
+  uint8_t space[256];
+  ByteClass()
+  {
+    for (int c = 0; c < 256; ++c) {
+      seq[c] = (c > 32 && c < 127) ? 1 : 0;
+      space[c] = (c == ' ' || (c >= 9 && c <= 13)) ? 1 : 0;
+    }
+    seq[(int)'>'] = seq[(int)'@'] = 2;
+    seq[(int)'+'] = 3;
+  }
+};
+const ByteClass kClass;
+
+enum class St { Seek, Name, Comment, Seq, Plus, Qual, QualTail, Done };
+
+} // namespace
+
+struct krepp_reader {
+  gzFile f = nullptr;
+  std::vector<unsigned char> buf;
+  size_t at = 0, end = 0;
+  bool eof = false;
+  St st = St::Seek;
+  std::string name, seq;   // the record being parsed
+  uint64_t qual_left = 0;
+  bool fresh = false;        // name/seq still hold the record returned last; cleared when parsing resumes
+  bool have_pending = false; // a complete record that did not fit the previous batch
+  std::string pend_name, pend_seq;
+};
+
+namespace {
+
+bool refill(krepp_reader* r)
+{
+  if (r->eof) return false;
+  const int n = gzread(r->f, r->buf.data(), (unsigned)r->buf.size());
+  r->at = 0;
+  r->end = n > 0 ? (size_t)n : 0;
+  if (n < (int)r->buf.size()) r->eof = true;
+  return r->end > 0;
+}
+
+// Advances the state machine until one complete record sits in r->name / r->seq (returns true) or the input ends.
+bool next_record(krepp_reader* r)
+{
+  if (r->fresh) { r->name.clear(); r->seq.clear(); r->fresh = false; }
+  for (;;) {
+    if (r->at >= r->end && !refill(r)) {
+      // end of input: a FASTA record in progress is complete, a FASTQ record is complete only when all of its quality
+      // characters were seen (ref src/kseq.h:203-213: -2 "truncated quality string" drops the record)
+      const St s = r->st;
+      r->st = St::Done;
+      // a header cut short by EOF is still a record with an empty sequence, unless nothing followed '>' / '@'
+      // (ref src/kseq.h:189-191: ks_getuntil returns -1 only when the stream is already exhausted)
+      const bool rec = s == St::Seq || s == St::QualTail || (s == St::Qual && r->qual_left == 0) || s == St::Comment ||
+                       (s == St::Name && !r->name.empty());
+      r->fresh = rec;
+      return rec;
+    }
+    const unsigned char* p = r->buf.data() + r->at;
+    const unsigned char* e = r->buf.data() + r->end;
+    switch (r->st) {
+      case St::Seek: {
+        while (p < e && *p != '>' && *p != '@') ++p;
+        if (p < e) { ++p; r->st = St::Name; r->name.clear(); r->seq.clear(); }
+        break;
+      }
+      case St::Name: {
+        const unsigned char* b = p;
+        while (p < e && !kClass.space[*p]) ++p;
+        r->name.append(reinterpret_cast<const char*>(b), p - b);
+        if (p < e) { r->st = (*p == '\n') ? St::Seq : St::Comment; ++p; }
+        break;
+      }
+      case St::Comment: {
+        const void* nl = memchr(p, '\n', e - p);
+        if (nl) { p = static_cast<const unsigned char*>(nl) + 1; r->st = St::Seq; } else p = e;
+        break;
+      }
+      case St::Seq: {
+        // run of sequence characters: copy whole spans between bytes of another class
+        while (p < e) {
+          const unsigned char* b = p;
+          while (p < e && kClass.seq[*p] == 1) ++p;
+          if (p > b) r->seq.append(reinterpret_cast<const char*>(b), p - b);
+          if (p == e) break;
+          const uint8_t c = kClass.seq[*p];
+          ++p;
+          if (c == 2) { r->at = p - r->buf.data(); r->st = St::Name; r->fresh = true; return true; } // header char already consumed
+          if (c == 3) { r->st = St::Plus; break; }
+        }
+        break;
+      }
+      case St::Plus: {
+        const void* nl = memchr(p, '\n', e - p);
+        if (nl) { p = static_cast<const unsigned char*>(nl) + 1; r->st = St::Qual; r->qual_left = r->seq.size(); } else p = e;
+        break;
+      }
+      case St::Qual: {
+        while (p < e && r->qual_left) { if (*p >= 33 && *p <= 127) --r->qual_left; ++p; }
+        if (!r->qual_left) r->st = St::QualTail;
+        break;
+      }
+      case St::QualTail: { // kseq consumes one more character after the last quality character (ref src/kseq.h:208)
+        ++p;
+        r->at = p - r->buf.data();
+        r->st = St::Seek;
+        r->fresh = true;
+        return true;
+      }
+      case St::Done: return false;
+    }
+    r->at = p - r->buf.data();
+  }
+}
+
+} // namespace
+
+extern "C" int krepp_reader_open(const char* path, krepp_reader_t** out)
+{
+  if (!path || !out) return set_error(KREPP_ERR_ARG, "krepp_reader_open: null argument");
+  *out = nullptr;
+  gzFile f = gzopen(path, "rb");
+  if (!f) return set_error(KREPP_ERR_IO, "Failed to open the file at %s", path);
+  gzbuffer(f, 1 << 20);
+  auto* r = new krepp_reader;
+  r->f = f;
+  r->buf.resize(4 << 20);
+  *out = r;
+  return KREPP_OK;
+}
+
+extern "C" void krepp_reader_close(krepp_reader_t* r)
+{
+  if (!r) return;
+  if (r->f) gzclose(r->f);
+  delete r;
+}
+
+extern "C" int krepp_reader_next(krepp_reader_t* r, char* bases, uint64_t max_bases, uint64_t* offsets, uint32_t max_reads,
+                                 char* names, uint64_t max_name_bytes, uint64_t* name_offsets, uint32_t* n_reads, int* eof)
+{
+  if (!r || !bases || !offsets || !names || !name_offsets || !n_reads || !eof) return set_error(KREPP_ERR_ARG, "krepp_reader_next: null argument");
+  uint32_t n = 0;
+  uint64_t nb = 0, nn = 0;
+  offsets[0] = 0;
+  *eof = 0;
+  auto fits = [&](const std::string& nm, const std::string& sq) {
+    return n < max_reads && nb + sq.size() <= max_bases && nn + nm.size() + 1 <= max_name_bytes;
+  };
+  auto put = [&](const std::string& nm, const std::string& sq) {
+    memcpy(bases + nb, sq.data(), sq.size());
+    nb += sq.size();
+    name_offsets[n] = nn;
+    memcpy(names + nn, nm.c_str(), nm.size() + 1);
+    nn += nm.size() + 1;
+    offsets[++n] = nb;
+  };
+  if (r->have_pending) {
+    if (!fits(r->pend_name, r->pend_seq))
+      return set_error(KREPP_ERR_CAPACITY, "a single sequence of %zu bases (name of %zu bytes) does not fit the batch buffers", r->pend_seq.size(), r->pend_name.size());
+    put(r->pend_name, r->pend_seq);
+    r->have_pending = false;
+  }
+  for (;;) {
+    if (n >= max_reads) break;
+    if (!next_record(r)) { *eof = 1; break; }
+    if (!fits(r->name, r->seq)) {
+      if (n == 0) return set_error(KREPP_ERR_CAPACITY, "a single sequence of %zu bases (name of %zu bytes) does not fit the batch buffers", r->seq.size(), r->name.size());
+      r->pend_name.swap(r->name);
+      r->pend_seq.swap(r->seq);
+      r->have_pending = true;
+      break;
+    }
+    put(r->name, r->seq);
+  }
+  if (r->st == St::Done && !r->have_pending) *eof = 1;
+  *n_reads = n;
+  return KREPP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ formatting
+
+namespace {
+
+struct Out {
+  char* buf;
+  size_t cap, len = 0;
+  Out(char* b, size_t c) : buf(b), cap(b ? c : 0) {}
+  void put(const char* s, size_t n)
+  {
+    if (len + n <= cap) memcpy(buf + len, s, n);
+    len += n;
+  }
+  void put(const char* s) { put(s, strlen(s)); }
+  void put(const std::string& s) { put(s.data(), s.size()); }
+  void ch(char c) { if (len < cap) buf[len] = c; ++len; }
+  void u32(uint32_t v)
+  {
+    char t[12];
+    int n = 0;
+    do { t[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (n) ch(t[--n]);
+  }
+  // std::fixed << precision(5): the exact binary value rounded to 5 decimals.  Fast path: scale, split, and fall back
+  // to printf whenever the scaled value sits close to a rounding boundary (or is large / non-finite).
+  void fixed5(double v)
+  {
+    const double a = fabs(v);
+    if (a < 1000.0) {
+      const double s = a * 100000.0;
+      const double fl = floor(s);
+      const double fr = s - fl;
+      if (fabs(fr - 0.5) > 1e-6) {
+        uint64_t q = (uint64_t)fl + (fr > 0.5 ? 1 : 0);
+        const uint32_t ip = (uint32_t)(q / 100000), fp = (uint32_t)(q % 100000);
+        if (std::signbit(v)) ch('-');
+        u32(ip);
+        ch('.');
+        char t[5];
+        uint32_t x = fp;
+        for (int i = 4; i >= 0; --i) { t[i] = (char)('0' + x % 10); x /= 10; }
+        put(t, 5);
+        return;
+      }
+    }
+    char t[400];
+    const int n = snprintf(t, sizeof t, "%.5f", v);
+    put(t, (size_t)n);
+  }
+};
+
+inline const char* name_of(const char* names, const uint64_t* name_offsets, uint32_t i) { return names + name_offsets[i]; }
+
+// Selected records (node_to_minfo) of one read by ascending leaf se: records are stored as forward leaves by ascending
+// se, then reverse leaves by ascending se, and at most one of the two strands of a leaf is selected.
+template <class F>
+void for_selected(const krepp_results_t* res, const krepp_read_summary_t& s, F&& f)
+{
+  const krepp_record_t* rec = res->records;
+  uint32_t i = s.rec_begin, ie = s.rec_begin + s.rec_count;
+  uint32_t nf = 0;
+  while (i + nf < ie && rec[i + nf].strand == 0) ++nf;
+  uint32_t j = i + nf;
+  const uint32_t je = ie;
+  ie = i + nf;
+  while (i < ie || j < je) {
+    const uint32_t si = i < ie ? rec[i].leaf_se : 0xFFFFFFFFu, sj = j < je ? rec[j].leaf_se : 0xFFFFFFFFu;
+    uint32_t pick;
+    if (si < sj) pick = i++;
+    else if (sj < si) pick = j++;
+    else { pick = (rec[i].flags & KREPP_REC_SELECTED) ? i : j; ++i; ++j; }
+    if (rec[pick].flags & KREPP_REC_SELECTED) f(rec[pick]);
+  }
+}
+
+} // namespace
+
+extern "C" size_t krepp_format_header(const krepp_index_t* ix, const krepp_params_t* p, int tabular, const char* invocation, char* buf, size_t cap)
+{
+  if (!ix || !p) return 0;
+  Out o(buf, cap);
+  const std::string inv = invocation ? invocation : "";
+  if (!p->place) { // header_dreport (ref src/krepp.cpp:311-319)
+    o.put("# software: krepp\tversion: " KREPP_VERSION_STRING "\tinvocation :" + inv);
+    o.put(p->summarize ? "\nREFERENCE_NAME\tWEIGHTED_COUNT\tSEQUENCE_ABUNDANCE\n" : "\nSEQ_ID\tREFERENCE_NAME\tDIST\n");
+  } else if (p->summarize || tabular) { // header_preport (ref src/krepp.cpp:396-408)
+    o.put("# software: krepp\tversion: " KREPP_VERSION_STRING "\tinvocation :" + inv);
+    o.put("\n# ");
+    o.put(ix->host.tree.jplace_newick());
+    o.put(p->summarize ? "\nDISTAL_NODE\tEDGE_NUM\tWEIGHTED_COUNT\tSEQUENCE_ABUNDANCE\n" : "\nSEQ_ID\tDISTAL_NODE\tEDGE_NUM\tLWR\tDIST\n");
+  } else { // begin_jplace (ref src/krepp.cpp:426-432)
+    o.put("{\n\t\"version\" : 3,\n\t\"fields\" : [\"edge_num\", \"pendant_length\", \"distal_length\", \"likelihood\", \"like_weight_ratio\", \"distance\"],\n\t\"placements\" : [\n");
+  }
+  return o.len;
+}
+
+extern "C" size_t krepp_format_dist(const krepp_index_t* ix, const krepp_params_t* p, const krepp_results_t* res, const char* names,
+                                    const uint64_t* name_offsets, double* wcount, char* buf, size_t cap)
+{
+  if (!ix || !p || !res || !names || !name_offsets) return 0;
+  Out o(buf, cap);
+  const HostTree& t = ix->host.tree;
+  const bool has_max = !std::isnan(p->dist_max);
+  std::vector<uint32_t> keep;
+  for (uint32_t r = 0; r < res->n_reads; ++r) {
+    const krepp_read_summary_t& s = res->reads[r];
+    const char* id = name_of(names, name_offsets, r);
+    if (p->summarize) { // ref src/query.cpp:160-171
+      if (!wcount) continue;
+      keep.clear();
+      for_selected(res, s, [&](const krepp_record_t& rec) {
+        if (rec.chisq < p->chisq && (!has_max || rec.d_llh < p->dist_max)) keep.push_back(rec.leaf_se);
+      });
+      for (uint32_t se : keep) wcount[se] += 1.0 / (double)keep.size();
+      continue;
+    }
+    if (s.closest < 0 || (has_max && res->records[s.closest].d_llh > p->dist_max)) { // ref :173-176
+      o.put(id); o.put("\tNA\tNaN\n");
+      continue;
+    }
+    if (p->multi) {
+      for_selected(res, s, [&](const krepp_record_t& rec) {
+        if (!p->no_filter && !(rec.chisq < p->chisq)) return;
+        if (has_max && !(rec.d_llh < p->dist_max)) return;
+        o.put(id); o.ch('\t'); o.put(t.node_name(rec.leaf_se, false)); o.ch('\t'); o.fixed5(rec.d_llh); o.ch('\n');
+      });
+    } else {
+      const krepp_record_t& rec = res->records[s.closest];
+      o.put(id); o.ch('\t'); o.put(t.node_name(rec.leaf_se, false)); o.ch('\t'); o.fixed5(rec.d_llh); o.ch('\n');
+    }
+  }
+  return o.len;
+}
+
+extern "C" size_t krepp_format_place(const krepp_index_t* ix, const krepp_params_t* p, const krepp_results_t* res, const char* names,
+                                     const uint64_t* name_offsets, int tabular, int* has_previous, double* wcount, char* buf, size_t cap)
+{
+  if (!ix || !p || !res || !names || !name_offsets) return 0;
+  Out o(buf, cap);
+  const HostTree& t = ix->host.tree;
+  int prev = has_previous ? *has_previous : 0;
+  auto jplace_row = [&](const krepp_placement_t& q) { // PP_JPLACE_FIELDS (ref src/query.hpp:202-204)
+    o.ch('['); o.u32(q.se - 1); o.put(", "); o.fixed5(q.pendant); o.put(", "); o.fixed5(q.distal); o.put(", "); o.fixed5(q.loglik);
+    o.put(", "); o.fixed5(q.lwr); o.put(", "); o.fixed5(q.d_llh); o.ch(']');
+  };
+  auto tab_row = [&](const char* id, const krepp_placement_t& q) { // PP_TABULAR_FIELDS (ref src/query.hpp:206)
+    o.put(id); o.ch('\t'); o.put(t.node_name(q.se, true)); o.ch('\t'); o.u32(q.se - 1); o.ch('\t'); o.fixed5(q.lwr); o.ch('\t'); o.fixed5(q.d_llh); o.ch('\n');
+  };
+  for (uint32_t r = 0; r < res->n_reads; ++r) {
+    const krepp_read_summary_t& s = res->reads[r];
+    if (!s.place_count) continue; // report_placement returned false (ref src/query.cpp:220-222)
+    const char* id = name_of(names, name_offsets, r);
+    const krepp_placement_t* q = res->placements + s.place_begin;
+    uint32_t nsel = 0;
+    for_selected(res, s, [&](const krepp_record_t&) { ++nsel; });
+    const bool text = !tabular && !p->summarize;
+    if (text) {
+      if (prev) o.put(",\n");
+      o.put("\t\t\t{\"n\" : [\""); o.put(id); o.put("\"], \"p\" : [");
+      prev = 1;
+    }
+    if (nsel == 1) { // single reference: the closest itself (ref src/query.cpp:231-241)
+      if (p->summarize) { if (wcount) wcount[q[0].se] += 1.0; }
+      else if (tabular) tab_row(id, q[0]);
+      else { jplace_row(q[0]); o.put("]}"); }
+      continue;
+    }
+    if (p->multi) { // ref src/query.cpp:293-310
+      for (uint32_t i = 0; i < s.place_count; ++i) {
+        if (p->summarize) { if (wcount) wcount[q[i].se] += 1.0 / (double)s.place_count; }
+        else if (tabular) tab_row(id, q[i]);
+        else { if (i) o.ch(','); o.put("\n\t\t\t\t"); jplace_row(q[i]); }
+      }
+      if (text) o.put("]\n\t\t\t}");
+    } else { // largest clade, then smallest distance (ref src/query.cpp:311-330; remaining ties: highest se)
+      uint32_t best = 0;
+      for (uint32_t i = 1; i < s.place_count; ++i) {
+        const uint32_t cb = t.card[q[best].se], ci = t.card[q[i].se];
+        if (ci > cb || (ci == cb && q[i].d_llh <= q[best].d_llh)) best = i;
+      }
+      if (p->summarize) { if (wcount) wcount[q[best].se] += 1.0; }
+      else if (tabular) tab_row(id, q[best]);
+      else { jplace_row(q[best]); o.put("]}"); }
+    }
+  }
+  if (has_previous) *has_previous = prev;
+  return o.len;
+}
+
+extern "C" size_t krepp_format_footer(const krepp_index_t* ix, const krepp_params_t* p, int tabular, const double* wcount, uint64_t total_queries,
+                                      const char* invocation, char* buf, size_t cap)
+{
+  if (!ix || !p) return 0;
+  Out o(buf, cap);
+  const HostTree& t = ix->host.tree;
+  if (p->summarize) { // ref src/krepp.cpp:385-392,492-497 (rows by ascending se; the reference's order is unspecified)
+    if (!wcount) return 0;
+    double total = 0;
+    for (uint32_t se = 1; se <= t.nnodes; ++se) total += wcount[se];
+    for (uint32_t se = 1; se <= t.nnodes; ++se) {
+      if (wcount[se] == 0) continue;
+      if (p->place) { o.put(t.node_name(se, true)); o.ch('\t'); o.u32(se - 1); }
+      else o.put(t.node_name(se, false));
+      o.ch('\t'); o.fixed5(wcount[se]); o.ch('\t'); o.fixed5(wcount[se] / total); o.ch('\n');
+    }
+  } else if (p->place && !tabular) { // end_jplace (ref src/krepp.cpp:410-424)
+    o.put("],\n\t\"metadata\" : {\n\t\t\"software\" : \"krepp\",\n\t\t\"version\" : \"" KREPP_VERSION_STRING "\",\n"
+          "\t\t\"repository\" : \"https://github.com/bo1929/krepp\",\n\t\t\"num_queries\" : \"");
+    o.put(std::to_string(total_queries));
+    o.put("\",\n\t\t\"invocation\" : \"");
+    o.put(invocation ? invocation : "");
+    o.put("\"\n\t},\n\t\"tree\" : \"");
+    o.put(t.jplace_newick());
+    o.put("\"\n}");
+  }
+  return o.len;
+}

@@ -169,3 +169,75 @@ def test_device_resident_input_and_idempotence(env):
         assert np.array_equal(key1[1]["d_llh"], rec2["d_llh"])
         for f in ("onmers", "wn", "hdist_filt", "rec_count"):
             assert np.array_equal(key1[0][f], r2["reads"][f]), f
+
+
+# ---------------------------------------------------------------------------------------------------- the CLI (C++ host)
+
+def _cli(*args):
+    import subprocess
+    exe = os.path.join(conftest.ROOT, "krepp_b200", "_build", "krepp_b200")
+    return subprocess.run([exe, *args], capture_output=True, text=True)
+
+
+def test_cli_dist_golden_small(tmp_path):
+    """`krepp_b200 dist` (C++ host over the C ABI: reader -> GPU -> formatter) against the reference's own TSV for the
+    committed fixture; tiny batches, several formatter threads and gzip input must not change a byte."""
+    import gzip
+    small = os.path.join(conftest.GOLDEN_DIR, "small")
+    with open(os.path.join(small, "ref_dist.tsv")) as f:
+        ref = sorted(f.read().splitlines())
+    r = _cli("dist", "-i", os.path.join(small, "index"), "-q", os.path.join(small, "reads.fq"))
+    assert r.returncode == 0, r.stderr
+    body = r.stdout.splitlines()
+    assert body[0].startswith("# software: krepp") and body[1] == "SEQ_ID\tREFERENCE_NAME\tDIST"
+    assert sorted(body[2:]) == ref
+    assert "Total number of sequences queried: 236" in r.stderr
+    gz = tmp_path / "reads.fq.gz"
+    with open(os.path.join(small, "reads.fq"), "rb") as f, gzip.open(gz, "wb") as g:
+        g.write(f.read())
+    out = tmp_path / "out.tsv"
+    r2 = _cli("--num-threads", "3", "dist", "-i", os.path.join(small, "index"), "-q", str(gz), "-o", str(out), "--batch-reads", "17", "--slots", "2")
+    assert r2.returncode == 0, r2.stderr
+    assert out.read_text().splitlines()[2:] == body[2:]  # same rows in the same (input) order
+
+
+def test_cli_place_golden_small(tmp_path):
+    import json
+    import oracle_lib as O
+    small = os.path.join(conftest.GOLDEN_DIR, "small")
+    r = _cli("place", "-i", os.path.join(small, "index"), "-q", os.path.join(small, "reads.fq"), "--batch-reads", "50")
+    assert r.returncode == 0, r.stderr
+    jp = json.loads(r.stdout)
+    with open(os.path.join(small, "ref_place.jplace")) as f:
+        ref = json.load(f)
+    assert jp["tree"] == ref["tree"] and jp["fields"] == ref["fields"] and jp["metadata"]["num_queries"] == "236"
+    o = O.OracleIndex(os.path.join(small, "index"))
+    names, reads = fastq_reads(os.path.join(small, "reads.fq"))
+    p = O.default_params(want_place=1, no_filter=0)
+    mine = {pl["n"][0]: pl["p"] for pl in jp["placements"]}
+    nrows = 0
+    for name, s in zip(names, reads):
+        want = o.query(s, p)["place"]
+        assert (name in mine) == bool(want), name
+        if want:
+            got = mine[name]
+            assert [row[0] for row in got] == [q["edge"] for q in want], name
+            for row, q in zip(got, want):
+                for a, b in zip(row[1:], (q["pendant"], q["distal"], -q["v"], q["lwr"], q["d"])):
+                    assert abs(a - b) <= 1.001e-5 + 1e-5 * abs(b), (name, row, q)
+            nrows += len(got)
+    assert nrows == 408
+    t = _cli("place", "-i", os.path.join(small, "index"), "-q", os.path.join(small, "reads.fq"), "--tabular")
+    assert t.returncode == 0 and len(t.stdout.splitlines()) == 408 + 3
+    bad = _cli("place", "-i", os.path.join(small, "index"), "-q", os.path.join(small, "reads.fq"), "--tau", "5")
+    assert bad.returncode != 0 and "Invalid configuration" in bad.stderr
+
+
+@needs_ref
+def test_cli_dist_equals_reference_cli_on_toy(env):
+    import subprocess
+    q = os.path.join(TOY_DIR, "query_toy.fq")
+    ref = subprocess.run([os.path.join(conftest.REF_DIR, "krepp"), "dist", "-i", env["dir"], "-q", q], capture_output=True, text=True, check=True).stdout.splitlines()[2:]
+    r = _cli("dist", "-i", env["dir"], "-q", q)
+    assert r.returncode == 0, r.stderr
+    assert sorted(r.stdout.splitlines()[2:]) == sorted(ref)
