@@ -498,12 +498,12 @@ int krepp_batch_wait(krepp_batch_t* b, krepp_results_t* out)
     // a result buffer was too small: grow it to what the kernels asked for and run the batch again
     if (attempt >= 4) return fail(KREPP_ERR_CAPACITY, "result buffer overflow persists");
     if (b->h_counters[2] & kErrRecOverflow) {
-      const uint64_t want = std::max<uint64_t>(2ull * b->h_counters[0], 2ull * b->rec_cap);
+      const uint64_t want = std::max<uint64_t>((uint64_t)b->h_counters[0] + b->h_counters[0] / 4, (uint64_t)b->rec_cap + 4096); // exact demand + 25 %
       if (want > 0x7FFFFFFFull) return fail(KREPP_ERR_CAPACITY, "batch produces too many records; submit fewer reads per batch");
       if (int rc = alloc_records(b, (uint32_t)want)) return rc;
     }
     if (b->h_counters[2] & kErrPlaceOverflow) {
-      const uint64_t want = std::max<uint64_t>(2ull * b->h_counters[3], 2ull * b->place_cap);
+      const uint64_t want = std::max<uint64_t>((uint64_t)b->h_counters[3] + b->h_counters[3] / 4, (uint64_t)b->place_cap + 4096);
       if (want > 0x7FFFFFFFull) return fail(KREPP_ERR_CAPACITY, "batch produces too many placements; submit fewer reads per batch");
       if (int rc = alloc_placements(b, (uint32_t)want)) return rc;
     }
