@@ -92,6 +92,7 @@ static std::vector<uint4> build_lut(const HostIndex& h)
 __global__ void __launch_bounds__(128) finalize_kernel(const SolveArgs a, krepp_record_t* out_rec, krepp_read_summary_t* out_read,
                                                         const uint32_t* wn, const uint32_t* place_begin, const uint32_t* place_count)
 {
+  if (a.counters[2] & (kErrRecOverflow | kErrStackOverflow)) return; // incomplete records: the host re-runs the batch
   const uint32_t n = a.counters[0] < a.n_records ? a.counters[0] : a.n_records;
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
   for (uint32_t i = tid; i < n; i += nth) {
@@ -148,7 +149,7 @@ struct krepp_batch {
   uint32_t *d_rec_read = nullptr, *d_rec_slot = nullptr, *d_rec_hist = nullptr, *d_rec_flags = nullptr, *d_rec_match = nullptr, *d_rec_hdmin = nullptr;
   double *d_rec_d = nullptr, *d_rec_v = nullptr, *d_rec_chisq = nullptr;
   uint32_t* d_counters = nullptr; unsigned long long* d_stats = nullptr;
-  uint32_t *d_acc = nullptr, *d_bitmap = nullptr, *d_marker = nullptr, *d_stack = nullptr;
+  uint32_t *d_acc = nullptr, *d_bitmap = nullptr, *d_marker = nullptr, *d_stack = nullptr, *d_tagctr = nullptr;
   uint32_t stack_cap = 0;
   krepp_record_t* d_out_rec = nullptr; krepp_read_summary_t* d_out_read = nullptr;
   // pinned host results
@@ -201,6 +202,12 @@ int krepp_index_open(const char* index_dir, int device, krepp_index_t** out)
   if (e == cudaSuccess) e = upload(h.inc32, &d.inc32, ix->allocs, ix->device_bytes, 1);
   if (e == cudaSuccess) e = upload(h.pse, reinterpret_cast<const uint64_t**>(&d.pse), ix->allocs, ix->device_bytes);
   if (e == cudaSuccess) e = upload(h.kind, &d.kind, ix->allocs, ix->device_bytes);
+  {
+    std::vector<uint32_t> cinfo(h.kind.size(), 0);
+    for (size_t se = 0; se < cinfo.size(); ++se)
+      cinfo[se] = h.kind[se] == 1 ? (0x80000000u | h.tree.leaf_rank[se]) : h.kind[se] == 2 ? 0x40000000u : 0u;
+    if (e == cudaSuccess) e = upload(cinfo, &d.cinfo, ix->allocs, ix->device_bytes);
+  }
   if (e == cudaSuccess) e = upload(h.rho, &d.rho, ix->allocs, ix->device_bytes);
   if (e == cudaSuccess) e = upload(h.tree.leaf_rank, &d.leaf_rank, ix->allocs, ix->device_bytes);
   if (e == cudaSuccess) e = upload(h.tree.leaf_se, &d.leaf_se, ix->allocs, ix->device_bytes);
@@ -219,16 +226,13 @@ int krepp_index_open(const char* index_dir, int device, krepp_index_t** out)
   d.m_shift = (h.m & (h.m - 1)) == 0 ? (uint32_t)__builtin_ctz(h.m) : 0xFFFFFFFFu;
   for (uint32_t i = 0; i < (uint32_t)kMaxResidues; ++i) d.res_numer[i] = i < h.m ? h.res_numer[i] : 0;
   d.local_expand = h.max_expand_depth + 2 <= 32 ? 1u : 0u;
-  ix->resident_warps = match_resident_warps(device, h.k);
-  { // scan group width (match.cu phase B).  Small buckets: every lane scans whole buckets on its own with 128-bit
-    // loads (G = 1).  Once a typical hit bucket spans several 128-byte lines, G lanes share one bucket so that a group
-    // reads one contiguous run per step.
+  { // scan strategy (match.cu phase B).  Small buckets: every lane scans whole buckets on its own with 128-bit loads.
+    // Once a typical hit bucket spans several 128-byte lines, buckets are streamed through shared memory by bulk copies.
     const double sb = h.size_biased_bucket; // entries in the bucket an indexed k-mer lands in
-    int g = 1;
-    if (sb > 24.0) { g = 4; while (g < 32 && 4.0 * g < sb) g *= 2; }
-    if (const char* env = getenv("KREPP_GROUP")) { const int v = atoi(env); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) g = v; }
-    ix->group = g;
+    ix->staged = sb > 24.0;
+    if (const char* env = getenv("KREPP_SCAN")) { if (!strcmp(env, "staged")) ix->staged = true; else if (!strcmp(env, "lane")) ix->staged = false; }
   }
+  ix->resident_warps = match_resident_warps(device, h.k, ix->staged);
   *out = ix;
   return KREPP_OK;
 }
@@ -356,6 +360,7 @@ int krepp_batch_create(krepp_index_t* ix, const krepp_params_t* p, uint32_t max_
   CU(cudaMalloc(&b->d_bitmap, 4 * warps * nbm)); CU(cudaMemset(b->d_bitmap, 0, 4 * warps * nbm));
   CU(cudaMalloc(&b->d_marker, 4 * warps * h.tree.nleaves)); CU(cudaMemset(b->d_marker, 0xFF, 4 * warps * h.tree.nleaves));
   CU(cudaMalloc(&b->d_stack, 4 * warps * b->stack_cap));
+  CU(cudaMalloc(&b->d_tagctr, 4 * warps)); CU(cudaMemset(b->d_tagctr, 0xFF, 4 * warps));
   const uint64_t want = std::max<uint64_t>(4ull * max_reads, 4096);
   if (int rc = alloc_records(b, (uint32_t)std::min<uint64_t>(want, 0x7FFFFFFFull))) return rc;
   if (p->place) {
@@ -379,7 +384,7 @@ void krepp_batch_destroy(krepp_batch_t* b)
   free_records(b);
   for (void* p : {(void*)b->d_bases, (void*)b->d_offsets, (void*)b->d_onmers, (void*)b->d_wn, (void*)b->d_hdfilt, (void*)b->d_rec_begin,
                   (void*)b->d_rec_count, (void*)b->d_closest, (void*)b->d_counters, (void*)b->d_stats, (void*)b->d_acc, (void*)b->d_bitmap,
-                  (void*)b->d_marker, (void*)b->d_stack, (void*)b->d_out_read, (void*)b->d_tap, (void*)b->d_tap_count, (void*)b->d_place_begin,
+                  (void*)b->d_marker, (void*)b->d_stack, (void*)b->d_tagctr, (void*)b->d_out_read, (void*)b->d_tap, (void*)b->d_tap_count, (void*)b->d_place_begin,
                   (void*)b->d_place_count, (void*)b->d_node_bitmap, (void*)b->d_node_list, (void*)b->d_node_cand, (void*)b->d_node_d, (void*)b->d_node_v,
                   (void*)b->d_node_chisq, (void*)b->d_place})
     if (p) cudaFree(p);
@@ -406,10 +411,10 @@ static int enqueue(krepp_batch* b)
   m.bases = b->in_bases; m.offsets = b->in_offsets; m.n_bases = b->n_bases; m.n_reads = b->n_reads; m.th = b->p.hdist_th;
   m.onmers = b->d_onmers; m.wn = b->d_wn; m.hdfilt = b->d_hdfilt; m.rec_begin = b->d_rec_begin; m.rec_count = b->d_rec_count;
   m.rec_read = b->d_rec_read; m.rec_slot = b->d_rec_slot; m.rec_hist = b->d_rec_hist; m.rec_cap = b->rec_cap; m.counters = b->d_counters;
-  m.acc = b->d_acc; m.bitmap = b->d_bitmap; m.marker = b->d_marker; m.stack = b->d_stack; m.stack_cap = b->stack_cap; m.stats = b->d_stats;
+  m.acc = b->d_acc; m.bitmap = b->d_bitmap; m.marker = b->d_marker; m.stack = b->d_stack; m.stack_cap = b->stack_cap; m.tagctr = b->d_tagctr; m.stats = b->d_stats;
   m.tap = b->d_tap; m.tap_count = b->d_tap_count; m.tap_cap = b->tap_cap;
   CU(cudaEventRecord(b->evm0, s));
-  CU(launch_match(ix->dev, m, ix->resident_warps, ix->group, b->d_tap != nullptr, s));
+  CU(launch_match(ix->dev, m, ix->resident_warps, ix->staged, b->d_tap != nullptr, s));
   CU(cudaEventRecord(b->evm1, s));
   SolveArgs sa{};
   sa.n_reads = b->n_reads; sa.th = b->p.hdist_th; sa.k = h.k; sa.h = h.h; sa.n_records = b->rec_cap; sa.counters = b->d_counters;

@@ -18,6 +18,7 @@ struct DevIndex {
                             //                                     ref FlatHT::inc_v   src/table.hpp:142
   const uint2* pse;         // nsubsets x (first, second)          ref CRecord::se_to_pse src/record.hpp:103
   const uint8_t* kind;      // nsubsets: 0 drop, 1 leaf, 2 expand  ref src/query.cpp:373-386
+  const uint32_t* cinfo;    // nsubsets: kind and leaf rank in one word: 0 drop, 0x80000000 | rank leaf, 0x40000000 expand
   const double* rho;        // by se, scaled                        ref CRecord::se_to_rho src/record.hpp:104
   const uint32_t* leaf_rank;// by se
   const uint32_t* leaf_se;  // by rank
@@ -54,8 +55,9 @@ struct MatchArgs {
   // per-warp scratch in HBM (sized by the host from the resident warp count)
   uint32_t* acc;              // [warps][2*nleaves*(th+1)] Hamming histograms being accumulated
   uint32_t* bitmap;           // [warps][ceil(2*nleaves/32)] touched (strand, leaf) slots
-  uint32_t* marker;           // [warps][nleaves] per-lookup min-hd markers (0xffffffff at rest)
+  uint32_t* marker;           // [warps][nleaves] per-lookup min-hd markers: tag << 5 | hd (0xffffffff at rest)
   uint32_t* stack;            // [warps][stack_cap] colour expansion stack
+  uint32_t* tagctr;           // [warps] marker tag counters (count down; persist across launches)
   uint32_t stack_cap;
   unsigned long long* stats;  // [0] algorithmic bytes, [1] lookups, [2] entries scanned
   // parity tap (stage 1)

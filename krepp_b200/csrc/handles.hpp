@@ -8,7 +8,8 @@
 struct krepp_index {
   krepp::HostIndex host;
   krepp::DevIndex dev{};
-  int device = 0, sms = 0, resident_warps = 0, group = 4;
+  int device = 0, sms = 0, resident_warps = 0;
+  bool staged = false; // match.cu phase B strategy: bucket streaming through shared memory (large buckets) or lane-per-bucket
   uint64_t device_bytes = 0;
   std::vector<void*> allocs;
 };

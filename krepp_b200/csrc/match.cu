@@ -10,17 +10,26 @@
 //   A2. the compacted list is completed with all lanes busy: residual q = pext(lr, mask_drop_lr) (ref src/lshf.cpp:64-69)
 //       and the bucket range [inc[off-1], inc[off]) (ref src/index.cpp:160-168, src/table.hpp:121-136); all range loads
 //       of a tile are in flight together; empty buckets are dropped from the list.
-//   B.  groups of G lanes (G chosen by the host from the index's bucket occupancy) pull lookups from the list and scan
-//       their buckets G entries per step with XOR/OR/popc (ref src/common.hpp:175, src/query.cpp:361-368); consecutive
-//       lanes read consecutive 8-byte entries.  Hits expand their colour through the se->(se,se) DAG to leaves on the
-//       device (ref src/query.cpp:369-387) and bump the per-(strand, leaf) Hamming histogram (ref src/query.hpp:153-176).
+//   B.  bucket scans with XOR/OR/popc (ref src/common.hpp:175, src/query.cpp:361-368), two strategies chosen by the
+//       host from the index's bucket occupancy:
+//       * small buckets (toy index): every lane pulls whole lookups from the list and scans its bucket with 128-bit
+//         loads;
+//       * large buckets (1,000-genome index, ~100 entries = ~800 contiguous bytes per lookup): the buckets of the
+//         lookup list are streamed through a per-warp shared-memory ring by 1-D bulk copies (cp.async.bulk, completion
+//         on an mbarrier per ring slot), several lookups ahead of the scan, so that each warp keeps kilobytes of HBM
+//         reads in flight instead of one dependent load; lanes then scan the staged entries out of shared memory.
+//       Hits expand their colour through the se->(se,se) DAG to leaves on the device (ref src/query.cpp:369-387) and
+//       bump the per-(strand, leaf) Hamming histogram (ref src/query.hpp:153-176).
 //
 // The reference's Minfo::update_match keeps, per (strand, leaf, position), the MINIMUM Hamming distance over all
 // matching entries.  All entries that can match one (read, strand, position) live in one bucket, so that minimum is
-// formed inside a single lookup: a lookup with one hit entry commits directly, a lookup with several hit entries goes
-// through a per-warp marker array (atomicMin, then commit-and-clear), which makes the result independent of the order
-// in which lanes run.  Histograms live in a per-warp accumulator and are emitted as records
-// (read, strand<<31|leaf_se, hist[0..th]) in (strand, leaf) order when the read is finished.
+// formed inside a single lookup.  A lookup with one hit entry commits directly.  Otherwise every lookup gets a tag
+// (a per-warp counter that only decreases) and each leaf reached does atomicMin(marker[leaf], tag << 5 | hd): the old
+// value tells whether this is the leaf's first hit in this lookup (histogram[hd] += 1) or an improvement over an
+// earlier, larger distance (histogram[old] -= 1, histogram[hd] += 1).  The updates telescope to exactly one count at
+// the minimum whatever order the lanes run in, with one pass and no reset of the marker array.  Histograms live in a
+// per-warp accumulator and are emitted as records (read, strand<<31|leaf_se, hist[0..th]) in (strand, leaf) order when
+// the read is finished.
 #include "device.cuh"
 #include "solve.cuh"
 
@@ -32,6 +41,11 @@ constexpr int kTileWords = 12;                 // 16 bases per 32-bit word -> 19
 constexpr int kLocalStack = 32;
 constexpr uint32_t kClaim = 4;                // reads claimed per atomic on the global work counter
 constexpr int kMaxLookups = 2 * kTileWindows;  // both strands
+constexpr int kChunk = 128;                    // staged path: bucket entries per ring slot (4 per lane)
+constexpr int kSlotEntries = kChunk + 2;       // + 16-byte alignment slack at either end of a chunk
+constexpr int kStages = 6;                     // ring slots per warp: up to ~6 kB of bucket reads in flight per warp
+constexpr uint32_t kTagStart = 0x07FFFFFEu;    // marker tags count down from here; 0x07FFFFFF is the rest value's tag
+constexpr uint32_t kInfoLeaf = 0x80000000u, kInfoExpand = 0x40000000u; // DevIndex::cinfo
 
 struct WarpSmem {
   uint32_t lk_a[kMaxLookups];  // A1: row offset | strand<<31; A2: first entry of the bucket
@@ -41,10 +55,15 @@ struct WarpSmem {
   uint32_t valid[kTileWords / 2 + 1];
   uint32_t cursor;
 };
+struct __align__(16) WarpStage {              // staged path only
+  unsigned long long bar[kStages];            // one mbarrier per ring slot
+  uint2 ent[kStages][kSlotEntries];           // slot stride 1040 B = 65 x 16
+};
 // LUT layout: [byte of the k-mer word][byte value] -> {rix fwd, q fwd, rix rc, q rc} parts; 7 bytes cover k <= 28
 // lut_pext always reads the first seven byte tables, so at least seven are staged (all-zero past the k-mer's last byte)
 __host__ __device__ inline uint32_t lut_chunks(uint32_t k) { const uint32_t n = (2 * k + 7) / 8; return n < 7 ? 7 : n; }
-__host__ __device__ inline size_t smem_bytes(uint32_t k) { return lut_chunks(k) * 256 * sizeof(uint4) + kWarpsPerCta * sizeof(WarpSmem); }
+__host__ __device__ inline size_t stage_offset(uint32_t k) { return (lut_chunks(k) * 256 * sizeof(uint4) + kWarpsPerCta * sizeof(WarpSmem) + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t smem_bytes(uint32_t k, bool staged) { return staged ? stage_offset(k) + kWarpsPerCta * sizeof(WarpStage) : lut_chunks(k) * 256 * sizeof(uint4) + kWarpsPerCta * sizeof(WarpSmem); }
 
 __device__ __forceinline__ void encode4(uint32_t u, uint32_t& code8, uint32_t& valid4)
 {
@@ -79,6 +98,27 @@ __device__ __forceinline__ uint4 lut_pext(const uint4* lut, uint32_t lo, uint32_
   return r;
 }
 
+// ---- mbarrier / bulk-copy primitives (PTX; SASS: SYNCS.*, UBLKCP)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+  asm volatile(
+    "{\n"
+    ".reg .pred p;\n"
+    "WAIT_%=:\n"
+    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+    "@p bra DONE_%=;\n"
+    "bra WAIT_%=;\n"
+    "DONE_%=:\n"
+    "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+
 struct WarpCtx {
   uint32_t* acc;      // [2*nleaves*(th+1)]
   uint32_t* bitmap;   // [ceil(2*nleaves/32)]
@@ -97,24 +137,36 @@ __device__ __forceinline__ void commit(const WarpCtx& w, uint32_t strand, uint32
   atomicOr(&w.bitmap[slot >> 5], 1u << (slot & 31));
 }
 
-// Lane-local colour expansion for a lookup with exactly one hit entry (no dedupe needed): depth-first with a small
-// private stack.  The host only enables it (ix.local_expand) when the deepest colour DAG of the index fits.
-__device__ __forceinline__ void expand_local(const DevIndex& ix, const WarpCtx& w, uint32_t se, uint32_t strand, uint32_t hd)
+// One leaf reached by a hit of the lookup tagged `tagbase` (= tag << 5): keeps the minimum distance per leaf and moves
+// the histogram count along with it (see the header).  Any number of lanes may run this concurrently.
+__device__ __forceinline__ void leaf_hit(const WarpCtx& w, uint32_t strand, uint32_t rank, uint32_t hd, uint32_t tagbase)
+{
+  const uint32_t old = atomicMin(&w.marker[rank], tagbase | hd);
+  if ((old ^ tagbase) >> 5) commit(w, strand, rank, hd);            // first hit of this leaf in this lookup
+  else if ((old & 31u) > hd) {                                        // a smaller distance than the one counted so far
+    uint32_t* h = w.acc + (size_t)(strand * w.nleaves + rank) * w.stride;
+    atomicSub(&h[old & 31u], 1u);
+    atomicAdd(&h[hd], 1u);
+  }
+}
+
+// Lane-local colour expansion: depth-first with a small private stack.  The host only enables it (ix.local_expand)
+// when the deepest colour DAG of the index fits.  tagbase == 0xffffffff: the lookup has this single hit, commit directly.
+__device__ __forceinline__ void expand_local(const DevIndex& ix, const WarpCtx& w, uint32_t se, uint32_t strand, uint32_t hd, uint32_t tagbase)
 {
   uint32_t st[kLocalStack];
   int sp = 0;
   st[sp++] = se;
   while (sp) {
     const uint32_t s = st[--sp];
-    const uint32_t kd = ix.kind[s];
-    if (kd == 1) commit(w, strand, ix.leaf_rank[s], hd);
-    else if (kd == 2) { const uint2 c = ix.pse[s]; st[sp++] = c.y; st[sp++] = c.x; }
+    const uint32_t ci = __ldg(&ix.cinfo[s]);
+    if (ci & kInfoLeaf) { if (tagbase == 0xFFFFFFFFu) commit(w, strand, ci & 0x3FFFFFFFu, hd); else leaf_hit(w, strand, ci & 0x3FFFFFFFu, hd, tagbase); }
+    else if (ci & kInfoExpand) { const uint2 c = __ldg(&ix.pse[s]); st[sp++] = c.y; st[sp++] = c.x; }
   }
 }
 
-// Warp-cooperative colour expansion over the per-warp HBM stack.  mode 0: commit every leaf; mode 1: marker[leaf] =
-// min(marker, hd); mode 2: commit marker value once per leaf and reset the marker.
-__device__ void expand_coop(const DevIndex& ix, const WarpCtx& w, uint32_t se, uint32_t strand, uint32_t hd, int mode)
+// Warp-cooperative colour expansion over the per-warp HBM stack, for colour DAGs too deep for the private stack.
+__device__ void expand_coop(const DevIndex& ix, const WarpCtx& w, uint32_t se, uint32_t strand, uint32_t hd, uint32_t tagbase)
 {
   const uint32_t lane = threadIdx.x & 31;
   uint32_t size = 1;
@@ -122,21 +174,17 @@ __device__ void expand_coop(const DevIndex& ix, const WarpCtx& w, uint32_t se, u
   __syncwarp();
   while (size) {
     const uint32_t take = min(size, 32u);
-    uint32_t s = 0, kd = 0;
-    if (lane < take) { s = w.stack[size - 1 - lane]; kd = ix.kind[s]; }
+    uint32_t s = 0, ci = 0;
+    if (lane < take) { s = w.stack[size - 1 - lane]; ci = __ldg(&ix.cinfo[s]); }
     __syncwarp();
     size -= take;
-    if (kd == 1) {
-      const uint32_t rank = ix.leaf_rank[s];
-      if (mode == 0) commit(w, strand, rank, hd);
-      else if (mode == 1) atomicMin(&w.marker[rank], hd);
-      else { const uint32_t old = atomicExch(&w.marker[rank], 0xFFFFFFFFu); if (old != 0xFFFFFFFFu) commit(w, strand, rank, old); }
-    }
-    const uint32_t ex = __ballot_sync(0xFFFFFFFFu, kd == 2);
+    if (ci & kInfoLeaf) { if (tagbase == 0xFFFFFFFFu) commit(w, strand, ci & 0x3FFFFFFFu, hd); else leaf_hit(w, strand, ci & 0x3FFFFFFFu, hd, tagbase); }
+    const bool expand = !(ci & kInfoLeaf) && (ci & kInfoExpand);
+    const uint32_t ex = __ballot_sync(0xFFFFFFFFu, expand);
     const uint32_t nex = __popc(ex);
     if (size + 2 * nex > w.stack_cap) { if (lane == 0) atomicOr(w.err, kErrStackOverflow); return; }
-    if (kd == 2) {
-      const uint2 c = ix.pse[s];
+    if (expand) {
+      const uint2 c = __ldg(&ix.pse[s]);
       const uint32_t at = size + 2 * __popc(ex & ((1u << lane) - 1));
       w.stack[at] = c.x; w.stack[at + 1] = c.y;
     }
@@ -145,50 +193,74 @@ __device__ void expand_coop(const DevIndex& ix, const WarpCtx& w, uint32_t se, u
   }
 }
 
-// Careful path for one lookup with several hit entries (or a colour too deep for the private stack): the whole warp
-// rescans the bucket, marks per-leaf minima, then commits them.
-__device__ void careful_lookup(const DevIndex& ix, const WarpCtx& w, uint32_t begin, uint32_t len, uint32_t q, uint32_t strand, uint32_t th)
+// Hits of one lookup held one per lane (hit lanes have hd <= th): expand all of them.
+__device__ __forceinline__ void expand_hits(const DevIndex& ix, const WarpCtx& w, bool hit, uint32_t se, uint32_t hd, uint32_t strand, uint32_t tagbase)
 {
-  const uint32_t lane = threadIdx.x & 31;
-  for (int pass = 1; pass <= 2; ++pass) {
-    for (uint32_t base = 0; base < len; base += 32) {
-      uint32_t se = 0, hd = 0xFFFFFFFFu;
-      if (base + lane < len) {
-        const uint2 e = ix.cmer[(size_t)begin + base + lane];
-        const uint32_t z = e.x ^ q;
-        hd = __popc((z | (z >> 16)) & 0xFFFFu);
-        se = e.y;
-      }
-      uint32_t hits = __ballot_sync(0xFFFFFFFFu, hd <= th);
-      while (hits) {
-        const int src = __ffs(hits) - 1;
-        hits &= hits - 1;
-        const uint32_t hse = __shfl_sync(0xFFFFFFFFu, se, src), hhd = __shfl_sync(0xFFFFFFFFu, hd, src);
-        expand_coop(ix, w, hse, strand, hhd, pass);
-      }
+  if (ix.local_expand) { if (hit) expand_local(ix, w, se, strand, hd, tagbase); }
+  else {
+    uint32_t hits = __ballot_sync(0xFFFFFFFFu, hit);
+    while (hits) {
+      const int src = __ffs(hits) - 1;
+      hits &= hits - 1;
+      expand_coop(ix, w, __shfl_sync(0xFFFFFFFFu, se, src), strand, __shfl_sync(0xFFFFFFFFu, hd, src), tagbase);
     }
   }
 }
 
-template <int G, bool TAP>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) match_kernel(const DevIndex ix, const MatchArgs a)
+// A fresh tag for the next lookup that needs the marker array (warp-uniform).  Tags only decrease, so a new lookup's
+// atomicMin always wins over whatever an older lookup left behind; when the counter runs out the markers are reset.
+__device__ __forceinline__ uint32_t next_tag(const WarpCtx& w, uint32_t& tag)
+{
+  if (tag <= 1u) {
+    for (uint32_t i = threadIdx.x & 31; i < w.nleaves; i += 32) w.marker[i] = 0xFFFFFFFFu;
+    __syncwarp();
+    tag = kTagStart;
+  } else --tag;
+  return tag << 5;
+}
+
+// Small-bucket path: one lookup with several hit entries (or a colour too deep for the private stack), rescanned by the
+// whole warp in a single pass.
+__device__ void careful_lookup(const DevIndex& ix, const WarpCtx& w, uint32_t begin, uint32_t len, uint32_t q, uint32_t strand, uint32_t th, uint32_t tagbase)
+{
+  const uint32_t lane = threadIdx.x & 31;
+  __syncwarp(); // lanes still expanding hits of the previous lookup must not meet this lookup's (smaller) tag in the markers
+  for (uint32_t base = 0; base < len; base += 32) {
+    uint32_t se = 0, hd = 0xFFFFFFFFu;
+    if (base + lane < len) {
+      const uint2 e = __ldg(&ix.cmer[(size_t)begin + base + lane]);
+      const uint32_t z = e.x ^ q;
+      hd = __popc((z | (z >> 16)) & 0xFFFFu);
+      se = e.y;
+    }
+    expand_hits(ix, w, hd <= th, se, hd, strand, tagbase);
+  }
+}
+
+template <bool STAGED, bool TAP>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, STAGED ? 2 : 4) match_kernel(const DevIndex ix, const MatchArgs a)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t nchunks = lut_chunks(ix.k);
   uint4* lut = reinterpret_cast<uint4*>(smem_raw);
   WarpSmem* smem = reinterpret_cast<WarpSmem*>(smem_raw + nchunks * 256 * sizeof(uint4));
   for (uint32_t i = threadIdx.x; i < nchunks * 256; i += blockDim.x) lut[i] = ix.lut[i];
-  __syncthreads();
   const bool wide = nchunks > 7;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t gwarp = blockIdx.x * kWarpsPerCta + warp;
   WarpSmem& sm = smem[warp];
+  WarpStage* stg = STAGED ? reinterpret_cast<WarpStage*>(smem_raw + stage_offset(ix.k)) + warp : nullptr;
+  if (STAGED) {
+    if (lane == 0) {
+      for (int i = 0; i < kStages; ++i) mbar_init(smem_u32(&stg->bar[i]), 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async;" ::: "memory");
+    }
+  }
+  __syncthreads();
   const uint32_t k = ix.k, th = a.th, stride = th + 1, nleaves = ix.nleaves;
   const uint32_t nslots = 2 * nleaves, nbm = (nslots + 31) >> 5;
   const uint32_t lt_mask = (1u << lane) - 1;
-  constexpr uint32_t NG = 32 / G;
-  const uint32_t gl = lane & (G - 1), gbase = lane & ~(uint32_t)(G - 1), gid = lane / G;
-  const uint32_t gmask = (G == 32) ? 0xFFFFFFFFu : (((1u << G) - 1u) << gbase);
 
   WarpCtx w;
   w.acc = a.acc + (size_t)gwarp * nslots * stride;
@@ -196,6 +268,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) match_kernel(const DevIndex
   w.marker = a.marker + (size_t)gwarp * nleaves;
   w.stack = a.stack + (size_t)gwarp * a.stack_cap;
   w.stack_cap = a.stack_cap; w.stride = stride; w.nleaves = nleaves; w.err = a.counters + 2;
+  uint32_t tag = min(a.tagctr[gwarp], kTagStart);   // persists across launches: markers are never cleared in between
+  uint32_t it_issued = 0, it_consumed = 0;          // ring items of this warp over the whole launch (mbarrier phases)
 
   unsigned long long st_bytes = 0, st_lookups = 0, st_entries = 0;
 
@@ -333,7 +407,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) match_kernel(const DevIndex
       }
 
       // ---- B. bucket scans.
-      if (G == 1) {
+      if (!STAGED) {
         // Small buckets: every lane pulls whole lookups from the list and scans its bucket two entries (one 128-bit
         // load) per step.  No warp-collective sits in this loop; lanes leave it independently.
         constexpr uint32_t kCareful = 0x40000000u;
@@ -362,9 +436,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) match_kernel(const DevIndex
           if (e >= hi) {
             have = false;
             if (cnt == 1) { // exactly one hit entry: no other entry can lower a leaf's distance
-              const uint32_t kd = ix.kind[fse];
-              if (kd == 1) commit(w, cs, ix.leaf_rank[fse], fhd);
-              else if (kd == 2) { if (ix.local_expand) expand_local(ix, w, fse, cs, fhd); else cnt = 2; }
+              const uint32_t ci = __ldg(&ix.cinfo[fse]);
+              if (ci & kInfoLeaf) commit(w, cs, ci & 0x3FFFFFFFu, fhd);
+              else if (ci & kInfoExpand) { if (ix.local_expand) expand_local(ix, w, fse, cs, fhd, 0xFFFFFFFFu); else cnt = 2; }
             }
             if (cnt > 1) sm.lk_l[idx] |= kCareful; // several hit entries: handled by the whole warp below
           }
@@ -377,62 +451,50 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) match_kernel(const DevIndex
             const int src = __ffs(need) - 1;
             need &= need - 1;
             const uint32_t ll = sm.lk_l[base + src];
-            careful_lookup(ix, w, sm.lk_a[base + src], ll & 0x3FFFFFFFu, sm.lk_q[base + src], ll >> 31, th);
+            careful_lookup(ix, w, sm.lk_a[base + src], ll & 0x3FFFFFFFu, sm.lk_q[base + src], ll >> 31, th, next_tag(w, tag));
           }
         }
       } else {
-        // Larger buckets: groups of G lanes walk the list (group g takes lookups g, g+NG, ...) and scan G consecutive
-        // entries per step, so that a group reads one contiguous run of 8*G bytes.
-        uint32_t idx = gid, cb = 0, cl = 0, cq = 0, cs = 0, pos = 0, cnt = 0, fse = 0, fhd = 0;
-        bool have = false;
-        for (;;) {
-          if (!have && idx < nout) {
-            cb = sm.lk_a[idx]; cq = sm.lk_q[idx];
-            const uint32_t l = sm.lk_l[idx];
-            cl = l & 0x7FFFFFFFu; cs = l >> 31;
-            idx += NG; have = true; pos = 0; cnt = 0;
+        // Large buckets: the list's buckets are cut into chunks of kChunk entries and streamed through the ring.  All
+        // cursors are warp-uniform; lane 0 issues the bulk copies.
+        uint32_t p_idx = 0, p_off = 0, c_idx = 0, c_off = 0, tagbase = 0;
+        auto issue = [&]() {
+          const uint32_t blen = sm.lk_l[p_idx] & 0x7FFFFFFFu, first = sm.lk_a[p_idx] + p_off;
+          const uint32_t cnt = min((uint32_t)kChunk, blen - p_off);
+          const uint32_t a0 = first & ~1u, a1 = (first + cnt + 1) & ~1u;  // 16-byte aligned source range (cmer is padded)
+          const uint32_t slot = it_issued % kStages;
+          if (lane == 0) {
+            const uint32_t bar = smem_u32(&stg->bar[slot]);
+            mbar_expect_tx(bar, (a1 - a0) * 8u);
+            bulk_g2s(smem_u32(&stg->ent[slot][0]), ix.cmer + a0, (a1 - a0) * 8u, bar);
           }
-          if (!__any_sync(0xFFFFFFFFu, have)) break;
-          bool careful = false;
-          if (have) {
-            const uint32_t e = pos + gl;
-            if (e < cl) {
-              const uint2 ent = __ldg(&ix.cmer[(size_t)cb + e]);
-              const uint32_t z = ent.x ^ cq;
-              const uint32_t hd = __popc((z | (z >> 16)) & 0xFFFFu);
-              if (hd <= th) {
-                if (!cnt) { fse = ent.y; fhd = hd; }
-                ++cnt;
-                if (cs) filt1 = min(filt1, hd); else filt0 = min(filt0, hd);
-              }
-            }
-            pos += G;
-            if (pos >= cl) { // this lookup is finished (uniform inside the group)
-              have = false;
-              if (__any_sync(gmask, cnt != 0)) {
-                uint32_t total = cnt;
+          ++it_issued;
+          p_off += cnt;
+          if (p_off >= blen) { ++p_idx; p_off = 0; }
+        };
+        while (p_idx < nout && it_issued - it_consumed < (uint32_t)kStages) issue();
+        while (it_consumed != it_issued) {
+          const uint32_t slot = it_consumed % kStages, parity = (it_consumed / kStages) & 1u;
+          const uint32_t l = sm.lk_l[c_idx], blen = l & 0x7FFFFFFFu, cs = l >> 31, cq = sm.lk_q[c_idx];
+          const uint32_t first = sm.lk_a[c_idx] + c_off, cnt = min((uint32_t)kChunk, blen - c_off);
+          if (c_off == 0) tagbase = next_tag(w, tag); // the __syncwarp below orders this lookup's hits after the previous one's
+          mbar_wait(smem_u32(&stg->bar[slot]), parity);
+          const uint2* sp = &stg->ent[slot][first & 1u];
+          uint2 ent[kChunk / 32];
 #pragma unroll
-                for (int o = G / 2; o; o >>= 1) total += __shfl_xor_sync(gmask, total, o);
-                uint32_t flag = total > 1;
-                if (total == 1 && cnt == 1) { // exactly one hit entry: no other entry can lower a leaf's distance
-                  const uint32_t kd = ix.kind[fse];
-                  if (kd == 1) commit(w, cs, ix.leaf_rank[fse], fhd);
-                  else if (kd == 2) { if (ix.local_expand) expand_local(ix, w, fse, cs, fhd); else flag = 1; }
-                }
+          for (int h = 0; h < kChunk / 32; ++h) ent[h] = (lane + 32 * h < cnt) ? sp[lane + 32 * h] : make_uint2(~cq, 0u);
+          __syncwarp();               // every lane has its entries in registers: the slot may be refilled
+          ++it_consumed;
+          c_off += cnt;
+          if (c_off >= blen) { ++c_idx; c_off = 0; }
+          if (p_idx < nout) issue();
 #pragma unroll
-                for (int o = G / 2; o; o >>= 1) flag |= __shfl_xor_sync(gmask, flag, o);
-                careful = flag != 0;
-              }
-            }
-          }
-          // several hit entries in one bucket: the warp handles those lookups together, one after the other
-          uint32_t need = __ballot_sync(0xFFFFFFFFu, careful && gl == 0);
-          while (need) {
-            const int src = __ffs(need) - 1;
-            need &= need - 1;
-            const uint32_t b = __shfl_sync(0xFFFFFFFFu, cb, src), l = __shfl_sync(0xFFFFFFFFu, cl, src);
-            const uint32_t qq = __shfl_sync(0xFFFFFFFFu, cq, src), ss = __shfl_sync(0xFFFFFFFFu, cs, src);
-            careful_lookup(ix, w, b, l, qq, ss, th);
+          for (int h = 0; h < kChunk / 32; ++h) {
+            const uint32_t z = ent[h].x ^ cq;
+            const uint32_t hd = __popc((z | (z >> 16)) & 0xFFFFu);  // padding lanes: z = 0xffffffff -> hd = 16 ...
+            const bool hit = hd <= th && (lane + 32 * h < cnt);       // ... which a threshold of 16 would accept, hence the bound
+            if (hit) { if (cs) filt1 = min(filt1, hd); else filt0 = min(filt0, hd); }
+            expand_hits(ix, w, hit, ent[h].y, hd, cs, tagbase);
           }
         }
       }
@@ -491,6 +553,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) match_kernel(const DevIndex
     }
     __syncwarp();
   }
+  if (lane == 0) a.tagctr[gwarp] = tag;
   // ---- roofline accounting
   for (int o = 16; o; o >>= 1) {
     st_bytes += __shfl_xor_sync(0xFFFFFFFFu, st_bytes, o);
@@ -502,43 +565,36 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) match_kernel(const DevIndex
 
 // ------------------------------------------------------------------------------------------------ host launchers
 
-template <int G, bool TAP>
+template <bool STAGED, bool TAP>
 static cudaError_t prepare()
 {
-  return cudaFuncSetAttribute(match_kernel<G, TAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(32));
+  return cudaFuncSetAttribute(match_kernel<STAGED, TAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(32, STAGED));
 }
 
-int match_resident_warps(int device, uint32_t k)
+int match_resident_warps(int device, uint32_t k, bool staged)
 {
   int sms = 0, per_sm = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  prepare<4, false>();
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, match_kernel<4, false>, kWarpsPerCta * 32, smem_bytes(k));
+  if (staged) { prepare<true, false>(); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, match_kernel<true, false>, kWarpsPerCta * 32, smem_bytes(k, true)); }
+  else { prepare<false, false>(); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, match_kernel<false, false>, kWarpsPerCta * 32, smem_bytes(k, false)); }
   if (per_sm < 1) per_sm = 1;
   return sms * per_sm * kWarpsPerCta;
 }
 
-template <int G>
-static cudaError_t launch_g(const DevIndex& ix, const MatchArgs& a, int grid, bool tap, cudaStream_t stream)
+template <bool STAGED>
+static cudaError_t launch_s(const DevIndex& ix, const MatchArgs& a, int grid, bool tap, cudaStream_t stream)
 {
-  cudaError_t e = tap ? prepare<G, true>() : prepare<G, false>();
+  cudaError_t e = tap ? prepare<STAGED, true>() : prepare<STAGED, false>();
   if (e != cudaSuccess) return e;
-  if (tap) match_kernel<G, true><<<grid, kWarpsPerCta * 32, smem_bytes(ix.k), stream>>>(ix, a);
-  else match_kernel<G, false><<<grid, kWarpsPerCta * 32, smem_bytes(ix.k), stream>>>(ix, a);
+  if (tap) match_kernel<STAGED, true><<<grid, kWarpsPerCta * 32, smem_bytes(ix.k, STAGED), stream>>>(ix, a);
+  else match_kernel<STAGED, false><<<grid, kWarpsPerCta * 32, smem_bytes(ix.k, STAGED), stream>>>(ix, a);
   return cudaGetLastError();
 }
 
-cudaError_t launch_match(const DevIndex& ix, const MatchArgs& a, int resident_warps, int group, bool tap, cudaStream_t stream)
+cudaError_t launch_match(const DevIndex& ix, const MatchArgs& a, int resident_warps, bool staged, bool tap, cudaStream_t stream)
 {
   const int grid = resident_warps / kWarpsPerCta;
-  switch (group) {
-    case 1: return launch_g<1>(ix, a, grid, tap, stream);
-    case 2: return launch_g<2>(ix, a, grid, tap, stream);
-    case 4: return launch_g<4>(ix, a, grid, tap, stream);
-    case 8: return launch_g<8>(ix, a, grid, tap, stream);
-    case 16: return launch_g<16>(ix, a, grid, tap, stream);
-    default: return launch_g<32>(ix, a, grid, tap, stream);
-  }
+  return staged ? launch_s<true>(ix, a, grid, tap, stream) : launch_s<false>(ix, a, grid, tap, stream);
 }
 
 } // namespace krepp

@@ -10,8 +10,8 @@ struct LlhTables {
   double hnk[kMaxTh + 1]; // C(k, x) - C(k-h, x) for 1 <= x <= th, and 0 for x = 0
 };
 
-int match_resident_warps(int device, uint32_t k);
-cudaError_t launch_match(const DevIndex& ix, const MatchArgs& a, int resident_warps, int group, bool tap, cudaStream_t stream);
+int match_resident_warps(int device, uint32_t k, bool staged);
+cudaError_t launch_match(const DevIndex& ix, const MatchArgs& a, int resident_warps, bool staged, bool tap, cudaStream_t stream);
 cudaError_t launch_solve(const SolveArgs& a, const LlhTables& tab, int sms, cudaStream_t stream);
 constexpr int kPlaceWarpsPerCta = 4;
 cudaError_t launch_place(const PlaceArgs& a, const LlhTables& tab, int grid, cudaStream_t stream);

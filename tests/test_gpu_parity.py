@@ -44,14 +44,15 @@ def test_golden_small_index_k21_h7():
     b = krepp_b200.IBatch(g, reads, names=names)
     with open(os.path.join(small, "ref_dist.tsv")) as f:
         assert sorted(b.estimate_distances().splitlines()) == sorted(f.read().splitlines())
-    for grp in ("1", "4", "32"):   # every scan strategy gives the same integers
-        os.environ["KREPP_GROUP"] = grp
+    for scan in ("lane", "staged"):   # every scan strategy gives the same integers
+        os.environ["KREPP_SCAN"] = scan
         try:
             g2 = krepp_b200.Index(os.path.join(small, "index"), 0)
             run_and_compare(small, reads, o, g2, check_lookups=False)
+            run_and_compare(small, reads, o, g2, check_lookups=False, place=True, no_filter=False)
             g2.close()
         finally:
-            del os.environ["KREPP_GROUP"]
+            del os.environ["KREPP_SCAN"]
 
 
 @needs_ref
@@ -241,3 +242,26 @@ def test_cli_dist_equals_reference_cli_on_toy(env):
     r = _cli("dist", "-i", env["dir"], "-q", q)
     assert r.returncode == 0, r.stderr
     assert sorted(r.stdout.splitlines()[2:]) == sorted(ref)
+
+
+@needs_ref
+@pytest.mark.parametrize("scan", ["lane", "staged"])
+def test_scan_strategies_on_toy(scan):
+    """Both phase-B strategies of the match kernel (lane-per-bucket, bulk-copy ring) on the toy index: all integer stages
+    bit-exact, incl. long reads that span many tiles and ring wrap-arounds."""
+    import krepp_b200
+    import oracle_lib as O
+    import synth
+    from gpu_common import run_and_compare
+    idx = os.path.join(TOY_DIR, "index_toy")
+    seq, offs = synth.load_packed(os.path.join(TOY_DIR, "genomes.npz"))
+    reads = [r.tobytes() for r in synth.sample_reads(seq, offs, 4000, seed=5)]
+    reads += [r.tobytes() for r in synth.sample_reads(seq, offs, 6, read_len=20000, max_sub=0.03, seed=6)]
+    os.environ["KREPP_SCAN"] = scan
+    try:
+        g = krepp_b200.Index(idx, 0)
+        st = run_and_compare(idx, reads, O.OracleIndex(idx), g)
+        assert st["max_rel_d"] < 1e-5
+        g.close()
+    finally:
+        del os.environ["KREPP_SCAN"]

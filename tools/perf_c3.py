@@ -22,7 +22,7 @@ def main():
     ap.add_argument("--length", type=int, default=3_000_000)
     ap.add_argument("--reads", type=int, default=2_000_000)
     ap.add_argument("--batch", type=int, default=250_000)
-    ap.add_argument("--groups", default="8,16,32")
+    ap.add_argument("--groups", default="staged")
     ap.add_argument("--out", default="/tmp/c3")
     ap.add_argument("--cpu-reads", type=int, default=100_000)
     ap.add_argument("--check", type=int, default=300)
@@ -58,8 +58,8 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     nb = (len(reads) + a.batch - 1) // a.batch
     d_reads = [torch.from_numpy(reads[i * a.batch:(i + 1) * a.batch].reshape(-1)).cuda() for i in range(nb)]
-    for g in [int(x) for x in a.groups.split(",")]:
-        os.environ["KREPP_GROUP"] = str(g)
+    for g in a.groups.split(","):
+        os.environ["KREPP_SCAN"] = g
         ix = krepp_b200.Index(idx, 0)
         b = krepp_b200.IBatch(ix, reads[:a.batch], place=a.place, no_filter=not a.place)
         d_o = torch.from_numpy(b.offsets.astype(np.int64)).cuda()
@@ -79,11 +79,11 @@ def main():
             res.append((mm, tt, time.time() - w0))
         mm, tt, wall = min(res)
         ab = b.algorithmic_bytes()
-        print(f"G={g:2d} reads {len(reads)}  match {mm:8.2f} ms  kernels {tt:8.2f} ms  wall {wall * 1e3:8.1f} ms -> {len(reads) / tt / 1e3:7.2f} M reads/s  "
+        print(f"scan={g} reads {len(reads)}  match {mm:8.2f} ms  kernels {tt:8.2f} ms  wall {wall * 1e3:8.1f} ms -> {len(reads) / tt / 1e3:7.2f} M reads/s  "
               f"algorithmic {alg / 1e9:7.1f} GB = {alg / len(reads) / 1e3:6.1f} kB/read -> {alg / mm / 1e6:7.1f} GB/s = {alg / mm / 1e6 / peak:5.3f} of measured HBM peak; "
               f"records/read {nrec / len(reads):5.1f}; entries/lookup {ab['entries'] / max(ab['lookups'], 1):5.1f}", flush=True)
         b.close(); ix.close()
-    os.environ.pop("KREPP_GROUP", None)
+    os.environ.pop("KREPP_SCAN", None)
 
     fq = os.path.join(a.out, "reads.fq")
     if not a.skip_cli:
