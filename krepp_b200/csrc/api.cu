@@ -233,6 +233,7 @@ int krepp_index_open(const char* index_dir, int device, krepp_index_t** out)
     if (const char* env = getenv("KREPP_SCAN")) { if (!strcmp(env, "staged")) ix->staged = true; else if (!strcmp(env, "lane")) ix->staged = false; }
   }
   ix->resident_warps = match_resident_warps(device, h.k, ix->staged);
+  if (ix->staged && ix->resident_warps == 0) { ix->staged = false; ix->resident_warps = match_resident_warps(device, h.k, false); } // k > 28: the ring does not fit beside an 8-table LUT
   *out = ix;
   return KREPP_OK;
 }

@@ -35,7 +35,8 @@
 
 namespace krepp {
 
-constexpr int kWarpsPerCta = 8;
+constexpr int kWarpsLane = 8, kWarpsStaged = 16; // warps per CTA: the staged path runs one 512-thread CTA per SM so that the LUT is staged once
+__host__ __device__ constexpr int warps_per_cta(bool staged) { return staged ? kWarpsStaged : kWarpsLane; }
 constexpr int kTileWindows = 128;              // windows handled per tile: 4 per lane
 constexpr int kTileWords = 12;                 // 16 bases per 32-bit word -> 192 bases >= 128 + 32 - 1
 constexpr int kLocalStack = 32;
@@ -43,7 +44,11 @@ constexpr uint32_t kClaim = 4;                // reads claimed per atomic on the
 constexpr int kMaxLookups = 2 * kTileWindows;  // both strands
 constexpr int kChunk = 128;                    // staged path: bucket entries per ring slot (4 per lane)
 constexpr int kSlotEntries = kChunk + 2;       // + 16-byte alignment slack at either end of a chunk
-constexpr int kStages = 6;                     // ring slots per warp: up to ~6 kB of bucket reads in flight per warp
+constexpr int kStages = 5;                     // ring slots per warp: up to ~5 kB of bucket reads in flight per warp
+constexpr int kHitCap = 256;                   // staged path: hit entries queued per warp between two resolutions
+constexpr int kTabSize = 512;                  // staged path: (lookup, leaf) -> min distance table, open addressing
+constexpr uint32_t kTabEmpty = 0xFFFFFFFFu;    // lookup id 127 is never handed out
+constexpr uint32_t kTabMaxLeaves = 1u << 19;   // leaf ranks must fit the table key
 constexpr uint32_t kTagStart = 0x07FFFFFEu;    // marker tags count down from here; 0x07FFFFFF is the rest value's tag
 constexpr uint32_t kInfoLeaf = 0x80000000u, kInfoExpand = 0x40000000u; // DevIndex::cinfo
 
@@ -56,14 +61,18 @@ struct WarpSmem {
   uint32_t cursor;
 };
 struct __align__(16) WarpStage {              // staged path only
-  unsigned long long bar[kStages];            // one mbarrier per ring slot
+  unsigned long long bar[kStages + 1];        // one mbarrier per ring slot (+1: keeps the rest 16-byte aligned)
   uint2 ent[kStages][kSlotEntries];           // slot stride 1040 B = 65 x 16
+  uint2 hitq[kHitCap];                        // queued hit entries: {colour id, lookup id << 25 | strand << 24 | hd}
+  uint32_t tab[kTabSize];                     // lookup id << 25 | strand << 24 | leaf rank << 5 | min hd
+  uint32_t ovf, pad[3];
 };
+static_assert(sizeof(WarpStage) % 16 == 0, "ring slots must stay 16-byte aligned");
 // LUT layout: [byte of the k-mer word][byte value] -> {rix fwd, q fwd, rix rc, q rc} parts; 7 bytes cover k <= 28
 // lut_pext always reads the first seven byte tables, so at least seven are staged (all-zero past the k-mer's last byte)
 __host__ __device__ inline uint32_t lut_chunks(uint32_t k) { const uint32_t n = (2 * k + 7) / 8; return n < 7 ? 7 : n; }
-__host__ __device__ inline size_t stage_offset(uint32_t k) { return (lut_chunks(k) * 256 * sizeof(uint4) + kWarpsPerCta * sizeof(WarpSmem) + 15) & ~(size_t)15; }
-__host__ __device__ inline size_t smem_bytes(uint32_t k, bool staged) { return staged ? stage_offset(k) + kWarpsPerCta * sizeof(WarpStage) : lut_chunks(k) * 256 * sizeof(uint4) + kWarpsPerCta * sizeof(WarpSmem); }
+__host__ __device__ inline size_t stage_offset(uint32_t k) { return (lut_chunks(k) * 256 * sizeof(uint4) + kWarpsStaged * sizeof(WarpSmem) + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t smem_bytes(uint32_t k, bool staged) { return staged ? stage_offset(k) + kWarpsStaged * sizeof(WarpStage) : lut_chunks(k) * 256 * sizeof(uint4) + kWarpsLane * sizeof(WarpSmem); }
 
 __device__ __forceinline__ void encode4(uint32_t u, uint32_t& code8, uint32_t& valid4)
 {
@@ -219,6 +228,62 @@ __device__ __forceinline__ uint32_t next_tag(const WarpCtx& w, uint32_t& tag)
   return tag << 5;
 }
 
+// Staged path: one leaf reached by a queued hit goes into the warp's shared-memory table keyed by (lookup, strand, leaf);
+// the value keeps the minimum distance.  Any number of lanes may insert concurrently (shared-memory atomics only).
+__device__ __forceinline__ void tab_insert(WarpStage* stg, uint32_t v)
+{
+  uint32_t slot = ((v >> 5) * 0x9E3779B1u) >> 23; // 9 bits
+  for (int probes = 0; probes < 48; ++probes) {
+    const uint32_t old = atomicCAS(&stg->tab[slot], kTabEmpty, v);
+    if (old == kTabEmpty) return;
+    if (((old ^ v) >> 5) == 0) { atomicMin(&stg->tab[slot], v); return; }
+    slot = (slot + 1) & (kTabSize - 1);
+  }
+  stg->ovf = 1; // too crowded: the whole batch is redone through the marker path
+}
+
+__device__ __forceinline__ void expand_to_table(const DevIndex& ix, WarpStage* stg, uint32_t se, uint32_t meta)
+{
+  uint32_t st[kLocalStack];
+  int sp = 0;
+  st[sp++] = se;
+  while (sp) {
+    const uint32_t s = st[--sp];
+    const uint32_t ci = __ldg(&ix.cinfo[s]);
+    if (ci & kInfoLeaf) tab_insert(stg, (meta & 0xFF000000u) | ((ci & 0x7FFFFu) << 5) | (meta & 31u));
+    else if (ci & kInfoExpand) { const uint2 c = __ldg(&ix.pse[s]); st[sp++] = c.y; st[sp++] = c.x; }
+  }
+}
+
+// Resolves the queued hits of a warp: colours are expanded with all lanes busy, leaves are deduplicated per lookup in the
+// shared-memory table, and every surviving (lookup, leaf) bumps the histogram once at its minimum distance.
+__device__ void resolve_hits(const DevIndex& ix, const WarpCtx& w, WarpStage* stg, uint32_t n_hits, uint32_t n_ids, uint32_t& tag)
+{
+  const uint32_t lane = threadIdx.x & 31;
+  __syncwarp();
+  for (uint32_t i = lane; i < n_hits; i += 32) { const uint2 h = stg->hitq[i]; expand_to_table(ix, stg, h.x, h.y); }
+  __syncwarp();
+  const bool overflow = *reinterpret_cast<volatile uint32_t*>(&stg->ovf) != 0;
+  for (uint32_t slot = lane; slot < (uint32_t)kTabSize; slot += 32) {
+    const uint32_t v = stg->tab[slot];
+    if (v == kTabEmpty) continue;
+    stg->tab[slot] = kTabEmpty;
+    if (!overflow) commit(w, (v >> 24) & 1u, (v >> 5) & 0x7FFFFu, v & 31u);
+  }
+  __syncwarp();
+  if (overflow) { // rare: more distinct (lookup, leaf) pairs than the table holds -- lookup by lookup through the markers
+    if (lane == 0) stg->ovf = 0;
+    for (uint32_t id = 0; id < n_ids; ++id) {
+      const uint32_t tagbase = next_tag(w, tag);
+      for (uint32_t i = lane; i < n_hits; i += 32) {
+        const uint2 h = stg->hitq[i];
+        if ((h.y >> 25) == id) expand_local(ix, w, h.x, (h.y >> 24) & 1u, h.y & 31u, tagbase);
+      }
+      __syncwarp();
+    }
+  }
+}
+
 // Small-bucket path: one lookup with several hit entries (or a colour too deep for the private stack), rescanned by the
 // whole warp in a single pass.
 __device__ void careful_lookup(const DevIndex& ix, const WarpCtx& w, uint32_t begin, uint32_t len, uint32_t q, uint32_t strand, uint32_t th, uint32_t tagbase)
@@ -238,8 +303,9 @@ __device__ void careful_lookup(const DevIndex& ix, const WarpCtx& w, uint32_t be
 }
 
 template <bool STAGED, bool TAP>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, STAGED ? 2 : 4) match_kernel(const DevIndex ix, const MatchArgs a)
+__global__ void __launch_bounds__(warps_per_cta(STAGED) * 32, STAGED ? 1 : 4) match_kernel(const DevIndex ix, const MatchArgs a)
 {
+  constexpr int kWarpsPerCta = warps_per_cta(STAGED);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t nchunks = lut_chunks(ix.k);
   uint4* lut = reinterpret_cast<uint4*>(smem_raw);
@@ -251,7 +317,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, STAGED ? 2 : 4) match_kerne
   WarpSmem& sm = smem[warp];
   WarpStage* stg = STAGED ? reinterpret_cast<WarpStage*>(smem_raw + stage_offset(ix.k)) + warp : nullptr;
   if (STAGED) {
+    for (uint32_t i = lane; i < (uint32_t)kTabSize; i += 32) stg->tab[i] = kTabEmpty;
     if (lane == 0) {
+      stg->ovf = 0;
       for (int i = 0; i < kStages; ++i) mbar_init(smem_u32(&stg->bar[i]), 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       asm volatile("fence.proxy.async;" ::: "memory");
@@ -269,7 +337,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, STAGED ? 2 : 4) match_kerne
   w.stack = a.stack + (size_t)gwarp * a.stack_cap;
   w.stack_cap = a.stack_cap; w.stride = stride; w.nleaves = nleaves; w.err = a.counters + 2;
   uint32_t tag = min(a.tagctr[gwarp], kTagStart);   // persists across launches: markers are never cleared in between
-  uint32_t it_issued = 0, it_consumed = 0;          // ring items of this warp over the whole launch (mbarrier phases)
+  uint32_t p_slot = 0, c_slot = 0, c_par = 0, n_fly = 0; // ring state of this warp over the whole launch (mbarrier phases)
+  const bool use_table = STAGED && ix.local_expand && nleaves <= kTabMaxLeaves;
 
   unsigned long long st_bytes = 0, st_lookups = 0, st_entries = 0;
 
@@ -456,47 +525,69 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, STAGED ? 2 : 4) match_kerne
         }
       } else {
         // Large buckets: the list's buckets are cut into chunks of kChunk entries and streamed through the ring.  All
-        // cursors are warp-uniform; lane 0 issues the bulk copies.
-        uint32_t p_idx = 0, p_off = 0, c_idx = 0, c_off = 0, tagbase = 0;
+        // cursors are warp-uniform; lane 0 issues the bulk copies.  Hit entries are queued and resolved in batches
+        // (resolve_hits) so that colour expansion and deduplication run with all lanes busy; only lookups larger than
+        // the queue go through the marker path on the spot.
+        uint32_t p_idx = 0, p_off = 0, c_idx = 0, c_off = 0, tagbase = 0, n_hits = 0, lk_id = 0;
+        bool big = false;
         auto issue = [&]() {
           const uint32_t blen = sm.lk_l[p_idx] & 0x7FFFFFFFu, first = sm.lk_a[p_idx] + p_off;
           const uint32_t cnt = min((uint32_t)kChunk, blen - p_off);
-          const uint32_t a0 = first & ~1u, a1 = (first + cnt + 1) & ~1u;  // 16-byte aligned source range (cmer is padded)
-          const uint32_t slot = it_issued % kStages;
           if (lane == 0) {
-            const uint32_t bar = smem_u32(&stg->bar[slot]);
+            const uint32_t a0 = first & ~1u, a1 = (first + cnt + 1) & ~1u;  // 16-byte aligned source range (cmer is padded)
+            const uint32_t bar = smem_u32(&stg->bar[p_slot]);
             mbar_expect_tx(bar, (a1 - a0) * 8u);
-            bulk_g2s(smem_u32(&stg->ent[slot][0]), ix.cmer + a0, (a1 - a0) * 8u, bar);
+            bulk_g2s(smem_u32(&stg->ent[p_slot][0]), ix.cmer + a0, (a1 - a0) * 8u, bar);
           }
-          ++it_issued;
+          p_slot = (p_slot + 1 == (uint32_t)kStages) ? 0u : p_slot + 1;
+          ++n_fly;
           p_off += cnt;
           if (p_off >= blen) { ++p_idx; p_off = 0; }
         };
-        while (p_idx < nout && it_issued - it_consumed < (uint32_t)kStages) issue();
-        while (it_consumed != it_issued) {
-          const uint32_t slot = it_consumed % kStages, parity = (it_consumed / kStages) & 1u;
+        while (p_idx < nout && n_fly < (uint32_t)kStages) issue();
+        while (n_fly) {
           const uint32_t l = sm.lk_l[c_idx], blen = l & 0x7FFFFFFFu, cs = l >> 31, cq = sm.lk_q[c_idx];
           const uint32_t first = sm.lk_a[c_idx] + c_off, cnt = min((uint32_t)kChunk, blen - c_off);
-          if (c_off == 0) tagbase = next_tag(w, tag); // the __syncwarp below orders this lookup's hits after the previous one's
-          mbar_wait(smem_u32(&stg->bar[slot]), parity);
-          const uint2* sp = &stg->ent[slot][first & 1u];
+          if (c_off == 0) { // a new lookup starts
+            big = !use_table || blen > (uint32_t)kHitCap;
+            if (big) tagbase = next_tag(w, tag); // the __syncwarp below orders this lookup's hits after the previous one's
+            else if (n_hits + blen > (uint32_t)kHitCap || lk_id >= 126u) { resolve_hits(ix, w, stg, n_hits, lk_id, tag); n_hits = 0; lk_id = 0; }
+          }
+          mbar_wait(smem_u32(&stg->bar[c_slot]), c_par);
+          const uint2* sp = &stg->ent[c_slot][first & 1u];
           uint2 ent[kChunk / 32];
 #pragma unroll
-          for (int h = 0; h < kChunk / 32; ++h) ent[h] = (lane + 32 * h < cnt) ? sp[lane + 32 * h] : make_uint2(~cq, 0u);
+          for (int h = 0; h < kChunk / 32; ++h) ent[h] = sp[lane + 32 * h]; // past cnt: stale bytes of the slot, masked below
           __syncwarp();               // every lane has its entries in registers: the slot may be refilled
-          ++it_consumed;
+          if (++c_slot == (uint32_t)kStages) { c_slot = 0; c_par ^= 1u; }
+          --n_fly;
           c_off += cnt;
-          if (c_off >= blen) { ++c_idx; c_off = 0; }
+          const bool last = c_off >= blen;
+          if (last) { ++c_idx; c_off = 0; }
           if (p_idx < nout) issue();
+          uint32_t hd[kChunk / 32], hmask = 0;
 #pragma unroll
           for (int h = 0; h < kChunk / 32; ++h) {
             const uint32_t z = ent[h].x ^ cq;
-            const uint32_t hd = __popc((z | (z >> 16)) & 0xFFFFu);  // padding lanes: z = 0xffffffff -> hd = 16 ...
-            const bool hit = hd <= th && (lane + 32 * h < cnt);       // ... which a threshold of 16 would accept, hence the bound
-            if (hit) { if (cs) filt1 = min(filt1, hd); else filt0 = min(filt0, hd); }
-            expand_hits(ix, w, hit, ent[h].y, hd, cs, tagbase);
+            hd[h] = __popc((z | (z >> 16)) & 0xFFFFu);
+            hmask |= (uint32_t)(hd[h] <= th && lane + 32 * h < cnt) << h;
           }
+          if (__any_sync(0xFFFFFFFFu, hmask != 0)) {
+#pragma unroll
+            for (int h = 0; h < kChunk / 32; ++h) {
+              const bool hit = (hmask >> h) & 1u;
+              if (hit) { if (cs) filt1 = min(filt1, hd[h]); else filt0 = min(filt0, hd[h]); }
+              if (big) expand_hits(ix, w, hit, ent[h].y, hd[h], cs, tagbase);
+              else {
+                const uint32_t bm = __ballot_sync(0xFFFFFFFFu, hit);
+                if (hit) stg->hitq[n_hits + __popc(bm & lt_mask)] = make_uint2(ent[h].y, lk_id << 25 | cs << 24 | hd[h]);
+                n_hits += __popc(bm);
+              }
+            }
+          }
+          if (last && !big) ++lk_id;
         }
+        if (n_hits) resolve_hits(ix, w, stg, n_hits, lk_id, tag);
       }
       __syncwarp();
     }
@@ -521,29 +612,36 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, STAGED ? 2 : 4) match_kerne
     rbegin = __shfl_sync(0xFFFFFFFFu, rbegin, 0);
     const bool fits = (uint64_t)rbegin + total <= a.rec_cap;
     if (!fits && lane == 0) atomicOr(a.counters + 2, kErrRecOverflow);
+    // records in ascending slot order; 16 bitmap words (<= 512 slots) per round: lanes 0..15 list the set bits of their
+    // word in shared memory, then every lane takes whole records, so clustered leaves do not pile up on one lane
     uint32_t done = 0;
-    for (uint32_t wbase = 0; wbase < nbm; wbase += 32) {
-      uint32_t bits = (wbase + lane < nbm) ? __ldcg(&w.bitmap[wbase + lane]) : 0u;
+    uint32_t* list = sm.lk_a; // the lookup list is dead here (512 entries with lk_l)
+    for (uint32_t wbase = 0; wbase < nbm; wbase += 16) {
+      uint32_t bits = (lane < 16 && wbase + lane < nbm) ? __ldcg(&w.bitmap[wbase + lane]) : 0u;
       const uint32_t c = __popc(bits);
       uint32_t incl = c;
       for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += t; }
-      uint32_t at = rbegin + done + incl - c;
-      done += __shfl_sync(0xFFFFFFFFu, incl, 31);
-      if (wbase + lane < nbm && bits) w.bitmap[wbase + lane] = 0;
-      while (bits) {
-        const uint32_t b = __ffs(bits) - 1;
-        bits &= bits - 1;
-        const uint32_t slot = (wbase + lane) * 32 + b;
+      const uint32_t cnt = __shfl_sync(0xFFFFFFFFu, incl, 31);
+      if (!cnt) continue;
+      if (bits) w.bitmap[wbase + lane] = 0;
+      uint32_t li = incl - c;
+      while (bits) { const uint32_t b = __ffs(bits) - 1; bits &= bits - 1; list[li++] = (wbase + lane) * 32 + b; }
+      __syncwarp();
+      for (uint32_t i = lane; i < cnt; i += 32) {
+        const uint32_t slot = list[i], at = rbegin + done + i;
         const uint32_t strand = slot >= nleaves, rank = slot - strand * nleaves;
         uint32_t* h = w.acc + (size_t)slot * stride;
+        uint32_t hv[kMaxTh + 1];
+        for (uint32_t x = 0; x < stride; ++x) hv[x] = __ldcg(&h[x]);
+        for (uint32_t x = 0; x < stride; ++x) h[x] = 0;
         if (fits) {
           a.rec_read[at] = read;
           a.rec_slot[at] = strand << 31 | ix.leaf_se[rank];
-          for (uint32_t x = 0; x < stride; ++x) a.rec_hist[(size_t)at * stride + x] = __ldcg(&h[x]);
+          for (uint32_t x = 0; x < stride; ++x) a.rec_hist[(size_t)at * stride + x] = hv[x];
         }
-        for (uint32_t x = 0; x < stride; ++x) h[x] = 0;
-        ++at;
       }
+      done += cnt;
+      __syncwarp();
     }
     if (lane == 0) {
       a.onmers[read] = onmers; a.wn[2 * read] = wn0; a.wn[2 * read + 1] = wn1;
@@ -566,34 +664,38 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, STAGED ? 2 : 4) match_kerne
 // ------------------------------------------------------------------------------------------------ host launchers
 
 template <bool STAGED, bool TAP>
-static cudaError_t prepare()
+static cudaError_t prepare(uint32_t k)
 {
-  return cudaFuncSetAttribute(match_kernel<STAGED, TAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(32, STAGED));
+  return cudaFuncSetAttribute(match_kernel<STAGED, TAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(k, STAGED));
 }
 
+// Resident warps of the persistent grid; 0 when the staged variant does not fit this device's shared memory for this k
+// (the caller then uses the lane-per-bucket variant).
 int match_resident_warps(int device, uint32_t k, bool staged)
 {
   int sms = 0, per_sm = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  if (staged) { prepare<true, false>(); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, match_kernel<true, false>, kWarpsPerCta * 32, smem_bytes(k, true)); }
-  else { prepare<false, false>(); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, match_kernel<false, false>, kWarpsPerCta * 32, smem_bytes(k, false)); }
-  if (per_sm < 1) per_sm = 1;
-  return sms * per_sm * kWarpsPerCta;
+  cudaError_t e;
+  if (staged) { e = prepare<true, false>(k); if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, match_kernel<true, false>, kWarpsStaged * 32, smem_bytes(k, true)); }
+  else { e = prepare<false, false>(k); if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, match_kernel<false, false>, kWarpsLane * 32, smem_bytes(k, false)); }
+  if (e != cudaSuccess) { cudaGetLastError(); per_sm = 0; }
+  if (per_sm < 1) { if (staged) return 0; per_sm = 1; }
+  return sms * per_sm * warps_per_cta(staged);
 }
 
 template <bool STAGED>
 static cudaError_t launch_s(const DevIndex& ix, const MatchArgs& a, int grid, bool tap, cudaStream_t stream)
 {
-  cudaError_t e = tap ? prepare<STAGED, true>() : prepare<STAGED, false>();
+  cudaError_t e = tap ? prepare<STAGED, true>(ix.k) : prepare<STAGED, false>(ix.k);
   if (e != cudaSuccess) return e;
-  if (tap) match_kernel<STAGED, true><<<grid, kWarpsPerCta * 32, smem_bytes(ix.k, STAGED), stream>>>(ix, a);
-  else match_kernel<STAGED, false><<<grid, kWarpsPerCta * 32, smem_bytes(ix.k, STAGED), stream>>>(ix, a);
+  if (tap) match_kernel<STAGED, true><<<grid, warps_per_cta(STAGED) * 32, smem_bytes(ix.k, STAGED), stream>>>(ix, a);
+  else match_kernel<STAGED, false><<<grid, warps_per_cta(STAGED) * 32, smem_bytes(ix.k, STAGED), stream>>>(ix, a);
   return cudaGetLastError();
 }
 
 cudaError_t launch_match(const DevIndex& ix, const MatchArgs& a, int resident_warps, bool staged, bool tap, cudaStream_t stream)
 {
-  const int grid = resident_warps / kWarpsPerCta;
+  const int grid = resident_warps / warps_per_cta(staged);
   return staged ? launch_s<true>(ix, a, grid, tap, stream) : launch_s<false>(ix, a, grid, tap, stream);
 }
 
