@@ -146,7 +146,7 @@ struct krepp_batch {
   // device state
   uint32_t *d_onmers = nullptr, *d_wn = nullptr, *d_hdfilt = nullptr, *d_rec_begin = nullptr, *d_rec_count = nullptr;
   int32_t* d_closest = nullptr;
-  uint32_t *d_rec_read = nullptr, *d_rec_slot = nullptr, *d_rec_hist = nullptr, *d_rec_flags = nullptr, *d_rec_match = nullptr, *d_rec_hdmin = nullptr;
+  uint32_t *d_rec_read = nullptr, *d_rec_slot = nullptr, *d_rec_hist = nullptr, *d_rec_flags = nullptr, *d_rec_match = nullptr, *d_rec_hdmin = nullptr, *d_rec_work = nullptr;
   double *d_rec_d = nullptr, *d_rec_v = nullptr, *d_rec_chisq = nullptr;
   uint32_t* d_counters = nullptr; unsigned long long* d_stats = nullptr;
   uint32_t *d_acc = nullptr, *d_bitmap = nullptr, *d_marker = nullptr, *d_stack = nullptr, *d_tagctr = nullptr;
@@ -203,10 +203,13 @@ int krepp_index_open(const char* index_dir, int device, krepp_index_t** out)
   if (e == cudaSuccess) e = upload(h.pse, reinterpret_cast<const uint64_t**>(&d.pse), ix->allocs, ix->device_bytes);
   if (e == cudaSuccess) e = upload(h.kind, &d.kind, ix->allocs, ix->device_bytes);
   {
-    std::vector<uint32_t> cinfo(h.kind.size(), 0);
-    for (size_t se = 0; se < cinfo.size(); ++se)
-      cinfo[se] = h.kind[se] == 1 ? (0x80000000u | h.tree.leaf_rank[se]) : h.kind[se] == 2 ? 0x40000000u : 0u;
-    if (e == cudaSuccess) e = upload(cinfo, &d.cinfo, ix->allocs, ix->device_bytes);
+    std::vector<uint2> cnode(h.kind.size(), make_uint2(0u, 0u));
+    for (size_t se = 0; se < cnode.size(); ++se) {
+      if (h.kind[se] == 1) cnode[se] = make_uint2(0x80000000u | h.tree.leaf_rank[se], 0u);
+      else if (h.kind[se] == 2) cnode[se] = make_uint2(0x40000000u | (uint32_t)h.pse[se], (uint32_t)(h.pse[se] >> 32));
+    }
+    if (h.nsubsets >= (1u << 30)) e = cudaErrorInvalidValue; // colour ids must leave the two flag bits free
+    if (e == cudaSuccess) e = upload(cnode, &d.cnode, ix->allocs, ix->device_bytes);
   }
   if (e == cudaSuccess) e = upload(h.rho, &d.rho, ix->allocs, ix->device_bytes);
   if (e == cudaSuccess) e = upload(h.tree.leaf_rank, &d.leaf_rank, ix->allocs, ix->device_bytes);
@@ -288,12 +291,12 @@ size_t krepp_index_jplace_tree(const krepp_index_t* ix, char* buf, size_t cap)
 
 static void free_records(krepp_batch* b)
 {
-  for (void* p : {(void*)b->d_rec_read, (void*)b->d_rec_slot, (void*)b->d_rec_hist, (void*)b->d_rec_flags, (void*)b->d_rec_match,
+  for (void* p : {(void*)b->d_rec_work, (void*)b->d_rec_read, (void*)b->d_rec_slot, (void*)b->d_rec_hist, (void*)b->d_rec_flags, (void*)b->d_rec_match,
                   (void*)b->d_rec_hdmin, (void*)b->d_rec_d, (void*)b->d_rec_v, (void*)b->d_rec_chisq, (void*)b->d_out_rec})
     if (p) cudaFree(p);
   if (b->h_rec) cudaFreeHost(b->h_rec);
   if (b->h_hist) cudaFreeHost(b->h_hist);
-  b->d_rec_read = b->d_rec_slot = b->d_rec_hist = b->d_rec_flags = b->d_rec_match = b->d_rec_hdmin = nullptr;
+  b->d_rec_read = b->d_rec_slot = b->d_rec_hist = b->d_rec_flags = b->d_rec_match = b->d_rec_hdmin = b->d_rec_work = nullptr;
   b->d_rec_d = b->d_rec_v = b->d_rec_chisq = nullptr; b->d_out_rec = nullptr; b->h_rec = nullptr; b->h_hist = nullptr;
 }
 
@@ -315,6 +318,7 @@ static int alloc_records(krepp_batch* b, uint32_t cap)
   b->rec_cap = cap;
   CU(cudaMalloc(&b->d_rec_read, 4ull * cap)); CU(cudaMalloc(&b->d_rec_slot, 4ull * cap)); CU(cudaMalloc(&b->d_rec_hist, 4ull * cap * stride));
   CU(cudaMalloc(&b->d_rec_flags, 4ull * cap)); CU(cudaMalloc(&b->d_rec_match, 4ull * cap)); CU(cudaMalloc(&b->d_rec_hdmin, 4ull * cap));
+  CU(cudaMalloc(&b->d_rec_work, 4ull * cap));
   CU(cudaMalloc(&b->d_rec_d, 8ull * cap)); CU(cudaMalloc(&b->d_rec_v, 8ull * cap)); CU(cudaMalloc(&b->d_rec_chisq, 8ull * cap));
   CU(cudaMalloc(&b->d_out_rec, sizeof(krepp_record_t) * (size_t)cap));
   CU(cudaMallocHost(&b->h_rec, sizeof(krepp_record_t) * (size_t)cap));
@@ -349,8 +353,8 @@ int krepp_batch_create(krepp_index_t* ix, const krepp_params_t* p, uint32_t max_
   CU(cudaMalloc(&b->d_bases, max_bases + 64)); CU(cudaMalloc(&b->d_offsets, 8ull * (max_reads + 1)));
   CU(cudaMalloc(&b->d_onmers, 4ull * max_reads)); CU(cudaMalloc(&b->d_wn, 8ull * max_reads)); CU(cudaMalloc(&b->d_hdfilt, 8ull * max_reads));
   CU(cudaMalloc(&b->d_rec_begin, 4ull * max_reads)); CU(cudaMalloc(&b->d_rec_count, 4ull * max_reads)); CU(cudaMalloc(&b->d_closest, 4ull * max_reads));
-  CU(cudaMalloc(&b->d_counters, 16)); CU(cudaMalloc(&b->d_stats, 32));
-  CU(cudaMallocHost(&b->h_counters, 16)); CU(cudaMallocHost(&b->h_stats, 32));
+  CU(cudaMalloc(&b->d_counters, 32)); CU(cudaMalloc(&b->d_stats, 32));
+  CU(cudaMallocHost(&b->h_counters, 32)); CU(cudaMallocHost(&b->h_stats, 32));
   CU(cudaMalloc(&b->d_out_read, sizeof(krepp_read_summary_t) * (size_t)max_reads));
   CU(cudaMallocHost(&b->h_read, sizeof(krepp_read_summary_t) * (size_t)max_reads));
   // per-warp scratch
@@ -405,7 +409,7 @@ static int enqueue(krepp_batch* b)
   krepp_index* ix = b->ix;
   const HostIndex& h = ix->host;
   cudaStream_t s = b->stream;
-  CU(cudaMemsetAsync(b->d_counters, 0, 16, s));
+  CU(cudaMemsetAsync(b->d_counters, 0, 32, s));
   CU(cudaMemsetAsync(b->d_stats, 0, 32, s));
   if (b->d_tap_count) CU(cudaMemsetAsync(b->d_tap_count, 0, 8, s));
   MatchArgs m{};
@@ -418,14 +422,14 @@ static int enqueue(krepp_batch* b)
   CU(launch_match(ix->dev, m, ix->resident_warps, ix->staged, b->d_tap != nullptr, s));
   CU(cudaEventRecord(b->evm1, s));
   SolveArgs sa{};
-  sa.n_reads = b->n_reads; sa.th = b->p.hdist_th; sa.k = h.k; sa.h = h.h; sa.n_records = b->rec_cap; sa.counters = b->d_counters;
+  sa.n_reads = b->n_reads; sa.th = b->p.hdist_th; sa.k = h.k; sa.h = h.h; sa.n_records = b->rec_cap; sa.counters = b->d_counters; sa.work = b->d_rec_work;
   sa.onmers = b->d_onmers; sa.hdfilt = b->d_hdfilt; sa.rec_begin = b->d_rec_begin; sa.rec_count = b->d_rec_count;
   sa.rec_read = b->d_rec_read; sa.rec_slot = b->d_rec_slot; sa.rec_hist = b->d_rec_hist; sa.rho = ix->dev.rho;
   sa.rec_d = b->d_rec_d; sa.rec_v = b->d_rec_v; sa.rec_chisq = b->d_rec_chisq; sa.rec_flags = b->d_rec_flags; sa.rec_match = b->d_rec_match;
   sa.rec_hdmin = b->d_rec_hdmin; sa.closest = b->d_closest;
   sa.want_chisq = (!b->p.no_filter || b->p.summarize || b->p.place) ? 1 : 0;
   CU(launch_solve(sa, b->tab, ix->sms, s));
-  b->launches = 4 + (sa.want_chisq ? 1 : 0);
+  b->launches = 5 + (sa.want_chisq ? 1 : 0);
   if (b->p.place) {
     PlaceArgs pa{};
     pa.s = sa; pa.offsets = b->in_offsets; pa.tau = b->p.tau; pa.no_filter = b->p.no_filter; pa.chisq_value = b->p.chisq;
@@ -440,7 +444,7 @@ static int enqueue(krepp_batch* b)
   finalize_kernel<<<ix->sms * 4, 128, 0, s>>>(sa, b->d_out_rec, b->d_out_read, b->d_wn, b->d_place_begin, b->d_place_count);
   CU(cudaGetLastError());
   CU(cudaEventRecord(b->ev1, s)); // kernels only: [ev0, ev1] excludes the host<->device copies on both sides
-  CU(cudaMemcpyAsync(b->h_counters, b->d_counters, 16, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(b->h_counters, b->d_counters, 32, cudaMemcpyDeviceToHost, s));
   CU(cudaMemcpyAsync(b->h_stats, b->d_stats, 32, cudaMemcpyDeviceToHost, s));
   CU(cudaMemcpyAsync(b->h_read, b->d_out_read, sizeof(krepp_read_summary_t) * (size_t)b->n_reads, cudaMemcpyDeviceToHost, s));
   return KREPP_OK;

@@ -18,7 +18,8 @@ struct DevIndex {
                             //                                     ref FlatHT::inc_v   src/table.hpp:142
   const uint2* pse;         // nsubsets x (first, second)          ref CRecord::se_to_pse src/record.hpp:103
   const uint8_t* kind;      // nsubsets: 0 drop, 1 leaf, 2 expand  ref src/query.cpp:373-386
-  const uint32_t* cinfo;    // nsubsets: kind and leaf rank in one word: 0 drop, 0x80000000 | rank leaf, 0x40000000 expand
+  const uint2* cnode;       // nsubsets: colour DAG node in one 8-byte word: x = 0 drop, 0x80000000 | leaf rank, or
+                            //           0x40000000 | first child with y = second child
   const double* rho;        // by se, scaled                        ref CRecord::se_to_rho src/record.hpp:104
   const uint32_t* leaf_rank;// by se
   const uint32_t* leaf_se;  // by rank
@@ -51,7 +52,7 @@ struct MatchArgs {
   uint32_t* rec_slot;         // [cap]  strand<<31 | leaf_se
   uint32_t* rec_hist;         // [cap * (th+1)]
   uint32_t rec_cap;
-  uint32_t* counters;         // [0] records reserved, [1] next read to claim, [2] error flags
+  uint32_t* counters;         // [0] records reserved, [1] next read to claim, [2] error flags, [3] placements, [4] solve work items
   // per-warp scratch in HBM (sized by the host from the resident warp count)
   uint32_t* acc;              // [warps][2*nleaves*(th+1)] Hamming histograms being accumulated
   uint32_t* bitmap;           // [warps][ceil(2*nleaves/32)] touched (strand, leaf) slots
@@ -71,7 +72,8 @@ constexpr uint32_t kErrRecOverflow = 1u, kErrStackOverflow = 2u, kErrPlaceOverfl
 struct SolveArgs {
   uint32_t n_reads, th, k, h;
   uint32_t n_records;                // filled from counters[0] on the device when 0xffffffff
-  const uint32_t* counters;
+  uint32_t* counters;                // [0] records, [2] error flags, [4] length of `work`
+  uint32_t* work;                    // [n_records] indices of the records that pass the hdist_filt gate (unordered)
   const uint32_t* onmers; const uint32_t* hdfilt;
   const uint32_t* rec_begin; const uint32_t* rec_count;
   const uint32_t* rec_read; const uint32_t* rec_slot; const uint32_t* rec_hist;

@@ -35,22 +35,25 @@
 
 namespace krepp {
 
-constexpr int kWarpsLane = 8, kWarpsStaged = 16; // warps per CTA: the staged path runs one 512-thread CTA per SM so that the LUT is staged once
+constexpr int kWarpsLane = 8, kWarpsStaged = 14; // warps per CTA: the staged path runs one big CTA per SM so that the LUT is staged once
 __host__ __device__ constexpr int warps_per_cta(bool staged) { return staged ? kWarpsStaged : kWarpsLane; }
 constexpr int kTileWindows = 128;              // windows handled per tile: 4 per lane
 constexpr int kTileWords = 12;                 // 16 bases per 32-bit word -> 192 bases >= 128 + 32 - 1
 constexpr int kLocalStack = 32;
 constexpr uint32_t kClaim = 4;                // reads claimed per atomic on the global work counter
 constexpr int kMaxLookups = 2 * kTileWindows;  // both strands
-constexpr int kChunk = 128;                    // staged path: bucket entries per ring slot (4 per lane)
-constexpr int kSlotEntries = kChunk + 2;       // + 16-byte alignment slack at either end of a chunk
-constexpr int kStages = 5;                     // ring slots per warp: up to ~5 kB of bucket reads in flight per warp
-constexpr int kHitCap = 256;                   // staged path: hit entries queued per warp between two resolutions
-constexpr int kTabSize = 512;                  // staged path: (lookup, leaf) -> min distance table, open addressing
+// staged path: a ROUND is four lookups, one per group of eight lanes; each lookup's bucket (<= kChunk entries; longer
+// buckets take the whole-warp path) is bulk-copied into its own ring slot, two rounds are in flight per warp
+constexpr int kChunk = 128;                    // bucket entries per ring slot (16 per lane of the group)
+constexpr int kSlotEntries = kChunk + 2;       // + 16-byte alignment slack at either end of a bucket
+constexpr int kGroups = 4, kRoundsInFlight = 2, kSlots = kGroups * kRoundsInFlight;
+constexpr int kLongCap = 16;                   // pending lookups with more than kChunk entries
+constexpr int kHitCap = 96;                    // hit entries queued per warp between two resolutions
+constexpr int kTabSize = 512;                  // (lookup, leaf) -> min distance table, open addressing (about 2 leaves per hit)
 constexpr uint32_t kTabEmpty = 0xFFFFFFFFu;    // lookup id 127 is never handed out
 constexpr uint32_t kTabMaxLeaves = 1u << 19;   // leaf ranks must fit the table key
 constexpr uint32_t kTagStart = 0x07FFFFFEu;    // marker tags count down from here; 0x07FFFFFF is the rest value's tag
-constexpr uint32_t kInfoLeaf = 0x80000000u, kInfoExpand = 0x40000000u; // DevIndex::cinfo
+constexpr uint32_t kInfoLeaf = 0x80000000u, kInfoExpand = 0x40000000u; // DevIndex::cnode[].x: leaf | rank, or expand | first child (.y = second child)
 
 struct WarpSmem {
   uint32_t lk_a[kMaxLookups];  // A1: row offset | strand<<31; A2: first entry of the bucket
@@ -61,13 +64,14 @@ struct WarpSmem {
   uint32_t cursor;
 };
 struct __align__(16) WarpStage {              // staged path only
-  unsigned long long bar[kStages + 1];        // one mbarrier per ring slot (+1: keeps the rest 16-byte aligned)
-  uint2 ent[kStages][kSlotEntries];           // slot stride 1040 B = 65 x 16
+  unsigned long long bar[kRoundsInFlight];    // one mbarrier per round in flight
+  uint2 ent[kSlots][kSlotEntries];            // ring slots, 16-byte aligned
   uint2 hitq[kHitCap];                        // queued hit entries: {colour id, lookup id << 25 | strand << 24 | hd}
   uint32_t tab[kTabSize];                     // lookup id << 25 | strand << 24 | leaf rank << 5 | min hd
+  uint32_t lg_a[kLongCap], lg_l[kLongCap], lg_q[kLongCap]; // lookups with more than kChunk entries (first, len | strand << 31, q)
   uint32_t ovf, pad[3];
 };
-static_assert(sizeof(WarpStage) % 16 == 0, "ring slots must stay 16-byte aligned");
+static_assert(sizeof(WarpStage) % 16 == 0 && (kSlotEntries * 8) % 16 == 0, "ring slots must stay 16-byte aligned");
 // LUT layout: [byte of the k-mer word][byte value] -> {rix fwd, q fwd, rix rc, q rc} parts; 7 bytes cover k <= 28
 // lut_pext always reads the first seven byte tables, so at least seven are staged (all-zero past the k-mer's last byte)
 __host__ __device__ inline uint32_t lut_chunks(uint32_t k) { const uint32_t n = (2 * k + 7) / 8; return n < 7 ? 7 : n; }
@@ -168,9 +172,10 @@ __device__ __forceinline__ void expand_local(const DevIndex& ix, const WarpCtx& 
   st[sp++] = se;
   while (sp) {
     const uint32_t s = st[--sp];
-    const uint32_t ci = __ldg(&ix.cinfo[s]);
+    const uint2 cn = __ldg(&ix.cnode[s]);
+    const uint32_t ci = cn.x;
     if (ci & kInfoLeaf) { if (tagbase == 0xFFFFFFFFu) commit(w, strand, ci & 0x3FFFFFFFu, hd); else leaf_hit(w, strand, ci & 0x3FFFFFFFu, hd, tagbase); }
-    else if (ci & kInfoExpand) { const uint2 c = __ldg(&ix.pse[s]); st[sp++] = c.y; st[sp++] = c.x; }
+    else if (ci & kInfoExpand) { st[sp++] = cn.y; st[sp++] = ci & 0x3FFFFFFFu; }
   }
 }
 
@@ -184,7 +189,8 @@ __device__ void expand_coop(const DevIndex& ix, const WarpCtx& w, uint32_t se, u
   while (size) {
     const uint32_t take = min(size, 32u);
     uint32_t s = 0, ci = 0;
-    if (lane < take) { s = w.stack[size - 1 - lane]; ci = __ldg(&ix.cinfo[s]); }
+    uint2 cn = make_uint2(0u, 0u);
+    if (lane < take) { s = w.stack[size - 1 - lane]; cn = __ldg(&ix.cnode[s]); ci = cn.x; }
     __syncwarp();
     size -= take;
     if (ci & kInfoLeaf) { if (tagbase == 0xFFFFFFFFu) commit(w, strand, ci & 0x3FFFFFFFu, hd); else leaf_hit(w, strand, ci & 0x3FFFFFFFu, hd, tagbase); }
@@ -193,9 +199,8 @@ __device__ void expand_coop(const DevIndex& ix, const WarpCtx& w, uint32_t se, u
     const uint32_t nex = __popc(ex);
     if (size + 2 * nex > w.stack_cap) { if (lane == 0) atomicOr(w.err, kErrStackOverflow); return; }
     if (expand) {
-      const uint2 c = __ldg(&ix.pse[s]);
       const uint32_t at = size + 2 * __popc(ex & ((1u << lane) - 1));
-      w.stack[at] = c.x; w.stack[at + 1] = c.y;
+      w.stack[at] = ci & 0x3FFFFFFFu; w.stack[at + 1] = cn.y;
     }
     size += 2 * nex;
     __syncwarp();
@@ -232,8 +237,8 @@ __device__ __forceinline__ uint32_t next_tag(const WarpCtx& w, uint32_t& tag)
 // the value keeps the minimum distance.  Any number of lanes may insert concurrently (shared-memory atomics only).
 __device__ __forceinline__ void tab_insert(WarpStage* stg, uint32_t v)
 {
-  uint32_t slot = ((v >> 5) * 0x9E3779B1u) >> 23; // 9 bits
-  for (int probes = 0; probes < 48; ++probes) {
+  uint32_t slot = ((v >> 5) * 0x9E3779B1u) >> 23; // 9 bits = kTabSize
+  for (int probes = 0; probes < 96; ++probes) {
     const uint32_t old = atomicCAS(&stg->tab[slot], kTabEmpty, v);
     if (old == kTabEmpty) return;
     if (((old ^ v) >> 5) == 0) { atomicMin(&stg->tab[slot], v); return; }
@@ -249,9 +254,10 @@ __device__ __forceinline__ void expand_to_table(const DevIndex& ix, WarpStage* s
   st[sp++] = se;
   while (sp) {
     const uint32_t s = st[--sp];
-    const uint32_t ci = __ldg(&ix.cinfo[s]);
+    const uint2 cn = __ldg(&ix.cnode[s]);
+    const uint32_t ci = cn.x;
     if (ci & kInfoLeaf) tab_insert(stg, (meta & 0xFF000000u) | ((ci & 0x7FFFFu) << 5) | (meta & 31u));
-    else if (ci & kInfoExpand) { const uint2 c = __ldg(&ix.pse[s]); st[sp++] = c.y; st[sp++] = c.x; }
+    else if (ci & kInfoExpand) { st[sp++] = cn.y; st[sp++] = ci & 0x3FFFFFFFu; }
   }
 }
 
@@ -271,24 +277,30 @@ __device__ void resolve_hits(const DevIndex& ix, const WarpCtx& w, WarpStage* st
     if (!overflow) commit(w, (v >> 24) & 1u, (v >> 5) & 0x7FFFFu, v & 31u);
   }
   __syncwarp();
-  if (overflow) { // rare: more distinct (lookup, leaf) pairs than the table holds -- lookup by lookup through the markers
+  if (overflow) { // more distinct (lookup, leaf) pairs than the table holds: lookup by lookup through the markers instead
     if (lane == 0) stg->ovf = 0;
-    for (uint32_t id = 0; id < n_ids; ++id) {
-      const uint32_t tagbase = next_tag(w, tag);
-      for (uint32_t i = lane; i < n_hits; i += 32) {
-        const uint2 h = stg->hitq[i];
-        if ((h.y >> 25) == id) expand_local(ix, w, h.x, (h.y >> 24) & 1u, h.y & 31u, tagbase);
-      }
+    uint32_t pos = 0, last_id = 0xFFFFFFFFu, tagbase = 0;
+    while (pos < n_hits) { // the queue is ordered by lookup id
+      const uint32_t id = stg->hitq[pos].y >> 25;
+      if (id != last_id) { tagbase = next_tag(w, tag); last_id = id; }
+      const uint32_t i = pos + lane;
+      uint2 h = make_uint2(0u, 0u);
+      if (i < n_hits) h = stg->hitq[i];
+      const uint32_t same = __ballot_sync(0xFFFFFFFFu, i < n_hits && (h.y >> 25) == id);
+      const uint32_t run = __ffs(~same) - 1; // entries of this lookup at the head of the window (>= 1)
+      if (lane < run) expand_local(ix, w, h.x, (h.y >> 24) & 1u, h.y & 31u, tagbase);
       __syncwarp();
+      pos += run;
     }
   }
 }
 
 // Small-bucket path: one lookup with several hit entries (or a colour too deep for the private stack), rescanned by the
 // whole warp in a single pass.
-__device__ void careful_lookup(const DevIndex& ix, const WarpCtx& w, uint32_t begin, uint32_t len, uint32_t q, uint32_t strand, uint32_t th, uint32_t tagbase)
+__device__ uint32_t careful_lookup(const DevIndex& ix, const WarpCtx& w, uint32_t begin, uint32_t len, uint32_t q, uint32_t strand, uint32_t th, uint32_t tagbase)
 {
   const uint32_t lane = threadIdx.x & 31;
+  uint32_t best = 0xFFFFFFFFu; // this lane's smallest distance among the hit entries
   __syncwarp(); // lanes still expanding hits of the previous lookup must not meet this lookup's (smaller) tag in the markers
   for (uint32_t base = 0; base < len; base += 32) {
     uint32_t se = 0, hd = 0xFFFFFFFFu;
@@ -298,8 +310,10 @@ __device__ void careful_lookup(const DevIndex& ix, const WarpCtx& w, uint32_t be
       hd = __popc((z | (z >> 16)) & 0xFFFFu);
       se = e.y;
     }
+    if (hd <= th) best = min(best, hd);
     expand_hits(ix, w, hd <= th, se, hd, strand, tagbase);
   }
+  return best;
 }
 
 template <bool STAGED, bool TAP>
@@ -320,7 +334,7 @@ __global__ void __launch_bounds__(warps_per_cta(STAGED) * 32, STAGED ? 1 : 4) ma
     for (uint32_t i = lane; i < (uint32_t)kTabSize; i += 32) stg->tab[i] = kTabEmpty;
     if (lane == 0) {
       stg->ovf = 0;
-      for (int i = 0; i < kStages; ++i) mbar_init(smem_u32(&stg->bar[i]), 1);
+      for (int i = 0; i < kRoundsInFlight; ++i) mbar_init(smem_u32(&stg->bar[i]), 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       asm volatile("fence.proxy.async;" ::: "memory");
     }
@@ -337,8 +351,9 @@ __global__ void __launch_bounds__(warps_per_cta(STAGED) * 32, STAGED ? 1 : 4) ma
   w.stack = a.stack + (size_t)gwarp * a.stack_cap;
   w.stack_cap = a.stack_cap; w.stride = stride; w.nleaves = nleaves; w.err = a.counters + 2;
   uint32_t tag = min(a.tagctr[gwarp], kTagStart);   // persists across launches: markers are never cleared in between
-  uint32_t p_slot = 0, c_slot = 0, c_par = 0, n_fly = 0; // ring state of this warp over the whole launch (mbarrier phases)
+  uint32_t p_round = 0, c_round = 0;                // rounds issued / consumed by this warp over the whole launch (mbarrier phases)
   const bool use_table = STAGED && ix.local_expand && nleaves <= kTabMaxLeaves;
+  const uint32_t bar0 = STAGED ? smem_u32(&stg->bar[0]) : 0u, ent0 = STAGED ? smem_u32(&stg->ent[0][0]) : 0u;
 
   unsigned long long st_bytes = 0, st_lookups = 0, st_entries = 0;
 
@@ -443,7 +458,17 @@ __global__ void __launch_bounds__(warps_per_cta(STAGED) * 32, STAGED ? 1 : 4) ma
 
       // ---- A2. bucket ranges [inc[off-1], inc[off]) with all loads of the tile in flight; empty buckets are dropped
       //          (in-place compaction: writes trail reads)
-      uint32_t nout = 0;
+      uint32_t nout = 0, n_long = 0;
+      auto flush_long = [&]() { // long buckets: scanned by the whole warp straight from HBM, deduplicated through the markers
+        __syncwarp();
+        for (uint32_t j = 0; j < n_long; ++j) {
+          const uint32_t l = stg->lg_l[j];
+          const uint32_t best = careful_lookup(ix, w, stg->lg_a[j], l & 0x7FFFFFFFu, stg->lg_q[j], l >> 31, th, next_tag(w, tag));
+          if (l >> 31) filt1 = min(filt1, best); else filt0 = min(filt0, best);
+        }
+        __syncwarp();
+        n_long = 0;
+      };
       for (uint32_t base = 0; base < nl; base += 128) {
         uint32_t qv[4], bg[4], en[4], sb[4];
 #pragma unroll
@@ -464,7 +489,16 @@ __global__ void __launch_bounds__(warps_per_cta(STAGED) * 32, STAGED ? 1 : 4) ma
           const uint32_t i = base + 32 * u + lane;
           const uint32_t blen = en[u] - bg[u];
           if (i < nl) { st_lookups += 1; st_entries += blen; }
-          const bool keep = i < nl && blen != 0;
+          const bool lng = STAGED && i < nl && blen > (uint32_t)kChunk; // staged path: too long for a ring slot
+          if (STAGED) {
+            const uint32_t lm = __ballot_sync(0xFFFFFFFFu, lng);
+            if (lm) {
+              if (n_long + __popc(lm) > (uint32_t)kLongCap) { flush_long(); }
+              if (lng) { const uint32_t o = n_long + __popc(lm & lt_mask); stg->lg_a[o] = bg[u]; stg->lg_l[o] = blen | sb[u]; stg->lg_q[o] = qv[u]; }
+              n_long += __popc(lm);
+            }
+          }
+          const bool keep = i < nl && blen != 0 && !lng;
           const uint32_t km = __ballot_sync(0xFFFFFFFFu, keep);
           if (keep) {
             const uint32_t o = nout + __popc(km & lt_mask);
@@ -473,6 +507,28 @@ __global__ void __launch_bounds__(warps_per_cta(STAGED) * 32, STAGED ? 1 : 4) ma
           nout += __popc(km);
         }
         __syncwarp();
+      }
+
+      if (STAGED && n_long) {
+        // Buckets of up to kGroups * kChunk entries become rounds of their own at the end of the list: one slot per
+        // kChunk entries, all groups under the lookup's single id (bit 30 of the length word).  Anything longer, or
+        // whatever does not fit the list, takes the whole-warp path.
+        bool fits = ((nout + 3u) & ~3u) + (uint32_t)kGroups * n_long <= (uint32_t)kMaxLookups;
+        for (uint32_t j = 0; j < n_long && fits; ++j) fits = (stg->lg_l[j] & 0x7FFFFFFFu) <= (uint32_t)(kGroups * kChunk);
+        if (!fits) flush_long();
+        else {
+          __syncwarp();
+          for (uint32_t i = nout + lane; i < ((nout + 3u) & ~3u); i += 32) { sm.lk_a[i] = 0; sm.lk_l[i] = 0; sm.lk_q[i] = 0; } // idle groups
+          nout = (nout + 3u) & ~3u;
+          for (uint32_t i = lane; i < (uint32_t)kGroups * n_long; i += 32) {
+            const uint32_t j = i / kGroups, c = i % kGroups, l = stg->lg_l[j], blen = l & 0x7FFFFFFFu;
+            const uint32_t cnt = blen > c * kChunk ? min((uint32_t)kChunk, blen - c * kChunk) : 0u;
+            sm.lk_a[nout + i] = stg->lg_a[j] + c * kChunk; sm.lk_l[nout + i] = cnt | (l & 0x80000000u) | 0x40000000u; sm.lk_q[nout + i] = stg->lg_q[j];
+          }
+          nout += (uint32_t)kGroups * n_long;
+          n_long = 0;
+          __syncwarp();
+        }
       }
 
       // ---- B. bucket scans.
@@ -505,7 +561,7 @@ __global__ void __launch_bounds__(warps_per_cta(STAGED) * 32, STAGED ? 1 : 4) ma
           if (e >= hi) {
             have = false;
             if (cnt == 1) { // exactly one hit entry: no other entry can lower a leaf's distance
-              const uint32_t ci = __ldg(&ix.cinfo[fse]);
+              const uint32_t ci = __ldg(&ix.cnode[fse]).x;
               if (ci & kInfoLeaf) commit(w, cs, ci & 0x3FFFFFFFu, fhd);
               else if (ci & kInfoExpand) { if (ix.local_expand) expand_local(ix, w, fse, cs, fhd, 0xFFFFFFFFu); else cnt = 2; }
             }
@@ -524,68 +580,101 @@ __global__ void __launch_bounds__(warps_per_cta(STAGED) * 32, STAGED ? 1 : 4) ma
           }
         }
       } else {
-        // Large buckets: the list's buckets are cut into chunks of kChunk entries and streamed through the ring.  All
-        // cursors are warp-uniform; lane 0 issues the bulk copies.  Hit entries are queued and resolved in batches
-        // (resolve_hits) so that colour expansion and deduplication run with all lanes busy; only lookups larger than
-        // the queue go through the marker path on the spot.
-        uint32_t p_idx = 0, p_off = 0, c_idx = 0, c_off = 0, tagbase = 0, n_hits = 0, lk_id = 0;
-        bool big = false;
-        auto issue = [&]() {
-          const uint32_t blen = sm.lk_l[p_idx] & 0x7FFFFFFFu, first = sm.lk_a[p_idx] + p_off;
-          const uint32_t cnt = min((uint32_t)kChunk, blen - p_off);
-          if (lane == 0) {
-            const uint32_t a0 = first & ~1u, a1 = (first + cnt + 1) & ~1u;  // 16-byte aligned source range (cmer is padded)
-            const uint32_t bar = smem_u32(&stg->bar[p_slot]);
-            mbar_expect_tx(bar, (a1 - a0) * 8u);
-            bulk_g2s(smem_u32(&stg->ent[p_slot][0]), ix.cmer + a0, (a1 - a0) * 8u, bar);
+        // Large buckets: rounds of four lookups, one per group of eight lanes.  The four buckets of a round are bulk-copied
+        // into four ring slots under one mbarrier, two rounds ahead of the scan; every lane then compares 16 rows of
+        // its group's slot.  Hit entries are queued and resolved in batches (resolve_hits) so that colour expansion and
+        // deduplication run with all lanes busy.  All cursors are warp-uniform.
+        constexpr uint32_t kSlotBytes = kSlotEntries * 8;
+        const uint32_t gl = lane & 7u, grp = lane >> 3;
+        uint32_t p_idx = 0, c_idx = 0, n_hits = 0, lk_id = 0;
+        auto issue_round = [&]() {
+          const uint32_t idx = p_idx + grp;
+          const bool leader = gl == 0 && idx < nout;
+          uint32_t a0 = 0, bytes = 0;
+          if (leader) {
+            const uint32_t first = sm.lk_a[idx], cnt = sm.lk_l[idx] & 0x3FFFFFFFu;
+            a0 = first & ~1u;                                     // 16-byte aligned source range (cmer is padded)
+            bytes = cnt ? (((first + cnt + 1) & ~1u) - a0) * 8u : 0u;
           }
-          p_slot = (p_slot + 1 == (uint32_t)kStages) ? 0u : p_slot + 1;
-          ++n_fly;
-          p_off += cnt;
-          if (p_off >= blen) { ++p_idx; p_off = 0; }
+          uint32_t total = bytes;
+          total += __shfl_xor_sync(0xFFFFFFFFu, total, 8);
+          total += __shfl_xor_sync(0xFFFFFFFFu, total, 16);
+          const uint32_t bar = bar0 + 8u * (p_round & 1u);
+          if (lane == 0) mbar_expect_tx(bar, total);
+          if (leader && bytes) bulk_g2s(ent0 + kSlotBytes * ((p_round & 1u) * kGroups + grp), ix.cmer + a0, bytes, bar);
+          p_idx = min(p_idx + (uint32_t)kGroups, nout);
+          ++p_round;
         };
-        while (p_idx < nout && n_fly < (uint32_t)kStages) issue();
-        while (n_fly) {
-          const uint32_t l = sm.lk_l[c_idx], blen = l & 0x7FFFFFFFu, cs = l >> 31, cq = sm.lk_q[c_idx];
-          const uint32_t first = sm.lk_a[c_idx] + c_off, cnt = min((uint32_t)kChunk, blen - c_off);
-          if (c_off == 0) { // a new lookup starts
-            big = !use_table || blen > (uint32_t)kHitCap;
-            if (big) tagbase = next_tag(w, tag); // the __syncwarp below orders this lookup's hits after the previous one's
-            else if (n_hits + blen > (uint32_t)kHitCap || lk_id >= 126u) { resolve_hits(ix, w, stg, n_hits, lk_id, tag); n_hits = 0; lk_id = 0; }
-          }
-          mbar_wait(smem_u32(&stg->bar[c_slot]), c_par);
-          const uint2* sp = &stg->ent[c_slot][first & 1u];
-          uint2 ent[kChunk / 32];
+        while (p_idx < nout && p_round - c_round < (uint32_t)kRoundsInFlight) issue_round();
+        while (c_idx < nout) {
+          const uint32_t idx = c_idx + grp;
+          uint32_t cnt = 0, cs = 0, cq = 0, first = 0, shared_id = 0;
+          if (idx < nout) { const uint32_t l = sm.lk_l[idx]; cnt = l & 0x3FFFFFFFu; cs = l >> 31; shared_id = (l >> 30) & 1u; cq = sm.lk_q[idx]; first = sm.lk_a[idx]; }
+          const uint32_t nrows = (__reduce_max_sync(0xFFFFFFFFu, cnt) + 7u) >> 3;
+          mbar_wait(bar0 + 8u * (c_round & 1u), (c_round >> 1) & 1u);
+          const uint2* sp = &stg->ent[(c_round & 1u) * kGroups + grp][(first & 1u) + gl];
+          uint32_t hmask = 0; // one bit per row, shifted in from the right: row r of the nrows4 processed ends at bit nrows4-1-r
+          const uint32_t thp1 = th + 1, nrows4 = (nrows + 3u) & ~3u;
+          for (uint32_t r = 0; r < nrows; r += 4) {
+            uint2 e4[4];
 #pragma unroll
-          for (int h = 0; h < kChunk / 32; ++h) ent[h] = sp[lane + 32 * h]; // past cnt: stale bytes of the slot, masked below
-          __syncwarp();               // every lane has its entries in registers: the slot may be refilled
-          if (++c_slot == (uint32_t)kStages) { c_slot = 0; c_par ^= 1u; }
-          --n_fly;
-          c_off += cnt;
-          const bool last = c_off >= blen;
-          if (last) { ++c_idx; c_off = 0; }
-          if (p_idx < nout) issue();
-          uint32_t hd[kChunk / 32], hmask = 0;
+            for (int j = 0; j < 4; ++j) e4[j] = sp[8 * (r + j)];   // past cnt: stale bytes of the slot, masked below
 #pragma unroll
-          for (int h = 0; h < kChunk / 32; ++h) {
-            const uint32_t z = ent[h].x ^ cq;
-            hd[h] = __popc((z | (z >> 16)) & 0xFFFFu);
-            hmask |= (uint32_t)(hd[h] <= th && lane + 32 * h < cnt) << h;
-          }
-          if (__any_sync(0xFFFFFFFFu, hmask != 0)) {
-#pragma unroll
-            for (int h = 0; h < kChunk / 32; ++h) {
-              const bool hit = (hmask >> h) & 1u;
-              if (hit) { if (cs) filt1 = min(filt1, hd[h]); else filt0 = min(filt0, hd[h]); }
-              if (big) expand_hits(ix, w, hit, ent[h].y, hd[h], cs, tagbase);
-              else {
-                const uint32_t bm = __ballot_sync(0xFFFFFFFFu, hit);
-                if (hit) stg->hitq[n_hits + __popc(bm & lt_mask)] = make_uint2(ent[h].y, lk_id << 25 | cs << 24 | hd[h]);
-                n_hits += __popc(bm);
-              }
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t z = e4[j].x ^ cq;
+              const uint32_t hd = __popc((z | (z >> 16)) & 0xFFFFu);
+              hmask = __funnelshift_l(hd - thp1, hmask, 1);         // hd <= th  <=>  the sign bit of hd - (th + 1)
             }
           }
-          if (last && !big) ++lk_id;
+          { // rows this lane really owns: gl + 8 r < cnt
+            const uint32_t own = cnt > gl ? (cnt - gl + 7u) >> 3 : 0u;                // rows 0 .. own-1
+            const uint32_t keep = own ? (0xFFFFFFFFu >> (32u - own)) << (nrows4 - own) : 0u; // their (reversed) bit positions
+            hmask &= keep;
+          }
+          if (__any_sync(0xFFFFFFFFu, hmask != 0)) {
+            const uint32_t mine = __popc(hmask), total = __reduce_add_sync(0xFFFFFFFFu, mine);
+            if (!use_table || total > (uint32_t)kHitCap) {
+              // marker path: the round's lookups one after the other, each under its own tag
+              const bool one_lookup = __shfl_sync(0xFFFFFFFFu, shared_id, 0) != 0; // a long bucket spread over the groups
+              uint32_t tagbase = 0;
+              for (uint32_t g = 0; g < (uint32_t)kGroups; ++g) {
+                if (!__any_sync(0xFFFFFFFFu, grp == g && hmask != 0)) continue;
+                if (!one_lookup || !tagbase) tagbase = next_tag(w, tag);
+                const uint32_t gcs = __shfl_sync(0xFFFFFFFFu, cs, 8 * g);
+                __syncwarp();
+                for (uint32_t r = 0; r < nrows4; ++r) {
+                  const bool hit = grp == g && ((hmask >> (nrows4 - 1u - r)) & 1u);
+                  if (!__any_sync(0xFFFFFFFFu, hit)) continue;
+                  uint32_t se = 0, hd = 0;
+                  if (hit) { const uint2 e = sp[8 * r]; const uint32_t z = e.x ^ cq; hd = __popc((z | (z >> 16)) & 0xFFFFu); se = e.y; if (cs) filt1 = min(filt1, hd); else filt0 = min(filt0, hd); }
+                  expand_hits(ix, w, hit, se, hd, gcs, tagbase);
+                }
+                __syncwarp();
+              }
+            } else {
+              if (n_hits + total > (uint32_t)kHitCap || lk_id + (uint32_t)kGroups > 126u) { resolve_hits(ix, w, stg, n_hits, lk_id, tag); n_hits = 0; lk_id = 0; }
+              uint32_t incl = mine;
+#pragma unroll
+              for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += t; }
+              uint32_t at = n_hits + incl - mine, m = hmask;
+              const uint32_t meta = (lk_id + (shared_id ? 0u : grp)) << 25 | cs << 24;
+              while (m) {
+                const uint32_t bit = 31u - __clz(m), r = nrows4 - 1u - bit; // highest bit first = ascending row
+                m ^= 1u << bit;
+                const uint2 e = sp[8 * r];
+                const uint32_t z = e.x ^ cq, hd = __popc((z | (z >> 16)) & 0xFFFFu);
+                if (cs) filt1 = min(filt1, hd); else filt0 = min(filt0, hd);
+                stg->hitq[at++] = make_uint2(e.y, meta | hd);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(ix.cnode + e.y)); // resolved later: have the colour node on its way
+              }
+              n_hits += total;
+            }
+          }
+          lk_id += kGroups;
+          __syncwarp();               // every lane is done with the round's slots: they may be refilled
+          c_idx = min(c_idx + (uint32_t)kGroups, nout);
+          ++c_round;
+          if (p_idx < nout) issue_round();
         }
         if (n_hits) resolve_hits(ix, w, stg, n_hits, lk_id, tag);
       }

@@ -94,33 +94,53 @@ __device__ void brent_minimum(const Objective& f, double& xo, double& fo)
   xo = x; fo = fx;
 }
 
-// One thread per record: match_count / hdist_min from the histogram, the hdist_filt gate, then Brent.
-__global__ void __launch_bounds__(128) solve_kernel(const SolveArgs a, const LlhTables tab)
+// One thread per record: match_count / hdist_min from the histogram and the hdist_filt gate of summarize_matches (ref
+// src/query.cpp:101-106,116-119).  Records that pass are appended to a work list, so that the Brent kernel below runs
+// with full warps (on the 1,000-genome index only about a quarter of the records pass).
+__global__ void __launch_bounds__(256) gate_kernel(const SolveArgs a)
 {
   if (a.counters[2] & (kErrRecOverflow | kErrStackOverflow)) return; // the host grows the buffers and runs the batch again
   const uint32_t n = a.counters[0] < a.n_records ? a.counters[0] : a.n_records;
+  const uint32_t stride = a.th + 1, lane = threadIdx.x & 31;
+  const uint32_t nround = (n + 31) & ~31u; // whole warps stay together for the ballot
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += gridDim.x * blockDim.x) {
+    bool pass = false;
+    if (i < n) {
+      const uint32_t read = a.rec_read[i], strand = a.rec_slot[i] >> 31;
+      uint32_t match = 0, hdmin = 0xFFFFFFFFu;
+      for (uint32_t x = 0; x < stride; ++x) {
+        const uint32_t c = a.rec_hist[(size_t)i * stride + x];
+        match += c;
+        if (c && hdmin == 0xFFFFFFFFu) hdmin = x;
+      }
+      a.rec_match[i] = match; a.rec_hdmin[i] = hdmin;
+      const uint32_t filt = 2u * a.hdfilt[2 * read + strand] + 1u; // uint32 wrap kept (ref src/query.cpp:101-102)
+      pass = !(hdmin > filt);
+      a.rec_d[i] = DBL_MAX; a.rec_v[i] = nan(""); a.rec_flags[i] = 0; a.rec_chisq[i] = nan(""); // Minfo defaults (ref src/query.hpp:225-226)
+    }
+    const uint32_t pm = __ballot_sync(0xFFFFFFFFu, pass);
+    uint32_t base = 0;
+    if (lane == 0 && pm) base = atomicAdd(a.counters + 4, __popc(pm));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (pass) a.work[base + __popc(pm & ((1u << lane) - 1))] = i;
+  }
+}
+
+// One thread per work item: Brent on the record's histogram.
+__global__ void __launch_bounds__(128) solve_kernel(const SolveArgs a, const LlhTables tab)
+{
+  if (a.counters[2] & (kErrRecOverflow | kErrStackOverflow)) return;
+  const uint32_t n = a.counters[4];
   const uint32_t stride = a.th + 1;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint32_t read = a.rec_read[i], slot = a.rec_slot[i];
-    const uint32_t strand = slot >> 31, se = slot & 0x7FFFFFFFu;
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const uint32_t i = a.work[j];
+    const uint32_t read = a.rec_read[i], se = a.rec_slot[i] & 0x7FFFFFFFu;
     double mc[kMaxTh + 1];
-    uint32_t match = 0, hdmin = 0xFFFFFFFFu;
-    for (uint32_t x = 0; x < stride; ++x) {
-      const uint32_t c = a.rec_hist[(size_t)i * stride + x];
-      mc[x] = (double)c;
-      match += c;
-      if (c && hdmin == 0xFFFFFFFFu) hdmin = x;
-    }
-    a.rec_match[i] = match; a.rec_hdmin[i] = hdmin;
-    const uint32_t filt = 2u * a.hdfilt[2 * read + strand] + 1u; // uint32 wrap kept (ref src/query.cpp:101-102)
-    double d = DBL_MAX, v = nan(""); // Minfo defaults (ref src/query.hpp:225-226)
-    uint32_t flags = 0;
-    if (!(hdmin > filt)) {
-      Objective f{&tab, mc, (double)a.onmers[read] - (double)match, a.rho[se], a.k, a.th};
-      brent_minimum(f, d, v);
-      flags = 1u; // KREPP_REC_SOLVED
-    }
-    a.rec_d[i] = d; a.rec_v[i] = v; a.rec_flags[i] = flags; a.rec_chisq[i] = nan("");
+    for (uint32_t x = 0; x < stride; ++x) mc[x] = (double)a.rec_hist[(size_t)i * stride + x];
+    double d, v;
+    Objective f{&tab, mc, (double)a.onmers[read] - (double)a.rec_match[i], a.rho[se], a.k, a.th};
+    brent_minimum(f, d, v);
+    a.rec_d[i] = d; a.rec_v[i] = v; a.rec_flags[i] = 1u; // KREPP_REC_SOLVED
   }
 }
 
@@ -349,6 +369,7 @@ cudaError_t launch_place(const PlaceArgs& a, const LlhTables& tab, int grid, cud
 cudaError_t launch_solve(const SolveArgs& a, const LlhTables& tab, int sms, cudaStream_t stream)
 {
   const int grid = sms * 8;
+  gate_kernel<<<sms * 4, 256, 0, stream>>>(a);
   solve_kernel<<<grid, 128, 0, stream>>>(a, tab);
   merge_kernel<<<grid, 128, 0, stream>>>(a);
   if (a.want_chisq) chisq_kernel<<<grid, 128, 0, stream>>>(a, tab);
