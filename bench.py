@@ -1,19 +1,23 @@
 #!/usr/bin/env python
 """bench.py -- reads/s of the `krepp dist` hot path (BASELINE.json metric) on N B200s of one node.
 
-Workload at every N (weak scaling: per-GPU work is fixed): BASELINE.json configs[1] -- the reference-built toy index
-(25 genomes, -k 27 -w 35 -h 11) and 1,000,000 synthetic 150 bp reads per GPU, sampled from the toy genomes with
-probability proportional to contig length, per-read substitution rate U(0, 0.15), random strand, numpy default_rng
-seed 1 + rank (tools/synth.py).  A step = one pass of the hot path (match + solve + merge + finalize kernels) over
-those reads.
+Default workload (every N; weak scaling: per-GPU work is fixed, index replicated, reads sharded, no data-path
+collective): BASELINE.json configs[2] -- the configuration the metric and the HBM-gather roofline target are quoted on:
+a synthetic 1,000-genome index (1,000 x 3 Mbp on a random binary tree, k27 w35 h11, ~1.6 GB of (k-mer, colour) entries,
+~93 per bucket: far larger than L2) and 10,000,000 synthetic 150 bp reads PER GPU (0-15 % substitutions, random
+strand).  The workload is generated on the box by tools/synth_index (tools/workload.py; cached under /tmp).
+`--workload toy` runs configs[1] (reference-built toy index, 1 M reads per GPU) instead.
 
-  value        whole-job reads/s with the reads already resident in HBM (krepp_batch_submit_device), CUDA-event timed
+A step = one pass of the hot path (match + gate + solve + merge + finalize kernels) over the rank's reads, in batches.
+
+  value        whole-job reads/s with the reads already resident in HBM (krepp_batch_submit_device); time = sum of the
+               library's CUDA-event kernel spans of all batches of the step, max over ranks
   e2e          the same reads through the reference-facing C ABI with HOST buffers: krepp_batch_submit (H2D from
-               pinned memory) + krepp_batch_wait (D2H of the result structs), 4 slots pipelined, wall-clock timed
+               page-locked host memory) + krepp_batch_wait (D2H of all result structs), 4 slots pipelined, wall clock
   roofline     match kernel: algorithmic bytes (len + sum over lookups (16 + 8*|bucket|) + 64*records,
                counted on the device) / its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
   cpu_baseline the reference binary (oracle/_ref/krepp, unmodified, built by oracle/Makefile) on a bounded sample of
-               the same reads with --num-threads = host cores
+               the same reads against the same index with --num-threads = host cores
 
 `--impl reference` times that reference CPU path alone and prints the same JSON shape with "impl": "reference".
 """
@@ -37,22 +41,41 @@ for p in (ROOT, os.path.join(ROOT, "tools"), os.path.join(ROOT, "tests")):
 
 import numpy as np  # noqa: E402
 
-TOY = os.path.join(ROOT, "oracle", "_ref", "toy")
-INDEX = os.path.join(TOY, "index_toy")
+import workload as W  # noqa: E402
+
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "krepp")
-READS_PER_GPU = 1_000_000
-READ_LEN = 150
+READ_LEN = W.READ_LEN
 METRIC = "reads/sec (krepp dist, 150bp)"
-WORKLOAD = "configs[1]: toy index (25 genomes, k27 w35 h11), 1M synthetic 150bp reads per GPU, 0-15% substitutions"
-# dram__bytes_read.sum + dram__bytes_write.sum of one match_kernel launch on this workload, from the ncu --set full
-# capture summarised in profiles/ (None until a capture exists for the current kernel).
-NCU_TRAFFIC_BYTES = None
+DEFAULT_READS = {"c3": 10_000_000, "toy": 1_000_000}
+DEFAULT_BATCH = {"c3": 1_000_000, "toy": 1_000_000}
+WORKLOADS = {
+    "c3": "configs[2]: synthetic 1,000-genome index (1,000 x 3 Mbp on a random binary tree, k27 w35 h11), 10M synthetic 150bp reads per GPU, "
+          "0-15% substitutions, krepp dist, index replicated",
+    "toy": "configs[1]: toy index (25 genomes, k27 w35 h11), 1M synthetic 150bp reads per GPU, 0-15% substitutions",
+}
+# dram__bytes_read.sum + dram__bytes_write.sum of one match_kernel launch (ncu --set full, summarised under profiles/),
+# keyed by (workload, reads in that launch); scaled linearly to the launch size the bench uses.
+NCU_TRAFFIC = {"c3": (250_000, 28.898431e9 + 1.543418e9, "profiles/r01l_match_c3.txt")}
 
 
-def make_reads(n: int, seed: int) -> np.ndarray:
-    import synth
-    seq, offs = synth.load_packed(os.path.join(TOY, "genomes.npz"))
-    return synth.sample_reads(seq, offs, n, read_len=READ_LEN, seed=seed)
+class Workload:
+    def __init__(self, name: str, reads_per_gpu: int, rank: int, world: int, need_reads: bool = True):
+        self.name = name
+        if name == "toy":
+            self.index = os.path.join(W.TOY, "index_toy")
+            if not os.path.isdir(self.index):
+                raise SystemExit("oracle/_ref/toy/index_toy is missing: run __graft_entry__.build() where /root/reference exists")
+            self.reads = W.toy_reads(reads_per_gpu, seed=1 + rank) if need_reads else None
+            self.info = {"seed": "numpy default_rng(1 + rank)"}
+            self.fastq = None
+        else:
+            d, wl = W.ensure_c3(reads_per_gpu * world)
+            self.index = os.path.join(d, "index")
+            self.reads = W.c3_reads(d, rank * reads_per_gpu, reads_per_gpu) if need_reads else None
+            self.info = {"generator": "tools/synth_index seed 7 (splitmix64), built on this box", "nkmers": wl["nkmers"],
+                         "mean_bucket": wl["mean_bucket"], "nsubsets": wl["nsubsets"], "tree_nodes": wl["nnodes"],
+                         "reads": "rank r takes reads [r*n, (r+1)*n) of the generated pool (a uniform sample)"}
+            self.fastq = os.path.join(d, "reads.fq")  # first 200k reads of the pool = head of rank 0's reads
 
 
 def measured_peak_gbs() -> tuple[float, str]:
@@ -103,13 +126,26 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def run_reference(fastq: str, threads: int) -> tuple[float, int]:
+def run_reference(index: str, fastq: str, threads: int) -> tuple[float, int]:
     """Runs the unmodified reference CLI; returns (seconds of its own 'Done estimating distances' line, reads)."""
-    p = subprocess.run([REF_BIN, "--num-threads", str(threads), "dist", "-i", INDEX, "-q", fastq, "-o", os.devnull],
+    p = subprocess.run([REF_BIN, "--num-threads", str(threads), "dist", "-i", index, "-q", fastq, "-o", os.devnull],
                        capture_output=True, text=True, check=True)
     sec = float(re.search(r"Done estimating distances, elapsed: ([0-9.eE+-]+) sec", p.stderr).group(1))
     n = int(re.search(r"Total number of sequences queried: (\d+)", p.stderr).group(1))
     return sec, n
+
+
+def sample_fastq(wl: Workload, td: str, sample: int) -> str:
+    """FASTQ of the first `sample` reads of rank 0's reads."""
+    fq = os.path.join(td, "sample.fq")
+    if wl.fastq is not None:
+        with open(wl.fastq, "rb") as f, open(fq, "wb") as g:
+            for _ in range(4 * sample):
+                g.write(f.readline())
+    else:
+        import synth
+        synth.write_fastq(fq, wl.reads[:sample])
+    return fq
 
 
 def reference_arm(args) -> None:
@@ -119,24 +155,23 @@ def reference_arm(args) -> None:
     if not os.path.exists(REF_BIN):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/krepp not built (needs /root/reference at build time)"}))
         return
-    import synth
     cores = os.cpu_count() or 1
-    sample = 100_000  # bounded sample of the 1M-read workload per step
-    reads = make_reads(sample, seed=1)
+    sample = args.cpu_sample or {"c3": 50_000, "toy": 100_000}[args.workload]  # bounded sample of the workload per step
+    n = args.reads or DEFAULT_READS[args.workload]
+    wl = Workload(args.workload, n, 0, max(args.gpus, 1), need_reads=(args.workload == "toy"))
     with tempfile.TemporaryDirectory() as td:
-        fq = os.path.join(td, "sample.fq")
-        synth.write_fastq(fq, reads)
+        fq = sample_fastq(wl, td, sample)
         for _ in range(args.warmup):
-            run_reference(fq, cores)
-        secs = [run_reference(fq, cores)[0] for _ in range(args.steps)]
+            run_reference(wl.index, fq, cores)
+        secs = [run_reference(wl.index, fq, cores)[0] for _ in range(args.steps)]
     t = sum(secs) / len(secs)
     v = sample / t
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32/f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": f"{sample} of the 1M reads per step"},
+        "config": {"workload": WORKLOADS[args.workload], "sample": f"{sample} of the step's reads per step", **wl.info},
         "cpu_baseline": {"value": v, "unit": "reads/s", "cores": cores, "kind": "reference",
-                         "sample": f"{sample} reads per step, oracle/_ref/krepp --num-threads {cores} dist, its own elapsed line (index load excluded)"},
+                         "sample": f"{sample} reads per step, oracle/_ref/krepp --num-threads {cores} dist -o /dev/null, its own elapsed line (index load excluded)"},
         "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
@@ -146,8 +181,13 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--reads", type=int, default=READS_PER_GPU)
+    ap.add_argument("--workload", default="c3", choices=["c3", "toy"])
+    ap.add_argument("--reads", type=int, default=0, help="reads per GPU per step (default: 10M for c3, 1M for toy)")
+    ap.add_argument("--batch", type=int, default=0, help="reads per batch of the device-resident arm")
+    ap.add_argument("--e2e-batch", type=int, default=250_000)
+    ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
@@ -166,16 +206,13 @@ def main() -> None:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     assert max(world, 1) == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
 
-    n = args.reads
-    reads = make_reads(n, seed=1 + rank)
-    index = krepp_b200.Index(INDEX, local)
-    nbytes = n * READ_LEN
-
-    # ---- device-resident arm (value): one slot, reads already in HBM
-    slot = krepp_b200.IBatch(index, reads)
-    d_bases = torch.from_numpy(slot.bases).cuda()
-    d_offs = torch.from_numpy(slot.offsets.astype(np.int64)).cuda()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    n = args.reads or DEFAULT_READS[args.workload]
+    batch = min(args.batch or DEFAULT_BATCH[args.workload], n)
+    t_wl = time.time()
+    wl = Workload(args.workload, n, rank, world)
+    t_wl = time.time() - t_wl
+    reads = wl.reads
+    index = krepp_b200.Index(wl.index, local)
 
     def barrier():
         torch.cuda.synchronize()
@@ -183,11 +220,25 @@ def main() -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- device-resident arm (value): one slot, all reads of the step already in HBM, processed in batches
+    slot = krepp_b200.IBatch(index, reads[:batch])
+    d_bases = torch.from_numpy(reads.reshape(-1)).cuda()
+    d_offs = torch.from_numpy(slot.offsets.astype(np.int64)).cuda()  # fixed-length reads: every batch has the same offsets
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    chunks = [(i, min(batch, n - i)) for i in range(0, n, batch)]
+
     def step_device():
         flush.zero_()  # evict the index and the reads from L2 between steps
         torch.cuda.synchronize()
-        slot.submit_device(d_bases.data_ptr(), d_offs.data_ptr(), n, nbytes)
-        return slot.wait()
+        gpu = mm = 0.0
+        launches = nrec = alg = lk = en = 0
+        for first, cnt in chunks:
+            slot.submit_device(d_bases.data_ptr() + first * READ_LEN, d_offs.data_ptr(), cnt, cnt * READ_LEN)
+            r = slot.wait()
+            gpu += r["gpu_ms"]; mm += r["match_ms"]; launches += r["gpu_launches"]; nrec += len(r["records"])
+            ab = slot.algorithmic_bytes()
+            alg += ab["bytes"]; lk += ab["lookups"]; en += ab["entries"]
+        return dict(gpu_ms=gpu, match_ms=mm, launches=launches, records=nrec, alg=alg, lookups=lk, entries=en)
 
     for _ in range(args.warmup):
         step_device()
@@ -200,47 +251,63 @@ def main() -> None:
         r = step_device()
         gpu_ms.append(r["gpu_ms"])
         match_ms.append(r["match_ms"])
-        launches += r["gpu_launches"]
+        launches += r["launches"]
     barrier()
     wall_device = time.perf_counter() - t0
     clocks = sampler.stop()
-    alg = slot.algorithmic_bytes()
-    n_records = len(r["records"])
+    last = r
     t_dev = torch.tensor([sum(gpu_ms) / 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
     t_dev = float(t_dev.item())
     value = world * n * args.steps / t_dev
+    slot.close()
+    del d_bases
 
     # ---- end-to-end arm (e2e): HOST buffers through krepp_batch_submit / krepp_batch_wait, 4 slots pipelined
-    nslots, chunk = 4, (n + 3) // 4
-    slots = []
-    for c in range(nslots):
-        sl = krepp_b200.IBatch(index, reads[c * chunk:(c + 1) * chunk])
-        sl.pin_inputs()  # the step's inputs live in pinned host memory; every step copies them host->device again
-        slots.append(sl)
-    h2d = sum(int(s.offsets[-1]) + 8 * (s.n_reads + 1) for s in slots)
+    e2e_out = None
+    if not args.no_e2e:
+        eb = min(args.e2e_batch, n)
+        nslots = 4
+        h_reads = torch.from_numpy(reads.reshape(-1)).pin_memory()  # the step's inputs live in page-locked host memory
+        h_offs = (np.arange(eb + 1, dtype=np.uint64) * np.uint64(READ_LEN))
+        slots = [krepp_b200.IBatch(index, reads[:eb]) for _ in range(nslots)]
+        echunks = [(i, min(eb, n - i)) for i in range(0, n, eb)]
+        h2d = n * READ_LEN + 8 * sum(c + 1 for _, c in echunks)
+        base_ptr = h_reads.data_ptr()
 
-    def step_e2e():
-        d2h = 0
-        for s in slots:
-            s.submit()
-        for s in slots:
-            res = s.wait()
-            d2h += res["reads"].nbytes + res["records"].nbytes + res["hist"].nbytes
-        return d2h
+        def step_e2e():
+            d2h, nrec, inflight = 0, 0, []
+            for j, (first, cnt) in enumerate(echunks):
+                s = slots[j % nslots]
+                if len(inflight) == nslots:
+                    res = inflight.pop(0).wait()
+                    d2h += res["reads"].nbytes + res["records"].nbytes + res["hist"].nbytes
+                    nrec += len(res["records"])
+                s.submit_host(base_ptr + first * READ_LEN, h_offs.ctypes.data, cnt)
+                inflight.append(s)
+            for s in inflight:
+                res = s.wait()
+                d2h += res["reads"].nbytes + res["records"].nbytes + res["hist"].nbytes
+                nrec += len(res["records"])
+            return d2h, nrec
 
-    for _ in range(args.warmup):
-        step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        d2h = step_e2e()
-    barrier()
-    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e = world * n * args.steps / float(t_e2e.item())
+        for _ in range(args.warmup):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            d2h, nrec_e2e = step_e2e()
+        barrier()
+        t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        e2e = world * n * args.steps / float(t_e2e.item())
+        e2e_out = {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "records_per_step": nrec_e2e,
+                   "how": f"krepp_batch_submit from page-locked host memory + krepp_batch_wait (all read summaries, records and histograms copied back), "
+                          f"{nslots} slots x {eb} reads pipelined, wall clock, max over ranks"}
+        for s in slots:
+            s.close()
 
     if rank != 0:
         if world > 1:
@@ -248,35 +315,40 @@ def main() -> None:
         return
 
     peak, peak_src = measured_peak_gbs()
-    mm = sum(match_ms) / len(match_ms)
-    achieved = alg["bytes"] / (mm / 1e3) / 1e9
+    mm = sum(match_ms) / len(match_ms)            # per step
+    launches_per_step = len(chunks)
+    achieved = last["alg"] / (mm / 1e3) / 1e9
+    traffic = None
+    if args.workload in NCU_TRAFFIC:
+        per, tb, _src = NCU_TRAFFIC[args.workload]
+        traffic = tb * (batch / per)
     out = {
         "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_dev * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32/f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "reads_per_gpu": n, "read_len": READ_LEN, "seed": "numpy default_rng(1 + rank)",
-                   "l2": "flushed between steps (256 MiB memset); the 72 MB toy index is re-read from HBM once per step and is L2-resident after that",
-                   "index": "replicated per GPU", "records_per_step": n_records, "wall_s_device_arm": wall_device},
-        "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "how": "krepp_batch_submit from pinned host buffers + krepp_batch_wait, 4 slots x 250k reads pipelined, wall clock"},
+        "config": {"workload": WORKLOADS[args.workload], "reads_per_gpu": n, "read_len": READ_LEN, "batch_reads": batch, **wl.info,
+                   "l2": "inputs larger than L2 (index image %.2f GB, reads %.2f GB per step) and a 256 MiB memset between steps" % (index.info.device_bytes / 1e9, n * READ_LEN / 1e9),
+                   "index": "replicated per GPU", "records_per_step": last["records"], "wall_s_device_arm": wall_device,
+                   "workload_setup_s": round(t_wl, 1)},
+        "e2e": e2e_out,
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "match_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": NCU_TRAFFIC_BYTES, "algorithmic_bytes_per_launch": alg["bytes"], "lookups_per_launch": alg["lookups"],
-                     "entries_scanned_per_launch": alg["entries"], "match_ms": mm, "match_share_of_step": mm / (t_dev * 1e3 / args.steps),
-                     "peak_source": peak_src,
-                     "note": "toy index is smaller than L2, so the algorithmic-byte rate measures gather throughput out of L2, not HBM (SURVEY.md 8d)"},
+                     "traffic": traffic, "traffic_source": NCU_TRAFFIC.get(args.workload, (0, 0, None))[2],
+                     "algorithmic_bytes_per_launch": last["alg"] / launches_per_step,
+                     "lookups_per_launch": last["lookups"] / launches_per_step, "entries_scanned_per_launch": last["entries"] / launches_per_step,
+                     "launches_per_step": launches_per_step, "match_ms_per_launch": mm / launches_per_step,
+                     "match_share_of_step": mm / (t_dev * 1e3 / args.steps), "peak_source": peak_src,
+                     "roofline_reads_per_s": peak * 1e9 / (last["alg"] / n)},
     }
     if not args.no_cpu_baseline and os.path.exists(REF_BIN):
-        import synth
         cores = os.cpu_count() or 1
-        sample = 200_000
+        sample = min(args.cpu_sample or {"c3": 200_000, "toy": 200_000}[args.workload], n)
         with tempfile.TemporaryDirectory() as td:
-            fq = os.path.join(td, "sample.fq")
-            synth.write_fastq(fq, reads[:sample])
-            sec, nq = run_reference(fq, cores)
+            fq = sample_fastq(wl, td, sample)
+            sec, nq = run_reference(wl.index, fq, cores)
         out["cpu_baseline"] = {"value": nq / sec, "unit": "reads/s", "cores": cores, "kind": "reference",
-                               "sample": f"first {sample} of the step's reads, oracle/_ref/krepp --num-threads {cores} dist -o /dev/null, "
+                               "sample": f"first {sample} of rank 0's reads, oracle/_ref/krepp --num-threads {cores} dist -o /dev/null on the same index, "
                                          f"its own elapsed line ({sec:.2f} s, index load excluded)"}
     else:
         out["cpu_baseline"] = None

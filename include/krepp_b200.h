@@ -139,8 +139,10 @@ void krepp_batch_destroy(krepp_batch_t* b);
 
 /* Replaces IBatch::estimate_distances / place_sequences up to (not including) text formatting (src/query.cpp:141-156,
  * 198-216): `bases` holds the reads' ASCII characters back to back, read i is bases[offsets[i] .. offsets[i+1]).
- * HOST buffers; the call stages them through the slot's pinned memory, enqueues H2D, all kernels and D2H on the slot's
- * stream and returns without waiting.  The caller may reuse `bases`/`offsets` as soon as the call returns. */
+ * HOST buffers; the call enqueues H2D, all kernels and D2H on the slot's stream and returns without waiting.  Pageable
+ * `bases` are first staged through the slot's pinned memory and may be reused as soon as the call returns; page-locked
+ * `bases` (cudaMallocHost / cudaHostRegister memory) are copied to the device from where they lie and must stay
+ * untouched until krepp_batch_wait returns.  `offsets` may always be reused at once. */
 int krepp_batch_submit(krepp_batch_t* b, const char* bases, const uint64_t* offsets, uint32_t n_reads);
 
 /* The slot's own pinned input buffers (max_bases + 64 bytes, max_reads + 1 offsets).  A producer that parses reads

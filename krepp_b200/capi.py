@@ -221,6 +221,10 @@ class IBatch:
     def submit(self):
         _check(load_library().krepp_batch_submit(self._h, self.bases.ctypes.data, self.offsets.ctypes.data, self.n_reads))
 
+    def submit_host(self, bases_ptr: int, offsets_ptr: int, n_reads: int):
+        """krepp_batch_submit on raw host pointers (e.g. a slice of one large page-locked buffer)."""
+        _check(load_library().krepp_batch_submit(self._h, bases_ptr, offsets_ptr, n_reads))
+
     def submit_device(self, d_bases_ptr: int, d_offsets_ptr: int, n_reads: int, n_bases: int):
         _check(load_library().krepp_batch_submit_device(self._h, d_bases_ptr, d_offsets_ptr, n_reads, n_bases))
 

@@ -466,14 +466,21 @@ int krepp_batch_submit(krepp_batch_t* b, const char* bases, const uint64_t* offs
   if (nb > b->max_bases) return fail(KREPP_ERR_CAPACITY, "batch of %llu bases exceeds the slot capacity of %llu", (unsigned long long)nb, (unsigned long long)b->max_bases);
   if (cudaSetDevice(b->ix->device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice failed");
   CU(cudaStreamSynchronize(b->stream)); // the previous batch of this slot must be finished before its buffers are reused
-  if (bases != b->h_bases) std::memcpy(b->h_bases, bases + offsets[0], nb);
+  // Page-locked caller memory (cudaMallocHost / cudaHostRegister) is copied to the device straight from where it lies;
+  // pageable memory goes through the slot's own pinned staging buffer first.
+  const char* src = b->h_bases;
+  if (bases != b->h_bases) {
+    cudaPointerAttributes at{};
+    if (nb && cudaPointerGetAttributes(&at, bases + offsets[0]) == cudaSuccess && at.type == cudaMemoryTypeHost) src = bases + offsets[0];
+    else { cudaGetLastError(); std::memcpy(b->h_bases, bases + offsets[0], nb); }
+  }
   if (offsets != b->h_offsets || offsets[0] != 0) {
     const uint64_t o0 = offsets[0];
     for (uint32_t i = 0; i <= n_reads; ++i) b->h_offsets[i] = offsets[i] - o0;
   }
   b->n_reads = n_reads; b->n_bases = nb; b->device_input = false;
   b->in_bases = b->d_bases; b->in_offsets = b->d_offsets;
-  CU(cudaMemcpyAsync(b->d_bases, b->h_bases, nb, cudaMemcpyHostToDevice, b->stream));
+  CU(cudaMemcpyAsync(b->d_bases, src, nb, cudaMemcpyHostToDevice, b->stream));
   CU(cudaMemcpyAsync(b->d_offsets, b->h_offsets, 8ull * (n_reads + 1), cudaMemcpyHostToDevice, b->stream));
   CU(cudaEventRecord(b->ev0, b->stream));
   if (int rc = enqueue(b)) return rc;

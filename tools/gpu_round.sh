@@ -1,19 +1,21 @@
 #!/bin/bash
-# One gpurun call: GPU parity tests, the bench (both arms), the ncu launch list and one full capture of the match kernel.
-# usage (here): gpurun --timeout 2400 -- 'bash tools/gpu_round.sh [tag]'
+# One gpurun call: GPU parity tests, smoke, the bench (config 3 default, both arms; toy = configs[1] as a side line), the
+# ncu launch list and one full capture of the match kernel on the config-3 workload.
+# usage (here): gpurun --timeout 2400 -- 'bash tools/gpu_round.sh [tag] [skip-ncu]'
 TAG=${1:-r01}
 O=gpurun_out/$TAG
 mkdir -p $O
 nvidia-smi > $O/nvsmi.txt 2>&1
-nproc > $O/nproc.txt
+( nproc; free -g; df -h /tmp /dev/shm ) > $O/box.txt 2>&1; cat $O/box.txt
 ( time timeout 1200 python -m pytest tests -m gpu -x -q ) > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $O/pytest_gpu.log
 tail -5 $O/pytest_gpu.log
 timeout 300 python __graft_entry__.py smoke > $O/smoke.log 2>&1; echo "smoke rc=$?"; tail -2 $O/smoke.log
+timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_ref.json 2> $O/bench_ref.err; echo "bench ref rc=$?"; cat $O/bench_ref.json; tail -3 $O/bench_ref.err
 timeout 900 python bench.py > $O/bench.json 2> $O/bench.err; echo "bench rc=$?"; cat $O/bench.json; tail -3 $O/bench.err
-timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_ref.json 2> $O/bench_ref.err; cat $O/bench_ref.json
-timeout 600 python tools/perf_match.py 1000000 lane,staged > $O/perf_match.log 2>&1; cat $O/perf_match.log
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv \
-    python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $O/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:match_kernel -s 3 -c 1 -f -o $O/match_full \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/ncu_full.log 2>&1; echo "ncu full rc=$?"
+timeout 600 python bench.py --workload toy --no-cpu-baseline > $O/bench_toy.json 2> $O/bench_toy.err; echo "bench toy rc=$?"; cat $O/bench_toy.json; tail -3 $O/bench_toy.err
+if [ "$2" != "skip-ncu" ]; then
+  CMD="python bench.py --reads 1000000 --batch 250000 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e"
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv $CMD > $O/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
+  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:match_kernel -s 5 -c 1 -f -o $O/match_full $CMD > $O/ncu_full.log 2>&1; echo "ncu full rc=$?"
+fi
 ls -la $O
