@@ -160,7 +160,11 @@ int krepp_batch_wait(krepp_batch_t* b, krepp_results_t* out);
 
 /* Parity taps (SURVEY.md section 8b "dump_stage").  stage 1: every eligible lookup of the last submitted batch as
  * 4 x u32 {read, strand<<31|pos, rix, enc32}, unordered (src/query.cpp:82-91 arguments of add_matching_mer).
- * Must be enabled before submit with krepp_batch_enable_tap.  Returns the number of items through *n. */
+ * Must be enabled before submit with krepp_batch_enable_tap.  Returns the number of items through *n.
+ * stage 2 (a switch, capacity_items != 0 turns it on; nothing to read back): records[] also keeps the (strand, leaf)
+ * pairs that fail the hdist_filt gate of summarize_matches (src/query.cpp:101-106,116-119) -- every Minfo the reference
+ * holds BEFORE that gate, with KREPP_REC_SOLVED clear on the failing ones.  By default those pairs are dropped on the
+ * device as soon as their read is finished, which is what the reference's node_to_minfo holds after the gate. */
 int krepp_batch_enable_tap(krepp_batch_t* b, int stage, uint64_t capacity_items);
 int krepp_batch_read_tap(krepp_batch_t* b, int stage, uint32_t* out, uint64_t cap_items, uint64_t* n);
 

@@ -206,6 +206,10 @@ class IBatch:
     def enable_tap(self, capacity_items: int):
         _check(load_library().krepp_batch_enable_tap(self._h, 1, capacity_items))
 
+    def keep_all_records(self, on: bool = True):
+        """Parity tap 2: also return the (strand, leaf) pairs that fail the hdist_filt gate (unsolved records)."""
+        _check(load_library().krepp_batch_enable_tap(self._h, 2, int(on)))
+
     def pin_inputs(self):
         """Moves this batch's reads into the slot's own pinned host buffers (krepp_batch_host_buffers) so that submit()
         copies host->device straight from pinned memory, without the staging memcpy."""

@@ -137,7 +137,7 @@ struct krepp_batch {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm0 = nullptr, evm1 = nullptr;
   uint32_t max_reads = 0, rec_cap = 0, n_reads = 0, launches = 0;
   uint64_t max_bases = 0, n_bases = 0;
-  bool submitted = false, device_input = false;
+  bool submitted = false, device_input = false, keep_all = false;
   const char* in_bases = nullptr;       // device pointers used by the last submit
   const uint64_t* in_offsets = nullptr;
   // pinned host staging + device inputs
@@ -413,7 +413,7 @@ static int enqueue(krepp_batch* b)
   CU(cudaMemsetAsync(b->d_stats, 0, 32, s));
   if (b->d_tap_count) CU(cudaMemsetAsync(b->d_tap_count, 0, 8, s));
   MatchArgs m{};
-  m.bases = b->in_bases; m.offsets = b->in_offsets; m.n_bases = b->n_bases; m.n_reads = b->n_reads; m.th = b->p.hdist_th;
+  m.bases = b->in_bases; m.offsets = b->in_offsets; m.n_bases = b->n_bases; m.n_reads = b->n_reads; m.th = b->p.hdist_th; m.keep_all = b->keep_all ? 1u : 0u;
   m.onmers = b->d_onmers; m.wn = b->d_wn; m.hdfilt = b->d_hdfilt; m.rec_begin = b->d_rec_begin; m.rec_count = b->d_rec_count;
   m.rec_read = b->d_rec_read; m.rec_slot = b->d_rec_slot; m.rec_hist = b->d_rec_hist; m.rec_cap = b->rec_cap; m.counters = b->d_counters;
   m.acc = b->d_acc; m.bitmap = b->d_bitmap; m.marker = b->d_marker; m.stack = b->d_stack; m.stack_cap = b->stack_cap; m.tagctr = b->d_tagctr; m.stats = b->d_stats;
@@ -547,9 +547,10 @@ int krepp_batch_wait(krepp_batch_t* b, krepp_results_t* out)
 
 int krepp_batch_enable_tap(krepp_batch_t* b, int stage, uint64_t capacity_items)
 {
-  if (!b || stage != 1 || !capacity_items) return fail(KREPP_ERR_ARG, "krepp_batch_enable_tap: bad argument");
+  if (!b || (stage != 1 && stage != 2) || (stage == 1 && !capacity_items)) return fail(KREPP_ERR_ARG, "krepp_batch_enable_tap: bad argument");
   if (cudaSetDevice(b->ix->device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice failed");
   CU(cudaStreamSynchronize(b->stream));
+  if (stage == 2) { b->keep_all = capacity_items != 0; return KREPP_OK; }
   if (b->d_tap) { cudaFree(b->d_tap); b->d_tap = nullptr; }
   if (!b->d_tap_count) CU(cudaMalloc(&b->d_tap_count, 8));
   CU(cudaMalloc(&b->d_tap, sizeof(uint4) * capacity_items));

@@ -41,6 +41,7 @@ struct MatchArgs {
   const uint64_t* offsets;    // n_reads + 1
   uint64_t n_bases;           // bytes readable at `bases`
   uint32_t n_reads, th;
+  uint32_t keep_all;          // 1: emit every (strand, leaf) pair with a hit (parity tap 2); 0: only those passing the hdist_filt gate
   // per-read outputs
   uint32_t* onmers;           // [n]
   uint32_t* wn;               // [2n]
@@ -65,6 +66,32 @@ struct MatchArgs {
   uint4* tap;
   unsigned long long* tap_count;
   unsigned long long tap_cap;
+  // mode B, owner side (match_kernel<.., OWNER>): a work item is the run of lookups one source read sent to this shard
+  const uint2* tuples;        // {row offset local to this shard | strand << 31, residual q}
+  const uint32_t* grp_begin;  // [n_reads] first tuple of the read's run
+  const uint32_t* grp_cnt;    // [n_reads] length of the run
+};
+
+// Mode B (index sharded by LSH bucket range): the home rank turns reads into lookups binned by owner.
+constexpr int kMaxShards = 16;
+struct ShardArgs {
+  uint32_t nshards, pitch;              // pitch = reads capacity of the per-shard count arrays
+  uint32_t row_split[kMaxShards + 1];   // shard p owns bucket rows [row_split[p], row_split[p+1])
+  uint32_t* cnt;                        // [nshards][pitch] lookups of each read that go to shard p
+  const uint32_t* begin;                // [nshards][pitch] exclusive prefix of cnt within shard p's segment
+  const uint32_t* seg_base;             // [nshards + 1] first tuple of shard p's segment
+  uint2* tuples;                        // all segments back to back
+};
+
+// Mode B, home side again: partial records returned by the owners are summed per (read, strand, leaf).
+struct CombineArgs {
+  uint32_t nshards, pitch, n_reads, th;
+  const uint32_t* rec_read; const uint32_t* rec_slot; const uint32_t* rec_hist; // received partial records, owner after owner
+  const uint32_t* seg_base;   // [nshards + 1] first partial record of owner p
+  const uint32_t* rc;         // [nshards][pitch] partial records of each read at owner p
+  const uint32_t* rbegin;     // [nshards][pitch] exclusive prefix of rc within owner p's segment
+  const uint32_t* hdfilt_in;  // [nshards][pitch][2]
+  const uint64_t* offsets;    // read offsets (for the algorithmic-byte count)
 };
 
 constexpr uint32_t kErrRecOverflow = 1u, kErrStackOverflow = 2u, kErrPlaceOverflow = 4u;

@@ -132,6 +132,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
     "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
 
+// The index fields the colour expansion and rescan helpers need.  Cold paths are compiled out of line (the staged
+// kernel is large enough for instruction-cache misses to show up as stall_no_inst) and take this small view by value:
+// handing them the kernel's DevIndex parameter by reference would force a per-thread copy of the whole struct.
+struct IxView {
+  const uint2* cmer;
+  const uint2* cnode;
+  uint32_t local_expand;
+};
+
 struct WarpCtx {
   uint32_t* acc;      // [2*nleaves*(th+1)]
   uint32_t* bitmap;   // [ceil(2*nleaves/32)]
@@ -165,7 +174,7 @@ __device__ __forceinline__ void leaf_hit(const WarpCtx& w, uint32_t strand, uint
 
 // Lane-local colour expansion: depth-first with a small private stack.  The host only enables it (ix.local_expand)
 // when the deepest colour DAG of the index fits.  tagbase == 0xffffffff: the lookup has this single hit, commit directly.
-__device__ __forceinline__ void expand_local(const DevIndex& ix, const WarpCtx& w, uint32_t se, uint32_t strand, uint32_t hd, uint32_t tagbase)
+__device__ __forceinline__ void expand_local(const IxView& ix, const WarpCtx& w, uint32_t se, uint32_t strand, uint32_t hd, uint32_t tagbase)
 {
   uint32_t st[kLocalStack];
   int sp = 0;
@@ -180,7 +189,7 @@ __device__ __forceinline__ void expand_local(const DevIndex& ix, const WarpCtx& 
 }
 
 // Warp-cooperative colour expansion over the per-warp HBM stack, for colour DAGs too deep for the private stack.
-__device__ void expand_coop(const DevIndex& ix, const WarpCtx& w, uint32_t se, uint32_t strand, uint32_t hd, uint32_t tagbase)
+__device__ __noinline__ void expand_coop(const IxView ix, const WarpCtx w, uint32_t se, uint32_t strand, uint32_t hd, uint32_t tagbase)
 {
   const uint32_t lane = threadIdx.x & 31;
   uint32_t size = 1;
@@ -208,7 +217,7 @@ __device__ void expand_coop(const DevIndex& ix, const WarpCtx& w, uint32_t se, u
 }
 
 // Hits of one lookup held one per lane (hit lanes have hd <= th): expand all of them.
-__device__ __forceinline__ void expand_hits(const DevIndex& ix, const WarpCtx& w, bool hit, uint32_t se, uint32_t hd, uint32_t strand, uint32_t tagbase)
+__device__ __forceinline__ void expand_hits(const IxView& ix, const WarpCtx& w, bool hit, uint32_t se, uint32_t hd, uint32_t strand, uint32_t tagbase)
 {
   if (ix.local_expand) { if (hit) expand_local(ix, w, se, strand, hd, tagbase); }
   else {
@@ -247,7 +256,7 @@ __device__ __forceinline__ void tab_insert(WarpStage* stg, uint32_t v)
   stg->ovf = 1; // too crowded: the whole batch is redone through the marker path
 }
 
-__device__ __forceinline__ void expand_to_table(const DevIndex& ix, WarpStage* stg, uint32_t se, uint32_t meta)
+__device__ __forceinline__ void expand_to_table(const IxView& ix, WarpStage* stg, uint32_t se, uint32_t meta)
 {
   uint32_t st[kLocalStack];
   int sp = 0;
@@ -261,9 +270,31 @@ __device__ __forceinline__ void expand_to_table(const DevIndex& ix, WarpStage* s
   }
 }
 
+// More distinct (lookup, leaf) pairs than the table holds (rare): the queue, which is ordered by lookup id, is replayed
+// lookup by lookup through the markers instead.  Returns the updated tag counter.
+__device__ __noinline__ uint32_t resolve_overflow(const IxView ix, const WarpCtx w, WarpStage* stg, uint32_t n_hits, uint32_t tag)
+{
+  const uint32_t lane = threadIdx.x & 31;
+  if (lane == 0) stg->ovf = 0;
+  uint32_t pos = 0, last_id = 0xFFFFFFFFu, tagbase = 0;
+  while (pos < n_hits) {
+    const uint32_t id = stg->hitq[pos].y >> 25;
+    if (id != last_id) { tagbase = next_tag(w, tag); last_id = id; }
+    const uint32_t i = pos + lane;
+    uint2 h = make_uint2(0u, 0u);
+    if (i < n_hits) h = stg->hitq[i];
+    const uint32_t same = __ballot_sync(0xFFFFFFFFu, i < n_hits && (h.y >> 25) == id);
+    const uint32_t run = __ffs(~same) - 1; // entries of this lookup at the head of the window (>= 1)
+    if (lane < run) expand_local(ix, w, h.x, (h.y >> 24) & 1u, h.y & 31u, tagbase);
+    __syncwarp();
+    pos += run;
+  }
+  return tag;
+}
+
 // Resolves the queued hits of a warp: colours are expanded with all lanes busy, leaves are deduplicated per lookup in the
 // shared-memory table, and every surviving (lookup, leaf) bumps the histogram once at its minimum distance.
-__device__ void resolve_hits(const DevIndex& ix, const WarpCtx& w, WarpStage* stg, uint32_t n_hits, uint32_t n_ids, uint32_t& tag)
+__device__ __forceinline__ void resolve_hits(const IxView& ix, const WarpCtx& w, WarpStage* stg, uint32_t n_hits, uint32_t n_ids, uint32_t& tag)
 {
   const uint32_t lane = threadIdx.x & 31;
   __syncwarp();
@@ -277,27 +308,12 @@ __device__ void resolve_hits(const DevIndex& ix, const WarpCtx& w, WarpStage* st
     if (!overflow) commit(w, (v >> 24) & 1u, (v >> 5) & 0x7FFFFu, v & 31u);
   }
   __syncwarp();
-  if (overflow) { // more distinct (lookup, leaf) pairs than the table holds: lookup by lookup through the markers instead
-    if (lane == 0) stg->ovf = 0;
-    uint32_t pos = 0, last_id = 0xFFFFFFFFu, tagbase = 0;
-    while (pos < n_hits) { // the queue is ordered by lookup id
-      const uint32_t id = stg->hitq[pos].y >> 25;
-      if (id != last_id) { tagbase = next_tag(w, tag); last_id = id; }
-      const uint32_t i = pos + lane;
-      uint2 h = make_uint2(0u, 0u);
-      if (i < n_hits) h = stg->hitq[i];
-      const uint32_t same = __ballot_sync(0xFFFFFFFFu, i < n_hits && (h.y >> 25) == id);
-      const uint32_t run = __ffs(~same) - 1; // entries of this lookup at the head of the window (>= 1)
-      if (lane < run) expand_local(ix, w, h.x, (h.y >> 24) & 1u, h.y & 31u, tagbase);
-      __syncwarp();
-      pos += run;
-    }
-  }
+  if (overflow) tag = resolve_overflow(ix, w, stg, n_hits, tag);
 }
 
 // Small-bucket path: one lookup with several hit entries (or a colour too deep for the private stack), rescanned by the
 // whole warp in a single pass.
-__device__ uint32_t careful_lookup(const DevIndex& ix, const WarpCtx& w, uint32_t begin, uint32_t len, uint32_t q, uint32_t strand, uint32_t th, uint32_t tagbase)
+__device__ __forceinline__ uint32_t careful_lookup(const IxView& ix, const WarpCtx& w, uint32_t begin, uint32_t len, uint32_t q, uint32_t strand, uint32_t th, uint32_t tagbase)
 {
   const uint32_t lane = threadIdx.x & 31;
   uint32_t best = 0xFFFFFFFFu; // this lane's smallest distance among the hit entries
@@ -314,6 +330,228 @@ __device__ uint32_t careful_lookup(const DevIndex& ix, const WarpCtx& w, uint32_
     expand_hits(ix, w, hd <= th, se, hd, strand, tagbase);
   }
   return best;
+}
+
+// Staged path, rare: lookups whose bucket does not fit the ring are scanned by the whole warp straight from HBM and
+// deduplicated through the markers.  Returns {tag, filt0, filt1} updated.
+__device__ __noinline__ uint3 long_lookups(const IxView ix, const WarpCtx w, const WarpStage* stg, uint32_t n_long, uint32_t th, uint32_t tag,
+                                           uint32_t filt0, uint32_t filt1)
+{
+  __syncwarp();
+  for (uint32_t j = 0; j < n_long; ++j) {
+    const uint32_t l = stg->lg_l[j];
+    const uint32_t best = careful_lookup(ix, w, stg->lg_a[j], l & 0x7FFFFFFFu, stg->lg_q[j], l >> 31, th, next_tag(w, tag));
+    if (l >> 31) filt1 = min(filt1, best); else filt0 = min(filt0, best);
+  }
+  __syncwarp();
+  return make_uint3(tag, filt0, filt1);
+}
+
+// Staged path, rare: a round with more hit entries than the queue holds (or an index whose colour DAG is too deep for
+// the table path) is resolved lookup by lookup under marker tags.  Lane state of the round comes in by value.
+__device__ __noinline__ uint3 marker_round(const IxView ix, const WarpCtx w, const uint2* slot, uint32_t hmask, uint32_t nbits, uint32_t cq, uint32_t cs,
+                                           uint32_t shared_id, uint32_t tag, uint32_t filt0, uint32_t filt1)
+{
+  const uint32_t lane = threadIdx.x & 31, gl = lane & 7u, grp = lane >> 3;
+  const bool one_lookup = __shfl_sync(0xFFFFFFFFu, shared_id, 0) != 0; // a long bucket spread over the groups
+  uint32_t tagbase = 0;
+  for (uint32_t g = 0; g < (uint32_t)kGroups; ++g) {
+    if (!__any_sync(0xFFFFFFFFu, grp == g && hmask != 0)) continue;
+    if (!one_lookup || !tagbase) tagbase = next_tag(w, tag);
+    const uint32_t gcs = __shfl_sync(0xFFFFFFFFu, cs, 8 * g);
+    __syncwarp();
+    for (uint32_t t = 0; t < nbits; ++t) {
+      const bool hit = grp == g && ((hmask >> (nbits - 1u - t)) & 1u);
+      if (!__any_sync(0xFFFFFFFFu, hit)) continue;
+      uint32_t se = 0, hd = 0;
+      if (hit) { const uint2 e = slot[2u * gl + 16u * (t >> 1) + (t & 1u)]; const uint32_t z = e.x ^ cq; hd = __popc((z | (z >> 16)) & 0xFFFFu); se = e.y; if (cs) filt1 = min(filt1, hd); else filt0 = min(filt0, hd); }
+      expand_hits(ix, w, hit, se, hd, gcs, tagbase);
+    }
+    __syncwarp();
+  }
+  return make_uint3(tag, filt0, filt1);
+}
+
+// A0 + A1 of one tile of a read (see the header): ASCII bases -> 2-bit stream in shared memory -> k-mer windows -> bucket
+// ids and residual encodings of both strands; the eligible lookups are compacted into sm.lk_a (row offset | strand << 31)
+// and sm.lk_q.  Returns their number; onmers / wn0 / wn1 are the read's running counts (warp-uniform).
+template <bool TAP>
+__device__ __forceinline__ uint32_t tile_lookups(const DevIndex& ix, const MatchArgs& a, WarpSmem& sm, const uint4* lut, bool wide, uint32_t read,
+                                                 uint64_t off, uint64_t len, uint64_t t0, uint32_t& onmers, uint32_t& wn0, uint32_t& wn1)
+{
+  const uint32_t lane = threadIdx.x & 31, lt_mask = (1u << lane) - 1, k = ix.k;
+  // ---- A0. load + encode the tile's bases: [t0, t0 + kTileWindows + k - 1) clipped to the read
+  const uint64_t rem = len - t0;                                  // bases available from t0
+  const uint32_t nb = (uint32_t)min((uint64_t)(kTileWindows + k - 1), rem);
+  const char* p0 = a.bases + off + t0;
+  const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(p0) & 15);
+  const char* al = p0 - sh;
+  uint32_t cw = 0, vw = 0;
+  if (lane <= kTileWords) {
+    const char* cp = al + 16 * lane;
+    if (cp < p0 + nb) {
+      uint4 u;
+      if (cp + 16 <= a.bases + a.n_bases) u = __ldg(reinterpret_cast<const uint4*>(cp));
+      else {
+        unsigned char b[16];
+        for (int i = 0; i < 16; ++i) b[i] = (cp + i < a.bases + a.n_bases) ? (unsigned char)cp[i] : 0;
+        u.x = b[0] | b[1] << 8 | b[2] << 16 | (uint32_t)b[3] << 24; u.y = b[4] | b[5] << 8 | b[6] << 16 | (uint32_t)b[7] << 24;
+        u.z = b[8] | b[9] << 8 | b[10] << 16 | (uint32_t)b[11] << 24; u.w = b[12] | b[13] << 8 | b[14] << 16 | (uint32_t)b[15] << 24;
+      }
+      uint32_t c0, c1, c2, c3, v0, v1, v2, v3;
+      encode4(u.x, c0, v0); encode4(u.y, c1, v1); encode4(u.z, c2, v2); encode4(u.w, c3, v3);
+      cw = c0 << 24 | c1 << 16 | c2 << 8 | c3;
+      vw = v0 << 12 | v1 << 8 | v2 << 4 | v3;
+    }
+  }
+  // align the stream to the tile start: word t covers tile bases 16t .. 16t+15
+  const uint32_t cn = __shfl_down_sync(0xFFFFFFFFu, cw, 1), vn = __shfl_down_sync(0xFFFFFFFFu, vw, 1);
+  const uint32_t cwa = __funnelshift_l(cn, cw, 2 * sh);
+  uint32_t vwa = (((vw << 16) | vn) << sh) >> 16;
+  { // clip validity to the bases that belong to this read
+    const int keep = (int)nb - 16 * (int)lane;    // number of leading bases of this word inside the read
+    if (keep <= 0) vwa = 0; else if (keep < 16) vwa &= 0xFFFFu << (16 - keep);
+  }
+  const uint32_t vhi = __shfl_sync(0xFFFFFFFFu, vwa, (2 * lane) & 31), vlo = __shfl_sync(0xFFFFFFFFu, vwa, (2 * lane + 1) & 31);
+  __syncwarp();
+  if (lane <= kTileWords) sm.code[lane] = cwa;
+  if (lane <= kTileWords / 2) sm.valid[lane] = (vhi << 16) | vlo;
+  if (lane == 0) sm.cursor = 0;
+  __syncwarp();
+
+  // ---- A1. windows -> k-mer words -> bucket ids; eligible lookups compacted into the list
+  const uint32_t nwin = (uint32_t)min((uint64_t)kTileWindows, rem - k + 1);
+  uint32_t nl = 0;
+#pragma unroll
+  for (uint32_t j = 0; j < kTileWindows / 32; ++j) {
+    const uint32_t p = lane + 32 * j;
+    bool valid = false;
+    uint64_t bp = 0;
+    if (p < nwin) {
+      const uint32_t vj = p >> 5, vs = p & 31;
+      const uint32_t vx = __funnelshift_l(sm.valid[vj + 1], sm.valid[vj], vs);
+      valid = (vx >> (32 - k)) == (0xFFFFFFFFu >> (32 - k));
+      const uint32_t cj = p >> 4, cs = 2 * (p & 15);
+      const uint32_t w0 = sm.code[cj], w1 = sm.code[cj + 1], w2 = sm.code[cj + 2];
+      const uint64_t x = ((uint64_t)__funnelshift_l(w1, w0, cs) << 32) | __funnelshift_l(w2, w1, cs);
+      bp = x >> (64 - 2 * k);
+    }
+    onmers += __popc(__ballot_sync(0xFFFFFFFFu, valid));   // warp-uniform counts: no reduction at the end of the read
+    const uint4 rq = lut_pext(lut, (uint32_t)bp, (uint32_t)(bp >> 32), wide);
+#pragma unroll
+    for (uint32_t strand = 0; strand < 2; ++strand) {
+      const uint32_t rix = strand ? rq.z : rq.x, q = strand ? rq.w : rq.y;
+      uint32_t quo, res;
+      if (ix.m_shift != 0xFFFFFFFFu) { quo = rix >> ix.m_shift; res = rix & (ix.m - 1); }
+      else { quo = rix / ix.m; res = rix - quo * ix.m; }
+      const int32_t numer = ix.res_numer[res];
+      const bool elig = valid && numer != 0;
+      const uint32_t offset = numer > 1 ? quo * (uint32_t)numer + res : quo;
+      const uint32_t em = __ballot_sync(0xFFFFFFFFu, elig);
+      if (elig) {
+        const uint32_t idx = nl + __popc(em & lt_mask);
+        sm.lk_a[idx] = offset | (strand << 31);
+        sm.lk_q[idx] = q;
+        if (TAP) {
+          const unsigned long long at = atomicAdd(a.tap_count, 1ull);
+          const uint32_t pos = strand ? (uint32_t)(len - (t0 + p) - k) : (uint32_t)(t0 + p);
+          if (at < a.tap_cap) a.tap[at] = make_uint4(read, strand << 31 | pos, rix, q);
+        }
+      }
+      nl += __popc(em);
+      if (strand) wn1 += __popc(em); else wn0 += __popc(em);
+    }
+  }
+  __syncwarp();
+  return nl;
+}
+
+// Emits one read's records in (strand, leaf) order from the warp's accumulator and clears it (see the header); returns
+// the number of records.  `list` is 512 words of the warp's shared memory.
+__device__ __forceinline__ uint32_t emit_records(const DevIndex& ix, const MatchArgs& a, const WarpCtx& w, uint32_t* list, uint32_t read,
+                                                 uint32_t filt0, uint32_t filt1, uint32_t& rbegin_out, bool& fits_out)
+{
+  const uint32_t lane = threadIdx.x & 31, nleaves = w.nleaves, stride = w.stride, nbm = (2 * nleaves + 31) >> 5;
+  __syncwarp();
+  uint32_t total = 0;
+  if (!a.keep_all) {
+    // The hdist_filt gate of summarize_matches (ref src/query.cpp:101-106,116-119) applied where the histograms are
+    // born: a (strand, leaf) pair whose smallest distance exceeds 2 * hdist_filt[strand] + 1 is never solved,
+    // reported or looked at again by the reference, so it is dropped here (its accumulator is cleared) instead of
+    // being written out, gated, merged and copied to the host.  keep_all (parity tap 2) keeps every pair.
+    const uint32_t g0 = 2u * filt0 + 1u, g1 = 2u * filt1 + 1u; // uint32 wrap kept, as in the reference
+    for (uint32_t wbase = 0; wbase < nbm; wbase += 16) {
+      uint32_t bits = (lane < 16 && wbase + lane < nbm) ? __ldcg(&w.bitmap[wbase + lane]) : 0u;
+      const uint32_t c = __popc(bits);
+      uint32_t incl = c;
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += t; }
+      const uint32_t cnt = __shfl_sync(0xFFFFFFFFu, incl, 31);
+      if (!cnt) continue;
+      uint32_t li = incl - c;
+      while (bits) { const uint32_t b = __ffs(bits) - 1; bits &= bits - 1; list[li++] = (wbase + lane) * 32 + b; }
+      __syncwarp();
+      for (uint32_t i = lane; i < ((cnt + 31u) & ~31u); i += 32) {
+        bool pass = false;
+        if (i < cnt) {
+          const uint32_t slot = list[i];
+          uint32_t* h = w.acc + (size_t)slot * stride;
+          uint32_t hdmin = 0xFFFFFFFFu;
+          for (uint32_t x = 0; x < stride; ++x) if (__ldcg(&h[x]) && hdmin == 0xFFFFFFFFu) hdmin = x;
+          pass = !(hdmin > (slot >= nleaves ? g1 : g0));
+          if (!pass) {
+            for (uint32_t x = 0; x < stride; ++x) h[x] = 0;
+            atomicAnd(&w.bitmap[slot >> 5], ~(1u << (slot & 31)));
+          }
+        }
+        total += __popc(__ballot_sync(0xFFFFFFFFu, pass));
+      }
+      __syncwarp();
+    }
+  } else {
+    for (uint32_t wbase = 0; wbase < nbm; wbase += 32) {
+      const uint32_t bits = (wbase + lane < nbm) ? __ldcg(&w.bitmap[wbase + lane]) : 0u;
+      uint32_t c = __popc(bits);
+      for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+      total += c;
+    }
+  }
+  uint32_t rbegin = 0;
+  if (lane == 0 && total) rbegin = atomicAdd(a.counters, total);
+  rbegin = __shfl_sync(0xFFFFFFFFu, rbegin, 0);
+  const bool fits = (uint64_t)rbegin + total <= a.rec_cap;
+  if (!fits && lane == 0) atomicOr(a.counters + 2, kErrRecOverflow);
+  // records in ascending slot order; 16 bitmap words (<= 512 slots) per round: lanes 0..15 list the set bits of their
+  // word in shared memory, then every lane takes whole records, so clustered leaves do not pile up on one lane
+  uint32_t done = 0;
+  for (uint32_t wbase = 0; wbase < nbm; wbase += 16) {
+    uint32_t bits = (lane < 16 && wbase + lane < nbm) ? __ldcg(&w.bitmap[wbase + lane]) : 0u;
+    const uint32_t c = __popc(bits);
+    uint32_t incl = c;
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += t; }
+    const uint32_t cnt = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    if (!cnt) continue;
+    if (bits) w.bitmap[wbase + lane] = 0;
+    uint32_t li = incl - c;
+    while (bits) { const uint32_t b = __ffs(bits) - 1; bits &= bits - 1; list[li++] = (wbase + lane) * 32 + b; }
+    __syncwarp();
+    for (uint32_t i = lane; i < cnt; i += 32) {
+      const uint32_t slot = list[i], at = rbegin + done + i;
+      const uint32_t strand = slot >= nleaves, rank = slot - strand * nleaves;
+      uint32_t* h = w.acc + (size_t)slot * stride;
+      uint32_t hv[kMaxTh + 1];
+      for (uint32_t x = 0; x < stride; ++x) hv[x] = __ldcg(&h[x]);
+      for (uint32_t x = 0; x < stride; ++x) h[x] = 0;
+      if (fits) {
+        a.rec_read[at] = read;
+        a.rec_slot[at] = strand << 31 | ix.leaf_se[rank];
+        for (uint32_t x = 0; x < stride; ++x) a.rec_hist[(size_t)at * stride + x] = hv[x];
+      }
+    }
+    done += cnt;
+    __syncwarp();
+  }
+  rbegin_out = rbegin; fits_out = fits;
+  return total;
 }
 
 template <bool STAGED, bool TAP>
@@ -350,6 +588,7 @@ __global__ void __launch_bounds__(warps_per_cta(STAGED) * 32, STAGED ? 1 : 4) ma
   w.marker = a.marker + (size_t)gwarp * nleaves;
   w.stack = a.stack + (size_t)gwarp * a.stack_cap;
   w.stack_cap = a.stack_cap; w.stride = stride; w.nleaves = nleaves; w.err = a.counters + 2;
+  IxView iv; iv.cmer = ix.cmer; iv.cnode = ix.cnode; iv.local_expand = ix.local_expand;
   uint32_t tag = min(a.tagctr[gwarp], kTagStart);   // persists across launches: markers are never cleared in between
   uint32_t p_round = 0, c_round = 0;                // rounds issued / consumed by this warp over the whole launch (mbarrier phases)
   const bool use_table = STAGED && ix.local_expand && nleaves <= kTabMaxLeaves;
@@ -372,101 +611,14 @@ __global__ void __launch_bounds__(warps_per_cta(STAGED) * 32, STAGED ? 1 : 4) ma
     st_bytes += (lane == 0) ? len : 0;
 
     for (uint64_t t0 = 0; t0 + k <= len; t0 += kTileWindows) {
-      // ---- A0. load + encode the tile's bases: [t0, t0 + kTileWindows + k - 1) clipped to the read
-      const uint64_t rem = len - t0;                                  // bases available from t0
-      const uint32_t nb = (uint32_t)min((uint64_t)(kTileWindows + k - 1), rem);
-      const char* p0 = a.bases + off + t0;
-      const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(p0) & 15);
-      const char* al = p0 - sh;
-      uint32_t cw = 0, vw = 0;
-      if (lane <= kTileWords) {
-        const char* cp = al + 16 * lane;
-        if (cp < p0 + nb) {
-          uint4 u;
-          if (cp + 16 <= a.bases + a.n_bases) u = __ldg(reinterpret_cast<const uint4*>(cp));
-          else {
-            unsigned char b[16];
-            for (int i = 0; i < 16; ++i) b[i] = (cp + i < a.bases + a.n_bases) ? (unsigned char)cp[i] : 0;
-            u.x = b[0] | b[1] << 8 | b[2] << 16 | (uint32_t)b[3] << 24; u.y = b[4] | b[5] << 8 | b[6] << 16 | (uint32_t)b[7] << 24;
-            u.z = b[8] | b[9] << 8 | b[10] << 16 | (uint32_t)b[11] << 24; u.w = b[12] | b[13] << 8 | b[14] << 16 | (uint32_t)b[15] << 24;
-          }
-          uint32_t c0, c1, c2, c3, v0, v1, v2, v3;
-          encode4(u.x, c0, v0); encode4(u.y, c1, v1); encode4(u.z, c2, v2); encode4(u.w, c3, v3);
-          cw = c0 << 24 | c1 << 16 | c2 << 8 | c3;
-          vw = v0 << 12 | v1 << 8 | v2 << 4 | v3;
-        }
-      }
-      // align the stream to the tile start: word t covers tile bases 16t .. 16t+15
-      const uint32_t cn = __shfl_down_sync(0xFFFFFFFFu, cw, 1), vn = __shfl_down_sync(0xFFFFFFFFu, vw, 1);
-      const uint32_t cwa = __funnelshift_l(cn, cw, 2 * sh);
-      uint32_t vwa = (((vw << 16) | vn) << sh) >> 16;
-      { // clip validity to the bases that belong to this read
-        const int keep = (int)nb - 16 * (int)lane;    // number of leading bases of this word inside the read
-        if (keep <= 0) vwa = 0; else if (keep < 16) vwa &= 0xFFFFu << (16 - keep);
-      }
-      const uint32_t vhi = __shfl_sync(0xFFFFFFFFu, vwa, (2 * lane) & 31), vlo = __shfl_sync(0xFFFFFFFFu, vwa, (2 * lane + 1) & 31);
-      __syncwarp();
-      if (lane <= kTileWords) sm.code[lane] = cwa;
-      if (lane <= kTileWords / 2) sm.valid[lane] = (vhi << 16) | vlo;
-      if (lane == 0) sm.cursor = 0;
-      __syncwarp();
-
-      // ---- A1. windows -> k-mer words -> bucket ids; eligible lookups compacted into the list
-      const uint32_t nwin = (uint32_t)min((uint64_t)kTileWindows, rem - k + 1);
-      uint32_t nl = 0;
-#pragma unroll
-      for (uint32_t j = 0; j < kTileWindows / 32; ++j) {
-        const uint32_t p = lane + 32 * j;
-        bool valid = false;
-        uint64_t bp = 0;
-        if (p < nwin) {
-          const uint32_t vj = p >> 5, vs = p & 31;
-          const uint32_t vx = __funnelshift_l(sm.valid[vj + 1], sm.valid[vj], vs);
-          valid = (vx >> (32 - k)) == (0xFFFFFFFFu >> (32 - k));
-          const uint32_t cj = p >> 4, cs = 2 * (p & 15);
-          const uint32_t w0 = sm.code[cj], w1 = sm.code[cj + 1], w2 = sm.code[cj + 2];
-          const uint64_t x = ((uint64_t)__funnelshift_l(w1, w0, cs) << 32) | __funnelshift_l(w2, w1, cs);
-          bp = x >> (64 - 2 * k);
-        }
-        onmers += valid;
-        const uint4 rq = lut_pext(lut, (uint32_t)bp, (uint32_t)(bp >> 32), wide);
-#pragma unroll
-        for (uint32_t strand = 0; strand < 2; ++strand) {
-          const uint32_t rix = strand ? rq.z : rq.x, q = strand ? rq.w : rq.y;
-          uint32_t quo, res;
-          if (ix.m_shift != 0xFFFFFFFFu) { quo = rix >> ix.m_shift; res = rix & (ix.m - 1); }
-          else { quo = rix / ix.m; res = rix - quo * ix.m; }
-          const int32_t numer = ix.res_numer[res];
-          const bool elig = valid && numer != 0;
-          const uint32_t offset = numer > 1 ? quo * (uint32_t)numer + res : quo;
-          const uint32_t em = __ballot_sync(0xFFFFFFFFu, elig);
-          if (elig) {
-            const uint32_t idx = nl + __popc(em & lt_mask);
-            sm.lk_a[idx] = offset | (strand << 31);
-            sm.lk_q[idx] = q;
-            if (strand) ++wn1; else ++wn0;
-            if (TAP) {
-              const unsigned long long at = atomicAdd(a.tap_count, 1ull);
-              const uint32_t pos = strand ? (uint32_t)(len - (t0 + p) - k) : (uint32_t)(t0 + p);
-              if (at < a.tap_cap) a.tap[at] = make_uint4(read, strand << 31 | pos, rix, q);
-            }
-          }
-          nl += __popc(em);
-        }
-      }
-      __syncwarp();
+      const uint32_t nl = tile_lookups<TAP>(ix, a, sm, lut, wide, read, off, len, t0, onmers, wn0, wn1);
 
       // ---- A2. bucket ranges [inc[off-1], inc[off]) with all loads of the tile in flight; empty buckets are dropped
       //          (in-place compaction: writes trail reads)
       uint32_t nout = 0, n_long = 0;
       auto flush_long = [&]() { // long buckets: scanned by the whole warp straight from HBM, deduplicated through the markers
-        __syncwarp();
-        for (uint32_t j = 0; j < n_long; ++j) {
-          const uint32_t l = stg->lg_l[j];
-          const uint32_t best = careful_lookup(ix, w, stg->lg_a[j], l & 0x7FFFFFFFu, stg->lg_q[j], l >> 31, th, next_tag(w, tag));
-          if (l >> 31) filt1 = min(filt1, best); else filt0 = min(filt0, best);
-        }
-        __syncwarp();
+        const uint3 r = long_lookups(iv, w, stg, n_long, th, tag, filt0, filt1);
+        tag = r.x; filt0 = r.y; filt1 = r.z;
         n_long = 0;
       };
       for (uint32_t base = 0; base < nl; base += 128) {
@@ -563,7 +715,7 @@ __global__ void __launch_bounds__(warps_per_cta(STAGED) * 32, STAGED ? 1 : 4) ma
             if (cnt == 1) { // exactly one hit entry: no other entry can lower a leaf's distance
               const uint32_t ci = __ldg(&ix.cnode[fse]).x;
               if (ci & kInfoLeaf) commit(w, cs, ci & 0x3FFFFFFFu, fhd);
-              else if (ci & kInfoExpand) { if (ix.local_expand) expand_local(ix, w, fse, cs, fhd, 0xFFFFFFFFu); else cnt = 2; }
+              else if (ci & kInfoExpand) { if (ix.local_expand) expand_local(iv, w, fse, cs, fhd, 0xFFFFFFFFu); else cnt = 2; }
             }
             if (cnt > 1) sm.lk_l[idx] |= kCareful; // several hit entries: handled by the whole warp below
           }
@@ -576,7 +728,7 @@ __global__ void __launch_bounds__(warps_per_cta(STAGED) * 32, STAGED ? 1 : 4) ma
             const int src = __ffs(need) - 1;
             need &= need - 1;
             const uint32_t ll = sm.lk_l[base + src];
-            careful_lookup(ix, w, sm.lk_a[base + src], ll & 0x3FFFFFFFu, sm.lk_q[base + src], ll >> 31, th, next_tag(w, tag));
+            careful_lookup(iv, w, sm.lk_a[base + src], ll & 0x3FFFFFFFu, sm.lk_q[base + src], ll >> 31, th, next_tag(w, tag));
           }
         }
       } else {
@@ -610,58 +762,47 @@ __global__ void __launch_bounds__(warps_per_cta(STAGED) * 32, STAGED ? 1 : 4) ma
           const uint32_t idx = c_idx + grp;
           uint32_t cnt = 0, cs = 0, cq = 0, first = 0, shared_id = 0;
           if (idx < nout) { const uint32_t l = sm.lk_l[idx]; cnt = l & 0x3FFFFFFFu; cs = l >> 31; shared_id = (l >> 30) & 1u; cq = sm.lk_q[idx]; first = sm.lk_a[idx]; }
-          const uint32_t nrows = (__reduce_max_sync(0xFFFFFFFFu, cnt) + 7u) >> 3;
+          const uint32_t lo = first & 1u, hi = lo + cnt;           // this lookup's entries inside its (16-byte aligned) slot
+          const uint32_t nrows = (__reduce_max_sync(0xFFFFFFFFu, cnt ? hi : 0u) + 15u) >> 4; // rows of 16 entries: two per lane of the group
           mbar_wait(bar0 + 8u * (c_round & 1u), (c_round >> 1) & 1u);
-          const uint2* sp = &stg->ent[(c_round & 1u) * kGroups + grp][(first & 1u) + gl];
-          uint32_t hmask = 0; // one bit per row, shifted in from the right: row r of the nrows4 processed ends at bit nrows4-1-r
-          const uint32_t thp1 = th + 1, nrows4 = (nrows + 3u) & ~3u;
-          for (uint32_t r = 0; r < nrows; r += 4) {
-            uint2 e4[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) e4[j] = sp[8 * (r + j)];   // past cnt: stale bytes of the slot, masked below
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t z = e4[j].x ^ cq;
-              const uint32_t hd = __popc((z | (z >> 16)) & 0xFFFFu);
-              hmask = __funnelshift_l(hd - thp1, hmask, 1);         // hd <= th  <=>  the sign bit of hd - (th + 1)
-            }
+          const uint2* slot = &stg->ent[(c_round & 1u) * kGroups + grp][0];
+          const uint4* sp = reinterpret_cast<const uint4*>(slot) + gl;
+          // one bit per entry compared, shifted in from the right: the t-th entry this lane looks at (slot index
+          // 2 gl + 16 (t >> 1) + (t & 1)) ends at bit nbits-1-t
+          uint32_t hmask = 0;
+          const uint32_t thp1 = th + 1, nbits = 2u * nrows;
+#define KREPP_CMP(enc) { const uint32_t z = (enc) ^ cq; hmask = __funnelshift_l(__popc((z | (z >> 16)) & 0xFFFFu) - thp1, hmask, 1); } // hd <= th <=> sign bit of hd - (th + 1)
+          uint32_t r = 0;
+          for (; r + 2 <= nrows; r += 2) {
+            const uint4 e0 = sp[8 * r], e1 = sp[8 * r + 8];          // past the bucket: stale bytes of the slot, masked below
+            KREPP_CMP(e0.x) KREPP_CMP(e0.z) KREPP_CMP(e1.x) KREPP_CMP(e1.z)
           }
-          { // rows this lane really owns: gl + 8 r < cnt
-            const uint32_t own = cnt > gl ? (cnt - gl + 7u) >> 3 : 0u;                // rows 0 .. own-1
-            const uint32_t keep = own ? (0xFFFFFFFFu >> (32u - own)) << (nrows4 - own) : 0u; // their (reversed) bit positions
-            hmask &= keep;
+          if (r < nrows) { const uint4 e0 = sp[8 * r]; KREPP_CMP(e0.x) KREPP_CMP(e0.z) }
+#undef KREPP_CMP
+          { // entries this lane really owns: lo <= slot index < hi
+            const uint32_t rem = hi > 2u * gl ? hi - 2u * gl : 0u;
+            const uint32_t own = 2u * (rem >> 4) + min(rem & 15u, 2u);                   // t = 0 .. own-1
+            uint32_t keep = own ? (0xFFFFFFFFu >> (32u - own)) << (nbits - own) : 0u;    // their (reversed) bit positions
+            if (gl == 0 && lo) keep &= ~(1u << (nbits - 1u));                              // slot entry 0 belongs to the bucket before
+            hmask &= cnt ? keep : 0u;
           }
           if (__any_sync(0xFFFFFFFFu, hmask != 0)) {
             const uint32_t mine = __popc(hmask), total = __reduce_add_sync(0xFFFFFFFFu, mine);
             if (!use_table || total > (uint32_t)kHitCap) {
-              // marker path: the round's lookups one after the other, each under its own tag
-              const bool one_lookup = __shfl_sync(0xFFFFFFFFu, shared_id, 0) != 0; // a long bucket spread over the groups
-              uint32_t tagbase = 0;
-              for (uint32_t g = 0; g < (uint32_t)kGroups; ++g) {
-                if (!__any_sync(0xFFFFFFFFu, grp == g && hmask != 0)) continue;
-                if (!one_lookup || !tagbase) tagbase = next_tag(w, tag);
-                const uint32_t gcs = __shfl_sync(0xFFFFFFFFu, cs, 8 * g);
-                __syncwarp();
-                for (uint32_t r = 0; r < nrows4; ++r) {
-                  const bool hit = grp == g && ((hmask >> (nrows4 - 1u - r)) & 1u);
-                  if (!__any_sync(0xFFFFFFFFu, hit)) continue;
-                  uint32_t se = 0, hd = 0;
-                  if (hit) { const uint2 e = sp[8 * r]; const uint32_t z = e.x ^ cq; hd = __popc((z | (z >> 16)) & 0xFFFFu); se = e.y; if (cs) filt1 = min(filt1, hd); else filt0 = min(filt0, hd); }
-                  expand_hits(ix, w, hit, se, hd, gcs, tagbase);
-                }
-                __syncwarp();
-              }
+              // marker path (out of line): the round's lookups one after the other, each under its own tag
+              const uint3 r3 = marker_round(iv, w, slot, hmask, nbits, cq, cs, shared_id, tag, filt0, filt1);
+              tag = r3.x; filt0 = r3.y; filt1 = r3.z;
             } else {
-              if (n_hits + total > (uint32_t)kHitCap || lk_id + (uint32_t)kGroups > 126u) { resolve_hits(ix, w, stg, n_hits, lk_id, tag); n_hits = 0; lk_id = 0; }
+              if (n_hits + total > (uint32_t)kHitCap || lk_id + (uint32_t)kGroups > 126u) { resolve_hits(iv, w, stg, n_hits, lk_id, tag); n_hits = 0; lk_id = 0; }
               uint32_t incl = mine;
 #pragma unroll
               for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += t; }
               uint32_t at = n_hits + incl - mine, m = hmask;
               const uint32_t meta = (lk_id + (shared_id ? 0u : grp)) << 25 | cs << 24;
               while (m) {
-                const uint32_t bit = 31u - __clz(m), r = nrows4 - 1u - bit; // highest bit first = ascending row
+                const uint32_t bit = 31u - __clz(m), t = nbits - 1u - bit; // highest bit first = ascending entry
                 m ^= 1u << bit;
-                const uint2 e = sp[8 * r];
+                const uint2 e = slot[2u * gl + 16u * (t >> 1) + (t & 1u)];
                 const uint32_t z = e.x ^ cq, hd = __popc((z | (z >> 16)) & 0xFFFFu);
                 if (cs) filt1 = min(filt1, hd); else filt0 = min(filt0, hd);
                 stg->hitq[at++] = make_uint2(e.y, meta | hd);
@@ -676,62 +817,18 @@ __global__ void __launch_bounds__(warps_per_cta(STAGED) * 32, STAGED ? 1 : 4) ma
           ++c_round;
           if (p_idx < nout) issue_round();
         }
-        if (n_hits) resolve_hits(ix, w, stg, n_hits, lk_id, tag);
+        if (n_hits) resolve_hits(iv, w, stg, n_hits, lk_id, tag);
       }
       __syncwarp();
     }
 
     // ---- per-read scalars
     for (int o = 16; o; o >>= 1) {
-      onmers += __shfl_xor_sync(0xFFFFFFFFu, onmers, o);
-      wn0 += __shfl_xor_sync(0xFFFFFFFFu, wn0, o); wn1 += __shfl_xor_sync(0xFFFFFFFFu, wn1, o);
       filt0 = min(filt0, __shfl_xor_sync(0xFFFFFFFFu, filt0, o)); filt1 = min(filt1, __shfl_xor_sync(0xFFFFFFFFu, filt1, o));
     }
     // ---- emit this read's records in (strand, leaf) order and reset the accumulator
-    __syncwarp();
-    uint32_t total = 0;
-    for (uint32_t wbase = 0; wbase < nbm; wbase += 32) {
-      const uint32_t bits = (wbase + lane < nbm) ? __ldcg(&w.bitmap[wbase + lane]) : 0u;
-      uint32_t c = __popc(bits);
-      for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
-      total += c;
-    }
-    uint32_t rbegin = 0;
-    if (lane == 0 && total) rbegin = atomicAdd(a.counters, total);
-    rbegin = __shfl_sync(0xFFFFFFFFu, rbegin, 0);
-    const bool fits = (uint64_t)rbegin + total <= a.rec_cap;
-    if (!fits && lane == 0) atomicOr(a.counters + 2, kErrRecOverflow);
-    // records in ascending slot order; 16 bitmap words (<= 512 slots) per round: lanes 0..15 list the set bits of their
-    // word in shared memory, then every lane takes whole records, so clustered leaves do not pile up on one lane
-    uint32_t done = 0;
-    uint32_t* list = sm.lk_a; // the lookup list is dead here (512 entries with lk_l)
-    for (uint32_t wbase = 0; wbase < nbm; wbase += 16) {
-      uint32_t bits = (lane < 16 && wbase + lane < nbm) ? __ldcg(&w.bitmap[wbase + lane]) : 0u;
-      const uint32_t c = __popc(bits);
-      uint32_t incl = c;
-      for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += t; }
-      const uint32_t cnt = __shfl_sync(0xFFFFFFFFu, incl, 31);
-      if (!cnt) continue;
-      if (bits) w.bitmap[wbase + lane] = 0;
-      uint32_t li = incl - c;
-      while (bits) { const uint32_t b = __ffs(bits) - 1; bits &= bits - 1; list[li++] = (wbase + lane) * 32 + b; }
-      __syncwarp();
-      for (uint32_t i = lane; i < cnt; i += 32) {
-        const uint32_t slot = list[i], at = rbegin + done + i;
-        const uint32_t strand = slot >= nleaves, rank = slot - strand * nleaves;
-        uint32_t* h = w.acc + (size_t)slot * stride;
-        uint32_t hv[kMaxTh + 1];
-        for (uint32_t x = 0; x < stride; ++x) hv[x] = __ldcg(&h[x]);
-        for (uint32_t x = 0; x < stride; ++x) h[x] = 0;
-        if (fits) {
-          a.rec_read[at] = read;
-          a.rec_slot[at] = strand << 31 | ix.leaf_se[rank];
-          for (uint32_t x = 0; x < stride; ++x) a.rec_hist[(size_t)at * stride + x] = hv[x];
-        }
-      }
-      done += cnt;
-      __syncwarp();
-    }
+    uint32_t rbegin; bool fits;
+    const uint32_t total = emit_records(ix, a, w, sm.lk_a, read, filt0, filt1, rbegin, fits); // the lookup list is dead here (512 words with lk_l)
     if (lane == 0) {
       a.onmers[read] = onmers; a.wn[2 * read] = wn0; a.wn[2 * read + 1] = wn1;
       a.hdfilt[2 * read] = filt0; a.hdfilt[2 * read + 1] = filt1;

@@ -93,14 +93,49 @@ def compare_place(i: int, g: dict, o: dict, stats: dict):
         assert rel_close(a["chisq"], b["chisq"]) or abs(a["chisq"] - b["chisq"]) < 1e-7, (i, "place chisq", a, b)
 
 
+def check_gated_subset(gated: dict, full: dict):
+    """The default (gated) output must be exactly the solved records of the keep-all output: per read the same records
+    in the same order with bit-identical numbers (reads land in the record arrays in completion order, which differs
+    from run to run), the same per-read scalars, the same closest record and the same placements."""
+    gr, fr = gated["reads"], full["reads"]
+    for name in ("onmers", "wn", "hdist_filt", "place_count"):
+        assert np.array_equal(gr[name], fr[name]), ("gated read summaries differ in", name)
+    assert len(gated["records"]) == int(((full["records"]["flags"] & 1) != 0).sum()), "gated record count"
+    fields = [n for n in full["records"].dtype.names]
+    for i in range(len(fr)):
+        b, n = int(fr["rec_begin"][i]), int(fr["rec_count"][i])
+        keep = np.nonzero((full["records"]["flags"][b:b + n] & 1) != 0)[0] + b
+        gb, gn = int(gr["rec_begin"][i]), int(gr["rec_count"][i])
+        assert gn == len(keep), (i, "gated rec_count", gn, len(keep))
+        for name in fields:
+            a, c = gated["records"][name][gb:gb + gn], full["records"][name][keep]
+            assert np.array_equal(a, c, equal_nan=(a.dtype.kind == "f")), (i, "gated records differ in", name, a, c)
+        assert np.array_equal(gated["hist"][gb:gb + gn], full["hist"][keep]), (i, "gated histograms differ")
+        cl, gcl = int(fr["closest"][i]), int(gr["closest"][i])
+        assert (cl < 0) == (gcl < 0), (i, "closest")
+        if cl >= 0:
+            assert gcl - gb == int(np.searchsorted(keep, cl)), (i, "closest index")
+        pb, pn, qb = int(fr["place_begin"][i]), int(fr["place_count"][i]), int(gr["place_begin"][i])
+        for name in full["placements"].dtype.names:
+            a, c = gated["placements"][name][qb:qb + pn], full["placements"][name][pb:pb + pn]
+            assert np.array_equal(a, c, equal_nan=(a.dtype.kind == "f")), (i, "gated placements differ in", name)
+
+
 def run_and_compare(index_dir: str, reads: list[bytes], oracle: "O.OracleIndex", gindex: "krepp_b200.Index",
                     check_lookups: bool = True, **params) -> dict:
     th = params.get("hdist_th", 4)
     batch = krepp_b200.IBatch(gindex, reads, **params)
     if check_lookups:
         batch.enable_tap(sum(max(len(r) - oracle.k + 1, 0) for r in reads) * 2 + 16)
+    # default output first: only the (strand, leaf) pairs that pass the hdist_filt gate leave the device ...
     batch.submit()
     res = batch.wait()
+    gated = {k: np.array(res[k], copy=True) for k in ("reads", "records", "hist", "placements")}
+    # ... then parity tap 2: every pair the reference holds before the gate, compared with the oracle stage by stage
+    batch.keep_all_records()
+    batch.submit()
+    res = batch.wait()
+    check_gated_subset(gated, res)
     tap = batch.read_tap() if check_lookups else None
     g = gpu_stage_dicts(batch, res, tap)
     place = bool(params.get("place", False))
