@@ -92,7 +92,7 @@ static std::vector<uint4> build_lut(const HostIndex& h)
 __global__ void __launch_bounds__(128) finalize_kernel(const SolveArgs a, krepp_record_t* out_rec, krepp_read_summary_t* out_read,
                                                         const uint32_t* wn, const uint32_t* place_begin, const uint32_t* place_count)
 {
-  if (a.counters[2] & (kErrRecOverflow | kErrStackOverflow)) return; // incomplete records: the host re-runs the batch
+  if (a.counters[2] & kErrRedo) return; // incomplete records: the host re-runs the batch
   const uint32_t n = a.counters[0] < a.n_records ? a.counters[0] : a.n_records;
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
   for (uint32_t i = tid; i < n; i += nth) {
@@ -160,6 +160,10 @@ struct krepp_batch {
   uint32_t *d_place_begin = nullptr, *d_place_count = nullptr, *d_node_bitmap = nullptr, *d_node_list = nullptr, *d_node_cand = nullptr;
   double *d_node_d = nullptr, *d_node_v = nullptr, *d_node_chisq = nullptr;
   krepp_placement_t *d_place = nullptr, *h_place = nullptr;
+  // bucket-sorted pipeline (sorted.cu)
+  bool sorted = false, fused_once = false;
+  SortArgs so{};
+  uint32_t* h_sc = nullptr;   // [0..7] copy of so.sc, [8] lookups of the batch
   // tap
   uint4* d_tap = nullptr; unsigned long long* d_tap_count = nullptr; unsigned long long tap_cap = 0;
 };
@@ -219,6 +223,12 @@ int krepp_index_open(const char* index_dir, int device, krepp_index_t** out)
   if (e == cudaSuccess) e = upload(h.tree.blen, &d.blen, ix->allocs, ix->device_bytes);
   if (e == cudaSuccess) e = upload(build_lut(h), &d.lut, ix->allocs, ix->device_bytes);
   if (e == cudaSuccess) e = upload(h.tree.subtree, &d.subtree, ix->allocs, ix->device_bytes);
+  d.cbeg = nullptr; d.cleaf = nullptr;
+  if (!h.cbeg.empty()) { // flattened colours: what the bucket-sorted pipeline (sorted.cu) expands hits with
+    if (e == cudaSuccess) e = upload(h.cbeg, &d.cbeg, ix->allocs, ix->device_bytes);
+    if (e == cudaSuccess) e = upload(h.cleaf, &d.cleaf, ix->allocs, ix->device_bytes, 1);
+    ix->sorted_ok = true;
+  }
   if (e != cudaSuccess) {
     for (void* p : ix->allocs) cudaFree(p);
     delete ix;
@@ -235,6 +245,9 @@ int krepp_index_open(const char* index_dir, int device, krepp_index_t** out)
     ix->staged = sb > 24.0;
     if (const char* env = getenv("KREPP_SCAN")) { if (!strcmp(env, "staged")) ix->staged = true; else if (!strcmp(env, "lane")) ix->staged = false; }
   }
+  // Pipeline (see sorted.cu): indexes with large buckets are matched bucket-sorted, so that a bucket is read from HBM once per
+  // batch; small-bucket indexes keep the fused kernel.  KREPP_PIPELINE=sorted|fused overrides (read again per batch slot).
+  ix->sorted_default = ix->sorted_ok && ix->staged;
   ix->resident_warps = match_resident_warps(device, h.k, ix->staged);
   if (ix->staged && ix->resident_warps == 0) { ix->staged = false; ix->resident_warps = match_resident_warps(device, h.k, false); } // k > 28: the ring does not fit beside an 8-table LUT
   *out = ix;
@@ -326,6 +339,48 @@ static int alloc_records(krepp_batch* b, uint32_t cap)
   return KREPP_OK;
 }
 
+static int alloc_tuples(krepp_batch* b, uint64_t cap)
+{
+  if (cap > 0xFFFFFFF0ull) return fail(KREPP_ERR_CAPACITY, "batch produces too many lookups; submit fewer reads per batch");
+  if (b->so.tuples) cudaFree(b->so.tuples);
+  b->so.tuples = nullptr; b->so.cap_lookups = (uint32_t)cap;
+  CU(cudaMalloc(&b->so.tuples, 16ull * cap));
+  return KREPP_OK;
+}
+
+static int alloc_hits(krepp_batch* b, uint64_t cap)
+{
+  if (cap > 0xFFFFFFF0ull) return fail(KREPP_ERR_CAPACITY, "batch produces too many hit entries; submit fewer reads per batch");
+  if (b->so.hits_tmp) cudaFree(b->so.hits_tmp);
+  if (b->so.hits) cudaFree(b->so.hits);
+  b->so.hits_tmp = b->so.hits = nullptr; b->so.cap_hits = (uint32_t)cap;
+  CU(cudaMalloc(&b->so.hits_tmp, 16ull * cap)); CU(cudaMalloc(&b->so.hits, 16ull * cap));
+  return KREPP_OK;
+}
+
+static int alloc_sorted(krepp_batch* b)
+{
+  const HostIndex& h = b->ix->host;
+  SortArgs& so = b->so;
+  so.nrows = h.nrows;
+  CU(cudaMalloc(&so.row_count, 4ull * h.nrows)); CU(cudaMalloc(&so.row_begin, 4ull * (h.nrows + 1))); CU(cudaMalloc(&so.row_cursor, 4ull * h.nrows));
+  CU(cudaMalloc(&so.hit_count, 4ull * b->max_reads)); CU(cudaMalloc(&so.hit_begin, 4ull * (b->max_reads + 1ull))); CU(cudaMalloc(&so.hit_cursor, 4ull * b->max_reads));
+  const uint64_t nmax = std::max<uint64_t>(h.nrows, b->max_reads);
+  CU(cudaMalloc(&so.partials, 4ull * (nmax / 4096 + 2)));
+  CU(cudaMalloc(&so.sc, 32));
+  CU(cudaMallocHost(&b->h_sc, 64));
+  if (const char* env = getenv("KREPP_SORT_WIDE")) so.extra_rank_bits = (uint32_t)std::min(24, std::max(0, atoi(env)));
+  so.cap_keys_g = 8192; // 64-bit keys per warp (a power of two): reads with more leaf hits send the batch to the fused kernel
+  CU(cudaMalloc(&so.keys_g, 8ull * so.cap_keys_g * (size_t)sorted_resolve_warps(b->ix->sms)));
+  // every base starts at most one window = two lookups, of which (r+1)/m are eligible on average; grown on demand
+  uint32_t present = 0;
+  for (uint32_t res = 0; res < h.m; ++res) present += h.res_numer[res] != 0;
+  const uint64_t want = (uint64_t)((double)b->max_bases * 2.0 * present / (double)h.m * 1.1) + 4096;
+  if (int rc = alloc_tuples(b, std::min<uint64_t>(want, 0xFFFFFFF0ull))) return rc;
+  if (int rc = alloc_hits(b, std::min<uint64_t>(std::max<uint64_t>(96ull * b->max_reads, 65536), 0xFFFFFFF0ull))) return rc;
+  return KREPP_OK;
+}
+
 int krepp_batch_create(krepp_index_t* ix, const krepp_params_t* p, uint32_t max_reads, uint64_t max_bases, krepp_batch_t** out)
 {
   if (!ix || !p || !out || !max_reads) return fail(KREPP_ERR_ARG, "krepp_batch_create: bad argument");
@@ -368,6 +423,12 @@ int krepp_batch_create(krepp_index_t* ix, const krepp_params_t* p, uint32_t max_
   CU(cudaMalloc(&b->d_tagctr, 4 * warps)); CU(cudaMemset(b->d_tagctr, 0xFF, 4 * warps));
   const uint64_t want = std::max<uint64_t>(4ull * max_reads, 4096);
   if (int rc = alloc_records(b, (uint32_t)std::min<uint64_t>(want, 0x7FFFFFFFull))) return rc;
+  b->sorted = ix->sorted_default;
+  if (const char* env = getenv("KREPP_PIPELINE")) {
+    if (!strcmp(env, "sorted")) { if (!ix->sorted_ok) return fail(KREPP_ERR_UNSUPPORTED, "KREPP_PIPELINE=sorted: the flattened colour lists of this index are too large"); b->sorted = true; }
+    else if (!strcmp(env, "fused")) b->sorted = false;
+  }
+  if (b->sorted) { if (int rc = alloc_sorted(b)) return rc; }
   if (p->place) {
     const size_t nn = h.tree.nnodes, nbm_nodes = (nn + 32) / 32;
     b->place_warps = (uint32_t)ix->sms * 4u * (uint32_t)kPlaceWarpsPerCta;
@@ -393,6 +454,10 @@ void krepp_batch_destroy(krepp_batch_t* b)
                   (void*)b->d_place_count, (void*)b->d_node_bitmap, (void*)b->d_node_list, (void*)b->d_node_cand, (void*)b->d_node_d, (void*)b->d_node_v,
                   (void*)b->d_node_chisq, (void*)b->d_place})
     if (p) cudaFree(p);
+  for (void* p : {(void*)b->so.row_count, (void*)b->so.row_begin, (void*)b->so.row_cursor, (void*)b->so.tuples, (void*)b->so.hits_tmp, (void*)b->so.hits,
+                  (void*)b->so.hit_count, (void*)b->so.hit_begin, (void*)b->so.hit_cursor, (void*)b->so.partials, (void*)b->so.sc, (void*)b->so.keys_g})
+    if (p) cudaFree(p);
+  if (b->h_sc) cudaFreeHost(b->h_sc);
   for (void* p : {(void*)b->h_bases, (void*)b->h_offsets, (void*)b->h_read, (void*)b->h_counters, (void*)b->h_stats, (void*)b->h_place})
     if (p) cudaFreeHost(p);
   if (b->ev0) cudaEventDestroy(b->ev0);
@@ -419,7 +484,12 @@ static int enqueue(krepp_batch* b)
   m.acc = b->d_acc; m.bitmap = b->d_bitmap; m.marker = b->d_marker; m.stack = b->d_stack; m.stack_cap = b->stack_cap; m.tagctr = b->d_tagctr; m.stats = b->d_stats;
   m.tap = b->d_tap; m.tap_count = b->d_tap_count; m.tap_cap = b->tap_cap;
   CU(cudaEventRecord(b->evm0, s));
-  CU(launch_match(ix->dev, m, ix->resident_warps, ix->staged, b->d_tap != nullptr, s));
+  uint32_t match_launches = 1;
+  if (b->sorted && !b->fused_once) {
+    CU(launch_match_sorted(ix->dev, m, b->so, ix->sms, b->d_tap != nullptr, s, &match_launches));
+    CU(cudaMemcpyAsync(b->h_sc, b->so.sc, 32, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(b->h_sc + 8, b->so.row_begin + b->so.nrows, 4, cudaMemcpyDeviceToHost, s));
+  } else CU(launch_match(ix->dev, m, ix->resident_warps, ix->staged, b->d_tap != nullptr, s));
   CU(cudaEventRecord(b->evm1, s));
   SolveArgs sa{};
   sa.n_reads = b->n_reads; sa.th = b->p.hdist_th; sa.k = h.k; sa.h = h.h; sa.n_records = b->rec_cap; sa.counters = b->d_counters; sa.work = b->d_rec_work;
@@ -429,7 +499,7 @@ static int enqueue(krepp_batch* b)
   sa.rec_hdmin = b->d_rec_hdmin; sa.closest = b->d_closest;
   sa.want_chisq = (!b->p.no_filter || b->p.summarize || b->p.place) ? 1 : 0;
   CU(launch_solve(sa, b->tab, ix->sms, s));
-  b->launches = 5 + (sa.want_chisq ? 1 : 0);
+  b->launches = 4 + match_launches + (sa.want_chisq ? 1 : 0);
   if (b->p.place) {
     PlaceArgs pa{};
     pa.s = sa; pa.offsets = b->in_offsets; pa.tau = b->p.tau; pa.no_filter = b->p.no_filter; pa.chisq_value = b->p.chisq;
@@ -478,7 +548,7 @@ int krepp_batch_submit(krepp_batch_t* b, const char* bases, const uint64_t* offs
     const uint64_t o0 = offsets[0];
     for (uint32_t i = 0; i <= n_reads; ++i) b->h_offsets[i] = offsets[i] - o0;
   }
-  b->n_reads = n_reads; b->n_bases = nb; b->device_input = false;
+  b->n_reads = n_reads; b->n_bases = nb; b->device_input = false; b->fused_once = false;
   b->in_bases = b->d_bases; b->in_offsets = b->d_offsets;
   CU(cudaMemcpyAsync(b->d_bases, src, nb, cudaMemcpyHostToDevice, b->stream));
   CU(cudaMemcpyAsync(b->d_offsets, b->h_offsets, 8ull * (n_reads + 1), cudaMemcpyHostToDevice, b->stream));
@@ -495,7 +565,7 @@ int krepp_batch_submit_device(krepp_batch_t* b, const char* d_bases, const uint6
   if (reinterpret_cast<uintptr_t>(d_bases) & 15) return fail(KREPP_ERR_ARG, "device bases pointer must be 16-byte aligned");
   if (cudaSetDevice(b->ix->device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice failed");
   CU(cudaStreamSynchronize(b->stream));
-  b->n_reads = n_reads; b->n_bases = n_bases; b->device_input = true;
+  b->n_reads = n_reads; b->n_bases = n_bases; b->device_input = true; b->fused_once = false;
   b->in_bases = d_bases; b->in_offsets = d_offsets;
   CU(cudaEventRecord(b->ev0, b->stream));
   if (int rc = enqueue(b)) return rc;
@@ -511,14 +581,23 @@ int krepp_batch_wait(krepp_batch_t* b, krepp_results_t* out)
   for (int attempt = 0;; ++attempt) {
     CU(cudaStreamSynchronize(b->stream));
     if (b->h_counters[2] & kErrStackOverflow) return fail(KREPP_ERR_CAPACITY, "colour expansion stack overflow on the device");
-    if (!(b->h_counters[2] & (kErrRecOverflow | kErrPlaceOverflow))) break;
+    if (!(b->h_counters[2] & (kErrRecOverflow | kErrPlaceOverflow | kErrLookupOverflow | kErrHitOverflow | kErrSortFallback))) break;
     // a result buffer was too small: grow it to what the kernels asked for and run the batch again
-    if (attempt >= 4) return fail(KREPP_ERR_CAPACITY, "result buffer overflow persists");
+    if (attempt >= 8) return fail(KREPP_ERR_CAPACITY, "result buffer overflow persists");
     if (b->h_counters[2] & kErrRecOverflow) {
       const uint64_t want = std::max<uint64_t>((uint64_t)b->h_counters[0] + b->h_counters[0] / 4, (uint64_t)b->rec_cap + 4096); // exact demand + 25 %
       if (want > 0x7FFFFFFFull) return fail(KREPP_ERR_CAPACITY, "batch produces too many records; submit fewer reads per batch");
       if (int rc = alloc_records(b, (uint32_t)want)) return rc;
     }
+    if (b->h_counters[2] & kErrLookupOverflow) { // the batch's lookup list: exact demand + 10 %
+      const uint64_t need = b->h_sc[8];
+      if (int rc = alloc_tuples(b, need + need / 10 + 4096)) return rc;
+    }
+    if (b->h_counters[2] & kErrHitOverflow) {
+      const uint64_t need = b->h_sc[0];
+      if (int rc = alloc_hits(b, need + need / 4 + 4096)) return rc;
+    }
+    if (b->h_counters[2] & kErrSortFallback) b->fused_once = true; // a read outside the sorted pipeline's limits: this batch goes through the fused kernel
     if (b->h_counters[2] & kErrPlaceOverflow) {
       const uint64_t want = std::max<uint64_t>((uint64_t)b->h_counters[3] + b->h_counters[3] / 4, (uint64_t)b->place_cap + 4096);
       if (want > 0x7FFFFFFFull) return fail(KREPP_ERR_CAPACITY, "batch produces too many placements; submit fewer reads per batch");

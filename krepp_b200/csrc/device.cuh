@@ -32,6 +32,8 @@ struct DevIndex {
   uint32_t k, h, m, m_shift; // m_shift = log2(m) when m is a power of two, else 0xffffffff
   uint32_t local_expand;    // 1 when the deepest colour DAG fits the lane-private expansion stack
   const uint4* lut;         // [bytes of the k-mer word][256]: {rix fwd, q fwd, rix rc, q rc} parts (match.cu lut_pext)
+  const uint32_t* cbeg;     // [nsubsets + 1] flattened colours: the leaves colour id se expands to (the walk of
+  const uint32_t* cleaf;    //   ref src/query.cpp:369-387 done once at load) are cleaf[cbeg[se] .. cbeg[se+1]), as leaf ranks
   int32_t res_numer[kMaxResidues];
 };
 
@@ -66,35 +68,32 @@ struct MatchArgs {
   uint4* tap;
   unsigned long long* tap_count;
   unsigned long long tap_cap;
-  // mode B, owner side (match_kernel<.., OWNER>): a work item is the run of lookups one source read sent to this shard
-  const uint2* tuples;        // {row offset local to this shard | strand << 31, residual q}
-  const uint32_t* grp_begin;  // [n_reads] first tuple of the read's run
-  const uint32_t* grp_cnt;    // [n_reads] length of the run
 };
 
-// Mode B (index sharded by LSH bucket range): the home rank turns reads into lookups binned by owner.
-constexpr int kMaxShards = 16;
-struct ShardArgs {
-  uint32_t nshards, pitch;              // pitch = reads capacity of the per-shard count arrays
-  uint32_t row_split[kMaxShards + 1];   // shard p owns bucket rows [row_split[p], row_split[p+1])
-  uint32_t* cnt;                        // [nshards][pitch] lookups of each read that go to shard p
-  const uint32_t* begin;                // [nshards][pitch] exclusive prefix of cnt within shard p's segment
-  const uint32_t* seg_base;             // [nshards + 1] first tuple of shard p's segment
-  uint2* tuples;                        // all segments back to back
-};
-
-// Mode B, home side again: partial records returned by the owners are summed per (read, strand, leaf).
-struct CombineArgs {
-  uint32_t nshards, pitch, n_reads, th;
-  const uint32_t* rec_read; const uint32_t* rec_slot; const uint32_t* rec_hist; // received partial records, owner after owner
-  const uint32_t* seg_base;   // [nshards + 1] first partial record of owner p
-  const uint32_t* rc;         // [nshards][pitch] partial records of each read at owner p
-  const uint32_t* rbegin;     // [nshards][pitch] exclusive prefix of rc within owner p's segment
-  const uint32_t* hdfilt_in;  // [nshards][pitch][2]
-  const uint64_t* offsets;    // read offsets (for the algorithmic-byte count)
+// Bucket-sorted pipeline (sorted.cu): per-slot buffers between its kernels.
+struct SortArgs {
+  uint32_t nrows;
+  uint32_t* row_count;    // [nrows] lookups per bucket row of this batch
+  uint32_t* row_begin;    // [nrows + 1] exclusive prefix of row_count; [nrows] = lookups of the batch
+  uint32_t* row_cursor;   // [nrows] fill cursors (start as row_begin)
+  uint4* tuples;          // [cap_lookups] {q, read, local lookup index | strand << 31, 0}, grouped by row
+  uint32_t cap_lookups;
+  uint4* hits_tmp;        // [cap_hits] {read, strand << 31 | local lookup index << 5 | hd, colour id, 0} in join order
+  uint4* hits;            // [cap_hits] {first leaf of the colour in cleaf, number of leaves, same meta word, 0}, grouped by read
+  uint32_t cap_hits;
+  uint32_t* hit_count;    // [n_reads] hit entries per read
+  uint32_t* hit_begin;    // [n_reads + 1] exclusive prefix; [n_reads] = hit entries of the batch
+  uint32_t* hit_cursor;   // [n_reads]
+  uint32_t* partials;     // scan scratch
+  uint32_t* sc;           // [0] hit entries appended, [1] next row to claim, [2] next read to claim (lookup pass 1), [3] (pass 2), [4] (resolve)
+  uint64_t* keys_g;       // [warps][cap_keys_g] per-warp sort scratch in HBM for reads whose leaf hits exceed shared memory
+  uint32_t cap_keys_g;
+  uint32_t extra_rank_bits; // test knob (KREPP_SORT_WIDE): widens the leaf field of the sort keys so that the 64-bit key path runs
 };
 
 constexpr uint32_t kErrRecOverflow = 1u, kErrStackOverflow = 2u, kErrPlaceOverflow = 4u;
+constexpr uint32_t kErrLookupOverflow = 8u, kErrHitOverflow = 16u, kErrSortFallback = 32u; // sorted pipeline: grow tuples / grow hits / redo the batch with the fused kernel
+constexpr uint32_t kErrRedo = kErrRecOverflow | kErrStackOverflow | kErrLookupOverflow | kErrHitOverflow | kErrSortFallback; // records are incomplete: later kernels skip, the host re-runs the batch
 
 struct SolveArgs {
   uint32_t n_reads, th, k, h;

@@ -10,6 +10,8 @@ struct krepp_index {
   krepp::DevIndex dev{};
   int device = 0, sms = 0, resident_warps = 0;
   bool staged = false; // match.cu phase B strategy: bucket streaming through shared memory (large buckets) or lane-per-bucket
+  bool sorted_ok = false;      // flattened colour lists are resident: the bucket-sorted pipeline (sorted.cu) can run
+  bool sorted_default = false; // ... and is what batch slots use unless KREPP_PIPELINE says otherwise
   uint64_t device_bytes = 0;
   std::vector<void*> allocs;
 };

@@ -341,13 +341,15 @@ std::string HostIndex::load(const std::string& dir)
   {
     std::vector<uint32_t> depth(nsubsets, 0), leaves(nsubsets, 0);
     std::vector<uint8_t> state(nsubsets, 0); // 0 new, 1 open, 2 done
-    std::vector<uint32_t> st;
+    std::vector<uint32_t> st, order; // order: colour ids, children before parents
+    order.reserve(nsubsets);
     for (uint32_t s0 = 0; s0 < nsubsets; ++s0) {
       if (state[s0]) continue;
       st.push_back(s0);
       while (!st.empty()) {
         const uint32_t se = st.back();
-        if (kind[se] != 2) { state[se] = 2; depth[se] = 0; leaves[se] = kind[se] == 1; st.pop_back(); continue; }
+        if (state[se] == 2) { st.pop_back(); continue; } // pushed twice before it was finished (both children of one node)
+        if (kind[se] != 2) { state[se] = 2; depth[se] = 0; leaves[se] = kind[se] == 1; order.push_back(se); st.pop_back(); continue; }
         const uint32_t a = (uint32_t)pse[se], b = (uint32_t)(pse[se] >> 32);
         if (a >= nsubsets || b >= nsubsets) return "The colour record of the index is corrupt (child id out of range)!";
         if (state[se] == 0) {
@@ -362,11 +364,38 @@ std::string HostIndex::load(const std::string& dir)
         state[se] = 2;
         depth[se] = 1 + std::max(depth[a], depth[b]);
         leaves[se] = leaves[a] + leaves[b];
+        order.push_back(se);
         st.pop_back();
       }
     }
     max_expand_depth = *std::max_element(depth.begin(), depth.end());
     max_colour_leaves = *std::max_element(leaves.begin(), leaves.end());
+    // flattened leaf lists, built children first; duplicates (a leaf reachable along two paths) are merged away
+    uint64_t total = 0;
+    for (uint32_t c : leaves) total += c;
+    if (total <= kMaxFlatLeaves && tree.nleaves) {
+      std::vector<uint64_t> start(nsubsets + 1, 0);
+      std::vector<uint32_t> flat;
+      flat.reserve(total);
+      std::vector<uint32_t> len(nsubsets, 0);
+      for (uint32_t se : order) {
+        start[se] = flat.size();
+        if (kind[se] == 1) { flat.push_back(tree.leaf_rank[se]); len[se] = 1; }
+        else if (kind[se] == 2) {
+          const uint32_t a = (uint32_t)pse[se], b = (uint32_t)(pse[se] >> 32);
+          const size_t at = flat.size();
+          flat.resize(at + len[a] + len[b]);
+          std::merge(flat.begin() + start[a], flat.begin() + start[a] + len[a], flat.begin() + start[b], flat.begin() + start[b] + len[b], flat.begin() + at);
+          const auto e = std::unique(flat.begin() + at, flat.end());
+          flat.resize(e - flat.begin());
+          len[se] = (uint32_t)(flat.size() - at);
+        }
+      }
+      cbeg.assign(nsubsets + 1, 0);
+      for (uint32_t se = 0; se < nsubsets; ++se) cbeg[se + 1] = cbeg[se] + len[se];
+      cleaf.resize(cbeg[nsubsets]);
+      for (uint32_t se = 0; se < nsubsets; ++se) std::copy(flat.begin() + start[se], flat.begin() + start[se] + len[se], cleaf.begin() + cbeg[se]);
+    }
   }
   return "";
 }

@@ -48,6 +48,11 @@ struct HostIndex {
   std::vector<uint8_t> kind;                  // [nsubsets]: 0 drop (null node), 1 leaf, 2 expand through pse
   uint32_t max_expand_depth = 0;              // deepest colour DAG expansion (bounds the device stack)
   uint32_t max_colour_leaves = 0;
+  // Flattened colours for the bucket-sorted pipeline: colour id se expands (the walk of ref src/query.cpp:369-387, null
+  // nodes dropped, a leaf reached twice kept once) to the leaf ranks cleaf[cbeg[se] .. cbeg[se+1]), ascending.  Empty
+  // when the lists would exceed kMaxFlatLeaves entries; the fused kernel, which walks the DAG on the device, is used then.
+  std::vector<uint32_t> cbeg, cleaf;
+  static constexpr uint64_t kMaxFlatLeaves = 1ull << 30;
   double mean_bucket = 0, size_biased_bucket = 0;
   HostTree tree;
   // Returns "" on success, else an error message (the reference's wording where it has one).

@@ -99,7 +99,7 @@ __device__ void brent_minimum(const Objective& f, double& xo, double& fo)
 // with full warps (on the 1,000-genome index only about a quarter of the records pass).
 __global__ void __launch_bounds__(256) gate_kernel(const SolveArgs a)
 {
-  if (a.counters[2] & (kErrRecOverflow | kErrStackOverflow)) return; // the host grows the buffers and runs the batch again
+  if (a.counters[2] & kErrRedo) return; // the host grows the buffers and runs the batch again
   const uint32_t n = a.counters[0] < a.n_records ? a.counters[0] : a.n_records;
   const uint32_t stride = a.th + 1, lane = threadIdx.x & 31;
   const uint32_t nround = (n + 31) & ~31u; // whole warps stay together for the ballot
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(256) gate_kernel(const SolveArgs a)
 // One thread per work item: Brent on the record's histogram.
 __global__ void __launch_bounds__(128) solve_kernel(const SolveArgs a, const LlhTables tab)
 {
-  if (a.counters[2] & (kErrRecOverflow | kErrStackOverflow)) return;
+  if (a.counters[2] & kErrRedo) return;
   const uint32_t n = a.counters[4];
   const uint32_t stride = a.th + 1;
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(128) solve_kernel(const SolveArgs a, const Llh
 // then reverse leaves by ascending se; `<=` kept so the last tied entry wins -- SURVEY.md section 0 fact 6).
 __global__ void __launch_bounds__(128) merge_kernel(const SolveArgs a)
 {
-  if (a.counters[2] & (kErrRecOverflow | kErrStackOverflow)) return; // the host grows the buffers and runs the batch again
+  if (a.counters[2] & kErrRedo) return; // the host grows the buffers and runs the batch again
   for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < a.n_reads; r += gridDim.x * blockDim.x) {
     const uint32_t b = a.rec_begin[r], n = a.rec_count[r];
     int32_t cl = -1;
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(128) merge_kernel(const SolveArgs a)
 // One thread per selected record: chisq = 2 * (f_closest(d_record) - v_closest).
 __global__ void __launch_bounds__(128) chisq_kernel(const SolveArgs a, const LlhTables tab)
 {
-  if (a.counters[2] & (kErrRecOverflow | kErrStackOverflow)) return; // the host grows the buffers and runs the batch again
+  if (a.counters[2] & kErrRedo) return; // the host grows the buffers and runs the batch again
   const uint32_t n = a.counters[0] < a.n_records ? a.counters[0] : a.n_records;
   const uint32_t stride = a.th + 1;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -221,7 +221,7 @@ __device__ __forceinline__ double jukes_cantor(double d) { return -0.75 * log(1 
 __global__ void __launch_bounds__(128) place_kernel(const PlaceArgs a, const LlhTables tab)
 {
   const SolveArgs& s = a.s;
-  if (s.counters[2] & (kErrRecOverflow | kErrStackOverflow)) return;
+  if (s.counters[2] & kErrRedo) return;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   const uint32_t stride = s.th + 1, nbm = (a.nnodes + 32) >> 5;

@@ -12,6 +12,9 @@ struct LlhTables {
 
 int match_resident_warps(int device, uint32_t k, bool staged);
 cudaError_t launch_match(const DevIndex& ix, const MatchArgs& a, int resident_warps, bool staged, bool tap, cudaStream_t stream);
+// sorted.cu: the bucket-sorted form of the match stage (same outputs as launch_match)
+int sorted_resolve_warps(int sms);
+cudaError_t launch_match_sorted(const DevIndex& ix, const MatchArgs& a, const SortArgs& s, int sms, bool tap, cudaStream_t stream, uint32_t* launches);
 cudaError_t launch_solve(const SolveArgs& a, const LlhTables& tab, int sms, cudaStream_t stream);
 constexpr int kPlaceWarpsPerCta = 4;
 cudaError_t launch_place(const PlaceArgs& a, const LlhTables& tab, int grid, cudaStream_t stream);

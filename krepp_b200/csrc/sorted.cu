@@ -1,0 +1,566 @@
+// sorted.cu -- the bucket-sorted form of K1..K3 (sm_100a): the same lookups, bucket scans, colour expansion and Hamming
+// histograms as the fused kernel of match.cu, organised so that every bucket of the index is read from HBM ONCE per
+// batch instead of once per lookup.
+//
+//   L1  lookup_kernel<COUNT>    warp per read: bases -> eligible lookups of both strands (tile_lookups, the A0/A1 stages
+//                               of match.cu; ref src/query.cpp:40-94, src/lshf.cpp:62-69, src/index.hpp:27); counts the
+//                               lookups of every bucket row; per-read onmers / wnmers
+//   S1  scan                    row counts -> row ranges of the batch's lookup list
+//   L2  lookup_kernel<SCATTER>  the same lookups again (cheaper than storing them), written into their row's range as
+//                               {q, read, local lookup index | strand}: a counting sort by LSH bucket
+//   J   join_kernel             warp per bucket row: the row's index entries sit in registers (one coalesced read of
+//                               cmer), the row's queries stream past them from shared memory; XOR / OR / popc
+//                               (ref src/common.hpp:175, src/query.cpp:361-368); hit entries {read, lookup, colour, hd}
+//                               are queued per warp and appended to a batch-wide list
+//   S2  scan + hit_scatter      hit entries grouped by read (counting sort by read), colour id -> its flattened leaf list
+//   R   resolve_kernel          warp per read: hit entries -> (strand, leaf, lookup, hd) keys -> bitonic sort in shared
+//                               memory -> per (strand, leaf): one count per lookup at its minimum distance
+//                               (Minfo::update_match, ref src/query.hpp:153-176), per-strand hdist_filt and its gate
+//                               (ref src/query.cpp:101-106,116-119), records in (strand, leaf) order
+//
+// Everything is integer work and bit-exact with the fused kernel (same records in the same order).  Batches or reads
+// that do not fit this pipeline's buffers raise a flag; the host then grows the buffer or redoes the batch with the
+// fused kernel (api.cu).
+#include "device.cuh"
+#include "match_common.cuh"
+#include "solve.cuh"
+
+namespace krepp {
+
+constexpr int kLkWarps = 16;           // lookup kernel: warps per CTA (two CTAs per SM beside the 28-32 kB LUT)
+constexpr uint32_t kLkClaim = 8;       // reads claimed per atomic
+constexpr int kJoinWarps = 8;
+constexpr uint32_t kRowClaim = 32;     // bucket rows claimed per atomic: one per lane
+constexpr int kJoinChunk = 128;        // index entries held in registers per pass: four per lane
+constexpr int kHitQ = 256;             // per-warp queue of hit entries; flushed once fewer than kJoinChunk slots are free
+constexpr int kResWarps = 8;
+constexpr int kResKeys = 1024;         // 32-bit sort keys per warp in shared memory (half as many 64-bit keys)
+constexpr uint32_t kResClaim = 4;
+constexpr uint32_t kMaxLoc = 1u << 26; // local lookup indices must fit bits 5..30 of the hit word
+
+// ---------------------------------------------------------------------------------------------------- L1 / L2
+
+template <bool SCATTER, bool TAP>
+__global__ void __launch_bounds__(kLkWarps * 32, 2) lookup_kernel(const DevIndex ix, const MatchArgs a, const SortArgs s)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const uint32_t nchunks = lut_chunks(ix.k);
+  uint4* lut = reinterpret_cast<uint4*>(smem_raw);
+  WarpSmem* smem = reinterpret_cast<WarpSmem*>(smem_raw + nchunks * 256 * sizeof(uint4));
+  if (SCATTER && s.row_begin[s.nrows] > s.cap_lookups) { // the lookup list does not fit: the host grows it and runs the batch again
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(a.counters + 2, kErrLookupOverflow);
+    return;
+  }
+  for (uint32_t i = threadIdx.x; i < nchunks * 256; i += blockDim.x) lut[i] = ix.lut[i];
+  __syncthreads();
+  const bool wide = nchunks > 7;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, k = ix.k;
+  WarpSmem& sm = smem[warp];
+  uint32_t* claimctr = s.sc + (SCATTER ? 3 : 2);
+  unsigned long long st_bytes = 0, st_lookups = 0;
+  uint32_t claim = 0, claim_end = 0;
+  for (;;) {
+    if (claim == claim_end) {
+      if (lane == 0) claim = atomicAdd(claimctr, kLkClaim);
+      claim = __shfl_sync(0xFFFFFFFFu, claim, 0);
+      claim_end = min(claim + kLkClaim, a.n_reads);
+      if (claim >= a.n_reads) break;
+    }
+    const uint32_t read = claim++;
+    const uint64_t off = a.offsets[read];
+    const uint64_t len = a.offsets[read + 1] - off;
+    uint32_t onmers = 0, wn0 = 0, wn1 = 0, loc = 0;
+    for (uint64_t t0 = 0; t0 + k <= len; t0 += kTileWindows) {
+      const uint32_t nl = tile_lookups<TAP && !SCATTER>(ix, a, sm, lut, wide, read, off, len, t0, onmers, wn0, wn1);
+      if (loc + nl >= kMaxLoc) { if (lane == 0) atomicOr(a.counters + 2, kErrSortFallback); break; }
+      for (uint32_t i = lane; i < nl; i += 32) {
+        const uint32_t ob = sm.lk_a[i], row = ob & 0x7FFFFFFFu;
+        if (!SCATTER) atomicAdd(&s.row_count[row], 1u);
+        else {
+          const uint32_t pos = atomicAdd(&s.row_cursor[row], 1u);
+          s.tuples[pos] = make_uint4(sm.lk_q[i], read, (loc + i) | (ob & 0x80000000u), 0u);
+        }
+      }
+      loc += nl;
+      __syncwarp();
+    }
+    if (!SCATTER && lane == 0) {
+      a.onmers[read] = onmers; a.wn[2 * read] = wn0; a.wn[2 * read + 1] = wn1;
+      st_bytes += len; st_lookups += wn0 + wn1;
+    }
+  }
+  if (!SCATTER && lane == 0 && (st_bytes | st_lookups)) { atomicAdd(a.stats, st_bytes + 16ull * st_lookups); atomicAdd(a.stats + 1, st_lookups); }
+}
+
+// ---------------------------------------------------------------------------------------------------- S1 / S2: exclusive scan
+
+constexpr int kScanThreads = 256, kScanItems = 16, kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* warp_sums, uint32_t& block_total)
+{
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  uint32_t incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += t; }
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();
+  uint32_t before = 0, total = 0;
+  for (uint32_t w = 0; w < nwarps; ++w) { const uint32_t x = warp_sums[w]; if (w < warp) before += x; total += x; }
+  __syncthreads();
+  block_total = total;
+  return before + incl - v;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_sums_kernel(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ partials)
+{
+  __shared__ uint32_t warp_sums[kScanThreads / 32];
+  const uint32_t base = blockIdx.x * kScanTile;
+  uint32_t v = 0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) { const uint32_t j = base + i * kScanThreads + threadIdx.x; if (j < n) v += in[j]; }
+  uint32_t total;
+  block_exclusive_scan(v, warp_sums, total);
+  if (threadIdx.x == 0) partials[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) scan_top_kernel(uint32_t* partials, uint32_t nb)
+{
+  __shared__ uint32_t warp_sums[32];
+  uint32_t carry = 0;
+  for (uint32_t base = 0; base < nb; base += 1024) {
+    const uint32_t j = base + threadIdx.x;
+    const uint32_t v = j < nb ? partials[j] : 0u;
+    uint32_t total;
+    const uint32_t ex = block_exclusive_scan(v, warp_sums, total);
+    if (j < nb) partials[j] = carry + ex;
+    carry += total;
+  }
+}
+
+// begin[i] = sum of in[0..i), begin[n] = the total; cursor (optional) starts as a copy of begin[0..n)
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t* __restrict__ in, uint32_t n, const uint32_t* __restrict__ partials,
+                                                                  uint32_t* __restrict__ begin, uint32_t* __restrict__ cursor)
+{
+  __shared__ uint32_t tile[kScanTile + kScanTile / 32];
+  __shared__ uint32_t warp_sums[kScanThreads / 32];
+  const uint32_t base = blockIdx.x * kScanTile;
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) {
+    const uint32_t t = i * kScanThreads + threadIdx.x, j = base + t;
+    tile[t + (t >> 5)] = j < n ? in[j] : 0u;
+  }
+  __syncthreads();
+  uint32_t v[kScanItems], sum = 0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) { const uint32_t t = threadIdx.x * kScanItems + i; v[i] = tile[t + (t >> 5)]; sum += v[i]; }
+  uint32_t total;
+  uint32_t run = partials[blockIdx.x] + block_exclusive_scan(sum, warp_sums, total);
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) { const uint32_t t = threadIdx.x * kScanItems + i; tile[t + (t >> 5)] = run; run += v[i]; }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) {
+    const uint32_t t = i * kScanThreads + threadIdx.x, j = base + t;
+    if (j < n) { const uint32_t x = tile[t + (t >> 5)]; begin[j] = x; if (cursor) cursor[j] = x; }
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) begin[n] = partials[blockIdx.x] + total;
+}
+
+static cudaError_t exclusive_scan(const uint32_t* in, uint32_t n, uint32_t* partials, uint32_t* begin, uint32_t* cursor, cudaStream_t stream)
+{
+  const uint32_t nb = (n + kScanTile - 1) / kScanTile;
+  scan_sums_kernel<<<nb, kScanThreads, 0, stream>>>(in, n, partials);
+  scan_top_kernel<<<1, 1024, 0, stream>>>(partials, nb);
+  scan_apply_kernel<<<nb, kScanThreads, 0, stream>>>(in, n, partials, begin, cursor);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------- J: join
+
+struct __align__(16) JoinWarpSmem {
+  uint4 qs[32];       // the queries being compared: {q, read, local lookup index | strand << 31, 0}
+  uint4 hq[kHitQ];    // queued hit entries: {read, strand << 31 | local lookup index << 5 | hd, colour id, 0}
+  uint32_t hq_n, pad[3];
+};
+
+__device__ __noinline__ void join_flush(JoinWarpSmem* w, const SortArgs s, uint32_t* counters)
+{
+  const uint32_t lane = threadIdx.x & 31;
+  __syncwarp();
+  const uint32_t n = *reinterpret_cast<volatile uint32_t*>(&w->hq_n);
+  if (n) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(s.sc, n);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if ((uint64_t)base + n > s.cap_hits && lane == 0) atomicOr(counters + 2, kErrHitOverflow); // s.sc[0] ends as the demand
+    for (uint32_t i = lane; i < n; i += 32) if (base + i < s.cap_hits) s.hits_tmp[base + i] = w->hq[i];
+  }
+  __syncwarp();
+  if (lane == 0) w->hq_n = 0;
+  __syncwarp();
+}
+
+// One block of up to 32 queries (in w->qs) against the E entries each lane holds.  thr[e] is the Hamming threshold, or
+// -1 for a register slot that holds no entry.
+template <int E>
+__device__ __forceinline__ void join_block(JoinWarpSmem* w, const SortArgs& s, uint32_t* counters, const uint32_t (&enc)[4], const uint32_t (&se)[4],
+                                           const int (&thr)[4], uint32_t cnt)
+{
+  for (uint32_t j = 0; j < cnt; ++j) {
+    const uint32_t q = w->qs[j].x;
+    int hd[E];
+    bool any = false;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const uint32_t z = enc[e] ^ q;
+      hd[e] = __popc((z | (z >> 16)) & 0xFFFFu);
+      any |= hd[e] <= thr[e];
+    }
+    if (__any_sync(0xFFFFFFFFu, any)) {
+      if (any) {
+        const uint4 t = w->qs[j];
+        const uint32_t meta = (t.z & 0x80000000u) | ((t.z & (kMaxLoc - 1u)) << 5);
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+          if (hd[e] <= thr[e]) {
+            const uint32_t at = atomicAdd(&w->hq_n, 1u);
+            w->hq[at] = make_uint4(t.y, meta | (uint32_t)hd[e], se[e], 0u);
+            atomicAdd(&s.hit_count[t.y], 1u);
+          }
+      }
+      __syncwarp();
+      if (*reinterpret_cast<volatile uint32_t*>(&w->hq_n) > (uint32_t)(kHitQ - kJoinChunk)) join_flush(w, s, counters);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kJoinWarps * 32) join_kernel(const DevIndex ix, const SortArgs s, uint32_t th, uint32_t* counters, unsigned long long* stats)
+{
+  __shared__ JoinWarpSmem jsm[kJoinWarps];
+  if (s.row_begin[s.nrows] > s.cap_lookups) return; // flagged by the lookup kernel
+  const uint32_t lane = threadIdx.x & 31;
+  JoinWarpSmem* w = &jsm[threadIdx.x >> 5];
+  if (lane == 0) w->hq_n = 0;
+  __syncwarp();
+  unsigned long long st_entries = 0;
+  for (;;) {
+    uint32_t r0 = 0;
+    if (lane == 0) r0 = atomicAdd(s.sc + 1, kRowClaim);
+    r0 = __shfl_sync(0xFFFFFFFFu, r0, 0);
+    if (r0 >= s.nrows) break;
+    const uint32_t row = r0 + lane; // every lane describes one row of the claim
+    uint32_t qb = 0, qe = 0, eb = 0, ee = 0;
+    if (row < s.nrows) {
+      qb = s.row_begin[row]; qe = s.row_begin[row + 1];
+      if (qe > qb) { eb = row ? __ldg(&ix.inc32[row - 1]) : 0u; ee = __ldg(&ix.inc32[row]); } // ref src/index.cpp:160-168, src/table.hpp:121-136
+    }
+    st_entries += (unsigned long long)(qe - qb) * (ee - eb);
+    uint32_t active = __ballot_sync(0xFFFFFFFFu, qe > qb && ee > eb);
+    while (active) {
+      const int src = __ffs(active) - 1;
+      active &= active - 1;
+      const uint32_t rqb = __shfl_sync(0xFFFFFFFFu, qb, src), nq = __shfl_sync(0xFFFFFFFFu, qe, src) - rqb;
+      const uint32_t reb = __shfl_sync(0xFFFFFFFFu, eb, src), ne = __shfl_sync(0xFFFFFFFFu, ee, src) - reb;
+      for (uint32_t c = 0; c < ne; c += kJoinChunk) {
+        uint32_t enc[4], se[4];
+        int thr[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t i = c + 32 * e + lane;
+          enc[e] = 0; se[e] = 0; thr[e] = -1;
+          if (i < ne) { const uint2 v = __ldg(&ix.cmer[(size_t)reb + i]); enc[e] = v.x; se[e] = v.y; thr[e] = (int)th; }
+        }
+        const uint32_t E = min(4u, (ne - c + 31u) >> 5);
+        for (uint32_t q0 = 0; q0 < nq; q0 += 32) {
+          const uint32_t cnt = min(32u, nq - q0);
+          __syncwarp();
+          if (lane < cnt) w->qs[lane] = s.tuples[rqb + q0 + lane];
+          __syncwarp();
+          switch (E) {
+            case 1: join_block<1>(w, s, counters, enc, se, thr, cnt); break;
+            case 2: join_block<2>(w, s, counters, enc, se, thr, cnt); break;
+            case 3: join_block<3>(w, s, counters, enc, se, thr, cnt); break;
+            default: join_block<4>(w, s, counters, enc, se, thr, cnt); break;
+          }
+        }
+      }
+    }
+  }
+  join_flush(w, s, counters);
+  for (int o = 16; o; o >>= 1) st_entries += __shfl_xor_sync(0xFFFFFFFFu, st_entries, o);
+  if (lane == 0 && st_entries) { atomicAdd(stats, 8ull * st_entries); atomicAdd(stats + 2, st_entries); }
+}
+
+// ---------------------------------------------------------------------------------------------------- S2: hits by read
+
+__global__ void __launch_bounds__(256) hit_scatter_kernel(const DevIndex ix, const SortArgs s, const uint32_t* counters)
+{
+  if (counters[2] & kErrRedo) return;
+  const uint32_t n = s.sc[0];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint4 h = s.hits_tmp[i];
+    const uint32_t pos = atomicAdd(&s.hit_cursor[h.x], 1u);
+    const uint32_t cs = __ldg(&ix.cbeg[h.z]), ce = __ldg(&ix.cbeg[h.z + 1]);
+    s.hits[pos] = make_uint4(cs, ce - cs, h.y, 0u);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------- R: resolve
+
+template <typename K>
+__device__ __forceinline__ void bitonic_sort(K* keys, uint32_t n) // n: power of two >= 32; ascending
+{
+  const uint32_t lane = threadIdx.x & 31;
+  for (uint32_t k = 2; k <= n; k <<= 1) {
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t t = lane; t < (n >> 1); t += 32) {
+        const uint32_t i = ((t & ~(j - 1u)) << 1) | (t & (j - 1u)), l = i | j;
+        const K x = keys[i], y = keys[l];
+        const bool up = (i & k) == 0;
+        if ((x > y) == up) { keys[i] = y; keys[l] = x; }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+struct ResolveOut { uint32_t total, rbegin; bool fits; };
+
+// One read's leaf hits, as sorted keys strand | leaf rank | lookup | hd, to its records (see the header).  seg_shift =
+// bits of lookup + hd; every lane returns the same ResolveOut.
+template <typename K>
+__device__ __forceinline__ ResolveOut emit_sorted(const DevIndex& ix, const MatchArgs& a, const K* keys, uint32_t T, uint32_t seg_shift, uint32_t rank_bits,
+                                                  uint32_t read, uint32_t g0, uint32_t g1, bool small_counts)
+{
+  const uint32_t lane = threadIdx.x & 31, lt_mask = (1u << lane) - 1u, stride = a.th + 1;
+  // pass A: (strand, leaf) segments that pass the hdist_filt gate
+  uint32_t total = 0;
+  for (uint32_t c = 0; c < T; c += 32) {
+    const uint32_t i = c + lane;
+    bool pass = false;
+    if (i < T) {
+      const K kk = keys[i];
+      const K sg = kk >> seg_shift;
+      if (i == 0 || (keys[i - 1] >> seg_shift) != sg) {
+        uint32_t hdmin = (uint32_t)kk & 31u;
+        for (uint32_t j = i + 1; j < T; ++j) { const K kj = keys[j]; if ((kj >> seg_shift) != sg) break; hdmin = min(hdmin, (uint32_t)kj & 31u); }
+        const uint32_t strand = (uint32_t)(sg >> rank_bits);
+        pass = a.keep_all || !(hdmin > (strand ? g1 : g0));
+      }
+    }
+    total += __popc(__ballot_sync(0xFFFFFFFFu, pass));
+  }
+  ResolveOut out;
+  out.total = total; out.rbegin = 0; out.fits = true;
+  if (!total) return out;
+  uint32_t rbegin = 0;
+  if (lane == 0) rbegin = atomicAdd(a.counters, total);
+  rbegin = __shfl_sync(0xFFFFFFFFu, rbegin, 0);
+  const bool fits = (uint64_t)rbegin + total <= a.rec_cap;
+  if (!fits && lane == 0) atomicOr(a.counters + 2, kErrRecOverflow);
+  out.rbegin = rbegin; out.fits = fits;
+  // pass B: histograms of the passing segments, one count per lookup at its smallest distance (a lookup's keys are
+  // adjacent and ascending in hd, so its first key carries the minimum)
+  uint32_t done = 0;
+  for (uint32_t c = 0; c < T; c += 32) {
+    const uint32_t i = c + lane;
+    bool pass = false;
+    uint32_t hv[kMaxTh + 1], strand = 0, rank = 0;
+#pragma unroll
+    for (int x = 0; x <= kMaxTh; ++x) hv[x] = 0;
+    if (i < T) {
+      const K kk = keys[i];
+      const K sg = kk >> seg_shift;
+      if (i == 0 || (keys[i - 1] >> seg_shift) != sg) {
+        uint32_t hdmin = 0xFFFFFFFFu;
+        if (small_counts) { // every count < 256 and th < 8: eight 8-bit counters in one word
+          unsigned long long packed = 0;
+          K prev_lk = ~(K)0;
+          for (uint32_t j = i; j < T; ++j) {
+            const K kj = keys[j];
+            if ((kj >> seg_shift) != sg) break;
+            const K lk = kj >> 5;
+            if (lk != prev_lk) { const uint32_t hd = (uint32_t)kj & 31u; packed += 1ull << (8u * hd); hdmin = min(hdmin, hd); prev_lk = lk; }
+          }
+#pragma unroll
+          for (int x = 0; x < 8; ++x) hv[x] = (uint32_t)(packed >> (8 * x)) & 0xFFu;
+        } else {
+          K prev_lk = ~(K)0;
+          for (uint32_t j = i; j < T; ++j) {
+            const K kj = keys[j];
+            if ((kj >> seg_shift) != sg) break;
+            const K lk = kj >> 5;
+            if (lk != prev_lk) {
+              const uint32_t hd = (uint32_t)kj & 31u;
+#pragma unroll
+              for (int x = 0; x <= kMaxTh; ++x) hv[x] += (hd == (uint32_t)x);
+              hdmin = min(hdmin, hd); prev_lk = lk;
+            }
+          }
+        }
+        strand = (uint32_t)(sg >> rank_bits);
+        rank = (uint32_t)sg & ((1u << rank_bits) - 1u);
+        pass = a.keep_all || !(hdmin > (strand ? g1 : g0));
+      }
+    }
+    const uint32_t pm = __ballot_sync(0xFFFFFFFFu, pass);
+    if (pass && fits) {
+      const uint32_t at = rbegin + done + __popc(pm & lt_mask);
+      a.rec_read[at] = read;
+      a.rec_slot[at] = strand << 31 | __ldg(&ix.leaf_se[rank]);
+#pragma unroll
+      for (int x = 0; x <= kMaxTh; ++x) if ((uint32_t)x < stride) a.rec_hist[(size_t)at * stride + x] = hv[x];
+    }
+    done += __popc(pm);
+  }
+  return out;
+}
+
+// Expands one read's hit entries into keys (written to `keys`, padded to a power of two), sorts them and emits the records.
+template <typename K>
+__device__ __forceinline__ ResolveOut resolve_read(const DevIndex& ix, const MatchArgs& a, const SortArgs& s, K* keys, uint32_t hb, uint32_t nh, uint32_t T,
+                                                   uint32_t rank_bits, uint32_t loc_bits, uint32_t read, uint32_t g0, uint32_t g1, bool small_counts)
+{
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t seg_shift = loc_bits + 5u, strand_shift = seg_shift + rank_bits;
+  uint32_t base = 0;
+  for (uint32_t c = 0; c < nh; c += 32) {
+    const uint32_t i = c + lane;
+    uint4 h = make_uint4(0u, 0u, 0u, 0u);
+    if (i < nh) h = s.hits[hb + i];
+    const uint32_t cnt = h.y;
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += t; }
+    const uint32_t at = base + incl - cnt;
+    const K fixed = ((K)(h.z >> 31) << strand_shift) | (K)(h.z & 0x7FFFFFFFu); // strand | lookup << 5 | hd
+    if (cnt <= 8u) {
+      for (uint32_t j = 0; j < cnt; ++j) keys[at + j] = fixed | ((K)__ldg(&ix.cleaf[h.x + j]) << seg_shift);
+    }
+    uint32_t big = __ballot_sync(0xFFFFFFFFu, cnt > 8u); // long leaf lists: all lanes together
+    while (big) {
+      const int src = __ffs(big) - 1;
+      big &= big - 1;
+      const uint32_t bx = __shfl_sync(0xFFFFFFFFu, h.x, src), bn = __shfl_sync(0xFFFFFFFFu, cnt, src), bat = __shfl_sync(0xFFFFFFFFu, at, src);
+      const uint32_t bz = __shfl_sync(0xFFFFFFFFu, h.z, src);
+      const K bfixed = ((K)(bz >> 31) << strand_shift) | (K)(bz & 0x7FFFFFFFu);
+      for (uint32_t j = lane; j < bn; j += 32) keys[bat + j] = bfixed | ((K)__ldg(&ix.cleaf[bx + j]) << seg_shift);
+    }
+    base += __shfl_sync(0xFFFFFFFFu, incl, 31);
+  }
+  uint32_t n = 32;
+  while (n < T) n <<= 1;
+  for (uint32_t i = T + lane; i < n; i += 32) keys[i] = ~(K)0; // never a real key: hd <= 16 < 31
+  __syncwarp();
+  bitonic_sort(keys, n);
+  return emit_sorted<K>(ix, a, keys, T, seg_shift, rank_bits, read, g0, g1, small_counts);
+}
+
+__global__ void __launch_bounds__(kResWarps * 32) resolve_kernel(const DevIndex ix, const MatchArgs a, const SortArgs s, uint32_t rank_bits)
+{
+  __shared__ __align__(16) uint32_t skeys[kResWarps][kResKeys];
+  if (a.counters[2] & kErrRedo) return;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t gwarp = blockIdx.x * kResWarps + warp;
+  uint64_t* gkeys = s.keys_g + (size_t)gwarp * s.cap_keys_g;
+  unsigned long long st_records = 0;
+  uint32_t claim = 0, claim_end = 0;
+  for (;;) {
+    if (claim == claim_end) {
+      if (lane == 0) claim = atomicAdd(s.sc + 4, kResClaim);
+      claim = __shfl_sync(0xFFFFFFFFu, claim, 0);
+      claim_end = min(claim + kResClaim, a.n_reads);
+      if (claim >= a.n_reads) break;
+    }
+    const uint32_t read = claim++;
+    const uint32_t hb = s.hit_begin[read], nh = s.hit_begin[read + 1] - hb;
+    uint32_t filt0 = 0xFFFFFFFFu, filt1 = 0xFFFFFFFFu;
+    ResolveOut out;
+    out.total = 0; out.rbegin = 0; out.fits = true;
+    if (nh) {
+      // leaf hits of the read and the per-strand minimum distance over all hit entries (IMers::hdist_filt, ref src/query.cpp:366)
+      unsigned long long T64 = 0;
+      for (uint32_t i = lane; i < nh; i += 32) {
+        const uint4 h = s.hits[hb + i];
+        T64 += h.y;
+        const uint32_t hd = h.z & 31u;
+        if (h.z >> 31) filt1 = min(filt1, hd); else filt0 = min(filt0, hd);
+      }
+      for (int o = 16; o; o >>= 1) {
+        T64 += __shfl_xor_sync(0xFFFFFFFFu, T64, o);
+        filt0 = min(filt0, __shfl_xor_sync(0xFFFFFFFFu, filt0, o)); filt1 = min(filt1, __shfl_xor_sync(0xFFFFFFFFu, filt1, o));
+      }
+      const uint32_t g0 = 2u * filt0 + 1u, g1 = 2u * filt1 + 1u; // uint32 wrap kept, as in the reference (src/query.cpp:101-102)
+      const uint32_t nlk = a.wn[2 * read] + a.wn[2 * read + 1];
+      const uint32_t loc_bits = nlk <= 1u ? 0u : 32u - __clz(nlk - 1u);
+      const bool narrow = 1u + rank_bits + loc_bits + 5u <= 32u;
+      const bool small_counts = nlk < 256u && a.th < 8u;
+      if (T64 == 0) { /* only colours without leaves: no records */ }
+      else if (narrow && T64 <= (unsigned long long)kResKeys)
+        out = resolve_read<uint32_t>(ix, a, s, skeys[warp], hb, nh, (uint32_t)T64, rank_bits, loc_bits, read, g0, g1, small_counts);
+      else if (!narrow && T64 <= (unsigned long long)(kResKeys / 2))
+        out = resolve_read<uint64_t>(ix, a, s, reinterpret_cast<uint64_t*>(skeys[warp]), hb, nh, (uint32_t)T64, rank_bits, loc_bits, read, g0, g1, small_counts);
+      else if (T64 <= (unsigned long long)s.cap_keys_g)
+        out = resolve_read<uint64_t>(ix, a, s, gkeys, hb, nh, (uint32_t)T64, rank_bits, loc_bits, read, g0, g1, small_counts);
+      else if (lane == 0) atomicOr(a.counters + 2, kErrSortFallback); // too many leaf hits for the scratch: the fused kernel redoes the batch
+      __syncwarp();
+    }
+    if (lane == 0) {
+      a.hdfilt[2 * read] = filt0; a.hdfilt[2 * read + 1] = filt1;
+      a.rec_begin[read] = out.fits ? out.rbegin : 0; a.rec_count[read] = out.fits ? out.total : 0;
+      st_records += out.total;
+    }
+  }
+  if (lane == 0 && st_records) atomicAdd(a.stats, 64ull * st_records);
+}
+
+// ---------------------------------------------------------------------------------------------------- host launcher
+
+static size_t lookup_smem(uint32_t k) { return lut_chunks(k) * 256 * sizeof(uint4) + kLkWarps * sizeof(WarpSmem); }
+
+int sorted_resolve_warps(int sms) { return sms * 6 * kResWarps; } // grid of the resolve kernel (sizes SortArgs::keys_g)
+
+template <bool SCATTER>
+static cudaError_t launch_lookup(const DevIndex& ix, const MatchArgs& a, const SortArgs& s, int sms, bool tap, cudaStream_t stream)
+{
+  const size_t sm = lookup_smem(ix.k);
+  cudaError_t e;
+  if (tap && !SCATTER) {
+    e = cudaFuncSetAttribute(lookup_kernel<SCATTER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return e;
+    lookup_kernel<SCATTER, true><<<sms * 2, kLkWarps * 32, sm, stream>>>(ix, a, s);
+  } else {
+    e = cudaFuncSetAttribute(lookup_kernel<SCATTER, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return e;
+    lookup_kernel<SCATTER, false><<<sms * 2, kLkWarps * 32, sm, stream>>>(ix, a, s);
+  }
+  return cudaGetLastError();
+}
+
+// Enqueues L1 .. R for one batch.  The caller has zeroed a.counters / a.stats; this zeroes the pipeline's own counters.
+cudaError_t launch_match_sorted(const DevIndex& ix, const MatchArgs& a, const SortArgs& s, int sms, bool tap, cudaStream_t stream, uint32_t* launches)
+{
+  cudaError_t e;
+  if (launches) *launches = 0;
+  if (!a.n_reads) return cudaSuccess;
+  if ((e = cudaMemsetAsync(s.row_count, 0, 4ull * s.nrows, stream)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(s.hit_count, 0, 4ull * a.n_reads, stream)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(s.sc, 0, 32, stream)) != cudaSuccess) return e;
+  if ((e = launch_lookup<false>(ix, a, s, sms, tap, stream)) != cudaSuccess) return e;
+  if ((e = exclusive_scan(s.row_count, s.nrows, s.partials, s.row_begin, s.row_cursor, stream)) != cudaSuccess) return e;
+  if ((e = launch_lookup<true>(ix, a, s, sms, false, stream)) != cudaSuccess) return e;
+  join_kernel<<<sms * 8, kJoinWarps * 32, 0, stream>>>(ix, s, a.th, a.counters, a.stats);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if ((e = exclusive_scan(s.hit_count, a.n_reads, s.partials, s.hit_begin, s.hit_cursor, stream)) != cudaSuccess) return e;
+  hit_scatter_kernel<<<sms * 8, 256, 0, stream>>>(ix, s, a.counters);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  uint32_t rank_bits = 0;
+  while ((1ull << rank_bits) < ix.nleaves) ++rank_bits;
+  rank_bits += s.extra_rank_bits;
+  resolve_kernel<<<sorted_resolve_warps(sms) / kResWarps, kResWarps * 32, 0, stream>>>(ix, a, s, rank_bits);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if (launches) *launches = 11;
+  return cudaSuccess;
+}
+
+} // namespace krepp

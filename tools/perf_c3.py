@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--reads", type=int, default=2_000_000)
     ap.add_argument("--batch", type=int, default=250_000)
     ap.add_argument("--groups", default="staged")
+    ap.add_argument("--pipelines", default="sorted,fused", help="KREPP_PIPELINE values to time (sorted.cu / match.cu)")
     ap.add_argument("--out", default="/tmp/c3")
     ap.add_argument("--cpu-reads", type=int, default=100_000)
     ap.add_argument("--check", type=int, default=300)
@@ -58,8 +59,8 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     nb = (len(reads) + a.batch - 1) // a.batch
     d_reads = [torch.from_numpy(reads[i * a.batch:(i + 1) * a.batch].reshape(-1)).cuda() for i in range(nb)]
-    for g in a.groups.split(","):
-        os.environ["KREPP_SCAN"] = g
+    for g in [(x, y) for y in a.pipelines.split(",") for x in a.groups.split(",")]:
+        os.environ["KREPP_SCAN"], os.environ["KREPP_PIPELINE"] = g
         ix = krepp_b200.Index(idx, 0)
         b = krepp_b200.IBatch(ix, reads[:a.batch], place=a.place, no_filter=not a.place)
         d_o = torch.from_numpy(b.offsets.astype(np.int64)).cuda()
@@ -84,6 +85,7 @@ def main():
               f"records/read {nrec / len(reads):5.1f}; entries/lookup {ab['entries'] / max(ab['lookups'], 1):5.1f}", flush=True)
         b.close(); ix.close()
     os.environ.pop("KREPP_SCAN", None)
+    os.environ.pop("KREPP_PIPELINE", None)
 
     fq = os.path.join(a.out, "reads.fq")
     if not a.skip_cli:
