@@ -232,13 +232,16 @@ def main() -> None:
         torch.cuda.synchronize()
         gpu = mm = 0.0
         launches = nrec = alg = lk = en = 0
+        stages: dict = {}
         for first, cnt in chunks:
             slot.submit_device(d_bases.data_ptr() + first * READ_LEN, d_offs.data_ptr(), cnt, cnt * READ_LEN)
             r = slot.wait()
             gpu += r["gpu_ms"]; mm += r["match_ms"]; launches += r["gpu_launches"]; nrec += len(r["records"])
             ab = slot.algorithmic_bytes()
             alg += ab["bytes"]; lk += ab["lookups"]; en += ab["entries"]
-        return dict(gpu_ms=gpu, match_ms=mm, launches=launches, records=nrec, alg=alg, lookups=lk, entries=en)
+            for name, ms in slot.stage_times():
+                stages[name] = stages.get(name, 0.0) + ms
+        return dict(gpu_ms=gpu, match_ms=mm, launches=launches, records=nrec, alg=alg, lookups=lk, entries=en, stages=stages)
 
     for _ in range(args.warmup):
         step_device()
@@ -246,12 +249,15 @@ def main() -> None:
     sampler = ClockSampler(local)
     sampler.start()
     gpu_ms, match_ms, launches = [], [], 0
+    stage_ms: dict = {}
     t0 = time.perf_counter()
     for _ in range(args.steps):
         r = step_device()
         gpu_ms.append(r["gpu_ms"])
         match_ms.append(r["match_ms"])
         launches += r["launches"]
+        for name, ms in r["stages"].items():
+            stage_ms[name] = stage_ms.get(name, 0.0) + ms / args.steps
     barrier()
     wall_device = time.perf_counter() - t0
     clocks = sampler.stop()
@@ -318,8 +324,15 @@ def main() -> None:
     mm = sum(match_ms) / len(match_ms)            # per step
     launches_per_step = len(chunks)
     achieved = last["alg"] / (mm / 1e3) / 1e9
+    # The match step (ref src/query.cpp:40-94,352-390) is ONE kernel in the fused pipeline and a short chain of kernels in
+    # the bucket-sorted one; the roofline is quoted over the whole chain (every launch between the library's two match
+    # events), which is the conservative reading: the algorithmic bytes are those of the step, the time is all of it.
+    sorted_pipeline = "join_kernel" in stage_ms
+    match_name = ("match step, bucket-sorted pipeline: lookup_kernel x2 + scans + join_kernel + hit_scatter_kernel + resolve_kernel"
+                  if sorted_pipeline else "match_kernel")
+    dom = max(stage_ms, key=stage_ms.get) if stage_ms else "match_kernel"
     traffic = None
-    if args.workload in NCU_TRAFFIC:
+    if args.workload in NCU_TRAFFIC and not sorted_pipeline:
         per, tb, _src = NCU_TRAFFIC[args.workload]
         traffic = tb * (batch / per)
     out = {
@@ -333,7 +346,11 @@ def main() -> None:
         "e2e": e2e_out,
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "match_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "roofline": {"bound": "hbm", "kernel": match_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "stages_ms_per_step": {k: round(v, 3) for k, v in stage_ms.items()},
+                     "dominant_kernel": {"name": dom, "ms_per_launch": stage_ms.get(dom, 0.0) / launches_per_step,
+                                         "share_of_step": stage_ms.get(dom, 0.0) / (t_dev * 1e3 / args.steps)},
+                     "whole_step_frac": (last["alg"] / (t_dev / args.steps) / 1e9) / peak,
                      "traffic": traffic, "traffic_source": NCU_TRAFFIC.get(args.workload, (0, 0, None))[2],
                      "algorithmic_bytes_per_launch": last["alg"] / launches_per_step,
                      "lookups_per_launch": last["lookups"] / launches_per_step, "entries_scanned_per_launch": last["entries"] / launches_per_step,

@@ -172,6 +172,11 @@ int krepp_batch_read_tap(krepp_batch_t* b, int stage, uint32_t* out, uint64_t ca
  * len + sum over eligible lookups (16 + 8*|bucket|) + 64 * records, computed on the device while matching. */
 int krepp_batch_algorithmic_bytes(krepp_batch_t* b, uint64_t* bytes, uint64_t* lookups, uint64_t* entries_scanned);
 
+/* Per-stage device times of the last waited batch (measurement only; no reference equivalent): CUDA events recorded on
+ * the slot's stream after every kernel (or short kernel group) of the batch.  ms[i] / names[i] (static strings) for
+ * i < min(*n, cap); *n = number of stages.  The stages of the match step (src/query.cpp:40-94,352-390) come first. */
+int krepp_batch_stage_times(krepp_batch_t* b, uint32_t cap, float* ms, const char** names, uint32_t* n);
+
 /* -------------------------------------------------------------------------------------------------- host I/O layer
  * The steps immediately either side of the GPU path.  Pure host code: usable
  * without a device (the index handle may have been opened with KREPP_DEVICE_NONE). */

@@ -98,6 +98,7 @@ def load_library():
     L.krepp_batch_enable_tap.argtypes = [C.c_void_p, C.c_int, C.c_uint64]
     L.krepp_batch_read_tap.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.krepp_batch_algorithmic_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.krepp_batch_stage_times.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_char_p), C.POINTER(C.c_uint32)]
     L.krepp_reader_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
     L.krepp_reader_close.argtypes = [C.c_void_p]
     L.krepp_reader_next.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p,
@@ -262,6 +263,12 @@ class IBatch:
         b, l, e = C.c_uint64(), C.c_uint64(), C.c_uint64()
         _check(load_library().krepp_batch_algorithmic_bytes(self._h, C.byref(b), C.byref(l), C.byref(e)))
         return dict(bytes=b.value, lookups=l.value, entries=e.value)
+
+    def stage_times(self) -> list:
+        """[(stage name, ms)] of the last waited batch, in launch order (CUDA events on the slot's stream)."""
+        ms, names, n = (C.c_float * 16)(), (C.c_char_p * 16)(), C.c_uint32()
+        _check(load_library().krepp_batch_stage_times(self._h, 16, ms, names, C.byref(n)))
+        return [(names[i].decode(), float(ms[i])) for i in range(min(n.value, 16))]
 
     # -- reference-shaped entry points ------------------------------------------------------------------------------
     def estimate_distances(self) -> str:

@@ -164,6 +164,7 @@ struct krepp_batch {
   bool sorted = false, fused_once = false;
   SortArgs so{};
   uint32_t* h_sc = nullptr;   // [0..7] copy of so.sc, [8] lookups of the batch
+  StageClock clk;             // per-stage events of the last enqueue
   // tap
   uint4* d_tap = nullptr; unsigned long long* d_tap_count = nullptr; unsigned long long tap_cap = 0;
 };
@@ -404,6 +405,7 @@ int krepp_batch_create(krepp_index_t* ix, const krepp_params_t* p, uint32_t max_
   }
   CU(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
   CU(cudaEventCreate(&b->ev0)); CU(cudaEventCreate(&b->ev1)); CU(cudaEventCreate(&b->evm0)); CU(cudaEventCreate(&b->evm1));
+  for (auto& ev : b->clk.ev) CU(cudaEventCreate(&ev));
   CU(cudaMallocHost(&b->h_bases, max_bases + 64)); CU(cudaMallocHost(&b->h_offsets, 8ull * (max_reads + 1)));
   CU(cudaMalloc(&b->d_bases, max_bases + 64)); CU(cudaMalloc(&b->d_offsets, 8ull * (max_reads + 1)));
   CU(cudaMalloc(&b->d_onmers, 4ull * max_reads)); CU(cudaMalloc(&b->d_wn, 8ull * max_reads)); CU(cudaMalloc(&b->d_hdfilt, 8ull * max_reads));
@@ -464,6 +466,7 @@ void krepp_batch_destroy(krepp_batch_t* b)
   if (b->ev1) cudaEventDestroy(b->ev1);
   if (b->evm0) cudaEventDestroy(b->evm0);
   if (b->evm1) cudaEventDestroy(b->evm1);
+  for (auto ev : b->clk.ev) if (ev) cudaEventDestroy(ev);
   if (b->stream) cudaStreamDestroy(b->stream);
   delete b;
 }
@@ -484,12 +487,17 @@ static int enqueue(krepp_batch* b)
   m.acc = b->d_acc; m.bitmap = b->d_bitmap; m.marker = b->d_marker; m.stack = b->d_stack; m.stack_cap = b->stack_cap; m.tagctr = b->d_tagctr; m.stats = b->d_stats;
   m.tap = b->d_tap; m.tap_count = b->d_tap_count; m.tap_cap = b->tap_cap;
   CU(cudaEventRecord(b->evm0, s));
+  b->clk.n = 0;
+  b->clk.tick("start", s);
   uint32_t match_launches = 1;
   if (b->sorted && !b->fused_once) {
-    CU(launch_match_sorted(ix->dev, m, b->so, ix->sms, b->d_tap != nullptr, s, &match_launches));
+    CU(launch_match_sorted(ix->dev, m, b->so, ix->sms, b->d_tap != nullptr, s, &match_launches, &b->clk));
     CU(cudaMemcpyAsync(b->h_sc, b->so.sc, 32, cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(b->h_sc + 8, b->so.row_begin + b->so.nrows, 4, cudaMemcpyDeviceToHost, s));
-  } else CU(launch_match(ix->dev, m, ix->resident_warps, ix->staged, b->d_tap != nullptr, s));
+  } else {
+    CU(launch_match(ix->dev, m, ix->resident_warps, ix->staged, b->d_tap != nullptr, s));
+    b->clk.tick("match_kernel", s);
+  }
   CU(cudaEventRecord(b->evm1, s));
   SolveArgs sa{};
   sa.n_reads = b->n_reads; sa.th = b->p.hdist_th; sa.k = h.k; sa.h = h.h; sa.n_records = b->rec_cap; sa.counters = b->d_counters; sa.work = b->d_rec_work;
@@ -498,7 +506,7 @@ static int enqueue(krepp_batch* b)
   sa.rec_d = b->d_rec_d; sa.rec_v = b->d_rec_v; sa.rec_chisq = b->d_rec_chisq; sa.rec_flags = b->d_rec_flags; sa.rec_match = b->d_rec_match;
   sa.rec_hdmin = b->d_rec_hdmin; sa.closest = b->d_closest;
   sa.want_chisq = (!b->p.no_filter || b->p.summarize || b->p.place) ? 1 : 0;
-  CU(launch_solve(sa, b->tab, ix->sms, s));
+  CU(launch_solve(sa, b->tab, ix->sms, s, &b->clk));
   b->launches = 4 + match_launches + (sa.want_chisq ? 1 : 0);
   if (b->p.place) {
     PlaceArgs pa{};
@@ -509,10 +517,12 @@ static int enqueue(krepp_batch* b)
     pa.node_cand = b->d_node_cand; pa.placements = b->d_place; pa.place_cap = b->place_cap; pa.counters = b->d_counters;
     pa.place_begin = b->d_place_begin; pa.place_count = b->d_place_count;
     CU(launch_place(pa, b->tab, (int)(b->place_warps / kPlaceWarpsPerCta), s));
+    b->clk.tick("place_kernel", s);
     b->launches += 1;
   }
   finalize_kernel<<<ix->sms * 4, 128, 0, s>>>(sa, b->d_out_rec, b->d_out_read, b->d_wn, b->d_place_begin, b->d_place_count);
   CU(cudaGetLastError());
+  b->clk.tick("finalize_kernel", s);
   CU(cudaEventRecord(b->ev1, s)); // kernels only: [ev0, ev1] excludes the host<->device copies on both sides
   CU(cudaMemcpyAsync(b->h_counters, b->d_counters, 32, cudaMemcpyDeviceToHost, s));
   CU(cudaMemcpyAsync(b->h_stats, b->d_stats, 32, cudaMemcpyDeviceToHost, s));
@@ -647,6 +657,22 @@ int krepp_batch_read_tap(krepp_batch_t* b, int stage, uint32_t* out, uint64_t ca
   *n = cnt;
   const uint64_t take = std::min<uint64_t>(std::min<uint64_t>(cnt, b->tap_cap), cap_items);
   if (out && take) CU(cudaMemcpy(out, b->d_tap, sizeof(uint4) * take, cudaMemcpyDeviceToHost));
+  return KREPP_OK;
+}
+
+int krepp_batch_stage_times(krepp_batch_t* b, uint32_t cap, float* ms, const char** names, uint32_t* n)
+{
+  if (!b || !n) return fail(KREPP_ERR_ARG, "krepp_batch_stage_times: null argument");
+  if (cudaSetDevice(b->ix->device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice failed");
+  CU(cudaStreamSynchronize(b->stream));
+  const uint32_t have = b->clk.n > 1 ? (uint32_t)b->clk.n - 1 : 0;
+  *n = have;
+  for (uint32_t i = 0; i < have && i < cap; ++i) {
+    float t = 0;
+    CU(cudaEventElapsedTime(&t, b->clk.ev[i], b->clk.ev[i + 1]));
+    if (ms) ms[i] = t;
+    if (names) names[i] = b->clk.name[i + 1];
+  }
   return KREPP_OK;
 }
 

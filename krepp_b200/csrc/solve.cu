@@ -366,13 +366,16 @@ cudaError_t launch_place(const PlaceArgs& a, const LlhTables& tab, int grid, cud
   return cudaGetLastError();
 }
 
-cudaError_t launch_solve(const SolveArgs& a, const LlhTables& tab, int sms, cudaStream_t stream)
+cudaError_t launch_solve(const SolveArgs& a, const LlhTables& tab, int sms, cudaStream_t stream, StageClock* clk)
 {
   const int grid = sms * 8;
   gate_kernel<<<sms * 4, 256, 0, stream>>>(a);
+  if (clk) clk->tick("gate_kernel", stream);
   solve_kernel<<<grid, 128, 0, stream>>>(a, tab);
+  if (clk) clk->tick("solve_kernel", stream);
   merge_kernel<<<grid, 128, 0, stream>>>(a);
   if (a.want_chisq) chisq_kernel<<<grid, 128, 0, stream>>>(a, tab);
+  if (clk) clk->tick(a.want_chisq ? "merge_kernel+chisq_kernel" : "merge_kernel", stream);
   return cudaGetLastError();
 }
 

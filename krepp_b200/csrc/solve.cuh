@@ -10,12 +10,21 @@ struct LlhTables {
   double hnk[kMaxTh + 1]; // C(k, x) - C(k-h, x) for 1 <= x <= th, and 0 for x = 0
 };
 
+// Per-stage CUDA events on the slot's stream (measurement only: bench.py reads them through krepp_batch_stage_times).
+struct StageClock {
+  static constexpr int kMax = 16;
+  cudaEvent_t ev[kMax] = {};
+  const char* name[kMax] = {};
+  int n = 0;
+  void tick(const char* nm, cudaStream_t s) { if (n < kMax && ev[n]) { cudaEventRecord(ev[n], s); name[n++] = nm; } }
+};
+
 int match_resident_warps(int device, uint32_t k, bool staged);
 cudaError_t launch_match(const DevIndex& ix, const MatchArgs& a, int resident_warps, bool staged, bool tap, cudaStream_t stream);
 // sorted.cu: the bucket-sorted form of the match stage (same outputs as launch_match)
 int sorted_resolve_warps(int sms);
-cudaError_t launch_match_sorted(const DevIndex& ix, const MatchArgs& a, const SortArgs& s, int sms, bool tap, cudaStream_t stream, uint32_t* launches);
-cudaError_t launch_solve(const SolveArgs& a, const LlhTables& tab, int sms, cudaStream_t stream);
+cudaError_t launch_match_sorted(const DevIndex& ix, const MatchArgs& a, const SortArgs& s, int sms, bool tap, cudaStream_t stream, uint32_t* launches, StageClock* clk = nullptr);
+cudaError_t launch_solve(const SolveArgs& a, const LlhTables& tab, int sms, cudaStream_t stream, StageClock* clk = nullptr);
 constexpr int kPlaceWarpsPerCta = 4;
 cudaError_t launch_place(const PlaceArgs& a, const LlhTables& tab, int grid, cudaStream_t stream);
 

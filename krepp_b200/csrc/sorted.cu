@@ -538,7 +538,7 @@ static cudaError_t launch_lookup(const DevIndex& ix, const MatchArgs& a, const S
 }
 
 // Enqueues L1 .. R for one batch.  The caller has zeroed a.counters / a.stats; this zeroes the pipeline's own counters.
-cudaError_t launch_match_sorted(const DevIndex& ix, const MatchArgs& a, const SortArgs& s, int sms, bool tap, cudaStream_t stream, uint32_t* launches)
+cudaError_t launch_match_sorted(const DevIndex& ix, const MatchArgs& a, const SortArgs& s, int sms, bool tap, cudaStream_t stream, uint32_t* launches, StageClock* clk)
 {
   cudaError_t e;
   if (launches) *launches = 0;
@@ -546,19 +546,26 @@ cudaError_t launch_match_sorted(const DevIndex& ix, const MatchArgs& a, const So
   if ((e = cudaMemsetAsync(s.row_count, 0, 4ull * s.nrows, stream)) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(s.hit_count, 0, 4ull * a.n_reads, stream)) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(s.sc, 0, 32, stream)) != cudaSuccess) return e;
+  if (clk) clk->tick("memsets", stream);
   if ((e = launch_lookup<false>(ix, a, s, sms, tap, stream)) != cudaSuccess) return e;
+  if (clk) clk->tick("lookup_kernel<count>", stream);
   if ((e = exclusive_scan(s.row_count, s.nrows, s.partials, s.row_begin, s.row_cursor, stream)) != cudaSuccess) return e;
+  if (clk) clk->tick("scan(rows)", stream);
   if ((e = launch_lookup<true>(ix, a, s, sms, false, stream)) != cudaSuccess) return e;
+  if (clk) clk->tick("lookup_kernel<scatter>", stream);
   join_kernel<<<sms * 8, kJoinWarps * 32, 0, stream>>>(ix, s, a.th, a.counters, a.stats);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if (clk) clk->tick("join_kernel", stream);
   if ((e = exclusive_scan(s.hit_count, a.n_reads, s.partials, s.hit_begin, s.hit_cursor, stream)) != cudaSuccess) return e;
   hit_scatter_kernel<<<sms * 8, 256, 0, stream>>>(ix, s, a.counters);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if (clk) clk->tick("scan(hits)+hit_scatter_kernel", stream);
   uint32_t rank_bits = 0;
   while ((1ull << rank_bits) < ix.nleaves) ++rank_bits;
   rank_bits += s.extra_rank_bits;
   resolve_kernel<<<sorted_resolve_warps(sms) / kResWarps, kResWarps * 32, 0, stream>>>(ix, a, s, rank_bits);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if (clk) clk->tick("resolve_kernel", stream);
   if (launches) *launches = 11;
   return cudaSuccess;
 }
