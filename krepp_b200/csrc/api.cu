@@ -394,15 +394,7 @@ int krepp_batch_create(krepp_index_t* ix, const krepp_params_t* p, uint32_t max_
   *out = b; // destroyed by the caller on failure
   b->ix = ix; b->p = *p; b->max_reads = max_reads; b->max_bases = max_bases;
   const HostIndex& h = ix->host;
-  { // HDistHistLLH tables (ref src/hdhistllh.hpp:51-69), exact integer arithmetic then converted
-    uint64_t ck[33] = {0}, vc = 1;
-    ck[0] = 1;
-    for (uint32_t i = 0; i < h.k; ++i) ck[i + 1] = (ck[i] * (h.k - i)) / (i + 1);
-    for (uint32_t i = 0; i <= h.k; ++i) b->tab.ck[i] = (double)ck[i];
-    b->tab.hnk[0] = 0;
-    const uint32_t nh = h.k - h.h;
-    for (uint32_t i = 1; i <= p->hdist_th; ++i) { vc = (vc * (nh - i + 1)) / i; b->tab.hnk[i] = (double)(ck[i] - vc); }
-  }
+  llh_tables(b->tab, h.k, h.h, p->hdist_th); // HDistHistLLH tables (ref src/hdhistllh.hpp:51-69), exact integer arithmetic then converted
   CU(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
   CU(cudaEventCreate(&b->ev0)); CU(cudaEventCreate(&b->ev1)); CU(cudaEventCreate(&b->evm0)); CU(cudaEventCreate(&b->evm1));
   for (auto& ev : b->clk.ev) CU(cudaEventCreate(&ev));

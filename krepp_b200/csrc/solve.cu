@@ -14,85 +14,37 @@
 #include "../../include/krepp_b200.h"
 #include "device.cuh"
 #include "solve.cuh"
+#include "llh_math.cuh"
 
 #include <cfloat>
 
 namespace krepp {
 
-struct Objective {
+// Objective with every histogram bin the library supports (placement and chisq: weighted / arbitrary th).
+using ObjectiveAny = Objective<kMaxTh + 1>;
+
+template <int N>
+struct PlainEval { // brent_minimum functor: the full objective at every abscissa
+  const Objective<N>* o;
   const LlhTables* t;
-  const double* mc; // hist as doubles
-  double uc, rho;
-  uint32_t k, th;
-  __device__ double operator()(double d) const
-  {
-    double sum = 0.0, lv_m = 0.0;
-    double powdc = pow((1.0 - d), (double)k);
-    double logdn = log(1.0 - d);
-    double logdp = log(d) - logdn;
-    logdn *= (double)k;
-    const double dratio = d / (1.0 - d);
-    for (uint32_t x = 0; x <= k; ++x) {
-      if (x <= th) {
-        sum -= (logdn + (double)x * logdp) * mc[x];
-        lv_m += t->hnk[x] * powdc;
-      } else {
-        lv_m += powdc * t->ck[x];
-      }
-      powdc *= dratio;
-    }
-    return sum - log(rho * lv_m + 1.0 - rho) * uc;
-  }
+  __device__ double operator()(double u, int) const { return o->eval(*t, u); }
 };
 
-__device__ void brent_minimum(const Objective& f, double& xo, double& fo)
-{
-  double min = 1e-10, max = 0.5;
-  const double tolerance = 3.0517578125e-05; // ldexp(1.0, 1 - 16)
-  const double golden = (double)0.3819660f;
-  double x, w, v, u, delta, delta2, fu, fv, fw, fx, mid, fract1, fract2;
-  x = w = v = max;
-  fw = fv = fx = f(x);
-  delta2 = delta = 0;
-  for (;;) {
-    mid = (min + max) / 2;
-    fract1 = tolerance * fabs(x) + tolerance / 4;
-    fract2 = 2 * fract1;
-    if (fabs(x - mid) <= (fract2 - (max - min) / 2)) break;
-    if (fabs(delta2) > fract1) {
-      double r = (x - w) * (fx - fv);
-      double q = (x - v) * (fx - fw);
-      double p = (x - v) * q - (x - w) * r;
-      q = 2 * (q - r);
-      if (q > 0) p = -p;
-      q = fabs(q);
-      const double td = delta2;
-      delta2 = delta;
-      if ((fabs(p) >= fabs(q * td / 2)) || (p <= q * (min - x)) || (p >= q * (max - x))) {
-        delta2 = (x >= mid) ? min - x : max - x;
-        delta = golden * delta2;
-      } else {
-        delta = p / q;
-        u = x + delta;
-        if (((u - min) < fract2) || ((max - u) < fract2)) delta = (mid - x) < 0 ? -fabs(fract1) : fabs(fract1);
-      }
-    } else {
-      delta2 = (x >= mid) ? min - x : max - x;
-      delta = golden * delta2;
+template <int N>
+struct MemoEval { // the same, with the d-only terms of the first three abscissae taken from the CTA's table (looked up by value)
+  const Objective<N>* o;
+  const LlhTables* t;
+  const double* su;   // [4] brent_first_points
+  const DTerms* st;   // [4] d_terms at those points
+  __device__ double operator()(double u, int it) const
+  {
+    if (it < 3) {
+      const int slot = it < 2 ? it : (u == su[2] ? 2 : 3);
+      if (u == su[slot]) return o->finish(st[slot]);
     }
-    u = (fabs(delta) >= fract1) ? (x + delta) : (delta > 0 ? (x + fabs(fract1)) : (x - fabs(fract1)));
-    fu = f(u);
-    if (fu <= fx) {
-      if (u >= x) min = x; else max = x;
-      v = w; w = x; x = u; fv = fw; fw = fx; fx = fu;
-    } else {
-      if (u < x) min = u; else max = u;
-      if ((fu <= fw) || (w == x)) { v = w; w = u; fv = fw; fw = fu; }
-      else if ((fu <= fv) || (v == x) || (v == w)) { v = u; fv = fu; }
-    }
+    return o->eval(*t, u);
   }
-  xo = x; fo = fx;
-}
+};
 
 // One thread per record: match_count / hdist_min from the histogram and the hdist_filt gate of summarize_matches (ref
 // src/query.cpp:101-106,116-119).  Records that pass are appended to a work list, so that the Brent kernel below runs
@@ -126,20 +78,32 @@ __global__ void __launch_bounds__(256) gate_kernel(const SolveArgs a)
   }
 }
 
-// One thread per work item: Brent on the record's histogram.
+// One thread per work item: Brent on the record's histogram.  N = histogram bins kept in registers (th + 1 <= N).
+template <int N>
 __global__ void __launch_bounds__(128) solve_kernel(const SolveArgs a, const LlhTables tab)
 {
+  __shared__ double su[4];
+  __shared__ DTerms st[4];
   if (a.counters[2] & kErrRedo) return;
+  if (threadIdx.x < 4) {
+    double u[4];
+    brent_first_points(u);
+    const double ut = threadIdx.x == 0 ? u[0] : threadIdx.x == 1 ? u[1] : threadIdx.x == 2 ? u[2] : u[3];
+    su[threadIdx.x] = ut;
+    st[threadIdx.x] = d_terms(tab, ut, a.k);
+  }
+  __syncthreads();
   const uint32_t n = a.counters[4];
   const uint32_t stride = a.th + 1;
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
     const uint32_t i = a.work[j];
     const uint32_t read = a.rec_read[i], se = a.rec_slot[i] & 0x7FFFFFFFu;
-    double mc[kMaxTh + 1];
-    for (uint32_t x = 0; x < stride; ++x) mc[x] = (double)a.rec_hist[(size_t)i * stride + x];
+    Objective<N> f;
+#pragma unroll
+    for (int x = 0; x < N; ++x) f.mc[x] = (uint32_t)x < stride ? (double)a.rec_hist[(size_t)i * stride + x] : 0.0;
+    f.uc = (double)a.onmers[read] - (double)a.rec_match[i]; f.rho = a.rho[se]; f.k = a.k; f.th = a.th;
     double d, v;
-    Objective f{&tab, mc, (double)a.onmers[read] - (double)a.rec_match[i], a.rho[se], a.k, a.th};
-    brent_minimum(f, d, v);
+    brent_minimum(MemoEval<N>{&f, &tab, su, st}, d, v);
     a.rec_d[i] = d; a.rec_v[i] = v; a.rec_flags[i] = 1u; // KREPP_REC_SOLVED
   }
 }
@@ -198,10 +162,10 @@ __global__ void __launch_bounds__(128) chisq_kernel(const SolveArgs a, const Llh
     const uint32_t read = a.rec_read[i];
     const int32_t cl = a.closest[read];
     if (cl < 0) continue;
-    double mc[kMaxTh + 1];
-    for (uint32_t x = 0; x < stride; ++x) mc[x] = (double)a.rec_hist[(size_t)cl * stride + x];
-    Objective f{&tab, mc, (double)a.onmers[read] - (double)a.rec_match[cl], a.rho[a.rec_slot[cl] & 0x7FFFFFFFu], a.k, a.th};
-    a.rec_chisq[i] = 2 * (f(a.rec_d[i]) - a.rec_v[cl]);
+    ObjectiveAny f;
+    for (uint32_t x = 0; x <= (uint32_t)kMaxTh; ++x) f.mc[x] = x < stride ? (double)a.rec_hist[(size_t)cl * stride + x] : 0.0;
+    f.uc = (double)a.onmers[read] - (double)a.rec_match[cl]; f.rho = a.rho[a.rec_slot[cl] & 0x7FFFFFFFu]; f.k = a.k; f.th = a.th;
+    a.rec_chisq[i] = 2 * (f.eval(tab, a.rec_d[i]) - a.rec_v[cl]);
   }
 }
 
@@ -245,9 +209,9 @@ __global__ void __launch_bounds__(128) place_kernel(const PlaceArgs a, const Llh
       double leq_cl = 0; // Minfo::get_leq_tau of the closest (ref src/query.hpp:189-196)
       for (uint32_t x = 0; x <= a.tau && x < stride; ++x) leq_cl += (double)s.rec_hist[(size_t)cl * stride + x];
       const uint32_t cl_se = s.rec_slot[cl] & 0x7FFFFFFFu;
-      double mc_cl[kMaxTh + 1];
-      for (uint32_t x = 0; x < stride; ++x) mc_cl[x] = (double)s.rec_hist[(size_t)cl * stride + x];
-      const Objective f_cl{&tab, mc_cl, (double)s.onmers[r] - (double)s.rec_match[cl], s.rho[cl_se], s.k, s.th};
+      ObjectiveAny f_cl;
+      for (uint32_t x = 0; x <= (uint32_t)kMaxTh; ++x) f_cl.mc[x] = x < stride ? (double)s.rec_hist[(size_t)cl * stride + x] : 0.0;
+      f_cl.uc = (double)s.onmers[r] - (double)s.rec_match[cl]; f_cl.rho = s.rho[cl_se]; f_cl.k = s.k; f_cl.th = s.th;
       const double v_cl = s.rec_v[cl];
       if (a.no_filter || leq_cl > 1.0) {
         if (nsel == 1) {
@@ -296,8 +260,9 @@ __global__ void __launch_bounds__(128) place_kernel(const PlaceArgs a, const Llh
               d = s.rec_d[rec]; v = s.rec_v[rec];
               for (uint32_t x = 0; x <= a.tau && x < stride; ++x) leq += (double)s.rec_hist[(size_t)rec * stride + x];
             } else {
-              double mc[kMaxTh + 1];
-              for (uint32_t x = 0; x < stride; ++x) mc[x] = 0;
+              ObjectiveAny f;
+              double (&mc)[kMaxTh + 1] = f.mc;
+              for (uint32_t x = 0; x <= (uint32_t)kMaxTh; ++x) mc[x] = 0;
               double nmers = 0, mismatch = 0, match = 0, rho = 0;
               const uint32_t lo = g - a.subtree[g]; // leaves below g have lo < se <= g
               uint32_t i = b, jx = b + nf;
@@ -320,13 +285,13 @@ __global__ void __launch_bounds__(128) place_kernel(const PlaceArgs a, const Llh
               }
               for (uint32_t x = 0; x <= a.tau && x < stride; ++x) leq += mc[x];
               if (a.no_filter || leq > 1.0) {
-                Objective f{&tab, mc, mismatch, rho, s.k, s.th};
-                brent_minimum(f, d, v);
+                f.uc = mismatch; f.rho = rho; f.k = s.k; f.th = s.th;
+                brent_minimum(PlainEval<kMaxTh + 1>{&f, &tab}, d, v);
               }
             }
             uint32_t cand = 0;
             if (a.nchildren[g] != 1 && (a.no_filter || leq > 1.0)) {
-              chisq = 2 * (f_cl(d) - v_cl);
+              chisq = 2 * (f_cl.eval(tab, d) - v_cl);
               cand = (chisq < a.chisq_value) && a.parent[g] != 0;
             }
             nd_d[j] = d; nd_v[j] = v; nd_c[j] = chisq; nd_k[j] = cand;
@@ -371,7 +336,8 @@ cudaError_t launch_solve(const SolveArgs& a, const LlhTables& tab, int sms, cuda
   const int grid = sms * 8;
   gate_kernel<<<sms * 4, 256, 0, stream>>>(a);
   if (clk) clk->tick("gate_kernel", stream);
-  solve_kernel<<<grid, 128, 0, stream>>>(a, tab);
+  if (a.th + 1 <= 5) solve_kernel<5><<<grid, 128, 0, stream>>>(a, tab);
+  else solve_kernel<kMaxTh + 1><<<grid, 128, 0, stream>>>(a, tab);
   if (clk) clk->tick("solve_kernel", stream);
   merge_kernel<<<grid, 128, 0, stream>>>(a);
   if (a.want_chisq) chisq_kernel<<<grid, 128, 0, stream>>>(a, tab);

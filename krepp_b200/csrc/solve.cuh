@@ -1,14 +1,9 @@
 // Declarations shared between the kernels' translation units and the C-ABI layer.
 #pragma once
 #include "device.cuh"
+#include "llh_math.cuh"
 
 namespace krepp {
-
-// Binomial tables of optimize::HDistHistLLH (ref src/hdhistllh.hpp:51-69), exact in double (values < 2^53).
-struct LlhTables {
-  double ck[33];          // C(k, x), x = 0..k
-  double hnk[kMaxTh + 1]; // C(k, x) - C(k-h, x) for 1 <= x <= th, and 0 for x = 0
-};
 
 // Per-stage CUDA events on the slot's stream (measurement only: bench.py reads them through krepp_batch_stage_times).
 struct StageClock {

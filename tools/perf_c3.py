@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--reads", type=int, default=2_000_000)
     ap.add_argument("--batch", type=int, default=250_000)
     ap.add_argument("--groups", default="staged")
+    ap.add_argument("--dedup", action="store_true", help="count the distinct solves of one batch")
     ap.add_argument("--pipelines", default="sorted,fused", help="KREPP_PIPELINE values to time (sorted.cu / match.cu)")
     ap.add_argument("--out", default="/tmp/c3")
     ap.add_argument("--cpu-reads", type=int, default=100_000)
@@ -80,6 +81,15 @@ def main():
             res.append((mm, tt, time.time() - w0))
         mm, tt, wall = min(res)
         ab = b.algorithmic_bytes()
+        print("   stages of the last batch (ms):", "  ".join(f"{nm} {ms:.2f}" for nm, ms in b.stage_times()), flush=True)
+        if a.dedup:  # how many distinct (leaf, histogram, mismatch count) solves the last batch holds
+            rec, rd, hist = r["records"], r["reads"], r["hist"]
+            solved = (rec["flags"] & 1) != 0
+            key = np.column_stack([rec["leaf_se"][solved], hist[solved], rd["onmers"][rec["read"][solved]] - rec["match_count"][solved]]).astype(np.uint32)
+            uniq = np.unique(key, axis=0)
+            print(f"   solves in the last batch {int(solved.sum())}, distinct (leaf, hist, mismatch) {len(uniq)} -> x{solved.sum() / max(len(uniq), 1):.2f}; "
+                  f"distinct (hist, mismatch) {len(np.unique(key[:, 1:], axis=0))}", flush=True)
+            a.dedup = False
         print(f"scan={g} reads {len(reads)}  match {mm:8.2f} ms  kernels {tt:8.2f} ms  wall {wall * 1e3:8.1f} ms -> {len(reads) / tt / 1e3:7.2f} M reads/s  "
               f"algorithmic {alg / 1e9:7.1f} GB = {alg / len(reads) / 1e3:6.1f} kB/read -> {alg / mm / 1e6:7.1f} GB/s = {alg / mm / 1e6 / peak:5.3f} of measured HBM peak; "
               f"records/read {nrec / len(reads):5.1f}; entries/lookup {ab['entries'] / max(ab['lookups'], 1):5.1f}", flush=True)
