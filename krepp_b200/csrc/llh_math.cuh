@@ -1,6 +1,6 @@
 // llh_math.cuh -- the floating-point core of K4/K5: optimize::HDistHistLLH and the Brent minimiser, written so that the
 // same source compiles for the device (solve.cu, with --fmad=false) and for the host (tests/test_llh_math_cpu.py builds
-// it with g++ -ffp-contract=off and checks it against the oracle).
+// it with g++ -ffp-contract=off and checks it against the CPU restatement of the reference).
 //
 //   objective  : optimize::HDistHistLLH::operator()          ref src/hdhistllh.hpp:71-89
 //   tables     : HDistHistLLH ctor                            ref src/hdhistllh.hpp:51-69
