@@ -46,12 +46,15 @@ import workload as W  # noqa: E402
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "krepp")
 READ_LEN = W.READ_LEN
 METRIC = "reads/sec (krepp dist, 150bp)"
-DEFAULT_READS = {"c3": 10_000_000, "toy": 1_000_000}
-DEFAULT_BATCH = {"c3": 1_000_000, "toy": 1_000_000}
+DEFAULT_READS = {"c3": 10_000_000, "toy": 1_000_000, "c5": 4_000_000}
+DEFAULT_BATCH = {"c3": 1_000_000, "toy": 1_000_000, "c5": 1_000_000}
 WORKLOADS = {
     "c3": "configs[2]: synthetic 1,000-genome index (1,000 x 3 Mbp on a random binary tree, k27 w35 h11), 10M synthetic 150bp reads per GPU, "
           "0-15% substitutions, krepp dist, index replicated",
     "toy": "configs[1]: toy index (25 genomes, k27 w35 h11), 1M synthetic 150bp reads per GPU, 0-15% substitutions",
+    "c5": "configs[4] analogue: index sharded by LSH bucket range over the GPUs (every GPU holds 1/N of the k-mer table; forced -- the "
+          "1,000-genome table of configs[2] stands in for one that exceeds a GPU's HBM, a 10,000-genome index cannot be generated on the "
+          "box within the bench's minutes), all-to-all of lookups and of hit entries over NCCL/NVLink, krepp dist",
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of one match_kernel launch (ncu --set full, summarised under profiles/),
 # keyed by (workload, reads in that launch); scaled linearly to the launch size the bench uses.
@@ -68,7 +71,7 @@ class Workload:
             self.reads = W.toy_reads(reads_per_gpu, seed=1 + rank) if need_reads else None
             self.info = {"seed": "numpy default_rng(1 + rank)"}
             self.fastq = None
-        else:
+        else:  # c3 and c5 share the generated index and read pool
             d, wl = W.ensure_c3(reads_per_gpu * world)
             self.index = os.path.join(d, "index")
             self.reads = W.c3_reads(d, rank * reads_per_gpu, reads_per_gpu) if need_reads else None
@@ -126,11 +129,11 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def run_reference(index: str, fastq: str, threads: int) -> tuple[float, int]:
+def run_reference(index: str, fastq: str, threads: int, mode: str = "dist") -> tuple[float, int]:
     """Runs the unmodified reference CLI; returns (seconds of its own 'Done estimating distances' line, reads)."""
-    p = subprocess.run([REF_BIN, "--num-threads", str(threads), "dist", "-i", index, "-q", fastq, "-o", os.devnull],
+    p = subprocess.run([REF_BIN, "--num-threads", str(threads), mode, "-i", index, "-q", fastq, "-o", os.devnull],
                        capture_output=True, text=True, check=True)
-    sec = float(re.search(r"Done estimating distances, elapsed: ([0-9.eE+-]+) sec", p.stderr).group(1))
+    sec = float(re.search(r"Done (?:estimating distances|placing queries), elapsed: ([0-9.eE+-]+) sec", p.stderr).group(1))
     n = int(re.search(r"Total number of sequences queried: (\d+)", p.stderr).group(1))
     return sec, n
 
@@ -162,17 +165,124 @@ def reference_arm(args) -> None:
     with tempfile.TemporaryDirectory() as td:
         fq = sample_fastq(wl, td, sample)
         for _ in range(args.warmup):
-            run_reference(wl.index, fq, cores)
-        secs = [run_reference(wl.index, fq, cores)[0] for _ in range(args.steps)]
+            run_reference(wl.index, fq, cores, args.mode)
+        secs = [run_reference(wl.index, fq, cores, args.mode)[0] for _ in range(args.steps)]
     t = sum(secs) / len(secs)
     v = sample / t
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "impl": "reference", "metric": METRIC if args.mode == "dist" else METRIC.replace("dist", "place"), "value": v, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32/f64", "data": "synthetic",
         "config": {"workload": WORKLOADS[args.workload], "sample": f"{sample} of the step's reads per step", **wl.info},
         "cpu_baseline": {"value": v, "unit": "reads/s", "cores": cores, "kind": "reference",
-                         "sample": f"{sample} reads per step, oracle/_ref/krepp --num-threads {cores} dist -o /dev/null, its own elapsed line (index load excluded)"},
+                         "sample": f"{sample} reads per step, oracle/_ref/krepp --num-threads {cores} {args.mode} -o /dev/null, its own elapsed line (index load excluded)"},
         "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def shard_arm(args) -> None:
+    """--workload c5: mode B.  One rank per GPU, each holding one bucket-range shard of the index and its own
+    reads; a step = every rank's reads through lookup -> all-to-all -> join on the owning shard -> all-to-all -> resolve /
+    solve, batch by batch.  Timed with CUDA events on torch's stream around the step (the library's calls return only once
+    their kernels are done, and the NCCL exchanges run on torch's stream), max over ranks."""
+    import torch
+    import torch.distributed as dist
+    import krepp_b200.dist as kd
+
+    rank, world, local = kd.env_rank_world()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the krepp_b200 hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = args.reads or DEFAULT_READS["c5"]
+    batch = min(args.batch or DEFAULT_BATCH["c5"], n)
+    t_wl = time.time()
+    wl = Workload("c5", n, rank, world)
+    t_wl = time.time() - t_wl
+    reads = wl.reads
+    me = kd.ShardRank(wl.index, local, rank, world, batch, batch * READ_LEN + 64)
+    job = kd.ShardedJob([me])
+    h_reads = torch.from_numpy(reads.reshape(-1)).pin_memory()
+    d_bases = torch.empty(n * READ_LEN + 64, dtype=torch.uint8, device="cuda")
+    d_bases[:n * READ_LEN].copy_(h_reads)
+    d_offs = (torch.arange(batch + 1, dtype=torch.int64, device="cuda") * READ_LEN)
+    stage = torch.empty(batch * READ_LEN + 64, dtype=torch.uint8, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    chunks = [(i, min(batch, n - i)) for i in range(0, n, batch)]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(from_host: bool):
+        nrec = d2h = 0
+        alg = dict(bytes=0, lookups=0, entries=0)
+        for first, cnt in chunks:
+            if from_host:
+                stage[:cnt * READ_LEN].copy_(h_reads[first * READ_LEN:(first + cnt) * READ_LEN], non_blocking=True)
+                src = stage
+            else:
+                src = d_bases[first * READ_LEN:]
+            r = job.run([(src[:cnt * READ_LEN + 64], d_offs, cnt)])[0]
+            nrec += len(r["records"]); d2h += r["reads"].nbytes + r["records"].nbytes + r["hist"].nbytes
+            ab = me.slot.algorithmic_bytes()
+            for k in alg:
+                alg[k] += ab[k]
+        return nrec, d2h, alg
+
+    def timed(from_host: bool):
+        for _ in range(args.warmup):
+            step(from_host)
+        barrier()
+        job.bytes_exchanged = 0
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        ev0.record()
+        for _ in range(args.steps):
+            if not from_host:
+                flush.zero_()
+            out = step(from_host)
+        ev1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        t = torch.tensor([ev0.elapsed_time(ev1) / 1e3, wall], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1]), out, job.bytes_exchanged / args.steps
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    t_dev, _, (nrec, _, alg), xbytes = timed(False)
+    clocks = sampler.stop()
+    stages = dict(me.slot.stage_times())
+    _, t_e2e, (_, d2h, _), _ = timed(True) if not args.no_e2e else (0, 0, (0, 0, 0), 0)
+    tot = kd.sum_over_ranks([alg["bytes"], alg["lookups"], alg["entries"], nrec, int(xbytes)], device="cuda")
+    sh = me.index.shard
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        achieved = tot[0] / (t_dev / args.steps) / 1e9
+        out = {
+            "metric": METRIC, "value": world * n * args.steps / t_dev, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t_dev * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32/f64", "data": "synthetic",
+            "config": {"workload": WORKLOADS["c5"], "reads_per_gpu": n, "read_len": READ_LEN, "batch_reads": batch, **wl.info,
+                       "index": f"sharded by bucket range, {world} shards; rank 0 holds rows [{sh.row0}, {sh.row1}) = {sh.n_entries} of {me.index.info.nkmers} entries "
+                                f"({me.index.info.device_bytes / 1e9:.2f} GB image per GPU)",
+                       "l2": "inputs larger than L2 and a 256 MiB memset between steps", "records_per_step": tot[3], "workload_setup_s": round(t_wl, 1)},
+            "e2e": None if args.no_e2e else {"value": world * n * args.steps / t_e2e, "unit": "reads/s", "h2d_bytes_per_step": n * READ_LEN, "d2h_bytes_per_step": d2h,
+                                             "how": "every batch copied from page-locked host memory inside the timed region, results copied back by krepp_batch_wait; wall clock, max over ranks"},
+            "gpu_launches": args.steps * len(chunks) * (13 + world + 9), "clocks": clocks,
+            "exchange": {"bytes_received_per_step_all_ranks": tot[4], "per_read": tot[4] / (world * n), "transport": "torch.distributed all_to_all_single (NCCL)" if world > 1 else "none (one shard)"},
+            "roofline": {"bound": "hbm", "kernel": "whole step of all ranks (lookup, exchange, join on the owning shard, exchange, resolve, solve)", "achieved": achieved,
+                         "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world), "traffic": None, "peak_source": peak_src + f" x {world} GPUs",
+                         "algorithmic_bytes_per_step": tot[0], "lookups_per_step": tot[1], "entries_scanned_per_step": tot[2],
+                         "last_batch_stages_ms_rank0": {k: round(v, 3) for k, v in stages.items()}},
+            "cpu_baseline": None,
+        }
+        print(json.dumps(out))
+    me.close()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main() -> None:
@@ -181,7 +291,8 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c3", choices=["c3", "toy"])
+    ap.add_argument("--workload", default="c3", choices=["c3", "toy", "c5"])
+    ap.add_argument("--mode", default="dist", choices=["dist", "place"], help="place = BASELINE configs[3]: krepp place (K5 placement kernel on top of dist)")
     ap.add_argument("--reads", type=int, default=0, help="reads per GPU per step (default: 10M for c3, 1M for toy)")
     ap.add_argument("--batch", type=int, default=0, help="reads per batch of the device-resident arm")
     ap.add_argument("--e2e-batch", type=int, default=250_000)
@@ -190,7 +301,12 @@ def main() -> None:
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
+        if args.workload == "c5":
+            args.workload = "c3"  # same index, same reads: the reference holds the whole table in host memory
         reference_arm(args)
+        return
+    if args.workload == "c5":
+        shard_arm(args)
         return
 
     import torch
@@ -221,7 +337,8 @@ def main() -> None:
         torch.cuda.synchronize()
 
     # ---- device-resident arm (value): one slot, all reads of the step already in HBM, processed in batches
-    slot = krepp_b200.IBatch(index, reads[:batch])
+    mode_kw = dict(place=True, no_filter=False) if args.mode == "place" else {}
+    slot = krepp_b200.IBatch(index, reads[:batch], **mode_kw)
     d_bases = torch.from_numpy(reads.reshape(-1)).cuda()
     d_offs = torch.from_numpy(slot.offsets.astype(np.int64)).cuda()  # fixed-length reads: every batch has the same offsets
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
@@ -231,17 +348,17 @@ def main() -> None:
         flush.zero_()  # evict the index and the reads from L2 between steps
         torch.cuda.synchronize()
         gpu = mm = 0.0
-        launches = nrec = alg = lk = en = 0
+        launches = nrec = alg = lk = en = npl = 0
         stages: dict = {}
         for first, cnt in chunks:
             slot.submit_device(d_bases.data_ptr() + first * READ_LEN, d_offs.data_ptr(), cnt, cnt * READ_LEN)
             r = slot.wait()
-            gpu += r["gpu_ms"]; mm += r["match_ms"]; launches += r["gpu_launches"]; nrec += len(r["records"])
+            gpu += r["gpu_ms"]; mm += r["match_ms"]; launches += r["gpu_launches"]; nrec += len(r["records"]); npl += len(r["placements"])
             ab = slot.algorithmic_bytes()
             alg += ab["bytes"]; lk += ab["lookups"]; en += ab["entries"]
             for name, ms in slot.stage_times():
                 stages[name] = stages.get(name, 0.0) + ms
-        return dict(gpu_ms=gpu, match_ms=mm, launches=launches, records=nrec, alg=alg, lookups=lk, entries=en, stages=stages)
+        return dict(gpu_ms=gpu, match_ms=mm, launches=launches, records=nrec, alg=alg, lookups=lk, entries=en, stages=stages, placements=npl)
 
     for _ in range(args.warmup):
         step_device()
@@ -277,7 +394,7 @@ def main() -> None:
         nslots = 4
         h_reads = torch.from_numpy(reads.reshape(-1)).pin_memory()  # the step's inputs live in page-locked host memory
         h_offs = (np.arange(eb + 1, dtype=np.uint64) * np.uint64(READ_LEN))
-        slots = [krepp_b200.IBatch(index, reads[:eb]) for _ in range(nslots)]
+        slots = [krepp_b200.IBatch(index, reads[:eb], **mode_kw) for _ in range(nslots)]
         echunks = [(i, min(eb, n - i)) for i in range(0, n, eb)]
         h2d = n * READ_LEN + 8 * sum(c + 1 for _, c in echunks)
         base_ptr = h_reads.data_ptr()
@@ -288,13 +405,13 @@ def main() -> None:
                 s = slots[j % nslots]
                 if len(inflight) == nslots:
                     res = inflight.pop(0).wait()
-                    d2h += res["reads"].nbytes + res["records"].nbytes + res["hist"].nbytes
+                    d2h += res["reads"].nbytes + res["records"].nbytes + res["hist"].nbytes + res["placements"].nbytes
                     nrec += len(res["records"])
                 s.submit_host(base_ptr + first * READ_LEN, h_offs.ctypes.data, cnt)
                 inflight.append(s)
             for s in inflight:
                 res = s.wait()
-                d2h += res["reads"].nbytes + res["records"].nbytes + res["hist"].nbytes
+                d2h += res["reads"].nbytes + res["records"].nbytes + res["hist"].nbytes + res["placements"].nbytes
                 nrec += len(res["records"])
             return d2h, nrec
 
@@ -335,13 +452,16 @@ def main() -> None:
     if args.workload in NCU_TRAFFIC and not sorted_pipeline:
         per, tb, _src = NCU_TRAFFIC[args.workload]
         traffic = tb * (batch / per)
+    wname = WORKLOADS[args.workload]
+    if args.mode == "place":
+        wname = wname.replace("configs[2]", "configs[3]").replace("krepp dist", "krepp place (per-read candidate placements: records of the jplace output)")
     out = {
-        "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC if args.mode == "dist" else METRIC.replace("dist", "place"), "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_dev * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32/f64", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload], "reads_per_gpu": n, "read_len": READ_LEN, "batch_reads": batch, **wl.info,
+        "config": {"workload": wname, "reads_per_gpu": n, "read_len": READ_LEN, "batch_reads": batch, **wl.info,
                    "l2": "inputs larger than L2 (index image %.2f GB, reads %.2f GB per step) and a 256 MiB memset between steps" % (index.info.device_bytes / 1e9, n * READ_LEN / 1e9),
-                   "index": "replicated per GPU", "records_per_step": last["records"], "wall_s_device_arm": wall_device,
+                   "index": "replicated per GPU", "records_per_step": last["records"], "placements_per_step": last["placements"], "wall_s_device_arm": wall_device,
                    "workload_setup_s": round(t_wl, 1)},
         "e2e": e2e_out,
         "gpu_launches": launches,
@@ -363,9 +483,9 @@ def main() -> None:
         sample = min(args.cpu_sample or {"c3": 200_000, "toy": 200_000}[args.workload], n)
         with tempfile.TemporaryDirectory() as td:
             fq = sample_fastq(wl, td, sample)
-            sec, nq = run_reference(wl.index, fq, cores)
+            sec, nq = run_reference(wl.index, fq, cores, args.mode)
         out["cpu_baseline"] = {"value": nq / sec, "unit": "reads/s", "cores": cores, "kind": "reference",
-                               "sample": f"first {sample} of rank 0's reads, oracle/_ref/krepp --num-threads {cores} dist -o /dev/null on the same index, "
+                               "sample": f"first {sample} of rank 0's reads, oracle/_ref/krepp --num-threads {cores} {args.mode} -o /dev/null on the same index, "
                                          f"its own elapsed line ({sec:.2f} s, index load excluded)"}
     else:
         out["cpu_baseline"] = None

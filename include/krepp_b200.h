@@ -177,6 +177,55 @@ int krepp_batch_algorithmic_bytes(krepp_batch_t* b, uint64_t* bytes, uint64_t* l
  * i < min(*n, cap); *n = number of stages.  The stages of the match step (src/query.cpp:40-94,352-390) come first. */
 int krepp_batch_stage_times(krepp_batch_t* b, uint32_t cap, float* ms, const char** names, uint32_t* n);
 
+/* -------------------------------------------------------------------------------------------------- bucket-range shards
+ * SURVEY.md section 8e, mode B: an index too large for one GPU is split by LSH bucket (row) range over the ranks of a
+ * job.  The reference has no counterpart (it holds the whole table of src/table.hpp:121-143 in one address space); what
+ * is replaced is still IBatch::search_mers + IMers::add_matching_mer (src/query.cpp:40-94,352-390), cut at the two
+ * points where data changes owner.  Every entry that can match a lookup lives in the lookup's bucket, hence on exactly
+ * one shard, so the per-(read, strand, leaf) histograms are complete after one round trip and identical to the
+ * unsharded result.
+ *
+ *   home rank    krepp_shard_lookup   reads -> eligible lookups ("tuples", 16 bytes: {enc32 q, read, strand << 31 | lookup
+ *                                     index, 0}) counting-sorted by row, so shard g's tuples are tuples[send_offsets[g] ..
+ *                                     send_offsets[g+1]) and its row directory is row_begin[row_splits[g] .. row_splits[g+1]]
+ *   (exchange)                        the caller moves both runs to rank g (an all-to-all-v; NCCL over NVLink in
+ *                                     krepp_b200/dist.py) -- the library never touches another rank's memory
+ *   owner rank   krepp_shard_join     per sender: its tuples against this shard's buckets -> hit entries (16 bytes: {read,
+ *                                     strand << 31 | lookup index << 5 | hd, colour id, 0}), appended sender by sender
+ *   (exchange)                        hit_offsets[src .. src+1) goes back to rank src
+ *   home rank    krepp_shard_finish   hit entries of the batch from all owners -> colour expansion, min-hd histograms, gate,
+ *                                     likelihood solve, merge: then krepp_batch_wait as for an unsharded batch
+ *
+ * All buffers passed here are DEVICE memory owned by the caller on the index's device.  The three calls of one batch run
+ * on one slot in this order; lookup and join return when their kernels have finished (their outputs size the exchange),
+ * finish only enqueues. */
+#define KREPP_MAX_SHARDS 256
+
+typedef struct {
+  uint32_t shard, nshards;
+  uint32_t row0, row1;              /* rows [row0, row1) of the table live on this shard */
+  uint64_t first_entry, n_entries;  /* entries [first_entry, first_entry + n_entries) of cmer-* */
+} krepp_shard_info_t;
+
+/* krepp_index_open for one shard: parses every file but keeps (and uploads) only this shard's slice of cmer-* and inc-*;
+ * colour record, tree and hash tables are replicated.  Shards are contiguous row ranges of (nearly) equal cmer bytes,
+ * derived from inc-* alone, so every rank computes the same split.  nshards = 1 is krepp_index_open. */
+int krepp_index_open_shard(const char* index_dir, int device, uint32_t shard, uint32_t nshards, krepp_index_t** out);
+/* row_splits (may be NULL): first row of every shard, nshards + 1 values (at most cap are written). */
+int krepp_index_shard_info(const krepp_index_t* ix, krepp_shard_info_t* out, uint32_t* row_splits, uint32_t cap);
+
+/* d_tuples: room for cap_tuples tuples; d_row_begin: nrows + 1 words; send_offsets: nshards + 1 host words.  Returns
+ * KREPP_ERR_CAPACITY when the batch has more lookups than cap_tuples (send_offsets[nshards] then holds the demand). */
+int krepp_shard_lookup(krepp_batch_t* b, const char* d_bases, const uint64_t* d_offsets, uint32_t n_reads, uint64_t n_bases,
+                       void* d_tuples, uint64_t cap_tuples, uint32_t* d_row_begin, uint64_t* send_offsets);
+/* d_tuples[src] / d_row_begin[src]: sender src's tuples for this shard and its row_begin[row0 .. row1] (row1 - row0 + 1
+ * words, positions still relative to the sender's list).  hit_offsets: n_sources + 1 host words.  KREPP_ERR_CAPACITY when
+ * cap_hits is too small (hit_offsets[n_sources] then holds the demand; call again with a larger buffer). */
+int krepp_shard_join(krepp_batch_t* b, uint32_t n_sources, const void* const* d_tuples, const uint32_t* const* d_row_begin,
+                     void* d_hits, uint64_t cap_hits, uint64_t* hit_offsets);
+/* d_hits must stay untouched until krepp_batch_wait has returned. */
+int krepp_shard_finish(krepp_batch_t* b, const void* d_hits, uint64_t n_hits);
+
 /* -------------------------------------------------------------------------------------------------- host I/O layer
  * The steps immediately either side of the GPU path.  Pure host code: usable
  * without a device (the index handle may have been opened with KREPP_DEVICE_NONE). */

@@ -30,6 +30,14 @@ class KreppError(RuntimeError):
         self.code = code
 
 
+class CapacityError(KreppError):
+    """A caller-owned buffer was too small; `demand` is the number of items the call needs room for."""
+
+    def __init__(self, demand: int, msg: str):
+        super().__init__(4, msg)
+        self.demand = demand
+
+
 class Params(C.Structure):
     _fields_ = [("hdist_th", C.c_uint32), ("chisq", C.c_double), ("dist_max", C.c_double), ("tau", C.c_uint32),
                 ("no_filter", C.c_int32), ("multi", C.c_int32), ("summarize", C.c_int32), ("place", C.c_int32)]
@@ -41,6 +49,11 @@ class IndexInfo(C.Structure):
                 ("nleaves", C.c_uint32), ("nsubsets", C.c_uint32), ("root_se", C.c_uint32), ("mask_hash_bp", C.c_uint64),
                 ("mask_drop_lr", C.c_uint64), ("device_bytes", C.c_uint64), ("mean_bucket", C.c_double),
                 ("size_biased_bucket", C.c_double)]
+
+
+class ShardInfo(C.Structure):
+    _fields_ = [("shard", C.c_uint32), ("nshards", C.c_uint32), ("row0", C.c_uint32), ("row1", C.c_uint32),
+                ("first_entry", C.c_uint64), ("n_entries", C.c_uint64)]
 
 
 class Results(C.Structure):
@@ -99,6 +112,11 @@ def load_library():
     L.krepp_batch_read_tap.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.krepp_batch_algorithmic_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.krepp_batch_stage_times.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_char_p), C.POINTER(C.c_uint32)]
+    L.krepp_index_open_shard.argtypes = [C.c_char_p, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]
+    L.krepp_index_shard_info.argtypes = [C.c_void_p, C.POINTER(ShardInfo), C.c_void_p, C.c_uint32]
+    L.krepp_shard_lookup.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    L.krepp_shard_join.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+    L.krepp_shard_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
     L.krepp_reader_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
     L.krepp_reader_close.argtypes = [C.c_void_p]
     L.krepp_reader_next.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p,
@@ -129,12 +147,16 @@ def _view(ptr, dtype, n):
 class Index:
     """Index image resident on one GPU (replaces Index + TargetIndex::load_index, src/krepp.cpp:66-108)."""
 
-    def __init__(self, index_dir: str, device: int = 0):
+    def __init__(self, index_dir: str, device: int = 0, shard: int = 0, nshards: int = 1):
+        """nshards > 1: this handle holds bucket-range shard `shard` of the table only (SURVEY.md 8e mode B)."""
         L = load_library()
         self._h = C.c_void_p()
-        _check(L.krepp_index_open(os.fsencode(index_dir), device, C.byref(self._h)))
+        _check(L.krepp_index_open_shard(os.fsencode(index_dir), device, shard, nshards, C.byref(self._h)))
         self.info = IndexInfo()
         _check(L.krepp_index_info(self._h, C.byref(self.info)))
+        self.shard = ShardInfo()
+        self.row_splits = np.zeros(nshards + 1, np.uint32)
+        _check(L.krepp_index_shard_info(self._h, C.byref(self.shard), self.row_splits.ctypes.data, nshards + 1))
         self.device = device
 
     def close(self):
@@ -232,6 +254,33 @@ class IBatch:
 
     def submit_device(self, d_bases_ptr: int, d_offsets_ptr: int, n_reads: int, n_bases: int):
         _check(load_library().krepp_batch_submit_device(self._h, d_bases_ptr, d_offsets_ptr, n_reads, n_bases))
+
+    # -- mode B: the three phases of a batch on a sharded index (device pointers as ints; see include/krepp_b200.h) ----
+    def shard_lookup(self, d_bases_ptr: int, d_offsets_ptr: int, n_reads: int, n_bases: int, d_tuples_ptr: int, cap_tuples: int,
+                     d_row_begin_ptr: int) -> np.ndarray:
+        """-> send_offsets[nshards + 1]: shard g's tuples are tuples[send_offsets[g] : send_offsets[g + 1]]."""
+        so = np.zeros(self.index.shard.nshards + 1, np.uint64)
+        rc = load_library().krepp_shard_lookup(self._h, d_bases_ptr, d_offsets_ptr, n_reads, n_bases, d_tuples_ptr, cap_tuples,
+                                               d_row_begin_ptr, so.ctypes.data)
+        if rc == 4 and int(so[-1]) > cap_tuples:
+            raise CapacityError(int(so[-1]), load_library().krepp_last_error().decode())
+        _check(rc)
+        return so
+
+    def shard_join(self, d_tuples_ptrs, d_row_begin_ptrs, d_hits_ptr: int, cap_hits: int) -> np.ndarray:
+        """-> hit_offsets[n_sources + 1]: the hit entries owed to sender s are hits[hit_offsets[s] : hit_offsets[s + 1]]."""
+        n = len(d_tuples_ptrs)
+        ho = np.zeros(n + 1, np.uint64)
+        tp = (C.c_void_p * max(n, 1))(*d_tuples_ptrs)
+        rp = (C.c_void_p * max(n, 1))(*d_row_begin_ptrs)
+        rc = load_library().krepp_shard_join(self._h, n, tp, rp, d_hits_ptr, cap_hits, ho.ctypes.data)
+        if rc == 4 and int(ho[-1]) > cap_hits:
+            raise CapacityError(int(ho[-1]), load_library().krepp_last_error().decode())
+        _check(rc)
+        return ho
+
+    def shard_finish(self, d_hits_ptr: int, n_hits: int):
+        _check(load_library().krepp_shard_finish(self._h, d_hits_ptr, n_hits))
 
     def wait(self) -> dict:
         r = Results()

@@ -163,7 +163,8 @@ struct krepp_batch {
   // bucket-sorted pipeline (sorted.cu)
   bool sorted = false, fused_once = false;
   SortArgs so{};
-  uint32_t* h_sc = nullptr;   // [0..7] copy of so.sc, [8] lookups of the batch
+  uint32_t* h_sc = nullptr;   // [0..7] copy of so.sc, [8] lookups of the batch, [9] hit entries handed to finish, [16..] mode B row/hit boundaries
+  const void* shard_hits = nullptr; uint64_t shard_n_hits = 0; // mode B: the batch is in its finish phase (krepp_shard_finish)
   StageClock clk;             // per-stage events of the last enqueue
   // tap
   uint4* d_tap = nullptr; unsigned long long* d_tap_count = nullptr; unsigned long long tap_cap = 0;
@@ -181,22 +182,28 @@ void krepp_params_default(krepp_params_t* p, int place)
   p->no_filter = place ? 0 : 1; p->multi = 1; p->summarize = 0; p->place = place ? 1 : 0;
 }
 
-int krepp_index_open(const char* index_dir, int device, krepp_index_t** out)
+int krepp_index_open(const char* index_dir, int device, krepp_index_t** out) { return krepp_index_open_shard(index_dir, device, 0, 1, out); }
+
+int krepp_index_open_shard(const char* index_dir, int device, uint32_t shard, uint32_t nshards, krepp_index_t** out)
 {
   if (!index_dir || !out) return fail(KREPP_ERR_ARG, "krepp_index_open: null argument");
   *out = nullptr;
+  if (!nshards || shard >= nshards || nshards > KREPP_MAX_SHARDS) return fail(KREPP_ERR_ARG, "krepp_index_open_shard: shard %u of %u is not valid (at most %d shards)", shard, nshards, KREPP_MAX_SHARDS);
   int ndev = 0;
   if (device != KREPP_DEVICE_NONE) {
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(KREPP_ERR_CUDA, "no CUDA device is available (the krepp_b200 query path has no CPU fallback)");
     if (device < 0 || device >= ndev) return fail(KREPP_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
   }
   auto* ix = new krepp_index;
-  std::string err = ix->host.load(index_dir);
+  std::string err = ix->host.load(index_dir, shard, nshards);
   if (!err.empty()) { delete ix; return fail(KREPP_ERR_IO, "%s", err.c_str()); }
   const HostIndex& h = ix->host;
   if (device == KREPP_DEVICE_NONE) { ix->device = device; *out = ix; return KREPP_OK; } // metadata / tree only, no queries
   if (h.m > (uint32_t)kMaxResidues) { const uint32_t m = h.m; delete ix; return fail(KREPP_ERR_UNSUPPORTED, "m = %u exceeds the %d residues supported on the device", m, kMaxResidues); }
-  if (h.inc32.empty() && h.nrows) { delete ix; return fail(KREPP_ERR_UNSUPPORTED, "indexes with 2^32 or more k-mers are not supported by the GPU path yet"); }
+  if (h.inc32.size() != (size_t)(h.row1 - h.row0)) {
+    delete ix;
+    return fail(KREPP_ERR_UNSUPPORTED, "2^32 or more k-mers on one device are not supported: open the index as bucket-range shards (krepp_index_open_shard)");
+  }
   ix->device = device;
   cudaError_t e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ix->sms, cudaDevAttrMultiProcessorCount, device);
@@ -235,7 +242,7 @@ int krepp_index_open(const char* index_dir, int device, krepp_index_t** out)
     delete ix;
     return fail(KREPP_ERR_CUDA, "uploading the index image failed: %s", cudaGetErrorString(e));
   }
-  d.nkmers = h.nkmers; d.nrows = h.nrows; d.nsubsets = h.nsubsets; d.nnodes = h.tree.nnodes; d.nleaves = h.tree.nleaves;
+  d.nkmers = h.nkmers; d.nrows = h.nrows; d.row0 = h.row0; d.nrows_local = h.row1 - h.row0; d.nsubsets = h.nsubsets; d.nnodes = h.tree.nnodes; d.nleaves = h.tree.nleaves;
   d.k = h.k; d.h = h.h; d.m = h.m;
   d.m_shift = (h.m & (h.m - 1)) == 0 ? (uint32_t)__builtin_ctz(h.m) : 0xFFFFFFFFu;
   for (uint32_t i = 0; i < (uint32_t)kMaxResidues; ++i) d.res_numer[i] = i < h.m ? h.res_numer[i] : 0;
@@ -248,7 +255,7 @@ int krepp_index_open(const char* index_dir, int device, krepp_index_t** out)
   }
   // Pipeline (see sorted.cu): indexes with large buckets are matched bucket-sorted, so that a bucket is read from HBM once per
   // batch; small-bucket indexes keep the fused kernel.  KREPP_PIPELINE=sorted|fused overrides (read again per batch slot).
-  ix->sorted_default = ix->sorted_ok && ix->staged;
+  ix->sorted_default = ix->sorted_ok && (ix->staged || h.nshards > 1);
   ix->resident_warps = match_resident_warps(device, h.k, ix->staged);
   if (ix->staged && ix->resident_warps == 0) { ix->staged = false; ix->resident_warps = match_resident_warps(device, h.k, false); } // k > 28: the ring does not fit beside an 8-table LUT
   *out = ix;
@@ -261,6 +268,15 @@ void krepp_index_close(krepp_index_t* ix)
   if (ix->device != KREPP_DEVICE_NONE) cudaSetDevice(ix->device);
   for (void* p : ix->allocs) cudaFree(p);
   delete ix;
+}
+
+int krepp_index_shard_info(const krepp_index_t* ix, krepp_shard_info_t* o, uint32_t* row_splits, uint32_t cap)
+{
+  if (!ix || !o) return fail(KREPP_ERR_ARG, "krepp_index_shard_info: null argument");
+  const HostIndex& h = ix->host;
+  o->shard = h.shard; o->nshards = h.nshards; o->row0 = h.row0; o->row1 = h.row1; o->first_entry = h.ent0; o->n_entries = h.cmer.size();
+  if (row_splits) for (uint32_t g = 0; g <= h.nshards && g < cap; ++g) row_splits[g] = h.row_splits[g];
+  return KREPP_OK;
 }
 
 int krepp_index_info(const krepp_index_t* ix, krepp_index_info_t* o)
@@ -369,7 +385,7 @@ static int alloc_sorted(krepp_batch* b)
   const uint64_t nmax = std::max<uint64_t>(h.nrows, b->max_reads);
   CU(cudaMalloc(&so.partials, 4ull * (nmax / 4096 + 2)));
   CU(cudaMalloc(&so.sc, 32));
-  CU(cudaMallocHost(&b->h_sc, 64));
+  CU(cudaMallocHost(&b->h_sc, 4ull * (16 + 2 * (KREPP_MAX_SHARDS + 1))));
   if (const char* env = getenv("KREPP_SORT_WIDE")) so.extra_rank_bits = (uint32_t)std::min(24, std::max(0, atoi(env)));
   so.cap_keys_g = 8192; // 64-bit keys per warp (a power of two): reads with more leaf hits send the batch to the fused kernel
   CU(cudaMalloc(&so.keys_g, 8ull * so.cap_keys_g * (size_t)sorted_resolve_warps(b->ix->sms)));
@@ -402,7 +418,7 @@ int krepp_batch_create(krepp_index_t* ix, const krepp_params_t* p, uint32_t max_
   CU(cudaMalloc(&b->d_bases, max_bases + 64)); CU(cudaMalloc(&b->d_offsets, 8ull * (max_reads + 1)));
   CU(cudaMalloc(&b->d_onmers, 4ull * max_reads)); CU(cudaMalloc(&b->d_wn, 8ull * max_reads)); CU(cudaMalloc(&b->d_hdfilt, 8ull * max_reads));
   CU(cudaMalloc(&b->d_rec_begin, 4ull * max_reads)); CU(cudaMalloc(&b->d_rec_count, 4ull * max_reads)); CU(cudaMalloc(&b->d_closest, 4ull * max_reads));
-  CU(cudaMalloc(&b->d_counters, 32)); CU(cudaMalloc(&b->d_stats, 32));
+  CU(cudaMalloc(&b->d_counters, 32)); CU(cudaMalloc(&b->d_stats, 64)); // stats: [0..3] live, [4..7] snapshot taken before a mode B finish
   CU(cudaMallocHost(&b->h_counters, 32)); CU(cudaMallocHost(&b->h_stats, 32));
   CU(cudaMalloc(&b->d_out_read, sizeof(krepp_read_summary_t) * (size_t)max_reads));
   CU(cudaMallocHost(&b->h_read, sizeof(krepp_read_summary_t) * (size_t)max_reads));
@@ -421,6 +437,11 @@ int krepp_batch_create(krepp_index_t* ix, const krepp_params_t* p, uint32_t max_
   if (const char* env = getenv("KREPP_PIPELINE")) {
     if (!strcmp(env, "sorted")) { if (!ix->sorted_ok) return fail(KREPP_ERR_UNSUPPORTED, "KREPP_PIPELINE=sorted: the flattened colour lists of this index are too large"); b->sorted = true; }
     else if (!strcmp(env, "fused")) b->sorted = false;
+  }
+  if (h.nshards > 1) { // the fused kernel walks the whole table: a shard can only serve the bucket-sorted chain
+    if (!ix->sorted_ok) return fail(KREPP_ERR_UNSUPPORTED, "sharded indexes need the flattened colour lists, which are too large for this index");
+    if (max_reads > (1u << 30)) return fail(KREPP_ERR_CAPACITY, "at most 2^30 reads per batch");
+    b->sorted = true;
   }
   if (b->sorted) { if (int rc = alloc_sorted(b)) return rc; }
   if (p->place) {
@@ -463,26 +484,40 @@ void krepp_batch_destroy(krepp_batch_t* b)
   delete b;
 }
 
-// Enqueues all kernels of one batch on the slot's stream (inputs already on the device).
-static int enqueue(krepp_batch* b)
+static MatchArgs match_args(krepp_batch* b)
 {
-  krepp_index* ix = b->ix;
-  const HostIndex& h = ix->host;
-  cudaStream_t s = b->stream;
-  CU(cudaMemsetAsync(b->d_counters, 0, 32, s));
-  CU(cudaMemsetAsync(b->d_stats, 0, 32, s));
-  if (b->d_tap_count) CU(cudaMemsetAsync(b->d_tap_count, 0, 8, s));
   MatchArgs m{};
   m.bases = b->in_bases; m.offsets = b->in_offsets; m.n_bases = b->n_bases; m.n_reads = b->n_reads; m.th = b->p.hdist_th; m.keep_all = b->keep_all ? 1u : 0u;
   m.onmers = b->d_onmers; m.wn = b->d_wn; m.hdfilt = b->d_hdfilt; m.rec_begin = b->d_rec_begin; m.rec_count = b->d_rec_count;
   m.rec_read = b->d_rec_read; m.rec_slot = b->d_rec_slot; m.rec_hist = b->d_rec_hist; m.rec_cap = b->rec_cap; m.counters = b->d_counters;
   m.acc = b->d_acc; m.bitmap = b->d_bitmap; m.marker = b->d_marker; m.stack = b->d_stack; m.stack_cap = b->stack_cap; m.tagctr = b->d_tagctr; m.stats = b->d_stats;
   m.tap = b->d_tap; m.tap_count = b->d_tap_count; m.tap_cap = b->tap_cap;
+  return m;
+}
+
+// Enqueues all kernels of one batch on the slot's stream (inputs already on the device).  In mode B's finish phase
+// (krepp_shard_finish) the match step starts from the hit entries the shard owners returned.
+static int enqueue(krepp_batch* b)
+{
+  krepp_index* ix = b->ix;
+  const HostIndex& h = ix->host;
+  cudaStream_t s = b->stream;
+  CU(cudaMemsetAsync(b->d_counters, 0, 32, s));
+  if (b->shard_hits) CU(cudaMemcpyAsync(b->d_stats, b->d_stats + 4, 32, cudaMemcpyDeviceToDevice, s)); // the lookup / join phases' counts
+  else CU(cudaMemsetAsync(b->d_stats, 0, 32, s));
+  if (b->d_tap_count && !b->shard_hits) CU(cudaMemsetAsync(b->d_tap_count, 0, 8, s));
+  MatchArgs m = match_args(b);
   CU(cudaEventRecord(b->evm0, s));
-  b->clk.n = 0;
-  b->clk.tick("start", s);
+  if (!b->shard_hits) { b->clk.n = 0; b->clk.tick("start", s); }
   uint32_t match_launches = 1;
-  if (b->sorted && !b->fused_once) {
+  if (b->shard_hits) {
+    SortArgs so = b->so;
+    so.hits_tmp = const_cast<uint4*>(static_cast<const uint4*>(b->shard_hits));
+    b->h_sc[9] = (uint32_t)b->shard_n_hits;
+    CU(cudaMemcpyAsync(so.sc, b->h_sc + 9, 4, cudaMemcpyHostToDevice, s));
+    CU(launch_shard_finish(ix->dev, m, so, ix->sms, s, &b->clk));
+    match_launches = 6;
+  } else if (b->sorted && !b->fused_once) {
     CU(launch_match_sorted(ix->dev, m, b->so, ix->sms, b->d_tap != nullptr, s, &match_launches, &b->clk));
     CU(cudaMemcpyAsync(b->h_sc, b->so.sc, 32, cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(b->h_sc + 8, b->so.row_begin + b->so.nrows, 4, cudaMemcpyDeviceToHost, s));
@@ -536,6 +571,7 @@ int krepp_batch_submit(krepp_batch_t* b, const char* bases, const uint64_t* offs
   if (n_reads > b->max_reads) return fail(KREPP_ERR_CAPACITY, "batch of %u reads exceeds the slot capacity of %u", n_reads, b->max_reads);
   const uint64_t nb = n_reads ? offsets[n_reads] - offsets[0] : 0;
   if (nb > b->max_bases) return fail(KREPP_ERR_CAPACITY, "batch of %llu bases exceeds the slot capacity of %llu", (unsigned long long)nb, (unsigned long long)b->max_bases);
+  if (b->ix->host.nshards > 1) return fail(KREPP_ERR_UNSUPPORTED, "this index handle holds one bucket-range shard: use krepp_shard_lookup / _join / _finish");
   if (cudaSetDevice(b->ix->device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice failed");
   CU(cudaStreamSynchronize(b->stream)); // the previous batch of this slot must be finished before its buffers are reused
   // Page-locked caller memory (cudaMallocHost / cudaHostRegister) is copied to the device straight from where it lies;
@@ -550,7 +586,7 @@ int krepp_batch_submit(krepp_batch_t* b, const char* bases, const uint64_t* offs
     const uint64_t o0 = offsets[0];
     for (uint32_t i = 0; i <= n_reads; ++i) b->h_offsets[i] = offsets[i] - o0;
   }
-  b->n_reads = n_reads; b->n_bases = nb; b->device_input = false; b->fused_once = false;
+  b->n_reads = n_reads; b->n_bases = nb; b->device_input = false; b->fused_once = false; b->shard_hits = nullptr;
   b->in_bases = b->d_bases; b->in_offsets = b->d_offsets;
   CU(cudaMemcpyAsync(b->d_bases, src, nb, cudaMemcpyHostToDevice, b->stream));
   CU(cudaMemcpyAsync(b->d_offsets, b->h_offsets, 8ull * (n_reads + 1), cudaMemcpyHostToDevice, b->stream));
@@ -565,9 +601,10 @@ int krepp_batch_submit_device(krepp_batch_t* b, const char* d_bases, const uint6
   if (!b || !d_bases || !d_offsets) return fail(KREPP_ERR_ARG, "krepp_batch_submit_device: null argument");
   if (n_reads > b->max_reads) return fail(KREPP_ERR_CAPACITY, "batch of %u reads exceeds the slot capacity of %u", n_reads, b->max_reads);
   if (reinterpret_cast<uintptr_t>(d_bases) & 15) return fail(KREPP_ERR_ARG, "device bases pointer must be 16-byte aligned");
+  if (b->ix->host.nshards > 1) return fail(KREPP_ERR_UNSUPPORTED, "this index handle holds one bucket-range shard: use krepp_shard_lookup / _join / _finish");
   if (cudaSetDevice(b->ix->device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice failed");
   CU(cudaStreamSynchronize(b->stream));
-  b->n_reads = n_reads; b->n_bases = n_bases; b->device_input = true; b->fused_once = false;
+  b->n_reads = n_reads; b->n_bases = n_bases; b->device_input = true; b->fused_once = false; b->shard_hits = nullptr;
   b->in_bases = d_bases; b->in_offsets = d_offsets;
   CU(cudaEventRecord(b->ev0, b->stream));
   if (int rc = enqueue(b)) return rc;
@@ -583,6 +620,9 @@ int krepp_batch_wait(krepp_batch_t* b, krepp_results_t* out)
   for (int attempt = 0;; ++attempt) {
     CU(cudaStreamSynchronize(b->stream));
     if (b->h_counters[2] & kErrStackOverflow) return fail(KREPP_ERR_CAPACITY, "colour expansion stack overflow on the device");
+    if (b->h_counters[2] & kErrShardData) return fail(KREPP_ERR_ARG, "krepp_shard_finish: a hit entry names a read outside the batch");
+    if (b->shard_hits && (b->h_counters[2] & kErrSortFallback))
+      return fail(KREPP_ERR_CAPACITY, "a read has more leaf hits than the bucket-sorted chain holds and a sharded index has no fused kernel to fall back to");
     if (!(b->h_counters[2] & (kErrRecOverflow | kErrPlaceOverflow | kErrLookupOverflow | kErrHitOverflow | kErrSortFallback))) break;
     // a result buffer was too small: grow it to what the kernels asked for and run the batch again
     if (attempt >= 8) return fail(KREPP_ERR_CAPACITY, "result buffer overflow persists");
@@ -623,6 +663,89 @@ int krepp_batch_wait(krepp_batch_t* b, krepp_results_t* out)
   float mms = 0;
   CU(cudaEventElapsedTime(&mms, b->evm0, b->evm1));
   out->gpu_ms = ms; out->match_ms = mms; out->gpu_launches = b->launches;
+  return KREPP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ mode B (bucket-range shards)
+
+int krepp_shard_lookup(krepp_batch_t* b, const char* d_bases, const uint64_t* d_offsets, uint32_t n_reads, uint64_t n_bases,
+                       void* d_tuples, uint64_t cap_tuples, uint32_t* d_row_begin, uint64_t* send_offsets)
+{
+  if (!b || !d_bases || !d_offsets || !d_tuples || !d_row_begin || !send_offsets) return fail(KREPP_ERR_ARG, "krepp_shard_lookup: null argument");
+  if (!b->sorted) return fail(KREPP_ERR_UNSUPPORTED, "krepp_shard_lookup: this slot does not run the bucket-sorted chain");
+  if (n_reads > b->max_reads) return fail(KREPP_ERR_CAPACITY, "batch of %u reads exceeds the slot capacity of %u", n_reads, b->max_reads);
+  if (reinterpret_cast<uintptr_t>(d_bases) & 15) return fail(KREPP_ERR_ARG, "device bases pointer must be 16-byte aligned");
+  if (cudaSetDevice(b->ix->device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice failed");
+  const HostIndex& h = b->ix->host;
+  cudaStream_t s = b->stream;
+  CU(cudaStreamSynchronize(s));
+  b->n_reads = n_reads; b->n_bases = n_bases; b->device_input = true; b->fused_once = false; b->shard_hits = nullptr; b->submitted = false;
+  b->in_bases = d_bases; b->in_offsets = d_offsets;
+  CU(cudaMemsetAsync(b->d_counters, 0, 32, s));
+  CU(cudaMemsetAsync(b->d_stats, 0, 32, s));
+  if (b->d_tap_count) CU(cudaMemsetAsync(b->d_tap_count, 0, 8, s));
+  MatchArgs m = match_args(b);
+  SortArgs so = b->so;
+  so.tuples = static_cast<uint4*>(d_tuples); so.cap_lookups = (uint32_t)std::min<uint64_t>(cap_tuples, 0xFFFFFFF0ull); so.row_begin = d_row_begin;
+  CU(cudaEventRecord(b->ev0, s));
+  b->clk.n = 0; b->clk.tick("start", s);
+  CU(launch_shard_lookup(b->ix->dev, m, so, b->ix->sms, b->d_tap != nullptr, s, &b->clk));
+  uint32_t* hb = b->h_sc + 16;
+  for (uint32_t g = 0; g <= h.nshards; ++g) CU(cudaMemcpyAsync(hb + g, d_row_begin + h.row_splits[g], 4, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(b->h_counters, b->d_counters, 32, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  for (uint32_t g = 0; g <= h.nshards; ++g) send_offsets[g] = hb[g];
+  if (b->h_counters[2] & kErrSortFallback) return fail(KREPP_ERR_CAPACITY, "a read has more lookups than the bucket-sorted chain holds");
+  if (b->h_counters[2] & kErrLookupOverflow) return fail(KREPP_ERR_CAPACITY, "the batch has %llu lookups but the tuple buffer holds %llu", (unsigned long long)hb[h.nshards], (unsigned long long)cap_tuples);
+  return KREPP_OK;
+}
+
+int krepp_shard_join(krepp_batch_t* b, uint32_t n_sources, const void* const* d_tuples, const uint32_t* const* d_row_begin,
+                     void* d_hits, uint64_t cap_hits, uint64_t* hit_offsets)
+{
+  if (!b || !d_hits || !hit_offsets || (n_sources && (!d_tuples || !d_row_begin))) return fail(KREPP_ERR_ARG, "krepp_shard_join: null argument");
+  if (!b->sorted) return fail(KREPP_ERR_UNSUPPORTED, "krepp_shard_join: this slot does not run the bucket-sorted chain");
+  if (n_sources > KREPP_MAX_SHARDS) return fail(KREPP_ERR_ARG, "krepp_shard_join: at most %d sources", KREPP_MAX_SHARDS);
+  if (cudaSetDevice(b->ix->device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice failed");
+  cudaStream_t s = b->stream;
+  CU(cudaStreamSynchronize(s));
+  CU(cudaMemsetAsync(b->d_counters + 2, 0, 4, s));
+  CU(cudaMemsetAsync(b->so.sc, 0, 4, s));
+  uint32_t* hb = b->h_sc + 16 + KREPP_MAX_SHARDS + 1;
+  hb[0] = 0;
+  b->clk.tick("(exchange of lookups)", s);
+  for (uint32_t src = 0; src < n_sources; ++src) {
+    SortArgs so = b->so;
+    so.nrows = b->ix->dev.nrows_local;
+    so.tuples = const_cast<uint4*>(static_cast<const uint4*>(d_tuples[src])); so.cap_lookups = 0xFFFFFFFFu;
+    so.row_begin = const_cast<uint32_t*>(d_row_begin[src]);
+    so.hits_tmp = static_cast<uint4*>(d_hits); so.cap_hits = (uint32_t)std::min<uint64_t>(cap_hits, 0xFFFFFFF0ull);
+    CU(launch_shard_join(b->ix->dev, so, b->p.hdist_th, b->d_counters, b->d_stats, b->ix->sms, s));
+    CU(cudaMemcpyAsync(hb + src + 1, b->so.sc, 4, cudaMemcpyDeviceToHost, s));
+  }
+  b->clk.tick("join_kernel (as shard owner)", s);
+  CU(cudaMemcpyAsync(b->h_counters, b->d_counters, 32, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  for (uint32_t src = 0; src <= n_sources; ++src) hit_offsets[src] = hb[src];
+  if (b->h_counters[2] & kErrHitOverflow)
+    return fail(KREPP_ERR_CAPACITY, "the joins produce %llu hit entries but the buffer holds %llu", (unsigned long long)hb[n_sources], (unsigned long long)cap_hits);
+  return KREPP_OK;
+}
+
+int krepp_shard_finish(krepp_batch_t* b, const void* d_hits, uint64_t n_hits)
+{
+  if (!b || (!d_hits && n_hits)) return fail(KREPP_ERR_ARG, "krepp_shard_finish: null argument");
+  if (!b->sorted || !b->in_bases) return fail(KREPP_ERR_ARG, "krepp_shard_finish: krepp_shard_lookup has not run on this slot");
+  if (n_hits > 0xFFFFFFF0ull) return fail(KREPP_ERR_CAPACITY, "batch produces too many hit entries; submit fewer reads per batch");
+  if (cudaSetDevice(b->ix->device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice failed");
+  CU(cudaStreamSynchronize(b->stream));
+  if (n_hits > b->so.cap_hits) { if (int rc = alloc_hits(b, n_hits + n_hits / 8 + 4096)) return rc; }
+  static const uint4 none = {0, 0, 0, 0};
+  b->shard_hits = n_hits ? d_hits : &none; b->shard_n_hits = n_hits; // (with no hits the pointer is never dereferenced)
+  CU(cudaMemcpyAsync(b->d_stats + 4, b->d_stats, 32, cudaMemcpyDeviceToDevice, b->stream));
+  b->clk.tick("(exchange of hit entries)", b->stream);
+  if (int rc = enqueue(b)) return rc;
+  b->submitted = true;
   return KREPP_OK;
 }
 

@@ -29,6 +29,7 @@ struct DevIndex {
   const uint32_t* subtree;  // by se: number of nodes in the subtree rooted there (post-order => se range (se-subtree, se])
   uint64_t nkmers;
   uint32_t nrows, nsubsets, nnodes, nleaves;
+  uint32_t row0, nrows_local; // bucket-range shard (SURVEY.md 8e mode B): cmer / inc32 cover rows [row0, row0 + nrows_local) only
   uint32_t k, h, m, m_shift; // m_shift = log2(m) when m is a power of two, else 0xffffffff
   uint32_t local_expand;    // 1 when the deepest colour DAG fits the lane-private expansion stack
   const uint4* lut;         // [bytes of the k-mer word][256]: {rix fwd, q fwd, rix rc, q rc} parts (match.cu lut_pext)
@@ -93,7 +94,8 @@ struct SortArgs {
 
 constexpr uint32_t kErrRecOverflow = 1u, kErrStackOverflow = 2u, kErrPlaceOverflow = 4u;
 constexpr uint32_t kErrLookupOverflow = 8u, kErrHitOverflow = 16u, kErrSortFallback = 32u; // sorted pipeline: grow tuples / grow hits / redo the batch with the fused kernel
-constexpr uint32_t kErrRedo = kErrRecOverflow | kErrStackOverflow | kErrLookupOverflow | kErrHitOverflow | kErrSortFallback; // records are incomplete: later kernels skip, the host re-runs the batch
+constexpr uint32_t kErrShardData = 64u; // mode B: a hit entry names a read outside the batch (the caller mixed up its exchange buffers)
+constexpr uint32_t kErrRedo = kErrRecOverflow | kErrStackOverflow | kErrLookupOverflow | kErrHitOverflow | kErrSortFallback | kErrShardData; // records are incomplete: later kernels skip, the host re-runs the batch
 
 struct SolveArgs {
   uint32_t n_reads, th, k, h;

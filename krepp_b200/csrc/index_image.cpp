@@ -228,8 +228,10 @@ std::vector<BitRun> runs_of(uint64_t mask)
 
 } // namespace
 
-std::string HostIndex::load(const std::string& dir)
+std::string HostIndex::load(const std::string& dir, uint32_t shard_id, uint32_t shard_count)
 {
+  if (!shard_count || shard_id >= shard_count) return "Bad shard arguments for the index!";
+  shard = shard_id; nshards = shard_count;
   // group files by suffix the way TargetIndex::load_index does (ref src/krepp.cpp:72-91)
   std::vector<std::string> suffixes;
   DIR* d = opendir(dir.c_str());
@@ -271,16 +273,7 @@ std::string HostIndex::load(const std::string& dir)
   if (!slurp(dir + "/tree" + sfx, buf)) return "Failed to open " + dir + "/tree" + sfx + " (indexes without a backbone tree are not supported by the GPU path yet)";
   if (std::string err = tree.parse(buf); !err.empty()) return err;
 
-  // ---- cmer / inc
-  {
-    std::ifstream f(dir + "/cmer" + sfx, std::ios::binary);
-    if (!f.is_open()) return "Failed to open " + dir + "/cmer" + sfx;
-    f.read(reinterpret_cast<char*>(&nkmers), 8);
-    if (!f.good()) return "Failed to read the k-mer vector of a partial index!";
-    cmer.resize(nkmers);
-    f.read(reinterpret_cast<char*>(cmer.data()), (std::streamsize)(nkmers * 8));
-    if (!f.good() && nkmers) return "Failed to read the k-mer vector of a partial index!";
-  }
+  // ---- inc, then the shard's slice of cmer
   {
     std::ifstream f(dir + "/inc" + sfx, std::ios::binary);
     if (!f.is_open()) return "Failed to open " + dir + "/inc" + sfx;
@@ -291,6 +284,12 @@ std::string HostIndex::load(const std::string& dir)
     inc.resize(nrows);
     f.read(reinterpret_cast<char*>(inc.data()), (std::streamsize)((uint64_t)nrows * 8));
     if (!f.good() && nrows) return "Failed to read the offset array of a partial index!";
+  }
+  {
+    std::ifstream f(dir + "/cmer" + sfx, std::ios::binary);
+    if (!f.is_open()) return "Failed to open " + dir + "/cmer" + sfx;
+    f.read(reinterpret_cast<char*>(&nkmers), 8);
+    if (!f.good()) return "Failed to read the k-mer vector of a partial index!";
     uint64_t prev = 0;
     double s1 = 0, s2 = 0;
     for (uint64_t v : inc) {
@@ -298,9 +297,25 @@ std::string HostIndex::load(const std::string& dir)
       const double len = (double)(v - prev);
       s1 += len; s2 += len * len; prev = v;
     }
-    if (nkmers < (1ull << 32)) { inc32.resize(nrows); for (size_t i = 0; i < inc.size(); ++i) inc32[i] = (uint32_t)inc[i]; }
     mean_bucket = nrows ? s1 / nrows : 0;
     size_biased_bucket = s1 > 0 ? s2 / s1 : 0;
+    // shard g starts at the first row whose bucket ends beyond g/nshards of the entries: contiguous row ranges of (nearly)
+    // equal cmer bytes, the same on every rank because they depend on inc-* alone
+    row_splits.assign(nshards + 1, 0);
+    for (uint32_t g = 1; g < nshards; ++g) {
+      const uint64_t target = (uint64_t)((unsigned __int128)nkmers * g / nshards);
+      const uint32_t at = (uint32_t)(std::upper_bound(inc.begin(), inc.end(), target) - inc.begin());
+      row_splits[g] = std::max(row_splits[g - 1], std::min(at, nrows));
+    }
+    row_splits[nshards] = nrows;
+    row0 = row_splits[shard]; row1 = row_splits[shard + 1];
+    ent0 = row0 ? inc[row0 - 1] : 0;
+    const uint64_t ent1 = row1 ? inc[row1 - 1] : 0;
+    cmer.resize(ent1 - ent0);
+    f.seekg((std::streamoff)(8 + 8 * ent0));
+    f.read(reinterpret_cast<char*>(cmer.data()), (std::streamsize)(cmer.size() * 8));
+    if (!f.good() && !cmer.empty()) return "Failed to read the k-mer vector of a partial index!";
+    if (ent1 - ent0 < (1ull << 32)) { inc32.resize(row1 - row0); for (uint32_t i = row0; i < row1; ++i) inc32[i - row0] = (uint32_t)(inc[i] - ent0); }
   }
   // every rix the hash can produce must address a row below nrows (ref src/krepp.cpp:5-16 set_nrows)
   {

@@ -55,8 +55,13 @@ struct HostIndex {
   static constexpr uint64_t kMaxFlatLeaves = 1ull << 30;
   double mean_bucket = 0, size_biased_bucket = 0;
   HostTree tree;
+  // Bucket-range shard held by this image (SURVEY.md 8e mode B): rows [row0, row1) of the table, entries [ent0, ent0 +
+  // cmer.size()) of cmer-*; `inc32` then holds row1 - row0 ends relative to ent0.  One shard = the whole table.
+  uint32_t shard = 0, nshards = 1, row0 = 0, row1 = 0;
+  uint64_t ent0 = 0;
+  std::vector<uint32_t> row_splits;           // [nshards + 1] first row of every shard; equal cmer bytes per shard
   // Returns "" on success, else an error message (the reference's wording where it has one).
-  std::string load(const std::string& dir);
+  std::string load(const std::string& dir, uint32_t shard = 0, uint32_t nshards = 1);
 };
 
 } // namespace krepp

@@ -19,6 +19,10 @@ cudaError_t launch_match(const DevIndex& ix, const MatchArgs& a, int resident_wa
 // sorted.cu: the bucket-sorted form of the match stage (same outputs as launch_match)
 int sorted_resolve_warps(int sms);
 cudaError_t launch_match_sorted(const DevIndex& ix, const MatchArgs& a, const SortArgs& s, int sms, bool tap, cudaStream_t stream, uint32_t* launches, StageClock* clk = nullptr);
+// mode B: the chain of launch_match_sorted cut at its two exchange points
+cudaError_t launch_shard_lookup(const DevIndex& ix, const MatchArgs& a, const SortArgs& s, int sms, bool tap, cudaStream_t stream, StageClock* clk = nullptr);
+cudaError_t launch_shard_join(const DevIndex& ix, const SortArgs& s, uint32_t th, uint32_t* counters, unsigned long long* stats, int sms, cudaStream_t stream);
+cudaError_t launch_shard_finish(const DevIndex& ix, const MatchArgs& a, const SortArgs& s, int sms, cudaStream_t stream, StageClock* clk = nullptr);
 cudaError_t launch_solve(const SolveArgs& a, const LlhTables& tab, int sms, cudaStream_t stream, StageClock* clk = nullptr);
 constexpr int kPlaceWarpsPerCta = 4;
 cudaError_t launch_place(const PlaceArgs& a, const LlhTables& tab, int grid, cudaStream_t stream);

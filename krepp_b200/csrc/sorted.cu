@@ -202,7 +202,7 @@ __device__ __noinline__ void join_flush(JoinWarpSmem* w, const SortArgs s, uint3
 
 // One block of up to 32 queries (in w->qs) against the E entries each lane holds.  thr[e] is the Hamming threshold, or
 // -1 for a register slot that holds no entry.
-template <int E>
+template <int E, bool COUNT>
 __device__ __forceinline__ void join_block(JoinWarpSmem* w, const SortArgs& s, uint32_t* counters, const uint32_t (&enc)[4], const uint32_t (&se)[4],
                                            const int (&thr)[4], uint32_t cnt)
 {
@@ -225,7 +225,7 @@ __device__ __forceinline__ void join_block(JoinWarpSmem* w, const SortArgs& s, u
           if (hd[e] <= thr[e]) {
             const uint32_t at = atomicAdd(&w->hq_n, 1u);
             w->hq[at] = make_uint4(t.y, meta | (uint32_t)hd[e], se[e], 0u);
-            atomicAdd(&s.hit_count[t.y], 1u);
+            if (COUNT) atomicAdd(&s.hit_count[t.y], 1u);
           }
       }
       __syncwarp();
@@ -234,10 +234,15 @@ __device__ __forceinline__ void join_block(JoinWarpSmem* w, const SortArgs& s, u
   }
 }
 
+// COUNT: also count the hit entries of every read (the batch's own reads).  Without it the rows are those of a bucket-range
+// shard and the queries another rank's (SURVEY.md 8e mode B): s.row_begin is then the sender's slice for these rows, still
+// holding positions in the sender's list, so everything is taken relative to its first element.
+template <bool COUNT>
 __global__ void __launch_bounds__(kJoinWarps * 32) join_kernel(const DevIndex ix, const SortArgs s, uint32_t th, uint32_t* counters, unsigned long long* stats)
 {
   __shared__ JoinWarpSmem jsm[kJoinWarps];
-  if (s.row_begin[s.nrows] > s.cap_lookups) return; // flagged by the lookup kernel
+  const uint32_t rb0 = s.row_begin[0];
+  if (s.row_begin[s.nrows] - rb0 > s.cap_lookups) return; // flagged by the lookup kernel
   const uint32_t lane = threadIdx.x & 31;
   JoinWarpSmem* w = &jsm[threadIdx.x >> 5];
   if (lane == 0) w->hq_n = 0;
@@ -251,7 +256,7 @@ __global__ void __launch_bounds__(kJoinWarps * 32) join_kernel(const DevIndex ix
     const uint32_t row = r0 + lane; // every lane describes one row of the claim
     uint32_t qb = 0, qe = 0, eb = 0, ee = 0;
     if (row < s.nrows) {
-      qb = s.row_begin[row]; qe = s.row_begin[row + 1];
+      qb = s.row_begin[row] - rb0; qe = s.row_begin[row + 1] - rb0;
       if (qe > qb) { eb = row ? __ldg(&ix.inc32[row - 1]) : 0u; ee = __ldg(&ix.inc32[row]); } // ref src/index.cpp:160-168, src/table.hpp:121-136
     }
     st_entries += (unsigned long long)(qe - qb) * (ee - eb);
@@ -277,10 +282,10 @@ __global__ void __launch_bounds__(kJoinWarps * 32) join_kernel(const DevIndex ix
           if (lane < cnt) w->qs[lane] = s.tuples[rqb + q0 + lane];
           __syncwarp();
           switch (E) {
-            case 1: join_block<1>(w, s, counters, enc, se, thr, cnt); break;
-            case 2: join_block<2>(w, s, counters, enc, se, thr, cnt); break;
-            case 3: join_block<3>(w, s, counters, enc, se, thr, cnt); break;
-            default: join_block<4>(w, s, counters, enc, se, thr, cnt); break;
+            case 1: join_block<1, COUNT>(w, s, counters, enc, se, thr, cnt); break;
+            case 2: join_block<2, COUNT>(w, s, counters, enc, se, thr, cnt); break;
+            case 3: join_block<3, COUNT>(w, s, counters, enc, se, thr, cnt); break;
+            default: join_block<4, COUNT>(w, s, counters, enc, se, thr, cnt); break;
           }
         }
       }
@@ -302,6 +307,17 @@ __global__ void __launch_bounds__(256) hit_scatter_kernel(const DevIndex ix, con
     const uint32_t pos = atomicAdd(&s.hit_cursor[h.x], 1u);
     const uint32_t cs = __ldg(&ix.cbeg[h.z]), ce = __ldg(&ix.cbeg[h.z + 1]);
     s.hits[pos] = make_uint4(cs, ce - cs, h.y, 0u);
+  }
+}
+
+// mode B, home side: the hit entries came back from the shard owners in no particular order; count them per read
+__global__ void __launch_bounds__(256) hit_count_kernel(const SortArgs s, uint32_t n_reads, uint32_t* counters)
+{
+  const uint32_t n = s.sc[0];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t read = s.hits_tmp[i].x;
+    if (read < n_reads) atomicAdd(&s.hit_count[read], 1u);
+    else atomicOr(counters + 2, kErrShardData); // not a hit entry of this batch
   }
 }
 
@@ -553,7 +569,7 @@ cudaError_t launch_match_sorted(const DevIndex& ix, const MatchArgs& a, const So
   if (clk) clk->tick("scan(rows)", stream);
   if ((e = launch_lookup<true>(ix, a, s, sms, false, stream)) != cudaSuccess) return e;
   if (clk) clk->tick("lookup_kernel<scatter>", stream);
-  join_kernel<<<sms * 8, kJoinWarps * 32, 0, stream>>>(ix, s, a.th, a.counters, a.stats);
+  join_kernel<true><<<sms * 8, kJoinWarps * 32, 0, stream>>>(ix, s, a.th, a.counters, a.stats);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   if (clk) clk->tick("join_kernel", stream);
   if ((e = exclusive_scan(s.hit_count, a.n_reads, s.partials, s.hit_begin, s.hit_cursor, stream)) != cudaSuccess) return e;
@@ -567,6 +583,60 @@ cudaError_t launch_match_sorted(const DevIndex& ix, const MatchArgs& a, const So
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   if (clk) clk->tick("resolve_kernel", stream);
   if (launches) *launches = 11;
+  return cudaSuccess;
+}
+
+// ---------------------------------------------------------------------------------------------------- mode B
+// The same chain cut at its two exchange points.  Home rank: L1, S1, L2 -> tuples grouped by row, so the tuples of every
+// shard's row range are one contiguous run.  Owner rank: J over one sender's run against its slice of the table, hit entries
+// appended to one list.  Home rank again: hit entries of its reads from all owners -> S2, R.  All entries that can match a
+// lookup live in one bucket, hence on one owner, and R orders a read's hits itself, so the records are those of the
+// unsharded chain bit for bit.
+
+cudaError_t launch_shard_lookup(const DevIndex& ix, const MatchArgs& a, const SortArgs& s, int sms, bool tap, cudaStream_t stream, StageClock* clk)
+{
+  cudaError_t e;
+  if ((e = cudaMemsetAsync(s.row_count, 0, 4ull * s.nrows, stream)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(s.sc, 0, 32, stream)) != cudaSuccess) return e;
+  if (!a.n_reads) return cudaMemsetAsync(s.row_begin, 0, 4ull * (s.nrows + 1), stream);
+  if ((e = launch_lookup<false>(ix, a, s, sms, tap, stream)) != cudaSuccess) return e;
+  if (clk) clk->tick("lookup_kernel<count>", stream);
+  if ((e = exclusive_scan(s.row_count, s.nrows, s.partials, s.row_begin, s.row_cursor, stream)) != cudaSuccess) return e;
+  if (clk) clk->tick("scan(rows)", stream);
+  if ((e = launch_lookup<true>(ix, a, s, sms, false, stream)) != cudaSuccess) return e;
+  if (clk) clk->tick("lookup_kernel<scatter>", stream);
+  return cudaSuccess;
+}
+
+// s.row_begin / s.tuples: one sender's slice for this shard's rows; s.nrows = rows of the shard; s.sc[0] keeps counting hits
+cudaError_t launch_shard_join(const DevIndex& ix, const SortArgs& s, uint32_t th, uint32_t* counters, unsigned long long* stats, int sms, cudaStream_t stream)
+{
+  cudaError_t e;
+  if (!s.nrows) return cudaSuccess;
+  if ((e = cudaMemsetAsync(s.sc + 1, 0, 4, stream)) != cudaSuccess) return e;
+  join_kernel<false><<<sms * 8, kJoinWarps * 32, 0, stream>>>(ix, s, th, counters, stats);
+  return cudaGetLastError();
+}
+
+// s.hits_tmp: the n_hits hit entries of this batch's reads (s.sc[0] already holds n_hits)
+cudaError_t launch_shard_finish(const DevIndex& ix, const MatchArgs& a, const SortArgs& s, int sms, cudaStream_t stream, StageClock* clk)
+{
+  cudaError_t e;
+  if (!a.n_reads) return cudaSuccess;
+  if ((e = cudaMemsetAsync(s.hit_count, 0, 4ull * a.n_reads, stream)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(s.sc + 4, 0, 4, stream)) != cudaSuccess) return e;
+  hit_count_kernel<<<sms * 8, 256, 0, stream>>>(s, a.n_reads, a.counters);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if ((e = exclusive_scan(s.hit_count, a.n_reads, s.partials, s.hit_begin, s.hit_cursor, stream)) != cudaSuccess) return e;
+  hit_scatter_kernel<<<sms * 8, 256, 0, stream>>>(ix, s, a.counters);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if (clk) clk->tick("hit_count+scan(hits)+hit_scatter_kernel", stream);
+  uint32_t rank_bits = 0;
+  while ((1ull << rank_bits) < ix.nleaves) ++rank_bits;
+  rank_bits += s.extra_rank_bits;
+  resolve_kernel<<<sorted_resolve_warps(sms) / kResWarps, kResWarps * 32, 0, stream>>>(ix, a, s, rank_bits);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if (clk) clk->tick("resolve_kernel", stream);
   return cudaSuccess;
 }
 

@@ -48,3 +48,153 @@ def gather_text(text: str) -> list[str]:
     out = [None] * dist.get_world_size()
     dist.all_gather_object(out, text)
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Mode B: the index is larger than one GPU's HBM, so the table is split by LSH bucket (row) range over the
+# ranks and the data path has two real exchange steps -- lookups to the shard that owns their bucket, hit entries back to
+# the read's home rank.  The kernels and the cut points live in the library (krepp_shard_lookup / _join / _finish,
+# include/krepp_b200.h); this file only moves the bytes: torch.distributed all_to_all_single (NCCL over NVLink on GPUs),
+# or, for several logical ranks inside one process (tests on a single GPU), plain tensor hand-over.
+
+TUPLE_WORDS = 4  # a lookup tuple and a hit entry are both 4 x u32
+
+
+def exchange_v(send, send_counts, group=None):
+    """All-to-all-v of the rows of `send` (a [n, w] tensor, rank g's rows contiguous, send_counts[g] of them).
+    Returns (recv, recv_counts): the rows every rank sent here, in rank order."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    sc = torch.as_tensor([int(c) for c in send_counts], dtype=torch.int64, device=send.device)
+    rc = torch.empty(world, dtype=torch.int64, device=send.device)
+    dist.all_to_all_single(rc, sc, group=group)
+    recv_counts = [int(x) for x in rc.tolist()]
+    recv = torch.empty((sum(recv_counts),) + tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
+    dist.all_to_all_single(recv, send[:sum(int(c) for c in send_counts)], output_split_sizes=recv_counts,
+                           input_split_sizes=[int(c) for c in send_counts], group=group)
+    return recv, recv_counts
+
+
+class ShardRank:
+    """One rank of a mode-B job: its shard of the index on its GPU, one batch slot, and the device buffers of the two
+    exchanges.  The three phases below are the library's; `ShardedJob` strings them together with the exchanges."""
+
+    def __init__(self, index_dir: str, device: int, rank: int, world: int, max_reads: int, max_bases: int, **batch_kw):
+        import numpy as np
+        import torch
+        from .capi import Index, IBatch
+        self.torch, self.rank, self.world = torch, rank, world
+        self.dev = torch.device("cuda", device)
+        with torch.cuda.device(self.dev):
+            self.index = Index(index_dir, device, shard=rank, nshards=world)
+            self.slot = IBatch(self.index, np.zeros((0, 1), np.uint8), capacity=(max_reads, max_bases), **batch_kw)
+            self.nrows = int(self.index.info.nrows)
+            self.splits = [int(x) for x in self.index.row_splits]
+            self.row_begin = torch.empty(self.nrows + 1, dtype=torch.int32, device=self.dev)
+            # 2 strands x one window per base, of which (r+1)/m are eligible on average
+            frac = (self.index.info.r + 1) / self.index.info.m if self.index.info.frac else 1.0 / self.index.info.m
+            self.tuples = torch.empty((int(max_bases * 2 * frac * 1.1) + 4096, TUPLE_WORDS), dtype=torch.int32, device=self.dev)
+            self.hits = torch.empty((max(96 * max_reads, 65536), TUPLE_WORDS), dtype=torch.int32, device=self.dev)
+        self._keep = None
+
+    # phase 1 (home): reads -> tuples grouped by row; what goes to every owner
+    def lookup(self, d_bases, d_offsets, n_reads: int):
+        from .capi import CapacityError
+        torch = self.torch
+        with torch.cuda.device(self.dev):
+            while True:
+                try:
+                    so = self.slot.shard_lookup(d_bases.data_ptr(), d_offsets.data_ptr(), n_reads, d_bases.numel(), self.tuples.data_ptr(),
+                                                self.tuples.shape[0], self.row_begin.data_ptr())
+                    break
+                except CapacityError as e:
+                    self.tuples = torch.empty((e.demand + e.demand // 10 + 4096, TUPLE_WORDS), dtype=torch.int32, device=self.dev)
+            counts = [int(so[g + 1] - so[g]) for g in range(self.world)]
+            # owner g needs row_begin[splits[g] .. splits[g+1]] inclusive: neighbouring slices share one word, so they are
+            # laid out one after the other for the all-to-all
+            rb = torch.cat([self.row_begin[self.splits[g]:self.splits[g + 1] + 1] for g in range(self.world)])
+            rb_counts = [self.splits[g + 1] - self.splits[g] + 1 for g in range(self.world)]
+        return self.tuples, counts, rb, rb_counts
+
+    # phase 2 (owner): every sender's tuples against this shard -> hit entries, sender by sender
+    def join(self, recv_tuples, recv_counts, recv_rb):
+        from .capi import CapacityError
+        torch = self.torch
+        nloc = self.splits[self.rank + 1] - self.splits[self.rank] + 1
+        tp, rp, at = [], [], 0
+        for s in range(self.world):
+            tp.append(recv_tuples.data_ptr() + 16 * at)  # a tuple is 16 bytes
+            rp.append(recv_rb.data_ptr() + 4 * nloc * s)
+            at += recv_counts[s]
+        with torch.cuda.device(self.dev):
+            torch.cuda.current_stream().synchronize()  # the exchange ran on torch's stream, the library has its own
+            while True:
+                try:
+                    ho = self.slot.shard_join(tp, rp, self.hits.data_ptr(), self.hits.shape[0])
+                    break
+                except CapacityError as e:
+                    self.hits = torch.empty((e.demand + e.demand // 8 + 4096, TUPLE_WORDS), dtype=torch.int32, device=self.dev)
+        return self.hits, [int(ho[s + 1] - ho[s]) for s in range(self.world)]
+
+    # phase 3 (home): the batch's hit entries from all owners -> records (enqueued; results() waits)
+    def finish(self, recv_hits):
+        self._keep = recv_hits  # must stay alive until the wait
+        with self.torch.cuda.device(self.dev):
+            self.torch.cuda.current_stream().synchronize()
+            self.slot.shard_finish(recv_hits.data_ptr(), recv_hits.shape[0])
+
+    def results(self) -> dict:
+        with self.torch.cuda.device(self.dev):
+            r = self.slot.wait()
+        self._keep = None
+        return r
+
+    def close(self):
+        self.slot.close()
+        self.index.close()
+
+
+class ShardedJob:
+    """Runs batches through mode B.  `ranks` is the list of ShardRank objects living in THIS process: one (its peers are
+    other processes, exchanges go through torch.distributed) or all of them (logical ranks on one GPU, exchanges are
+    tensor hand-overs)."""
+
+    def __init__(self, ranks, group=None):
+        self.ranks, self.group = ranks, group
+        self.local = len(ranks) > 1 or ranks[0].world == 1
+        if self.local:
+            assert [r.rank for r in ranks] == list(range(ranks[0].world)), "an in-process job holds every rank"
+        self.bytes_exchanged = 0
+
+    def _exchange(self, sends):
+        """sends[i] = (tensor, counts) of in-process rank i -> [(recv tensor, recv counts)] per in-process rank."""
+        import torch
+        if not self.local:
+            t, c = sends[0]
+            recv, rc = exchange_v(t, c, self.group)
+            self.bytes_exchanged += recv.numel() * recv.element_size()
+            return [(recv, rc)]
+        out = []
+        for j in range(len(self.ranks)):
+            parts, rc = [], []
+            for t, c in sends:
+                o = sum(c[:j])
+                parts.append(t[o:o + c[j]])
+                rc.append(c[j])
+            recv = torch.cat(parts)
+            self.bytes_exchanged += recv.numel() * recv.element_size()
+            out.append((recv, rc))
+        return out
+
+    def run(self, batches):
+        """batches[i] = (d_bases uint8 tensor, d_offsets int64 tensor, n_reads) of in-process rank i.  Returns the result
+        dicts (krepp_batch_wait) in the same order."""
+        p1 = [r.lookup(*b) for r, b in zip(self.ranks, batches)]
+        tup = self._exchange([(t, c) for t, c, _, _ in p1])
+        rbs = self._exchange([(rb.view(-1, 1), rc) for _, _, rb, rc in p1])
+        p2 = [r.join(t, c, rb.view(-1)) for r, (t, c), (rb, _) in zip(self.ranks, tup, rbs)]
+        back = self._exchange(p2)
+        for r, (h, _) in zip(self.ranks, back):
+            r.finish(h)
+        return [r.results() for r in self.ranks]
