@@ -224,8 +224,11 @@ def shard_arm(args) -> None:
                 src = stage
             else:
                 src = d_bases[first * READ_LEN:]
-            r = job.run([(src[:cnt * READ_LEN + 64], d_offs, cnt)])[0]
-            nrec += len(r["records"]); d2h += r["reads"].nbytes + r["records"].nbytes + r["hist"].nbytes
+            r = job.run([(src[:cnt * READ_LEN + 64], d_offs, cnt)], rows=from_host)[0]
+            if from_host:
+                nrec += len(r["records"]); d2h += r["reads"].nbytes + r["records"].nbytes + r["hist"].nbytes
+            else:
+                nrec += r["n_records"]
             ab = me.slot.algorithmic_bytes()
             for k in alg:
                 alg[k] += ab[k]

@@ -158,6 +158,12 @@ int krepp_batch_submit_device(krepp_batch_t* b, const char* d_bases, const uint6
  * on this slot).  Replaces reading IBatch::node_to_minfo / get_summary() (src/query.hpp:64,95). */
 int krepp_batch_wait(krepp_batch_t* b, krepp_results_t* out);
 
+/* The same wait (including the grow-and-rerun of a batch whose result buffers were too small) without copying the record,
+ * histogram and placement rows to the host: `reads` (40 bytes per read) and the counts are valid, the three row pointers
+ * are NULL and the rows stay in HBM.  For callers that only need the per-read summaries, and for timing the kernels
+ * without the PCIe transfer of the rows. */
+int krepp_batch_wait_device(krepp_batch_t* b, krepp_results_t* out);
+
 /* Parity taps (SURVEY.md section 8b "dump_stage").  stage 1: every eligible lookup of the last submitted batch as
  * 4 x u32 {read, strand<<31|pos, rix, enc32}, unordered (src/query.cpp:82-91 arguments of add_matching_mer).
  * Must be enabled before submit with krepp_batch_enable_tap.  Returns the number of items through *n.

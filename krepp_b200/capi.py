@@ -108,6 +108,7 @@ def load_library():
     L.krepp_batch_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
     L.krepp_batch_submit_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64]
     L.krepp_batch_wait.argtypes = [C.c_void_p, C.POINTER(Results)]
+    L.krepp_batch_wait_device.argtypes = [C.c_void_p, C.POINTER(Results)]
     L.krepp_batch_enable_tap.argtypes = [C.c_void_p, C.c_int, C.c_uint64]
     L.krepp_batch_read_tap.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.krepp_batch_algorithmic_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
@@ -292,6 +293,13 @@ class IBatch:
             placements=_view(r.placements, PLACEMENT_DTYPE, int(r.n_placements)), gpu_ms=float(r.gpu_ms), match_ms=float(r.match_ms),
             gpu_launches=int(r.gpu_launches))
         return self._res
+
+    def wait_device(self) -> dict:
+        """krepp_batch_wait_device: per-read summaries and counts only; record / placement rows stay in HBM."""
+        r = Results()
+        _check(load_library().krepp_batch_wait_device(self._h, C.byref(r)))
+        return dict(reads=_view(r.reads, READ_DTYPE, r.n_reads), n_records=int(r.n_records), n_placements=int(r.n_placements),
+                    gpu_ms=float(r.gpu_ms), match_ms=float(r.match_ms), gpu_launches=int(r.gpu_launches))
 
     def results(self) -> dict:
         if self._res is None:

@@ -157,8 +157,10 @@ struct krepp_batch {
   uint32_t* h_counters = nullptr; unsigned long long* h_stats = nullptr;
   // placement (K5)
   uint32_t place_cap = 0, place_warps = 0;
-  uint32_t *d_place_begin = nullptr, *d_place_count = nullptr, *d_node_bitmap = nullptr, *d_node_list = nullptr, *d_node_cand = nullptr;
-  double *d_node_d = nullptr, *d_node_v = nullptr, *d_node_chisq = nullptr;
+  uint32_t *d_place_begin = nullptr, *d_place_count = nullptr, *d_node_bitmap = nullptr, *d_node_list = nullptr;
+  uint32_t node_cap = 0;      // tree nodes touched by a batch (place_collect_kernel's entries)
+  uint32_t *d_pn_read = nullptr, *d_pn_se = nullptr, *d_pn_flags = nullptr, *d_pn_work = nullptr, *d_pn_begin = nullptr, *d_pn_count = nullptr;
+  double *d_pn_mc = nullptr, *d_pn_uc = nullptr, *d_pn_rho = nullptr, *d_pn_d = nullptr, *d_pn_v = nullptr, *d_pn_chisq = nullptr;
   krepp_placement_t *d_place = nullptr, *h_place = nullptr;
   // bucket-sorted pipeline (sorted.cu)
   bool sorted = false, fused_once = false;
@@ -341,6 +343,22 @@ static int alloc_placements(krepp_batch* b, uint32_t cap)
   return KREPP_OK;
 }
 
+static int alloc_place_nodes(krepp_batch* b, uint64_t cap)
+{
+  if (cap > 0x7FFFFFFFull) return fail(KREPP_ERR_CAPACITY, "batch touches too many tree nodes; submit fewer reads per batch");
+  for (void* p : {(void*)b->d_pn_read, (void*)b->d_pn_se, (void*)b->d_pn_flags, (void*)b->d_pn_work, (void*)b->d_pn_mc, (void*)b->d_pn_uc, (void*)b->d_pn_rho,
+                  (void*)b->d_pn_d, (void*)b->d_pn_v, (void*)b->d_pn_chisq})
+    if (p) cudaFree(p);
+  b->d_pn_read = b->d_pn_se = b->d_pn_flags = b->d_pn_work = nullptr;
+  b->d_pn_mc = b->d_pn_uc = b->d_pn_rho = b->d_pn_d = b->d_pn_v = b->d_pn_chisq = nullptr;
+  b->node_cap = (uint32_t)cap;
+  const size_t stride = b->p.hdist_th + 1;
+  CU(cudaMalloc(&b->d_pn_read, 4ull * cap)); CU(cudaMalloc(&b->d_pn_se, 4ull * cap)); CU(cudaMalloc(&b->d_pn_flags, 4ull * cap)); CU(cudaMalloc(&b->d_pn_work, 4ull * cap));
+  CU(cudaMalloc(&b->d_pn_mc, 8ull * cap * stride)); CU(cudaMalloc(&b->d_pn_uc, 8ull * cap)); CU(cudaMalloc(&b->d_pn_rho, 8ull * cap));
+  CU(cudaMalloc(&b->d_pn_d, 8ull * cap)); CU(cudaMalloc(&b->d_pn_v, 8ull * cap)); CU(cudaMalloc(&b->d_pn_chisq, 8ull * cap));
+  return KREPP_OK;
+}
+
 static int alloc_records(krepp_batch* b, uint32_t cap)
 {
   free_records(b);
@@ -450,8 +468,9 @@ int krepp_batch_create(krepp_index_t* ix, const krepp_params_t* p, uint32_t max_
     const size_t pw = b->place_warps;
     CU(cudaMalloc(&b->d_place_begin, 4ull * max_reads)); CU(cudaMalloc(&b->d_place_count, 4ull * max_reads));
     CU(cudaMalloc(&b->d_node_bitmap, 4 * pw * nbm_nodes)); CU(cudaMemset(b->d_node_bitmap, 0, 4 * pw * nbm_nodes));
-    CU(cudaMalloc(&b->d_node_list, 4 * pw * nn)); CU(cudaMalloc(&b->d_node_cand, 4 * pw * nn));
-    CU(cudaMalloc(&b->d_node_d, 8 * pw * nn)); CU(cudaMalloc(&b->d_node_v, 8 * pw * nn)); CU(cudaMalloc(&b->d_node_chisq, 8 * pw * nn));
+    CU(cudaMalloc(&b->d_node_list, 4 * pw * nn));
+    CU(cudaMalloc(&b->d_pn_begin, 4ull * max_reads)); CU(cudaMalloc(&b->d_pn_count, 4ull * max_reads));
+    if (int rc = alloc_place_nodes(b, std::max<uint64_t>(32ull * max_reads, 4096))) return rc; // grown to the demand when a batch needs more
     if (int rc = alloc_placements(b, (uint32_t)std::min<uint64_t>(std::max<uint64_t>(8ull * max_reads, 4096), 0x7FFFFFFFull))) return rc;
   }
   return KREPP_OK;
@@ -466,8 +485,9 @@ void krepp_batch_destroy(krepp_batch_t* b)
   for (void* p : {(void*)b->d_bases, (void*)b->d_offsets, (void*)b->d_onmers, (void*)b->d_wn, (void*)b->d_hdfilt, (void*)b->d_rec_begin,
                   (void*)b->d_rec_count, (void*)b->d_closest, (void*)b->d_counters, (void*)b->d_stats, (void*)b->d_acc, (void*)b->d_bitmap,
                   (void*)b->d_marker, (void*)b->d_stack, (void*)b->d_tagctr, (void*)b->d_out_read, (void*)b->d_tap, (void*)b->d_tap_count, (void*)b->d_place_begin,
-                  (void*)b->d_place_count, (void*)b->d_node_bitmap, (void*)b->d_node_list, (void*)b->d_node_cand, (void*)b->d_node_d, (void*)b->d_node_v,
-                  (void*)b->d_node_chisq, (void*)b->d_place})
+                  (void*)b->d_place_count, (void*)b->d_node_bitmap, (void*)b->d_node_list, (void*)b->d_pn_begin, (void*)b->d_pn_count, (void*)b->d_pn_read,
+                  (void*)b->d_pn_se, (void*)b->d_pn_flags, (void*)b->d_pn_work, (void*)b->d_pn_mc, (void*)b->d_pn_uc, (void*)b->d_pn_rho, (void*)b->d_pn_d,
+                  (void*)b->d_pn_v, (void*)b->d_pn_chisq, (void*)b->d_place})
     if (p) cudaFree(p);
   for (void* p : {(void*)b->so.row_count, (void*)b->so.row_begin, (void*)b->so.row_cursor, (void*)b->so.tuples, (void*)b->so.hits_tmp, (void*)b->so.hits,
                   (void*)b->so.hit_count, (void*)b->so.hit_begin, (void*)b->so.hit_cursor, (void*)b->so.partials, (void*)b->so.sc, (void*)b->so.keys_g})
@@ -540,12 +560,14 @@ static int enqueue(krepp_batch* b)
     pa.s = sa; pa.offsets = b->in_offsets; pa.tau = b->p.tau; pa.no_filter = b->p.no_filter; pa.chisq_value = b->p.chisq;
     pa.parent = ix->dev.parent; pa.nchildren = ix->dev.nchildren; pa.subtree = ix->dev.subtree; pa.blen = ix->dev.blen; pa.leaf_rank = ix->dev.leaf_rank;
     pa.nnodes = h.tree.nnodes;
-    pa.node_bitmap = b->d_node_bitmap; pa.node_list = b->d_node_list; pa.node_d = b->d_node_d; pa.node_v = b->d_node_v; pa.node_chisq = b->d_node_chisq;
-    pa.node_cand = b->d_node_cand; pa.placements = b->d_place; pa.place_cap = b->place_cap; pa.counters = b->d_counters;
+    pa.node_bitmap = b->d_node_bitmap; pa.node_list = b->d_node_list;
+    pa.node_cap = b->node_cap; pa.pn_read = b->d_pn_read; pa.pn_se = b->d_pn_se; pa.pn_flags = b->d_pn_flags; pa.pn_work = b->d_pn_work;
+    pa.pn_mc = b->d_pn_mc; pa.pn_uc = b->d_pn_uc; pa.pn_rho = b->d_pn_rho; pa.pn_d = b->d_pn_d; pa.pn_v = b->d_pn_v; pa.pn_chisq = b->d_pn_chisq;
+    pa.pn_begin = b->d_pn_begin; pa.pn_count = b->d_pn_count;
+    pa.placements = b->d_place; pa.place_cap = b->place_cap; pa.counters = b->d_counters;
     pa.place_begin = b->d_place_begin; pa.place_count = b->d_place_count;
-    CU(launch_place(pa, b->tab, (int)(b->place_warps / kPlaceWarpsPerCta), s));
-    b->clk.tick("place_kernel", s);
-    b->launches += 1;
+    CU(launch_place(pa, b->tab, (int)(b->place_warps / kPlaceWarpsPerCta), ix->sms, s, &b->clk));
+    b->launches += 4;
   }
   finalize_kernel<<<ix->sms * 4, 128, 0, s>>>(sa, b->d_out_rec, b->d_out_read, b->d_wn, b->d_place_begin, b->d_place_count);
   CU(cudaGetLastError());
@@ -612,7 +634,11 @@ int krepp_batch_submit_device(krepp_batch_t* b, const char* d_bases, const uint6
   return KREPP_OK;
 }
 
-int krepp_batch_wait(krepp_batch_t* b, krepp_results_t* out)
+static int wait_impl(krepp_batch_t* b, krepp_results_t* out, bool copy_rows);
+int krepp_batch_wait(krepp_batch_t* b, krepp_results_t* out) { return wait_impl(b, out, true); }
+int krepp_batch_wait_device(krepp_batch_t* b, krepp_results_t* out) { return wait_impl(b, out, false); }
+
+static int wait_impl(krepp_batch_t* b, krepp_results_t* out, bool copy_rows)
 {
   if (!b || !out) return fail(KREPP_ERR_ARG, "krepp_batch_wait: null argument");
   if (!b->submitted) return fail(KREPP_ERR_ARG, "krepp_batch_wait: nothing was submitted on this slot");
@@ -623,7 +649,7 @@ int krepp_batch_wait(krepp_batch_t* b, krepp_results_t* out)
     if (b->h_counters[2] & kErrShardData) return fail(KREPP_ERR_ARG, "krepp_shard_finish: a hit entry names a read outside the batch");
     if (b->shard_hits && (b->h_counters[2] & kErrSortFallback))
       return fail(KREPP_ERR_CAPACITY, "a read has more leaf hits than the bucket-sorted chain holds and a sharded index has no fused kernel to fall back to");
-    if (!(b->h_counters[2] & (kErrRecOverflow | kErrPlaceOverflow | kErrLookupOverflow | kErrHitOverflow | kErrSortFallback))) break;
+    if (!(b->h_counters[2] & (kErrRecOverflow | kErrPlaceOverflow | kErrNodeOverflow | kErrLookupOverflow | kErrHitOverflow | kErrSortFallback))) break;
     // a result buffer was too small: grow it to what the kernels asked for and run the batch again
     if (attempt >= 8) return fail(KREPP_ERR_CAPACITY, "result buffer overflow persists");
     if (b->h_counters[2] & kErrRecOverflow) {
@@ -640,6 +666,10 @@ int krepp_batch_wait(krepp_batch_t* b, krepp_results_t* out)
       if (int rc = alloc_hits(b, need + need / 4 + 4096)) return rc;
     }
     if (b->h_counters[2] & kErrSortFallback) b->fused_once = true; // a read outside the sorted pipeline's limits: this batch goes through the fused kernel
+    if (b->h_counters[2] & kErrNodeOverflow) { // counters[5] = tree nodes the batch touches
+      const uint64_t need = b->h_counters[5];
+      if (int rc = alloc_place_nodes(b, need + need / 8 + 4096)) return rc;
+    }
     if (b->h_counters[2] & kErrPlaceOverflow) {
       const uint64_t want = std::max<uint64_t>((uint64_t)b->h_counters[3] + b->h_counters[3] / 4, (uint64_t)b->place_cap + 4096);
       if (want > 0x7FFFFFFFull) return fail(KREPP_ERR_CAPACITY, "batch produces too many placements; submit fewer reads per batch");
@@ -649,17 +679,18 @@ int krepp_batch_wait(krepp_batch_t* b, krepp_results_t* out)
   }
   const uint32_t nrec = b->h_counters[0];
   const size_t stride = b->p.hdist_th + 1;
-  if (nrec) {
+  if (nrec && copy_rows) {
     CU(cudaMemcpyAsync(b->h_rec, b->d_out_rec, sizeof(krepp_record_t) * (size_t)nrec, cudaMemcpyDeviceToHost, b->stream));
     CU(cudaMemcpyAsync(b->h_hist, b->d_rec_hist, 4ull * nrec * stride, cudaMemcpyDeviceToHost, b->stream));
   }
   const uint32_t nplace = b->p.place ? b->h_counters[3] : 0;
-  if (nplace) CU(cudaMemcpyAsync(b->h_place, b->d_place, sizeof(krepp_placement_t) * (size_t)nplace, cudaMemcpyDeviceToHost, b->stream));
+  if (nplace && copy_rows) CU(cudaMemcpyAsync(b->h_place, b->d_place, sizeof(krepp_placement_t) * (size_t)nplace, cudaMemcpyDeviceToHost, b->stream));
   CU(cudaStreamSynchronize(b->stream));
   float ms = 0;
   CU(cudaEventElapsedTime(&ms, b->ev0, b->ev1));
   out->n_reads = b->n_reads; out->hist_stride = (uint32_t)stride; out->n_records = nrec; out->n_placements = nplace;
-  out->reads = b->h_read; out->records = b->h_rec; out->hist = b->h_hist; out->placements = nplace ? b->h_place : nullptr;
+  out->reads = b->h_read; out->records = copy_rows ? b->h_rec : nullptr; out->hist = copy_rows ? b->h_hist : nullptr;
+  out->placements = nplace && copy_rows ? b->h_place : nullptr;
   float mms = 0;
   CU(cudaEventElapsedTime(&mms, b->evm0, b->evm1));
   out->gpu_ms = ms; out->match_ms = mms; out->gpu_launches = b->launches;

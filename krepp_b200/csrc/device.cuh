@@ -94,6 +94,7 @@ struct SortArgs {
 
 constexpr uint32_t kErrRecOverflow = 1u, kErrStackOverflow = 2u, kErrPlaceOverflow = 4u;
 constexpr uint32_t kErrLookupOverflow = 8u, kErrHitOverflow = 16u, kErrSortFallback = 32u; // sorted pipeline: grow tuples / grow hits / redo the batch with the fused kernel
+constexpr uint32_t kErrNodeOverflow = 128u; // placement: the batch touches more tree nodes than PlaceArgs::node_cap
 constexpr uint32_t kErrShardData = 64u; // mode B: a hit entry names a read outside the batch (the caller mixed up its exchange buffers)
 constexpr uint32_t kErrRedo = kErrRecOverflow | kErrStackOverflow | kErrLookupOverflow | kErrHitOverflow | kErrSortFallback | kErrShardData; // records are incomplete: later kernels skip, the host re-runs the batch
 
@@ -120,15 +121,22 @@ struct PlaceArgs {
   // flattened tree (by se)
   const uint32_t* parent; const uint32_t* nchildren; const uint32_t* subtree; const double* blen; const uint32_t* leaf_rank;
   uint32_t nnodes;
-  // per-warp scratch
+  // per-warp scratch of the collect kernel
   uint32_t* node_bitmap;       // [warps][ceil((nnodes+1)/32)]
   uint32_t* node_list;         // [warps][nnodes]
-  double* node_d; double* node_v; double* node_chisq; uint32_t* node_cand;  // [warps][nnodes]
+  // tree nodes touched by the batch's reads (every selected leaf and all its ancestors), read by read, ascending se
+  uint32_t node_cap;
+  uint32_t* pn_read; uint32_t* pn_se; uint32_t* pn_flags;  // [node_cap]; flags: kPnSolve | kPnEligible | kPnCandidate
+  double* pn_mc;               // [node_cap * (th+1)] weighted histogram of an internal node (Minfo::add, ref src/query.hpp:139-152)
+  double* pn_uc; double* pn_rho; double* pn_d; double* pn_v; double* pn_chisq;  // [node_cap]
+  uint32_t* pn_work;           // [node_cap] entries whose likelihood has to be maximised
+  uint32_t* pn_begin; uint32_t* pn_count;  // [n_reads]
   // outputs
   void* placements;            // krepp_placement_t[place_cap]
   uint32_t place_cap;
-  uint32_t* counters;          // [3] placements reserved, [2] error flags
+  uint32_t* counters;          // [3] placements reserved, [2] error flags, [5] node entries reserved, [6] length of pn_work
   uint32_t* place_begin; uint32_t* place_count;  // [n_reads]
 };
+constexpr uint32_t kPnSolve = 1u, kPnEligible = 2u, kPnCandidate = 4u;
 
 } // namespace krepp

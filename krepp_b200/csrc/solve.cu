@@ -182,25 +182,28 @@ __global__ void __launch_bounds__(128) chisq_kernel(const SolveArgs a, const Llh
 // is the contiguous range (g - subtree[g], g], which makes "is leaf l below g" two comparisons.
 __device__ __forceinline__ double jukes_cantor(double d) { return -0.75 * log(1 - 4.0 / 3.0 * d); }
 
-__global__ void __launch_bounds__(128) place_kernel(const PlaceArgs a, const LlhTables tab)
+// The work is cut so that every Brent minimisation of the batch runs in one thread-per-item kernel with full warps (an
+// internal node costs as much as a record of K4, and a read with 20 selected leaves touches about a hundred nodes):
+//   place_collect_kernel  warp per read: gates, the single-reference shortcut, marked nodes in ascending se, one lane per
+//                         node accumulating its weighted histogram -> node entries + work list
+//   place_solve_kernel    thread per internal node entry: the same minimiser as solve_kernel
+//   place_chisq_kernel    thread per node entry: likelihood-ratio test against the closest reference
+//   place_emit_kernel     warp per read: candidates in ascending se, lwr, placement rows
+__global__ void __launch_bounds__(128) place_collect_kernel(const PlaceArgs a)
 {
   const SolveArgs& s = a.s;
   if (s.counters[2] & kErrRedo) return;
-  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t lane = threadIdx.x & 31, lt_mask = (1u << lane) - 1u;
   const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   const uint32_t stride = s.th + 1, nbm = (a.nnodes + 32) >> 5;
   uint32_t* bm = a.node_bitmap + (size_t)gwarp * nbm;
   uint32_t* list = a.node_list + (size_t)gwarp * a.nnodes;
-  double* nd_d = a.node_d + (size_t)gwarp * a.nnodes;
-  double* nd_v = a.node_v + (size_t)gwarp * a.nnodes;
-  double* nd_c = a.node_chisq + (size_t)gwarp * a.nnodes;
-  uint32_t* nd_k = a.node_cand + (size_t)gwarp * a.nnodes;
   krepp_placement_t* out = static_cast<krepp_placement_t*>(a.placements);
 
   for (uint32_t r = gwarp; r < s.n_reads; r += nwarps) {
     const uint32_t b = s.rec_begin[r], n = s.rec_count[r];
     const int32_t cl = s.closest[r];
-    uint32_t pbegin = 0, pcount = 0;
+    uint32_t pbegin = 0, pcount = 0, nbegin = 0, ncount = 0;
     if (cl >= 0) {
       // number of selected references; records are forward leaves by ascending se, then reverse leaves by ascending se
       uint32_t nsel = 0, nf = 0;
@@ -209,17 +212,13 @@ __global__ void __launch_bounds__(128) place_kernel(const PlaceArgs a, const Llh
       double leq_cl = 0; // Minfo::get_leq_tau of the closest (ref src/query.hpp:189-196)
       for (uint32_t x = 0; x <= a.tau && x < stride; ++x) leq_cl += (double)s.rec_hist[(size_t)cl * stride + x];
       const uint32_t cl_se = s.rec_slot[cl] & 0x7FFFFFFFu;
-      ObjectiveAny f_cl;
-      for (uint32_t x = 0; x <= (uint32_t)kMaxTh; ++x) f_cl.mc[x] = x < stride ? (double)s.rec_hist[(size_t)cl * stride + x] : 0.0;
-      f_cl.uc = (double)s.onmers[r] - (double)s.rec_match[cl]; f_cl.rho = s.rho[cl_se]; f_cl.k = s.k; f_cl.th = s.th;
-      const double v_cl = s.rec_v[cl];
       if (a.no_filter || leq_cl > 1.0) {
         if (nsel == 1) {
           if (lane == 0) {
             pbegin = atomicAdd(a.counters + 3, 1u); pcount = 1;
             if (pbegin < a.place_cap) {
               const double bl = a.blen[cl_se], mid = isnan(bl) ? 0.0 : bl / 2.0, d = s.rec_d[cl];
-              krepp_placement_t p; p.read = r; p.se = cl_se; p.pendant = jukes_cantor(d) - mid; p.distal = mid; p.loglik = -v_cl;
+              krepp_placement_t p; p.read = r; p.se = cl_se; p.pendant = jukes_cantor(d) - mid; p.distal = mid; p.loglik = -s.rec_v[cl];
               p.lwr = 1; p.d_llh = d; p.chisq = 0;
               out[pbegin] = p;
             } else atomicOr(a.counters + 2, kErrPlaceOverflow);
@@ -249,85 +248,179 @@ __global__ void __launch_bounds__(128) place_kernel(const PlaceArgs a, const Llh
             while (bits) { const uint32_t q = __ffs(bits) - 1; bits &= bits - 1; list[at++] = (wb + lane) * 32 + q; }
           }
           __syncwarp();
-          // 3. one lane per marked node: accumulate, solve, test
+          if (lane == 0) nbegin = atomicAdd(a.counters + 5, cnt);
+          nbegin = __shfl_sync(0xFFFFFFFFu, nbegin, 0);
+          ncount = cnt;
+          if ((uint64_t)nbegin + cnt > a.node_cap) { // counters[5] ends as the demand; the host grows the node arrays and runs the batch again
+            if (lane == 0) atomicOr(a.counters + 2, kErrNodeOverflow);
+            ncount = 0; cnt = 0;
+          }
+          // 3. one lane per marked node: a selected leaf brings its own record, an internal node accumulates the leaves below it
           const uint32_t enmers = (uint32_t)(a.offsets[r + 1] - a.offsets[r]) - s.k + 1;
-          for (uint32_t j = lane; j < cnt; j += 32) {
-            const uint32_t g = __ldcg(&list[j]);
-            double d = DBL_MAX, v = nan(""), chisq = nan(""), leq = 0;
-            if (a.leaf_rank[g] != 0xFFFFFFFFu) { // a selected leaf: its own record
-              uint32_t rec = 0xFFFFFFFFu;
-              for (uint32_t i = 0; i < n; ++i) if ((s.rec_flags[b + i] & 2u) && (s.rec_slot[b + i] & 0x7FFFFFFFu) == g) rec = b + i;
-              d = s.rec_d[rec]; v = s.rec_v[rec];
-              for (uint32_t x = 0; x <= a.tau && x < stride; ++x) leq += (double)s.rec_hist[(size_t)rec * stride + x];
-            } else {
-              ObjectiveAny f;
-              double (&mc)[kMaxTh + 1] = f.mc;
-              for (uint32_t x = 0; x <= (uint32_t)kMaxTh; ++x) mc[x] = 0;
-              double nmers = 0, mismatch = 0, match = 0, rho = 0;
-              const uint32_t lo = g - a.subtree[g]; // leaves below g have lo < se <= g
-              uint32_t i = b, jx = b + nf;
-              const uint32_t ie = b + nf, je = b + n;
-              while (i < ie || jx < je) { // selected records by ascending leaf se (merge of the two strands' runs)
-                const uint32_t si = i < ie ? (s.rec_slot[i] & 0x7FFFFFFFu) : 0xFFFFFFFFu, sj = jx < je ? (s.rec_slot[jx] & 0x7FFFFFFFu) : 0xFFFFFFFFu;
-                uint32_t rec, se;
-                if (si <= sj) { rec = i; se = si; ++i; if (si == sj) { if (!(s.rec_flags[rec] & 2u)) rec = jx; ++jx; } }
-                else { rec = jx; se = sj; ++jx; }
-                if (!(s.rec_flags[rec] & 2u) || !(se > lo && se <= g)) continue;
-                double denom = 1.0;
-                for (uint32_t node = a.parent[se];; node = a.parent[node]) { denom /= (double)a.nchildren[node]; if (node == g) break; }
-                const double m = (double)s.rec_match[rec];
-                mismatch = nmers != 0 ? mismatch : (double)enmers;      // Minfo::add (ref src/query.hpp:139-152)
-                match += m * denom;
-                mismatch -= m * denom;
-                for (uint32_t x = 0; x < stride; ++x) mc[x] = mc[x] + (double)s.rec_hist[(size_t)rec * stride + x] * denom;
-                nmers = fmax(nmers, (double)enmers);
-                rho = fmax(rho, s.rho[se]);
-              }
-              for (uint32_t x = 0; x <= a.tau && x < stride; ++x) leq += mc[x];
-              if (a.no_filter || leq > 1.0) {
-                f.uc = mismatch; f.rho = rho; f.k = s.k; f.th = s.th;
-                brent_minimum(PlainEval<kMaxTh + 1>{&f, &tab}, d, v);
-              }
-            }
-            uint32_t cand = 0;
-            if (a.nchildren[g] != 1 && (a.no_filter || leq > 1.0)) {
-              chisq = 2 * (f_cl.eval(tab, d) - v_cl);
-              cand = (chisq < a.chisq_value) && a.parent[g] != 0;
-            }
-            nd_d[j] = d; nd_v[j] = v; nd_c[j] = chisq; nd_k[j] = cand;
-          }
-          __syncwarp();
-          // 4. candidates in ascending se: lwr = exp(-chisq/2) / total
-          if (lane == 0) {
-            double total = 0;
-            uint32_t nc = 0;
-            for (uint32_t j = 0; j < cnt; ++j) if (__ldcg(&nd_k[j])) { total = total + exp(-__ldcg(&nd_c[j]) / 2); ++nc; }
-            if (nc) {
-              pbegin = atomicAdd(a.counters + 3, nc); pcount = nc;
-              if ((uint64_t)pbegin + nc <= a.place_cap) {
-                uint32_t at = pbegin;
-                for (uint32_t j = 0; j < cnt; ++j) {
-                  if (!__ldcg(&nd_k[j])) continue;
-                  const uint32_t g = __ldcg(&list[j]);
-                  const double bl = a.blen[g], mid = isnan(bl) ? 0.0 : bl / 2.0, d = __ldcg(&nd_d[j]), c = __ldcg(&nd_c[j]);
-                  krepp_placement_t p; p.read = r; p.se = g; p.pendant = jukes_cantor(d) - mid; p.distal = mid; p.loglik = -__ldcg(&nd_v[j]);
-                  p.lwr = exp(-c / 2) / total; p.d_llh = d; p.chisq = c;
-                  out[at++] = p;
+          for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
+            const uint32_t j = j0 + lane;
+            bool solve = false;
+            if (j < cnt) {
+              const uint32_t g = __ldcg(&list[j]), e = nbegin + j;
+              double d = DBL_MAX, v = nan(""), leq = 0;
+              if (a.leaf_rank[g] != 0xFFFFFFFFu) {
+                uint32_t rec = 0xFFFFFFFFu;
+                for (uint32_t i = 0; i < n; ++i) if ((s.rec_flags[b + i] & 2u) && (s.rec_slot[b + i] & 0x7FFFFFFFu) == g) rec = b + i;
+                d = s.rec_d[rec]; v = s.rec_v[rec];
+                for (uint32_t x = 0; x <= a.tau && x < stride; ++x) leq += (double)s.rec_hist[(size_t)rec * stride + x];
+              } else {
+                double mc[kMaxTh + 1];
+                for (uint32_t x = 0; x <= (uint32_t)kMaxTh; ++x) mc[x] = 0;
+                double nmers = 0, mismatch = 0, match = 0, rho = 0;
+                const uint32_t lo = g - a.subtree[g]; // leaves below g have lo < se <= g
+                uint32_t i = b, jx = b + nf;
+                const uint32_t ie = b + nf, je = b + n;
+                while (i < ie || jx < je) { // selected records by ascending leaf se (merge of the two strands' runs)
+                  const uint32_t si = i < ie ? (s.rec_slot[i] & 0x7FFFFFFFu) : 0xFFFFFFFFu, sj = jx < je ? (s.rec_slot[jx] & 0x7FFFFFFFu) : 0xFFFFFFFFu;
+                  uint32_t rec, se;
+                  if (si <= sj) { rec = i; se = si; ++i; if (si == sj) { if (!(s.rec_flags[rec] & 2u)) rec = jx; ++jx; } }
+                  else { rec = jx; se = sj; ++jx; }
+                  if (!(s.rec_flags[rec] & 2u) || !(se > lo && se <= g)) continue;
+                  double denom = 1.0;
+                  for (uint32_t node = a.parent[se];; node = a.parent[node]) { denom /= (double)a.nchildren[node]; if (node == g) break; }
+                  const double m = (double)s.rec_match[rec];
+                  mismatch = nmers != 0 ? mismatch : (double)enmers;      // Minfo::add (ref src/query.hpp:139-152)
+                  match += m * denom;
+                  mismatch -= m * denom;
+                  for (uint32_t x = 0; x < stride; ++x) mc[x] = mc[x] + (double)s.rec_hist[(size_t)rec * stride + x] * denom;
+                  nmers = fmax(nmers, (double)enmers);
+                  rho = fmax(rho, s.rho[se]);
                 }
-              } else { atomicOr(a.counters + 2, kErrPlaceOverflow); pcount = 0; }
+                for (uint32_t x = 0; x <= a.tau && x < stride; ++x) leq += mc[x];
+                solve = a.no_filter || leq > 1.0;
+                if (solve) {
+                  for (uint32_t x = 0; x < stride; ++x) a.pn_mc[(size_t)e * stride + x] = mc[x];
+                  a.pn_uc[e] = mismatch; a.pn_rho[e] = rho;
+                }
+              }
+              const bool eligible = a.nchildren[g] != 1 && (a.no_filter || leq > 1.0);
+              a.pn_read[e] = r; a.pn_se[e] = g; a.pn_flags[e] = (solve ? kPnSolve : 0u) | (eligible ? kPnEligible : 0u);
+              a.pn_d[e] = d; a.pn_v[e] = v; a.pn_chisq[e] = nan("");
             }
+            const uint32_t sm = __ballot_sync(0xFFFFFFFFu, solve);
+            uint32_t wbase = 0;
+            if (lane == 0 && sm) wbase = atomicAdd(a.counters + 6, __popc(sm));
+            wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+            if (solve) a.pn_work[wbase + __popc(sm & lt_mask)] = nbegin + j;
           }
-          __syncwarp();
         }
       }
     }
-    if (lane == 0) { a.place_begin[r] = pbegin; a.place_count[r] = pcount; }
+    if (lane == 0) { a.place_begin[r] = pbegin; a.place_count[r] = pcount; a.pn_begin[r] = nbegin; a.pn_count[r] = ncount; }
   }
 }
 
-cudaError_t launch_place(const PlaceArgs& a, const LlhTables& tab, int grid, cudaStream_t stream)
+template <int N>
+__global__ void __launch_bounds__(128) place_solve_kernel(const PlaceArgs a, const LlhTables tab)
 {
-  place_kernel<<<grid, 128, 0, stream>>>(a, tab);
+  __shared__ double su[4];
+  __shared__ DTerms st[4];
+  const SolveArgs& s = a.s;
+  if (s.counters[2] & kErrRedo) return;
+  if (threadIdx.x < 4) {
+    double u[4];
+    brent_first_points(u);
+    const double ut = threadIdx.x == 0 ? u[0] : threadIdx.x == 1 ? u[1] : threadIdx.x == 2 ? u[2] : u[3];
+    su[threadIdx.x] = ut;
+    st[threadIdx.x] = d_terms(tab, ut, s.k);
+  }
+  __syncthreads();
+  const uint32_t n = a.counters[6], stride = s.th + 1;
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const uint32_t e = a.pn_work[j];
+    Objective<N> f;
+#pragma unroll
+    for (int x = 0; x < N; ++x) f.mc[x] = (uint32_t)x < stride ? a.pn_mc[(size_t)e * stride + x] : 0.0;
+    f.uc = a.pn_uc[e]; f.rho = a.pn_rho[e]; f.k = s.k; f.th = s.th;
+    double d, v;
+    brent_minimum(MemoEval<N>{&f, &tab, su, st}, d, v);
+    a.pn_d[e] = d; a.pn_v[e] = v;
+  }
+}
+
+// chisq of a node = 2 * (f_closest(d_node) - v_closest) (ref src/query.cpp:262-279); candidate when below the threshold and not the root
+template <int N>
+__global__ void __launch_bounds__(128) place_chisq_kernel(const PlaceArgs a, const LlhTables tab)
+{
+  const SolveArgs& s = a.s;
+  if (s.counters[2] & kErrRedo) return;
+  if (s.counters[2] & kErrNodeOverflow) return; // entries are incomplete: the host grows the node arrays and runs the batch again
+  const uint32_t n = a.counters[5], stride = s.th + 1;
+  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const uint32_t fl = a.pn_flags[e];
+    if (!(fl & kPnEligible)) continue;
+    const uint32_t r = a.pn_read[e], g = a.pn_se[e];
+    const uint32_t cl = (uint32_t)s.closest[r];
+    Objective<N> f;
+#pragma unroll
+    for (int x = 0; x < N; ++x) f.mc[x] = (uint32_t)x < stride ? (double)s.rec_hist[(size_t)cl * stride + x] : 0.0;
+    f.uc = (double)s.onmers[r] - (double)s.rec_match[cl]; f.rho = s.rho[s.rec_slot[cl] & 0x7FFFFFFFu]; f.k = s.k; f.th = s.th;
+    const double chisq = 2 * (f.eval(tab, a.pn_d[e]) - s.rec_v[cl]);
+    a.pn_chisq[e] = chisq;
+    if ((chisq < a.chisq_value) && a.parent[g] != 0) a.pn_flags[e] = fl | kPnCandidate;
+  }
+}
+
+// candidates in ascending se: lwr = exp(-chisq/2) / total, the total summed in that order (ref src/query.cpp:284-296)
+__global__ void __launch_bounds__(128) place_emit_kernel(const PlaceArgs a)
+{
+  const SolveArgs& s = a.s;
+  if (s.counters[2] & kErrRedo) return;
+  const uint32_t lane = threadIdx.x & 31, lt_mask = (1u << lane) - 1u;
+  const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  krepp_placement_t* out = static_cast<krepp_placement_t*>(a.placements);
+  for (uint32_t r = gwarp; r < s.n_reads; r += nwarps) {
+    const uint32_t nb = a.pn_begin[r], cnt = a.pn_count[r];
+    if (!cnt) continue;
+    double total = 0;
+    uint32_t nc = 0;
+    for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
+      const uint32_t j = j0 + lane;
+      const bool cand = j < cnt && (a.pn_flags[nb + j] & kPnCandidate);
+      const double w = cand ? exp(-a.pn_chisq[nb + j] / 2) : 0.0;
+      uint32_t cm = __ballot_sync(0xFFFFFFFFu, cand);
+      nc += __popc(cm);
+      while (cm) { const int src = __ffs(cm) - 1; cm &= cm - 1; total = total + __shfl_sync(0xFFFFFFFFu, w, src); }
+    }
+    if (!nc) continue;
+    uint32_t pbegin = 0;
+    if (lane == 0) pbegin = atomicAdd(a.counters + 3, nc);
+    pbegin = __shfl_sync(0xFFFFFFFFu, pbegin, 0);
+    if ((uint64_t)pbegin + nc > a.place_cap) { if (lane == 0) atomicOr(a.counters + 2, kErrPlaceOverflow); continue; }
+    uint32_t done = 0;
+    for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
+      const uint32_t j = j0 + lane;
+      const bool cand = j < cnt && (a.pn_flags[nb + j] & kPnCandidate);
+      const uint32_t cm = __ballot_sync(0xFFFFFFFFu, cand);
+      if (cand) {
+        const uint32_t e = nb + j, g = a.pn_se[e];
+        const double bl = a.blen[g], mid = isnan(bl) ? 0.0 : bl / 2.0, d = a.pn_d[e], c = a.pn_chisq[e];
+        krepp_placement_t p; p.read = r; p.se = g; p.pendant = jukes_cantor(d) - mid; p.distal = mid; p.loglik = -a.pn_v[e];
+        p.lwr = exp(-c / 2) / total; p.d_llh = d; p.chisq = c;
+        out[pbegin + done + __popc(cm & lt_mask)] = p;
+      }
+      done += __popc(cm);
+    }
+    if (lane == 0) { a.place_begin[r] = pbegin; a.place_count[r] = nc; }
+  }
+}
+
+cudaError_t launch_place(const PlaceArgs& a, const LlhTables& tab, int grid, int sms, cudaStream_t stream, StageClock* clk)
+{
+  place_collect_kernel<<<grid, 128, 0, stream>>>(a);
+  if (clk) clk->tick("place_collect_kernel", stream);
+  if (a.s.th + 1 <= 5) place_solve_kernel<5><<<sms * 8, 128, 0, stream>>>(a, tab);
+  else place_solve_kernel<kMaxTh + 1><<<sms * 8, 128, 0, stream>>>(a, tab);
+  if (clk) clk->tick("place_solve_kernel", stream);
+  if (a.s.th + 1 <= 5) place_chisq_kernel<5><<<sms * 8, 128, 0, stream>>>(a, tab);
+  else place_chisq_kernel<kMaxTh + 1><<<sms * 8, 128, 0, stream>>>(a, tab);
+  place_emit_kernel<<<grid, 128, 0, stream>>>(a);
+  if (clk) clk->tick("place_chisq_kernel+place_emit_kernel", stream);
   return cudaGetLastError();
 }
 

@@ -25,6 +25,6 @@ cudaError_t launch_shard_join(const DevIndex& ix, const SortArgs& s, uint32_t th
 cudaError_t launch_shard_finish(const DevIndex& ix, const MatchArgs& a, const SortArgs& s, int sms, cudaStream_t stream, StageClock* clk = nullptr);
 cudaError_t launch_solve(const SolveArgs& a, const LlhTables& tab, int sms, cudaStream_t stream, StageClock* clk = nullptr);
 constexpr int kPlaceWarpsPerCta = 4;
-cudaError_t launch_place(const PlaceArgs& a, const LlhTables& tab, int grid, cudaStream_t stream);
+cudaError_t launch_place(const PlaceArgs& a, const LlhTables& tab, int grid, int sms, cudaStream_t stream, StageClock* clk = nullptr);
 
 } // namespace krepp

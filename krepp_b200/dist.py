@@ -144,9 +144,9 @@ class ShardRank:
             self.torch.cuda.current_stream().synchronize()
             self.slot.shard_finish(recv_hits.data_ptr(), recv_hits.shape[0])
 
-    def results(self) -> dict:
+    def results(self, rows: bool = True) -> dict:
         with self.torch.cuda.device(self.dev):
-            r = self.slot.wait()
+            r = self.slot.wait() if rows else self.slot.wait_device()
         self._keep = None
         return r
 
@@ -187,9 +187,9 @@ class ShardedJob:
             out.append((recv, rc))
         return out
 
-    def run(self, batches):
+    def run(self, batches, rows: bool = True):
         """batches[i] = (d_bases uint8 tensor, d_offsets int64 tensor, n_reads) of in-process rank i.  Returns the result
-        dicts (krepp_batch_wait) in the same order."""
+        dicts (krepp_batch_wait; krepp_batch_wait_device when rows is False) in the same order."""
         p1 = [r.lookup(*b) for r, b in zip(self.ranks, batches)]
         tup = self._exchange([(t, c) for t, c, _, _ in p1])
         rbs = self._exchange([(rb.view(-1, 1), rc) for _, _, rb, rc in p1])
@@ -197,4 +197,4 @@ class ShardedJob:
         back = self._exchange(p2)
         for r, (h, _) in zip(self.ranks, back):
             r.finish(h)
-        return [r.results() for r in self.ranks]
+        return [r.results(rows) for r in self.ranks]

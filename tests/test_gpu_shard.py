@@ -102,7 +102,9 @@ def test_small_index_shards_match_unsharded_and_oracle(world):
         assert_same_results(r, ref, f"world {world}")
         g = gpu_stage_dicts(types.SimpleNamespace(n_reads=len(part)), r, None)
         for i, s in enumerate(part):
-            compare_read(i, g[i], oracle.query(s, p), False, False, stats)
+            o = oracle.query(s, p)
+            o["minfo"] = [m for m in o["minfo"] if m["solved"]]  # the default output drops the pairs that fail the hdist_filt gate
+            compare_read(i, g[i], o, False, False, stats)
         for k in alg:
             alg[k] += a[k]
     assert stats["solves"] > 500

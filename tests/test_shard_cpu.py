@@ -116,8 +116,6 @@ def _worker(rank, world, port, q):
             hd = _hd(ents[:, 0], np.uint32(enc))
             want += [(int(read), int(meta), int(ents[k, 1]), int(hd[k])) for k in np.nonzero(hd <= th)[0]]
         assert got == sorted(want), (rank, len(got), len(want))
-        # and those hits are what the oracle's histograms count: one per lookup and leaf at the minimum distance is a
-        # subset of them, so at least every record's match_count is covered
         tot = kd.sum_over_ranks([len(mine), len(tup), len(got)])
         if rank == 0:
             q.put(tot)
