@@ -323,9 +323,9 @@ class IBatch:
 
     def stage_times(self) -> list:
         """[(stage name, ms)] of the last waited batch, in launch order (CUDA events on the slot's stream)."""
-        ms, names, n = (C.c_float * 16)(), (C.c_char_p * 16)(), C.c_uint32()
-        _check(load_library().krepp_batch_stage_times(self._h, 16, ms, names, C.byref(n)))
-        return [(names[i].decode(), float(ms[i])) for i in range(min(n.value, 16))]
+        ms, names, n = (C.c_float * 24)(), (C.c_char_p * 24)(), C.c_uint32()
+        _check(load_library().krepp_batch_stage_times(self._h, 24, ms, names, C.byref(n)))
+        return [(names[i].decode(), float(ms[i])) for i in range(min(n.value, 24))]
 
     # -- reference-shaped entry points ------------------------------------------------------------------------------
     def estimate_distances(self) -> str:

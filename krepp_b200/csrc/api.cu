@@ -148,6 +148,7 @@ struct krepp_batch {
   int32_t* d_closest = nullptr;
   uint32_t *d_rec_read = nullptr, *d_rec_slot = nullptr, *d_rec_hist = nullptr, *d_rec_flags = nullptr, *d_rec_match = nullptr, *d_rec_hdmin = nullptr, *d_rec_work = nullptr;
   double *d_rec_d = nullptr, *d_rec_v = nullptr, *d_rec_chisq = nullptr;
+  uint32_t* d_rec_alias = nullptr; unsigned long long* d_memo_key = nullptr; uint32_t* d_memo_owner = nullptr; uint32_t memo_mask = 0, memo_bits = 0;
   uint32_t* d_counters = nullptr; unsigned long long* d_stats = nullptr;
   uint32_t *d_acc = nullptr, *d_bitmap = nullptr, *d_marker = nullptr, *d_stack = nullptr, *d_tagctr = nullptr;
   uint32_t stack_cap = 0;
@@ -158,6 +159,7 @@ struct krepp_batch {
   // placement (K5)
   uint32_t place_cap = 0, place_warps = 0;
   uint32_t *d_place_begin = nullptr, *d_place_count = nullptr, *d_node_bitmap = nullptr, *d_node_list = nullptr;
+  uint32_t* d_sel = nullptr; double* d_chain = nullptr; uint32_t chain_cap = 0;
   uint32_t node_cap = 0;      // tree nodes touched by a batch (place_collect_kernel's entries)
   uint32_t *d_pn_read = nullptr, *d_pn_se = nullptr, *d_pn_flags = nullptr, *d_pn_work = nullptr, *d_pn_begin = nullptr, *d_pn_count = nullptr;
   double *d_pn_mc = nullptr, *d_pn_uc = nullptr, *d_pn_rho = nullptr, *d_pn_d = nullptr, *d_pn_v = nullptr, *d_pn_chisq = nullptr;
@@ -233,6 +235,7 @@ int krepp_index_open_shard(const char* index_dir, int device, uint32_t shard, ui
   if (e == cudaSuccess) e = upload(h.tree.blen, &d.blen, ix->allocs, ix->device_bytes);
   if (e == cudaSuccess) e = upload(build_lut(h), &d.lut, ix->allocs, ix->device_bytes);
   if (e == cudaSuccess) e = upload(h.tree.subtree, &d.subtree, ix->allocs, ix->device_bytes);
+  if (e == cudaSuccess) e = upload(h.tree.depth, &d.depth, ix->allocs, ix->device_bytes);
   d.cbeg = nullptr; d.cleaf = nullptr;
   if (!h.cbeg.empty()) { // flattened colours: what the bucket-sorted pipeline (sorted.cu) expands hits with
     if (e == cudaSuccess) e = upload(h.cbeg, &d.cbeg, ix->allocs, ix->device_bytes);
@@ -323,12 +326,12 @@ size_t krepp_index_jplace_tree(const krepp_index_t* ix, char* buf, size_t cap)
 
 static void free_records(krepp_batch* b)
 {
-  for (void* p : {(void*)b->d_rec_work, (void*)b->d_rec_read, (void*)b->d_rec_slot, (void*)b->d_rec_hist, (void*)b->d_rec_flags, (void*)b->d_rec_match,
+  for (void* p : {(void*)b->d_rec_alias, (void*)b->d_rec_work, (void*)b->d_rec_read, (void*)b->d_rec_slot, (void*)b->d_rec_hist, (void*)b->d_rec_flags, (void*)b->d_rec_match,
                   (void*)b->d_rec_hdmin, (void*)b->d_rec_d, (void*)b->d_rec_v, (void*)b->d_rec_chisq, (void*)b->d_out_rec})
     if (p) cudaFree(p);
   if (b->h_rec) cudaFreeHost(b->h_rec);
   if (b->h_hist) cudaFreeHost(b->h_hist);
-  b->d_rec_read = b->d_rec_slot = b->d_rec_hist = b->d_rec_flags = b->d_rec_match = b->d_rec_hdmin = b->d_rec_work = nullptr;
+  b->d_rec_read = b->d_rec_slot = b->d_rec_hist = b->d_rec_flags = b->d_rec_match = b->d_rec_hdmin = b->d_rec_work = b->d_rec_alias = nullptr;
   b->d_rec_d = b->d_rec_v = b->d_rec_chisq = nullptr; b->d_out_rec = nullptr; b->h_rec = nullptr; b->h_hist = nullptr;
 }
 
@@ -366,7 +369,7 @@ static int alloc_records(krepp_batch* b, uint32_t cap)
   b->rec_cap = cap;
   CU(cudaMalloc(&b->d_rec_read, 4ull * cap)); CU(cudaMalloc(&b->d_rec_slot, 4ull * cap)); CU(cudaMalloc(&b->d_rec_hist, 4ull * cap * stride));
   CU(cudaMalloc(&b->d_rec_flags, 4ull * cap)); CU(cudaMalloc(&b->d_rec_match, 4ull * cap)); CU(cudaMalloc(&b->d_rec_hdmin, 4ull * cap));
-  CU(cudaMalloc(&b->d_rec_work, 4ull * cap));
+  CU(cudaMalloc(&b->d_rec_work, 4ull * cap)); CU(cudaMalloc(&b->d_rec_alias, 4ull * cap));
   CU(cudaMalloc(&b->d_rec_d, 8ull * cap)); CU(cudaMalloc(&b->d_rec_v, 8ull * cap)); CU(cudaMalloc(&b->d_rec_chisq, 8ull * cap));
   CU(cudaMalloc(&b->d_out_rec, sizeof(krepp_record_t) * (size_t)cap));
   CU(cudaMallocHost(&b->h_rec, sizeof(krepp_record_t) * (size_t)cap));
@@ -451,6 +454,16 @@ int krepp_batch_create(krepp_index_t* ix, const krepp_params_t* p, uint32_t max_
   CU(cudaMalloc(&b->d_tagctr, 4 * warps)); CU(cudaMemset(b->d_tagctr, 0xFF, 4 * warps));
   const uint64_t want = std::max<uint64_t>(4ull * max_reads, 4096);
   if (int rc = alloc_records(b, (uint32_t)std::min<uint64_t>(want, 0x7FFFFFFFull))) return rc;
+  { // solve memo (see SolveArgs): a table of 8 slots per read, between 2^16 and 2^24 slots; KREPP_MEMO=0 turns it off
+    b->memo_bits = std::min<uint32_t>(12, (64 - 29) / (p->hdist_th + 1));
+    const char* env = getenv("KREPP_MEMO");
+    if (b->memo_bits >= 4 && !(env && !strcmp(env, "0"))) {
+      uint64_t slots = 1ull << 16;
+      while (slots < 8ull * max_reads && slots < (1ull << 24)) slots <<= 1;
+      b->memo_mask = (uint32_t)(slots - 1);
+      CU(cudaMalloc(&b->d_memo_key, 8 * slots)); CU(cudaMalloc(&b->d_memo_owner, 4 * slots));
+    }
+  }
   b->sorted = ix->sorted_default;
   if (const char* env = getenv("KREPP_PIPELINE")) {
     if (!strcmp(env, "sorted")) { if (!ix->sorted_ok) return fail(KREPP_ERR_UNSUPPORTED, "KREPP_PIPELINE=sorted: the flattened colour lists of this index are too large"); b->sorted = true; }
@@ -469,6 +482,8 @@ int krepp_batch_create(krepp_index_t* ix, const krepp_params_t* p, uint32_t max_
     CU(cudaMalloc(&b->d_place_begin, 4ull * max_reads)); CU(cudaMalloc(&b->d_place_count, 4ull * max_reads));
     CU(cudaMalloc(&b->d_node_bitmap, 4 * pw * nbm_nodes)); CU(cudaMemset(b->d_node_bitmap, 0, 4 * pw * nbm_nodes));
     CU(cudaMalloc(&b->d_node_list, 4 * pw * nn));
+    b->chain_cap = 4096; // doubles per warp: sum over a read's selected references of their depth; reads beyond it take the slow walk
+    CU(cudaMalloc(&b->d_sel, 4 * pw * 3 * (size_t)std::max<uint32_t>(h.tree.nleaves, 1))); CU(cudaMalloc(&b->d_chain, 8 * pw * (size_t)b->chain_cap));
     CU(cudaMalloc(&b->d_pn_begin, 4ull * max_reads)); CU(cudaMalloc(&b->d_pn_count, 4ull * max_reads));
     if (int rc = alloc_place_nodes(b, std::max<uint64_t>(32ull * max_reads, 4096))) return rc; // grown to the demand when a batch needs more
     if (int rc = alloc_placements(b, (uint32_t)std::min<uint64_t>(std::max<uint64_t>(8ull * max_reads, 4096), 0x7FFFFFFFull))) return rc;
@@ -483,9 +498,9 @@ void krepp_batch_destroy(krepp_batch_t* b)
   if (b->stream) cudaStreamSynchronize(b->stream);
   free_records(b);
   for (void* p : {(void*)b->d_bases, (void*)b->d_offsets, (void*)b->d_onmers, (void*)b->d_wn, (void*)b->d_hdfilt, (void*)b->d_rec_begin,
-                  (void*)b->d_rec_count, (void*)b->d_closest, (void*)b->d_counters, (void*)b->d_stats, (void*)b->d_acc, (void*)b->d_bitmap,
+                  (void*)b->d_rec_count, (void*)b->d_closest, (void*)b->d_memo_key, (void*)b->d_memo_owner, (void*)b->d_counters, (void*)b->d_stats, (void*)b->d_acc, (void*)b->d_bitmap,
                   (void*)b->d_marker, (void*)b->d_stack, (void*)b->d_tagctr, (void*)b->d_out_read, (void*)b->d_tap, (void*)b->d_tap_count, (void*)b->d_place_begin,
-                  (void*)b->d_place_count, (void*)b->d_node_bitmap, (void*)b->d_node_list, (void*)b->d_pn_begin, (void*)b->d_pn_count, (void*)b->d_pn_read,
+                  (void*)b->d_place_count, (void*)b->d_node_bitmap, (void*)b->d_node_list, (void*)b->d_sel, (void*)b->d_chain, (void*)b->d_pn_begin, (void*)b->d_pn_count, (void*)b->d_pn_read,
                   (void*)b->d_pn_se, (void*)b->d_pn_flags, (void*)b->d_pn_work, (void*)b->d_pn_mc, (void*)b->d_pn_uc, (void*)b->d_pn_rho, (void*)b->d_pn_d,
                   (void*)b->d_pn_v, (void*)b->d_pn_chisq, (void*)b->d_place})
     if (p) cudaFree(p);
@@ -552,14 +567,15 @@ static int enqueue(krepp_batch* b)
   sa.rec_read = b->d_rec_read; sa.rec_slot = b->d_rec_slot; sa.rec_hist = b->d_rec_hist; sa.rho = ix->dev.rho;
   sa.rec_d = b->d_rec_d; sa.rec_v = b->d_rec_v; sa.rec_chisq = b->d_rec_chisq; sa.rec_flags = b->d_rec_flags; sa.rec_match = b->d_rec_match;
   sa.rec_hdmin = b->d_rec_hdmin; sa.closest = b->d_closest;
+  sa.memo_key = b->d_memo_key; sa.memo_owner = b->d_memo_owner; sa.memo_mask = b->memo_mask; sa.memo_bits = b->memo_bits; sa.rec_alias = b->d_rec_alias;
   sa.want_chisq = (!b->p.no_filter || b->p.summarize || b->p.place) ? 1 : 0;
   CU(launch_solve(sa, b->tab, ix->sms, s, &b->clk));
-  b->launches = 4 + match_launches + (sa.want_chisq ? 1 : 0);
+  b->launches = 4 + match_launches + (sa.want_chisq ? 1 : 0) + (sa.memo_mask ? 1 : 0);
   if (b->p.place) {
     PlaceArgs pa{};
     pa.s = sa; pa.offsets = b->in_offsets; pa.tau = b->p.tau; pa.no_filter = b->p.no_filter; pa.chisq_value = b->p.chisq;
-    pa.parent = ix->dev.parent; pa.nchildren = ix->dev.nchildren; pa.subtree = ix->dev.subtree; pa.blen = ix->dev.blen; pa.leaf_rank = ix->dev.leaf_rank;
-    pa.nnodes = h.tree.nnodes;
+    pa.parent = ix->dev.parent; pa.nchildren = ix->dev.nchildren; pa.subtree = ix->dev.subtree; pa.depth = ix->dev.depth; pa.blen = ix->dev.blen; pa.leaf_rank = ix->dev.leaf_rank;
+    pa.nnodes = h.tree.nnodes; pa.nleaves = h.tree.nleaves; pa.sel = b->d_sel; pa.chain = b->d_chain; pa.chain_cap = b->chain_cap;
     pa.node_bitmap = b->d_node_bitmap; pa.node_list = b->d_node_list;
     pa.node_cap = b->node_cap; pa.pn_read = b->d_pn_read; pa.pn_se = b->d_pn_se; pa.pn_flags = b->d_pn_flags; pa.pn_work = b->d_pn_work;
     pa.pn_mc = b->d_pn_mc; pa.pn_uc = b->d_pn_uc; pa.pn_rho = b->d_pn_rho; pa.pn_d = b->d_pn_d; pa.pn_v = b->d_pn_v; pa.pn_chisq = b->d_pn_chisq;

@@ -26,6 +26,7 @@ struct DevIndex {
   const uint32_t* parent;   // by se (0 for root)                  ref Node::parent
   const uint32_t* nchildren;// by se
   const double* blen;       // by se
+  const uint32_t* depth;    // by se: number of ancestors
   const uint32_t* subtree;  // by se: number of nodes in the subtree rooted there (post-order => se range (se-subtree, se])
   uint64_t nkmers;
   uint32_t nrows, nsubsets, nnodes, nleaves;
@@ -111,6 +112,15 @@ struct SolveArgs {
   double* rec_d; double* rec_v; double* rec_chisq; uint32_t* rec_flags; uint32_t* rec_match; uint32_t* rec_hdmin;
   int32_t* closest;                  // [n_reads] record index or -1
   int want_chisq;
+  // Identical problems are solved once per batch: the objective of a record is a function of (histogram, onmers - matches,
+  // rho of the leaf) alone, and on a large index most records are weak matches that share those (about nine in ten of the
+  // 1,000-genome workload's).  The gate enters each record in a hash table keyed by the exact tuple; the first to arrive
+  // is solved, the others copy its result, which is bit-identical to solving them.
+  unsigned long long* memo_key;      // [memo_mask + 1] packed tuple, 0 = empty (zeroed per batch)
+  uint32_t* memo_owner;              // [memo_mask + 1] record that is solved for the slot
+  uint32_t memo_mask;                // slots - 1 (a power of two), 0 = no table
+  uint32_t memo_bits;                // bits per histogram bin in the key: (th + 1) * memo_bits + 8 (onmers) + 21 (leaf se) <= 64
+  uint32_t* rec_alias;               // [n_records] slot whose owner's result the record takes, 0xffffffff = solved itself
 };
 
 // K5 (placement) arguments: everything K4 produced plus the flattened phytree.
@@ -119,11 +129,14 @@ struct PlaceArgs {
   const uint64_t* offsets;     // read offsets (enmers = len - k + 1, ref src/query.cpp:345-349)
   uint32_t tau; int no_filter; double chisq_value;
   // flattened tree (by se)
-  const uint32_t* parent; const uint32_t* nchildren; const uint32_t* subtree; const double* blen; const uint32_t* leaf_rank;
-  uint32_t nnodes;
+  const uint32_t* parent; const uint32_t* nchildren; const uint32_t* subtree; const uint32_t* depth; const double* blen; const uint32_t* leaf_rank;
+  uint32_t nnodes, nleaves;
   // per-warp scratch of the collect kernel
   uint32_t* node_bitmap;       // [warps][ceil((nnodes+1)/32)]
   uint32_t* node_list;         // [warps][nnodes]
+  uint32_t* sel;               // [warps][3 * nleaves] the read's selected references by ascending se: record, se, start of its chain
+  double* chain;               // [warps][chain_cap] per selected leaf, level by level towards the root: prod 1/eff_nchildren
+  uint32_t chain_cap;
   // tree nodes touched by the batch's reads (every selected leaf and all its ancestors), read by read, ascending se
   uint32_t node_cap;
   uint32_t* pn_read; uint32_t* pn_se; uint32_t* pn_flags;  // [node_cap]; flags: kPnSolve | kPnEligible | kPnCandidate

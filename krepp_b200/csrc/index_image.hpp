@@ -19,6 +19,7 @@ struct BitRun { uint8_t src, width, dst; }; // ((x >> src) & ((1<<width)-1)) << 
 struct HostTree {
   uint32_t nnodes = 0, root = 0, nleaves = 0;
   std::vector<uint32_t> parent, nchildren, card, first_child, next_sibling; // [nnodes+1], by se
+  std::vector<uint32_t> depth;           // ancestors of se (0 for the root)
   std::vector<uint32_t> subtree;         // nodes in the subtree rooted at se; post-order => it spans se in (se-subtree, se]
   std::vector<uint8_t> is_leaf;
   std::vector<double> blen;              // NaN when absent

@@ -69,12 +69,44 @@ __global__ void __launch_bounds__(256) gate_kernel(const SolveArgs a)
       const uint32_t filt = 2u * a.hdfilt[2 * read + strand] + 1u; // uint32 wrap kept (ref src/query.cpp:101-102)
       pass = !(hdmin > filt);
       a.rec_d[i] = DBL_MAX; a.rec_v[i] = nan(""); a.rec_flags[i] = 0; a.rec_chisq[i] = nan(""); // Minfo defaults (ref src/query.hpp:225-226)
+      uint32_t alias = 0xFFFFFFFFu;
+      if (pass && a.memo_mask) { // same (histogram, onmers, leaf) as an earlier record of the batch?
+        const uint32_t se = a.rec_slot[i] & 0x7FFFFFFFu, on = a.onmers[read], lim = (1u << a.memo_bits) - 1u;
+        unsigned long long key = 0;
+        bool fits = se < (1u << 21) && on < 256u;
+        for (uint32_t x = 0; x < stride; ++x) { const uint32_t c = a.rec_hist[(size_t)i * stride + x]; fits = fits && c <= lim; key = key << a.memo_bits | c; }
+        if (fits) {
+          key = (key << 8 | on) << 21 | se; // never 0: a record has at least one match
+          unsigned long long hsh = key * 0x9E3779B97F4A7C15ull;
+          hsh ^= hsh >> 29;
+          uint32_t slot = (uint32_t)hsh & a.memo_mask;
+          for (int probe = 0; probe < 32; ++probe, slot = (slot + 1) & a.memo_mask) {
+            const unsigned long long prev = atomicCAS(a.memo_key + slot, 0ull, key);
+            if (prev == 0ull) { a.memo_owner[slot] = i; break; }          // first of its kind: solved below
+            if (prev == key) { alias = slot; pass = false; break; }       // takes the owner's result (alias_kernel)
+          }                                                               // 32 occupied slots in a row: solved on its own
+        }
+      }
+      a.rec_alias[i] = alias;
     }
     const uint32_t pm = __ballot_sync(0xFFFFFFFFu, pass);
     uint32_t base = 0;
     if (lane == 0 && pm) base = atomicAdd(a.counters + 4, __popc(pm));
     base = __shfl_sync(0xFFFFFFFFu, base, 0);
     if (pass) a.work[base + __popc(pm & ((1u << lane) - 1))] = i;
+  }
+}
+
+// Records that share their problem with an earlier one take its result.
+__global__ void __launch_bounds__(256) alias_kernel(const SolveArgs a)
+{
+  if (a.counters[2] & kErrRedo) return;
+  const uint32_t n = a.counters[0] < a.n_records ? a.counters[0] : a.n_records;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t slot = a.rec_alias[i];
+    if (slot == 0xFFFFFFFFu) continue;
+    const uint32_t o = a.memo_owner[slot];
+    a.rec_d[i] = a.rec_d[o]; a.rec_v[i] = a.rec_v[o]; a.rec_flags[i] = 1u; // KREPP_REC_SOLVED
   }
 }
 
@@ -255,7 +287,41 @@ __global__ void __launch_bounds__(128) place_collect_kernel(const PlaceArgs a)
             if (lane == 0) atomicOr(a.counters + 2, kErrNodeOverflow);
             ncount = 0; cnt = 0;
           }
-          // 3. one lane per marked node: a selected leaf brings its own record, an internal node accumulates the leaves below it
+          // 3a. the read's selected references by ascending se (at most one per leaf), and for each the weights it carries to
+          //     its ancestors: level l = its (l+1)-th ancestor, weight = 1 / nch(1st) / ... / nch((l+1)-th), formed by the
+          //     same successive divisions as the reference (ref src/query.cpp:250-259), once per leaf instead of once per
+          //     (leaf, ancestor) pair
+          uint32_t* sel_rec = a.sel + (size_t)gwarp * 3 * a.nleaves;
+          uint32_t* sel_se = sel_rec + a.nleaves;
+          uint32_t* sel_off = sel_se + a.nleaves;
+          double* chain = a.chain + (size_t)gwarp * a.chain_cap;
+          for (uint32_t i = lane; i < n; i += 32) {
+            if (!(s.rec_flags[b + i] & 2u)) continue;
+            const uint32_t se = s.rec_slot[b + i] & 0x7FFFFFFFu;
+            uint32_t rank = 0;
+            for (uint32_t q = 0; q < n; ++q) rank += (s.rec_flags[b + q] & 2u) && (s.rec_slot[b + q] & 0x7FFFFFFFu) < se;
+            sel_rec[rank] = b + i; sel_se[rank] = se;
+          }
+          __syncwarp();
+          uint32_t chain_len = 0;
+          for (uint32_t i0 = 0; i0 < nsel; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            const uint32_t dep = i < nsel ? a.depth[__ldcg(&sel_se[i])] : 0u;
+            uint32_t incl = dep;
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += t; }
+            if (i < nsel) sel_off[i] = chain_len + incl - dep;
+            chain_len += __shfl_sync(0xFFFFFFFFu, incl, 31);
+          }
+          const bool chained = chain_len <= a.chain_cap;
+          __syncwarp();
+          if (chained)
+            for (uint32_t i = lane; i < nsel; i += 32) {
+              double denom = 1.0;
+              uint32_t at = __ldcg(&sel_off[i]);
+              for (uint32_t node = a.parent[__ldcg(&sel_se[i])]; node; node = a.parent[node]) { denom /= (double)a.nchildren[node]; chain[at++] = denom; }
+            }
+          __syncwarp();
+          // 3b. one lane per marked node: a selected leaf brings its own record, an internal node accumulates the leaves below it
           const uint32_t enmers = (uint32_t)(a.offsets[r + 1] - a.offsets[r]) - s.k + 1;
           for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
             const uint32_t j = j0 + lane;
@@ -263,26 +329,25 @@ __global__ void __launch_bounds__(128) place_collect_kernel(const PlaceArgs a)
             if (j < cnt) {
               const uint32_t g = __ldcg(&list[j]), e = nbegin + j;
               double d = DBL_MAX, v = nan(""), leq = 0;
+              const uint32_t lo = g - a.subtree[g]; // leaves below g have lo < se <= g
+              uint32_t first = 0; // first selected reference with se > lo
+              for (uint32_t hi = nsel; first < hi;) { const uint32_t mid = (first + hi) >> 1; if (__ldcg(&sel_se[mid]) > lo) hi = mid; else first = mid + 1; }
               if (a.leaf_rank[g] != 0xFFFFFFFFu) {
-                uint32_t rec = 0xFFFFFFFFu;
-                for (uint32_t i = 0; i < n; ++i) if ((s.rec_flags[b + i] & 2u) && (s.rec_slot[b + i] & 0x7FFFFFFFu) == g) rec = b + i;
+                const uint32_t rec = __ldcg(&sel_rec[first]); // lo = g - 1: the leaf itself
                 d = s.rec_d[rec]; v = s.rec_v[rec];
                 for (uint32_t x = 0; x <= a.tau && x < stride; ++x) leq += (double)s.rec_hist[(size_t)rec * stride + x];
               } else {
                 double mc[kMaxTh + 1];
                 for (uint32_t x = 0; x <= (uint32_t)kMaxTh; ++x) mc[x] = 0;
                 double nmers = 0, mismatch = 0, match = 0, rho = 0;
-                const uint32_t lo = g - a.subtree[g]; // leaves below g have lo < se <= g
-                uint32_t i = b, jx = b + nf;
-                const uint32_t ie = b + nf, je = b + n;
-                while (i < ie || jx < je) { // selected records by ascending leaf se (merge of the two strands' runs)
-                  const uint32_t si = i < ie ? (s.rec_slot[i] & 0x7FFFFFFFu) : 0xFFFFFFFFu, sj = jx < je ? (s.rec_slot[jx] & 0x7FFFFFFFu) : 0xFFFFFFFFu;
-                  uint32_t rec, se;
-                  if (si <= sj) { rec = i; se = si; ++i; if (si == sj) { if (!(s.rec_flags[rec] & 2u)) rec = jx; ++jx; } }
-                  else { rec = jx; se = sj; ++jx; }
-                  if (!(s.rec_flags[rec] & 2u) || !(se > lo && se <= g)) continue;
+                const uint32_t gdep = a.depth[g];
+                for (uint32_t i = first; i < nsel; ++i) { // ascending leaf se: the order Minfo::add is applied in
+                  const uint32_t se = __ldcg(&sel_se[i]);
+                  if (se > g) break;
+                  const uint32_t rec = __ldcg(&sel_rec[i]);
                   double denom = 1.0;
-                  for (uint32_t node = a.parent[se];; node = a.parent[node]) { denom /= (double)a.nchildren[node]; if (node == g) break; }
+                  if (chained) denom = __ldcg(&chain[__ldcg(&sel_off[i]) + a.depth[se] - gdep - 1]);
+                  else for (uint32_t node = a.parent[se];; node = a.parent[node]) { denom /= (double)a.nchildren[node]; if (node == g) break; }
                   const double m = (double)s.rec_match[rec];
                   mismatch = nmers != 0 ? mismatch : (double)enmers;      // Minfo::add (ref src/query.hpp:139-152)
                   match += m * denom;
@@ -427,14 +492,16 @@ cudaError_t launch_place(const PlaceArgs& a, const LlhTables& tab, int grid, int
 cudaError_t launch_solve(const SolveArgs& a, const LlhTables& tab, int sms, cudaStream_t stream, StageClock* clk)
 {
   const int grid = sms * 8;
+  if (a.memo_mask) { const cudaError_t e = cudaMemsetAsync(a.memo_key, 0, 8ull * ((size_t)a.memo_mask + 1), stream); if (e != cudaSuccess) return e; }
   gate_kernel<<<sms * 4, 256, 0, stream>>>(a);
   if (clk) clk->tick("gate_kernel", stream);
   if (a.th + 1 <= 5) solve_kernel<5><<<grid, 128, 0, stream>>>(a, tab);
   else solve_kernel<kMaxTh + 1><<<grid, 128, 0, stream>>>(a, tab);
   if (clk) clk->tick("solve_kernel", stream);
+  if (a.memo_mask) alias_kernel<<<sms * 8, 256, 0, stream>>>(a);
   merge_kernel<<<grid, 128, 0, stream>>>(a);
   if (a.want_chisq) chisq_kernel<<<grid, 128, 0, stream>>>(a, tab);
-  if (clk) clk->tick(a.want_chisq ? "merge_kernel+chisq_kernel" : "merge_kernel", stream);
+  if (clk) clk->tick(a.want_chisq ? "alias_kernel+merge_kernel+chisq_kernel" : "alias_kernel+merge_kernel", stream);
   return cudaGetLastError();
 }
 

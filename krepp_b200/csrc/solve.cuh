@@ -7,7 +7,7 @@ namespace krepp {
 
 // Per-stage CUDA events on the slot's stream (measurement only: bench.py reads them through krepp_batch_stage_times).
 struct StageClock {
-  static constexpr int kMax = 16;
+  static constexpr int kMax = 24;
   cudaEvent_t ev[kMax] = {};
   const char* name[kMax] = {};
   int n = 0;
