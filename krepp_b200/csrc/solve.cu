@@ -216,6 +216,8 @@ __device__ __forceinline__ double jukes_cantor(double d) { return -0.75 * log(1 
 
 // The work is cut so that every Brent minimisation of the batch runs in one thread-per-item kernel with full warps (an
 // internal node costs as much as a record of K4, and a read with 20 selected leaves touches about a hundred nodes):
+// (The per-warp scratch lists in HBM are written and read by the same warp with __syncwarp() in between, i.e. on one SM,
+// so ordinary cached loads see the stores and the lists are served from L1.)
 //   place_collect_kernel  warp per read: gates, the single-reference shortcut, marked nodes in ascending se, one lane per
 //                         node accumulating its weighted histogram -> node entries + work list
 //   place_solve_kernel    thread per internal node entry: the same minimiser as solve_kernel
@@ -270,7 +272,7 @@ __global__ void __launch_bounds__(128) place_collect_kernel(const PlaceArgs a)
           // 2. ascending list of marked nodes
           uint32_t cnt = 0;
           for (uint32_t wb = 0; wb < nbm; wb += 32) {
-            uint32_t bits = (wb + lane < nbm) ? __ldcg(&bm[wb + lane]) : 0u;
+            uint32_t bits = (wb + lane < nbm) ? __ldcg(&bm[wb + lane]) : 0u; // set by atomics, which live in L2
             const uint32_t c = __popc(bits);
             uint32_t incl = c;
             for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += t; }
@@ -306,7 +308,7 @@ __global__ void __launch_bounds__(128) place_collect_kernel(const PlaceArgs a)
           uint32_t chain_len = 0;
           for (uint32_t i0 = 0; i0 < nsel; i0 += 32) {
             const uint32_t i = i0 + lane;
-            const uint32_t dep = i < nsel ? a.depth[__ldcg(&sel_se[i])] : 0u;
+            const uint32_t dep = i < nsel ? a.depth[sel_se[i]] : 0u;
             uint32_t incl = dep;
             for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += t; }
             if (i < nsel) sel_off[i] = chain_len + incl - dep;
@@ -317,8 +319,8 @@ __global__ void __launch_bounds__(128) place_collect_kernel(const PlaceArgs a)
           if (chained)
             for (uint32_t i = lane; i < nsel; i += 32) {
               double denom = 1.0;
-              uint32_t at = __ldcg(&sel_off[i]);
-              for (uint32_t node = a.parent[__ldcg(&sel_se[i])]; node; node = a.parent[node]) { denom /= (double)a.nchildren[node]; chain[at++] = denom; }
+              uint32_t at = sel_off[i];
+              for (uint32_t node = a.parent[sel_se[i]]; node; node = a.parent[node]) { denom /= (double)a.nchildren[node]; chain[at++] = denom; }
             }
           __syncwarp();
           // 3b. one lane per marked node: a selected leaf brings its own record, an internal node accumulates the leaves below it
@@ -327,13 +329,13 @@ __global__ void __launch_bounds__(128) place_collect_kernel(const PlaceArgs a)
             const uint32_t j = j0 + lane;
             bool solve = false;
             if (j < cnt) {
-              const uint32_t g = __ldcg(&list[j]), e = nbegin + j;
+              const uint32_t g = list[j], e = nbegin + j;
               double d = DBL_MAX, v = nan(""), leq = 0;
               const uint32_t lo = g - a.subtree[g]; // leaves below g have lo < se <= g
               uint32_t first = 0; // first selected reference with se > lo
-              for (uint32_t hi = nsel; first < hi;) { const uint32_t mid = (first + hi) >> 1; if (__ldcg(&sel_se[mid]) > lo) hi = mid; else first = mid + 1; }
+              for (uint32_t hi = nsel; first < hi;) { const uint32_t mid = (first + hi) >> 1; if (sel_se[mid] > lo) hi = mid; else first = mid + 1; }
               if (a.leaf_rank[g] != 0xFFFFFFFFu) {
-                const uint32_t rec = __ldcg(&sel_rec[first]); // lo = g - 1: the leaf itself
+                const uint32_t rec = sel_rec[first]; // lo = g - 1: the leaf itself
                 d = s.rec_d[rec]; v = s.rec_v[rec];
                 for (uint32_t x = 0; x <= a.tau && x < stride; ++x) leq += (double)s.rec_hist[(size_t)rec * stride + x];
               } else {
@@ -342,11 +344,11 @@ __global__ void __launch_bounds__(128) place_collect_kernel(const PlaceArgs a)
                 double nmers = 0, mismatch = 0, match = 0, rho = 0;
                 const uint32_t gdep = a.depth[g];
                 for (uint32_t i = first; i < nsel; ++i) { // ascending leaf se: the order Minfo::add is applied in
-                  const uint32_t se = __ldcg(&sel_se[i]);
+                  const uint32_t se = sel_se[i];
                   if (se > g) break;
-                  const uint32_t rec = __ldcg(&sel_rec[i]);
+                  const uint32_t rec = sel_rec[i];
                   double denom = 1.0;
-                  if (chained) denom = __ldcg(&chain[__ldcg(&sel_off[i]) + a.depth[se] - gdep - 1]);
+                  if (chained) denom = chain[sel_off[i] + a.depth[se] - gdep - 1];
                   else for (uint32_t node = a.parent[se];; node = a.parent[node]) { denom /= (double)a.nchildren[node]; if (node == g) break; }
                   const double m = (double)s.rec_match[rec];
                   mismatch = nmers != 0 ? mismatch : (double)enmers;      // Minfo::add (ref src/query.hpp:139-152)
