@@ -158,6 +158,15 @@ int krepp_batch_submit_device(krepp_batch_t* b, const char* d_bases, const uint6
  * on this slot).  Replaces reading IBatch::node_to_minfo / get_summary() (src/query.hpp:64,95). */
 int krepp_batch_wait(krepp_batch_t* b, krepp_results_t* out);
 
+/* Which row arrays krepp_batch_wait copies to the host (default: all).  The text formatters below read `records` and
+ * `placements` but never `hist`; a front end that only prints distances can leave the histograms (4 * (hdist_th + 1)
+ * bytes per record) in HBM and save a quarter of the device-to-host traffic.  Arrays that are not copied come back NULL. */
+#define KREPP_OUT_RECORDS 1u
+#define KREPP_OUT_HIST 2u
+#define KREPP_OUT_PLACEMENTS 4u
+#define KREPP_OUT_ALL 7u
+int krepp_batch_set_output(krepp_batch_t* b, uint32_t rows);
+
 /* The same wait (including the grow-and-rerun of a batch whose result buffers were too small) without copying the record,
  * histogram and placement rows to the host: `reads` (40 bytes per read) and the counts are valid, the three row pointers
  * are NULL and the rows stay in HBM.  For callers that only need the per-read summaries, and for timing the kernels

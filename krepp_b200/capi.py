@@ -109,6 +109,7 @@ def load_library():
     L.krepp_batch_submit_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64]
     L.krepp_batch_wait.argtypes = [C.c_void_p, C.POINTER(Results)]
     L.krepp_batch_wait_device.argtypes = [C.c_void_p, C.POINTER(Results)]
+    L.krepp_batch_set_output.argtypes = [C.c_void_p, C.c_uint32]
     L.krepp_batch_enable_tap.argtypes = [C.c_void_p, C.c_int, C.c_uint64]
     L.krepp_batch_read_tap.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.krepp_batch_algorithmic_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
@@ -289,10 +290,14 @@ class IBatch:
         nrec = int(r.n_records)
         self._res = dict(
             reads=_view(r.reads, READ_DTYPE, r.n_reads), records=_view(r.records, RECORD_DTYPE, nrec),
-            hist=_view(r.hist, np.dtype("<u4"), nrec * r.hist_stride).reshape(nrec, r.hist_stride),
+            hist=_view(r.hist, np.dtype("<u4"), nrec * r.hist_stride).reshape(-1, r.hist_stride),
             placements=_view(r.placements, PLACEMENT_DTYPE, int(r.n_placements)), gpu_ms=float(r.gpu_ms), match_ms=float(r.match_ms),
             gpu_launches=int(r.gpu_launches))
         return self._res
+
+    def set_output(self, records: bool = True, hist: bool = True, placements: bool = True):
+        """krepp_batch_set_output: which row arrays wait() copies to the host (the others come back empty)."""
+        _check(load_library().krepp_batch_set_output(self._h, int(records) | 2 * int(hist) | 4 * int(placements)))
 
     def wait_device(self) -> dict:
         """krepp_batch_wait_device: per-read summaries and counts only; record / placement rows stay in HBM."""

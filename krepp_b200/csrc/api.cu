@@ -138,6 +138,7 @@ struct krepp_batch {
   uint32_t max_reads = 0, rec_cap = 0, n_reads = 0, launches = 0;
   uint64_t max_bases = 0, n_bases = 0;
   bool submitted = false, device_input = false, keep_all = false;
+  uint32_t out_rows = KREPP_OUT_ALL;    // which row arrays krepp_batch_wait copies to the host
   const char* in_bases = nullptr;       // device pointers used by the last submit
   const uint64_t* in_offsets = nullptr;
   // pinned host staging + device inputs
@@ -650,11 +651,18 @@ int krepp_batch_submit_device(krepp_batch_t* b, const char* d_bases, const uint6
   return KREPP_OK;
 }
 
-static int wait_impl(krepp_batch_t* b, krepp_results_t* out, bool copy_rows);
-int krepp_batch_wait(krepp_batch_t* b, krepp_results_t* out) { return wait_impl(b, out, true); }
-int krepp_batch_wait_device(krepp_batch_t* b, krepp_results_t* out) { return wait_impl(b, out, false); }
+static int wait_impl(krepp_batch_t* b, krepp_results_t* out, uint32_t rows);
+int krepp_batch_wait(krepp_batch_t* b, krepp_results_t* out) { return wait_impl(b, out, b ? b->out_rows : 0u); }
+int krepp_batch_wait_device(krepp_batch_t* b, krepp_results_t* out) { return wait_impl(b, out, 0u); }
 
-static int wait_impl(krepp_batch_t* b, krepp_results_t* out, bool copy_rows)
+int krepp_batch_set_output(krepp_batch_t* b, uint32_t rows)
+{
+  if (!b || (rows & ~(uint32_t)KREPP_OUT_ALL)) return fail(KREPP_ERR_ARG, "krepp_batch_set_output: bad argument");
+  b->out_rows = rows;
+  return KREPP_OK;
+}
+
+static int wait_impl(krepp_batch_t* b, krepp_results_t* out, uint32_t rows)
 {
   if (!b || !out) return fail(KREPP_ERR_ARG, "krepp_batch_wait: null argument");
   if (!b->submitted) return fail(KREPP_ERR_ARG, "krepp_batch_wait: nothing was submitted on this slot");
@@ -695,18 +703,16 @@ static int wait_impl(krepp_batch_t* b, krepp_results_t* out, bool copy_rows)
   }
   const uint32_t nrec = b->h_counters[0];
   const size_t stride = b->p.hdist_th + 1;
-  if (nrec && copy_rows) {
-    CU(cudaMemcpyAsync(b->h_rec, b->d_out_rec, sizeof(krepp_record_t) * (size_t)nrec, cudaMemcpyDeviceToHost, b->stream));
-    CU(cudaMemcpyAsync(b->h_hist, b->d_rec_hist, 4ull * nrec * stride, cudaMemcpyDeviceToHost, b->stream));
-  }
+  if (nrec && (rows & KREPP_OUT_RECORDS)) CU(cudaMemcpyAsync(b->h_rec, b->d_out_rec, sizeof(krepp_record_t) * (size_t)nrec, cudaMemcpyDeviceToHost, b->stream));
+  if (nrec && (rows & KREPP_OUT_HIST)) CU(cudaMemcpyAsync(b->h_hist, b->d_rec_hist, 4ull * nrec * stride, cudaMemcpyDeviceToHost, b->stream));
   const uint32_t nplace = b->p.place ? b->h_counters[3] : 0;
-  if (nplace && copy_rows) CU(cudaMemcpyAsync(b->h_place, b->d_place, sizeof(krepp_placement_t) * (size_t)nplace, cudaMemcpyDeviceToHost, b->stream));
+  if (nplace && (rows & KREPP_OUT_PLACEMENTS)) CU(cudaMemcpyAsync(b->h_place, b->d_place, sizeof(krepp_placement_t) * (size_t)nplace, cudaMemcpyDeviceToHost, b->stream));
   CU(cudaStreamSynchronize(b->stream));
   float ms = 0;
   CU(cudaEventElapsedTime(&ms, b->ev0, b->ev1));
   out->n_reads = b->n_reads; out->hist_stride = (uint32_t)stride; out->n_records = nrec; out->n_placements = nplace;
-  out->reads = b->h_read; out->records = copy_rows ? b->h_rec : nullptr; out->hist = copy_rows ? b->h_hist : nullptr;
-  out->placements = nplace && copy_rows ? b->h_place : nullptr;
+  out->reads = b->h_read; out->records = (rows & KREPP_OUT_RECORDS) ? b->h_rec : nullptr; out->hist = (rows & KREPP_OUT_HIST) ? b->h_hist : nullptr;
+  out->placements = nplace && (rows & KREPP_OUT_PLACEMENTS) ? b->h_place : nullptr;
   float mms = 0;
   CU(cudaEventElapsedTime(&mms, b->evm0, b->evm1));
   out->gpu_ms = ms; out->match_ms = mms; out->gpu_launches = b->launches;
