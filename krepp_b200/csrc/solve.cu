@@ -81,7 +81,8 @@ __global__ void __launch_bounds__(256) gate_kernel(const SolveArgs a)
           hsh ^= hsh >> 29;
           uint32_t slot = (uint32_t)hsh & a.memo_mask;
           for (int probe = 0; probe < 32; ++probe, slot = (slot + 1) & a.memo_mask) {
-            const unsigned long long prev = atomicCAS(a.memo_key + slot, 0ull, key);
+            unsigned long long prev = __ldcg(a.memo_key + slot); // a slot never changes once set: most records find their key with a plain load
+            if (prev == 0ull) prev = atomicCAS(a.memo_key + slot, 0ull, key);
             if (prev == 0ull) { a.memo_owner[slot] = i; break; }          // first of its kind: solved below
             if (prev == key) { alias = slot; pass = false; break; }       // takes the owner's result (alias_kernel)
           }                                                               // 32 occupied slots in a row: solved on its own

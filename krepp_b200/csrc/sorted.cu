@@ -73,12 +73,23 @@ __global__ void __launch_bounds__(kLkWarps * 32, 2) lookup_kernel(const DevIndex
     for (uint64_t t0 = 0; t0 + k <= len; t0 += kTileWindows) {
       const uint32_t nl = tile_lookups<TAP && !SCATTER>(ix, a, sm, lut, wide, read, off, len, t0, onmers, wn0, wn1);
       if (loc + nl >= kMaxLoc) { if (lane == 0) atomicOr(a.counters + 2, kErrSortFallback); break; }
-      for (uint32_t i = lane; i < nl; i += 32) {
-        const uint32_t ob = sm.lk_a[i], row = ob & 0x7FFFFFFFu;
-        if (!SCATTER) atomicAdd(&s.row_count[row], 1u);
-        else {
-          const uint32_t pos = atomicAdd(&s.row_cursor[row], 1u);
-          s.tuples[pos] = make_uint4(sm.lk_q[i], read, (loc + i) | (ob & 0x80000000u), 0u);
+      if (!SCATTER) {
+        for (uint32_t i = lane; i < nl; i += 32) atomicAdd(&s.row_count[sm.lk_a[i] & 0x7FFFFFFFu], 1u);
+      } else {
+        // the cursor atomics return positions: four are kept in flight per lane before the stores that need them
+        for (uint32_t i0 = lane; i0 < nl; i0 += 128) {
+          uint32_t ob[4], pos[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t i = i0 + 32 * u;
+            ob[u] = 0; pos[u] = 0;
+            if (i < nl) { ob[u] = sm.lk_a[i]; pos[u] = atomicAdd(&s.row_cursor[ob[u] & 0x7FFFFFFFu], 1u); }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t i = i0 + 32 * u;
+            if (i < nl) s.tuples[pos[u]] = make_uint4(sm.lk_q[i], read, (loc + i) | (ob[u] & 0x80000000u), 0u);
+          }
         }
       }
       loc += nl;
@@ -340,6 +351,43 @@ __device__ __forceinline__ void bitonic_sort(K* keys, uint32_t n) // n: power of
   }
 }
 
+// The same network with the keys in registers, E per lane (key i sits in lane i / E, slot i % E): exchanges between lanes
+// are shuffles, exchanges inside a lane are register swaps.  n = 32 * E.
+template <typename K, int E>
+__device__ __forceinline__ void bitonic_sort_regs(K* keys)
+{
+  const uint32_t lane = threadIdx.x & 31;
+  K v[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) v[e] = keys[lane * E + e];
+#pragma unroll
+  for (int k = 2; k <= 32 * E; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= E) { // partner in lane ^ (j / E), same slot
+        const bool lower = (lane & (uint32_t)(j / E)) == 0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const bool up = ((lane * E + e) & (uint32_t)k) == 0;
+          const K o = __shfl_xor_sync(0xFFFFFFFFu, v[e], j / E);
+          v[e] = (lower == up) ? (v[e] < o ? v[e] : o) : (v[e] < o ? o : v[e]);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          if ((e & j) == 0) {
+            const bool up = ((lane * E + e) & (uint32_t)k) == 0;
+            const K x = v[e], y = v[e | j];
+            if ((x > y) == up) { v[e] = y; v[e | j] = x; }
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < E; ++e) keys[lane * E + e] = v[e];
+}
+
 struct ResolveOut { uint32_t total, rbegin; bool fits; };
 
 // One read's leaf hits, as sorted keys strand | leaf rank | lookup | hd, to its records (see the header).  seg_shift =
@@ -468,7 +516,12 @@ __device__ __forceinline__ ResolveOut resolve_read(const DevIndex& ix, const Mat
   while (n < T) n <<= 1;
   for (uint32_t i = T + lane; i < n; i += 32) keys[i] = ~(K)0; // never a real key: hd <= 16 < 31
   __syncwarp();
-  bitonic_sort(keys, n);
+  if (n == 32) bitonic_sort_regs<K, 1>(keys);
+  else if (n == 64) bitonic_sort_regs<K, 2>(keys);
+  else if (n == 128) bitonic_sort_regs<K, 4>(keys);
+  else if (n == 256 && sizeof(K) == 4) bitonic_sort_regs<K, (sizeof(K) == 4 ? 8 : 4)>(keys);
+  else bitonic_sort(keys, n);
+  __syncwarp();
   return emit_sorted<K>(ix, a, keys, T, seg_shift, rank_bits, read, g0, g1, small_counts);
 }
 
