@@ -57,6 +57,7 @@ struct krepp_reader {
   uint64_t qual_left = 0;
   bool fresh = false;        // name/seq still hold the record returned last; cleared when parsing resumes
   bool have_pending = false; // a complete record that did not fit the previous batch
+  bool fast = true;          // four-line FASTQ fast path (KREPP_READER_FAST=0 leaves every record to the state machine)
   std::string pend_name, pend_seq;
 };
 
@@ -148,6 +149,79 @@ bool next_record(krepp_reader* r)
 
 } // namespace
 
+namespace {
+
+inline uint64_t load8(const unsigned char* p) { uint64_t x; memcpy(&x, p, 8); return x; }
+// true when every byte of [p, p + n) is a sequence character: 33..126 and none of '>', '@', '+' (ByteClass::seq == 1)
+inline bool all_seq_chars(const unsigned char* p, size_t n)
+{
+  const uint64_t k01 = 0x0101010101010101ull, k80 = 0x8080808080808080ull;
+  auto has = [&](uint64_t x, unsigned char c) { const uint64_t y = x ^ (k01 * c); return ((y - k01) & ~y & k80) != 0; }; // some byte == c
+  size_t i = 0;
+  for (; i + 8 <= n; i += 8) {
+    const uint64_t x = load8(p + i);
+    if (x & k80) return false;                                   // a byte >= 128
+    if (((x - k01 * 33) & ~x & k80) != 0) return false;          // a byte < 33 (no byte has its top bit set here)
+    if (has(x, 127) || has(x, '>') || has(x, '@') || has(x, '+')) return false;
+  }
+  for (; i < n; ++i) if (kClass.seq[p[i]] != 1) return false;
+  return true;
+}
+// true when every byte of [p, p + n) is a quality character as the Qual state counts them: 33..127
+inline bool all_qual_chars(const unsigned char* p, size_t n)
+{
+  const uint64_t k01 = 0x0101010101010101ull, k80 = 0x8080808080808080ull;
+  size_t i = 0;
+  for (; i + 8 <= n; i += 8) {
+    const uint64_t x = load8(p + i);
+    if ((x & k80) || ((x - k01 * 33) & ~x & k80)) return false;
+  }
+  for (; i < n; ++i) if (p[i] < 33 || p[i] > 127) return false;
+  return true;
+}
+
+// Fast path of krepp_reader_next for the overwhelmingly common record: a four-line FASTQ record lying whole in the buffer.
+// With the parser in state Seek at an '@', it is recognised by three memchr()s and two range checks and copied straight into
+// the batch arrays; the conditions are exactly those under which the state machine of next_record() would walk
+// Name[/Comment] -> Seq (one unbroken run of sequence characters, then the newline, then '+') -> Plus -> Qual (as many
+// quality characters as bases, back to back) -> QualTail (one more byte) -> Seek.  Anything else -- FASTA, wrapped lines,
+// stray characters, a record cut by the end of the buffer -- returns false and is left to the state machine.
+bool fast_fastq(krepp_reader* r, char* bases, uint64_t max_bases, uint64_t& nb, char* names, uint64_t max_name_bytes, uint64_t& nn,
+                uint64_t* offsets, uint64_t* name_offsets, uint32_t& n)
+{
+  const unsigned char* const b0 = r->buf.data();
+  const unsigned char* p = b0 + r->at;
+  const unsigned char* const e = b0 + r->end;
+  if (p >= e || *p != '@') return false;
+  const unsigned char* nl1 = static_cast<const unsigned char*>(memchr(p + 1, '\n', e - (p + 1)));
+  if (!nl1) return false;
+  const unsigned char* ne = p + 1;
+  while (!kClass.space[*ne]) ++ne;                                  // stops at nl1 at the latest
+  const size_t name_len = ne - (p + 1);
+  if (name_len == 0) return false;
+  const unsigned char* sq = nl1 + 1;
+  const unsigned char* nl2 = static_cast<const unsigned char*>(memchr(sq, '\n', e - sq));
+  if (!nl2 || nl2 + 1 >= e || nl2[1] != '+') return false;
+  const size_t len = nl2 - sq;
+  if (!all_seq_chars(sq, len)) return false;
+  const unsigned char* nl3 = static_cast<const unsigned char*>(memchr(nl2 + 1, '\n', e - (nl2 + 1)));
+  if (!nl3) return false;
+  const unsigned char* q = nl3 + 1;
+  if ((size_t)(e - q) < len + 1 || !all_qual_chars(q, len)) return false; // the byte after the last quality character is consumed too
+  if (nb + len > max_bases || nn + name_len + 1 > max_name_bytes) return false; // does not fit: the general path keeps it for the next batch
+  memcpy(bases + nb, sq, len);
+  nb += len;
+  name_offsets[n] = nn;
+  memcpy(names + nn, p + 1, name_len);
+  names[nn + name_len] = 0;
+  nn += name_len + 1;
+  offsets[++n] = nb;
+  r->at = (q + len + 1) - b0;
+  return true;
+}
+
+} // namespace
+
 extern "C" int krepp_reader_open(const char* path, krepp_reader_t** out)
 {
   if (!path || !out) return set_error(KREPP_ERR_ARG, "krepp_reader_open: null argument");
@@ -158,6 +232,7 @@ extern "C" int krepp_reader_open(const char* path, krepp_reader_t** out)
   auto* r = new krepp_reader;
   r->f = f;
   r->buf.resize(4 << 20);
+  if (const char* env = getenv("KREPP_READER_FAST")) r->fast = strcmp(env, "0") != 0;
   *out = r;
   return KREPP_OK;
 }
@@ -196,6 +271,7 @@ extern "C" int krepp_reader_next(krepp_reader_t* r, char* bases, uint64_t max_ba
   }
   for (;;) {
     if (n >= max_reads) break;
+    if (r->fast && r->st == St::Seek && fast_fastq(r, bases, max_bases, nb, names, max_name_bytes, nn, offsets, name_offsets, n)) continue;
     if (!next_record(r)) { *eof = 1; break; }
     if (!fits(r->name, r->seq)) {
       if (n == 0) return set_error(KREPP_ERR_CAPACITY, "a single sequence of %zu bases (name of %zu bytes) does not fit the batch buffers", r->seq.size(), r->name.size());

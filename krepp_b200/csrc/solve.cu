@@ -231,7 +231,16 @@ __global__ void __launch_bounds__(128) place_collect_kernel(const PlaceArgs a)
   const uint32_t lane = threadIdx.x & 31, lt_mask = (1u << lane) - 1u;
   const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   const uint32_t stride = s.th + 1, nbm = (a.nnodes + 32) >> 5;
+  // marked-node bitmap of the warp: in shared memory when the tree has at most 8,192 nodes (marking is a chain of dependent
+  // atomics up the tree, a microsecond each in L2), else in the warp's HBM scratch (zeroed at allocation, left clean by step 2)
+  constexpr uint32_t kSmemBm = 256;
+  __shared__ uint32_t sbm[kPlaceWarpsPerCta][kSmemBm];
   uint32_t* bm = a.node_bitmap + (size_t)gwarp * nbm;
+  if (nbm <= kSmemBm) {
+    bm = sbm[threadIdx.x >> 5];
+    for (uint32_t i = lane; i < nbm; i += 32) bm[i] = 0;
+    __syncwarp();
+  }
   uint32_t* list = a.node_list + (size_t)gwarp * a.nnodes;
   krepp_placement_t* out = static_cast<krepp_placement_t*>(a.placements);
 
@@ -273,7 +282,7 @@ __global__ void __launch_bounds__(128) place_collect_kernel(const PlaceArgs a)
           // 2. ascending list of marked nodes
           uint32_t cnt = 0;
           for (uint32_t wb = 0; wb < nbm; wb += 32) {
-            uint32_t bits = (wb + lane < nbm) ? __ldcg(&bm[wb + lane]) : 0u; // set by atomics, which live in L2
+            uint32_t bits = (wb + lane < nbm) ? *reinterpret_cast<volatile uint32_t*>(&bm[wb + lane]) : 0u; // set by atomics
             const uint32_t c = __popc(bits);
             uint32_t incl = c;
             for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += t; }

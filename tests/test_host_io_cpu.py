@@ -243,3 +243,57 @@ def test_fixed5_equals_printf(K, small):
     names = ["q"] * n
     got = K.format_dist(small["index"], K.Params(4, 2.706, float("nan"), 2, 1, 1, 0, 0), res, names).splitlines()
     assert [l.split("\t")[2] for l in got] == ["%.5f" % v for v in vals]
+
+
+def test_reader_fast_path_equals_state_machine(K, tmp_path, monkeypatch):
+    """The four-line FASTQ fast path (memchr + range checks) must frame every input exactly as the byte-wise state machine
+    (KREPP_READER_FAST=0): well-formed records mixed with everything that has to fall back -- wrapped sequence / quality
+    lines, CRLF, comments, '@' / '+' / '>' inside quality strings, blank lines, FASTA records, short or missing quality,
+    non-printable bytes -- and records cut by the 4 MB read buffer."""
+    import random
+    rng = random.Random(5)
+    alpha = b"ACGTNacgtn"
+
+    def seq(n):
+        return bytes(rng.choice(alpha) for _ in range(n))
+
+    def qual(n, nasty=False):
+        pool = b"IIIIFFF#5:<" + (b"@+>" if nasty else b"")
+        return bytes(rng.choice(pool) for _ in range(n))
+
+    def record(i):
+        n = rng.choice([0, 1, 7, 26, 27, 150, 150, 150, 151, 300])
+        s, kind = seq(n), rng.randrange(12)
+        name = b"r%d" % i
+        if kind <= 4:
+            return b"@" + name + b"\n" + s + b"\n+\n" + qual(n) + b"\n"
+        if kind == 5:
+            return b"@" + name + b" some comment\tx\n" + s + b"\n+" + name + b"\n" + qual(n, True) + b"\n"
+        if kind == 6:
+            return b"@" + name + b"\r\n" + s + b"\r\n+\r\n" + qual(n) + b"\r\n"
+        if kind == 7:  # wrapped lines
+            h = n // 2
+            return b"@" + name + b"\n" + s[:h] + b"\n" + s[h:] + b"\n+\n" + qual(n)[:h] + b"\n" + qual(n)[h:] + b"\n"
+        if kind == 8:
+            return b">" + name + b" fasta\n" + s[:n // 3] + b"\n" + s[n // 3:] + b"\n"
+        if kind == 9:
+            return b"\n\n@" + name + b"\n" + s + b"\n+\n" + qual(max(n - 3, 0)) + b"\n"  # short quality: runs into what follows
+        if kind == 10:
+            return b"@" + name + b"\n" + s[:n // 2] + b" \x01" + s[n // 2:] + b"\n+\n" + qual(n) + b"\n"
+        return b"@" + name + b"\n" + s + b"\n+\n" + qual(n) + b"x\n"  # one extra character after the quality string
+
+    def parse(path, fast, **kw):
+        monkeypatch.setenv("KREPP_READER_FAST", "1" if fast else "0")
+        return K.Reader(str(path)).read_all(**kw)
+
+    small = tmp_path / "mix.fq"
+    small.write_bytes(b"".join(record(i) for i in range(3000)))
+    a, b = parse(small, True), parse(small, False)
+    assert a == b and len(a[0]) > 2500
+    assert parse(small, True, max_reads=97, max_bases=4000) == b          # batch boundaries fall anywhere
+    big = tmp_path / "big.fq"                                             # > 4 MB: records straddle the read buffer
+    with open(big, "wb") as f:
+        for i in range(30000):
+            f.write(b"@q%d\n" % i + seq(150) + b"\n+\n" + qual(150) + b"\n" if i % 50 else record(i))
+    a, b = parse(big, True), parse(big, False)
+    assert a == b and len(a[0]) > 29000

@@ -5,18 +5,18 @@
 O=${1:-gpurun_out/cli}; N=${2:-200000}; mkdir -p $O
 D=$(python -c "import sys; sys.path.insert(0,'tools'); import workload as W; print(W.ensure_c3($N, fastq_reads=$N)[0])")
 T=$(nproc)
-( /usr/bin/time -v oracle/_ref/krepp --num-threads $T dist -i $D/index -q $D/reads.fq -o /tmp/ref_dist.tsv ) > $O/ref_dist.log 2>&1
-( /usr/bin/time -v krepp_b200/_build/krepp_b200 --num-threads $T dist -i $D/index -q $D/reads.fq -o /tmp/gpu_dist.tsv ) > $O/gpu_dist.log 2>&1
-( /usr/bin/time -v oracle/_ref/krepp --num-threads $T place -i $D/index -q $D/reads.fq -o /tmp/ref_place.jplace ) > $O/ref_place.log 2>&1
-( /usr/bin/time -v krepp_b200/_build/krepp_b200 --num-threads $T place -i $D/index -q $D/reads.fq -o /tmp/gpu_place.jplace ) > $O/gpu_place.log 2>&1
+( TIMEFORMAT="wall %R s"; time oracle/_ref/krepp --num-threads $T dist -i $D/index -q $D/reads.fq -o /tmp/ref_dist.tsv ) > $O/ref_dist.log 2>&1
+( TIMEFORMAT="wall %R s"; time krepp_b200/_build/krepp_b200 --num-threads $T dist -i $D/index -q $D/reads.fq -o /tmp/gpu_dist.tsv ) > $O/gpu_dist.log 2>&1
+( TIMEFORMAT="wall %R s"; time oracle/_ref/krepp --num-threads $T place -i $D/index -q $D/reads.fq -o /tmp/ref_place.jplace ) > $O/ref_place.log 2>&1
+( TIMEFORMAT="wall %R s"; time krepp_b200/_build/krepp_b200 --num-threads $T place -i $D/index -q $D/reads.fq -o /tmp/gpu_place.jplace ) > $O/gpu_place.log 2>&1
 python - $O $N $T <<'PY' | tee $O/cli_c3.txt
 import re, sys, json
 O, N, T = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
 def t(log, what):
     s = open(f"{O}/{log}.log").read()
     el = re.search(r"Done (?:estimating distances|placing queries), elapsed: ([0-9.eE+-]+) sec", s)
-    wall = re.search(r"Elapsed \(wall clock\) time \(h:mm:ss or m:ss\): (?:(\d+):)?(\d+):([0-9.]+)", s)
-    w = (int(wall.group(1) or 0) * 3600 + int(wall.group(2)) * 60 + float(wall.group(3))) if wall else float("nan")
+    wall = re.search(r"wall ([0-9.]+) s", s)
+    w = float(wall.group(1)) if wall else float("nan")
     return (float(el.group(1)) if el else float("nan")), w
 print(f"# config 3 drop-in check: {N} reads (150 bp) against the 1,000-genome index, --num-threads {T}")
 for cmd in ("dist", "place"):
