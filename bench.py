@@ -56,9 +56,14 @@ WORKLOADS = {
           "1,000-genome table of configs[2] stands in for one that exceeds a GPU's HBM, a 10,000-genome index cannot be generated on the "
           "box within the bench's minutes), all-to-all of lookups and of hit entries over NCCL/NVLink, krepp dist",
 }
-# dram__bytes_read.sum + dram__bytes_write.sum of one match_kernel launch (ncu --set full, summarised under profiles/),
-# keyed by (workload, reads in that launch); scaled linearly to the launch size the bench uses.
-NCU_TRAFFIC = {"c3": (250_000, 28.898431e9 + 1.543418e9, "profiles/r01l_match_c3.txt")}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the same command
+# at the same batch size (tools/gpu_round.sh -> profiles/<tag>_chain_full.txt), keyed by workload then kernel.
+NCU_TRAFFIC = {"c3": {"source": "profiles/r06m_chain_full.txt", "batch_reads": 1_000_000, "kernels": {}}}
+try:
+    with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as _f:
+        NCU_TRAFFIC = json.load(_f)
+except Exception:
+    pass
 
 
 class Workload:
@@ -454,10 +459,21 @@ def main() -> None:
     match_name = ("match step, bucket-sorted pipeline: lookup_kernel x2 + scans + join_kernel + hit_scatter_kernel + resolve_kernel"
                   if sorted_pipeline else "match_kernel")
     dom = max(stage_ms, key=stage_ms.get) if stage_ms else "match_kernel"
-    traffic = None
-    if args.workload in NCU_TRAFFIC and not sorted_pipeline:
-        per, tb, _src = NCU_TRAFFIC[args.workload]
-        traffic = tb * (batch / per)
+    # ncu DRAM traffic of the match step's kernels, per launch of `batch` reads (null when the capture was taken at another batch size)
+    nt = NCU_TRAFFIC.get(args.workload, {})
+    kt = nt.get("kernels", {}) if nt.get("batch_reads") == batch and args.mode == "dist" else {}
+    chain = ["lookup_kernel<count>", "lookup_kernel<scatter>", "join_kernel", "hit_scatter_kernel", "resolve_kernel"] if sorted_pipeline else ["match_kernel"]
+    traffic = sum(kt[k] for k in chain) if kt and all(k in kt for k in chain) else None
+    # the dominant kernel on its own.  For join_kernel the algorithmic bytes are the bucket bytes of every lookup (8 B per entry
+    # scanned, SURVEY 8d: no credit for reuse); the kernel reads each bucket ONCE per batch for all its lookups, which is why its
+    # algorithmic rate exceeds the HBM peak while its DRAM traffic is a small fraction of the algorithmic bytes.
+    dom_obj = {"name": dom, "ms_per_launch": stage_ms.get(dom, 0.0) / launches_per_step,
+               "share_of_step": stage_ms.get(dom, 0.0) / (t_dev * 1e3 / args.steps)}
+    if dom == "join_kernel":
+        ab = 8.0 * last["entries"] / launches_per_step
+        dom_obj.update({"algorithmic_bytes_per_launch": ab, "achieved": ab / (dom_obj["ms_per_launch"] / 1e3) / 1e9, "unit": "GB/s",
+                        "frac": ab / (dom_obj["ms_per_launch"] / 1e3) / 1e9 / peak, "traffic": kt.get("join_kernel"),
+                        "bound": "issue slots / popc pipe, not DRAM (ncu: 72 % issue-active; DRAM traffic ~ 1/10 of the algorithmic bytes)"})
     wname = WORKLOADS[args.workload]
     if args.mode == "place":
         wname = wname.replace("configs[2]", "configs[3]").replace("krepp dist", "krepp place (per-read candidate placements: records of the jplace output)")
@@ -474,10 +490,9 @@ def main() -> None:
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": match_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "stages_ms_per_step": {k: round(v, 3) for k, v in stage_ms.items()},
-                     "dominant_kernel": {"name": dom, "ms_per_launch": stage_ms.get(dom, 0.0) / launches_per_step,
-                                         "share_of_step": stage_ms.get(dom, 0.0) / (t_dev * 1e3 / args.steps)},
+                     "dominant_kernel": dom_obj,
                      "whole_step_frac": (last["alg"] / (t_dev / args.steps) / 1e9) / peak,
-                     "traffic": traffic, "traffic_source": NCU_TRAFFIC.get(args.workload, (0, 0, None))[2],
+                     "traffic": traffic, "traffic_source": nt.get("source"),
                      "algorithmic_bytes_per_launch": last["alg"] / launches_per_step,
                      "lookups_per_launch": last["lookups"] / launches_per_step, "entries_scanned_per_launch": last["entries"] / launches_per_step,
                      "launches_per_step": launches_per_step, "match_ms_per_launch": mm / launches_per_step,

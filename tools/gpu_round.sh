@@ -14,9 +14,9 @@ timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_ref
 timeout 900 python bench.py > $O/bench.json 2> $O/bench.err; echo "bench rc=$?"; cat $O/bench.json; tail -3 $O/bench.err
 timeout 600 python bench.py --workload toy --no-cpu-baseline > $O/bench_toy.json 2> $O/bench_toy.err; echo "bench toy rc=$?"; cat $O/bench_toy.json; tail -3 $O/bench_toy.err
 if [ "$2" != "skip-ncu" ]; then
-  CMD="python bench.py --reads 1000000 --batch 250000 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e"
+  CMD="python bench.py --reads 2000000 --batch 1000000 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e"  # launches of 1M reads, as the bench line
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv $CMD > $O/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
-  # one batch's worth of the heavy kernels (8 matching launches per batch; the 4 warm-up batches are skipped)
-  timeout 1500 ncu --set full --clock-control none --import-source on -k "regex:lookup_kernel|join_kernel|hit_scatter_kernel|resolve_kernel|gate_kernel|solve_kernel|alias_kernel" -s 32 -c 8 -f -o $O/chain_full $CMD > $O/ncu_full.log 2>&1; echo "ncu full rc=$?"
+  # one batch's worth of the heavy kernels (8 matching launches per batch; the 2 warm-up batches are skipped)
+  timeout 1500 ncu --set full --clock-control none --import-source on -k "regex:lookup_kernel|join_kernel|hit_scatter_kernel|resolve_kernel|gate_kernel|solve_kernel|alias_kernel" -s 16 -c 8 -f -o $O/chain_full $CMD > $O/ncu_full.log 2>&1; echo "ncu full rc=$?"
 fi
 ls -la $O

@@ -3,7 +3,8 @@
    profiles/<tag>_launches.txt   per-kernel totals and shares from the ncu launch list (gpu__time_duration.sum)
    profiles/<tag>_<rep>.txt      selected raw metrics + hottest source lines of every *.ncu-rep capture (--set full)
    profiles/<tag>_bench.json     the bench lines of that run
-usage: profile_summary.py gpurun_out/<tag> [out_tag]"""
+usage: profile_summary.py gpurun_out/<tag> [out_tag [batch_reads_of_the_full_capture]]   (the third argument also writes
+profiles/ncu_traffic.json from chain_full.ncu-rep)"""
 import csv
 import glob
 import io
@@ -64,9 +65,35 @@ def capture(rep, out, top=40):
         f.write("\n## hottest source lines (share of executed warp instructions / of stall samples)\n" + src)
 
 
+def traffic_json(rep, out, source, batch_reads):
+    """profiles/ncu_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per launch of every kernel of the chain, as
+    bench.py's roofline.traffic quotes them (valid for launches of `batch_reads` reads on the config-3 workload)."""
+    import json
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    if len(rows) < 3:
+        return
+    hdr, units = rows[0], rows[1]
+    ik, ir, iw = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    names = [("lookup_kernel<0", "lookup_kernel<count>"), ("lookup_kernel<1", "lookup_kernel<scatter>"), ("join_kernel", "join_kernel"),
+             ("hit_scatter_kernel", "hit_scatter_kernel"), ("resolve_kernel", "resolve_kernel"), ("gate_kernel", "gate_kernel"),
+             ("solve_kernel", "solve_kernel"), ("alias_kernel", "alias_kernel")]
+    k = {}
+    for vals in rows[2:]:
+        for pat, key in names:
+            if pat in vals[ik] and key not in k:
+                k[key] = float(vals[ir].replace(",", "")) * mult[units[ir]] + float(vals[iw].replace(",", "")) * mult[units[iw]]
+    with open(out, "w") as f:
+        json.dump({"c3": {"source": source, "batch_reads": batch_reads, "kernels": k}}, f, indent=1)
+        f.write("\n")
+
+
 def main():
     d = sys.argv[1].rstrip("/")
     tag = sys.argv[2] if len(sys.argv) > 2 else os.path.basename(d)
+    if len(sys.argv) > 3 and os.path.exists(os.path.join(d, "chain_full.ncu-rep")):
+        traffic_json(os.path.join(d, "chain_full.ncu-rep"), os.path.join(ROOT, "profiles", "ncu_traffic.json"), f"profiles/{tag}_chain_full.txt", int(sys.argv[3]))
     P = os.path.join(ROOT, "profiles")
     os.makedirs(P, exist_ok=True)
     for lc in glob.glob(os.path.join(d, "launches*.csv")):
