@@ -303,7 +303,7 @@ def main() -> None:
     ap.add_argument("--mode", default="dist", choices=["dist", "place"], help="place = BASELINE configs[3]: krepp place (K5 placement kernel on top of dist)")
     ap.add_argument("--reads", type=int, default=0, help="reads per GPU per step (default: 10M for c3, 1M for toy)")
     ap.add_argument("--batch", type=int, default=0, help="reads per batch of the device-resident arm")
-    ap.add_argument("--e2e-batch", type=int, default=250_000)
+    ap.add_argument("--e2e-batch", type=int, default=500_000)
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -403,8 +403,11 @@ def main() -> None:
         h_reads = torch.from_numpy(reads.reshape(-1)).pin_memory()  # the step's inputs live in page-locked host memory
         h_offs = (np.arange(eb + 1, dtype=np.uint64) * np.uint64(READ_LEN))
         slots = [krepp_b200.IBatch(index, reads[:eb], **mode_kw) for _ in range(nslots)]
-        for s_ in slots:
-            s_.set_output(hist=False)  # what the dist / place front end asks for: its writers never read the histograms
+        for s_ in slots:  # what the CLI asks for (cli.cpp): dist prints from the 16-byte rows, place from the full rows; no writer reads the histograms
+            if args.mode == "dist":
+                s_.set_output(records=False, hist=False, placements=False, brief=True)
+            else:
+                s_.set_output(hist=False)
         echunks = [(i, min(eb, n - i)) for i in range(0, n, eb)]
         h2d = n * READ_LEN + 8 * sum(c + 1 for _, c in echunks)
         base_ptr = h_reads.data_ptr()
@@ -415,14 +418,14 @@ def main() -> None:
                 s = slots[j % nslots]
                 if len(inflight) == nslots:
                     res = inflight.pop(0).wait()
-                    d2h += res["reads"].nbytes + res["records"].nbytes + res["hist"].nbytes + res["placements"].nbytes
-                    nrec += len(res["records"])
+                    d2h += res["reads"].nbytes + res["records"].nbytes + res["hist"].nbytes + res["placements"].nbytes + res["brief"].nbytes
+                    nrec += res["n_records"]
                 s.submit_host(base_ptr + first * READ_LEN, h_offs.ctypes.data, cnt)
                 inflight.append(s)
             for s in inflight:
                 res = s.wait()
-                d2h += res["reads"].nbytes + res["records"].nbytes + res["hist"].nbytes + res["placements"].nbytes
-                nrec += len(res["records"])
+                d2h += res["reads"].nbytes + res["records"].nbytes + res["hist"].nbytes + res["placements"].nbytes + res["brief"].nbytes
+                nrec += res["n_records"]
             return d2h, nrec
 
         for _ in range(args.warmup):
@@ -437,8 +440,9 @@ def main() -> None:
             dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
         e2e = world * n * args.steps / float(t_e2e.item())
         e2e_out = {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "records_per_step": nrec_e2e,
-                   "how": f"krepp_batch_submit from page-locked host memory + krepp_batch_wait (all read summaries and record / placement rows copied back; the Hamming "
-                          f"histograms, which no writer of the CLI reads, stay in HBM: krepp_batch_set_output), "
+                   "how": f"krepp_batch_submit from page-locked host memory + krepp_batch_wait with the output the CLI asks for (krepp_batch_set_output): every read "
+                          f"summary and, for dist, every record as a 16-byte row (read, reference, flags, distance); for place the full record and placement rows; "
+                          f"the Hamming histograms, which no writer reads, stay in HBM; "
                           f"{nslots} slots x {eb} reads pipelined, wall clock, max over ranks"}
         for s in slots:
             s.close()

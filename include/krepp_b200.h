@@ -116,6 +116,18 @@ typedef struct {
   int32_t closest;                   /* index into records[] of mi_closest, -1 when node_to_minfo is empty */
 } krepp_read_summary_t;
 
+/* The 16-byte form of a record, for front ends that only print distances (`krepp dist`): what report_distances
+ * (src/query.cpp:158-196) reads of a Minfo.  Same order and indices as records[]. */
+typedef struct {
+  uint32_t read;
+  uint32_t ref;   /* leaf_se | strand << 27 | flags (KREPP_REC_*) << 28 | (chisq < params.chisq) << 31 */
+  double d_llh;
+} krepp_brief_t;
+#define KREPP_BRIEF_SE(ref) ((ref) & 0x07FFFFFFu)
+#define KREPP_BRIEF_STRAND(ref) (((ref) >> 27) & 1u)
+#define KREPP_BRIEF_FLAGS(ref) (((ref) >> 28) & 7u)
+#define KREPP_BRIEF_CHISQ_OK(ref) ((ref) >> 31)
+
 typedef struct {
   uint32_t n_reads;
   uint32_t hist_stride;               /* hdist_th + 1 */
@@ -127,6 +139,7 @@ typedef struct {
   float gpu_ms;                       /* device time of all kernels of this batch, copies excluded (CUDA events on the slot's stream) */
   float match_ms;                     /* device time of the match kernel alone (same stream, CUDA events) */
   uint32_t gpu_launches;              /* kernels launched for this batch */
+  const krepp_brief_t* brief;         /* [n_records] when KREPP_OUT_BRIEF was asked for, else NULL */
 } krepp_results_t;
 
 /* -------------------------------------------------------------------------------------------------- batches */
@@ -165,6 +178,8 @@ int krepp_batch_wait(krepp_batch_t* b, krepp_results_t* out);
 #define KREPP_OUT_HIST 2u
 #define KREPP_OUT_PLACEMENTS 4u
 #define KREPP_OUT_ALL 7u
+#define KREPP_OUT_BRIEF 8u /* krepp_brief_t rows (16 bytes per record instead of 56 + histogram); not part of KREPP_OUT_ALL.
+                              krepp_format_dist reads them when `records` is NULL. */
 int krepp_batch_set_output(krepp_batch_t* b, uint32_t rows);
 
 /* The same wait (including the grow-and-rerun of a batch whose result buffers were too small) without copying the record,
@@ -270,7 +285,7 @@ size_t krepp_format_header(const krepp_index_t* ix, const krepp_params_t* p, int
                            char* buf, size_t cap);
 /* IBatch::report_distances for every read of a batch (src/query.cpp:158-196): reads in input order, references by
  * ascending se.  With p->summarize the rows are not written; the per-node weights are added to wcount[nnodes+1]
- * instead (src/query.cpp:160-171) and 0 is returned. */
+ * instead (src/query.cpp:160-171) and 0 is returned.  Reads res->records, or res->brief when records is NULL. */
 size_t krepp_format_dist(const krepp_index_t* ix, const krepp_params_t* p, const krepp_results_t* res,
                          const char* names, const uint64_t* name_offsets, double* wcount, char* buf, size_t cap);
 /* IBatch::place_sequences / report_placement text for a batch (src/query.cpp:198-333): jplace "placements" entries

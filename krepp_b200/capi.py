@@ -59,7 +59,7 @@ class ShardInfo(C.Structure):
 class Results(C.Structure):
     _fields_ = [("n_reads", C.c_uint32), ("hist_stride", C.c_uint32), ("n_records", C.c_uint64), ("n_placements", C.c_uint64),
                 ("reads", C.c_void_p), ("records", C.c_void_p), ("hist", C.c_void_p), ("placements", C.c_void_p),
-                ("gpu_ms", C.c_float), ("match_ms", C.c_float), ("gpu_launches", C.c_uint32)]
+                ("gpu_ms", C.c_float), ("match_ms", C.c_float), ("gpu_launches", C.c_uint32), ("brief", C.c_void_p)]
 
 
 RECORD_DTYPE = np.dtype([("read", "<u4"), ("leaf_se", "<u4"), ("strand", "<u4"), ("match_count", "<u4"), ("hdist_min", "<u4"),
@@ -68,7 +68,18 @@ READ_DTYPE = np.dtype([("onmers", "<u4"), ("wn", "<u4", (2,)), ("hdist_filt", "<
                        ("rec_count", "<u4"), ("place_begin", "<u4"), ("place_count", "<u4"), ("closest", "<i4")])
 PLACEMENT_DTYPE = np.dtype([("read", "<u4"), ("se", "<u4"), ("pendant", "<f8"), ("distal", "<f8"), ("loglik", "<f8"),
                             ("lwr", "<f8"), ("d_llh", "<f8"), ("chisq", "<f8")])
+BRIEF_DTYPE = np.dtype([("read", "<u4"), ("ref", "<u4"), ("d_llh", "<f8")])  # krepp_brief_t
 REC_SOLVED, REC_SELECTED, REC_CLOSEST = 1, 2, 4
+
+
+def brief_from_records(records: np.ndarray, chisq_value: float) -> np.ndarray:
+    """krepp_brief_t rows equivalent to full records (what the device writes with KREPP_OUT_BRIEF)."""
+    out = np.zeros(len(records), BRIEF_DTYPE)
+    out["read"], out["d_llh"] = records["read"], records["d_llh"]
+    with np.errstate(invalid="ignore"):
+        ok = (records["chisq"] < chisq_value).astype(np.uint32)
+    out["ref"] = records["leaf_se"] | records["strand"] << 27 | (records["flags"] & 7) << 28 | ok << 31
+    return out
 
 
 def library_path() -> str:
@@ -291,13 +302,13 @@ class IBatch:
         self._res = dict(
             reads=_view(r.reads, READ_DTYPE, r.n_reads), records=_view(r.records, RECORD_DTYPE, nrec),
             hist=_view(r.hist, np.dtype("<u4"), nrec * r.hist_stride).reshape(-1, r.hist_stride),
-            placements=_view(r.placements, PLACEMENT_DTYPE, int(r.n_placements)), gpu_ms=float(r.gpu_ms), match_ms=float(r.match_ms),
-            gpu_launches=int(r.gpu_launches))
+            placements=_view(r.placements, PLACEMENT_DTYPE, int(r.n_placements)), brief=_view(r.brief, BRIEF_DTYPE, nrec),
+            n_records=nrec, gpu_ms=float(r.gpu_ms), match_ms=float(r.match_ms), gpu_launches=int(r.gpu_launches))
         return self._res
 
-    def set_output(self, records: bool = True, hist: bool = True, placements: bool = True):
+    def set_output(self, records: bool = True, hist: bool = True, placements: bool = True, brief: bool = False):
         """krepp_batch_set_output: which row arrays wait() copies to the host (the others come back empty)."""
-        _check(load_library().krepp_batch_set_output(self._h, int(records) | 2 * int(hist) | 4 * int(placements)))
+        _check(load_library().krepp_batch_set_output(self._h, int(records) | 2 * int(hist) | 4 * int(placements) | 8 * int(brief)))
 
     def wait_device(self) -> dict:
         """krepp_batch_wait_device: per-read summaries and counts only; record / placement rows stay in HBM."""
@@ -438,9 +449,14 @@ def pack_names(names) -> tuple[np.ndarray, np.ndarray]:
     return np.frombuffer(blob + b"\0", dtype=np.uint8).copy(), offs
 
 
-def results_struct(reads: np.ndarray, records: np.ndarray, hist: np.ndarray, placements: np.ndarray | None = None) -> Results:
+def results_struct(reads: np.ndarray, records: np.ndarray | None, hist: np.ndarray, placements: np.ndarray | None = None,
+                   brief: np.ndarray | None = None) -> Results:
     """A krepp_results_t over caller-owned numpy arrays (kept alive by the caller)."""
     r = Results()
+    if records is None:  # brief rows only
+        r.n_reads, r.hist_stride, r.n_records, r.n_placements = len(reads), 0, len(brief), 0
+        r.reads, r.records, r.hist, r.placements, r.brief = reads.ctypes.data, None, None, None, brief.ctypes.data
+        return r
     r.n_reads, r.hist_stride = len(reads), hist.shape[1] if hist.ndim == 2 else 0
     r.n_records, r.n_placements = len(records), 0 if placements is None else len(placements)
     r.reads, r.records, r.hist = reads.ctypes.data, records.ctypes.data, hist.ctypes.data

@@ -90,12 +90,22 @@ static std::vector<uint4> build_lut(const HostIndex& h)
 
 // AoS assembly of the public result structs on the device (one D2H copy each, no host-side gather).
 __global__ void __launch_bounds__(128) finalize_kernel(const SolveArgs a, krepp_record_t* out_rec, krepp_read_summary_t* out_read,
-                                                        const uint32_t* wn, const uint32_t* place_begin, const uint32_t* place_count)
+                                                        const uint32_t* wn, const uint32_t* place_begin, const uint32_t* place_count,
+                                                        krepp_brief_t* out_brief, double chisq_value)
 {
   if (a.counters[2] & kErrRedo) return; // incomplete records: the host re-runs the batch
   const uint32_t n = a.counters[0] < a.n_records ? a.counters[0] : a.n_records;
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-  for (uint32_t i = tid; i < n; i += nth) {
+  if (out_brief)
+    for (uint32_t i = tid; i < n; i += nth) {
+      const uint32_t slot = a.rec_slot[i];
+      krepp_brief_t r;
+      r.read = a.rec_read[i];
+      r.ref = (slot & 0x07FFFFFFu) | (slot >> 31) << 27 | (a.rec_flags[i] & 7u) << 28 | (a.rec_chisq[i] < chisq_value ? 1u : 0u) << 31;
+      r.d_llh = a.rec_d[i];
+      out_brief[i] = r;
+    }
+  for (uint32_t i = tid; out_rec && i < n; i += nth) {
     krepp_record_t r;
     const uint32_t slot = a.rec_slot[i];
     r.read = a.rec_read[i]; r.leaf_se = slot & 0x7FFFFFFFu; r.strand = slot >> 31;
@@ -154,6 +164,7 @@ struct krepp_batch {
   uint32_t *d_acc = nullptr, *d_bitmap = nullptr, *d_marker = nullptr, *d_stack = nullptr, *d_tagctr = nullptr;
   uint32_t stack_cap = 0;
   krepp_record_t* d_out_rec = nullptr; krepp_read_summary_t* d_out_read = nullptr;
+  krepp_brief_t *d_out_brief = nullptr, *h_brief = nullptr;
   // pinned host results
   krepp_record_t* h_rec = nullptr; krepp_read_summary_t* h_read = nullptr; uint32_t* h_hist = nullptr;
   uint32_t* h_counters = nullptr; unsigned long long* h_stats = nullptr;
@@ -332,6 +343,9 @@ static void free_records(krepp_batch* b)
     if (p) cudaFree(p);
   if (b->h_rec) cudaFreeHost(b->h_rec);
   if (b->h_hist) cudaFreeHost(b->h_hist);
+  if (b->d_out_brief) cudaFree(b->d_out_brief);
+  if (b->h_brief) cudaFreeHost(b->h_brief);
+  b->d_out_brief = nullptr; b->h_brief = nullptr;
   b->d_rec_read = b->d_rec_slot = b->d_rec_hist = b->d_rec_flags = b->d_rec_match = b->d_rec_hdmin = b->d_rec_work = b->d_rec_alias = nullptr;
   b->d_rec_d = b->d_rec_v = b->d_rec_chisq = nullptr; b->d_out_rec = nullptr; b->h_rec = nullptr; b->h_hist = nullptr;
 }
@@ -375,6 +389,7 @@ static int alloc_records(krepp_batch* b, uint32_t cap)
   CU(cudaMalloc(&b->d_out_rec, sizeof(krepp_record_t) * (size_t)cap));
   CU(cudaMallocHost(&b->h_rec, sizeof(krepp_record_t) * (size_t)cap));
   CU(cudaMallocHost(&b->h_hist, 4ull * cap * stride));
+  if (b->out_rows & KREPP_OUT_BRIEF) { CU(cudaMalloc(&b->d_out_brief, sizeof(krepp_brief_t) * (size_t)cap)); CU(cudaMallocHost(&b->h_brief, sizeof(krepp_brief_t) * (size_t)cap)); }
   return KREPP_OK;
 }
 
@@ -586,7 +601,10 @@ static int enqueue(krepp_batch* b)
     CU(launch_place(pa, b->tab, (int)(b->place_warps / kPlaceWarpsPerCta), ix->sms, s, &b->clk));
     b->launches += 4;
   }
-  finalize_kernel<<<ix->sms * 4, 128, 0, s>>>(sa, b->d_out_rec, b->d_out_read, b->d_wn, b->d_place_begin, b->d_place_count);
+  // the 56-byte rows are assembled unless only the brief ones leave the device (placement text needs the full rows)
+  const bool want_full = (b->out_rows & KREPP_OUT_RECORDS) || !(b->out_rows & KREPP_OUT_BRIEF);
+  finalize_kernel<<<ix->sms * 4, 128, 0, s>>>(sa, want_full ? b->d_out_rec : nullptr, b->d_out_read, b->d_wn, b->d_place_begin, b->d_place_count,
+                                              (b->out_rows & KREPP_OUT_BRIEF) ? b->d_out_brief : nullptr, b->p.chisq);
   CU(cudaGetLastError());
   b->clk.tick("finalize_kernel", s);
   CU(cudaEventRecord(b->ev1, s)); // kernels only: [ev0, ev1] excludes the host<->device copies on both sides
@@ -657,8 +675,13 @@ int krepp_batch_wait_device(krepp_batch_t* b, krepp_results_t* out) { return wai
 
 int krepp_batch_set_output(krepp_batch_t* b, uint32_t rows)
 {
-  if (!b || (rows & ~(uint32_t)KREPP_OUT_ALL)) return fail(KREPP_ERR_ARG, "krepp_batch_set_output: bad argument");
+  if (!b || (rows & ~(uint32_t)(KREPP_OUT_ALL | KREPP_OUT_BRIEF))) return fail(KREPP_ERR_ARG, "krepp_batch_set_output: bad argument");
+  if (cudaSetDevice(b->ix->device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice failed");
+  CU(cudaStreamSynchronize(b->stream));
   b->out_rows = rows;
+  if ((rows & KREPP_OUT_BRIEF) && !b->d_out_brief) {
+    CU(cudaMalloc(&b->d_out_brief, sizeof(krepp_brief_t) * (size_t)b->rec_cap)); CU(cudaMallocHost(&b->h_brief, sizeof(krepp_brief_t) * (size_t)b->rec_cap));
+  }
   return KREPP_OK;
 }
 
@@ -704,6 +727,7 @@ static int wait_impl(krepp_batch_t* b, krepp_results_t* out, uint32_t rows)
   const uint32_t nrec = b->h_counters[0];
   const size_t stride = b->p.hdist_th + 1;
   if (nrec && (rows & KREPP_OUT_RECORDS)) CU(cudaMemcpyAsync(b->h_rec, b->d_out_rec, sizeof(krepp_record_t) * (size_t)nrec, cudaMemcpyDeviceToHost, b->stream));
+  if (nrec && (rows & KREPP_OUT_BRIEF)) CU(cudaMemcpyAsync(b->h_brief, b->d_out_brief, sizeof(krepp_brief_t) * (size_t)nrec, cudaMemcpyDeviceToHost, b->stream));
   if (nrec && (rows & KREPP_OUT_HIST)) CU(cudaMemcpyAsync(b->h_hist, b->d_rec_hist, 4ull * nrec * stride, cudaMemcpyDeviceToHost, b->stream));
   const uint32_t nplace = b->p.place ? b->h_counters[3] : 0;
   if (nplace && (rows & KREPP_OUT_PLACEMENTS)) CU(cudaMemcpyAsync(b->h_place, b->d_place, sizeof(krepp_placement_t) * (size_t)nplace, cudaMemcpyDeviceToHost, b->stream));
@@ -713,6 +737,7 @@ static int wait_impl(krepp_batch_t* b, krepp_results_t* out, uint32_t rows)
   out->n_reads = b->n_reads; out->hist_stride = (uint32_t)stride; out->n_records = nrec; out->n_placements = nplace;
   out->reads = b->h_read; out->records = (rows & KREPP_OUT_RECORDS) ? b->h_rec : nullptr; out->hist = (rows & KREPP_OUT_HIST) ? b->h_hist : nullptr;
   out->placements = nplace && (rows & KREPP_OUT_PLACEMENTS) ? b->h_place : nullptr;
+  out->brief = (rows & KREPP_OUT_BRIEF) ? b->h_brief : nullptr;
   float mms = 0;
   CU(cudaEventElapsedTime(&mms, b->evm0, b->evm1));
   out->gpu_ms = ms; out->match_ms = mms; out->gpu_launches = b->launches;

@@ -198,7 +198,8 @@ int main(int argc, char** argv)
     Slot& s = slots[i];
     s.gpu = (int)(i % o.devices.size());
     check(krepp_batch_create(index[s.gpu], &p, o.batch_reads, o.batch_bases, &s.batch));
-    check(krepp_batch_set_output(s.batch, KREPP_OUT_RECORDS | KREPP_OUT_PLACEMENTS)); // the writers never read the histograms
+    // the writers never read the histograms, and `dist` needs only the 16-byte rows
+    check(krepp_batch_set_output(s.batch, place ? (KREPP_OUT_RECORDS | KREPP_OUT_PLACEMENTS) : KREPP_OUT_BRIEF));
     check(krepp_batch_host_buffers(s.batch, &s.bases, &s.offsets));
     s.names.resize(64ull * o.batch_reads);
     s.name_off.resize(o.batch_reads);

@@ -342,24 +342,74 @@ inline const char* name_of(const char* names, const uint64_t* name_offsets, uint
 
 // Selected records (node_to_minfo) of one read by ascending leaf se: records are stored as forward leaves by ascending
 // se, then reverse leaves by ascending se, and at most one of the two strands of a leaf is selected.
-template <class F>
-void for_selected(const krepp_results_t* res, const krepp_read_summary_t& s, F&& f)
+// field access for the two row forms (krepp_record_t, and the 16-byte krepp_brief_t that `dist` front ends ask for)
+inline uint32_t r_se(const krepp_record_t& r) { return r.leaf_se; }
+inline uint32_t r_se(const krepp_brief_t& r) { return KREPP_BRIEF_SE(r.ref); }
+inline uint32_t r_strand(const krepp_record_t& r) { return r.strand; }
+inline uint32_t r_strand(const krepp_brief_t& r) { return KREPP_BRIEF_STRAND(r.ref); }
+inline uint32_t r_flags(const krepp_record_t& r) { return r.flags; }
+inline uint32_t r_flags(const krepp_brief_t& r) { return KREPP_BRIEF_FLAGS(r.ref); }
+inline bool r_chisq_ok(const krepp_record_t& r, const krepp_params_t* p) { return r.chisq < p->chisq; }
+inline bool r_chisq_ok(const krepp_brief_t& r, const krepp_params_t*) { return KREPP_BRIEF_CHISQ_OK(r.ref) != 0; }
+
+template <class R, class F>
+void for_selected(const R* rec, const krepp_read_summary_t& s, F&& f)
 {
-  const krepp_record_t* rec = res->records;
   uint32_t i = s.rec_begin, ie = s.rec_begin + s.rec_count;
   uint32_t nf = 0;
-  while (i + nf < ie && rec[i + nf].strand == 0) ++nf;
+  while (i + nf < ie && r_strand(rec[i + nf]) == 0) ++nf;
   uint32_t j = i + nf;
   const uint32_t je = ie;
   ie = i + nf;
   while (i < ie || j < je) {
-    const uint32_t si = i < ie ? rec[i].leaf_se : 0xFFFFFFFFu, sj = j < je ? rec[j].leaf_se : 0xFFFFFFFFu;
+    const uint32_t si = i < ie ? r_se(rec[i]) : 0xFFFFFFFFu, sj = j < je ? r_se(rec[j]) : 0xFFFFFFFFu;
     uint32_t pick;
     if (si < sj) pick = i++;
     else if (sj < si) pick = j++;
-    else { pick = (rec[i].flags & KREPP_REC_SELECTED) ? i : j; ++i; ++j; }
-    if (rec[pick].flags & KREPP_REC_SELECTED) f(rec[pick]);
+    else { pick = (r_flags(rec[i]) & KREPP_REC_SELECTED) ? i : j; ++i; ++j; }
+    if (r_flags(rec[pick]) & KREPP_REC_SELECTED) f(rec[pick]);
   }
+}
+template <class F>
+void for_selected(const krepp_results_t* res, const krepp_read_summary_t& s, F&& f) { for_selected(res->records, s, f); }
+
+// IBatch::report_distances over either row form (ref src/query.cpp:158-196)
+template <class R>
+size_t format_dist_rows(const krepp_index_t* ix, const krepp_params_t* p, const krepp_results_t* res, const R* rows, const char* names,
+                        const uint64_t* name_offsets, double* wcount, char* buf, size_t cap)
+{
+  Out o(buf, cap);
+  const HostTree& t = ix->host.tree;
+  const bool has_max = !std::isnan(p->dist_max);
+  std::vector<uint32_t> keep;
+  for (uint32_t r = 0; r < res->n_reads; ++r) {
+    const krepp_read_summary_t& s = res->reads[r];
+    const char* id = name_of(names, name_offsets, r);
+    if (p->summarize) { // ref src/query.cpp:160-171
+      if (!wcount) continue;
+      keep.clear();
+      for_selected(rows, s, [&](const R& rec) {
+        if (r_chisq_ok(rec, p) && (!has_max || rec.d_llh < p->dist_max)) keep.push_back(r_se(rec));
+      });
+      for (uint32_t se : keep) wcount[se] += 1.0 / (double)keep.size();
+      continue;
+    }
+    if (s.closest < 0 || (has_max && rows[s.closest].d_llh > p->dist_max)) { // ref :173-176
+      o.put(id); o.put("\tNA\tNaN\n");
+      continue;
+    }
+    if (p->multi) {
+      for_selected(rows, s, [&](const R& rec) {
+        if (!p->no_filter && !r_chisq_ok(rec, p)) return;
+        if (has_max && !(rec.d_llh < p->dist_max)) return;
+        o.put(id); o.ch('\t'); o.put(t.node_name(r_se(rec), false)); o.ch('\t'); o.fixed5(rec.d_llh); o.ch('\n');
+      });
+    } else {
+      const R& rec = rows[s.closest];
+      o.put(id); o.ch('\t'); o.put(t.node_name(r_se(rec), false)); o.ch('\t'); o.fixed5(rec.d_llh); o.ch('\n');
+    }
+  }
+  return o.len;
 }
 
 } // namespace
@@ -387,38 +437,8 @@ extern "C" size_t krepp_format_dist(const krepp_index_t* ix, const krepp_params_
                                     const uint64_t* name_offsets, double* wcount, char* buf, size_t cap)
 {
   if (!ix || !p || !res || !names || !name_offsets) return 0;
-  Out o(buf, cap);
-  const HostTree& t = ix->host.tree;
-  const bool has_max = !std::isnan(p->dist_max);
-  std::vector<uint32_t> keep;
-  for (uint32_t r = 0; r < res->n_reads; ++r) {
-    const krepp_read_summary_t& s = res->reads[r];
-    const char* id = name_of(names, name_offsets, r);
-    if (p->summarize) { // ref src/query.cpp:160-171
-      if (!wcount) continue;
-      keep.clear();
-      for_selected(res, s, [&](const krepp_record_t& rec) {
-        if (rec.chisq < p->chisq && (!has_max || rec.d_llh < p->dist_max)) keep.push_back(rec.leaf_se);
-      });
-      for (uint32_t se : keep) wcount[se] += 1.0 / (double)keep.size();
-      continue;
-    }
-    if (s.closest < 0 || (has_max && res->records[s.closest].d_llh > p->dist_max)) { // ref :173-176
-      o.put(id); o.put("\tNA\tNaN\n");
-      continue;
-    }
-    if (p->multi) {
-      for_selected(res, s, [&](const krepp_record_t& rec) {
-        if (!p->no_filter && !(rec.chisq < p->chisq)) return;
-        if (has_max && !(rec.d_llh < p->dist_max)) return;
-        o.put(id); o.ch('\t'); o.put(t.node_name(rec.leaf_se, false)); o.ch('\t'); o.fixed5(rec.d_llh); o.ch('\n');
-      });
-    } else {
-      const krepp_record_t& rec = res->records[s.closest];
-      o.put(id); o.ch('\t'); o.put(t.node_name(rec.leaf_se, false)); o.ch('\t'); o.fixed5(rec.d_llh); o.ch('\n');
-    }
-  }
-  return o.len;
+  if (res->records || !res->brief) return format_dist_rows(ix, p, res, res->records, names, name_offsets, wcount, buf, cap);
+  return format_dist_rows(ix, p, res, res->brief, names, name_offsets, wcount, buf, cap);
 }
 
 extern "C" size_t krepp_format_place(const krepp_index_t* ix, const krepp_params_t* p, const krepp_results_t* res, const char* names,

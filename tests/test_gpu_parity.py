@@ -265,3 +265,30 @@ def test_scan_strategies_on_toy(scan):
         g.close()
     finally:
         del os.environ["KREPP_SCAN"]
+
+
+def test_brief_rows_equal_full_rows():
+    """KREPP_OUT_BRIEF: the 16-byte rows the `dist` front end copies back carry the same reference, strand, flags, filter
+    decision and distance (bit for bit) as the full records, and format to the same TSV."""
+    import krepp_b200
+    from krepp_b200 import capi
+    small = os.path.join(conftest.GOLDEN_DIR, "small")
+    names, reads = fastq_reads(os.path.join(small, "reads.fq"))
+    g = krepp_b200.Index(os.path.join(small, "index"), 0)
+    for kw in (dict(), dict(no_filter=False)):
+        b = krepp_b200.IBatch(g, reads, names=names, **kw)
+        b.set_output(brief=True)
+        b.submit()
+        r = b.wait()
+        want = capi.brief_from_records(r["records"], 2.706)
+        assert len(r["brief"]) == len(r["records"]) > 500
+        for f in ("read", "ref", "d_llh"):
+            assert np.array_equal(r["brief"][f], want[f]), f
+        b.set_output(records=False, hist=False, placements=False, brief=True)   # what the CLI asks for
+        b.submit()
+        r2 = b.wait()
+        assert len(r2["records"]) == 0 and np.array_equal(r2["brief"], r["brief"]) and np.array_equal(r2["reads"], r["reads"])
+        full = capi.results_struct(np.array(r["reads"]), np.array(r["records"]), np.array(r["hist"]))
+        brief = capi.results_struct(np.array(r2["reads"]), None, None, brief=np.array(r2["brief"]))
+        assert capi.format_dist(g, b.params, full, names) == capi.format_dist(g, b.params, brief, names)
+        b.close()

@@ -183,6 +183,15 @@ def test_format_dist_equals_reference_tsv(K, small):
     assert abs(w.sum() - sum(1 for o in outs if o["sel"])) < 1e-9
     foot = K.format_footer(small["index"], ps, wcount=w).splitlines()
     assert len(foot) == int((w > 0).sum()) and abs(sum(float(l.split("\t")[2]) for l in foot) - 1) < 1e-3
+    # the 16-byte rows (krepp_brief_t, what `dist` front ends copy back) give the same text in every mode
+    brief = K.brief_from_records(arrs[1], 2.706)
+    rb = K.results_struct(arrs[0], None, None, brief=brief)
+    for prm in (p, K.Params(4, 2.706, float("nan"), 2, 1, 0, 0, 0), K.Params(4, 2.706, 0.05, 2, 1, 1, 0, 0), K.Params(4, 2.706, float("nan"), 2, 0, 1, 0, 0),
+                K.Params(4, 2.706, 0.08, 2, 0, 0, 0, 0)):
+        assert K.format_dist(small["index"], prm, rb, small["names"]) == K.format_dist(small["index"], prm, res, small["names"])
+    wb = np.zeros_like(w)
+    K.format_dist(small["index"], ps, rb, small["names"], wcount=wb)
+    assert np.array_equal(w, wb)
 
 
 def test_format_place_equals_reference_jplace_on_untied_reads(K, small):

@@ -9,6 +9,7 @@ import csv
 import glob
 import io
 import os
+import re
 import shutil
 import subprocess
 import sys
@@ -82,7 +83,7 @@ def traffic_json(rep, out, source, batch_reads):
     k = {}
     for vals in rows[2:]:
         for pat, key in names:
-            if pat in vals[ik] and key not in k:
+            if re.search(r"(^|[^a-z_])" + re.escape(pat), vals[ik]) and key not in k:
                 k[key] = float(vals[ir].replace(",", "")) * mult[units[ir]] + float(vals[iw].replace(",", "")) * mult[units[iw]]
     with open(out, "w") as f:
         json.dump({"c3": {"source": source, "batch_reads": batch_reads, "kernels": k}}, f, indent=1)
