@@ -279,16 +279,20 @@ def test_brief_rows_equal_full_rows():
         b = krepp_b200.IBatch(g, reads, names=names, **kw)
         b.set_output(brief=True)
         b.submit()
-        r = b.wait()
+        r = {k: np.array(v, copy=True) for k, v in b.wait().items() if isinstance(v, np.ndarray)}  # the views die with the next submit
         want = capi.brief_from_records(r["records"], 2.706)
         assert len(r["brief"]) == len(r["records"]) > 500
         for f in ("read", "ref", "d_llh"):
             assert np.array_equal(r["brief"][f], want[f]), f
         b.set_output(records=False, hist=False, placements=False, brief=True)   # what the CLI asks for
         b.submit()
-        r2 = b.wait()
-        assert len(r2["records"]) == 0 and np.array_equal(r2["brief"], r["brief"]) and np.array_equal(r2["reads"], r["reads"])
-        full = capi.results_struct(np.array(r["reads"]), np.array(r["records"]), np.array(r["hist"]))
-        brief = capi.results_struct(np.array(r2["reads"]), None, None, brief=np.array(r2["brief"]))
+        r2 = {k: np.array(v, copy=True) for k, v in b.wait().items() if isinstance(v, np.ndarray)}
+        assert len(r2["records"]) == 0 and all(np.array_equal(r2["reads"][f], r["reads"][f]) for f in ("onmers", "wn", "hdist_filt", "rec_count"))
+        # (reads land in the row arrays in completion order, which differs from run to run: compare per read)
+        for i in range(len(reads)):
+            a0, n0, a1 = int(r["reads"]["rec_begin"][i]), int(r["reads"]["rec_count"][i]), int(r2["reads"]["rec_begin"][i])
+            assert np.array_equal(r["brief"][a0:a0 + n0], r2["brief"][a1:a1 + n0]), i
+        full = capi.results_struct(r["reads"], r["records"], r["hist"])
+        brief = capi.results_struct(r2["reads"], None, None, brief=r2["brief"])
         assert capi.format_dist(g, b.params, full, names) == capi.format_dist(g, b.params, brief, names)
         b.close()
