@@ -189,7 +189,7 @@ static cudaError_t exclusive_scan(const uint32_t* in, uint32_t n, uint32_t* part
 // ---------------------------------------------------------------------------------------------------- J: join
 
 struct __align__(16) JoinWarpSmem {
-  uint4 qs[32];       // the queries being compared: {q, read, local lookup index | strand << 31, 0}
+  uint4 qs[32];       // the queries being compared: {q low half, q high half, read, local lookup index | strand << 31}
   uint4 hq[kHitQ];    // queued hit entries: {read, strand << 31 | local lookup index << 5 | hd, colour id, 0}
   uint32_t hq_n, pad[3];
 };
@@ -212,31 +212,32 @@ __device__ __noinline__ void join_flush(JoinWarpSmem* w, const SortArgs s, uint3
 }
 
 // One block of up to 32 queries (in w->qs) against the E entries each lane holds.  thr[e] is the Hamming threshold, or
-// -1 for a register slot that holds no entry.
+// -1 for a register slot that holds no entry.  The residual encoding keeps bit 0 of the 16 kept positions in its low half
+// and bit 1 in its high half (ref src/lshf.cpp:64-69), so the mismatch mask is (e.lo ^ q.lo) | (e.hi ^ q.hi): with both
+// halves of entries and queries split once, a comparison is two LOP3, one POPC and one ISETP.
 template <int E, bool COUNT>
-__device__ __forceinline__ void join_block(JoinWarpSmem* w, const SortArgs& s, uint32_t* counters, const uint32_t (&enc)[4], const uint32_t (&se)[4],
-                                           const int (&thr)[4], uint32_t cnt)
+__device__ __forceinline__ void join_block(JoinWarpSmem* w, const SortArgs& s, uint32_t* counters, const uint32_t (&elo)[4], const uint32_t (&ehi)[4],
+                                           const uint32_t (&se)[4], const int (&thr)[4], uint32_t cnt)
 {
   for (uint32_t j = 0; j < cnt; ++j) {
-    const uint32_t q = w->qs[j].x;
+    const uint2 qq = *reinterpret_cast<const uint2*>(&w->qs[j]); // {q.lo, q.hi}
     int hd[E];
     bool any = false;
 #pragma unroll
     for (int e = 0; e < E; ++e) {
-      const uint32_t z = enc[e] ^ q;
-      hd[e] = __popc((z | (z >> 16)) & 0xFFFFu);
+      hd[e] = __popc((elo[e] ^ qq.x) | (ehi[e] ^ qq.y));
       any |= hd[e] <= thr[e];
     }
     if (__any_sync(0xFFFFFFFFu, any)) {
       if (any) {
         const uint4 t = w->qs[j];
-        const uint32_t meta = (t.z & 0x80000000u) | ((t.z & (kMaxLoc - 1u)) << 5);
+        const uint32_t meta = (t.w & 0x80000000u) | ((t.w & (kMaxLoc - 1u)) << 5);
 #pragma unroll
         for (int e = 0; e < E; ++e)
           if (hd[e] <= thr[e]) {
             const uint32_t at = atomicAdd(&w->hq_n, 1u);
-            w->hq[at] = make_uint4(t.y, meta | (uint32_t)hd[e], se[e], 0u);
-            if (COUNT) atomicAdd(&s.hit_count[t.y], 1u);
+            w->hq[at] = make_uint4(t.z, meta | (uint32_t)hd[e], se[e], 0u);
+            if (COUNT) atomicAdd(&s.hit_count[t.z], 1u);
           }
       }
       __syncwarp();
@@ -278,25 +279,25 @@ __global__ void __launch_bounds__(kJoinWarps * 32) join_kernel(const DevIndex ix
       const uint32_t rqb = __shfl_sync(0xFFFFFFFFu, qb, src), nq = __shfl_sync(0xFFFFFFFFu, qe, src) - rqb;
       const uint32_t reb = __shfl_sync(0xFFFFFFFFu, eb, src), ne = __shfl_sync(0xFFFFFFFFu, ee, src) - reb;
       for (uint32_t c = 0; c < ne; c += kJoinChunk) {
-        uint32_t enc[4], se[4];
+        uint32_t elo[4], ehi[4], se[4];
         int thr[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const uint32_t i = c + 32 * e + lane;
-          enc[e] = 0; se[e] = 0; thr[e] = -1;
-          if (i < ne) { const uint2 v = __ldg(&ix.cmer[(size_t)reb + i]); enc[e] = v.x; se[e] = v.y; thr[e] = (int)th; }
+          elo[e] = 0; ehi[e] = 0; se[e] = 0; thr[e] = -1;
+          if (i < ne) { const uint2 v = __ldg(&ix.cmer[(size_t)reb + i]); elo[e] = v.x & 0xFFFFu; ehi[e] = v.x >> 16; se[e] = v.y; thr[e] = (int)th; }
         }
         const uint32_t E = min(4u, (ne - c + 31u) >> 5);
         for (uint32_t q0 = 0; q0 < nq; q0 += 32) {
           const uint32_t cnt = min(32u, nq - q0);
           __syncwarp();
-          if (lane < cnt) w->qs[lane] = s.tuples[rqb + q0 + lane];
+          if (lane < cnt) { const uint4 t = s.tuples[rqb + q0 + lane]; w->qs[lane] = make_uint4(t.x & 0xFFFFu, t.x >> 16, t.y, t.z); } // {q.lo, q.hi, read, lookup}
           __syncwarp();
           switch (E) {
-            case 1: join_block<1, COUNT>(w, s, counters, enc, se, thr, cnt); break;
-            case 2: join_block<2, COUNT>(w, s, counters, enc, se, thr, cnt); break;
-            case 3: join_block<3, COUNT>(w, s, counters, enc, se, thr, cnt); break;
-            default: join_block<4, COUNT>(w, s, counters, enc, se, thr, cnt); break;
+            case 1: join_block<1, COUNT>(w, s, counters, elo, ehi, se, thr, cnt); break;
+            case 2: join_block<2, COUNT>(w, s, counters, elo, ehi, se, thr, cnt); break;
+            case 3: join_block<3, COUNT>(w, s, counters, elo, ehi, se, thr, cnt); break;
+            default: join_block<4, COUNT>(w, s, counters, elo, ehi, se, thr, cnt); break;
           }
         }
       }
