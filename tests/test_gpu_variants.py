@@ -1,0 +1,36 @@
+"""GPU: the CUDA path against the oracle on index geometries other than the default (tests/variants.py; the oracle itself is
+pinned on them against the reference in tests/test_variants_cpu.py): k from 19 to 31 (7- and 8-table LUTs, residual
+encodings of 14 to 16 positions), m = 1, 2, 3, 4, 5 with frac and no-frac row addressing, dist and place, both forms of the
+match step, and the reference's own `krepp dist` output through the C++ formatters."""
+import os
+import subprocess
+
+import pytest
+
+from conftest import REF_DIR, needs_ref
+from test_gpu_parity import fastq_reads
+from variants import SMALL, VARIANTS, build
+
+pytestmark = [pytest.mark.gpu, needs_ref]
+
+
+@pytest.mark.parametrize("pipeline", ["fused", "sorted"])
+@pytest.mark.parametrize("label,args", VARIANTS, ids=[v[0] for v in VARIANTS])
+def test_gpu_equals_oracle_on_variant(label, args, pipeline, tmp_path_factory, monkeypatch):
+    import krepp_b200
+    import oracle_lib as O
+    from gpu_common import run_and_compare
+    monkeypatch.setenv("KREPP_PIPELINE", pipeline)
+    idx = build(label, args, tmp_path_factory.getbasetemp())
+    names, reads = fastq_reads(os.path.join(SMALL, "reads.fq"))
+    o, g = O.OracleIndex(idx), krepp_b200.Index(idx, 0)
+    st = run_and_compare(idx, reads, o, g)
+    assert st["solves"] > 20, (label, st)
+    st = run_and_compare(idx, reads, o, g, check_lookups=False, place=True, no_filter=False)
+    assert st["placements"] > 10, (label, st)
+    b = krepp_b200.IBatch(g, reads, names=names)
+    ref = subprocess.run([os.path.join(REF_DIR, "krepp"), "dist", "-i", idx, "-q", os.path.join(SMALL, "reads.fq")], capture_output=True, text=True,
+                         check=True).stdout.splitlines()[2:]
+    assert sorted(b.estimate_distances().splitlines()) == sorted(ref), label
+    b.close()
+    g.close()

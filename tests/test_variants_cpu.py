@@ -1,0 +1,41 @@
+"""CPU: the oracle against the unmodified reference on index geometries other than the default (tests/variants.py): stage
+dump (lookups, histograms, solves, placements) of `ref_dump` and the `krepp dist` TSV.  Pins the oracle for the rows the
+GPU variant test (tests/test_gpu_variants.py) then checks the CUDA path against."""
+import os
+import subprocess
+
+import pytest
+
+from conftest import REF_DIR, needs_ref
+from test_gpu_parity import fastq_reads
+from variants import SMALL, VARIANTS, build
+
+pytestmark = [needs_ref]
+
+
+@pytest.mark.parametrize("label,args", VARIANTS, ids=[v[0] for v in VARIANTS])
+def test_oracle_equals_reference_on_variant(label, args, tmp_path_factory):
+    import oracle_lib as O
+    idx = build(label, args, tmp_path_factory.getbasetemp())
+    fq = os.path.join(SMALL, "reads.fq")
+    names, reads = fastq_reads(fq)
+    dump = O.parse_ref_dump(subprocess.run([os.path.join(REF_DIR, "ref_dump"), idx, fq, "--lookups", "--place"], capture_output=True, text=True,
+                                           check=True).stdout)
+    ix = O.OracleIndex(idx)
+    p = O.default_params(want_lookups=1, want_place=1, no_filter=0)
+    nrec = 0
+    for i, s in enumerate(reads):
+        o, r = ix.query(s, p), dump["reads"][i]
+        for key in ("onmers", "wn", "hdist_filt", "lookups"):
+            assert o[key] == r[key], (label, i, key)
+        key_m = lambda m: (m["strand"], m["leaf_se"], m["match"], m["hdist_min"], m["rho"], m["hist"])
+        assert [key_m(m) for m in o["minfo"]] == [key_m(m) for m in r["minfo"]], (label, i)
+        key_s = lambda s_: (s_["leaf_se"], s_["strand"], s_["d"], s_["v"], s_["chisq"], s_["is_closest"])
+        assert [key_s(x) for x in o["sel"]] == [key_s(x) for x in r["sel"]], (label, i)
+        assert [tuple(q.values()) for q in o["place"]] == [tuple(q.values()) for q in r["place"]], (label, i)
+        nrec += len(o["minfo"])
+    assert nrec > 40, (label, nrec)
+    ref = subprocess.run([os.path.join(REF_DIR, "krepp"), "dist", "-i", idx, "-q", fq], capture_output=True, text=True, check=True).stdout.splitlines()[2:]
+    ora = subprocess.run([os.path.join(os.path.dirname(REF_DIR), "_build", "krepp_oracle"), "dist", idx, fq], capture_output=True, text=True,
+                         check=True).stdout.splitlines()[1:]
+    assert sorted(ref) == sorted(ora), label
