@@ -499,8 +499,12 @@ __device__ __forceinline__ ResolveOut resolve_read(const DevIndex& ix, const Mat
     for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += t; }
     const uint32_t at = base + incl - cnt;
     const K fixed = ((K)(h.z >> 31) << strand_shift) | (K)(h.z & 0x7FFFFFFFu); // strand | lookup << 5 | hd
-    if (cnt <= 8u) {
-      for (uint32_t j = 0; j < cnt; ++j) keys[at + j] = fixed | ((K)__ldg(&ix.cleaf[h.x + j]) << seg_shift);
+    if (cnt <= 8u) { // all leaf loads of the lane in flight before the first one is used
+      uint32_t lf[8];
+#pragma unroll
+      for (uint32_t j = 0; j < 8u; ++j) lf[j] = j < cnt ? __ldg(&ix.cleaf[h.x + j]) : 0u;
+#pragma unroll
+      for (uint32_t j = 0; j < 8u; ++j) if (j < cnt) keys[at + j] = fixed | ((K)lf[j] << seg_shift);
     }
     uint32_t big = __ballot_sync(0xFFFFFFFFu, cnt > 8u); // long leaf lists: all lanes together
     while (big) {

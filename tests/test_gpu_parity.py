@@ -202,6 +202,23 @@ def test_cli_dist_golden_small(tmp_path):
     assert out.read_text().splitlines()[2:] == body[2:]  # same rows in the same (input) order
 
 
+def test_cli_two_gpus_same_bytes(tmp_path):
+    """--num-gpus 2 (index replicated, batches dealt round-robin to the GPUs: SURVEY.md 8e mode A) must not change a byte of
+    the output, which stays in input order.  Skipped on one-GPU boxes."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    small = os.path.join(conftest.GOLDEN_DIR, "small")
+    args = ("--num-threads", "2", "dist", "-i", os.path.join(small, "index"), "-q", os.path.join(small, "reads.fq"), "--batch-reads", "23")
+    one, two = _cli(*args), _cli(*args, "--num-gpus", "2")
+    assert one.returncode == 0 and two.returncode == 0, two.stderr
+    assert one.stdout.splitlines()[1:] == two.stdout.splitlines()[1:] and len(two.stdout.splitlines()) > 200
+    pl = ("place", "-i", os.path.join(small, "index"), "-q", os.path.join(small, "reads.fq"), "--batch-reads", "31", "--tabular")
+    one, two = _cli(*pl), _cli(*pl, "--devices", "1,0")
+    assert one.returncode == 0 and two.returncode == 0, two.stderr
+    assert one.stdout.splitlines()[1:] == two.stdout.splitlines()[1:]
+
+
 def test_cli_place_golden_small(tmp_path):
     import json
     import oracle_lib as O
