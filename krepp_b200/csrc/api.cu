@@ -357,7 +357,6 @@ static int alloc_placements(krepp_batch* b, uint32_t cap)
   b->d_place = nullptr; b->h_place = nullptr;
   b->place_cap = cap;
   CU(cudaMalloc(&b->d_place, sizeof(krepp_placement_t) * (size_t)cap));
-  CU(cudaMallocHost(&b->h_place, sizeof(krepp_placement_t) * (size_t)cap));
   return KREPP_OK;
 }
 
@@ -387,9 +386,8 @@ static int alloc_records(krepp_batch* b, uint32_t cap)
   CU(cudaMalloc(&b->d_rec_work, 4ull * cap)); CU(cudaMalloc(&b->d_rec_alias, 4ull * cap));
   CU(cudaMalloc(&b->d_rec_d, 8ull * cap)); CU(cudaMalloc(&b->d_rec_v, 8ull * cap)); CU(cudaMalloc(&b->d_rec_chisq, 8ull * cap));
   CU(cudaMalloc(&b->d_out_rec, sizeof(krepp_record_t) * (size_t)cap));
-  CU(cudaMallocHost(&b->h_rec, sizeof(krepp_record_t) * (size_t)cap));
-  CU(cudaMallocHost(&b->h_hist, 4ull * cap * stride));
-  if (b->out_rows & KREPP_OUT_BRIEF) { CU(cudaMalloc(&b->d_out_brief, sizeof(krepp_brief_t) * (size_t)cap)); CU(cudaMallocHost(&b->h_brief, sizeof(krepp_brief_t) * (size_t)cap)); }
+  if (b->out_rows & KREPP_OUT_BRIEF) CU(cudaMalloc(&b->d_out_brief, sizeof(krepp_brief_t) * (size_t)cap));
+  (void)stride; // the page-locked host copies are sized when a wait first needs them (host_rows): page-locking is slow and most callers want one form only
   return KREPP_OK;
 }
 
@@ -680,8 +678,19 @@ int krepp_batch_set_output(krepp_batch_t* b, uint32_t rows)
   CU(cudaStreamSynchronize(b->stream));
   b->out_rows = rows;
   if ((rows & KREPP_OUT_BRIEF) && !b->d_out_brief) {
-    CU(cudaMalloc(&b->d_out_brief, sizeof(krepp_brief_t) * (size_t)b->rec_cap)); CU(cudaMallocHost(&b->h_brief, sizeof(krepp_brief_t) * (size_t)b->rec_cap));
+    CU(cudaMalloc(&b->d_out_brief, sizeof(krepp_brief_t) * (size_t)b->rec_cap));
   }
+  return KREPP_OK;
+}
+
+// page-locked host arrays for the row forms this wait copies back (freed with the device arrays when those grow)
+static int host_rows(krepp_batch* b, uint32_t rows)
+{
+  const size_t cap = b->rec_cap, stride = b->p.hdist_th + 1;
+  if ((rows & KREPP_OUT_RECORDS) && !b->h_rec) CU(cudaMallocHost(&b->h_rec, sizeof(krepp_record_t) * cap));
+  if ((rows & KREPP_OUT_HIST) && !b->h_hist) CU(cudaMallocHost(&b->h_hist, 4ull * cap * stride));
+  if ((rows & KREPP_OUT_BRIEF) && !b->h_brief) CU(cudaMallocHost(&b->h_brief, sizeof(krepp_brief_t) * cap));
+  if ((rows & KREPP_OUT_PLACEMENTS) && b->p.place && !b->h_place) CU(cudaMallocHost(&b->h_place, sizeof(krepp_placement_t) * (size_t)b->place_cap));
   return KREPP_OK;
 }
 
@@ -726,6 +735,7 @@ static int wait_impl(krepp_batch_t* b, krepp_results_t* out, uint32_t rows)
   }
   const uint32_t nrec = b->h_counters[0];
   const size_t stride = b->p.hdist_th + 1;
+  if (int rc = host_rows(b, rows)) return rc;
   if (nrec && (rows & KREPP_OUT_RECORDS)) CU(cudaMemcpyAsync(b->h_rec, b->d_out_rec, sizeof(krepp_record_t) * (size_t)nrec, cudaMemcpyDeviceToHost, b->stream));
   if (nrec && (rows & KREPP_OUT_BRIEF)) CU(cudaMemcpyAsync(b->h_brief, b->d_out_brief, sizeof(krepp_brief_t) * (size_t)nrec, cudaMemcpyDeviceToHost, b->stream));
   if (nrec && (rows & KREPP_OUT_HIST)) CU(cudaMemcpyAsync(b->h_hist, b->d_rec_hist, 4ull * nrec * stride, cudaMemcpyDeviceToHost, b->stream));

@@ -11,6 +11,9 @@
 
 #include <zlib.h>
 
+#include <fcntl.h>
+#include <unistd.h>
+
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -48,7 +51,8 @@ enum class St { Seek, Name, Comment, Seq, Plus, Qual, QualTail, Done };
 } // namespace
 
 struct krepp_reader {
-  gzFile f = nullptr;
+  gzFile f = nullptr;   // gzip input (zlib inflates; its "transparent" mode for plain files is a slow copy, hence:)
+  int fd = -1;          // plain input: read(2) straight into the buffer
   std::vector<unsigned char> buf;
   size_t at = 0, end = 0;
   bool eof = false;
@@ -63,13 +67,27 @@ struct krepp_reader {
 
 namespace {
 
+// up to `want` bytes of input at `dst`; fewer only at the end of the input (or on a read error)
+size_t read_input(krepp_reader* r, unsigned char* dst, size_t want)
+{
+  size_t got = 0;
+  while (got < want) {
+    long n;
+    if (r->fd >= 0) n = (long)read(r->fd, dst + got, want - got);
+    else n = gzread(r->f, dst + got, (unsigned)(want - got));
+    if (n <= 0) break;
+    got += (size_t)n;
+  }
+  return got;
+}
+
 bool refill(krepp_reader* r)
 {
   if (r->eof) return false;
-  const int n = gzread(r->f, r->buf.data(), (unsigned)r->buf.size());
+  const long n = (long)read_input(r, r->buf.data(), r->buf.size());
   r->at = 0;
   r->end = n > 0 ? (size_t)n : 0;
-  if (n < (int)r->buf.size()) r->eof = true;
+  if (n < (long)r->buf.size()) r->eof = true;
   return r->end > 0;
 }
 
@@ -226,11 +244,20 @@ extern "C" int krepp_reader_open(const char* path, krepp_reader_t** out)
 {
   if (!path || !out) return set_error(KREPP_ERR_ARG, "krepp_reader_open: null argument");
   *out = nullptr;
-  gzFile f = gzopen(path, "rb");
-  if (!f) return set_error(KREPP_ERR_IO, "Failed to open the file at %s", path);
-  gzbuffer(f, 1 << 20);
+  int fd = open(path, O_RDONLY);
+  if (fd < 0) return set_error(KREPP_ERR_IO, "Failed to open the file at %s", path);
+  unsigned char magic[2] = {0, 0};
+  const bool gz = pread(fd, magic, 2, 0) == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
+  gzFile f = nullptr;
+  if (gz) {
+    close(fd);
+    fd = -1;
+    f = gzopen(path, "rb");
+    if (!f) return set_error(KREPP_ERR_IO, "Failed to open the file at %s", path);
+    gzbuffer(f, 1 << 20);
+  }
   auto* r = new krepp_reader;
-  r->f = f;
+  r->f = f; r->fd = fd;
   r->buf.resize(4 << 20);
   if (const char* env = getenv("KREPP_READER_FAST")) r->fast = strcmp(env, "0") != 0;
   *out = r;
@@ -241,6 +268,7 @@ extern "C" void krepp_reader_close(krepp_reader_t* r)
 {
   if (!r) return;
   if (r->f) gzclose(r->f);
+  if (r->fd >= 0) close(r->fd);
   delete r;
 }
 
