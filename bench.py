@@ -279,7 +279,7 @@ def shard_arm(args) -> None:
                        "l2": "inputs larger than L2 and a 256 MiB memset between steps", "records_per_step": tot[3], "workload_setup_s": round(t_wl, 1)},
             "e2e": None if args.no_e2e else {"value": world * n * args.steps / t_e2e, "unit": "reads/s", "h2d_bytes_per_step": n * READ_LEN, "d2h_bytes_per_step": d2h,
                                              "how": "every batch copied from page-locked host memory inside the timed region, results copied back by krepp_batch_wait; wall clock, max over ranks"},
-            "gpu_launches": args.steps * len(chunks) * (13 + world + 9), "clocks": clocks,
+            "gpu_launches": args.steps * len(chunks) * (16 + world), "clocks": clocks,  # per batch: 5 lookup/scan + one join per sender + 6 regroup/resolve + 5 gate..finalize
             "exchange": {"bytes_received_per_step_all_ranks": tot[4], "per_read": tot[4] / (world * n), "transport": "torch.distributed all_to_all_single (NCCL)" if world > 1 else "none (one shard)"},
             "roofline": {"bound": "hbm", "kernel": "whole step of all ranks (lookup, exchange, join on the owning shard, exchange, resolve, solve)", "achieved": achieved,
                          "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world), "traffic": None, "peak_source": peak_src + f" x {world} GPUs",
