@@ -171,7 +171,7 @@ struct krepp_batch {
   // placement (K5)
   uint32_t place_cap = 0, place_warps = 0;
   uint32_t *d_place_begin = nullptr, *d_place_count = nullptr, *d_node_bitmap = nullptr, *d_node_list = nullptr;
-  uint32_t* d_sel = nullptr; double* d_chain = nullptr; uint32_t chain_cap = 0;
+  uint32_t* d_sel = nullptr; double* d_chain = nullptr; uint32_t chain_cap = 0; uint32_t* d_node_order = nullptr;
   uint32_t node_cap = 0;      // tree nodes touched by a batch (place_collect_kernel's entries)
   uint32_t *d_pn_read = nullptr, *d_pn_se = nullptr, *d_pn_flags = nullptr, *d_pn_work = nullptr, *d_pn_begin = nullptr, *d_pn_count = nullptr;
   double *d_pn_mc = nullptr, *d_pn_uc = nullptr, *d_pn_rho = nullptr, *d_pn_d = nullptr, *d_pn_v = nullptr, *d_pn_chisq = nullptr;
@@ -495,7 +495,7 @@ int krepp_batch_create(krepp_index_t* ix, const krepp_params_t* p, uint32_t max_
     const size_t pw = b->place_warps;
     CU(cudaMalloc(&b->d_place_begin, 4ull * max_reads)); CU(cudaMalloc(&b->d_place_count, 4ull * max_reads));
     CU(cudaMalloc(&b->d_node_bitmap, 4 * pw * nbm_nodes)); CU(cudaMemset(b->d_node_bitmap, 0, 4 * pw * nbm_nodes));
-    CU(cudaMalloc(&b->d_node_list, 4 * pw * nn));
+    CU(cudaMalloc(&b->d_node_list, 4 * pw * nn)); CU(cudaMalloc(&b->d_node_order, 4 * pw * nn));
     b->chain_cap = 4096; // doubles per warp: sum over a read's selected references of their depth; reads beyond it take the slow walk
     CU(cudaMalloc(&b->d_sel, 4 * pw * 3 * (size_t)std::max<uint32_t>(h.tree.nleaves, 1))); CU(cudaMalloc(&b->d_chain, 8 * pw * (size_t)b->chain_cap));
     CU(cudaMalloc(&b->d_pn_begin, 4ull * max_reads)); CU(cudaMalloc(&b->d_pn_count, 4ull * max_reads));
@@ -514,7 +514,7 @@ void krepp_batch_destroy(krepp_batch_t* b)
   for (void* p : {(void*)b->d_bases, (void*)b->d_offsets, (void*)b->d_onmers, (void*)b->d_wn, (void*)b->d_hdfilt, (void*)b->d_rec_begin,
                   (void*)b->d_rec_count, (void*)b->d_closest, (void*)b->d_memo_key, (void*)b->d_memo_owner, (void*)b->d_counters, (void*)b->d_stats, (void*)b->d_acc, (void*)b->d_bitmap,
                   (void*)b->d_marker, (void*)b->d_stack, (void*)b->d_tagctr, (void*)b->d_out_read, (void*)b->d_tap, (void*)b->d_tap_count, (void*)b->d_place_begin,
-                  (void*)b->d_place_count, (void*)b->d_node_bitmap, (void*)b->d_node_list, (void*)b->d_sel, (void*)b->d_chain, (void*)b->d_pn_begin, (void*)b->d_pn_count, (void*)b->d_pn_read,
+                  (void*)b->d_place_count, (void*)b->d_node_bitmap, (void*)b->d_node_list, (void*)b->d_node_order, (void*)b->d_sel, (void*)b->d_chain, (void*)b->d_pn_begin, (void*)b->d_pn_count, (void*)b->d_pn_read,
                   (void*)b->d_pn_se, (void*)b->d_pn_flags, (void*)b->d_pn_work, (void*)b->d_pn_mc, (void*)b->d_pn_uc, (void*)b->d_pn_rho, (void*)b->d_pn_d,
                   (void*)b->d_pn_v, (void*)b->d_pn_chisq, (void*)b->d_place})
     if (p) cudaFree(p);
@@ -590,7 +590,7 @@ static int enqueue(krepp_batch* b)
     pa.s = sa; pa.offsets = b->in_offsets; pa.tau = b->p.tau; pa.no_filter = b->p.no_filter; pa.chisq_value = b->p.chisq;
     pa.parent = ix->dev.parent; pa.nchildren = ix->dev.nchildren; pa.subtree = ix->dev.subtree; pa.depth = ix->dev.depth; pa.blen = ix->dev.blen; pa.leaf_rank = ix->dev.leaf_rank;
     pa.nnodes = h.tree.nnodes; pa.nleaves = h.tree.nleaves; pa.sel = b->d_sel; pa.chain = b->d_chain; pa.chain_cap = b->chain_cap;
-    pa.node_bitmap = b->d_node_bitmap; pa.node_list = b->d_node_list;
+    pa.node_bitmap = b->d_node_bitmap; pa.node_list = b->d_node_list; pa.node_order = b->d_node_order;
     pa.node_cap = b->node_cap; pa.pn_read = b->d_pn_read; pa.pn_se = b->d_pn_se; pa.pn_flags = b->d_pn_flags; pa.pn_work = b->d_pn_work;
     pa.pn_mc = b->d_pn_mc; pa.pn_uc = b->d_pn_uc; pa.pn_rho = b->d_pn_rho; pa.pn_d = b->d_pn_d; pa.pn_v = b->d_pn_v; pa.pn_chisq = b->d_pn_chisq;
     pa.pn_begin = b->d_pn_begin; pa.pn_count = b->d_pn_count;

@@ -134,6 +134,7 @@ struct PlaceArgs {
   // per-warp scratch of the collect kernel
   uint32_t* node_bitmap;       // [warps][ceil((nnodes+1)/32)]
   uint32_t* node_list;         // [warps][nnodes]
+  uint32_t* node_order;        // [warps][nnodes] visiting order of the list (heaviest nodes first)
   uint32_t* sel;               // [warps][3 * nleaves] the read's selected references by ascending se: record, se, start of its chain
   double* chain;               // [warps][chain_cap] per selected leaf, level by level towards the root: prod 1/eff_nchildren
   uint32_t chain_cap;

@@ -224,6 +224,7 @@ __device__ __forceinline__ double jukes_cantor(double d) { return -0.75 * log(1 
 //   place_solve_kernel    thread per internal node entry: the same minimiser as solve_kernel
 //   place_chisq_kernel    thread per node entry: likelihood-ratio test against the closest reference
 //   place_emit_kernel     warp per read: candidates in ascending se, lwr, placement rows
+template <int N> // N = histogram bins kept in registers (th + 1 <= N)
 __global__ void __launch_bounds__(128) place_collect_kernel(const PlaceArgs a)
 {
   const SolveArgs& s = a.s;
@@ -334,11 +335,37 @@ __global__ void __launch_bounds__(128) place_collect_kernel(const PlaceArgs a)
             }
           __syncwarp();
           // 3b. one lane per marked node: a selected leaf brings its own record, an internal node accumulates the leaves below it
+          //     A node costs as many steps as selected leaves sit below it, and a warp round lasts as long as its heaviest
+          //     lane, so the nodes are visited heaviest first (three classes): the handful of near-root nodes that see every
+          //     leaf share their rounds instead of each holding up a round of single-leaf nodes.  Entry j of the read stays
+          //     node j of the ascending list whatever the visiting order.
+          uint32_t* order = a.node_order + (size_t)gwarp * a.nnodes;
+          {
+            uint32_t placed = 0;
+            for (int cls = 0; cls < 3; ++cls)
+              for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
+                const uint32_t j = j0 + lane;
+                bool mine = false;
+                if (j < cnt) {
+                  const uint32_t g = list[j], lo = g - a.subtree[g];
+                  uint32_t f0 = 0, f1 = 0; // selected references with se <= lo, with se <= g
+                  for (uint32_t hi = nsel; f0 < hi;) { const uint32_t mid = (f0 + hi) >> 1; if (sel_se[mid] > lo) hi = mid; else f0 = mid + 1; }
+                  for (uint32_t hi = nsel; f1 < hi;) { const uint32_t mid = (f1 + hi) >> 1; if (sel_se[mid] > g) hi = mid; else f1 = mid + 1; }
+                  const uint32_t w = f1 - f0;
+                  mine = cls == 0 ? w >= 8u : cls == 1 ? (w >= 3u && w < 8u) : w < 3u;
+                }
+                const uint32_t mm = __ballot_sync(0xFFFFFFFFu, mine);
+                if (mine) order[placed + __popc(mm & lt_mask)] = j;
+                placed += __popc(mm);
+              }
+          }
+          __syncwarp();
           const uint32_t enmers = (uint32_t)(a.offsets[r + 1] - a.offsets[r]) - s.k + 1;
           for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
-            const uint32_t j = j0 + lane;
+            const bool active = j0 + lane < cnt;
+            const uint32_t j = active ? order[j0 + lane] : 0u;
             bool solve = false;
-            if (j < cnt) {
+            if (active) {
               const uint32_t g = list[j], e = nbegin + j;
               double d = DBL_MAX, v = nan(""), leq = 0;
               const uint32_t lo = g - a.subtree[g]; // leaves below g have lo < se <= g
@@ -349,8 +376,9 @@ __global__ void __launch_bounds__(128) place_collect_kernel(const PlaceArgs a)
                 d = s.rec_d[rec]; v = s.rec_v[rec];
                 for (uint32_t x = 0; x <= a.tau && x < stride; ++x) leq += (double)s.rec_hist[(size_t)rec * stride + x];
               } else {
-                double mc[kMaxTh + 1];
-                for (uint32_t x = 0; x <= (uint32_t)kMaxTh; ++x) mc[x] = 0;
+                double mc[N];
+#pragma unroll
+                for (int x = 0; x < N; ++x) mc[x] = 0;
                 double nmers = 0, mismatch = 0, match = 0, rho = 0;
                 const uint32_t gdep = a.depth[g];
                 for (uint32_t i = first; i < nsel; ++i) { // ascending leaf se: the order Minfo::add is applied in
@@ -364,14 +392,17 @@ __global__ void __launch_bounds__(128) place_collect_kernel(const PlaceArgs a)
                   mismatch = nmers != 0 ? mismatch : (double)enmers;      // Minfo::add (ref src/query.hpp:139-152)
                   match += m * denom;
                   mismatch -= m * denom;
-                  for (uint32_t x = 0; x < stride; ++x) mc[x] = mc[x] + (double)s.rec_hist[(size_t)rec * stride + x] * denom;
+#pragma unroll
+                  for (int x = 0; x < N; ++x) if ((uint32_t)x < stride) mc[x] = mc[x] + (double)s.rec_hist[(size_t)rec * stride + x] * denom;
                   nmers = fmax(nmers, (double)enmers);
                   rho = fmax(rho, s.rho[se]);
                 }
-                for (uint32_t x = 0; x <= a.tau && x < stride; ++x) leq += mc[x];
+#pragma unroll
+                for (int x = 0; x < N; ++x) if ((uint32_t)x <= a.tau && (uint32_t)x < stride) leq += mc[x];
                 solve = a.no_filter || leq > 1.0;
                 if (solve) {
-                  for (uint32_t x = 0; x < stride; ++x) a.pn_mc[(size_t)e * stride + x] = mc[x];
+#pragma unroll
+                  for (int x = 0; x < N; ++x) if ((uint32_t)x < stride) a.pn_mc[(size_t)e * stride + x] = mc[x];
                   a.pn_uc[e] = mismatch; a.pn_rho[e] = rho;
                 }
               }
@@ -489,7 +520,8 @@ __global__ void __launch_bounds__(128) place_emit_kernel(const PlaceArgs a)
 
 cudaError_t launch_place(const PlaceArgs& a, const LlhTables& tab, int grid, int sms, cudaStream_t stream, StageClock* clk)
 {
-  place_collect_kernel<<<grid, 128, 0, stream>>>(a);
+  if (a.s.th + 1 <= 5) place_collect_kernel<5><<<grid, 128, 0, stream>>>(a);
+  else place_collect_kernel<kMaxTh + 1><<<grid, 128, 0, stream>>>(a);
   if (clk) clk->tick("place_collect_kernel", stream);
   if (a.s.th + 1 <= 5) place_solve_kernel<5><<<sms * 8, 128, 0, stream>>>(a, tab);
   else place_solve_kernel<kMaxTh + 1><<<sms * 8, 128, 0, stream>>>(a, tab);
