@@ -1,7 +1,7 @@
 #!/bin/bash
 # N GPUs of one box: [cli] the config-3 drop-in check, [tests] the shard parity tests (incl. the NCCL two-GPU test), then the
 # sharded arm (mode B) and the replicated arm (mode A) under torchrun.
-# usage: gpurun --gpus N --timeout 1500 -- 'bash tools/gpu_shard2.sh <tag> <N> [cli] [tests]'
+# usage: gpurun --gpus N --timeout 1500 -- 'bash tools/gpu_multi.sh <tag> <N> [cli] [tests]'
 TAG=${1:-shard2}; N=${2:-2}; O=gpurun_out/$TAG; mkdir -p $O
 ( nproc; free -g; nvidia-smi -L; nvidia-smi topo -m ) > $O/box.txt 2>&1
 if [[ " $* " == *" tests "* ]]; then
