@@ -537,14 +537,14 @@ cudaError_t launch_solve(const SolveArgs& a, const LlhTables& tab, int sms, cuda
 {
   const int grid = sms * 8;
   if (a.memo_mask) { const cudaError_t e = cudaMemsetAsync(a.memo_key, 0, 8ull * ((size_t)a.memo_mask + 1), stream); if (e != cudaSuccess) return e; }
-  gate_kernel<<<sms * 4, 256, 0, stream>>>(a);
+  gate_kernel<<<sms * 8, 256, 0, stream>>>(a); // latency-bound streaming kernels run at full occupancy (64 warps per SM)
   if (clk) clk->tick("gate_kernel", stream);
   if (a.th + 1 <= 5) solve_kernel<5><<<grid, 128, 0, stream>>>(a, tab);
   else solve_kernel<kMaxTh + 1><<<grid, 128, 0, stream>>>(a, tab);
   if (clk) clk->tick("solve_kernel", stream);
   if (a.memo_mask) alias_kernel<<<sms * 8, 256, 0, stream>>>(a);
-  merge_kernel<<<grid, 128, 0, stream>>>(a);
-  if (a.want_chisq) chisq_kernel<<<grid, 128, 0, stream>>>(a, tab);
+  merge_kernel<<<sms * 16, 128, 0, stream>>>(a);
+  if (a.want_chisq) chisq_kernel<<<sms * 16, 128, 0, stream>>>(a, tab);
   if (clk) clk->tick(a.want_chisq ? "alias_kernel+merge_kernel+chisq_kernel" : "alias_kernel+merge_kernel", stream);
   return cudaGetLastError();
 }
