@@ -5,7 +5,7 @@
 TAG=${1:-shard2}; N=${2:-2}; O=gpurun_out/$TAG; mkdir -p $O
 ( nproc; free -g; nvidia-smi -L; nvidia-smi topo -m ) > $O/box.txt 2>&1
 if [[ " $* " == *" tests "* ]]; then
-  ( time timeout 900 python -m pytest tests/test_gpu_shard.py -x -q ) > $O/pytest_shard.log 2>&1; echo "pytest rc=$?" | tee -a $O/pytest_shard.log; tail -4 $O/pytest_shard.log
+  ( time timeout 900 python -m pytest tests/test_gpu_shard.py tests/test_gpu_parity.py::test_cli_two_gpus_same_bytes -x -q ) > $O/pytest_shard.log 2>&1; echo "pytest rc=$?" | tee -a $O/pytest_shard.log; tail -4 $O/pytest_shard.log
 fi
 if [[ " $* " == *" cli "* ]]; then timeout 900 bash tools/gpu_cli_c3.sh $O 200000; fi
 python -c "import sys; sys.path.insert(0,'tools'); import workload as W; W.ensure_c3(4000000*$N)" > $O/workload.log 2>&1
