@@ -231,7 +231,7 @@ def shard_arm(args) -> None:
                 src = d_bases[first * READ_LEN:]
             r = job.run([(src[:cnt * READ_LEN + 64], d_offs, cnt)], rows=from_host)[0]
             if from_host:
-                nrec += len(r["records"]); d2h += r["reads"].nbytes + r["records"].nbytes + r["hist"].nbytes
+                nrec += r["n_records"]; d2h += r["reads"].nbytes + r["brief"].nbytes
             else:
                 nrec += r["n_records"]
             ab = me.slot.algorithmic_bytes()
@@ -264,6 +264,7 @@ def shard_arm(args) -> None:
     t_dev, _, (nrec, _, alg), xbytes = timed(False)
     clocks = sampler.stop()
     stages = dict(me.slot.stage_times())
+    me.slot.set_output(records=False, hist=False, placements=False, brief=True)  # what the dist front end asks for: 16-byte rows
     _, t_e2e, (_, d2h, _), _ = timed(True) if not args.no_e2e else (0, 0, (0, 0, 0), 0)
     tot = kd.sum_over_ranks([alg["bytes"], alg["lookups"], alg["entries"], nrec, int(xbytes)], device="cuda")
     sh = me.index.shard
@@ -278,7 +279,7 @@ def shard_arm(args) -> None:
                                 f"({me.index.info.device_bytes / 1e9:.2f} GB image per GPU)",
                        "l2": "inputs larger than L2 and a 256 MiB memset between steps", "records_per_step": tot[3], "workload_setup_s": round(t_wl, 1)},
             "e2e": None if args.no_e2e else {"value": world * n * args.steps / t_e2e, "unit": "reads/s", "h2d_bytes_per_step": n * READ_LEN, "d2h_bytes_per_step": d2h,
-                                             "how": "every batch copied from page-locked host memory inside the timed region, results copied back by krepp_batch_wait; wall clock, max over ranks"},
+                                             "how": "every batch copied from page-locked host memory inside the timed region, read summaries and 16-byte record rows copied back by krepp_batch_wait (krepp_batch_set_output, as the dist command line); wall clock, max over ranks"},
             "gpu_launches": args.steps * len(chunks) * (16 + world), "clocks": clocks,  # per batch: 5 lookup/scan + one join per sender + 6 regroup/resolve + 5 gate..finalize
             "exchange": {"bytes_received_per_step_all_ranks": tot[4], "per_read": tot[4] / (world * n), "transport": "torch.distributed all_to_all_single (NCCL)" if world > 1 else "none (one shard)"},
             "roofline": {"bound": "hbm", "kernel": "whole step of all ranks (lookup, exchange, join on the owning shard, exchange, resolve, solve)", "achieved": achieved,
