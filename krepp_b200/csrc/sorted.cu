@@ -22,6 +22,9 @@
 // that do not fit this pipeline's buffers raise a flag; the host then grows the buffer or redoes the batch with the
 // fused kernel (api.cu).
 #include "device.cuh"
+
+#include <algorithm>
+#include <cstdlib>
 #include "match_common.cuh"
 #include "solve.cuh"
 
@@ -594,11 +597,31 @@ static size_t lookup_smem(uint32_t k) { return lut_chunks(k) * 256 * sizeof(uint
 
 int sorted_resolve_warps(int sms) { return sms * 6 * kResWarps; } // grid of the resolve kernel (sizes SortArgs::keys_g)
 
+// CTAs per SM of the scatter pass (KREPP_SCATTER_CTAS = 1 or 2, default 2).  Measured on B200 (r06, config 3): the pass takes
+// the same 4.6 ms per 1M reads with one CTA per SM as with two -- it is bound by the SM's limit on outstanding returning
+// atomics, not by issue slots or registers -- so at 1 it leaves half the register file to kernels of other batch slots.
+// Together with KREPP_JOIN_CTAS / KREPP_RESOLVE_CTAS (CTAs per SM of those grids) this is the knob set for co-scheduling the
+// atomic-bound and the issue-bound kernels of neighbouring batches; with join and resolve throttled to make room, pipelined
+// slots did overlap (end-to-end above the serial sum) but lost more in the throttled kernels than they hid, so the defaults
+// keep every kernel at full occupancy.
+static int env_int(const char* name, int dflt)
+{
+  const char* e = getenv(name);
+  const int x = e ? atoi(e) : dflt;
+  return x > 0 ? x : dflt;
+}
+static int scatter_ctas_per_sm()
+{
+  static const int v = [] { const char* e = getenv("KREPP_SCATTER_CTAS"); const int x = e ? atoi(e) : 2; return x == 1 ? 1 : 2; }();
+  return v;
+}
+
 template <bool SCATTER>
 static cudaError_t launch_lookup(const DevIndex& ix, const MatchArgs& a, const SortArgs& s, int sms, bool tap, cudaStream_t stream)
 {
   const size_t sm = lookup_smem(ix.k);
   cudaError_t e;
+  if (SCATTER) sms = sms * scatter_ctas_per_sm() / 2; // the launches below use sms * 2 CTAs
   if (tap && !SCATTER) {
     e = cudaFuncSetAttribute(lookup_kernel<SCATTER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (e != cudaSuccess) return e;
@@ -627,7 +650,7 @@ cudaError_t launch_match_sorted(const DevIndex& ix, const MatchArgs& a, const So
   if (clk) clk->tick("scan(rows)", stream);
   if ((e = launch_lookup<true>(ix, a, s, sms, false, stream)) != cudaSuccess) return e;
   if (clk) clk->tick("lookup_kernel<scatter>", stream);
-  join_kernel<true><<<sms * 8, kJoinWarps * 32, 0, stream>>>(ix, s, a.th, a.counters, a.stats);
+  join_kernel<true><<<sms * env_int("KREPP_JOIN_CTAS", 8), kJoinWarps * 32, 0, stream>>>(ix, s, a.th, a.counters, a.stats);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   if (clk) clk->tick("join_kernel", stream);
   if ((e = exclusive_scan(s.hit_count, a.n_reads, s.partials, s.hit_begin, s.hit_cursor, stream)) != cudaSuccess) return e;
@@ -637,7 +660,7 @@ cudaError_t launch_match_sorted(const DevIndex& ix, const MatchArgs& a, const So
   uint32_t rank_bits = 0;
   while ((1ull << rank_bits) < ix.nleaves) ++rank_bits;
   rank_bits += s.extra_rank_bits;
-  resolve_kernel<<<sorted_resolve_warps(sms) / kResWarps, kResWarps * 32, 0, stream>>>(ix, a, s, rank_bits);
+  resolve_kernel<<<std::min(sorted_resolve_warps(sms) / kResWarps, sms * env_int("KREPP_RESOLVE_CTAS", 6)), kResWarps * 32, 0, stream>>>(ix, a, s, rank_bits);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   if (clk) clk->tick("resolve_kernel", stream);
   if (launches) *launches = 11;
