@@ -439,6 +439,7 @@ int krepp_batch_create(krepp_index_t* ix, const krepp_params_t* p, uint32_t max_
   *out = nullptr;
   if (p->hdist_th > (uint32_t)kMaxTh) return fail(KREPP_ERR_ARG, "--hdist-th %u exceeds %d", p->hdist_th, kMaxTh);
   if (p->place && p->hdist_th < p->tau) return fail(KREPP_ERR_ARG, "The threshold tau must be less than HD threshold --hdist-th!");
+  if (p->place && !ix->host.wbackbone) return fail(KREPP_ERR_ARG, "Given index lacks a tree and no backbone tree is provided..."); // ref src/krepp.cpp:61-63
   if (ix->device == KREPP_DEVICE_NONE) return fail(KREPP_ERR_CUDA, "this index handle was opened without a device (KREPP_DEVICE_NONE); queries need a GPU");
   if (cudaSetDevice(ix->device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice(%d) failed", ix->device);
   auto* b = new krepp_batch;

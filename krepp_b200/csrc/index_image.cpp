@@ -271,8 +271,33 @@ std::string HostIndex::load(const std::string& dir, uint32_t shard_id, uint32_t 
   if (frac) { for (uint32_t i = 0; i <= r && i < m; ++i) res_numer[i] = (int32_t)(r + 1); }
   else if (r < m) res_numer[r] = 1;
 
-  // ---- tree
-  if (!slurp(dir + "/tree" + sfx, buf)) return "Failed to open " + dir + "/tree" + sfx + " (indexes without a backbone tree are not supported by the GPU path yet)";
+  // ---- tree: the backbone tree file, else the balanced tree the reference generates over reflist-* (ref src/index.cpp:3-27,
+  //      Node::generate_tree src/phytree.cpp:217-253), written as Newick so that the same parser numbers it
+  wbackbone = slurp(dir + "/tree" + sfx, buf);
+  if (!wbackbone) {
+    std::string rl;
+    if (!slurp(dir + "/reflist" + sfx, rl)) return "Unable to open reference list file for an index without a tree.";
+    std::vector<std::string> names;
+    for (size_t at = 0; at < rl.size();) { // std::getline: one name per line, a last line without newline counts
+      size_t e = rl.find('\n', at);
+      if (e == std::string::npos) e = rl.size();
+      names.push_back(rl.substr(at, e - at));
+      at = e + 1;
+    }
+    if (names.empty()) return "Unable to open reference list file for an index without a tree.";
+    buf.clear();
+    struct Gen {
+      const std::vector<std::string>& nm; std::string& out;
+      void run(size_t lo, size_t hi)
+      { // a range of one name is a leaf; a longer one gets the SECOND half as its first child; every branch length is 1
+        if (hi - lo == 1) { out += '\''; for (char c : nm[lo]) { if (c == '\'') out += '\''; out += c; } out += '\''; }
+        else { const size_t half = lo + (hi - lo) / 2; out += '('; run(half, hi); out += ','; run(lo, half); out += ')'; }
+        out += ":1";
+      }
+    } gen{names, buf};
+    gen.run(0, names.size());
+    buf += ';';
+  }
   if (std::string err = tree.parse(buf); !err.empty()) return err;
 
   // ---- inc, then the shard's slice of cmer

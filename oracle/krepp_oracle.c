@@ -357,6 +357,48 @@ static void tree_free(ko_tree_t* t)
 
 /* ------------------------------------------------------------------------------------------------ index loading */
 
+/* ref src/phytree.cpp:217-253 (Node::generate_tree): a range of one name is a leaf; a longer range [first, last) gets two
+ * children, the SECOND half [first + size/2, last) created before the first half, every branch length 1, internal nodes
+ * unnamed.  Written as Newick (names quoted, a quote doubled) so that the post-order numbering of the parser reproduces se. */
+static void gen_newick(char** names, size_t lo, size_t hi, char** out, size_t* len, size_t* cap)
+{
+#define KO_PUT(ch) do { if (*len + 2 > *cap) { *cap = *cap * 2 + 64; *out = (char*)realloc(*out, *cap); } (*out)[(*len)++] = (ch); } while (0)
+  if (hi - lo == 1) {
+    KO_PUT('\'');
+    for (const char* c = names[lo]; *c; ++c) { if (*c == '\'') KO_PUT('\''); KO_PUT(*c); }
+    KO_PUT('\'');
+  } else {
+    const size_t half = lo + (hi - lo) / 2;
+    KO_PUT('(');
+    gen_newick(names, half, hi, out, len, cap);
+    KO_PUT(',');
+    gen_newick(names, lo, half, out, len, cap);
+    KO_PUT(')');
+  }
+  KO_PUT(':'); KO_PUT('1');
+#undef KO_PUT
+}
+
+static char* newick_from_reflist(char* text, size_t n, size_t* out_len)
+{
+  size_t cnt = 0, capn = 16;
+  char** names = (char**)malloc(capn * sizeof(char*));
+  size_t at = 0;
+  while (at < n) { /* std::getline: one name per line, a final line without newline counts */
+    size_t e = at;
+    while (e < n && text[e] != '\n') ++e;
+    if (cnt == capn) { capn *= 2; names = (char**)realloc(names, capn * sizeof(char*)); }
+    names[cnt] = (char*)malloc(e - at + 1); memcpy(names[cnt], text + at, e - at); names[cnt][e - at] = 0; ++cnt;
+    at = e + 1;
+  }
+  char* out = NULL; size_t len = 0, cap = 0;
+  if (cnt) { gen_newick(names, 0, cnt, &out, &len, &cap); out[len++] = ';'; out[len] = 0; }
+  for (size_t i = 0; i < cnt; ++i) free(names[i]);
+  free(names);
+  *out_len = len;
+  return out;
+}
+
 static char* slurp(const char* path, size_t* n)
 {
   FILE* f = fopen(path, "rb"); if (!f) return NULL;
@@ -403,11 +445,18 @@ ko_index_t* ko_index_load(const char* dir, char* err, size_t errlen)
     }
     free(md);
     t->r = r; t->frac = frac;
-    /* tree: ref src/index.cpp:29-49 (tree-less indexes, generate_partial_tree, are not restated) */
+    /* tree: ref src/index.cpp:29-49; without a tree file the balanced tree over reflist-* (generate_partial_tree, ref
+     * src/index.cpp:3-27, Node::generate_tree src/phytree.cpp:217-253) is restated as the Newick text the parser then reads */
     if (!ix->have_tree) {
       snprintf(path, sizeof path, "%s/tree%s", dir, sfx[s]);
       char* nwk = slurp(path, &n);
-      if (!nwk) { seterr(err, errlen, "Failed to open %s", path); goto fail; }
+      if (!nwk) {
+        snprintf(path, sizeof path, "%s/reflist%s", dir, sfx[s]);
+        char* rl = slurp(path, &n);
+        if (!rl) { seterr(err, errlen, "Unable to open reference list file for an index without a tree."); goto fail; }
+        nwk = newick_from_reflist(rl, n, &n); free(rl);
+        if (!nwk) { seterr(err, errlen, "Unable to open reference list file for an index without a tree."); goto fail; }
+      }
       int rc = tree_from_newick(&ix->tree, nwk, n, err, errlen); free(nwk);
       if (rc) goto fail;
       ix->have_tree = 1;

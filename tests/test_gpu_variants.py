@@ -9,7 +9,7 @@ import pytest
 
 from conftest import REF_DIR, needs_ref
 from test_gpu_parity import fastq_reads
-from variants import SMALL, VARIANTS, build
+from variants import SMALL, TREELESS, VARIANTS, build
 
 pytestmark = [pytest.mark.gpu, needs_ref]
 
@@ -33,4 +33,26 @@ def test_gpu_equals_oracle_on_variant(label, args, pipeline, tmp_path_factory, m
                          check=True).stdout.splitlines()[2:]
     assert sorted(b.estimate_distances().splitlines()) == sorted(ref), label
     b.close()
+    g.close()
+
+
+def test_gpu_treeless_index(tmp_path_factory):
+    """dist on an index built without a backbone tree (tree generated from reflist-*): stages against the oracle, TSV against
+    the reference; place is refused with the reference's message."""
+    import krepp_b200
+    import oracle_lib as O
+    from gpu_common import run_and_compare
+    from krepp_b200.capi import KreppError
+    idx = build(*TREELESS, tmp_path_factory.getbasetemp(), with_tree=False)
+    names, reads = fastq_reads(os.path.join(SMALL, "reads.fq"))
+    o, g = O.OracleIndex(idx), krepp_b200.Index(idx, 0)
+    st = run_and_compare(idx, reads, o, g)
+    assert st["solves"] > 500
+    b = krepp_b200.IBatch(g, reads, names=names)
+    ref = subprocess.run([os.path.join(REF_DIR, "krepp"), "dist", "-i", idx, "-q", os.path.join(SMALL, "reads.fq")], capture_output=True, text=True,
+                         check=True).stdout.splitlines()[2:]
+    assert sorted(b.estimate_distances().splitlines()) == sorted(ref)
+    b.close()
+    with pytest.raises(KreppError, match="lacks a tree"):
+        krepp_b200.IBatch(g, reads[:4], place=True, no_filter=False)
     g.close()

@@ -8,7 +8,7 @@ import pytest
 
 from conftest import REF_DIR, needs_ref
 from test_gpu_parity import fastq_reads
-from variants import SMALL, VARIANTS, build
+from variants import SMALL, TREELESS, VARIANTS, build
 
 pytestmark = [needs_ref]
 
@@ -39,3 +39,23 @@ def test_oracle_equals_reference_on_variant(label, args, tmp_path_factory):
     ora = subprocess.run([os.path.join(os.path.dirname(REF_DIR), "_build", "krepp_oracle"), "dist", idx, fq], capture_output=True, text=True,
                          check=True).stdout.splitlines()[1:]
     assert sorted(ref) == sorted(ora), label
+
+
+def test_treeless_index_dist_equals_reference(tmp_path_factory):
+    """No tree-* file: the tree is the balanced one the reference generates over reflist-*.  The oracle's and the C++
+    loader's restatement of it must give the reference's leaf numbering (else every reference name below would be wrong)."""
+    import krepp_b200
+    import oracle_lib as O
+    idx = build(*TREELESS, tmp_path_factory.getbasetemp(), with_tree=False)
+    assert os.path.exists(os.path.join(idx, "reflist-m4r1-frac")) and not os.path.exists(os.path.join(idx, "tree-m4r1-frac"))
+    fq = os.path.join(SMALL, "reads.fq")
+    ref = subprocess.run([os.path.join(REF_DIR, "krepp"), "dist", "-i", idx, "-q", fq], capture_output=True, text=True, check=True).stdout.splitlines()[2:]
+    ora = subprocess.run([os.path.join(os.path.dirname(REF_DIR), "_build", "krepp_oracle"), "dist", idx, fq], capture_output=True, text=True,
+                         check=True).stdout.splitlines()[1:]
+    assert len(ref) > 300 and sorted(ref) == sorted(ora)
+    ix, o = krepp_b200.Index(idx, device=-1), O.OracleIndex(idx)   # the C++ loader builds the same tree as the oracle
+    assert ix.info.nnodes == 15 and ix.info.nleaves == 8
+    for se in range(1, ix.info.nnodes + 1):
+        assert ix.node_name(se) == o.name(se), se
+    place = subprocess.run([os.path.join(REF_DIR, "krepp"), "place", "-i", idx, "-q", fq], capture_output=True, text=True)
+    assert place.returncode != 0 and "lacks a tree" in place.stderr   # what krepp_batch_create answers for place on this handle

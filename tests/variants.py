@@ -22,7 +22,12 @@ VARIANTS = [
 ]
 
 
-def build(label, args, tmp_root):
+# An index built WITHOUT a backbone tree: the reference writes reflist-* instead of tree-* and generates a balanced tree over
+# the names at load time (ref src/index.cpp:3-27, src/phytree.cpp:217-253); `dist` works on it, `place` needs a tree.
+TREELESS = ("treeless_k21_h7", ["-k", "21", "-w", "25", "-h", "7"])
+
+
+def build(label, args, tmp_root, with_tree=True):
     """Runs the reference's `krepp index` in a scratch copy of the golden genomes; returns the index directory."""
     work = os.path.join(str(tmp_root), label)
     if not os.path.isdir(os.path.join(work, "index")):
@@ -30,6 +35,6 @@ def build(label, args, tmp_root):
         for item in ("genomes", "input_map.tsv", "tree.nwk"):
             src, dst = os.path.join(SMALL, item), os.path.join(work, item)
             (shutil.copytree if os.path.isdir(src) else shutil.copy)(src, dst)
-        subprocess.run([os.path.join(REF_DIR, "krepp"), "index", *args, "-o", "index", "-i", "input_map.tsv", "-t", "tree.nwk"], cwd=work, check=True,
-                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        subprocess.run([os.path.join(REF_DIR, "krepp"), "index", *args, "-o", "index", "-i", "input_map.tsv", *(["-t", "tree.nwk"] if with_tree else [])],
+                       cwd=work, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     return os.path.join(work, "index")
