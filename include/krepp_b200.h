@@ -256,6 +256,13 @@ int krepp_shard_join(krepp_batch_t* b, uint32_t n_sources, const void* const* d_
 /* d_hits must stay untouched until krepp_batch_wait has returned. */
 int krepp_shard_finish(krepp_batch_t* b, const void* d_hits, uint64_t n_hits);
 
+/* Device memory for the exchange buffers, for hosts that do not link the CUDA runtime themselves (the krepp_b200 executable:
+ * all shards in one process, runs moved between GPUs by peer copies over NVLink).  krepp_device_copy is synchronous; a
+ * device of KREPP_DEVICE_NONE means host memory. */
+int krepp_device_alloc(int device, uint64_t bytes, void** out);
+void krepp_device_free(int device, void* p);
+int krepp_device_copy(int dst_device, void* dst, int src_device, const void* src, uint64_t bytes);
+
 /* -------------------------------------------------------------------------------------------------- host I/O layer
  * The steps immediately either side of the GPU path.  Pure host code: usable
  * without a device (the index handle may have been opened with KREPP_DEVICE_NONE). */

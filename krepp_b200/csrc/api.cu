@@ -838,6 +838,35 @@ int krepp_shard_finish(krepp_batch_t* b, const void* d_hits, uint64_t n_hits)
   return KREPP_OK;
 }
 
+int krepp_device_alloc(int device, uint64_t bytes, void** out)
+{
+  if (!out) return fail(KREPP_ERR_ARG, "krepp_device_alloc: null argument");
+  *out = nullptr;
+  if (cudaSetDevice(device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+  CU(cudaMalloc(out, bytes ? bytes : 16));
+  return KREPP_OK;
+}
+
+void krepp_device_free(int device, void* p)
+{
+  if (!p) return;
+  cudaSetDevice(device);
+  cudaFree(p);
+}
+
+int krepp_device_copy(int dst_device, void* dst, int src_device, const void* src, uint64_t bytes)
+{
+  if (!bytes) return KREPP_OK;
+  if (!dst || !src) return fail(KREPP_ERR_ARG, "krepp_device_copy: null argument");
+  if (dst_device == KREPP_DEVICE_NONE && src_device == KREPP_DEVICE_NONE) { std::memcpy(dst, src, bytes); return KREPP_OK; }
+  if (cudaSetDevice(dst_device == KREPP_DEVICE_NONE ? src_device : dst_device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice failed");
+  if (dst_device == KREPP_DEVICE_NONE) CU(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+  else if (src_device == KREPP_DEVICE_NONE) CU(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+  else if (src_device == dst_device) CU(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToDevice));
+  else CU(cudaMemcpyPeer(dst, dst_device, src, src_device, bytes)); // NVLink when peer access is possible, staged through the host otherwise
+  return KREPP_OK;
+}
+
 int krepp_batch_enable_tap(krepp_batch_t* b, int stage, uint64_t capacity_items)
 {
   if (!b || (stage != 1 && stage != 2) || (stage == 1 && !capacity_items)) return fail(KREPP_ERR_ARG, "krepp_batch_enable_tap: bad argument");

@@ -8,6 +8,7 @@
 // GPUs given by --num-gpus / --devices (index replicated per GPU, no data-path collective: SURVEY.md section 8e mode A).
 #include "../../include/krepp_b200.h"
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <condition_variable>
@@ -38,6 +39,7 @@ struct Options {
   bool multi = true, filter = false, summarize = false, tabular = false, verbose = false;
   // additions of this implementation
   std::vector<int> devices;
+  bool shard_index = false; // --shard-index: every device holds one bucket-range shard of the table (SURVEY.md 8e mode B)
   uint32_t batch_reads = 1u << 18, slots_per_gpu = 3;
   uint64_t batch_bases = 64ull << 20;
 };
@@ -50,7 +52,9 @@ const char* kUsage =
   "  dist:    --dist-max X   --multi/--no-multi [true]   --filter/--no-filter [false]\n"
   "  place:   --tau N [2]   --multi/--no-multi [true]   --filter/--no-filter [true]   --tabular/--no-tabular [false]\n"
   "           -t,--nwk-file / -l,--lineage-file (not supported by the GPU path yet)\n"
-  "  GPU:     --num-gpus N [1] | --devices 0,1,..   --batch-reads N [262144]   --batch-bases N [67108864]   --slots N [3]\n";
+  "  GPU:     --num-gpus N [1] | --devices 0,1,..   --batch-reads N [262144]   --batch-bases N [67108864]   --slots N [3]\n"
+  "           --shard-index   split the index by LSH bucket range over the devices instead of replicating it (for an index\n"
+  "                           larger than one GPU's memory; lookups and hits travel between the GPUs by peer copies)\n";
 
 bool exists(const std::string& p, bool dir)
 {
@@ -102,6 +106,7 @@ Options parse(int argc, char** argv)
     else if (k == "--devices") { const std::string v = need(i, k); size_t p = 0; while (p < v.size()) { o.devices.push_back(atoi(v.c_str() + p)); p = v.find(',', p); if (p == std::string::npos) break; ++p; } }
     else if (k == "--batch-reads") o.batch_reads = (uint32_t)strtoul(need(i, k).c_str(), nullptr, 10);
     else if (k == "--batch-bases") o.batch_bases = strtoull(need(i, k).c_str(), nullptr, 10);
+    else if (k == "--shard-index") o.shard_index = true;
     else if (k == "--slots") o.slots_per_gpu = (uint32_t)strtoul(need(i, k).c_str(), nullptr, 10);
     else error_exit("The following argument was not expected: " + a[i]);
   }
@@ -155,6 +160,176 @@ void check(int rc) { if (rc != KREPP_OK) error_exit(krepp_last_error()); }
 
 } // namespace
 
+// ------------------------------------------------------------------------------------------------ --shard-index (mode B)
+// All shards live in this process, one per entry of --devices (an entry may repeat: several shards on one GPU).  A round takes
+// one sub-batch of reads per device and walks the three phases of include/krepp_b200.h "bucket-range shards", one thread per
+// device inside a phase and a join between phases; runs of lookup tuples and of hit entries change device by
+// krepp_device_copy (peer copies).  Output order is input order.
+struct ShardDev {
+  int dev = 0;
+  krepp_index_t* ix = nullptr;
+  krepp_batch_t* slot = nullptr;
+  char* h_bases = nullptr; uint64_t* h_offsets = nullptr;
+  std::vector<char> names; std::vector<uint64_t> name_off;
+  uint32_t n = 0; uint64_t nb = 0;
+  void *d_bases = nullptr, *d_offsets = nullptr, *d_tuples = nullptr, *d_rowbegin = nullptr, *recv_tuples = nullptr, *recv_rb = nullptr, *d_hits = nullptr,
+       *recv_hits = nullptr;
+  uint64_t cap_tuples = 0, cap_recv_tuples = 0, cap_hits = 0, cap_recv_hits = 0;
+  std::vector<uint64_t> so, ho;
+  uint32_t row0 = 0, row1 = 0;
+  std::vector<char> text; size_t text_len = 0;
+  std::vector<double> w;
+};
+
+template <class F>
+static void each_device(size_t n, F&& f)
+{
+  std::vector<std::thread> th;
+  for (size_t g = 1; g < n; ++g) th.emplace_back(f, g);
+  f(0);
+  for (auto& t : th) t.join();
+}
+
+static void grow(int dev, void*& p, uint64_t& cap, uint64_t want_items)
+{ // 16-byte items; contents are not kept
+  if (want_items <= cap) return;
+  krepp_device_free(dev, p);
+  cap = want_items + want_items / 8 + 4096;
+  check(krepp_device_alloc(dev, 16 * cap, &p));
+}
+
+static int run_sharded(const Options& o, const krepp_params_t& p, bool place, const std::string& invocation, FILE* out)
+{
+  const size_t N = o.devices.size();
+  std::vector<ShardDev> D(N);
+  each_device(N, [&](size_t g) { D[g].dev = o.devices[g]; check(krepp_index_open_shard(o.index_dir.c_str(), D[g].dev, (uint32_t)g, (uint32_t)N, &D[g].ix)); });
+  krepp_index_info_t info;
+  check(krepp_index_info(D[0].ix, &info));
+  std::vector<uint32_t> splits(N + 1);
+  { krepp_shard_info_t si; check(krepp_index_shard_info(D[0].ix, &si, splits.data(), (uint32_t)N + 1)); }
+  for (size_t g = 0; g < N; ++g) {
+    ShardDev& d = D[g];
+    d.row0 = splits[g]; d.row1 = splits[g + 1];
+    check(krepp_batch_create(d.ix, &p, o.batch_reads, o.batch_bases, &d.slot));
+    check(krepp_batch_set_output(d.slot, place ? (KREPP_OUT_RECORDS | KREPP_OUT_PLACEMENTS) : KREPP_OUT_BRIEF));
+    check(krepp_batch_host_buffers(d.slot, &d.h_bases, &d.h_offsets));
+    d.names.resize(64ull * o.batch_reads); d.name_off.resize(o.batch_reads);
+    check(krepp_device_alloc(d.dev, o.batch_bases + 64, &d.d_bases));
+    check(krepp_device_alloc(d.dev, 8ull * (o.batch_reads + 1), &d.d_offsets));
+    check(krepp_device_alloc(d.dev, 4ull * (info.nrows + 1), &d.d_rowbegin));
+    check(krepp_device_alloc(d.dev, 4ull * N * (d.row1 - d.row0 + 1), &d.recv_rb));
+    d.so.assign(N + 1, 0); d.ho.assign(N + 1, 0);
+    d.text.resize(1 << 20);
+  }
+  std::vector<char> text(1 << 20);
+  { size_t n = krepp_format_header(D[0].ix, &p, o.tabular, invocation.c_str(), text.data(), text.size());
+    if (n > text.size()) { text.resize(n); n = krepp_format_header(D[0].ix, &p, o.tabular, invocation.c_str(), text.data(), text.size()); }
+    if (n && fwrite(text.data(), 1, n, out) != n) error_exit("Failed to write the output"); }
+  krepp_reader_t* reader = nullptr;
+  check(krepp_reader_open(o.query.c_str(), &reader));
+  uint64_t total_queries = 0;
+  std::vector<double> wcount(info.nnodes + 1, 0.0);
+  int has_previous = 0, eof = 0;
+  const bool jplace = place && !o.tabular && !p.summarize;
+  while (!eof) {
+    uint64_t round_reads = 0;
+    for (size_t g = 0; g < N; ++g) { // one sub-batch per device, in input order
+      ShardDev& d = D[g];
+      d.n = 0; d.nb = 0;
+      if (!eof) check(krepp_reader_next(reader, d.h_bases, o.batch_bases, d.h_offsets, o.batch_reads, d.names.data(), d.names.size(), d.name_off.data(), &d.n, &eof));
+      if (!d.n) d.h_offsets[0] = 0;
+      d.nb = d.h_offsets[d.n];
+      round_reads += d.n;
+    }
+    if (!round_reads) break;
+    total_queries += round_reads;
+    // phase 1, home: reads -> tuples grouped by row
+    each_device(N, [&](size_t g) {
+      ShardDev& d = D[g];
+      check(krepp_device_copy(d.dev, d.d_bases, KREPP_DEVICE_NONE, d.h_bases, d.nb));
+      check(krepp_device_copy(d.dev, d.d_offsets, KREPP_DEVICE_NONE, d.h_offsets, 8ull * (d.n + 1)));
+      for (;;) {
+        if (!d.cap_tuples) grow(d.dev, d.d_tuples, d.cap_tuples, std::max<uint64_t>((uint64_t)o.batch_bases / 2, 4096));
+        const int rc = krepp_shard_lookup(d.slot, (const char*)d.d_bases, (const uint64_t*)d.d_offsets, d.n, d.nb + 64, d.d_tuples, d.cap_tuples, (uint32_t*)d.d_rowbegin, d.so.data());
+        if (rc == KREPP_ERR_CAPACITY && d.so[N] > d.cap_tuples) { grow(d.dev, d.d_tuples, d.cap_tuples, d.so[N]); continue; }
+        check(rc);
+        break;
+      }
+    });
+    // phase 2, owner: every sender's run against this shard
+    each_device(N, [&](size_t g) {
+      ShardDev& d = D[g];
+      const uint64_t nloc = (uint64_t)d.row1 - d.row0 + 1;
+      uint64_t total = 0;
+      for (size_t s = 0; s < N; ++s) total += D[s].so[g + 1] - D[s].so[g];
+      grow(d.dev, d.recv_tuples, d.cap_recv_tuples, total);
+      std::vector<const void*> tp(N), rp(N);
+      uint64_t at = 0;
+      for (size_t s = 0; s < N; ++s) {
+        const uint64_t cnt = D[s].so[g + 1] - D[s].so[g];
+        check(krepp_device_copy(d.dev, (char*)d.recv_tuples + 16 * at, D[s].dev, (const char*)D[s].d_tuples + 16 * D[s].so[g], 16 * cnt));
+        check(krepp_device_copy(d.dev, (char*)d.recv_rb + 4 * nloc * s, D[s].dev, (const char*)D[s].d_rowbegin + 4ull * d.row0, 4 * nloc));
+        tp[s] = (const char*)d.recv_tuples + 16 * at;
+        rp[s] = (const char*)d.recv_rb + 4 * nloc * s;
+        at += cnt;
+      }
+      for (;;) {
+        if (!d.cap_hits) grow(d.dev, d.d_hits, d.cap_hits, std::max<uint64_t>(96ull * o.batch_reads, 65536));
+        const int rc = krepp_shard_join(d.slot, (uint32_t)N, tp.data(), reinterpret_cast<const uint32_t* const*>(rp.data()), d.d_hits, d.cap_hits, d.ho.data());
+        if (rc == KREPP_ERR_CAPACITY && d.ho[N] > d.cap_hits) { grow(d.dev, d.d_hits, d.cap_hits, d.ho[N]); continue; }
+        check(rc);
+        break;
+      }
+    });
+    // phase 3, home again: the batch's hit entries from all owners -> results -> text
+    each_device(N, [&](size_t g) {
+      ShardDev& d = D[g];
+      uint64_t total = 0;
+      for (size_t ow = 0; ow < N; ++ow) total += D[ow].ho[g + 1] - D[ow].ho[g];
+      grow(d.dev, d.recv_hits, d.cap_recv_hits, total);
+      uint64_t at = 0;
+      for (size_t ow = 0; ow < N; ++ow) {
+        const uint64_t cnt = D[ow].ho[g + 1] - D[ow].ho[g];
+        check(krepp_device_copy(d.dev, (char*)d.recv_hits + 16 * at, D[ow].dev, (const char*)D[ow].d_hits + 16 * D[ow].ho[g], 16 * cnt));
+        at += cnt;
+      }
+      check(krepp_shard_finish(d.slot, d.recv_hits, total));
+      krepp_results_t res;
+      check(krepp_batch_wait(d.slot, &res));
+      double* w = nullptr;
+      if (p.summarize) { d.w.assign(info.nnodes + 1, 0.0); w = d.w.data(); }
+      for (;;) {
+        int prev = 0;
+        const size_t n = place ? krepp_format_place(d.ix, &p, &res, d.names.data(), d.name_off.data(), o.tabular, &prev, w, d.text.data(), d.text.size())
+                               : krepp_format_dist(d.ix, &p, &res, d.names.data(), d.name_off.data(), w, d.text.data(), d.text.size());
+        if (n <= d.text.size()) { d.text_len = n; break; }
+        d.text.resize(n + n / 4);
+        if (w) d.w.assign(info.nnodes + 1, 0.0);
+      }
+    });
+    for (size_t g = 0; g < N; ++g) {
+      ShardDev& d = D[g];
+      if (p.summarize) { for (uint32_t se = 0; se <= info.nnodes; ++se) wcount[se] += d.w[se]; continue; }
+      if (!d.text_len) continue;
+      if (jplace && has_previous) fwrite(",\n", 1, 2, out); // ref src/krepp.cpp:476-481
+      if (fwrite(d.text.data(), 1, d.text_len, out) != d.text_len) error_exit("Failed to write the output");
+      has_previous = 1;
+    }
+  }
+  krepp_reader_close(reader);
+  { size_t n = krepp_format_footer(D[0].ix, &p, o.tabular, wcount.data(), total_queries, invocation.c_str(), text.data(), text.size());
+    if (n > text.size()) { text.resize(n); n = krepp_format_footer(D[0].ix, &p, o.tabular, wcount.data(), total_queries, invocation.c_str(), text.data(), text.size()); }
+    if (n && fwrite(text.data(), 1, n, out) != n) error_exit("Failed to write the output"); }
+  fflush(out);
+  fprintf(stderr, "Total number of sequences queried: %llu\n", (unsigned long long)total_queries);
+  for (ShardDev& d : D) {
+    krepp_batch_destroy(d.slot);
+    for (void* q : {d.d_bases, d.d_offsets, d.d_tuples, d.d_rowbegin, d.recv_tuples, d.recv_rb, d.d_hits, d.recv_hits}) krepp_device_free(d.dev, q);
+    krepp_index_close(d.ix);
+  }
+  return 0;
+}
+
 int main(int argc, char** argv)
 {
   fprintf(stderr, "krepp_b200 version: v0.8.3+b200\n");
@@ -175,6 +350,16 @@ int main(int argc, char** argv)
   }
 
   fprintf(stderr, place ? "Loading the index and the backbone tree...\n" : "Loading the index and initializing...\n");
+  if (o.shard_index) {
+    FILE* sout = stdout;
+    if (!o.output_path.empty()) { sout = fopen(o.output_path.c_str(), "wb"); if (!sout) error_exit("Failed to open the output file at " + o.output_path); }
+    const auto tq = std::chrono::system_clock::now();
+    run_sharded(o, p, place, invocation, sout);
+    if (sout != stdout) fclose(sout);
+    const std::chrono::duration<float> es = std::chrono::system_clock::now() - tq;
+    fprintf(stderr, place ? "Done placing queries, elapsed: %g sec\n" : "Done estimating distances, elapsed: %g sec\n", es.count());
+    return 0;
+  }
   std::vector<krepp_index_t*> index(o.devices.size(), nullptr);
   { // one replica of the index image per GPU, uploaded concurrently
     std::vector<std::thread> th;

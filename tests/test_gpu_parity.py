@@ -202,6 +202,29 @@ def test_cli_dist_golden_small(tmp_path):
     assert out.read_text().splitlines()[2:] == body[2:]  # same rows in the same (input) order
 
 
+def test_cli_shard_index_same_bytes(tmp_path):
+    """--shard-index (SURVEY.md 8e mode B inside one process: every --devices entry holds one bucket-range shard, runs of lookups
+    and hits move between them by peer copies) must not change a byte of dist / place output.  Three shards on cuda:0 here; on a
+    multi-GPU box also one shard per GPU."""
+    import torch
+    small = os.path.join(conftest.GOLDEN_DIR, "small")
+    base = ("-i", os.path.join(small, "index"), "-q", os.path.join(small, "reads.fq"))
+    layouts = [("--devices", "0,0,0")] + ([("--num-gpus", "2")] if torch.cuda.device_count() >= 2 else [])
+    for sub in (("dist",), ("dist", "--filter", "--batch-reads", "29"), ("place", "--batch-reads", "40"), ("place", "--tabular")):
+        one = _cli("--num-threads", "2", *sub, *base)
+        assert one.returncode == 0, one.stderr
+        for lay in layouts:
+            sh = _cli("--num-threads", "2", *sub, *base, "--shard-index", *lay)
+            assert sh.returncode == 0, sh.stderr
+            if sub[0] == "place" and "--tabular" not in sub:
+                import json
+                a, b = json.loads(one.stdout), json.loads(sh.stdout)
+                assert a["placements"] == b["placements"] and a["tree"] == b["tree"] and len(b["placements"]) > 100
+            else:
+                assert one.stdout.splitlines()[1:] == sh.stdout.splitlines()[1:] and len(sh.stdout.splitlines()) > 200, (sub, lay)
+            assert "Total number of sequences queried: 236" in sh.stderr
+
+
 def test_cli_two_gpus_same_bytes(tmp_path):
     """--num-gpus 2 (index replicated, batches dealt round-robin to the GPUs: SURVEY.md 8e mode A) must not change a byte of
     the output, which stays in input order.  Skipped on one-GPU boxes."""
