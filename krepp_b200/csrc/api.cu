@@ -862,8 +862,13 @@ int krepp_device_copy(int dst_device, void* dst, int src_device, const void* src
   if (cudaSetDevice(dst_device == KREPP_DEVICE_NONE ? src_device : dst_device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice failed");
   if (dst_device == KREPP_DEVICE_NONE) CU(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
   else if (src_device == KREPP_DEVICE_NONE) CU(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
-  else if (src_device == dst_device) CU(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToDevice));
-  else CU(cudaMemcpyPeer(dst, dst_device, src, src_device, bytes)); // NVLink when peer access is possible, staged through the host otherwise
+  else {
+    // device-to-device copies return before they have run (and the legacy stream they run on does not order the slots' non-blocking
+    // streams), so wait for them: the caller launches kernels on other streams that read `dst` next
+    if (src_device == dst_device) CU(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToDevice));
+    else CU(cudaMemcpyPeer(dst, dst_device, src, src_device, bytes)); // NVLink when peer access is possible, staged through the host otherwise
+    CU(cudaStreamSynchronize(cudaStreamLegacy));
+  }
   return KREPP_OK;
 }
 

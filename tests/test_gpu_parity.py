@@ -223,6 +223,18 @@ def test_cli_shard_index_same_bytes(tmp_path):
             else:
                 assert one.stdout.splitlines()[1:] == sh.stdout.splitlines()[1:] and len(sh.stdout.splitlines()) > 200, (sub, lay)
             assert "Total number of sequences queried: 236" in sh.stderr
+    if conftest.have_ref():  # and at a size where a missing synchronisation between the phases shows: 20,000 reads on the toy index
+        import synth
+        seq, offs = synth.load_packed(os.path.join(TOY_DIR, "genomes.npz"))
+        fq = str(tmp_path / "toy20k.fq")
+        synth.write_fastq(fq, synth.sample_reads(seq, offs, 20000, seed=8))
+        base = ("--num-threads", "4", "dist", "-i", os.path.join(TOY_DIR, "index_toy"), "-q", fq, "--batch-reads", "3000")
+        one = _cli(*base)
+        assert one.returncode == 0, one.stderr
+        for lay in [("--devices", "0,0")] + layouts:
+            sh = _cli(*base, "--shard-index", *lay)
+            assert sh.returncode == 0, sh.stderr
+            assert one.stdout.splitlines()[1:] == sh.stdout.splitlines()[1:] and len(sh.stdout.splitlines()) > 20000, lay
 
 
 def test_cli_two_gpus_same_bytes(tmp_path):
