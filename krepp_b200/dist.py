@@ -103,6 +103,7 @@ class ShardRank:
         from .capi import CapacityError
         torch = self.torch
         with torch.cuda.device(self.dev):
+            torch.cuda.current_stream().synchronize()  # the reads may still be on their way (torch's stream); the library has its own
             while True:
                 try:
                     so = self.slot.shard_lookup(d_bases.data_ptr(), d_offsets.data_ptr(), n_reads, d_bases.numel(), self.tuples.data_ptr(),
