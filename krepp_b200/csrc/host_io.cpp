@@ -413,6 +413,7 @@ size_t format_dist_rows(const krepp_index_t* ix, const krepp_params_t* p, const 
   for (uint32_t r = 0; r < res->n_reads; ++r) {
     const krepp_read_summary_t& s = res->reads[r];
     const char* id = name_of(names, name_offsets, r);
+    const size_t id_len = strlen(id);
     if (p->summarize) { // ref src/query.cpp:160-171
       if (!wcount) continue;
       keep.clear();
@@ -430,11 +431,11 @@ size_t format_dist_rows(const krepp_index_t* ix, const krepp_params_t* p, const 
       for_selected(rows, s, [&](const R& rec) {
         if (!p->no_filter && !r_chisq_ok(rec, p)) return;
         if (has_max && !(rec.d_llh < p->dist_max)) return;
-        o.put(id); o.ch('\t'); o.put(t.node_name(r_se(rec), false)); o.ch('\t'); o.fixed5(rec.d_llh); o.ch('\n');
+        o.put(id, id_len); o.ch('\t'); o.put(t.shown[r_se(rec)]); o.ch('\t'); o.fixed5(rec.d_llh); o.ch('\n');
       });
     } else {
       const R& rec = rows[s.closest];
-      o.put(id); o.ch('\t'); o.put(t.node_name(r_se(rec), false)); o.ch('\t'); o.fixed5(rec.d_llh); o.ch('\n');
+      o.put(id, id_len); o.ch('\t'); o.put(t.shown[r_se(rec)]); o.ch('\t'); o.fixed5(rec.d_llh); o.ch('\n');
     }
   }
   return o.len;
