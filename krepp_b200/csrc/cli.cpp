@@ -404,16 +404,37 @@ int main(int argc, char** argv)
   uint64_t total_queries = 0;
   std::vector<double> wcount(info.nnodes + 1, 0.0);
 
-  std::thread consumer([&] {
+  // The text of a batch is formatted by --num-threads workers into one of two buffer sets and written by a writer thread of its
+  // own, so that the next batch is formatted (and its slot handed back to the reader) while this one goes to the file.
+  struct TextSet { std::vector<std::vector<char>> part; std::vector<size_t> len; };
+  const uint32_t T = o.num_threads;
+  std::vector<TextSet> sets(2);
+  Channel<TextSet*> sets_free, sets_full;
+  for (TextSet& ts : sets) { ts.part.assign(T, std::vector<char>(1 << 20)); ts.len.assign(T, 0); sets_free.push(&ts); }
+  const bool jplace = place && !o.tabular && !p.summarize;
+
+  std::thread writer([&] {
     int has_previous = 0;
-    const uint32_t T = o.num_threads;
-    std::vector<std::vector<char>> part(T, std::vector<char>(1 << 20));
-    std::vector<size_t> part_len(T, 0);
+    TextSet* ts = nullptr;
+    while (sets_full.pop(ts)) {
+      for (uint32_t t = 0; t < T; ++t) {
+        if (!ts->len[t]) continue;
+        if (jplace && has_previous) fwrite(",\n", 1, 2, out); // ref src/krepp.cpp:476-481
+        if (fwrite(ts->part[t].data(), 1, ts->len[t], out) != ts->len[t]) error_exit("Failed to write the output");
+        has_previous = 1;
+      }
+      sets_free.push(ts);
+    }
+  });
+
+  std::thread consumer([&] {
     std::vector<std::vector<double>> part_w(T);
     Slot* s = nullptr;
     while (busy_q.pop(s)) {
       krepp_results_t res;
       check(krepp_batch_wait(s->batch, &res));
+      TextSet* ts = nullptr;
+      sets_free.pop(ts);
       // split the batch's reads over T workers; every worker formats its range into its own buffer
       auto work = [&](uint32_t t) {
         const uint32_t lo = (uint32_t)((uint64_t)res.n_reads * t / T), hi = (uint32_t)((uint64_t)res.n_reads * (t + 1) / T);
@@ -422,27 +443,25 @@ int main(int argc, char** argv)
         sub.n_reads = hi - lo;
         double* w = nullptr;
         if (p.summarize) { part_w[t].assign(info.nnodes + 1, 0.0); w = part_w[t].data(); }
+        std::vector<char>& buf = ts->part[t];
         for (;;) {
           int prev = 0;
-          const size_t n = place ? krepp_format_place(index[0], &p, &sub, s->names.data(), s->name_off.data() + lo, o.tabular, &prev, w, part[t].data(), part[t].size())
-                                 : krepp_format_dist(index[0], &p, &sub, s->names.data(), s->name_off.data() + lo, w, part[t].data(), part[t].size());
-          if (n <= part[t].size()) { part_len[t] = n; break; }
-          part[t].resize(n + n / 4);
+          const size_t n = place ? krepp_format_place(index[0], &p, &sub, s->names.data(), s->name_off.data() + lo, o.tabular, &prev, w, buf.data(), buf.size())
+                                 : krepp_format_dist(index[0], &p, &sub, s->names.data(), s->name_off.data() + lo, w, buf.data(), buf.size());
+          if (n <= buf.size()) { ts->len[t] = n; break; }
+          buf.resize(n + n / 4);
           if (w) part_w[t].assign(info.nnodes + 1, 0.0);
         }
       };
       if (T == 1) work(0);
       else { std::vector<std::thread> th; for (uint32_t t = 0; t < T; ++t) th.emplace_back(work, t); for (auto& x : th) x.join(); }
-      const bool jplace = place && !o.tabular && !p.summarize;
-      for (uint32_t t = 0; t < T; ++t) {
-        if (p.summarize) { for (uint32_t se = 0; se <= info.nnodes; ++se) wcount[se] += part_w[t][se]; continue; }
-        if (!part_len[t]) continue;
-        if (jplace && has_previous) fwrite(",\n", 1, 2, out); // ref src/krepp.cpp:476-481
-        if (fwrite(part[t].data(), 1, part_len[t], out) != part_len[t]) error_exit("Failed to write the output");
-        has_previous = 1;
-      }
-      free_q.push(s);
+      free_q.push(s); // results and names are no longer needed: the reader may fill the slot again
+      if (p.summarize) {
+        for (uint32_t t = 0; t < T; ++t) { for (uint32_t se = 0; se <= info.nnodes; ++se) wcount[se] += part_w[t][se]; ts->len[t] = 0; }
+        sets_free.push(ts);
+      } else sets_full.push(ts);
     }
+    sets_full.close();
   });
 
   krepp_reader_t* reader = nullptr;
@@ -462,6 +481,7 @@ int main(int argc, char** argv)
   krepp_reader_close(reader);
   busy_q.close();
   consumer.join();
+  writer.join();
 
   { // --summarize table / end_jplace
     size_t n = krepp_format_footer(index[0], &p, o.tabular, wcount.data(), total_queries, invocation.c_str(), text.data(), text.size());
