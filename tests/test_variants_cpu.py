@@ -59,3 +59,29 @@ def test_treeless_index_dist_equals_reference(tmp_path_factory):
         assert ix.node_name(se) == o.name(se), se
     place = subprocess.run([os.path.join(REF_DIR, "krepp"), "place", "-i", idx, "-q", fq], capture_output=True, text=True)
     assert place.returncode != 0 and "lacks a tree" in place.stderr   # what krepp_batch_create answers for place on this handle
+
+
+def test_partial_library_directory_oracle_pinned_loader_refuses(tmp_path_factory):
+    """A directory holding several partial libraries (three `krepp index --no-frac` runs with r = 0, 2, 3 of m = 4 into one
+    -o directory; every partial has its own table, colour record and rho).  The oracle restates the per-residue dispatch
+    (ref src/index.cpp:144-168) and is pinned here against the reference's `dist`; the GPU path does not model this form yet
+     and must say so instead of loading one of the partials."""
+    import shutil
+    import krepp_b200
+    from krepp_b200.capi import KreppError
+    work = os.path.join(str(tmp_path_factory.getbasetemp()), "partials")
+    os.makedirs(work, exist_ok=True)
+    for item in ("genomes", "input_map.tsv", "tree.nwk"):
+        src, dst = os.path.join(SMALL, item), os.path.join(work, item)
+        if not os.path.exists(dst):
+            (shutil.copytree if os.path.isdir(src) else shutil.copy)(src, dst)
+    for r in ("0", "2", "3"):
+        subprocess.run([os.path.join(REF_DIR, "krepp"), "index", "-k", "21", "-w", "25", "-h", "7", "-m", "4", "-r", r, "--no-frac", "-o", "index",
+                        "-i", "input_map.tsv", "-t", "tree.nwk"], cwd=work, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    idx, fq = os.path.join(work, "index"), os.path.join(SMALL, "reads.fq")
+    ref = subprocess.run([os.path.join(REF_DIR, "krepp"), "dist", "-i", idx, "-q", fq], capture_output=True, text=True, check=True).stdout.splitlines()[2:]
+    ora = subprocess.run([os.path.join(os.path.dirname(REF_DIR), "_build", "krepp_oracle"), "dist", idx, fq], capture_output=True, text=True,
+                         check=True).stdout.splitlines()[1:]
+    assert len(ref) > 1000 and sorted(ref) == sorted(ora)
+    with pytest.raises(KreppError, match="several partial libraries"):
+        krepp_b200.Index(idx, device=-1)
