@@ -1,0 +1,56 @@
+"""CPU: the command line's argument handling (everything that is decided before a GPU is touched) against the reference's own
+CLI11 front end (ref src/krepp.cpp:593-716): same required options, same ranges, same validation messages, non-zero exit."""
+import os
+import subprocess
+
+import pytest
+
+from conftest import GOLDEN_DIR, REF_DIR, ROOT, needs_ref
+
+CLI = os.path.join(ROOT, "krepp_b200", "_build", "krepp_b200")
+S = os.path.join(GOLDEN_DIR, "small")
+IDX, FQ = os.path.join(S, "index"), os.path.join(S, "reads.fq")
+
+CASES = [
+    ([], "A subcommand is required"),
+    (["dist"], "--query is required"),
+    (["dist", "-q", FQ], "--index-dir is required"),
+    (["dist", "-q", "nope.fq", "-i", IDX], "File does not exist: nope.fq"),
+    (["dist", "-q", FQ, "-i", "nope_dir"], "Directory does not exist: nope_dir"),
+    (["place", "-i", IDX, "-q", FQ, "--tau", "9"], "The threshold tau must be less than HD threshold --hdist-th!"),
+    (["dist", "-i", IDX, "-q", FQ, "--dist-max", "0.9"], "not in range [1e-08 - 0.33]"),
+    (["dist", "-i", IDX, "-q", FQ, "--bogus"], "The following argument was not expected: --bogus"),
+]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    import krepp_b200
+    krepp_b200.build_library()
+
+
+@pytest.mark.parametrize("args,msg", CASES, ids=[" ".join(a[:2]) + f" #{i}" for i, (a, _) in enumerate(CASES)])
+def test_argument_errors(args, msg):
+    r = subprocess.run([CLI, *args], capture_output=True, text=True, timeout=60)
+    assert r.returncode != 0 and msg in r.stderr, r.stderr
+    if os.path.exists(os.path.join(REF_DIR, "krepp")):  # the reference says the same thing
+        q = subprocess.run([os.path.join(REF_DIR, "krepp"), *args], capture_output=True, text=True, timeout=60)
+        assert q.returncode != 0 and msg in (q.stderr + q.stdout), q.stderr
+
+
+def test_subcommands_outside_the_query_path_are_refused_by_name():
+    for sub in ("index", "sketch", "seek", "inspect"):
+        r = subprocess.run([CLI, sub, "-i", "x"], capture_output=True, text=True, timeout=60)
+        assert r.returncode != 0 and f"Subcommand '{sub}' is not part of the GPU query path" in r.stderr
+    r = subprocess.run([CLI, "place", "-i", IDX, "-q", FQ, "-t", os.path.join(S, "tree.nwk")], capture_output=True, text=True, timeout=60)
+    assert r.returncode != 0 and "not supported by the GPU path yet" in r.stderr
+    r = subprocess.run([CLI, "--help"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "--shard-index" in r.stdout and "--num-gpus" in r.stdout
+
+
+def test_no_gpu_means_an_error_not_a_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = subprocess.run([CLI, "dist", "-i", IDX, "-q", FQ], capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr and r.stdout.strip() == ""
