@@ -1,5 +1,6 @@
-// api.cu -- the C ABI declared in include/krepp_b200.h: index image upload, batch slots (one CUDA stream each),
-// submit / wait, parity taps.  No CPU fallback exists: every compute entry point needs a CUDA device.
+// api.cu -- the C ABI declared in include/krepp_b200.h: index image upload (whole, or one bucket-range shard), batch slots
+// (one CUDA stream each), submit / wait with selectable result rows, the three phases of a batch on a sharded index,
+// parity taps.  No CPU fallback exists: every compute entry point needs a CUDA device.
 #include "../../include/krepp_b200.h"
 
 #include "device.cuh"

@@ -1,5 +1,6 @@
-// solve.cu -- K4 of the query path: maximum-likelihood distance per (read, strand, leaf) record, then the per-read
-// strand merge / closest selection and the likelihood-ratio statistic.
+// solve.cu -- K4 of the query path: maximum-likelihood distance per (read, strand, leaf) record (identical problems of a
+// batch solved once: the solve memo of gate_kernel / alias_kernel), then the per-read strand merge / closest selection and
+// the likelihood-ratio statistic; and K5, placement, as a chain of four kernels (further down).
 //
 // THIS FILE IS COMPILED WITH --fmad=false: the reference runs on x86-64 without FMA contraction, and Brent's
 // parabolic-vs-golden decisions (tolerance only 2^-15) must follow the same iteration

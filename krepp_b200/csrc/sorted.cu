@@ -13,20 +13,22 @@
 //                               (ref src/common.hpp:175, src/query.cpp:361-368); hit entries {read, lookup, colour, hd}
 //                               are queued per warp and appended to a batch-wide list
 //   S2  scan + hit_scatter      hit entries grouped by read (counting sort by read), colour id -> its flattened leaf list
-//   R   resolve_kernel          warp per read: hit entries -> (strand, leaf, lookup, hd) keys -> bitonic sort in shared
-//                               memory -> per (strand, leaf): one count per lookup at its minimum distance
+//   R   resolve_kernel          warp per read: hit entries -> (strand, leaf, lookup, hd) keys -> bitonic sort (in registers
+//                               with shuffles up to 256 keys, in shared memory up to 1,024, in HBM scratch beyond) ->
+//                               per (strand, leaf): one count per lookup at its minimum distance
 //                               (Minfo::update_match, ref src/query.hpp:153-176), per-strand hdist_filt and its gate
 //                               (ref src/query.cpp:101-106,116-119), records in (strand, leaf) order
 //
 // Everything is integer work and bit-exact with the fused kernel (same records in the same order).  Batches or reads
 // that do not fit this pipeline's buffers raise a flag; the host then grows the buffer or redoes the batch with the
-// fused kernel (api.cu).
+// fused kernel (api.cu).  For an index split by bucket range over several GPUs (SURVEY.md 8e mode B) the same chain is cut
+// after L2 and after J, where lookups and hit entries change owner (launch_shard_lookup / _join / _finish at the end).
 #include "device.cuh"
+#include "match_common.cuh"
+#include "solve.cuh"
 
 #include <algorithm>
 #include <cstdlib>
-#include "match_common.cuh"
-#include "solve.cuh"
 
 namespace krepp {
 
