@@ -57,6 +57,11 @@ typedef struct {
 int krepp_index_open(const char* index_dir, int device, krepp_index_t** out);
 void krepp_index_close(krepp_index_t* ix);
 int krepp_index_info(const krepp_index_t* ix, krepp_index_info_t* out);
+/* Wrapping 64-bit sums over the arrays of the host image this handle holds, for checking a loader (or a shard's slice) without
+ * a device: out[0] = sum of the cmer words (enc | se << 32), out[1] = sum of the bucket ends (relative to the shard's first
+ * entry), out[2] = sum over colour ids c of c * (number of leaves c expands to), out[3] = sum over colour ids c and their
+ * leaves l (leaf ranks, ascending) of (c + 1) * (l + 1). */
+int krepp_index_host_checksums(const krepp_index_t* ix, uint64_t out[4]);
 /* Node::get_name(return_na) (src/phytree.hpp:133-144): label, else to_string(se-1) or "NA".  Pointer valid until the
  * next call from the same thread. */
 const char* krepp_index_node_name(const krepp_index_t* ix, uint32_t se, int return_na);

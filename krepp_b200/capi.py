@@ -107,6 +107,7 @@ def load_library():
     L.krepp_index_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
     L.krepp_index_close.argtypes = [C.c_void_p]
     L.krepp_index_info.argtypes = [C.c_void_p, C.POINTER(IndexInfo)]
+    L.krepp_index_host_checksums.argtypes = [C.c_void_p, C.c_void_p]
     L.krepp_index_node_name.restype = C.c_char_p
     L.krepp_index_node_name.argtypes = [C.c_void_p, C.c_uint32, C.c_int]
     L.krepp_index_tree.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -178,6 +179,12 @@ class Index:
             self._h = None
 
     __del__ = close
+
+    def host_checksums(self) -> list:
+        """krepp_index_host_checksums: [sum cmer words, sum bucket ends, sum c * |leaves(c)|, sum (c+1)(leaf rank+1)] mod 2^64."""
+        out = np.zeros(4, np.uint64)
+        _check(load_library().krepp_index_host_checksums(self._h, out.ctypes.data))
+        return [int(x) for x in out]
 
     def node_name(self, se: int, return_na: bool = False) -> str:
         return load_library().krepp_index_node_name(self._h, se, int(return_na)).decode()

@@ -308,6 +308,21 @@ int krepp_index_info(const krepp_index_t* ix, krepp_index_info_t* o)
   return KREPP_OK;
 }
 
+int krepp_index_host_checksums(const krepp_index_t* ix, uint64_t out[4])
+{
+  if (!ix || !out) return fail(KREPP_ERR_ARG, "krepp_index_host_checksums: null argument");
+  const HostIndex& h = ix->host;
+  uint64_t a = 0, b = 0, c = 0, d = 0;
+  for (uint64_t e : h.cmer) a += e;
+  for (uint32_t v : h.inc32) b += v;
+  for (size_t col = 0; col + 1 < h.cbeg.size(); ++col) {
+    c += (uint64_t)col * (h.cbeg[col + 1] - h.cbeg[col]);
+    for (uint32_t i = h.cbeg[col]; i < h.cbeg[col + 1]; ++i) d += (uint64_t)(col + 1) * ((uint64_t)h.cleaf[i] + 1);
+  }
+  out[0] = a; out[1] = b; out[2] = c; out[3] = d;
+  return KREPP_OK;
+}
+
 const char* krepp_index_node_name(const krepp_index_t* ix, uint32_t se, int return_na)
 {
   if (!ix) return "";

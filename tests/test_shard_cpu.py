@@ -136,3 +136,67 @@ def test_two_rank_gloo_bucket_range_exchange():
         p.join(timeout=120)
         assert p.exitcode == 0
     assert tot[0] == 236 and tot[1] > 10_000 and tot[2] > 1_000
+
+
+def _expected_checksums(d, row0=None, row1=None):
+    """The sums krepp_index_host_checksums defines, from the index files alone (numpy + a plain restatement of the colour
+    walk of ref src/query.cpp:369-387: a colour id is a tree leaf, or expands through crecord's pairs; null nodes drop out,
+    a leaf reached twice counts once)."""
+    import struct
+    import krepp_b200
+    sfx = [f[8:] for f in os.listdir(d) if f.startswith("metadata-") and "." not in f][0]
+    cm = np.fromfile(os.path.join(d, "cmer" + sfx), dtype=np.uint64, offset=8)
+    inc = np.fromfile(os.path.join(d, "inc" + sfx), dtype=np.uint64, offset=4)
+    row0, row1 = (0, len(inc)) if row0 is None else (row0, row1)
+    e0 = int(inc[row0 - 1]) if row0 else 0
+    e1 = int(inc[row1 - 1]) if row1 else 0
+    M = (1 << 64) - 1
+    a = int(cm[e0:e1].sum(dtype=np.uint64))
+    b = int((inc[row0:row1] - np.uint64(e0)).sum(dtype=np.uint64))
+    raw = open(os.path.join(d, "crecord" + sfx), "rb").read()
+    nn, ns = struct.unpack("<II", raw[:8])
+    pse = np.frombuffer(raw[8:8 + 8 * ns], dtype="<u4").reshape(ns, 2)
+    ix = krepp_b200.Index(d, device=-1)
+    leaf = ix.tree()["is_leaf"]
+    rank, r = {}, 0
+    for se in range(1, nn):
+        if leaf[se]:
+            rank[se] = r
+            r += 1
+    memo = {}
+
+    def leaves(c):
+        if c in memo:
+            return memo[c]
+        if c == 0:
+            out = frozenset()
+        elif c < nn:
+            out = frozenset([rank[c]]) if leaf[c] else leaves(int(pse[c][0])) | leaves(int(pse[c][1]))
+        else:
+            out = leaves(int(pse[c][0])) | leaves(int(pse[c][1]))
+        memo[c] = out
+        return out
+
+    c_sum = d_sum = 0
+    for c in range(ns):
+        ls = leaves(c)
+        c_sum = (c_sum + c * len(ls)) & M
+        d_sum = (d_sum + (c + 1) * sum(l + 1 for l in ls)) & M
+    return [a & M, b & M, c_sum, d_sum]
+
+
+def test_host_image_checksums_whole_and_shards():
+    """What the loader holds in memory -- the k-mer table (or a shard's slice of it), the rebased bucket ends and the flattened
+    colour lists -- against the index files, without a device."""
+    import sys
+    import krepp_b200
+    sys.setrecursionlimit(10000)
+    from conftest import TOY_DIR, have_ref
+    dirs = [SMALL] + ([os.path.join(TOY_DIR, "index_toy")] if have_ref() else [])   # 0.5 MB, and the 72 MB toy index
+    for d in dirs:
+        whole = krepp_b200.Index(d, device=-1)
+        assert whole.host_checksums() == _expected_checksums(d), d
+        for nshards in (2, 5):
+            for g in range(nshards):
+                ix = krepp_b200.Index(d, device=-1, shard=g, nshards=nshards)
+                assert ix.host_checksums() == _expected_checksums(d, int(ix.shard.row0), int(ix.shard.row1)), (d, nshards, g)
