@@ -42,8 +42,8 @@ int fail(int code, const char* fmt, ...)
     if (e__ != cudaSuccess) return fail(KREPP_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__));      \
   } while (0)
 
-template <class T>
-cudaError_t upload(const std::vector<T>& v, const T** out, std::vector<void*>& allocs, uint64_t& bytes, size_t pad = 0)
+template <class T, class A>
+cudaError_t upload(const std::vector<T, A>& v, const T** out, std::vector<void*>& allocs, uint64_t& bytes, size_t pad = 0)
 {
   void* p = nullptr;
   const size_t n = (v.size() + pad) * sizeof(T);

@@ -9,10 +9,29 @@
 //   tree-*      Newick text                                                 (ref src/phytree.cpp:394-404)
 #pragma once
 #include <cstdint>
+#include <new>
 #include <string>
 #include <vector>
 
 namespace krepp {
+
+// Allocator whose resize() leaves trivially constructible elements uninitialised: the k-mer table is gigabytes that are
+// overwritten from the file right away, and zero-filling them first costs as much as reading them.
+template <class T>
+struct NoInitAlloc {
+  using value_type = T;
+  NoInitAlloc() = default;
+  template <class U> NoInitAlloc(const NoInitAlloc<U>&) {}
+  T* allocate(size_t n) { return static_cast<T*>(::operator new(n * sizeof(T))); }
+  void deallocate(T* p, size_t) { ::operator delete(p); }
+  template <class U, class... A> void construct(U* p, A&&... a)
+  {
+    if constexpr (sizeof...(A) == 0) ::new (static_cast<void*>(p)) U;
+    else ::new (static_cast<void*>(p)) U(static_cast<A&&>(a)...);
+  }
+  template <class U> bool operator==(const NoInitAlloc<U>&) const { return true; }
+  template <class U> bool operator!=(const NoInitAlloc<U>&) const { return false; }
+};
 
 struct BitRun { uint8_t src, width, dst; }; // ((x >> src) & ((1<<width)-1)) << dst
 
@@ -41,7 +60,7 @@ struct HostIndex {
   uint64_t mask_hash_bp = 0, mask_drop_lr = 0, mask_drop_bp = 0;
   std::vector<BitRun> hash_runs, drop_runs;   // pext plans over the 2-bit (bp) k-mer word
   std::vector<int32_t> res_numer;             // [m]: 0 = residue absent, else numerator (ref src/index.cpp:144-157)
-  std::vector<uint64_t> cmer;                 // nkmers x (enc | se<<32)
+  std::vector<uint64_t, NoInitAlloc<uint64_t>> cmer; // nkmers x (enc | se<<32)
   std::vector<uint64_t> inc;                  // nrows
   std::vector<uint32_t> inc32;                // nrows, present when nkmers < 2^32 (what the device scans with)
   uint32_t cr_nnodes = 0, nsubsets = 0;
