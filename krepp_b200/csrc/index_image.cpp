@@ -440,27 +440,52 @@ std::string HostIndex::load(const std::string& dir, uint32_t shard_id, uint32_t 
     uint64_t total = 0;
     for (uint32_t c : leaves) total += c;
     if (total <= kMaxFlatLeaves && tree.nleaves) {
+      // Every colour gets room for its list WITH duplicates (leaves[], an upper bound), so the lists of one DAG level -- whose
+      // children all sit on lower levels and are finished -- can be built independently, by several threads; the lists are then
+      // packed in colour-id order.
       std::vector<uint64_t> start(nsubsets + 1, 0);
-      std::vector<uint32_t> flat;
-      flat.reserve(total);
+      for (uint32_t se = 0; se < nsubsets; ++se) start[se + 1] = start[se] + leaves[se];
+      std::vector<uint32_t, NoInitAlloc<uint32_t>> flat;
+      flat.resize(total);
       std::vector<uint32_t> len(nsubsets, 0);
-      for (uint32_t se : order) {
-        start[se] = flat.size();
-        if (kind[se] == 1) { flat.push_back(tree.leaf_rank[se]); len[se] = 1; }
-        else if (kind[se] == 2) {
-          const uint32_t a = (uint32_t)pse[se], b = (uint32_t)(pse[se] >> 32);
-          const size_t at = flat.size();
-          flat.resize(at + len[a] + len[b]);
-          std::merge(flat.begin() + start[a], flat.begin() + start[a] + len[a], flat.begin() + start[b], flat.begin() + start[b] + len[b], flat.begin() + at);
-          const auto e = std::unique(flat.begin() + at, flat.end());
-          flat.resize(e - flat.begin());
-          len[se] = (uint32_t)(flat.size() - at);
+      std::vector<uint32_t> level_begin(max_expand_depth + 2, 0), bylevel(nsubsets);
+      for (uint32_t se = 0; se < nsubsets; ++se) ++level_begin[depth[se] + 1];
+      for (uint32_t d = 0; d <= max_expand_depth; ++d) level_begin[d + 1] += level_begin[d];
+      { std::vector<uint32_t> cur(level_begin.begin(), level_begin.end() - 1); for (uint32_t se = 0; se < nsubsets; ++se) bylevel[cur[depth[se]]++] = se; }
+      auto build = [&](uint32_t lo, uint32_t hi) {
+        for (uint32_t i = lo; i < hi; ++i) {
+          const uint32_t se = bylevel[i];
+          uint32_t* out = flat.data() + start[se];
+          if (kind[se] == 1) { out[0] = tree.leaf_rank[se]; len[se] = 1; }
+          else if (kind[se] == 2) { // sorted union of the two children's lists
+            const uint32_t ca = (uint32_t)pse[se], cb = (uint32_t)(pse[se] >> 32);
+            const uint32_t *pa = flat.data() + start[ca], *ea = pa + len[ca], *pb = flat.data() + start[cb], *eb = pb + len[cb];
+            uint32_t n = 0;
+            while (pa < ea && pb < eb) {
+              const uint32_t x = *pa, y = *pb;
+              out[n++] = x < y ? x : y;
+              pa += x <= y; pb += y <= x;
+            }
+            while (pa < ea) out[n++] = *pa++;
+            while (pb < eb) out[n++] = *pb++;
+            len[se] = n;
+          }
         }
-      }
+      };
+      auto in_parallel = [&](uint32_t lo, uint32_t hi, auto&& fn) {
+        const uint32_t n = hi - lo, nth = n < (1u << 14) ? 1u : 8u;
+        std::vector<std::thread> th;
+        for (uint32_t t = 1; t < nth; ++t) th.emplace_back(fn, lo + (uint64_t)n * t / nth, lo + (uint64_t)n * (t + 1) / nth);
+        fn(lo, lo + (uint64_t)n / nth);
+        for (auto& x : th) x.join();
+      };
+      for (uint32_t d = 0; d <= max_expand_depth; ++d) in_parallel(level_begin[d], level_begin[d + 1], build);
       cbeg.assign(nsubsets + 1, 0);
       for (uint32_t se = 0; se < nsubsets; ++se) cbeg[se + 1] = cbeg[se] + len[se];
       cleaf.resize(cbeg[nsubsets]);
-      for (uint32_t se = 0; se < nsubsets; ++se) std::copy(flat.begin() + start[se], flat.begin() + start[se] + len[se], cleaf.begin() + cbeg[se]);
+      in_parallel(0, nsubsets, [&](uint32_t lo, uint32_t hi) {
+        for (uint32_t se = lo; se < hi; ++se) std::copy(flat.data() + start[se], flat.data() + start[se] + len[se], cleaf.begin() + cbeg[se]);
+      });
     }
   }
   return "";
