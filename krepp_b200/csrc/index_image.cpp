@@ -402,7 +402,16 @@ std::string HostIndex::load(const std::string& dir, uint32_t shard_id, uint32_t 
   kind.assign(nsubsets, 2);
   kind[0] = 0;
   for (uint32_t se = 1; se <= tree.nnodes; ++se) kind[se] = tree.is_leaf[se] ? 1 : 2;
-  for (uint64_t e : cmer) if ((uint32_t)(e >> 32) >= nsubsets) return "Failed to read the k-mer vector of a partial index!";
+  { // every entry's colour id must exist (several threads: the table is most of the index)
+    const size_t n = cmer.size(), nth = n < (1u << 22) ? 1 : 8;
+    std::vector<char> bad(nth, 0);
+    std::vector<std::thread> th;
+    auto scan = [&](size_t t) { for (size_t i = n * t / nth, e = n * (t + 1) / nth; i < e; ++i) if ((uint32_t)(cmer[i] >> 32) >= nsubsets) { bad[t] = 1; return; } };
+    for (size_t t = 1; t < nth; ++t) th.emplace_back(scan, t);
+    scan(0);
+    for (auto& x : th) x.join();
+    for (char b : bad) if (b) return "Failed to read the k-mer vector of a partial index!";
+  }
   // expansion depth / leaf count per colour (iterative post-order over the DAG; also rejects cycles)
   {
     std::vector<uint32_t> depth(nsubsets, 0), leaves(nsubsets, 0);
