@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define KREPP_ABI_VERSION 1
+#define KREPP_ABI_VERSION 2
 #define KREPP_MAX_TH 16 /* k-h <= 16 positions survive in the 32-bit residual encoding (src/lshf.cpp:39-54) */
 
 enum {
@@ -133,11 +133,21 @@ typedef struct {
 #define KREPP_BRIEF_FLAGS(ref) (((ref) >> 28) & 7u)
 #define KREPP_BRIEF_CHISQ_OK(ref) ((ref) >> 31)
 
+/* The rows `krepp dist` prints, chosen, ordered and rounded on the device (KREPP_OUT_DIST): everything report_distances
+ * (src/query.cpp:158-196) decides -- the NA rule, --no-multi, --filter / --chisq, --dist-max, --summarize's kept set -- is applied
+ * by a kernel, and what leaves the GPU per read is one word of dist_begin plus its rows, references by ascending se, the distance
+ * as the integer its five printed decimals show (round-to-nearest of the exact binary value, ties to even, as the reference's
+ * std::fixed << setprecision(5)).  Read i owns rows [KREPP_DIST_BEGIN(dist_begin[i]), KREPP_DIST_BEGIN(dist_begin[i + 1]));
+ * KREPP_DIST_NA(dist_begin[i]) says the read prints "NA\tNaN" instead (no match, or closest beyond --dist-max).  A row is 4 bytes
+ * (leaf rank << 16 | distance units; indexes of at most 65,536 references) or 8 bytes (leaf se | (uint64) units << 32). */
+#define KREPP_DIST_BEGIN(w) ((w) & 0x7FFFFFFFu)
+#define KREPP_DIST_NA(w) ((w) >> 31)
+
 typedef struct {
   uint32_t n_reads;
   uint32_t hist_stride;               /* hdist_th + 1 */
   uint64_t n_records, n_placements;
-  const krepp_read_summary_t* reads;  /* [n_reads] */
+  const krepp_read_summary_t* reads;  /* [n_reads]; NULL when KREPP_OUT_SUMMARIES was not asked for */
   const krepp_record_t* records;      /* [n_records] */
   const uint32_t* hist;               /* [n_records * hist_stride]: Minfo::hdisthist_v */
   const krepp_placement_t* placements;/* [n_placements] */
@@ -145,6 +155,10 @@ typedef struct {
   float match_ms;                     /* device time of the match kernel alone (same stream, CUDA events) */
   uint32_t gpu_launches;              /* kernels launched for this batch */
   const krepp_brief_t* brief;         /* [n_records] when KREPP_OUT_BRIEF was asked for, else NULL */
+  const uint32_t* dist_begin;         /* [n_reads + 1] when KREPP_OUT_DIST was asked for, else NULL */
+  const void* dist_rows;              /* [n_dist_rows] rows of dist_row_bytes bytes */
+  uint64_t n_dist_rows;
+  uint32_t dist_row_bytes;            /* 4 or 8 */
 } krepp_results_t;
 
 /* -------------------------------------------------------------------------------------------------- batches */
@@ -182,15 +196,20 @@ int krepp_batch_wait(krepp_batch_t* b, krepp_results_t* out);
 #define KREPP_OUT_RECORDS 1u
 #define KREPP_OUT_HIST 2u
 #define KREPP_OUT_PLACEMENTS 4u
-#define KREPP_OUT_ALL 7u
 #define KREPP_OUT_BRIEF 8u /* krepp_brief_t rows (16 bytes per record instead of 56 + histogram); not part of KREPP_OUT_ALL.
                               krepp_format_dist reads them when `records` is NULL. */
+#define KREPP_OUT_DIST 16u /* the printed rows of `krepp dist` (see krepp_results_t): 4 bytes per read + 4 or 8 per printed row.
+                              Not part of KREPP_OUT_ALL; krepp_format_dist prefers them when present. */
+#define KREPP_OUT_SUMMARIES 32u /* the 40-byte krepp_read_summary_t rows; a front end that asks for KREPP_OUT_DIST alone does without */
+#define KREPP_OUT_ALL 39u
+/* Must be called while no batch is pending on the slot (before krepp_batch_submit, or after the krepp_batch_wait that follows
+ * it): the kernels that assemble the rows run as part of the submit.  KREPP_ERR_ARG otherwise. */
 int krepp_batch_set_output(krepp_batch_t* b, uint32_t rows);
 
 /* The same wait (including the grow-and-rerun of a batch whose result buffers were too small) without copying the record,
  * histogram and placement rows to the host: `reads` (40 bytes per read) and the counts are valid, the three row pointers
  * are NULL and the rows stay in HBM.  For callers that only need the per-read summaries, and for timing the kernels
- * without the PCIe transfer of the rows. */
+ * without the PCIe transfer of the rows.  (The summaries are copied here even if KREPP_OUT_SUMMARIES was not asked for.) */
 int krepp_batch_wait_device(krepp_batch_t* b, krepp_results_t* out);
 
 /* Parity taps (SURVEY.md section 8b "dump_stage").  stage 1: every eligible lookup of the last submitted batch as
@@ -246,6 +265,13 @@ typedef struct {
  * colour record, tree and hash tables are replicated.  Shards are contiguous row ranges of (nearly) equal cmer bytes,
  * derived from inc-* alone, so every rank computes the same split.  nshards = 1 is krepp_index_open. */
 int krepp_index_open_shard(const char* index_dir, int device, uint32_t shard, uint32_t nshards, krepp_index_t** out);
+/* How many bucket-range shards an index needs so that every shard's device image (its slice of the table plus the replicated
+ * colour record, colour lists, tree and hash tables) stays within `budget_bytes` per GPU: 1 = it can be replicated (mode A).
+ * budget_bytes = 0 means "what is free on `device` now, less 25 % for the batch slots".  Reads everything but the table itself.
+ * whole_bytes / shard_bytes (may be NULL): image size unsharded, and of the largest shard at *nshards.  KREPP_ERR_CAPACITY when
+ * even KREPP_MAX_SHARDS shards do not fit. */
+int krepp_index_plan_shards(const char* index_dir, int device, uint64_t budget_bytes, uint32_t* nshards, uint64_t* whole_bytes,
+                            uint64_t* shard_bytes);
 /* row_splits (may be NULL): first row of every shard, nshards + 1 values (at most cap are written). */
 int krepp_index_shard_info(const krepp_index_t* ix, krepp_shard_info_t* out, uint32_t* row_splits, uint32_t cap);
 

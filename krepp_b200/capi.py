@@ -59,7 +59,8 @@ class ShardInfo(C.Structure):
 class Results(C.Structure):
     _fields_ = [("n_reads", C.c_uint32), ("hist_stride", C.c_uint32), ("n_records", C.c_uint64), ("n_placements", C.c_uint64),
                 ("reads", C.c_void_p), ("records", C.c_void_p), ("hist", C.c_void_p), ("placements", C.c_void_p),
-                ("gpu_ms", C.c_float), ("match_ms", C.c_float), ("gpu_launches", C.c_uint32), ("brief", C.c_void_p)]
+                ("gpu_ms", C.c_float), ("match_ms", C.c_float), ("gpu_launches", C.c_uint32), ("brief", C.c_void_p),
+                ("dist_begin", C.c_void_p), ("dist_rows", C.c_void_p), ("n_dist_rows", C.c_uint64), ("dist_row_bytes", C.c_uint32)]
 
 
 RECORD_DTYPE = np.dtype([("read", "<u4"), ("leaf_se", "<u4"), ("strand", "<u4"), ("match_count", "<u4"), ("hdist_min", "<u4"),
@@ -80,6 +81,40 @@ def brief_from_records(records: np.ndarray, chisq_value: float) -> np.ndarray:
         ok = (records["chisq"] < chisq_value).astype(np.uint32)
     out["ref"] = records["leaf_se"] | records["strand"] << 27 | (records["flags"] & 7) << 28 | ok << 31
     return out
+
+
+def dist_rows_from_records(index: "Index", params: "Params", reads: np.ndarray, records: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+    """The KREPP_OUT_DIST form (dist_begin, dist_rows) derived on the host from full results: a restatement of
+    report_distances' decisions (ref src/query.cpp:158-196) used to check what the device writes."""
+    is_leaf = index.tree()["is_leaf"]
+    rank = np.cumsum(is_leaf) - 1
+    wide = index.info.nleaves > 65536
+    has_max = not math.isnan(params.dist_max)
+    begin = np.zeros(len(reads) + 1, np.uint32)
+    rows = []
+    for r, s in enumerate(reads):
+        first = len(rows)
+        b, n, cl = int(s["rec_begin"]), int(s["rec_count"]), int(s["closest"])
+        rr = records[b:b + n]
+        na = False
+        picked = []
+        if not params.summarize and (cl < 0 or (has_max and records[cl]["d_llh"] > params.dist_max)):
+            na = True
+        elif not params.summarize and not params.multi:
+            picked = [records[cl]]
+        else:
+            for x in sorted((x for x in rr if x["flags"] & REC_SELECTED), key=lambda x: x["leaf_se"]):
+                keep = (not has_max) or x["d_llh"] < params.dist_max
+                if params.summarize or not params.no_filter:
+                    keep = keep and bool(x["chisq"] < params.chisq)
+                if keep:
+                    picked.append(x)
+        for x in picked:
+            units = int(("%.5f" % x["d_llh"]).replace(".", ""))
+            rows.append((int(x["leaf_se"]) | units << 32) if wide else (int(rank[x["leaf_se"]]) << 16 | units))
+        begin[r] = first | (0x80000000 if na else 0)
+    begin[len(reads)] = len(rows)
+    return begin, np.array(rows, dtype=np.uint64 if wide else np.uint32)
 
 
 def library_path() -> str:
@@ -128,6 +163,7 @@ def load_library():
     L.krepp_batch_stage_times.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_char_p), C.POINTER(C.c_uint32)]
     L.krepp_index_open_shard.argtypes = [C.c_char_p, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]
     L.krepp_index_shard_info.argtypes = [C.c_void_p, C.POINTER(ShardInfo), C.c_void_p, C.c_uint32]
+    L.krepp_index_plan_shards.argtypes = [C.c_char_p, C.c_int, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.krepp_shard_lookup.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
     L.krepp_shard_join.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
     L.krepp_shard_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
@@ -202,6 +238,13 @@ class Index:
         buf = C.create_string_buffer(n + 1)
         L.krepp_index_jplace_tree(self._h, buf, n + 1)
         return buf.value.decode()
+
+
+def plan_shards(index_dir: str, budget_bytes: int, device: int = 0) -> dict:
+    """krepp_index_plan_shards: bucket-range shards needed to keep every GPU's image within budget_bytes (0 = free memory of `device`)."""
+    n, whole, shard = C.c_uint32(), C.c_uint64(), C.c_uint64()
+    _check(load_library().krepp_index_plan_shards(os.fsencode(index_dir), device, budget_bytes, C.byref(n), C.byref(whole), C.byref(shard)))
+    return dict(nshards=n.value, whole_bytes=whole.value, shard_bytes=shard.value)
 
 
 def pack_reads(reads) -> tuple[np.ndarray, np.ndarray]:
@@ -310,12 +353,16 @@ class IBatch:
             reads=_view(r.reads, READ_DTYPE, r.n_reads), records=_view(r.records, RECORD_DTYPE, nrec),
             hist=_view(r.hist, np.dtype("<u4"), nrec * r.hist_stride).reshape(-1, r.hist_stride),
             placements=_view(r.placements, PLACEMENT_DTYPE, int(r.n_placements)), brief=_view(r.brief, BRIEF_DTYPE, nrec),
+            dist_begin=_view(r.dist_begin, np.dtype("<u4"), r.n_reads + 1 if r.dist_begin else 0),
+            dist_rows=_view(r.dist_rows, np.dtype("<u4" if r.dist_row_bytes == 4 else "<u8"), int(r.n_dist_rows) if r.dist_begin else 0),
             n_records=nrec, gpu_ms=float(r.gpu_ms), match_ms=float(r.match_ms), gpu_launches=int(r.gpu_launches))
         return self._res
 
-    def set_output(self, records: bool = True, hist: bool = True, placements: bool = True, brief: bool = False):
+    def set_output(self, records: bool = True, hist: bool = True, placements: bool = True, brief: bool = False, dist: bool = False,
+                   summaries: bool = True):
         """krepp_batch_set_output: which row arrays wait() copies to the host (the others come back empty)."""
-        _check(load_library().krepp_batch_set_output(self._h, int(records) | 2 * int(hist) | 4 * int(placements) | 8 * int(brief)))
+        _check(load_library().krepp_batch_set_output(self._h, int(records) | 2 * int(hist) | 4 * int(placements) | 8 * int(brief) | 16 * int(dist)
+                                                     | 32 * int(summaries)))
 
     def wait_device(self) -> dict:
         """krepp_batch_wait_device: per-read summaries and counts only; record / placement rows stay in HBM."""
@@ -456,10 +503,14 @@ def pack_names(names) -> tuple[np.ndarray, np.ndarray]:
     return np.frombuffer(blob + b"\0", dtype=np.uint8).copy(), offs
 
 
-def results_struct(reads: np.ndarray, records: np.ndarray | None, hist: np.ndarray, placements: np.ndarray | None = None,
-                   brief: np.ndarray | None = None) -> Results:
+def results_struct(reads: np.ndarray | None, records: np.ndarray | None, hist: np.ndarray | None, placements: np.ndarray | None = None,
+                   brief: np.ndarray | None = None, dist_begin: np.ndarray | None = None, dist_rows: np.ndarray | None = None) -> Results:
     """A krepp_results_t over caller-owned numpy arrays (kept alive by the caller)."""
     r = Results()
+    if dist_begin is not None:  # the device-selected `dist` rows only
+        r.n_reads, r.n_dist_rows, r.dist_row_bytes = len(dist_begin) - 1, len(dist_rows), dist_rows.dtype.itemsize
+        r.dist_begin, r.dist_rows = dist_begin.ctypes.data, dist_rows.ctypes.data
+        return r
     if records is None:  # brief rows only
         r.n_reads, r.hist_stride, r.n_records, r.n_placements = len(reads), 0, len(brief), 0
         r.reads, r.records, r.hist, r.placements, r.brief = reads.ctypes.data, None, None, None, brief.ctypes.data

@@ -6,6 +6,7 @@
 #include "device.cuh"
 #include "handles.hpp"
 #include "index_image.hpp"
+#include "fixed5.h"
 #include "solve.cuh"
 
 #include <algorithm>
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(128) finalize_kernel(const SolveArgs a, krepp_
     r.rho = a.rho[r.leaf_se]; r.d_llh = a.rec_d[i]; r.v_llh = a.rec_v[i]; r.chisq = a.rec_chisq[i];
     out_rec[i] = r;
   }
-  for (uint32_t i = tid; i < a.n_reads; i += nth) {
+  for (uint32_t i = tid; out_read && i < a.n_reads; i += nth) {
     krepp_read_summary_t s;
     s.onmers = a.onmers[i]; s.wn[0] = wn[2 * i]; s.wn[1] = wn[2 * i + 1];
     s.hdist_filt[0] = a.hdfilt[2 * i]; s.hdist_filt[1] = a.hdfilt[2 * i + 1];
@@ -122,6 +123,82 @@ __global__ void __launch_bounds__(128) finalize_kernel(const SolveArgs a, krepp_
     s.place_begin = place_begin ? place_begin[i] : 0; s.place_count = place_count ? place_count[i] : 0;
     s.closest = a.closest[i];
     out_read[i] = s;
+  }
+}
+
+
+// ---- KREPP_OUT_DIST: the rows `krepp dist` prints, chosen on the device (IBatch::report_distances, ref src/query.cpp:158-196)
+struct DistOut {
+  uint32_t n_reads;
+  const uint32_t *rec_begin, *rec_count, *rec_slot, *rec_flags;
+  const double *rec_d, *rec_chisq;
+  const int32_t* closest;
+  const uint32_t* leaf_rank;   // by se
+  const uint32_t* counters;
+  int summarize, multi, no_filter, has_max;
+  double dist_max, chisq_value;
+  uint32_t* cnt;               // [n_reads] printed rows per read
+  const uint32_t* begin;       // [n_reads + 1] exclusive prefix of cnt
+  uint32_t* out_begin;         // [n_reads + 1] begin | NA << 31
+  void* rows;
+  uint32_t row_bytes;
+};
+
+// Calls emit(record index) for every row of read r in print order (references by ascending se: the records are forward leaves
+// by ascending se, then reverse leaves by ascending se, and at most one strand of a leaf is selected); returns true when the
+// read prints "NA\tNaN" instead (ref src/query.cpp:173-176).
+template <class F>
+__device__ __forceinline__ bool dist_rows_of(const DistOut& a, uint32_t r, F&& emit)
+{
+  const uint32_t b = a.rec_begin[r], n = a.rec_count[r];
+  const int32_t cl = a.closest[r];
+  if (!a.summarize) {
+    if (cl < 0 || (a.has_max && a.rec_d[cl] > a.dist_max)) return true;
+    if (!a.multi) { emit((uint32_t)cl); return false; }       // ref :193-195
+  }
+  uint32_t nf = 0;
+  while (nf < n && !(a.rec_slot[b + nf] >> 31)) ++nf;
+  uint32_t i = b, j = b + nf;
+  const uint32_t ie = b + nf, je = b + n;
+  while (i < ie || j < je) {
+    const uint32_t si = i < ie ? (a.rec_slot[i] & 0x7FFFFFFFu) : 0xFFFFFFFFu, sj = j < je ? (a.rec_slot[j] & 0x7FFFFFFFu) : 0xFFFFFFFFu;
+    uint32_t pick;
+    if (si < sj) pick = i++;
+    else if (sj < si) pick = j++;
+    else { pick = (a.rec_flags[i] & KREPP_REC_SELECTED) ? i : j; ++i; ++j; }
+    if (!(a.rec_flags[pick] & KREPP_REC_SELECTED)) continue;
+    const bool dmax_ok = !a.has_max || a.rec_d[pick] < a.dist_max;
+    bool keep = dmax_ok;
+    if (a.summarize || !a.no_filter) keep = keep && (a.rec_chisq[pick] < a.chisq_value); // ref :164-166,186-188 (NaN never passes)
+    if (keep) emit(pick);
+  }
+  return false;
+}
+
+__global__ void __launch_bounds__(128) dist_count_kernel(const DistOut a)
+{
+  if (a.counters[2] & kErrRedo) return;
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < a.n_reads; r += gridDim.x * blockDim.x) {
+    uint32_t c = 0;
+    dist_rows_of(a, r, [&](uint32_t) { ++c; });
+    a.cnt[r] = c;
+  }
+}
+
+__global__ void __launch_bounds__(128) dist_emit_kernel(const DistOut a)
+{
+  if (a.counters[2] & kErrRedo) return;
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < a.n_reads; r += gridDim.x * blockDim.x) {
+    uint32_t at = a.begin[r];
+    const uint32_t first = at;
+    const bool na = dist_rows_of(a, r, [&](uint32_t i) {
+      const uint32_t se = a.rec_slot[i] & 0x7FFFFFFFu, units = fixed5_units(a.rec_d[i]);
+      if (a.row_bytes == 4) static_cast<uint32_t*>(a.rows)[at] = a.leaf_rank[se] << 16 | (units < 0xFFFFu ? units : 0xFFFFu);
+      else static_cast<uint2*>(a.rows)[at] = make_uint2(se, units);
+      ++at;
+    });
+    a.out_begin[r] = first | (na ? 0x80000000u : 0u);
+    if (r == a.n_reads - 1) a.out_begin[a.n_reads] = at;
   }
 }
 
@@ -142,13 +219,14 @@ int set_error(int code, const char* fmt, ...)
 
 struct krepp_batch {
   krepp_index* ix = nullptr;
+  int device = 0;                       // the index's device (kept here: krepp_batch_destroy must not touch the index handle)
   krepp_params_t p{};
   LlhTables tab{};
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm0 = nullptr, evm1 = nullptr;
   uint32_t max_reads = 0, rec_cap = 0, n_reads = 0, launches = 0;
   uint64_t max_bases = 0, n_bases = 0;
-  bool submitted = false, device_input = false, keep_all = false;
+  bool submitted = false, pending = false, device_input = false, keep_all = false; // pending: submitted and not yet waited for
   uint32_t out_rows = KREPP_OUT_ALL;    // which row arrays krepp_batch_wait copies to the host
   const char* in_bases = nullptr;       // device pointers used by the last submit
   const uint64_t* in_offsets = nullptr;
@@ -166,6 +244,11 @@ struct krepp_batch {
   uint32_t stack_cap = 0;
   krepp_record_t* d_out_rec = nullptr; krepp_read_summary_t* d_out_read = nullptr;
   krepp_brief_t *d_out_brief = nullptr, *h_brief = nullptr;
+  // KREPP_OUT_DIST: printed rows per read, their exclusive prefix, the rows (4 or 8 bytes each; at most one per record)
+  uint32_t *d_dist_cnt = nullptr, *d_dist_begin = nullptr, *d_dist_out_begin = nullptr, *d_dist_partials = nullptr, *h_dist_begin = nullptr;
+  void *d_dist_rows = nullptr, *h_dist_rows = nullptr;
+  uint32_t dist_row_bytes = 4;
+  bool summaries_copied = false;
   // pinned host results
   krepp_record_t* h_rec = nullptr; krepp_read_summary_t* h_read = nullptr; uint32_t* h_hist = nullptr;
   uint32_t* h_counters = nullptr; unsigned long long* h_stats = nullptr;
@@ -297,6 +380,27 @@ int krepp_index_shard_info(const krepp_index_t* ix, krepp_shard_info_t* o, uint3
   return KREPP_OK;
 }
 
+int krepp_index_plan_shards(const char* index_dir, int device, uint64_t budget_bytes, uint32_t* nshards, uint64_t* whole_bytes, uint64_t* shard_bytes)
+{
+  if (!index_dir || !nshards) return fail(KREPP_ERR_ARG, "krepp_index_plan_shards: null argument");
+  if (!budget_bytes) {
+    size_t fr = 0, tot = 0;
+    if (cudaSetDevice(device) != cudaSuccess || cudaMemGetInfo(&fr, &tot) != cudaSuccess) return fail(KREPP_ERR_CUDA, "no CUDA device %d to take the memory budget from", device);
+    budget_bytes = (uint64_t)fr / 4 * 3;
+  }
+  HostIndex h;
+  std::string err = h.load(index_dir, 0, 1, false);
+  if (!err.empty()) return fail(KREPP_ERR_IO, "%s", err.c_str());
+  const uint64_t repl = h.replicated_device_bytes();
+  if (whole_bytes) *whole_bytes = repl + h.shard_table_device_bytes(1);
+  for (uint32_t n = 1; n <= KREPP_MAX_SHARDS; ++n) {
+    const uint64_t b = repl + h.shard_table_device_bytes(n);
+    if (b <= budget_bytes) { *nshards = n; if (shard_bytes) *shard_bytes = b; return KREPP_OK; }
+  }
+  return fail(KREPP_ERR_CAPACITY, "the index does not fit %llu bytes per GPU even as %d bucket-range shards (%llu bytes are replicated on every shard)",
+              (unsigned long long)budget_bytes, KREPP_MAX_SHARDS, (unsigned long long)repl);
+}
+
 int krepp_index_info(const krepp_index_t* ix, krepp_index_info_t* o)
 {
   if (!ix || !o) return fail(KREPP_ERR_ARG, "krepp_index_info: null argument");
@@ -362,6 +466,9 @@ static void free_records(krepp_batch* b)
   if (b->d_out_brief) cudaFree(b->d_out_brief);
   if (b->h_brief) cudaFreeHost(b->h_brief);
   b->d_out_brief = nullptr; b->h_brief = nullptr;
+  if (b->d_dist_rows) cudaFree(b->d_dist_rows);
+  if (b->h_dist_rows) cudaFreeHost(b->h_dist_rows);
+  b->d_dist_rows = nullptr; b->h_dist_rows = nullptr;
   b->d_rec_read = b->d_rec_slot = b->d_rec_hist = b->d_rec_flags = b->d_rec_match = b->d_rec_hdmin = b->d_rec_work = b->d_rec_alias = nullptr;
   b->d_rec_d = b->d_rec_v = b->d_rec_chisq = nullptr; b->d_out_rec = nullptr; b->h_rec = nullptr; b->h_hist = nullptr;
 }
@@ -403,6 +510,7 @@ static int alloc_records(krepp_batch* b, uint32_t cap)
   CU(cudaMalloc(&b->d_rec_d, 8ull * cap)); CU(cudaMalloc(&b->d_rec_v, 8ull * cap)); CU(cudaMalloc(&b->d_rec_chisq, 8ull * cap));
   CU(cudaMalloc(&b->d_out_rec, sizeof(krepp_record_t) * (size_t)cap));
   if (b->out_rows & KREPP_OUT_BRIEF) CU(cudaMalloc(&b->d_out_brief, sizeof(krepp_brief_t) * (size_t)cap));
+  if (b->out_rows & KREPP_OUT_DIST) CU(cudaMalloc(&b->d_dist_rows, (size_t)b->dist_row_bytes * cap));
   (void)stride; // the page-locked host copies are sized when a wait first needs them (host_rows): page-locking is slow and most callers want one form only
   return KREPP_OK;
 }
@@ -426,6 +534,25 @@ static int alloc_hits(krepp_batch* b, uint64_t cap)
   return KREPP_OK;
 }
 
+// Sort scratch of the resolve kernel for reads whose leaf hits exceed shared memory: one region of `cap` 64-bit keys (a power of
+// two) per warp of its grid.  The default grid gets 8,192 keys per warp; a read that needs more makes the host grow the
+// regions to its demand, and once they are large the grid is cut down so that the scratch stays within ~2 GB (such reads --
+// contigs, or short reads on an index of many near-identical genomes -- are then resolved by fewer warps at a time).
+static int alloc_keys(krepp_batch* b, uint64_t need)
+{
+  uint64_t cap = 8192;
+  while (cap < need) cap <<= 1;
+  if (cap > (1ull << 28)) return fail(KREPP_ERR_CAPACITY, "a read has %llu leaf hits, more than the sort scratch of the bucket-sorted chain can hold", (unsigned long long)need);
+  const uint64_t per_cta = 8ull * cap * (uint64_t)sorted_resolve_warps_per_cta(), budget = 2ull << 30;
+  const uint64_t dflt = (uint64_t)sorted_resolve_warps(b->ix->sms) / (uint64_t)sorted_resolve_warps_per_cta();
+  const uint64_t ctas = std::max<uint64_t>(1, std::min<uint64_t>(dflt, budget / per_cta));
+  uint64_t* fresh = nullptr;
+  CU(cudaMalloc(&fresh, per_cta * ctas));
+  if (b->so.keys_g) cudaFree(b->so.keys_g);
+  b->so.keys_g = fresh; b->so.cap_keys_g = (uint32_t)cap; b->so.res_ctas = (uint32_t)ctas;
+  return KREPP_OK;
+}
+
 static int alloc_sorted(krepp_batch* b)
 {
   const HostIndex& h = b->ix->host;
@@ -438,14 +565,33 @@ static int alloc_sorted(krepp_batch* b)
   CU(cudaMalloc(&so.sc, 32));
   CU(cudaMallocHost(&b->h_sc, 4ull * (16 + 2 * (KREPP_MAX_SHARDS + 1))));
   if (const char* env = getenv("KREPP_SORT_WIDE")) so.extra_rank_bits = (uint32_t)std::min(24, std::max(0, atoi(env)));
-  so.cap_keys_g = 8192; // 64-bit keys per warp (a power of two): reads with more leaf hits send the batch to the fused kernel
-  CU(cudaMalloc(&so.keys_g, 8ull * so.cap_keys_g * (size_t)sorted_resolve_warps(b->ix->sms)));
+  if (int rc = alloc_keys(b, 8192)) return rc;
+  if (b->max_bases >= (1ull << 31)) return fail(KREPP_ERR_CAPACITY, "the bucket-sorted chain counts a batch's lookups in 32 bits: at most 2^31 - 1 bases per batch");
   // every base starts at most one window = two lookups, of which (r+1)/m are eligible on average; grown on demand
   uint32_t present = 0;
   for (uint32_t res = 0; res < h.m; ++res) present += h.res_numer[res] != 0;
   const uint64_t want = (uint64_t)((double)b->max_bases * 2.0 * present / (double)h.m * 1.1) + 4096;
   if (int rc = alloc_tuples(b, std::min<uint64_t>(want, 0xFFFFFFF0ull))) return rc;
   if (int rc = alloc_hits(b, std::min<uint64_t>(std::max<uint64_t>(96ull * b->max_reads, 65536), 0xFFFFFFF0ull))) return rc;
+  return KREPP_OK;
+}
+
+// Per-warp scratch of the fused match kernel (match.cu): Hamming-histogram accumulators of 2 * nleaves * (th + 1) words per
+// resident warp and friends -- gigabytes on an index of many thousand references.  A slot that runs the bucket-sorted chain
+// never touches it, and a bucket-range shard cannot run the fused kernel at all, so it is allocated by the first batch that
+// takes the fused path (a small-bucket index, KREPP_PIPELINE=fused, or the fallback for a read outside the chain's limits).
+static int fused_scratch(krepp_batch* b)
+{
+  if (b->d_acc) return KREPP_OK;
+  const HostIndex& h = b->ix->host;
+  const size_t warps = (size_t)b->ix->resident_warps, nslots = 2ull * h.tree.nleaves, stride = b->p.hdist_th + 1;
+  const size_t nbm = (nslots + 31) / 32;
+  b->stack_cap = 32 * (h.max_expand_depth + 2) + 64;
+  CU(cudaMalloc(&b->d_acc, 4 * warps * nslots * stride)); CU(cudaMemsetAsync(b->d_acc, 0, 4 * warps * nslots * stride, b->stream));
+  CU(cudaMalloc(&b->d_bitmap, 4 * warps * nbm)); CU(cudaMemsetAsync(b->d_bitmap, 0, 4 * warps * nbm, b->stream));
+  CU(cudaMalloc(&b->d_marker, 4 * warps * h.tree.nleaves)); CU(cudaMemsetAsync(b->d_marker, 0xFF, 4 * warps * h.tree.nleaves, b->stream));
+  CU(cudaMalloc(&b->d_stack, 4 * warps * b->stack_cap));
+  CU(cudaMalloc(&b->d_tagctr, 4 * warps)); CU(cudaMemsetAsync(b->d_tagctr, 0xFF, 4 * warps, b->stream));
   return KREPP_OK;
 }
 
@@ -460,8 +606,9 @@ int krepp_batch_create(krepp_index_t* ix, const krepp_params_t* p, uint32_t max_
   if (cudaSetDevice(ix->device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice(%d) failed", ix->device);
   auto* b = new krepp_batch;
   *out = b; // destroyed by the caller on failure
-  b->ix = ix; b->p = *p; b->max_reads = max_reads; b->max_bases = max_bases;
+  b->ix = ix; b->device = ix->device; b->p = *p; b->max_reads = max_reads; b->max_bases = max_bases;
   const HostIndex& h = ix->host;
+  b->dist_row_bytes = h.tree.nleaves <= 65536u ? 4u : 8u;
   llh_tables(b->tab, h.k, h.h, p->hdist_th); // HDistHistLLH tables (ref src/hdhistllh.hpp:51-69), exact integer arithmetic then converted
   CU(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
   CU(cudaEventCreate(&b->ev0)); CU(cudaEventCreate(&b->ev1)); CU(cudaEventCreate(&b->evm0)); CU(cudaEventCreate(&b->evm1));
@@ -474,15 +621,10 @@ int krepp_batch_create(krepp_index_t* ix, const krepp_params_t* p, uint32_t max_
   CU(cudaMallocHost(&b->h_counters, 32)); CU(cudaMallocHost(&b->h_stats, 32));
   CU(cudaMalloc(&b->d_out_read, sizeof(krepp_read_summary_t) * (size_t)max_reads));
   CU(cudaMallocHost(&b->h_read, sizeof(krepp_read_summary_t) * (size_t)max_reads));
-  // per-warp scratch
-  const size_t warps = (size_t)ix->resident_warps, nslots = 2ull * h.tree.nleaves, stride = p->hdist_th + 1;
-  const size_t nbm = (nslots + 31) / 32;
-  b->stack_cap = 32 * (h.max_expand_depth + 2) + 64;
-  CU(cudaMalloc(&b->d_acc, 4 * warps * nslots * stride)); CU(cudaMemset(b->d_acc, 0, 4 * warps * nslots * stride));
-  CU(cudaMalloc(&b->d_bitmap, 4 * warps * nbm)); CU(cudaMemset(b->d_bitmap, 0, 4 * warps * nbm));
-  CU(cudaMalloc(&b->d_marker, 4 * warps * h.tree.nleaves)); CU(cudaMemset(b->d_marker, 0xFF, 4 * warps * h.tree.nleaves));
-  CU(cudaMalloc(&b->d_stack, 4 * warps * b->stack_cap));
-  CU(cudaMalloc(&b->d_tagctr, 4 * warps)); CU(cudaMemset(b->d_tagctr, 0xFF, 4 * warps));
+  // (the fused kernel's per-warp scratch is allocated by the first batch that runs it: fused_scratch)
+  CU(cudaMalloc(&b->d_dist_cnt, 4ull * max_reads)); CU(cudaMalloc(&b->d_dist_begin, 4ull * (max_reads + 1ull))); CU(cudaMalloc(&b->d_dist_out_begin, 4ull * (max_reads + 1ull)));
+  CU(cudaMalloc(&b->d_dist_partials, 4ull * (max_reads / 4096 + 2)));
+  CU(cudaMallocHost(&b->h_dist_begin, 4ull * (max_reads + 1ull)));
   const uint64_t want = std::max<uint64_t>(4ull * max_reads, 4096);
   if (int rc = alloc_records(b, (uint32_t)std::min<uint64_t>(want, 0x7FFFFFFFull))) return rc;
   { // solve memo (see SolveArgs): a table of 8 slots per read, between 2^16 and 2^24 slots; KREPP_MEMO=0 turns it off
@@ -525,9 +667,11 @@ int krepp_batch_create(krepp_index_t* ix, const krepp_params_t* p, uint32_t max_
 void krepp_batch_destroy(krepp_batch_t* b)
 {
   if (!b) return;
-  cudaSetDevice(b->ix->device);
+  cudaSetDevice(b->device);
   if (b->stream) cudaStreamSynchronize(b->stream);
   free_records(b);
+  for (void* p : {(void*)b->d_dist_cnt, (void*)b->d_dist_begin, (void*)b->d_dist_out_begin, (void*)b->d_dist_partials}) if (p) cudaFree(p);
+  if (b->h_dist_begin) cudaFreeHost(b->h_dist_begin);
   for (void* p : {(void*)b->d_bases, (void*)b->d_offsets, (void*)b->d_onmers, (void*)b->d_wn, (void*)b->d_hdfilt, (void*)b->d_rec_begin,
                   (void*)b->d_rec_count, (void*)b->d_closest, (void*)b->d_memo_key, (void*)b->d_memo_owner, (void*)b->d_counters, (void*)b->d_stats, (void*)b->d_acc, (void*)b->d_bitmap,
                   (void*)b->d_marker, (void*)b->d_stack, (void*)b->d_tagctr, (void*)b->d_out_read, (void*)b->d_tap, (void*)b->d_tap_count, (void*)b->d_place_begin,
@@ -572,6 +716,8 @@ static int enqueue(krepp_batch* b)
   if (b->shard_hits) CU(cudaMemcpyAsync(b->d_stats, b->d_stats + 4, 32, cudaMemcpyDeviceToDevice, s)); // the lookup / join phases' counts
   else CU(cudaMemsetAsync(b->d_stats, 0, 32, s));
   if (b->d_tap_count && !b->shard_hits) CU(cudaMemsetAsync(b->d_tap_count, 0, 8, s));
+  const bool fused = !b->shard_hits && !(b->sorted && !b->fused_once);
+  if (fused) { if (int rc = fused_scratch(b)) return rc; }
   MatchArgs m = match_args(b);
   CU(cudaEventRecord(b->evm0, s));
   if (!b->shard_hits) { b->clk.n = 0; b->clk.tick("start", s); }
@@ -582,6 +728,7 @@ static int enqueue(krepp_batch* b)
     b->h_sc[9] = (uint32_t)b->shard_n_hits;
     CU(cudaMemcpyAsync(so.sc, b->h_sc + 9, 4, cudaMemcpyHostToDevice, s));
     CU(launch_shard_finish(ix->dev, m, so, ix->sms, s, &b->clk));
+    CU(cudaMemcpyAsync(b->h_sc + 5, so.sc + 5, 4, cudaMemcpyDeviceToHost, s));
     match_launches = 6;
   } else if (b->sorted && !b->fused_once) {
     CU(launch_match_sorted(ix->dev, m, b->so, ix->sms, b->d_tap != nullptr, s, &match_launches, &b->clk));
@@ -590,6 +737,7 @@ static int enqueue(krepp_batch* b)
   } else {
     CU(launch_match(ix->dev, m, ix->resident_warps, ix->staged, b->d_tap != nullptr, s));
     b->clk.tick("match_kernel", s);
+    (void)fused;
   }
   CU(cudaEventRecord(b->evm1, s));
   SolveArgs sa{};
@@ -601,7 +749,7 @@ static int enqueue(krepp_batch* b)
   sa.memo_key = b->d_memo_key; sa.memo_owner = b->d_memo_owner; sa.memo_mask = b->memo_mask; sa.memo_bits = b->memo_bits; sa.rec_alias = b->d_rec_alias;
   sa.want_chisq = (!b->p.no_filter || b->p.summarize || b->p.place) ? 1 : 0;
   CU(launch_solve(sa, b->tab, ix->sms, s, &b->clk));
-  b->launches = 4 + match_launches + (sa.want_chisq ? 1 : 0) + (sa.memo_mask ? 1 : 0);
+  b->launches = 3 + match_launches + (sa.want_chisq ? 1 : 0) + (sa.memo_mask ? 1 : 0);
   if (b->p.place) {
     PlaceArgs pa{};
     pa.s = sa; pa.offsets = b->in_offsets; pa.tau = b->p.tau; pa.no_filter = b->p.no_filter; pa.chisq_value = b->p.chisq;
@@ -616,16 +764,39 @@ static int enqueue(krepp_batch* b)
     CU(launch_place(pa, b->tab, (int)(b->place_warps / kPlaceWarpsPerCta), ix->sms, s, &b->clk));
     b->launches += 4;
   }
-  // the 56-byte rows are assembled unless only the brief ones leave the device (placement text needs the full rows)
-  const bool want_full = (b->out_rows & KREPP_OUT_RECORDS) || !(b->out_rows & KREPP_OUT_BRIEF);
-  finalize_kernel<<<ix->sms * 4, 128, 0, s>>>(sa, want_full ? b->d_out_rec : nullptr, b->d_out_read, b->d_wn, b->d_place_begin, b->d_place_count,
-                                              (b->out_rows & KREPP_OUT_BRIEF) ? b->d_out_brief : nullptr, b->p.chisq);
-  CU(cudaGetLastError());
-  b->clk.tick("finalize_kernel", s);
+  // Output rows in the forms the caller asked for (krepp_batch_set_output): the public AoS structs, and / or the printed rows of
+  // `krepp dist` chosen, ordered and rounded here so that 4 bytes per read and 4-8 per printed row leave the device.
+  const bool want_full = (b->out_rows & KREPP_OUT_RECORDS) != 0, want_brief = (b->out_rows & KREPP_OUT_BRIEF) != 0;
+  const bool want_sum = (b->out_rows & KREPP_OUT_SUMMARIES) != 0, want_dist = (b->out_rows & KREPP_OUT_DIST) != 0;
+  if (want_full || want_brief || want_sum) {
+    finalize_kernel<<<ix->sms * 4, 128, 0, s>>>(sa, want_full ? b->d_out_rec : nullptr, want_sum ? b->d_out_read : nullptr, b->d_wn, b->d_place_begin, b->d_place_count,
+                                                want_brief ? b->d_out_brief : nullptr, b->p.chisq);
+    CU(cudaGetLastError());
+    ++b->launches;
+  }
+  if (want_dist) {
+    DistOut d{};
+    d.n_reads = b->n_reads; d.rec_begin = b->d_rec_begin; d.rec_count = b->d_rec_count; d.rec_slot = b->d_rec_slot; d.rec_flags = b->d_rec_flags;
+    d.rec_d = b->d_rec_d; d.rec_chisq = b->d_rec_chisq; d.closest = b->d_closest; d.leaf_rank = ix->dev.leaf_rank; d.counters = b->d_counters;
+    d.summarize = b->p.summarize; d.multi = b->p.multi; d.no_filter = b->p.no_filter; d.has_max = std::isnan(b->p.dist_max) ? 0 : 1;
+    d.dist_max = b->p.dist_max; d.chisq_value = b->p.chisq;
+    d.cnt = b->d_dist_cnt; d.begin = b->d_dist_begin; d.out_begin = b->d_dist_out_begin; d.rows = b->d_dist_rows; d.row_bytes = b->dist_row_bytes;
+    if (b->n_reads) {
+      dist_count_kernel<<<ix->sms * 8, 128, 0, s>>>(d);
+      CU(cudaGetLastError());
+      CU(exclusive_scan(b->d_dist_cnt, b->n_reads, b->d_dist_partials, b->d_dist_begin, nullptr, s));
+      dist_emit_kernel<<<ix->sms * 8, 128, 0, s>>>(d);
+      CU(cudaGetLastError());
+      b->launches += 5;
+    }
+  }
+  b->clk.tick("finalize_kernel / dist rows", s);
   CU(cudaEventRecord(b->ev1, s)); // kernels only: [ev0, ev1] excludes the host<->device copies on both sides
   CU(cudaMemcpyAsync(b->h_counters, b->d_counters, 32, cudaMemcpyDeviceToHost, s));
   CU(cudaMemcpyAsync(b->h_stats, b->d_stats, 32, cudaMemcpyDeviceToHost, s));
-  CU(cudaMemcpyAsync(b->h_read, b->d_out_read, sizeof(krepp_read_summary_t) * (size_t)b->n_reads, cudaMemcpyDeviceToHost, s));
+  b->summaries_copied = want_sum;
+  if (want_sum) CU(cudaMemcpyAsync(b->h_read, b->d_out_read, sizeof(krepp_read_summary_t) * (size_t)b->n_reads, cudaMemcpyDeviceToHost, s));
+  if (want_dist && b->n_reads) CU(cudaMemcpyAsync(b->h_dist_begin, b->d_dist_out_begin, 4ull * (b->n_reads + 1ull), cudaMemcpyDeviceToHost, s));
   return KREPP_OK;
 }
 
@@ -644,7 +815,7 @@ int krepp_batch_submit(krepp_batch_t* b, const char* bases, const uint64_t* offs
   const uint64_t nb = n_reads ? offsets[n_reads] - offsets[0] : 0;
   if (nb > b->max_bases) return fail(KREPP_ERR_CAPACITY, "batch of %llu bases exceeds the slot capacity of %llu", (unsigned long long)nb, (unsigned long long)b->max_bases);
   if (b->ix->host.nshards > 1) return fail(KREPP_ERR_UNSUPPORTED, "this index handle holds one bucket-range shard: use krepp_shard_lookup / _join / _finish");
-  if (cudaSetDevice(b->ix->device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice failed");
+  if (cudaSetDevice(b->device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice failed");
   CU(cudaStreamSynchronize(b->stream)); // the previous batch of this slot must be finished before its buffers are reused
   // Page-locked caller memory (cudaMallocHost / cudaHostRegister) is copied to the device straight from where it lies;
   // pageable memory goes through the slot's own pinned staging buffer first.
@@ -664,7 +835,7 @@ int krepp_batch_submit(krepp_batch_t* b, const char* bases, const uint64_t* offs
   CU(cudaMemcpyAsync(b->d_offsets, b->h_offsets, 8ull * (n_reads + 1), cudaMemcpyHostToDevice, b->stream));
   CU(cudaEventRecord(b->ev0, b->stream));
   if (int rc = enqueue(b)) return rc;
-  b->submitted = true;
+  b->submitted = true; b->pending = true;
   return KREPP_OK;
 }
 
@@ -674,13 +845,13 @@ int krepp_batch_submit_device(krepp_batch_t* b, const char* d_bases, const uint6
   if (n_reads > b->max_reads) return fail(KREPP_ERR_CAPACITY, "batch of %u reads exceeds the slot capacity of %u", n_reads, b->max_reads);
   if (reinterpret_cast<uintptr_t>(d_bases) & 15) return fail(KREPP_ERR_ARG, "device bases pointer must be 16-byte aligned");
   if (b->ix->host.nshards > 1) return fail(KREPP_ERR_UNSUPPORTED, "this index handle holds one bucket-range shard: use krepp_shard_lookup / _join / _finish");
-  if (cudaSetDevice(b->ix->device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice failed");
+  if (cudaSetDevice(b->device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice failed");
   CU(cudaStreamSynchronize(b->stream));
   b->n_reads = n_reads; b->n_bases = n_bases; b->device_input = true; b->fused_once = false; b->shard_hits = nullptr;
   b->in_bases = d_bases; b->in_offsets = d_offsets;
   CU(cudaEventRecord(b->ev0, b->stream));
   if (int rc = enqueue(b)) return rc;
-  b->submitted = true;
+  b->submitted = true; b->pending = true;
   return KREPP_OK;
 }
 
@@ -690,13 +861,14 @@ int krepp_batch_wait_device(krepp_batch_t* b, krepp_results_t* out) { return wai
 
 int krepp_batch_set_output(krepp_batch_t* b, uint32_t rows)
 {
-  if (!b || (rows & ~(uint32_t)(KREPP_OUT_ALL | KREPP_OUT_BRIEF))) return fail(KREPP_ERR_ARG, "krepp_batch_set_output: bad argument");
-  if (cudaSetDevice(b->ix->device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice failed");
+  if (!b || (rows & ~(uint32_t)(KREPP_OUT_ALL | KREPP_OUT_BRIEF | KREPP_OUT_DIST))) return fail(KREPP_ERR_ARG, "krepp_batch_set_output: bad argument");
+  if (b->pending) return fail(KREPP_ERR_ARG, "krepp_batch_set_output: a batch is pending on this slot (the rows are assembled by the submit); call it before krepp_batch_submit or after krepp_batch_wait");
+  if ((rows & KREPP_OUT_DIST) && b->p.place) return fail(KREPP_ERR_ARG, "krepp_batch_set_output: KREPP_OUT_DIST rows are those of `dist`; this slot runs `place`");
+  if (cudaSetDevice(b->device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice failed");
   CU(cudaStreamSynchronize(b->stream));
   b->out_rows = rows;
-  if ((rows & KREPP_OUT_BRIEF) && !b->d_out_brief) {
-    CU(cudaMalloc(&b->d_out_brief, sizeof(krepp_brief_t) * (size_t)b->rec_cap));
-  }
+  if ((rows & KREPP_OUT_BRIEF) && !b->d_out_brief) CU(cudaMalloc(&b->d_out_brief, sizeof(krepp_brief_t) * (size_t)b->rec_cap));
+  if ((rows & KREPP_OUT_DIST) && !b->d_dist_rows) CU(cudaMalloc(&b->d_dist_rows, (size_t)b->dist_row_bytes * b->rec_cap));
   return KREPP_OK;
 }
 
@@ -707,6 +879,7 @@ static int host_rows(krepp_batch* b, uint32_t rows)
   if ((rows & KREPP_OUT_RECORDS) && !b->h_rec) CU(cudaMallocHost(&b->h_rec, sizeof(krepp_record_t) * cap));
   if ((rows & KREPP_OUT_HIST) && !b->h_hist) CU(cudaMallocHost(&b->h_hist, 4ull * cap * stride));
   if ((rows & KREPP_OUT_BRIEF) && !b->h_brief) CU(cudaMallocHost(&b->h_brief, sizeof(krepp_brief_t) * cap));
+  if ((rows & KREPP_OUT_DIST) && !b->h_dist_rows) CU(cudaMallocHost(&b->h_dist_rows, (size_t)b->dist_row_bytes * cap));
   if ((rows & KREPP_OUT_PLACEMENTS) && b->p.place && !b->h_place) CU(cudaMallocHost(&b->h_place, sizeof(krepp_placement_t) * (size_t)b->place_cap));
   return KREPP_OK;
 }
@@ -715,14 +888,15 @@ static int wait_impl(krepp_batch_t* b, krepp_results_t* out, uint32_t rows)
 {
   if (!b || !out) return fail(KREPP_ERR_ARG, "krepp_batch_wait: null argument");
   if (!b->submitted) return fail(KREPP_ERR_ARG, "krepp_batch_wait: nothing was submitted on this slot");
-  if (cudaSetDevice(b->ix->device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice failed");
+  if (cudaSetDevice(b->device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice failed");
   for (int attempt = 0;; ++attempt) {
     CU(cudaStreamSynchronize(b->stream));
     if (b->h_counters[2] & kErrStackOverflow) return fail(KREPP_ERR_CAPACITY, "colour expansion stack overflow on the device");
     if (b->h_counters[2] & kErrShardData) return fail(KREPP_ERR_ARG, "krepp_shard_finish: a hit entry names a read outside the batch");
     if (b->shard_hits && (b->h_counters[2] & kErrSortFallback))
-      return fail(KREPP_ERR_CAPACITY, "a read has more leaf hits than the bucket-sorted chain holds and a sharded index has no fused kernel to fall back to");
-    if (!(b->h_counters[2] & (kErrRecOverflow | kErrPlaceOverflow | kErrNodeOverflow | kErrLookupOverflow | kErrHitOverflow | kErrSortFallback))) break;
+      return fail(KREPP_ERR_CAPACITY, "a read has 2^26 or more lookups, which the bucket-sorted chain cannot index, and a sharded index has no fused kernel to fall back to");
+    if (b->h_counters[2] & kErrHitWrap) return fail(KREPP_ERR_CAPACITY, "batch produces 2^32 or more hit entries; submit fewer reads per batch");
+    if (!(b->h_counters[2] & (kErrRecOverflow | kErrPlaceOverflow | kErrNodeOverflow | kErrLookupOverflow | kErrHitOverflow | kErrSortFallback | kErrKeysOverflow))) break;
     // a result buffer was too small: grow it to what the kernels asked for and run the batch again
     if (attempt >= 8) return fail(KREPP_ERR_CAPACITY, "result buffer overflow persists");
     if (b->h_counters[2] & kErrRecOverflow) {
@@ -738,7 +912,12 @@ static int wait_impl(krepp_batch_t* b, krepp_results_t* out, uint32_t rows)
       const uint64_t need = b->h_sc[0];
       if (int rc = alloc_hits(b, need + need / 4 + 4096)) return rc;
     }
-    if (b->h_counters[2] & kErrSortFallback) b->fused_once = true; // a read outside the sorted pipeline's limits: this batch goes through the fused kernel
+    if (b->h_counters[2] & kErrKeysOverflow) { // a read with more leaf hits than a warp's sort scratch: grow it to the demand (h_sc[5])
+      const int rc = alloc_keys(b, b->h_sc[5]);
+      if (rc && !b->shard_hits) { b->fused_once = true; cudaGetLastError(); } // beyond any scratch: the fused kernel handles reads of any size (no such fallback on a shard)
+      else if (rc) return rc;
+    }
+    if (b->h_counters[2] & kErrSortFallback) b->fused_once = true; // a read with 2^26 or more lookups: this batch goes through the fused kernel
     if (b->h_counters[2] & kErrNodeOverflow) { // counters[5] = tree nodes the batch touches
       const uint64_t need = b->h_counters[5];
       if (int rc = alloc_place_nodes(b, need + need / 8 + 4096)) return rc;
@@ -758,16 +937,36 @@ static int wait_impl(krepp_batch_t* b, krepp_results_t* out, uint32_t rows)
   if (nrec && (rows & KREPP_OUT_HIST)) CU(cudaMemcpyAsync(b->h_hist, b->d_rec_hist, 4ull * nrec * stride, cudaMemcpyDeviceToHost, b->stream));
   const uint32_t nplace = b->p.place ? b->h_counters[3] : 0;
   if (nplace && (rows & KREPP_OUT_PLACEMENTS)) CU(cudaMemcpyAsync(b->h_place, b->d_place, sizeof(krepp_placement_t) * (size_t)nplace, cudaMemcpyDeviceToHost, b->stream));
+  const bool have_dist = (rows & KREPP_OUT_DIST) && (b->out_rows & KREPP_OUT_DIST);
+  const uint64_t ndist = have_dist && b->n_reads ? KREPP_DIST_BEGIN(b->h_dist_begin[b->n_reads]) : 0;
+  if (have_dist && !b->n_reads) b->h_dist_begin[0] = 0;
+  if (ndist) CU(cudaMemcpyAsync(b->h_dist_rows, b->d_dist_rows, (size_t)b->dist_row_bytes * ndist, cudaMemcpyDeviceToHost, b->stream));
+  const bool want_sum = (rows & KREPP_OUT_SUMMARIES) || rows == 0; // krepp_batch_wait_device always hands out the summaries
+  if (want_sum && !b->summaries_copied) {
+    if (!(b->out_rows & KREPP_OUT_SUMMARIES)) { // they were not assembled by the submit: do it now
+      SolveArgs sa{};
+      sa.n_reads = b->n_reads; sa.n_records = 0; sa.counters = b->d_counters; sa.onmers = b->d_onmers; sa.hdfilt = b->d_hdfilt;
+      sa.rec_begin = b->d_rec_begin; sa.rec_count = b->d_rec_count; sa.closest = b->d_closest;
+      finalize_kernel<<<b->ix->sms * 4, 128, 0, b->stream>>>(sa, nullptr, b->d_out_read, b->d_wn, b->d_place_begin, b->d_place_count, nullptr, b->p.chisq);
+      CU(cudaGetLastError());
+    }
+    CU(cudaMemcpyAsync(b->h_read, b->d_out_read, sizeof(krepp_read_summary_t) * (size_t)b->n_reads, cudaMemcpyDeviceToHost, b->stream));
+    b->summaries_copied = true;
+  }
   CU(cudaStreamSynchronize(b->stream));
   float ms = 0;
   CU(cudaEventElapsedTime(&ms, b->ev0, b->ev1));
   out->n_reads = b->n_reads; out->hist_stride = (uint32_t)stride; out->n_records = nrec; out->n_placements = nplace;
-  out->reads = b->h_read; out->records = (rows & KREPP_OUT_RECORDS) ? b->h_rec : nullptr; out->hist = (rows & KREPP_OUT_HIST) ? b->h_hist : nullptr;
+  out->reads = want_sum ? b->h_read : nullptr;
+  out->records = (rows & KREPP_OUT_RECORDS) ? b->h_rec : nullptr; out->hist = (rows & KREPP_OUT_HIST) ? b->h_hist : nullptr;
   out->placements = nplace && (rows & KREPP_OUT_PLACEMENTS) ? b->h_place : nullptr;
   out->brief = (rows & KREPP_OUT_BRIEF) ? b->h_brief : nullptr;
+  out->dist_begin = have_dist ? b->h_dist_begin : nullptr; out->dist_rows = have_dist ? b->h_dist_rows : nullptr;
+  out->n_dist_rows = ndist; out->dist_row_bytes = b->dist_row_bytes;
   float mms = 0;
   CU(cudaEventElapsedTime(&mms, b->evm0, b->evm1));
   out->gpu_ms = ms; out->match_ms = mms; out->gpu_launches = b->launches;
+  b->pending = false;
   return KREPP_OK;
 }
 
@@ -780,7 +979,7 @@ int krepp_shard_lookup(krepp_batch_t* b, const char* d_bases, const uint64_t* d_
   if (!b->sorted) return fail(KREPP_ERR_UNSUPPORTED, "krepp_shard_lookup: this slot does not run the bucket-sorted chain");
   if (n_reads > b->max_reads) return fail(KREPP_ERR_CAPACITY, "batch of %u reads exceeds the slot capacity of %u", n_reads, b->max_reads);
   if (reinterpret_cast<uintptr_t>(d_bases) & 15) return fail(KREPP_ERR_ARG, "device bases pointer must be 16-byte aligned");
-  if (cudaSetDevice(b->ix->device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice failed");
+  if (cudaSetDevice(b->device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice failed");
   const HostIndex& h = b->ix->host;
   cudaStream_t s = b->stream;
   CU(cudaStreamSynchronize(s));
@@ -811,7 +1010,7 @@ int krepp_shard_join(krepp_batch_t* b, uint32_t n_sources, const void* const* d_
   if (!b || !d_hits || !hit_offsets || (n_sources && (!d_tuples || !d_row_begin))) return fail(KREPP_ERR_ARG, "krepp_shard_join: null argument");
   if (!b->sorted) return fail(KREPP_ERR_UNSUPPORTED, "krepp_shard_join: this slot does not run the bucket-sorted chain");
   if (n_sources > KREPP_MAX_SHARDS) return fail(KREPP_ERR_ARG, "krepp_shard_join: at most %d sources", KREPP_MAX_SHARDS);
-  if (cudaSetDevice(b->ix->device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice failed");
+  if (cudaSetDevice(b->device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice failed");
   cudaStream_t s = b->stream;
   CU(cudaStreamSynchronize(s));
   CU(cudaMemsetAsync(b->d_counters + 2, 0, 4, s));
@@ -842,7 +1041,7 @@ int krepp_shard_finish(krepp_batch_t* b, const void* d_hits, uint64_t n_hits)
   if (!b || (!d_hits && n_hits)) return fail(KREPP_ERR_ARG, "krepp_shard_finish: null argument");
   if (!b->sorted || !b->in_bases) return fail(KREPP_ERR_ARG, "krepp_shard_finish: krepp_shard_lookup has not run on this slot");
   if (n_hits > 0xFFFFFFF0ull) return fail(KREPP_ERR_CAPACITY, "batch produces too many hit entries; submit fewer reads per batch");
-  if (cudaSetDevice(b->ix->device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice failed");
+  if (cudaSetDevice(b->device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice failed");
   CU(cudaStreamSynchronize(b->stream));
   if (n_hits > b->so.cap_hits) { if (int rc = alloc_hits(b, n_hits + n_hits / 8 + 4096)) return rc; }
   static const uint4 none = {0, 0, 0, 0};
@@ -850,7 +1049,7 @@ int krepp_shard_finish(krepp_batch_t* b, const void* d_hits, uint64_t n_hits)
   CU(cudaMemcpyAsync(b->d_stats + 4, b->d_stats, 32, cudaMemcpyDeviceToDevice, b->stream));
   b->clk.tick("(exchange of hit entries)", b->stream);
   if (int rc = enqueue(b)) return rc;
-  b->submitted = true;
+  b->submitted = true; b->pending = true;
   return KREPP_OK;
 }
 
@@ -891,7 +1090,7 @@ int krepp_device_copy(int dst_device, void* dst, int src_device, const void* src
 int krepp_batch_enable_tap(krepp_batch_t* b, int stage, uint64_t capacity_items)
 {
   if (!b || (stage != 1 && stage != 2) || (stage == 1 && !capacity_items)) return fail(KREPP_ERR_ARG, "krepp_batch_enable_tap: bad argument");
-  if (cudaSetDevice(b->ix->device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice failed");
+  if (cudaSetDevice(b->device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice failed");
   CU(cudaStreamSynchronize(b->stream));
   if (stage == 2) { b->keep_all = capacity_items != 0; return KREPP_OK; }
   if (b->d_tap) { cudaFree(b->d_tap); b->d_tap = nullptr; }
@@ -904,7 +1103,7 @@ int krepp_batch_enable_tap(krepp_batch_t* b, int stage, uint64_t capacity_items)
 int krepp_batch_read_tap(krepp_batch_t* b, int stage, uint32_t* out, uint64_t cap_items, uint64_t* n)
 {
   if (!b || stage != 1 || !n || !b->d_tap) return fail(KREPP_ERR_ARG, "krepp_batch_read_tap: bad argument or tap not enabled");
-  if (cudaSetDevice(b->ix->device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice failed");
+  if (cudaSetDevice(b->device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice failed");
   CU(cudaStreamSynchronize(b->stream));
   unsigned long long cnt = 0;
   CU(cudaMemcpy(&cnt, b->d_tap_count, 8, cudaMemcpyDeviceToHost));
@@ -917,7 +1116,7 @@ int krepp_batch_read_tap(krepp_batch_t* b, int stage, uint32_t* out, uint64_t ca
 int krepp_batch_stage_times(krepp_batch_t* b, uint32_t cap, float* ms, const char** names, uint32_t* n)
 {
   if (!b || !n) return fail(KREPP_ERR_ARG, "krepp_batch_stage_times: null argument");
-  if (cudaSetDevice(b->ix->device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice failed");
+  if (cudaSetDevice(b->device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice failed");
   CU(cudaStreamSynchronize(b->stream));
   const uint32_t have = b->clk.n > 1 ? (uint32_t)b->clk.n - 1 : 0;
   *n = have;

@@ -211,7 +211,7 @@ static int run_sharded(const Options& o, const krepp_params_t& p, bool place, co
     ShardDev& d = D[g];
     d.row0 = splits[g]; d.row1 = splits[g + 1];
     check(krepp_batch_create(d.ix, &p, o.batch_reads, o.batch_bases, &d.slot));
-    check(krepp_batch_set_output(d.slot, place ? (KREPP_OUT_RECORDS | KREPP_OUT_PLACEMENTS) : KREPP_OUT_BRIEF));
+    check(krepp_batch_set_output(d.slot, place ? (KREPP_OUT_RECORDS | KREPP_OUT_PLACEMENTS | KREPP_OUT_SUMMARIES) : KREPP_OUT_DIST));
     check(krepp_batch_host_buffers(d.slot, &d.h_bases, &d.h_offsets));
     d.names.resize(64ull * o.batch_reads); d.name_off.resize(o.batch_reads);
     check(krepp_device_alloc(d.dev, o.batch_bases + 64, &d.d_bases));
@@ -383,8 +383,8 @@ int main(int argc, char** argv)
     Slot& s = slots[i];
     s.gpu = (int)(i % o.devices.size());
     check(krepp_batch_create(index[s.gpu], &p, o.batch_reads, o.batch_bases, &s.batch));
-    // the writers never read the histograms, and `dist` needs only the 16-byte rows
-    check(krepp_batch_set_output(s.batch, place ? (KREPP_OUT_RECORDS | KREPP_OUT_PLACEMENTS) : KREPP_OUT_BRIEF));
+    // the writers never read the histograms, and `dist` needs only the rows it prints, which the device selects and rounds
+    check(krepp_batch_set_output(s.batch, place ? (KREPP_OUT_RECORDS | KREPP_OUT_PLACEMENTS | KREPP_OUT_SUMMARIES) : KREPP_OUT_DIST));
     check(krepp_batch_host_buffers(s.batch, &s.bases, &s.offsets));
     s.names.resize(64ull * o.batch_reads);
     s.name_off.resize(o.batch_reads);
@@ -439,7 +439,8 @@ int main(int argc, char** argv)
       auto work = [&](uint32_t t) {
         const uint32_t lo = (uint32_t)((uint64_t)res.n_reads * t / T), hi = (uint32_t)((uint64_t)res.n_reads * (t + 1) / T);
         krepp_results_t sub = res;
-        sub.reads = res.reads + lo;
+        if (res.reads) sub.reads = res.reads + lo;
+        if (res.dist_begin) sub.dist_begin = res.dist_begin + lo;
         sub.n_reads = hi - lo;
         double* w = nullptr;
         if (p.summarize) { part_w[t].assign(info.nnodes + 1, 0.0); w = part_w[t].data(); }

@@ -441,6 +441,38 @@ size_t format_dist_rows(const krepp_index_t* ix, const krepp_params_t* p, const 
   return o.len;
 }
 
+// The same text from the rows the device already chose, ordered and rounded (KREPP_OUT_DIST, include/krepp_b200.h): per read one
+// word of dist_begin and its rows; nothing is decided here.
+template <class Row>
+size_t format_dist_compact(const krepp_index_t* ix, const krepp_params_t* p, const krepp_results_t* res, const Row* rows, const char* names,
+                           const uint64_t* name_offsets, double* wcount, char* buf, size_t cap)
+{
+  Out o(buf, cap);
+  const HostTree& t = ix->host.tree;
+  for (uint32_t r = 0; r < res->n_reads; ++r) {
+    const uint32_t w0 = res->dist_begin[r], b = KREPP_DIST_BEGIN(w0), e = KREPP_DIST_BEGIN(res->dist_begin[r + 1]);
+    auto se_of = [&](const Row& row) -> uint32_t { if constexpr (sizeof(Row) == 4) return t.leaf_se[row >> 16]; else return (uint32_t)row; };
+    if (p->summarize) { // ref src/query.cpp:160-171
+      if (wcount) for (uint32_t i = b; i < e; ++i) wcount[se_of(rows[i])] += 1.0 / (double)(e - b);
+      continue;
+    }
+    const char* id = name_of(names, name_offsets, r);
+    const size_t id_len = strlen(id);
+    if (KREPP_DIST_NA(w0)) { o.put(id, id_len); o.put("\tNA\tNaN\n"); continue; }
+    for (uint32_t i = b; i < e; ++i) {
+      uint32_t units;
+      if constexpr (sizeof(Row) == 4) units = rows[i] & 0xFFFFu; else units = (uint32_t)(rows[i] >> 32);
+      o.put(id, id_len); o.ch('\t'); o.put(t.shown[se_of(rows[i])]); o.ch('\t');
+      o.u32(units / 100000u); o.ch('.');
+      char d5[5];
+      uint32_t x = units % 100000u;
+      for (int k = 4; k >= 0; --k) { d5[k] = (char)('0' + x % 10); x /= 10; }
+      o.put(d5, 5); o.ch('\n');
+    }
+  }
+  return o.len;
+}
+
 } // namespace
 
 extern "C" size_t krepp_format_header(const krepp_index_t* ix, const krepp_params_t* p, int tabular, const char* invocation, char* buf, size_t cap)
@@ -466,6 +498,10 @@ extern "C" size_t krepp_format_dist(const krepp_index_t* ix, const krepp_params_
                                     const uint64_t* name_offsets, double* wcount, char* buf, size_t cap)
 {
   if (!ix || !p || !res || !names || !name_offsets) return 0;
+  if (res->dist_begin) {
+    if (res->dist_row_bytes == 4) return format_dist_compact(ix, p, res, static_cast<const uint32_t*>(res->dist_rows), names, name_offsets, wcount, buf, cap);
+    return format_dist_compact(ix, p, res, static_cast<const uint64_t*>(res->dist_rows), names, name_offsets, wcount, buf, cap);
+  }
   if (res->records || !res->brief) return format_dist_rows(ix, p, res, res->records, names, name_offsets, wcount, buf, cap);
   return format_dist_rows(ix, p, res, res->brief, names, name_offsets, wcount, buf, cap);
 }

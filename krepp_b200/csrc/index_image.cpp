@@ -235,7 +235,38 @@ std::vector<BitRun> runs_of(uint64_t mask)
 
 } // namespace
 
-std::string HostIndex::load(const std::string& dir, uint32_t shard_id, uint32_t shard_count)
+static std::vector<uint32_t> split_rows(const std::vector<uint64_t>& inc, uint64_t nkmers, uint32_t nrows, uint32_t nshards)
+{ // shard g starts at the first row whose bucket ends beyond g/nshards of the entries: contiguous row ranges of (nearly) equal
+  // cmer bytes, the same on every rank because they depend on inc-* alone
+  std::vector<uint32_t> row_splits(nshards + 1, 0);
+  for (uint32_t g = 1; g < nshards; ++g) {
+    const uint64_t target = (uint64_t)((unsigned __int128)nkmers * g / nshards);
+    const uint32_t at = (uint32_t)(std::upper_bound(inc.begin(), inc.end(), target) - inc.begin());
+    row_splits[g] = std::max(row_splits[g - 1], std::min(at, nrows));
+  }
+  row_splits[nshards] = nrows;
+  return row_splits;
+}
+
+uint64_t HostIndex::replicated_device_bytes() const
+{ // what krepp_index_open_shard uploads besides cmer / inc32 (api.cu)
+  const uint64_t nn = (uint64_t)tree.nnodes + 1;
+  return 8ull * pse.size() + kind.size() + 8ull * kind.size() + 8ull * rho.size() + 4ull * nn * 6 + 8ull * nn + 4ull * tree.leaf_se.size() + 8ull * 256 * 16 +
+         4ull * cbeg.size() + 4ull * (cleaf.size() + 1);
+}
+
+uint64_t HostIndex::shard_table_device_bytes(uint32_t n) const
+{
+  const std::vector<uint32_t> sp = split_rows(inc, nkmers, nrows, n);
+  uint64_t worst = 0;
+  for (uint32_t g = 0; g < n; ++g) {
+    const uint64_t e0 = sp[g] ? inc[sp[g] - 1] : 0, e1 = sp[g + 1] ? inc[sp[g + 1] - 1] : 0;
+    worst = std::max<uint64_t>(worst, 8ull * (e1 - e0 + 4) + 4ull * ((uint64_t)sp[g + 1] - sp[g] + 1));
+  }
+  return worst;
+}
+
+std::string HostIndex::load(const std::string& dir, uint32_t shard_id, uint32_t shard_count, bool with_table)
 {
   if (!shard_count || shard_id >= shard_count) return "Bad shard arguments for the index!";
   shard = shard_id; nshards = shard_count;
@@ -331,20 +362,12 @@ std::string HostIndex::load(const std::string& dir, uint32_t shard_id, uint32_t 
     }
     mean_bucket = nrows ? s1 / nrows : 0;
     size_biased_bucket = s1 > 0 ? s2 / s1 : 0;
-    // shard g starts at the first row whose bucket ends beyond g/nshards of the entries: contiguous row ranges of (nearly)
-    // equal cmer bytes, the same on every rank because they depend on inc-* alone
-    row_splits.assign(nshards + 1, 0);
-    for (uint32_t g = 1; g < nshards; ++g) {
-      const uint64_t target = (uint64_t)((unsigned __int128)nkmers * g / nshards);
-      const uint32_t at = (uint32_t)(std::upper_bound(inc.begin(), inc.end(), target) - inc.begin());
-      row_splits[g] = std::max(row_splits[g - 1], std::min(at, nrows));
-    }
-    row_splits[nshards] = nrows;
+    row_splits = split_rows(inc, nkmers, nrows, nshards);
     row0 = row_splits[shard]; row1 = row_splits[shard + 1];
     ent0 = row0 ? inc[row0 - 1] : 0;
     const uint64_t ent1 = row1 ? inc[row1 - 1] : 0;
-    cmer.resize(ent1 - ent0);
-    { // the table is most of the index (1.6 GB for 1,000 genomes): read it with several threads, each pread()ing its own range
+    cmer.resize(with_table ? ent1 - ent0 : 0);
+    if (with_table) { // the table is most of the index (1.6 GB for 1,000 genomes): read it with several threads, each pread()ing its own range
       const int fd = open((dir + "/cmer" + sfx).c_str(), O_RDONLY);
       if (fd < 0) return "Failed to open " + dir + "/cmer" + sfx;
       const size_t bytes = cmer.size() * 8, nth = std::max<size_t>(1, std::min<size_t>(8, bytes >> 24));

@@ -83,7 +83,12 @@ struct HostIndex {
   uint64_t ent0 = 0;
   std::vector<uint32_t> row_splits;           // [nshards + 1] first row of every shard; equal cmer bytes per shard
   // Returns "" on success, else an error message (the reference's wording where it has one).
-  std::string load(const std::string& dir, uint32_t shard = 0, uint32_t nshards = 1);
+  // with_table = false: everything but the k-mer table itself (cmer stays empty) -- enough to plan a sharding (plan_shards).
+  std::string load(const std::string& dir, uint32_t shard = 0, uint32_t nshards = 1, bool with_table = true);
+  // Device bytes of the parts every shard replicates (colour record, flattened colour lists, tree, hash tables), and of the
+  // largest shard's slice of the table when it is split into n bucket-range shards (the split rule of load()).
+  uint64_t replicated_device_bytes() const;
+  uint64_t shard_table_device_bytes(uint32_t n) const;
 };
 
 } // namespace krepp

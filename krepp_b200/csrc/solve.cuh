@@ -18,6 +18,9 @@ int match_resident_warps(int device, uint32_t k, bool staged);
 cudaError_t launch_match(const DevIndex& ix, const MatchArgs& a, int resident_warps, bool staged, bool tap, cudaStream_t stream);
 // sorted.cu: the bucket-sorted form of the match stage (same outputs as launch_match)
 int sorted_resolve_warps(int sms);
+int sorted_resolve_warps_per_cta();
+// begin[i] = sum of in[0..i), begin[n] = the total; cursor (optional) = copy of begin[0..n); partials: n / 4096 + 2 words of scratch
+cudaError_t exclusive_scan(const uint32_t* in, uint32_t n, uint32_t* partials, uint32_t* begin, uint32_t* cursor, cudaStream_t stream);
 cudaError_t launch_match_sorted(const DevIndex& ix, const MatchArgs& a, const SortArgs& s, int sms, bool tap, cudaStream_t stream, uint32_t* launches, StageClock* clk = nullptr);
 // mode B: the chain of launch_match_sorted cut at its two exchange points
 cudaError_t launch_shard_lookup(const DevIndex& ix, const MatchArgs& a, const SortArgs& s, int sms, bool tap, cudaStream_t stream, StageClock* clk = nullptr);

@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t
   if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) begin[n] = partials[blockIdx.x] + total;
 }
 
-static cudaError_t exclusive_scan(const uint32_t* in, uint32_t n, uint32_t* partials, uint32_t* begin, uint32_t* cursor, cudaStream_t stream)
+cudaError_t exclusive_scan(const uint32_t* in, uint32_t n, uint32_t* partials, uint32_t* begin, uint32_t* cursor, cudaStream_t stream)
 {
   const uint32_t nb = (n + kScanTile - 1) / kScanTile;
   scan_sums_kernel<<<nb, kScanThreads, 0, stream>>>(in, n, partials);
@@ -208,7 +208,7 @@ __device__ __noinline__ void join_flush(JoinWarpSmem* w, const SortArgs s, uint3
     uint32_t base = 0;
     if (lane == 0) base = atomicAdd(s.sc, n);
     base = __shfl_sync(0xFFFFFFFFu, base, 0);
-    if ((uint64_t)base + n > s.cap_hits && lane == 0) atomicOr(counters + 2, kErrHitOverflow); // s.sc[0] ends as the demand
+    if ((uint64_t)base + n > s.cap_hits && lane == 0) atomicOr(counters + 2, (uint64_t)base + n > 0xFFFFFFF0ull ? (kErrHitOverflow | kErrHitWrap) : kErrHitOverflow); // s.sc[0] ends as the demand
     for (uint32_t i = lane; i < n; i += 32) if (base + i < s.cap_hits) s.hits_tmp[base + i] = w->hq[i];
   }
   __syncwarp();
@@ -581,7 +581,10 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_kernel(const DevIndex 
         out = resolve_read<uint64_t>(ix, a, s, reinterpret_cast<uint64_t*>(skeys[warp]), hb, nh, (uint32_t)T64, rank_bits, loc_bits, read, g0, g1, small_counts);
       else if (T64 <= (unsigned long long)s.cap_keys_g)
         out = resolve_read<uint64_t>(ix, a, s, gkeys, hb, nh, (uint32_t)T64, rank_bits, loc_bits, read, g0, g1, small_counts);
-      else if (lane == 0) atomicOr(a.counters + 2, kErrSortFallback); // too many leaf hits for the scratch: the fused kernel redoes the batch
+      else if (lane == 0) { // more leaf hits than the warp's scratch holds: the host grows it to the largest demand and runs the batch again
+        atomicMax(s.sc + 5, (uint32_t)min(T64, 0xFFFFFFFFull));
+        atomicOr(a.counters + 2, kErrKeysOverflow);
+      }
       __syncwarp();
     }
     if (lane == 0) {
@@ -617,6 +620,13 @@ static int scatter_ctas_per_sm()
   static const int v = [] { const char* e = getenv("KREPP_SCATTER_CTAS"); const int x = e ? atoi(e) : 2; return x == 1 ? 1 : 2; }();
   return v;
 }
+
+static int resolve_grid(const SortArgs& s, int sms)
+{ // keys_g holds one region per warp of the grid it was sized for (api.cu grow_keys shrinks the grid when the regions get large)
+  const int dflt = std::min(sorted_resolve_warps(sms) / kResWarps, sms * env_int("KREPP_RESOLVE_CTAS", 6));
+  return s.res_ctas ? std::min<int>((int)s.res_ctas, dflt) : dflt;
+}
+int sorted_resolve_warps_per_cta() { return kResWarps; }
 
 template <bool SCATTER>
 static cudaError_t launch_lookup(const DevIndex& ix, const MatchArgs& a, const SortArgs& s, int sms, bool tap, cudaStream_t stream)
@@ -662,7 +672,7 @@ cudaError_t launch_match_sorted(const DevIndex& ix, const MatchArgs& a, const So
   uint32_t rank_bits = 0;
   while ((1ull << rank_bits) < ix.nleaves) ++rank_bits;
   rank_bits += s.extra_rank_bits;
-  resolve_kernel<<<std::min(sorted_resolve_warps(sms) / kResWarps, sms * env_int("KREPP_RESOLVE_CTAS", 6)), kResWarps * 32, 0, stream>>>(ix, a, s, rank_bits);
+  resolve_kernel<<<resolve_grid(s, sms), kResWarps * 32, 0, stream>>>(ix, a, s, rank_bits);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   if (clk) clk->tick("resolve_kernel", stream);
   if (launches) *launches = 11;
@@ -707,7 +717,7 @@ cudaError_t launch_shard_finish(const DevIndex& ix, const MatchArgs& a, const So
   cudaError_t e;
   if (!a.n_reads) return cudaSuccess;
   if ((e = cudaMemsetAsync(s.hit_count, 0, 4ull * a.n_reads, stream)) != cudaSuccess) return e;
-  if ((e = cudaMemsetAsync(s.sc + 4, 0, 4, stream)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(s.sc + 4, 0, 8, stream)) != cudaSuccess) return e;
   hit_count_kernel<<<sms * 8, 256, 0, stream>>>(s, a.n_reads, a.counters);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   if ((e = exclusive_scan(s.hit_count, a.n_reads, s.partials, s.hit_begin, s.hit_cursor, stream)) != cudaSuccess) return e;
@@ -717,7 +727,7 @@ cudaError_t launch_shard_finish(const DevIndex& ix, const MatchArgs& a, const So
   uint32_t rank_bits = 0;
   while ((1ull << rank_bits) < ix.nleaves) ++rank_bits;
   rank_bits += s.extra_rank_bits;
-  resolve_kernel<<<sorted_resolve_warps(sms) / kResWarps, kResWarps * 32, 0, stream>>>(ix, a, s, rank_bits);
+  resolve_kernel<<<resolve_grid(s, sms), kResWarps * 32, 0, stream>>>(ix, a, s, rank_bits);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   if (clk) clk->tick("resolve_kernel", stream);
   return cudaSuccess;

@@ -26,7 +26,7 @@ def test_exports_every_declared_symbol(lib):
     assert len(names) >= 18
     for n in sorted(names):
         assert hasattr(lib, n), f"{n} is declared in include/krepp_b200.h but not exported"
-    assert lib.krepp_abi_version() == 1
+    assert lib.krepp_abi_version() == 2
 
 
 def test_header_is_plain_c(tmp_path):

@@ -348,3 +348,47 @@ def test_brief_rows_equal_full_rows():
         brief = capi.results_struct(r2["reads"], None, None, brief=r2["brief"])
         assert capi.format_dist(g, b.params, full, names) == capi.format_dist(g, b.params, brief, names)
         b.close()
+
+
+def test_dist_rows_selected_on_the_device():
+    """KREPP_OUT_DIST: the rows `krepp dist` prints, selected / ordered / rounded by the device, equal the selection made on the
+    host from the full records (a restatement of report_distances, ref src/query.cpp:158-196) in every mode, format to the same
+    TSV, and are all that leaves the device when asked for alone; krepp_batch_set_output refuses a pending slot."""
+    import math
+    import krepp_b200
+    from krepp_b200 import capi
+    small = os.path.join(conftest.GOLDEN_DIR, "small")
+    names, reads = fastq_reads(os.path.join(small, "reads.fq"))
+    g = krepp_b200.Index(os.path.join(small, "index"), 0)
+    modes = [dict(), dict(no_filter=False), dict(multi=False), dict(dist_max=0.05), dict(no_filter=False, dist_max=0.03), dict(multi=False, dist_max=0.08),
+             dict(summarize=True), dict(summarize=True, dist_max=0.05)]
+    for kw in modes:
+        b = krepp_b200.IBatch(g, reads, names=names, **kw)
+        b.set_output(dist=True)
+        b.submit()
+        with pytest.raises(capi.KreppError):
+            b.set_output(dist=False)          # a batch is pending
+        r = {k: np.array(v, copy=True) for k, v in b.wait().items() if isinstance(v, np.ndarray)}
+        want_begin, want_rows = capi.dist_rows_from_records(g, b.params, r["reads"], r["records"])
+        assert np.array_equal(r["dist_begin"], want_begin), kw
+        assert np.array_equal(r["dist_rows"], want_rows) and r["dist_rows"].dtype == np.uint32, kw
+        if not kw.get("summarize"):
+            assert len(want_rows) > (100 if kw.get("dist_max") else 200) or kw.get("multi") is False
+            full = capi.results_struct(r["reads"], r["records"], r["hist"])
+            compact = capi.results_struct(None, None, None, dist_begin=r["dist_begin"], dist_rows=r["dist_rows"])
+            assert capi.format_dist(g, b.params, full, names) == capi.format_dist(g, b.params, compact, names)
+        b.set_output(records=False, hist=False, placements=False, summaries=False, dist=True)   # what the dist command line asks for
+        b.submit()
+        r2 = b.wait()
+        assert len(r2["records"]) == 0 and len(r2["reads"]) == 0 and len(r2["brief"]) == 0
+        assert np.array_equal(r2["dist_begin"], want_begin) and np.array_equal(r2["dist_rows"], want_rows), kw
+        sums = b.wait_device()["reads"]       # the summaries are still to be had
+        assert np.array_equal(sums["onmers"], r["reads"]["onmers"]) and np.array_equal(sums["rec_count"], r["reads"]["rec_count"])
+        b.close()
+    # empty batch
+    b = krepp_b200.IBatch(g, [b""], capacity=(4, 64))
+    b.set_output(records=False, hist=False, placements=False, summaries=False, dist=True)
+    b.submit()
+    r = b.wait()
+    assert list(r["dist_begin"]) == [0x80000000, 0] and len(r["dist_rows"]) == 0
+    b.close()

@@ -192,6 +192,19 @@ def test_format_dist_equals_reference_tsv(K, small):
     wb = np.zeros_like(w)
     K.format_dist(small["index"], ps, rb, small["names"], wcount=wb)
     assert np.array_equal(w, wb)
+    # ... and so do the rows the device selects, orders and rounds itself (KREPP_OUT_DIST): 4 bytes per read + 4 per printed row
+    for prm in (p, K.Params(4, 2.706, float("nan"), 2, 1, 0, 0, 0), K.Params(4, 2.706, 0.05, 2, 1, 1, 0, 0), K.Params(4, 2.706, float("nan"), 2, 0, 1, 0, 0),
+                K.Params(4, 2.706, 0.08, 2, 0, 0, 0, 0), K.Params(4, 2.706, 0.03, 2, 0, 1, 0, 0)):
+        db, dr = K.dist_rows_from_records(small["index"], prm, arrs[0], arrs[1])
+        assert dr.dtype == np.uint32
+        rc = K.results_struct(None, None, None, dist_begin=db, dist_rows=dr)
+        assert K.format_dist(small["index"], prm, rc, small["names"]) == K.format_dist(small["index"], prm, res, small["names"])
+    for prm in (ps, K.Params(4, 2.706, 0.05, 2, 1, 1, 1, 0)):
+        db, dr = K.dist_rows_from_records(small["index"], prm, arrs[0], arrs[1])
+        wf, wc = np.zeros_like(w), np.zeros_like(w)
+        K.format_dist(small["index"], prm, res, small["names"], wcount=wf)
+        K.format_dist(small["index"], prm, K.results_struct(None, None, None, dist_begin=db, dist_rows=dr), small["names"], wcount=wc)
+        assert np.array_equal(wf, wc) and wf.sum() > 0
 
 
 def test_format_place_equals_reference_jplace_on_untied_reads(K, small):
