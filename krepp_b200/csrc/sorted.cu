@@ -37,7 +37,7 @@ constexpr uint32_t kLkClaim = 8;       // reads claimed per atomic
 constexpr int kJoinWarps = 8;
 constexpr uint32_t kRowClaim = 32;     // bucket rows claimed per atomic: one per lane
 constexpr int kJoinChunk = 128;        // index entries held in registers per pass: four per lane
-constexpr int kHitQ = 256;             // per-warp queue of hit entries; flushed once fewer than kJoinChunk slots are free
+constexpr int kHitQ = 128;             // per-warp queue of hit entries; flushed once fewer than 32 slots (one ballot's worth) are free
 constexpr int kResWarps = 8;
 constexpr int kResKeys = 1024;         // 32-bit sort keys per warp in shared memory (half as many 64-bit keys)
 constexpr uint32_t kResClaim = 4;
@@ -194,16 +194,16 @@ cudaError_t exclusive_scan(const uint32_t* in, uint32_t n, uint32_t* partials, u
 // ---------------------------------------------------------------------------------------------------- J: join
 
 struct __align__(16) JoinWarpSmem {
-  uint4 qs[32];       // the queries being compared: {q low half, q high half, read, local lookup index | strand << 31}
+  uint2 q2[32];       // the queries being compared, split into their bit-planes: {q low half, q high half}; read two at a time
+  uint2 meta[32];     // {read, strand << 31 | local lookup index << 5}
   uint4 hq[kHitQ];    // queued hit entries: {read, strand << 31 | local lookup index << 5 | hd, colour id, 0}
-  uint32_t hq_n, pad[3];
 };
 
-__device__ __noinline__ void join_flush(JoinWarpSmem* w, const SortArgs s, uint32_t* counters)
+// appends the warp's n queued hit entries to the batch-wide list
+__device__ __noinline__ void join_flush(JoinWarpSmem* w, const SortArgs s, uint32_t* counters, uint32_t n)
 {
   const uint32_t lane = threadIdx.x & 31;
   __syncwarp();
-  const uint32_t n = *reinterpret_cast<volatile uint32_t*>(&w->hq_n);
   if (n) {
     uint32_t base = 0;
     if (lane == 0) base = atomicAdd(s.sc, n);
@@ -212,41 +212,56 @@ __device__ __noinline__ void join_flush(JoinWarpSmem* w, const SortArgs s, uint3
     for (uint32_t i = lane; i < n; i += 32) if (base + i < s.cap_hits) s.hits_tmp[base + i] = w->hq[i];
   }
   __syncwarp();
-  if (lane == 0) w->hq_n = 0;
-  __syncwarp();
 }
 
-// One block of up to 32 queries (in w->qs) against the E entries each lane holds.  thr[e] is the Hamming threshold, or
-// -1 for a register slot that holds no entry.  The residual encoding keeps bit 0 of the 16 kept positions in its low half
-// and bit 1 in its high half (ref src/lshf.cpp:64-69), so the mismatch mask is (e.lo ^ q.lo) | (e.hi ^ q.hi): with both
-// halves of entries and queries split once, a comparison is two LOP3, one POPC and one ISETP.
+__device__ __forceinline__ int min_of(const int (&p)[1]) { return p[0]; }
+__device__ __forceinline__ int min_of(const int (&p)[2]) { return min(p[0], p[1]); }
+__device__ __forceinline__ int min_of(const int (&p)[3]) { return __vimin3_s32(p[0], p[1], p[2]); }
+__device__ __forceinline__ int min_of(const int (&p)[4]) { return min(__vimin3_s32(p[0], p[1], p[2]), p[3]); }
+
+// One block of up to 32 queries (in w->q2 / w->meta) against the E entries each lane holds (nv of them real; the others are
+// all-ones words, whose distance to any query is at least 16).  The residual encoding keeps bit 0 of the 16 kept positions in
+// its low half and bit 1 in its high half (ref src/lshf.cpp:64-69), so the mismatch mask is (e.lo ^ q.lo) | (e.hi ^ q.hi): with
+// both halves of entries and queries split once, a comparison is two LOP3 and one POPC.  Two queries per trip; per query the
+// minimum over the lane's entries is what is tested, so the loop carries one ISETP per query and one vote per trip.  Hits are
+// rare per comparison (a few per thousand) but not per trip (96 entries x 2 queries), so what follows a vote is kept short:
+// one more vote per query, and only for a query with a hit the E comparisons again, each compacted into the warp's queue by
+// ballot (the queue length lives in a register; no shared-memory atomics).
 template <int E, bool COUNT>
 __device__ __forceinline__ void join_block(JoinWarpSmem* w, const SortArgs& s, uint32_t* counters, const uint32_t (&elo)[4], const uint32_t (&ehi)[4],
-                                           const uint32_t (&se)[4], const int (&thr)[4], uint32_t cnt)
+                                           const uint32_t (&se)[4], uint32_t nv, uint32_t cnt, int th, uint32_t& hq_n)
 {
-  for (uint32_t j = 0; j < cnt; ++j) {
-    const uint2 qq = *reinterpret_cast<const uint2*>(&w->qs[j]); // {q.lo, q.hi}
-    int hd[E];
-    bool any = false;
+  const uint32_t lane = threadIdx.x & 31, lt_mask = (1u << lane) - 1u;
+  for (uint32_t j = 0; j < cnt; j += 2) {
+    const uint4 qq = *reinterpret_cast<const uint4*>(&w->q2[j]); // {q[j].lo, q[j].hi, q[j+1].lo, q[j+1].hi}
+    int p0[E], p1[E];
 #pragma unroll
     for (int e = 0; e < E; ++e) {
-      hd[e] = __popc((elo[e] ^ qq.x) | (ehi[e] ^ qq.y));
-      any |= hd[e] <= thr[e];
+      p0[e] = __popc((elo[e] ^ qq.x) | (ehi[e] ^ qq.y));
+      p1[e] = __popc((elo[e] ^ qq.z) | (ehi[e] ^ qq.w));
     }
-    if (__any_sync(0xFFFFFFFFu, any)) {
-      if (any) {
-        const uint4 t = w->qs[j];
-        const uint32_t meta = (t.w & 0x80000000u) | ((t.w & (kMaxLoc - 1u)) << 5);
+    const bool h0 = min_of(p0) <= th, h1 = min_of(p1) <= th;
+    if (__any_sync(0xFFFFFFFFu, h0 | h1)) {
 #pragma unroll
-        for (int e = 0; e < E; ++e)
-          if (hd[e] <= thr[e]) {
-            const uint32_t at = atomicAdd(&w->hq_n, 1u);
-            w->hq[at] = make_uint4(t.z, meta | (uint32_t)hd[e], se[e], 0u);
-            if (COUNT) atomicAdd(&s.hit_count[t.z], 1u);
+      for (int q = 0; q < 2; ++q) {
+        if (j + q < cnt && __any_sync(0xFFFFFFFFu, q ? h1 : h0)) {
+          const uint2 mt = w->meta[j + q];
+          const uint32_t qlo = q ? qq.z : qq.x, qhi = q ? qq.w : qq.y;
+          uint32_t total = 0;
+#pragma unroll
+          for (int e = 0; e < E; ++e) {
+            const int hd = __popc((elo[e] ^ qlo) | (ehi[e] ^ qhi));
+            const bool hit = hd <= th && (uint32_t)e < nv;
+            const uint32_t bm = __ballot_sync(0xFFFFFFFFu, hit);
+            if (bm) {
+              if (hit) w->hq[hq_n + __popc(bm & lt_mask)] = make_uint4(mt.x, mt.y | (uint32_t)hd, se[e], 0u);
+              hq_n += __popc(bm); total += __popc(bm);
+              if (hq_n > (uint32_t)(kHitQ - 32)) { join_flush(w, s, counters, hq_n); hq_n = 0; }
+            }
           }
+          if (COUNT && total && lane == 0) atomicAdd(&s.hit_count[mt.x], total);
+        }
       }
-      __syncwarp();
-      if (*reinterpret_cast<volatile uint32_t*>(&w->hq_n) > (uint32_t)(kHitQ - kJoinChunk)) join_flush(w, s, counters);
     }
   }
 }
@@ -255,15 +270,14 @@ __device__ __forceinline__ void join_block(JoinWarpSmem* w, const SortArgs& s, u
 // shard and the queries another rank's (SURVEY.md 8e mode B): s.row_begin is then the sender's slice for these rows, still
 // holding positions in the sender's list, so everything is taken relative to its first element.
 template <bool COUNT>
-__global__ void __launch_bounds__(kJoinWarps * 32) join_kernel(const DevIndex ix, const SortArgs s, uint32_t th, uint32_t* counters, unsigned long long* stats)
+__global__ void __launch_bounds__(kJoinWarps * 32, 5) join_kernel(const DevIndex ix, const SortArgs s, uint32_t th, uint32_t* counters, unsigned long long* stats)
 {
   __shared__ JoinWarpSmem jsm[kJoinWarps];
   const uint32_t rb0 = s.row_begin[0];
   if (s.row_begin[s.nrows] - rb0 > s.cap_lookups) return; // flagged by the lookup kernel
   const uint32_t lane = threadIdx.x & 31;
   JoinWarpSmem* w = &jsm[threadIdx.x >> 5];
-  if (lane == 0) w->hq_n = 0;
-  __syncwarp();
+  uint32_t hq_n = 0; // entries in the warp's hit queue (warp-uniform)
   unsigned long long st_entries = 0;
   for (;;) {
     uint32_t r0 = 0;
@@ -284,31 +298,34 @@ __global__ void __launch_bounds__(kJoinWarps * 32) join_kernel(const DevIndex ix
       const uint32_t rqb = __shfl_sync(0xFFFFFFFFu, qb, src), nq = __shfl_sync(0xFFFFFFFFu, qe, src) - rqb;
       const uint32_t reb = __shfl_sync(0xFFFFFFFFu, eb, src), ne = __shfl_sync(0xFFFFFFFFu, ee, src) - reb;
       for (uint32_t c = 0; c < ne; c += kJoinChunk) {
-        uint32_t elo[4], ehi[4], se[4];
-        int thr[4];
+        uint32_t elo[4], ehi[4], se[4], nv = 0;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const uint32_t i = c + 32 * e + lane;
-          elo[e] = 0; ehi[e] = 0; se[e] = 0; thr[e] = -1;
-          if (i < ne) { const uint2 v = __ldg(&ix.cmer[(size_t)reb + i]); elo[e] = v.x & 0xFFFFu; ehi[e] = v.x >> 16; se[e] = v.y; thr[e] = (int)th; }
+          elo[e] = 0xFFFFFFFFu; ehi[e] = 0xFFFFFFFFu; se[e] = 0;
+          if (i < ne) { const uint2 v = __ldg(&ix.cmer[(size_t)reb + i]); elo[e] = v.x & 0xFFFFu; ehi[e] = v.x >> 16; se[e] = v.y; nv = e + 1; }
         }
         const uint32_t E = min(4u, (ne - c + 31u) >> 5);
         for (uint32_t q0 = 0; q0 < nq; q0 += 32) {
           const uint32_t cnt = min(32u, nq - q0);
           __syncwarp();
-          if (lane < cnt) { const uint4 t = s.tuples[rqb + q0 + lane]; w->qs[lane] = make_uint4(t.x & 0xFFFFu, t.x >> 16, t.y, t.z); } // {q.lo, q.hi, read, lookup}
+          if (lane < cnt) {
+            const uint4 t = s.tuples[rqb + q0 + lane]; // {q, read, local lookup index | strand << 31, 0}
+            w->q2[lane] = make_uint2(t.x & 0xFFFFu, t.x >> 16);
+            w->meta[lane] = make_uint2(t.y, (t.z & 0x80000000u) | ((t.z & (kMaxLoc - 1u)) << 5));
+          } else if (lane == cnt) w->q2[lane] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu); // the odd query's partner: at distance >= 16 of everything
           __syncwarp();
           switch (E) {
-            case 1: join_block<1, COUNT>(w, s, counters, elo, ehi, se, thr, cnt); break;
-            case 2: join_block<2, COUNT>(w, s, counters, elo, ehi, se, thr, cnt); break;
-            case 3: join_block<3, COUNT>(w, s, counters, elo, ehi, se, thr, cnt); break;
-            default: join_block<4, COUNT>(w, s, counters, elo, ehi, se, thr, cnt); break;
+            case 1: join_block<1, COUNT>(w, s, counters, elo, ehi, se, nv, cnt, (int)th, hq_n); break;
+            case 2: join_block<2, COUNT>(w, s, counters, elo, ehi, se, nv, cnt, (int)th, hq_n); break;
+            case 3: join_block<3, COUNT>(w, s, counters, elo, ehi, se, nv, cnt, (int)th, hq_n); break;
+            default: join_block<4, COUNT>(w, s, counters, elo, ehi, se, nv, cnt, (int)th, hq_n); break;
           }
         }
       }
     }
   }
-  join_flush(w, s, counters);
+  join_flush(w, s, counters, hq_n);
   for (int o = 16; o; o >>= 1) st_entries += __shfl_xor_sync(0xFFFFFFFFu, st_entries, o);
   if (lane == 0 && st_entries) { atomicAdd(stats, 8ull * st_entries); atomicAdd(stats + 2, st_entries); }
 }
