@@ -262,6 +262,7 @@ struct krepp_batch {
   krepp_placement_t *d_place = nullptr, *h_place = nullptr;
   // bucket-sorted pipeline (sorted.cu)
   bool sorted = false, fused_once = false;
+  bool bins_off = false;      // a batch overflowed a coarse bin of the two-level lookup sort: this slot keeps to the two-pass sort
   SortArgs so{};
   uint32_t* h_sc = nullptr;   // [0..7] copy of so.sc, [8] lookups of the batch, [9] hit entries handed to finish, [16..] mode B row/hit boundaries
   const void* shard_hits = nullptr; uint64_t shard_n_hits = 0; // mode B: the batch is in its finish phase (krepp_shard_finish)
@@ -521,6 +522,23 @@ static int alloc_tuples(krepp_batch* b, uint64_t cap)
   if (b->so.tuples) cudaFree(b->so.tuples);
   b->so.tuples = nullptr; b->so.cap_lookups = (uint32_t)cap;
   CU(cudaMalloc(&b->so.tuples, 16ull * cap));
+  // coarse bins of the two-level lookup sort (sorted.cu lookup_partition_kernel): at most 1,024 bins of a power-of-two number of
+  // rows, each with room for a quarter more than an even share of the lookups.  KREPP_LOOKUP=two_pass keeps the two-pass sort.
+  if (b->so.binned) cudaFree(b->so.binned);
+  b->so.binned = nullptr; b->so.nbins = 0;
+  const HostIndex& h = b->ix->host;
+  const char* env = getenv("KREPP_LOOKUP");
+  uint32_t shift = 0;
+  while ((((uint64_t)h.nrows - 1) >> shift) + 1 > 1024) ++shift;
+  if (!(env && !strcmp(env, "two_pass")) && !b->bins_off && h.nrows && (1u << shift) <= 8192u) {
+    const uint32_t nbins = (uint32_t)((((uint64_t)h.nrows - 1) >> shift) + 1);
+    const uint64_t per = ((cap + cap / 4) / nbins + 64 + 3) / 4 * 4;
+    if (per < (1ull << 31)) {
+      if (!b->so.bin_cursor) CU(cudaMalloc(&b->so.bin_cursor, 4ull * 1024));
+      CU(cudaMalloc(&b->so.binned, 16ull * per * nbins));
+      b->so.nbins = nbins; b->so.bin_cap = (uint32_t)per; b->so.bin_shift = shift;
+    }
+  }
   return KREPP_OK;
 }
 
@@ -679,7 +697,7 @@ void krepp_batch_destroy(krepp_batch_t* b)
                   (void*)b->d_pn_se, (void*)b->d_pn_flags, (void*)b->d_pn_work, (void*)b->d_pn_mc, (void*)b->d_pn_uc, (void*)b->d_pn_rho, (void*)b->d_pn_d,
                   (void*)b->d_pn_v, (void*)b->d_pn_chisq, (void*)b->d_place})
     if (p) cudaFree(p);
-  for (void* p : {(void*)b->so.row_count, (void*)b->so.row_begin, (void*)b->so.row_cursor, (void*)b->so.tuples, (void*)b->so.hits_tmp, (void*)b->so.hits,
+  for (void* p : {(void*)b->so.binned, (void*)b->so.bin_cursor, (void*)b->so.row_count, (void*)b->so.row_begin, (void*)b->so.row_cursor, (void*)b->so.tuples, (void*)b->so.hits_tmp, (void*)b->so.hits,
                   (void*)b->so.hit_count, (void*)b->so.hit_begin, (void*)b->so.hit_cursor, (void*)b->so.partials, (void*)b->so.sc, (void*)b->so.keys_g})
     if (p) cudaFree(p);
   if (b->h_sc) cudaFreeHost(b->h_sc);
@@ -896,7 +914,7 @@ static int wait_impl(krepp_batch_t* b, krepp_results_t* out, uint32_t rows)
     if (b->shard_hits && (b->h_counters[2] & kErrSortFallback))
       return fail(KREPP_ERR_CAPACITY, "a read has 2^26 or more lookups, which the bucket-sorted chain cannot index, and a sharded index has no fused kernel to fall back to");
     if (b->h_counters[2] & kErrHitWrap) return fail(KREPP_ERR_CAPACITY, "batch produces 2^32 or more hit entries; submit fewer reads per batch");
-    if (!(b->h_counters[2] & (kErrRecOverflow | kErrPlaceOverflow | kErrNodeOverflow | kErrLookupOverflow | kErrHitOverflow | kErrSortFallback | kErrKeysOverflow))) break;
+    if (!(b->h_counters[2] & (kErrRecOverflow | kErrPlaceOverflow | kErrNodeOverflow | kErrLookupOverflow | kErrHitOverflow | kErrSortFallback | kErrKeysOverflow | kErrBinOverflow))) break;
     // a result buffer was too small: grow it to what the kernels asked for and run the batch again
     if (attempt >= 8) return fail(KREPP_ERR_CAPACITY, "result buffer overflow persists");
     if (b->h_counters[2] & kErrRecOverflow) {
@@ -904,6 +922,7 @@ static int wait_impl(krepp_batch_t* b, krepp_results_t* out, uint32_t rows)
       if (want > 0x7FFFFFFFull) return fail(KREPP_ERR_CAPACITY, "batch produces too many records; submit fewer reads per batch");
       if (int rc = alloc_records(b, (uint32_t)want)) return rc;
     }
+    if (b->h_counters[2] & kErrBinOverflow) { b->bins_off = true; b->so.nbins = 0; } // lookups piled on few rows: the two-pass sort sizes every row exactly
     if (b->h_counters[2] & kErrLookupOverflow) { // the batch's lookup list: exact demand + 10 %
       const uint64_t need = b->h_sc[8];
       if (int rc = alloc_tuples(b, need + need / 10 + 4096)) return rc;
@@ -993,11 +1012,19 @@ int krepp_shard_lookup(krepp_batch_t* b, const char* d_bases, const uint64_t* d_
   so.tuples = static_cast<uint4*>(d_tuples); so.cap_lookups = (uint32_t)std::min<uint64_t>(cap_tuples, 0xFFFFFFF0ull); so.row_begin = d_row_begin;
   CU(cudaEventRecord(b->ev0, s));
   b->clk.n = 0; b->clk.tick("start", s);
-  CU(launch_shard_lookup(b->ix->dev, m, so, b->ix->sms, b->d_tap != nullptr, s, &b->clk));
   uint32_t* hb = b->h_sc + 16;
-  for (uint32_t g = 0; g <= h.nshards; ++g) CU(cudaMemcpyAsync(hb + g, d_row_begin + h.row_splits[g], 4, cudaMemcpyDeviceToHost, s));
-  CU(cudaMemcpyAsync(b->h_counters, b->d_counters, 32, cudaMemcpyDeviceToHost, s));
-  CU(cudaStreamSynchronize(s));
+  for (;;) {
+    CU(launch_shard_lookup(b->ix->dev, m, so, b->ix->sms, b->d_tap != nullptr, s, &b->clk));
+    for (uint32_t g = 0; g <= h.nshards; ++g) CU(cudaMemcpyAsync(hb + g, d_row_begin + h.row_splits[g], 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(b->h_counters, b->d_counters, 32, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (!(b->h_counters[2] & kErrBinOverflow)) break;
+    b->bins_off = true; b->so.nbins = 0; so.nbins = 0; // lookups piled on few rows: again with the two-pass sort
+    CU(cudaMemsetAsync(b->d_counters, 0, 32, s));
+    CU(cudaMemsetAsync(b->d_stats, 0, 32, s));
+    if (b->d_tap_count) CU(cudaMemsetAsync(b->d_tap_count, 0, 8, s));
+    b->clk.n = 0; b->clk.tick("start", s);
+  }
   for (uint32_t g = 0; g <= h.nshards; ++g) send_offsets[g] = hb[g];
   if (b->h_counters[2] & kErrSortFallback) return fail(KREPP_ERR_CAPACITY, "a read has more lookups than the bucket-sorted chain holds");
   if (b->h_counters[2] & kErrLookupOverflow) return fail(KREPP_ERR_CAPACITY, "the batch has %llu lookups but the tuple buffer holds %llu", (unsigned long long)hb[h.nshards], (unsigned long long)cap_tuples);

@@ -88,9 +88,14 @@ struct SortArgs {
   uint32_t* hit_cursor;   // [n_reads]
   uint32_t* partials;     // scan scratch
   uint32_t* sc;           // [0] hit entries appended, [1] next row to claim, [2] next read to claim (lookup pass 1), [3] (pass 2), [4] (resolve),
-                          // [5] most leaf hits of one read that did not fit keys_g (the host grows it to that)
+                          // [5] most leaf hits of one read that did not fit keys_g (the host grows it to that), [6] next bin to claim (bin sort)
   uint64_t* keys_g;       // [warps][cap_keys_g] per-warp sort scratch in HBM for reads whose leaf hits exceed shared memory
   uint32_t cap_keys_g;
+  // two-level sort of the lookups (lookup_partition_kernel -> bin_sort_kernel): coarse bins of 2^bin_shift rows, each with room
+  // for bin_cap tuples {q, read, local lookup index | strand << 31, row}; nbins = 0 switches the path off
+  uint4* binned;          // [nbins * bin_cap]
+  uint32_t* bin_cursor;   // [nbins] tuples appended to every bin
+  uint32_t nbins, bin_cap, bin_shift;
   uint32_t res_ctas;      // CTAs of the resolve kernel (keys_g holds res_ctas * warps per CTA regions); 0 = the default grid
   uint32_t extra_rank_bits; // test knob (KREPP_SORT_WIDE): widens the leaf field of the sort keys so that the 64-bit key path runs
 };
@@ -100,8 +105,9 @@ constexpr uint32_t kErrLookupOverflow = 8u, kErrHitOverflow = 16u, kErrSortFallb
 constexpr uint32_t kErrNodeOverflow = 128u; // placement: the batch touches more tree nodes than PlaceArgs::node_cap
 constexpr uint32_t kErrKeysOverflow = 256u; // sorted pipeline: a read has more leaf hits than a warp's sort scratch (SortArgs::keys_g): grown by the host
 constexpr uint32_t kErrHitWrap = 512u;      // sorted pipeline: 2^32 or more hit entries in one batch
+constexpr uint32_t kErrBinOverflow = 1024u; // sorted pipeline: a coarse bin of the two-level lookup sort is full (skewed rows): the batch re-runs with the two-pass counting sort
 constexpr uint32_t kErrShardData = 64u; // mode B: a hit entry names a read outside the batch (the caller mixed up its exchange buffers)
-constexpr uint32_t kErrRedo = kErrRecOverflow | kErrStackOverflow | kErrLookupOverflow | kErrHitOverflow | kErrSortFallback | kErrShardData | kErrKeysOverflow | kErrHitWrap; // records are incomplete: later kernels skip, the host re-runs the batch
+constexpr uint32_t kErrRedo = kErrRecOverflow | kErrStackOverflow | kErrLookupOverflow | kErrHitOverflow | kErrSortFallback | kErrShardData | kErrKeysOverflow | kErrHitWrap | kErrBinOverflow; // records are incomplete: later kernels skip, the host re-runs the batch
 
 struct SolveArgs {
   uint32_t n_reads, th, k, h;

@@ -20,6 +20,14 @@ struct WarpSmem {
   uint32_t valid[kTileWords / 2 + 1];
   uint32_t cursor;
 };
+// The same without the bucket fields: what the bucket-sorted pipeline's lookup kernels need per warp.
+struct WarpSmemLite {
+  uint32_t lk_a[kMaxLookups];  // row offset | strand<<31
+  uint32_t lk_q[kMaxLookups];  // residual encoding q of the query k-mer
+  uint32_t code[kTileWords + 1];
+  uint32_t valid[kTileWords / 2 + 1];
+  uint32_t cursor;
+};
 // LUT layout: [byte of the k-mer word][byte value] -> {rix fwd, q fwd, rix rc, q rc} parts; 7 bytes cover k <= 28
 // lut_pext always reads the first seven byte tables, so at least seven are staged (all-zero past the k-mer's last byte)
 __host__ __device__ inline uint32_t lut_chunks(uint32_t k) { const uint32_t n = (2 * k + 7) / 8; return n < 7 ? 7 : n; }
@@ -60,8 +68,8 @@ __device__ __forceinline__ uint4 lut_pext(const uint4* lut, uint32_t lo, uint32_
 // A0 + A1 of one tile of a read (see the header): ASCII bases -> 2-bit stream in shared memory -> k-mer windows -> bucket
 // ids and residual encodings of both strands; the eligible lookups are compacted into sm.lk_a (row offset | strand << 31)
 // and sm.lk_q.  Returns their number; onmers / wn0 / wn1 are the read's running counts (warp-uniform).
-template <bool TAP>
-__device__ __forceinline__ uint32_t tile_lookups(const DevIndex& ix, const MatchArgs& a, WarpSmem& sm, const uint4* lut, bool wide, uint32_t read,
+template <bool TAP, class WS>
+__device__ __forceinline__ uint32_t tile_lookups(const DevIndex& ix, const MatchArgs& a, WS& sm, const uint4* lut, bool wide, uint32_t read,
                                                  uint64_t off, uint64_t len, uint64_t t0, uint32_t& onmers, uint32_t& wn0, uint32_t& wn1)
 {
   const uint32_t lane = threadIdx.x & 31, lt_mask = (1u << lane) - 1, k = ix.k;

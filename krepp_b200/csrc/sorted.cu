@@ -191,6 +191,189 @@ cudaError_t exclusive_scan(const uint32_t* in, uint32_t n, uint32_t* partials, u
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------- L1' / L2': two-level sort
+//
+// The two passes above sort the lookups by row with one global atomic per lookup per pass; the second pass needs the value the
+// atomic returns, and an SM can keep only so many of those in flight (it runs at a third of the speed of the first pass, which
+// does the same work with fire-and-forget reductions).  The two-level form computes every lookup ONCE and needs no per-lookup
+// global atomic:
+//
+//   L1' lookup_partition_kernel  one CTA of 32 warps per SM.  A round = every warp turns one tile of a read into lookups (in its
+//                                own shared-memory segment), then the CTA appends the round's lookups to at most 1,024 coarse bins
+//                                (2^bin_shift rows each): arrivals are counted per bin with shared-memory atomics, joined to the few
+//                                tuples the bin still holds from earlier rounds, and leave for the bin's region in HBM in whole
+//                                64-byte lines at a position taken with ONE global atomic per bin per round; the remainder (fewer
+//                                than a line) waits in shared memory for the next round.
+//   L2' bin_sort_kernel          CTA per bin: counting sort of the bin's tuples by row through shared-memory counters (histogram,
+//                                scan, scatter with shared-memory cursors) into the dense row-grouped list, and the rows' ranges --
+//                                exactly what the two-pass form leaves for the join (and, in mode B, for the exchange).
+//
+// Bins have room for a quarter more than an even share of the batch's lookups; reads that pile their lookups on few rows
+// (low-complexity input) can overflow one, which is flagged -- the host then runs the batch through the two-pass form.
+
+constexpr int kLpWarps = 32;
+constexpr int kLpBinsMax = 1024;
+constexpr int kLpLine = 4;             // tuples per line sent to a bin (64 bytes)
+constexpr int kBsThreads = 256;
+constexpr uint32_t kBsRowsMax = 8192;  // rows per bin the bin sort's shared-memory counters hold
+
+struct LpShared {
+  WarpSmemLite w[kLpWarps];
+  uint4 stage[kLpBinsMax][kLpLine];    // per bin: tuples waiting for a full line
+  uint32_t cnt[kLpBinsMax];            // arrivals of the round, then the cursor that ranks them
+  uint32_t left[kLpBinsMax];           // tuples waiting in stage[]
+  uint32_t gbase[kLpBinsMax];          // where the bin's lines of this round start in its region
+  uint32_t lim[kLpBinsMax];            // tuples of this round's lines (a multiple of kLpLine)
+  uint32_t nl[kLpWarps], rd[kLpWarps], locb[kLpWarps];
+};
+
+template <bool TAP>
+__global__ void __launch_bounds__(kLpWarps * 32, 1) lookup_partition_kernel(const DevIndex ix, const MatchArgs a, const SortArgs s)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const uint32_t nchunks = lut_chunks(ix.k);
+  uint4* lut = reinterpret_cast<uint4*>(smem_raw);
+  LpShared& sh = *reinterpret_cast<LpShared*>(smem_raw + nchunks * 256 * sizeof(uint4));
+  for (uint32_t i = threadIdx.x; i < nchunks * 256; i += blockDim.x) lut[i] = ix.lut[i];
+  for (uint32_t b = threadIdx.x; b < (uint32_t)kLpBinsMax; b += blockDim.x) { sh.cnt[b] = 0; sh.left[b] = 0; }
+  __syncthreads();
+  const bool wide = nchunks > 7;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, k = ix.k;
+  WarpSmemLite& sm = sh.w[warp];
+  unsigned long long st_bytes = 0, st_lookups = 0;
+  uint32_t claim = 0, claim_end = 0;
+  bool have = false, exhausted = false;
+  uint32_t read = 0, onmers = 0, wn0 = 0, wn1 = 0, loc = 0;
+  uint64_t off = 0, len = 0, t0 = 0;
+  for (;;) {
+    // ---- every warp: the next tile of its read (a read shorter than k has none and is finished at once)
+    while (!have && !exhausted) {
+      if (claim == claim_end) {
+        if (lane == 0) claim = atomicAdd(s.sc + 2, kLkClaim);
+        claim = __shfl_sync(0xFFFFFFFFu, claim, 0);
+        claim_end = min(claim + kLkClaim, a.n_reads);
+        if (claim >= a.n_reads) { exhausted = true; break; }
+      }
+      read = claim++;
+      off = a.offsets[read];
+      len = a.offsets[read + 1] - off;
+      onmers = wn0 = wn1 = loc = 0; t0 = 0;
+      if (len >= k) have = true;
+      else if (lane == 0) { a.onmers[read] = 0; a.wn[2 * read] = 0; a.wn[2 * read + 1] = 0; st_bytes += len; }
+    }
+    uint32_t nlk = 0;
+    const bool did = have;
+    if (have) {
+      nlk = tile_lookups<TAP>(ix, a, sm, lut, wide, read, off, len, t0, onmers, wn0, wn1);
+      if (loc + nlk >= kMaxLoc) { if (lane == 0) atomicOr(a.counters + 2, kErrSortFallback); nlk = 0; t0 = len; } // the read cannot be indexed: the host redoes the batch
+      if (lane == 0) { sh.nl[warp] = nlk; sh.rd[warp] = read; sh.locb[warp] = loc; }
+      loc += nlk;
+      t0 += kTileWindows;
+      if (t0 + k > len) { // the read is finished
+        if (lane == 0) { a.onmers[read] = onmers; a.wn[2 * read] = wn0; a.wn[2 * read + 1] = wn1; st_bytes += len; st_lookups += wn0 + wn1; }
+        have = false;
+      }
+    } else if (lane == 0) sh.nl[warp] = 0;
+    if (!__syncthreads_or(did ? 1 : 0)) break; // no warp had a tile: all reads are done
+    // ---- a. arrivals per bin
+    for (uint32_t slot = threadIdx.x; slot < (uint32_t)(kLpWarps * kMaxLookups); slot += blockDim.x) {
+      const uint32_t w = slot / kMaxLookups, i = slot % kMaxLookups;
+      if (i < sh.nl[w]) atomicAdd(&sh.cnt[(sh.w[w].lk_a[i] & 0x7FFFFFFFu) >> s.bin_shift], 1u);
+    }
+    __syncthreads();
+    // ---- b. per bin: whole lines leave; their place in the bin's region; the tuples that waited go first
+    for (uint32_t b = threadIdx.x; b < s.nbins; b += blockDim.x) {
+      const uint32_t l = sh.left[b], t = l + sh.cnt[b], out = t - t % kLpLine;
+      uint32_t g = 0;
+      if (out) {
+        g = atomicAdd(&s.bin_cursor[b], out);
+        if ((uint64_t)g + out > s.bin_cap) atomicOr(a.counters + 2, kErrBinOverflow);
+        uint4* dst = s.binned + (size_t)b * s.bin_cap;
+        for (uint32_t i = 0; i < l; ++i) if (g + i < s.bin_cap) dst[g + i] = sh.stage[b][i];
+      }
+      sh.gbase[b] = g; sh.lim[b] = out; sh.cnt[b] = l; sh.left[b] = t - out;
+    }
+    __syncthreads();
+    // ---- c. every arrival takes its rank in its bin: into one of the bin's lines, or into the waiting slots
+    for (uint32_t slot = threadIdx.x; slot < (uint32_t)(kLpWarps * kMaxLookups); slot += blockDim.x) {
+      const uint32_t w = slot / kMaxLookups, i = slot % kMaxLookups;
+      if (i < sh.nl[w]) {
+        const uint32_t ob = sh.w[w].lk_a[i], row = ob & 0x7FFFFFFFu, b = row >> s.bin_shift;
+        const uint4 tup = make_uint4(sh.w[w].lk_q[i], sh.rd[w], (sh.locb[w] + i) | (ob & 0x80000000u), row);
+        const uint32_t c = atomicAdd(&sh.cnt[b], 1u), lim = sh.lim[b];
+        if (c < lim) { const uint32_t g = sh.gbase[b] + c; if (g < s.bin_cap) s.binned[(size_t)b * s.bin_cap + g] = tup; }
+        else sh.stage[b][c - lim] = tup;
+      }
+    }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < s.nbins; b += blockDim.x) sh.cnt[b] = 0;
+    // (the next use of cnt[] lies behind the barrier that follows the next round's tiles)
+  }
+  // ---- the tuples still waiting leave as short lines
+  for (uint32_t b = threadIdx.x; b < s.nbins; b += blockDim.x) {
+    const uint32_t l = sh.left[b];
+    if (!l) continue;
+    const uint32_t g = atomicAdd(&s.bin_cursor[b], l);
+    if ((uint64_t)g + l > s.bin_cap) atomicOr(a.counters + 2, kErrBinOverflow);
+    uint4* dst = s.binned + (size_t)b * s.bin_cap;
+    for (uint32_t i = 0; i < l; ++i) if (g + i < s.bin_cap) dst[g + i] = sh.stage[b][i];
+  }
+  if (lane == 0 && (st_bytes | st_lookups)) { atomicAdd(a.stats, st_bytes + 16ull * st_lookups); atomicAdd(a.stats + 1, st_lookups); }
+}
+
+__global__ void __launch_bounds__(kBsThreads) bin_sort_kernel(const SortArgs s, uint32_t* counters)
+{
+  extern __shared__ uint32_t bs_smem[];
+  uint32_t* hist = bs_smem;                              // [rows per bin] counts, then cursors
+  uint32_t* bin_begin = bs_smem + (1u << s.bin_shift);   // [nbins + 1] exclusive prefix of the bin sizes
+  __shared__ uint32_t warp_sums[kBsThreads / 32];
+  __shared__ uint32_t claimed;
+  const uint32_t tid = threadIdx.x, rows_per_bin = 1u << s.bin_shift;
+  if (counters[2] & kErrRedo) return;
+  { // every CTA scans the (at most 1,024) bin sizes itself
+    const uint32_t per = (s.nbins + kBsThreads - 1) / kBsThreads, lo = min(tid * per, s.nbins), hi = min(lo + per, s.nbins);
+    uint32_t sum = 0;
+    for (uint32_t b = lo; b < hi; ++b) sum += s.bin_cursor[b];
+    uint32_t total;
+    uint32_t run = block_exclusive_scan(sum, warp_sums, total);
+    for (uint32_t b = lo; b < hi; ++b) { bin_begin[b] = run; run += s.bin_cursor[b]; }
+    if (tid == 0) bin_begin[s.nbins] = total;
+    __syncthreads();
+    if (total > s.cap_lookups) { // the dense list does not fit: the host grows it (s.row_begin[nrows] is the demand) and runs the batch again
+      if (blockIdx.x == 0 && tid == 0) { s.row_begin[s.nrows] = total; atomicOr(counters + 2, kErrLookupOverflow); }
+      return;
+    }
+  }
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) claimed = atomicAdd(s.sc + 6, 1u);
+    __syncthreads();
+    const uint32_t b = claimed;
+    if (b >= s.nbins) break;
+    const uint32_t n = s.bin_cursor[b], dst0 = bin_begin[b], row0 = b << s.bin_shift, nr = min(rows_per_bin, s.nrows - row0);
+    const uint4* src = s.binned + (size_t)b * s.bin_cap;
+    for (uint32_t r = tid; r < nr; r += kBsThreads) hist[r] = 0;
+    __syncthreads();
+    for (uint32_t i = tid; i < n; i += kBsThreads) atomicAdd(&hist[__ldg(reinterpret_cast<const uint32_t*>(src + i) + 3) - row0], 1u);
+    __syncthreads();
+    { // exclusive scan of the row counts; hist[] becomes the rows' cursors into the dense list
+      const uint32_t per = (nr + kBsThreads - 1) / kBsThreads, lo = min(tid * per, nr), hi = min(lo + per, nr);
+      uint32_t sum = 0;
+      for (uint32_t r = lo; r < hi; ++r) sum += hist[r];
+      uint32_t total;
+      uint32_t run = dst0 + block_exclusive_scan(sum, warp_sums, total);
+      for (uint32_t r = lo; r < hi; ++r) { const uint32_t c = hist[r]; hist[r] = run; s.row_begin[row0 + r] = run; run += c; }
+      if (b == s.nbins - 1 && tid == 0) s.row_begin[s.nrows] = dst0 + n;
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < n; i += kBsThreads) {
+      const uint4 t = __ldg(src + i);
+      const uint32_t pos = atomicAdd(&hist[t.w - row0], 1u);
+      s.tuples[pos] = make_uint4(t.x, t.y, t.z, 0u);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------- J: join
 
 struct __align__(16) JoinWarpSmem {
@@ -273,6 +456,7 @@ template <bool COUNT>
 __global__ void __launch_bounds__(kJoinWarps * 32, 5) join_kernel(const DevIndex ix, const SortArgs s, uint32_t th, uint32_t* counters, unsigned long long* stats)
 {
   __shared__ JoinWarpSmem jsm[kJoinWarps];
+  if (counters[2] & (kErrBinOverflow | kErrLookupOverflow | kErrSortFallback)) return; // the lookup list is incomplete: the host runs the batch again
   const uint32_t rb0 = s.row_begin[0];
   if (s.row_begin[s.nrows] - rb0 > s.cap_lookups) return; // flagged by the lookup kernel
   const uint32_t lane = threadIdx.x & 31;
@@ -663,22 +847,51 @@ static cudaError_t launch_lookup(const DevIndex& ix, const MatchArgs& a, const S
   return cudaGetLastError();
 }
 
-// Enqueues L1 .. R for one batch.  The caller has zeroed a.counters / a.stats; this zeroes the pipeline's own counters.
-cudaError_t launch_match_sorted(const DevIndex& ix, const MatchArgs& a, const SortArgs& s, int sms, bool tap, cudaStream_t stream, uint32_t* launches, StageClock* clk)
+// L1 + S1 + L2, or L1' + L2' when the slot has bins (s.nbins): leaves the lookups grouped by row in s.tuples / s.row_begin
+static cudaError_t launch_lookup_sort(const DevIndex& ix, const MatchArgs& a, const SortArgs& s, int sms, bool tap, cudaStream_t stream, StageClock* clk, uint32_t* launches)
 {
   cudaError_t e;
-  if (launches) *launches = 0;
-  if (!a.n_reads) return cudaSuccess;
+  if (s.nbins) {
+    if ((e = cudaMemsetAsync(s.bin_cursor, 0, 4ull * s.nbins, stream)) != cudaSuccess) return e;
+    const size_t sm1 = lut_chunks(ix.k) * 256 * sizeof(uint4) + sizeof(LpShared);
+    if (tap) {
+      if ((e = cudaFuncSetAttribute(lookup_partition_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1)) != cudaSuccess) return e;
+      lookup_partition_kernel<true><<<sms, kLpWarps * 32, sm1, stream>>>(ix, a, s);
+    } else {
+      if ((e = cudaFuncSetAttribute(lookup_partition_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1)) != cudaSuccess) return e;
+      lookup_partition_kernel<false><<<sms, kLpWarps * 32, sm1, stream>>>(ix, a, s);
+    }
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (clk) clk->tick("lookup_partition_kernel", stream);
+    const size_t sm2 = 4ull * ((1ull << s.bin_shift) + s.nbins + 1);
+    if ((e = cudaFuncSetAttribute(bin_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2)) != cudaSuccess) return e;
+    bin_sort_kernel<<<std::min<uint32_t>(s.nbins, (uint32_t)sms * 8u), kBsThreads, sm2, stream>>>(s, a.counters);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (clk) clk->tick("bin_sort_kernel", stream);
+    if (launches) *launches += 2;
+    return cudaSuccess;
+  }
   if ((e = cudaMemsetAsync(s.row_count, 0, 4ull * s.nrows, stream)) != cudaSuccess) return e;
-  if ((e = cudaMemsetAsync(s.hit_count, 0, 4ull * a.n_reads, stream)) != cudaSuccess) return e;
-  if ((e = cudaMemsetAsync(s.sc, 0, 32, stream)) != cudaSuccess) return e;
-  if (clk) clk->tick("memsets", stream);
   if ((e = launch_lookup<false>(ix, a, s, sms, tap, stream)) != cudaSuccess) return e;
   if (clk) clk->tick("lookup_kernel<count>", stream);
   if ((e = exclusive_scan(s.row_count, s.nrows, s.partials, s.row_begin, s.row_cursor, stream)) != cudaSuccess) return e;
   if (clk) clk->tick("scan(rows)", stream);
   if ((e = launch_lookup<true>(ix, a, s, sms, false, stream)) != cudaSuccess) return e;
   if (clk) clk->tick("lookup_kernel<scatter>", stream);
+  if (launches) *launches += 5;
+  return cudaSuccess;
+}
+
+// Enqueues L1 .. R for one batch.  The caller has zeroed a.counters / a.stats; this zeroes the pipeline's own counters.
+cudaError_t launch_match_sorted(const DevIndex& ix, const MatchArgs& a, const SortArgs& s, int sms, bool tap, cudaStream_t stream, uint32_t* launches, StageClock* clk)
+{
+  cudaError_t e;
+  if (launches) *launches = 0;
+  if (!a.n_reads) return cudaSuccess;
+  if ((e = cudaMemsetAsync(s.hit_count, 0, 4ull * a.n_reads, stream)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(s.sc, 0, 32, stream)) != cudaSuccess) return e;
+  if (clk) clk->tick("memsets", stream);
+  if ((e = launch_lookup_sort(ix, a, s, sms, tap, stream, clk, launches)) != cudaSuccess) return e;
   join_kernel<true><<<sms * env_int("KREPP_JOIN_CTAS", 8), kJoinWarps * 32, 0, stream>>>(ix, s, a.th, a.counters, a.stats);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   if (clk) clk->tick("join_kernel", stream);
@@ -692,7 +905,7 @@ cudaError_t launch_match_sorted(const DevIndex& ix, const MatchArgs& a, const So
   resolve_kernel<<<resolve_grid(s, sms), kResWarps * 32, 0, stream>>>(ix, a, s, rank_bits);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   if (clk) clk->tick("resolve_kernel", stream);
-  if (launches) *launches = 11;
+  if (launches) *launches += 6;
   return cudaSuccess;
 }
 
@@ -706,16 +919,9 @@ cudaError_t launch_match_sorted(const DevIndex& ix, const MatchArgs& a, const So
 cudaError_t launch_shard_lookup(const DevIndex& ix, const MatchArgs& a, const SortArgs& s, int sms, bool tap, cudaStream_t stream, StageClock* clk)
 {
   cudaError_t e;
-  if ((e = cudaMemsetAsync(s.row_count, 0, 4ull * s.nrows, stream)) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(s.sc, 0, 32, stream)) != cudaSuccess) return e;
   if (!a.n_reads) return cudaMemsetAsync(s.row_begin, 0, 4ull * (s.nrows + 1), stream);
-  if ((e = launch_lookup<false>(ix, a, s, sms, tap, stream)) != cudaSuccess) return e;
-  if (clk) clk->tick("lookup_kernel<count>", stream);
-  if ((e = exclusive_scan(s.row_count, s.nrows, s.partials, s.row_begin, s.row_cursor, stream)) != cudaSuccess) return e;
-  if (clk) clk->tick("scan(rows)", stream);
-  if ((e = launch_lookup<true>(ix, a, s, sms, false, stream)) != cudaSuccess) return e;
-  if (clk) clk->tick("lookup_kernel<scatter>", stream);
-  return cudaSuccess;
+  return launch_lookup_sort(ix, a, s, sms, tap, stream, clk, nullptr);
 }
 
 // s.row_begin / s.tuples: one sender's slice for this shard's rows; s.nrows = rows of the shard; s.sc[0] keeps counting hits

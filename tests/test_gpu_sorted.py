@@ -42,9 +42,13 @@ def test_sorted_golden_small_index(sorted_pipeline):
 
 
 @needs_ref
-def test_sorted_toy_query_and_20k(env, sorted_pipeline):
+@pytest.mark.parametrize("lookup", ["binned", "two_pass"])
+def test_sorted_toy_query_and_20k(env, sorted_pipeline, monkeypatch, lookup):
+    """Both forms of the lookup sort: the two-level one (lookup_partition_kernel + bin_sort_kernel, the default) and the two-pass
+    counting sort it falls back to (KREPP_LOOKUP=two_pass)."""
     import synth
     from gpu_common import run_and_compare
+    monkeypatch.setenv("KREPP_LOOKUP", lookup)
     names, reads = fastq_reads(os.path.join(TOY_DIR, "query_toy.fq"))
     st = run_and_compare(env["dir"], reads, env["oracle"], env["gpu"])
     assert st["reads"] == 100 and st["solves"] > 100
@@ -129,3 +133,29 @@ def test_sorted_equals_fused_bit_for_bit(env, monkeypatch):
         assert np.array_equal(f["hist"][fb:fb + n], s["hist"][sb:sb + n]), (i, "hist")
         fc, sc = int(f["reads"]["closest"][i]), int(s["reads"]["closest"][i])
         assert (fc < 0 and sc < 0) or fc - fb == sc - sb, (i, "closest")
+
+
+@needs_ref
+def test_sorted_skewed_rows_fall_back_to_two_pass(env, sorted_pipeline):
+    """Reads that pile their lookups on a few rows (a thousand copies of poly-A, poly-AC and one genomic read among ordinary
+    reads) overflow a coarse bin of the two-level lookup sort; the batch is redone with the exact two-pass sort and the slot stays
+    on it: same records as the oracle either way, before and after."""
+    import krepp_b200
+    import synth
+    from gpu_common import run_and_compare
+    seq, offs = synth.load_packed(os.path.join(TOY_DIR, "genomes.npz"))
+    normal = [r.tobytes() for r in synth.sample_reads(seq, offs, 600, seed=17)]
+    skew = [b"A" * 150] * 1000 + [b"AC" * 75] * 1000 + [normal[0]] * 1500
+    run_and_compare(env["dir"], normal + skew, env["oracle"], env["gpu"])
+    b = krepp_b200.IBatch(env["gpu"], normal + skew)
+    b.submit(); b.wait()
+    assert "lookup_kernel<scatter>" in [n for n, _ in b.stage_times()]       # the two-pass form ran ...
+    b.bases, b.offsets = krepp_b200.capi.pack_reads(normal)
+    b.n_reads = len(normal)
+    b.submit(); r = b.wait()
+    assert "lookup_kernel<scatter>" in [n for n, _ in b.stage_times()] and r["n_records"] > 500   # ... and the slot stays on it
+    b.close()
+    b = krepp_b200.IBatch(env["gpu"], normal)
+    b.submit(); b.wait()
+    assert "bin_sort_kernel" in [n for n, _ in b.stage_times()]              # a fresh slot starts with the two-level form
+    b.close()
