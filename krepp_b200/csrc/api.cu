@@ -522,19 +522,19 @@ static int alloc_tuples(krepp_batch* b, uint64_t cap)
   if (b->so.tuples) cudaFree(b->so.tuples);
   b->so.tuples = nullptr; b->so.cap_lookups = (uint32_t)cap;
   CU(cudaMalloc(&b->so.tuples, 16ull * cap));
-  // coarse bins of the two-level lookup sort (sorted.cu lookup_partition_kernel): at most 1,024 bins of a power-of-two number of
+  // coarse bins of the two-level lookup sort (sorted.cu lookup_partition_kernel): at most 512 bins of a power-of-two number of
   // rows, each with room for a quarter more than an even share of the lookups.  KREPP_LOOKUP=two_pass keeps the two-pass sort.
   if (b->so.binned) cudaFree(b->so.binned);
   b->so.binned = nullptr; b->so.nbins = 0;
   const HostIndex& h = b->ix->host;
   const char* env = getenv("KREPP_LOOKUP");
   uint32_t shift = 0;
-  while ((((uint64_t)h.nrows - 1) >> shift) + 1 > 1024) ++shift;
+  while ((((uint64_t)h.nrows - 1) >> shift) + 1 > 512) ++shift;
   if (!(env && !strcmp(env, "two_pass")) && !b->bins_off && h.nrows && (1u << shift) <= 8192u) {
     const uint32_t nbins = (uint32_t)((((uint64_t)h.nrows - 1) >> shift) + 1);
     const uint64_t per = ((cap + cap / 4) / nbins + 64 + 3) / 4 * 4;
     if (per < (1ull << 31)) {
-      if (!b->so.bin_cursor) CU(cudaMalloc(&b->so.bin_cursor, 4ull * 1024));
+      if (!b->so.bin_cursor) CU(cudaMalloc(&b->so.bin_cursor, 4ull * 512));
       CU(cudaMalloc(&b->so.binned, 16ull * per * nbins));
       b->so.nbins = nbins; b->so.bin_cap = (uint32_t)per; b->so.bin_shift = shift;
     }

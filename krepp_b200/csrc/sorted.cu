@@ -198,8 +198,8 @@ cudaError_t exclusive_scan(const uint32_t* in, uint32_t n, uint32_t* partials, u
 // does the same work with fire-and-forget reductions).  The two-level form computes every lookup ONCE and needs no per-lookup
 // global atomic:
 //
-//   L1' lookup_partition_kernel  one CTA of 32 warps per SM.  A round = every warp turns one tile of a read into lookups (in its
-//                                own shared-memory segment), then the CTA appends the round's lookups to at most 1,024 coarse bins
+//   L1' lookup_partition_kernel  two CTAs of 16 warps per SM.  A round = every warp turns one tile of a read into lookups (in its
+//                                own shared-memory segment), then the CTA appends the round's lookups to at most 512 coarse bins
 //                                (2^bin_shift rows each): arrivals are counted per bin with shared-memory atomics, joined to the few
 //                                tuples the bin still holds from earlier rounds, and leave for the bin's region in HBM in whole
 //                                64-byte lines at a position taken with ONE global atomic per bin per round; the remainder (fewer
@@ -211,10 +211,11 @@ cudaError_t exclusive_scan(const uint32_t* in, uint32_t n, uint32_t* partials, u
 // Bins have room for a quarter more than an even share of the batch's lookups; reads that pile their lookups on few rows
 // (low-complexity input) can overflow one, which is flagged -- the host then runs the batch through the two-pass form.
 
-constexpr int kLpWarps = 32;
-constexpr int kLpBinsMax = 1024;
+constexpr int kLpWarps = 16;           // two CTAs per SM: one computes tiles while the other sits in the barriers of its append
+constexpr int kLpBinsMax = 512;
 constexpr int kLpLine = 4;             // tuples per line sent to a bin (64 bytes)
-constexpr int kBsThreads = 256;
+constexpr int kBsThreads = 1024;       // one CTA per SM, bins one after the other: few bins are open at a time, so the partly
+                                       // written sectors at the tail of every row stay in L2 until their second half arrives
 constexpr uint32_t kBsRowsMax = 8192;  // rows per bin the bin sort's shared-memory counters hold
 
 struct LpShared {
@@ -228,7 +229,7 @@ struct LpShared {
 };
 
 template <bool TAP>
-__global__ void __launch_bounds__(kLpWarps * 32, 1) lookup_partition_kernel(const DevIndex ix, const MatchArgs a, const SortArgs s)
+__global__ void __launch_bounds__(kLpWarps * 32, 2) lookup_partition_kernel(const DevIndex ix, const MatchArgs a, const SortArgs s)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t nchunks = lut_chunks(ix.k);
@@ -326,7 +327,7 @@ __global__ void __launch_bounds__(kBsThreads) bin_sort_kernel(const SortArgs s, 
   extern __shared__ uint32_t bs_smem[];
   uint32_t* hist = bs_smem;                              // [rows per bin] counts, then cursors
   uint32_t* bin_begin = bs_smem + (1u << s.bin_shift);   // [nbins + 1] exclusive prefix of the bin sizes
-  __shared__ uint32_t warp_sums[kBsThreads / 32];
+  __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t claimed;
   const uint32_t tid = threadIdx.x, rows_per_bin = 1u << s.bin_shift;
   if (counters[2] & kErrRedo) return;
@@ -856,16 +857,16 @@ static cudaError_t launch_lookup_sort(const DevIndex& ix, const MatchArgs& a, co
     const size_t sm1 = lut_chunks(ix.k) * 256 * sizeof(uint4) + sizeof(LpShared);
     if (tap) {
       if ((e = cudaFuncSetAttribute(lookup_partition_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1)) != cudaSuccess) return e;
-      lookup_partition_kernel<true><<<sms, kLpWarps * 32, sm1, stream>>>(ix, a, s);
+      lookup_partition_kernel<true><<<sms * 2, kLpWarps * 32, sm1, stream>>>(ix, a, s);
     } else {
       if ((e = cudaFuncSetAttribute(lookup_partition_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1)) != cudaSuccess) return e;
-      lookup_partition_kernel<false><<<sms, kLpWarps * 32, sm1, stream>>>(ix, a, s);
+      lookup_partition_kernel<false><<<sms * 2, kLpWarps * 32, sm1, stream>>>(ix, a, s);
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (clk) clk->tick("lookup_partition_kernel", stream);
     const size_t sm2 = 4ull * ((1ull << s.bin_shift) + s.nbins + 1);
     if ((e = cudaFuncSetAttribute(bin_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2)) != cudaSuccess) return e;
-    bin_sort_kernel<<<std::min<uint32_t>(s.nbins, (uint32_t)sms * 8u), kBsThreads, sm2, stream>>>(s, a.counters);
+    bin_sort_kernel<<<std::min<uint32_t>(s.nbins, (uint32_t)sms), kBsThreads, sm2, stream>>>(s, a.counters);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (clk) clk->tick("bin_sort_kernel", stream);
     if (launches) *launches += 2;
