@@ -294,6 +294,17 @@ int krepp_device_alloc(int device, uint64_t bytes, void** out);
 void krepp_device_free(int device, void* p);
 int krepp_device_copy(int dst_device, void* dst, int src_device, const void* src, uint64_t bytes);
 
+/* -------------------------------------------------------------------------------------------------- index side
+ * What `krepp index` does to one reference genome before the colour unions: RSeq::extract_mers (src/rqseq.cpp:51-144; sdust
+ * off, not canonical: every valid forward k-mer, xur64_hash minimizer of every window of w valid bases, the LSH residue filter,
+ * row and 32-bit residual encoding, and the end-of-sequence emit of :112-116) followed by the per-row sort and unique of
+ * DynHT::fill_table (src/table.cpp:110-117,157-166,248-260).  Geometry (k, w, h, m, r, frac, positions) is that of `ix`, which
+ * must be open on a GPU.  bases / offsets: HOST memory, the genome's sequences back to back (sequences shorter than w are
+ * skipped, src/rqseq.hpp:80-86).  keys: row << 32 | encoding, ascending -- one leaf table; *n_keys is always the number found;
+ * KREPP_ERR_CAPACITY when cap is too small (cap = 0 just counts). */
+int krepp_extract_mers(const krepp_index_t* ix, const char* bases, const uint64_t* offsets, uint32_t n_seqs, uint64_t* keys,
+                       uint64_t cap, uint64_t* n_keys);
+
 /* -------------------------------------------------------------------------------------------------- host I/O layer
  * The steps immediately either side of the GPU path.  Pure host code: usable
  * without a device (the index handle may have been opened with KREPP_DEVICE_NONE). */

@@ -167,6 +167,7 @@ def load_library():
     L.krepp_shard_lookup.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
     L.krepp_shard_join.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
     L.krepp_shard_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+    L.krepp_extract_mers.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.krepp_reader_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
     L.krepp_reader_close.argtypes = [C.c_void_p]
     L.krepp_reader_next.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p,
@@ -215,6 +216,18 @@ class Index:
             self._h = None
 
     __del__ = close
+
+    def extract_mers(self, seqs) -> np.ndarray:
+        """krepp_extract_mers: the leaf table of one genome (list of its sequences as bytes) under this index's geometry --
+        sorted unique row << 32 | encoding keys (RSeq::extract_mers + DynHT::fill_table, ref src/rqseq.cpp:51-144,
+        src/table.cpp:248-260), computed on the GPU."""
+        bases, offs = pack_reads(list(seqs))
+        bases = np.ascontiguousarray(bases) if len(bases) else np.zeros(1, np.uint8)
+        n = C.c_uint64()
+        _check(load_library().krepp_extract_mers(self._h, bases.ctypes.data, offs.ctypes.data, len(offs) - 1, None, 0, C.byref(n)))
+        out = np.zeros(max(n.value, 1), np.uint64)
+        _check(load_library().krepp_extract_mers(self._h, bases.ctypes.data, offs.ctypes.data, len(offs) - 1, out.ctypes.data, len(out), C.byref(n)))
+        return out[:n.value]
 
     def host_checksums(self) -> list:
         """krepp_index_host_checksums: [sum cmer words, sum bucket ends, sum c * |leaves(c)|, sum (c+1)(leaf rank+1)] mod 2^64."""

@@ -68,9 +68,12 @@ __device__ __forceinline__ uint4 lut_pext(const uint4* lut, uint32_t lo, uint32_
 // A0 + A1 of one tile of a read (see the header): ASCII bases -> 2-bit stream in shared memory -> k-mer windows -> bucket
 // ids and residual encodings of both strands; the eligible lookups are compacted into sm.lk_a (row offset | strand << 31)
 // and sm.lk_q.  Returns their number; onmers / wn0 / wn1 are the read's running counts (warp-uniform).
+// bin_cnt (optional): shared-memory counters of the two-level lookup sort (sorted.cu); every eligible lookup also counts itself
+// in the coarse bin of its row, bin_cnt[row >> bin_shift].
 template <bool TAP, class WS>
 __device__ __forceinline__ uint32_t tile_lookups(const DevIndex& ix, const MatchArgs& a, WS& sm, const uint4* lut, bool wide, uint32_t read,
-                                                 uint64_t off, uint64_t len, uint64_t t0, uint32_t& onmers, uint32_t& wn0, uint32_t& wn1)
+                                                 uint64_t off, uint64_t len, uint64_t t0, uint32_t& onmers, uint32_t& wn0, uint32_t& wn1,
+                                                 uint32_t* bin_cnt = nullptr, uint32_t bin_shift = 0)
 {
   const uint32_t lane = threadIdx.x & 31, lt_mask = (1u << lane) - 1, k = ix.k;
   // ---- A0. load + encode the tile's bases: [t0, t0 + kTileWindows + k - 1) clipped to the read
@@ -145,6 +148,7 @@ __device__ __forceinline__ uint32_t tile_lookups(const DevIndex& ix, const Match
         const uint32_t idx = nl + __popc(em & lt_mask);
         sm.lk_a[idx] = offset | (strand << 31);
         sm.lk_q[idx] = q;
+        if (bin_cnt) atomicAdd(&bin_cnt[offset >> bin_shift], 1u);
         if (TAP) {
           const unsigned long long at = atomicAdd(a.tap_count, 1ull);
           const uint32_t pos = strand ? (uint32_t)(len - (t0 + p) - k) : (uint32_t)(t0 + p);

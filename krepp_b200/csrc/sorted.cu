@@ -221,7 +221,8 @@ constexpr uint32_t kBsRowsMax = 8192;  // rows per bin the bin sort's shared-mem
 struct LpShared {
   WarpSmemLite w[kLpWarps];
   uint4 stage[kLpBinsMax][kLpLine];    // per bin: tuples waiting for a full line
-  uint32_t cnt[kLpBinsMax];            // arrivals of the round, then the cursor that ranks them
+  uint32_t cnt[kLpBinsMax];            // arrivals of the round (counted by the warps as they find their lookups)
+  uint32_t rank[kLpBinsMax];           // the cursor that ranks the arrivals
   uint32_t left[kLpBinsMax];           // tuples waiting in stage[]
   uint32_t gbase[kLpBinsMax];          // where the bin's lines of this round start in its region
   uint32_t lim[kLpBinsMax];            // tuples of this round's lines (a multiple of kLpLine)
@@ -265,8 +266,8 @@ __global__ void __launch_bounds__(kLpWarps * 32, 2) lookup_partition_kernel(cons
     uint32_t nlk = 0;
     const bool did = have;
     if (have) {
-      nlk = tile_lookups<TAP>(ix, a, sm, lut, wide, read, off, len, t0, onmers, wn0, wn1);
-      if (loc + nlk >= kMaxLoc) { if (lane == 0) atomicOr(a.counters + 2, kErrSortFallback); nlk = 0; t0 = len; } // the read cannot be indexed: the host redoes the batch
+      nlk = tile_lookups<TAP>(ix, a, sm, lut, wide, read, off, len, t0, onmers, wn0, wn1, sh.cnt, s.bin_shift);
+      if (loc + nlk >= kMaxLoc) { if (lane == 0) atomicOr(a.counters + 2, kErrSortFallback); t0 = len; } // the read cannot be indexed: the host redoes the batch
       if (lane == 0) { sh.nl[warp] = nlk; sh.rd[warp] = read; sh.locb[warp] = loc; }
       loc += nlk;
       t0 += kTileWindows;
@@ -276,12 +277,6 @@ __global__ void __launch_bounds__(kLpWarps * 32, 2) lookup_partition_kernel(cons
       }
     } else if (lane == 0) sh.nl[warp] = 0;
     if (!__syncthreads_or(did ? 1 : 0)) break; // no warp had a tile: all reads are done
-    // ---- a. arrivals per bin
-    for (uint32_t slot = threadIdx.x; slot < (uint32_t)(kLpWarps * kMaxLookups); slot += blockDim.x) {
-      const uint32_t w = slot / kMaxLookups, i = slot % kMaxLookups;
-      if (i < sh.nl[w]) atomicAdd(&sh.cnt[(sh.w[w].lk_a[i] & 0x7FFFFFFFu) >> s.bin_shift], 1u);
-    }
-    __syncthreads();
     // ---- b. per bin: whole lines leave; their place in the bin's region; the tuples that waited go first
     for (uint32_t b = threadIdx.x; b < s.nbins; b += blockDim.x) {
       const uint32_t l = sh.left[b], t = l + sh.cnt[b], out = t - t % kLpLine;
@@ -292,7 +287,7 @@ __global__ void __launch_bounds__(kLpWarps * 32, 2) lookup_partition_kernel(cons
         uint4* dst = s.binned + (size_t)b * s.bin_cap;
         for (uint32_t i = 0; i < l; ++i) if (g + i < s.bin_cap) dst[g + i] = sh.stage[b][i];
       }
-      sh.gbase[b] = g; sh.lim[b] = out; sh.cnt[b] = l; sh.left[b] = t - out;
+      sh.gbase[b] = g; sh.lim[b] = out; sh.rank[b] = l; sh.left[b] = t - out; sh.cnt[b] = 0;
     }
     __syncthreads();
     // ---- c. every arrival takes its rank in its bin: into one of the bin's lines, or into the waiting slots
@@ -301,14 +296,12 @@ __global__ void __launch_bounds__(kLpWarps * 32, 2) lookup_partition_kernel(cons
       if (i < sh.nl[w]) {
         const uint32_t ob = sh.w[w].lk_a[i], row = ob & 0x7FFFFFFFu, b = row >> s.bin_shift;
         const uint4 tup = make_uint4(sh.w[w].lk_q[i], sh.rd[w], (sh.locb[w] + i) | (ob & 0x80000000u), row);
-        const uint32_t c = atomicAdd(&sh.cnt[b], 1u), lim = sh.lim[b];
+        const uint32_t c = atomicAdd(&sh.rank[b], 1u), lim = sh.lim[b];
         if (c < lim) { const uint32_t g = sh.gbase[b] + c; if (g < s.bin_cap) s.binned[(size_t)b * s.bin_cap + g] = tup; }
         else sh.stage[b][c - lim] = tup;
       }
     }
-    __syncthreads();
-    for (uint32_t b = threadIdx.x; b < s.nbins; b += blockDim.x) sh.cnt[b] = 0;
-    // (the next use of cnt[] lies behind the barrier that follows the next round's tiles)
+    __syncthreads(); // the next round's tiles count into cnt[] (zeroed in b) and overwrite the warps' lookup lists
   }
   // ---- the tuples still waiting leave as short lines
   for (uint32_t b = threadIdx.x; b < s.nbins; b += blockDim.x) {
@@ -355,7 +348,13 @@ __global__ void __launch_bounds__(kBsThreads) bin_sort_kernel(const SortArgs s, 
     const uint4* src = s.binned + (size_t)b * s.bin_cap;
     for (uint32_t r = tid; r < nr; r += kBsThreads) hist[r] = 0;
     __syncthreads();
-    for (uint32_t i = tid; i < n; i += kBsThreads) atomicAdd(&hist[__ldg(reinterpret_cast<const uint32_t*>(src + i) + 3) - row0], 1u);
+    for (uint32_t i0 = 0; i0 < n; i0 += 8 * kBsThreads) { // eight loads in flight per thread: the pass is bound by memory latency
+      uint32_t rw[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { const uint32_t i = i0 + u * kBsThreads + tid; rw[u] = i < n ? __ldg(reinterpret_cast<const uint32_t*>(src + i) + 3) : 0xFFFFFFFFu; }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) if (rw[u] != 0xFFFFFFFFu) atomicAdd(&hist[rw[u] - row0], 1u);
+    }
     __syncthreads();
     { // exclusive scan of the row counts; hist[] becomes the rows' cursors into the dense list
       const uint32_t per = (nr + kBsThreads - 1) / kBsThreads, lo = min(tid * per, nr), hi = min(lo + per, nr);
@@ -367,10 +366,13 @@ __global__ void __launch_bounds__(kBsThreads) bin_sort_kernel(const SortArgs s, 
       if (b == s.nbins - 1 && tid == 0) s.row_begin[s.nrows] = dst0 + n;
     }
     __syncthreads();
-    for (uint32_t i = tid; i < n; i += kBsThreads) {
-      const uint4 t = __ldg(src + i);
-      const uint32_t pos = atomicAdd(&hist[t.w - row0], 1u);
-      s.tuples[pos] = make_uint4(t.x, t.y, t.z, 0u);
+    for (uint32_t i0 = 0; i0 < n; i0 += 4 * kBsThreads) {
+      uint4 t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const uint32_t i = i0 + u * kBsThreads + tid; t[u] = i < n ? __ldg(src + i) : make_uint4(0u, 0u, 0u, 0xFFFFFFFFu); }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (t[u].w != 0xFFFFFFFFu) { const uint32_t pos = atomicAdd(&hist[t[u].w - row0], 1u); s.tuples[pos] = make_uint4(t[u].x, t[u].y, t[u].z, 0u); }
     }
   }
 }

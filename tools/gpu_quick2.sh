@@ -4,7 +4,7 @@
 TAG=${1:-q}; shift
 O=gpurun_out/$TAG
 mkdir -p $O
-( time timeout 900 python -m pytest tests/test_gpu_sorted.py tests/test_gpu_c3.py -m gpu -q -x -k "not cli" ) > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $O/pytest_gpu.log
+( time timeout 900 python -m pytest ${TESTS:-tests/test_gpu_sorted.py tests/test_gpu_c3.py} -m gpu -q -x -k "not cli" ) > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $O/pytest_gpu.log
 tail -8 $O/pytest_gpu.log
 timeout 600 python bench.py --no-place --no-cpu-baseline "$@" > $O/bench.json 2> $O/bench.err; echo "bench rc=$?"; tail -3 $O/bench.err
 python - $O/bench.json <<'PY'
