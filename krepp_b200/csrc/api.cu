@@ -523,14 +523,17 @@ static int alloc_tuples(krepp_batch* b, uint64_t cap)
   b->so.tuples = nullptr; b->so.cap_lookups = (uint32_t)cap;
   CU(cudaMalloc(&b->so.tuples, 16ull * cap));
   // coarse bins of the two-level lookup sort (sorted.cu lookup_partition_kernel): at most 512 bins of a power-of-two number of
-  // rows, each with room for a quarter more than an even share of the lookups.  KREPP_LOOKUP=two_pass keeps the two-pass sort.
+  // rows, each with room for a quarter more than an even share of the lookups.  Opt-in (KREPP_LOOKUP=binned): measured on B200
+  // (r07e/f, config 3) it only ties the two-pass sort -- 28.0 + 32.3 ms against 14.0 + 47.1 ms per 10 M reads: the partition's
+  // append rounds double the lookup kernel, and the bin sort's 16-byte scatter into 3.9 MB windows (148 of them open at a time,
+  // far more than L2 holds) reaches DRAM as partly written sectors (8.3 GB moved for 6 GB, 2.5 TB/s).
   if (b->so.binned) cudaFree(b->so.binned);
   b->so.binned = nullptr; b->so.nbins = 0;
   const HostIndex& h = b->ix->host;
   const char* env = getenv("KREPP_LOOKUP");
   uint32_t shift = 0;
   while ((((uint64_t)h.nrows - 1) >> shift) + 1 > 512) ++shift;
-  if (!(env && !strcmp(env, "two_pass")) && !b->bins_off && h.nrows && (1u << shift) <= 8192u) {
+  if (env && !strcmp(env, "binned") && !b->bins_off && h.nrows && (1u << shift) <= 8192u) {
     const uint32_t nbins = (uint32_t)((((uint64_t)h.nrows - 1) >> shift) + 1);
     const uint64_t per = ((cap + cap / 4) / nbins + 64 + 3) / 4 * 4;
     if (per < (1ull << 31)) {

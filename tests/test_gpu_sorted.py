@@ -44,8 +44,8 @@ def test_sorted_golden_small_index(sorted_pipeline):
 @needs_ref
 @pytest.mark.parametrize("lookup", ["binned", "two_pass"])
 def test_sorted_toy_query_and_20k(env, sorted_pipeline, monkeypatch, lookup):
-    """Both forms of the lookup sort: the two-level one (lookup_partition_kernel + bin_sort_kernel, the default) and the two-pass
-    counting sort it falls back to (KREPP_LOOKUP=two_pass)."""
+    """Both forms of the lookup sort: the two-pass counting sort (the default) and the two-level one (lookup_partition_kernel +
+    bin_sort_kernel, KREPP_LOOKUP=binned)."""
     import synth
     from gpu_common import run_and_compare
     monkeypatch.setenv("KREPP_LOOKUP", lookup)
@@ -136,13 +136,14 @@ def test_sorted_equals_fused_bit_for_bit(env, monkeypatch):
 
 
 @needs_ref
-def test_sorted_skewed_rows_fall_back_to_two_pass(env, sorted_pipeline):
+def test_sorted_skewed_rows_fall_back_to_two_pass(env, sorted_pipeline, monkeypatch):
     """Reads that pile their lookups on a few rows (a thousand copies of poly-A, poly-AC and one genomic read among ordinary
     reads) overflow a coarse bin of the two-level lookup sort; the batch is redone with the exact two-pass sort and the slot stays
     on it: same records as the oracle either way, before and after."""
     import krepp_b200
     import synth
     from gpu_common import run_and_compare
+    monkeypatch.setenv("KREPP_LOOKUP", "binned")
     seq, offs = synth.load_packed(os.path.join(TOY_DIR, "genomes.npz"))
     normal = [r.tobytes() for r in synth.sample_reads(seq, offs, 600, seed=17)]
     skew = [b"A" * 150] * 1000 + [b"AC" * 75] * 1000 + [normal[0]] * 1500
@@ -157,5 +158,5 @@ def test_sorted_skewed_rows_fall_back_to_two_pass(env, sorted_pipeline):
     b.close()
     b = krepp_b200.IBatch(env["gpu"], normal)
     b.submit(); b.wait()
-    assert "bin_sort_kernel" in [n for n, _ in b.stage_times()]              # a fresh slot starts with the two-level form
+    assert "bin_sort_kernel" in [n for n, _ in b.stage_times()]              # a fresh slot (with KREPP_LOOKUP=binned) starts with the two-level form
     b.close()
