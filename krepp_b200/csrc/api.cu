@@ -333,6 +333,7 @@ int krepp_index_open_shard(const char* index_dir, int device, uint32_t shard, ui
   if (e == cudaSuccess) e = upload(build_lut(h), &d.lut, ix->allocs, ix->device_bytes);
   if (e == cudaSuccess) e = upload(h.tree.subtree, &d.subtree, ix->allocs, ix->device_bytes);
   if (e == cudaSuccess) e = upload(h.tree.depth, &d.depth, ix->allocs, ix->device_bytes);
+  if (e == cudaSuccess) e = upload(h.tree.logw, &d.logw, ix->allocs, ix->device_bytes);
   d.cbeg = nullptr; d.cleaf = nullptr;
   if (!h.cbeg.empty()) { // flattened colours: what the bucket-sorted pipeline (sorted.cu) expands hits with
     if (e == cudaSuccess) e = upload(h.cbeg, &d.cbeg, ix->allocs, ix->device_bytes);
@@ -776,7 +777,7 @@ static int enqueue(krepp_batch* b)
   if (b->p.place) {
     PlaceArgs pa{};
     pa.s = sa; pa.offsets = b->in_offsets; pa.tau = b->p.tau; pa.no_filter = b->p.no_filter; pa.chisq_value = b->p.chisq;
-    pa.parent = ix->dev.parent; pa.nchildren = ix->dev.nchildren; pa.subtree = ix->dev.subtree; pa.depth = ix->dev.depth; pa.blen = ix->dev.blen; pa.leaf_rank = ix->dev.leaf_rank;
+    pa.parent = ix->dev.parent; pa.nchildren = ix->dev.nchildren; pa.subtree = ix->dev.subtree; pa.depth = ix->dev.depth; pa.logw = getenv("KREPP_PLACE_ORDERED") ? nullptr : ix->dev.logw; pa.blen = ix->dev.blen; pa.leaf_rank = ix->dev.leaf_rank;
     pa.nnodes = h.tree.nnodes; pa.nleaves = h.tree.nleaves; pa.sel = b->d_sel; pa.chain = b->d_chain; pa.chain_cap = b->chain_cap;
     pa.node_bitmap = b->d_node_bitmap; pa.node_list = b->d_node_list; pa.node_order = b->d_node_order;
     pa.node_cap = b->node_cap; pa.pn_read = b->d_pn_read; pa.pn_se = b->d_pn_se; pa.pn_flags = b->d_pn_flags; pa.pn_work = b->d_pn_work;

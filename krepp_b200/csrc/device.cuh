@@ -27,6 +27,7 @@ struct DevIndex {
   const uint32_t* nchildren;// by se
   const double* blen;       // by se
   const uint32_t* depth;    // by se: number of ancestors
+  const uint32_t* logw;     // by se: log2 of the product of the ancestors' child counts when they are all powers of two (HostTree::logw)
   const uint32_t* subtree;  // by se: number of nodes in the subtree rooted there (post-order => se range (se-subtree, se])
   uint64_t nkmers;
   uint32_t nrows, nsubsets, nnodes, nleaves;
@@ -140,7 +141,7 @@ struct PlaceArgs {
   const uint64_t* offsets;     // read offsets (enmers = len - k + 1, ref src/query.cpp:345-349)
   uint32_t tau; int no_filter; double chisq_value;
   // flattened tree (by se)
-  const uint32_t* parent; const uint32_t* nchildren; const uint32_t* subtree; const uint32_t* depth; const double* blen; const uint32_t* leaf_rank;
+  const uint32_t* parent; const uint32_t* nchildren; const uint32_t* subtree; const uint32_t* depth; const uint32_t* logw; const double* blen; const uint32_t* leaf_rank;
   uint32_t nnodes, nleaves;
   // per-warp scratch of the collect kernel
   uint32_t* node_bitmap;       // [warps][ceil((nnodes+1)/32)]

@@ -167,6 +167,13 @@ std::string HostTree::parse(const std::string& newick)
   for (uint32_t se = 1; se <= nnodes; ++se) shown[se] = name[se].empty() ? std::to_string(se - 1) : name[se];
   depth.assign(N, 0);
   for (uint32_t se = nnodes; se >= 1; --se) if (parent[se]) depth[se] = depth[parent[se]] + 1;  // parents have the larger se
+  logw.assign(nnodes + 1, 0);
+  for (uint32_t se = nnodes; se >= 1; --se) {
+    const uint32_t p = parent[se];
+    if (!p) continue;
+    const uint32_t nc = nchildren[p];
+    logw[se] = (logw[p] == 0xFFFFFFFFu || nc == 0 || (nc & (nc - 1))) ? 0xFFFFFFFFu : logw[p] + (uint32_t)__builtin_ctz(nc);
+  }
   return "";
 }
 

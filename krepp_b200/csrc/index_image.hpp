@@ -39,6 +39,8 @@ struct HostTree {
   uint32_t nnodes = 0, root = 0, nleaves = 0;
   std::vector<uint32_t> parent, nchildren, card, first_child, next_sibling; // [nnodes+1], by se
   std::vector<uint32_t> depth;           // ancestors of se (0 for the root)
+  std::vector<uint32_t> logw;            // sum of log2(nchildren) over the proper ancestors of se when every one of them has a power-of-two
+                                         // number of children (a leaf's weight at an ancestor g is then exactly 2^-(logw[leaf] - logw[g])), else 0xffffffff
   std::vector<uint32_t> subtree;         // nodes in the subtree rooted at se; post-order => it spans se in (se-subtree, se]
   std::vector<uint8_t> is_leaf;
   std::vector<double> blen;              // NaN when absent

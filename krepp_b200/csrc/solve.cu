@@ -237,6 +237,10 @@ __global__ void __launch_bounds__(128) place_collect_kernel(const PlaceArgs a)
   // atomics up the tree, a microsecond each in L2), else in the warp's HBM scratch (zeroed at allocation, left clean by step 2)
   constexpr uint32_t kSmemBm = 256;
   __shared__ uint32_t sbm[kPlaceWarpsPerCta][kSmemBm];
+  // exact mode (see 3a'): prefix sums over the read's selected references of their scaled histograms (+ match count)
+  constexpr uint32_t kPfxCap = 64;
+  __shared__ double spfx[kPlaceWarpsPerCta][kPfxCap + 1][N + 1];
+  double (*pfx)[N + 1] = spfx[threadIdx.x >> 5];
   uint32_t* bm = a.node_bitmap + (size_t)gwarp * nbm;
   if (nbm <= kSmemBm) {
     bm = sbm[threadIdx.x >> 5];
@@ -317,7 +321,34 @@ __global__ void __launch_bounds__(128) place_collect_kernel(const PlaceArgs a)
             sel_rec[rank] = b + i; sel_se[rank] = se;
           }
           __syncwarp();
+          const uint32_t enmers = (uint32_t)(a.offsets[r + 1] - a.offsets[r]) - s.k + 1;
+          // 3a'. Exact mode.  When every ancestor of the selected references has a power-of-two number of children (any binary
+          //      tree), a leaf's weight at an ancestor g is exactly 2^-(logw[leaf] - logw[g]) and every sum Minfo::add forms is
+          //      exactly representable (counts below 2^16, at most 64 leaves, weights down to 2^-30: 52 bits), so the order of
+          //      the additions cannot matter and a node's histogram is a difference of prefix sums over the leaves below it --
+          //      O(1) per node instead of one step per leaf below -- with the same bits as the reference's ordered sum.
+          bool exact = nsel <= kPfxCap && enmers < 65536u && a.logw != nullptr;
+          {
+            bool bad = false;
+            for (uint32_t i = lane; i < nsel; i += 32) bad = bad || a.logw[sel_se[i]] > 30u;
+            exact = exact && !__any_sync(0xFFFFFFFFu, bad);
+          }
+          if (exact) {
+            if (lane <= stride && lane <= (uint32_t)N) { // lane x: component x of the histogram, lane `stride`: the match count
+              double run = 0;
+              pfx[0][lane] = 0;
+              for (uint32_t i = 0; i < nsel; ++i) {
+                const uint32_t rec = sel_rec[i];
+                const double scale = __hiloint2double((int)((1023u - a.logw[sel_se[i]]) << 20), 0); // 2^-logw
+                const double val = lane < stride ? (double)s.rec_hist[(size_t)rec * stride + lane] : (double)s.rec_match[rec];
+                run = run + val * scale;
+                pfx[i + 1][lane] = run;
+              }
+            }
+            __syncwarp();
+          }
           uint32_t chain_len = 0;
+          if (!exact)
           for (uint32_t i0 = 0; i0 < nsel; i0 += 32) {
             const uint32_t i = i0 + lane;
             const uint32_t dep = i < nsel ? a.depth[sel_se[i]] : 0u;
@@ -326,7 +357,7 @@ __global__ void __launch_bounds__(128) place_collect_kernel(const PlaceArgs a)
             if (i < nsel) sel_off[i] = chain_len + incl - dep;
             chain_len += __shfl_sync(0xFFFFFFFFu, incl, 31);
           }
-          const bool chained = chain_len <= a.chain_cap;
+          const bool chained = !exact && chain_len <= a.chain_cap;
           __syncwarp();
           if (chained)
             for (uint32_t i = lane; i < nsel; i += 32) {
@@ -341,7 +372,7 @@ __global__ void __launch_bounds__(128) place_collect_kernel(const PlaceArgs a)
           //     leaf share their rounds instead of each holding up a round of single-leaf nodes.  Entry j of the read stays
           //     node j of the ascending list whatever the visiting order.
           uint32_t* order = a.node_order + (size_t)gwarp * a.nnodes;
-          {
+          if (!exact) {
             uint32_t placed = 0;
             for (int cls = 0; cls < 3; ++cls)
               for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
@@ -361,10 +392,9 @@ __global__ void __launch_bounds__(128) place_collect_kernel(const PlaceArgs a)
               }
           }
           __syncwarp();
-          const uint32_t enmers = (uint32_t)(a.offsets[r + 1] - a.offsets[r]) - s.k + 1;
           for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
             const bool active = j0 + lane < cnt;
-            const uint32_t j = active ? order[j0 + lane] : 0u;
+            const uint32_t j = active ? (exact ? j0 + lane : order[j0 + lane]) : 0u;
             bool solve = false;
             if (active) {
               const uint32_t g = list[j], e = nbegin + j;
@@ -382,6 +412,16 @@ __global__ void __launch_bounds__(128) place_collect_kernel(const PlaceArgs a)
                 for (int x = 0; x < N; ++x) mc[x] = 0;
                 double nmers = 0, mismatch = 0, match = 0, rho = 0;
                 const uint32_t gdep = a.depth[g];
+                if (exact) {
+                  uint32_t last = first; // first selected reference with se > g
+                  for (uint32_t hi = nsel; last < hi;) { const uint32_t mid = (last + hi) >> 1; if (sel_se[mid] > g) hi = mid; else last = mid + 1; }
+                  const double up = __hiloint2double((int)((1023u + a.logw[g]) << 20), 0); // 2^logw[g]
+#pragma unroll
+                  for (int x = 0; x < N; ++x) if ((uint32_t)x < stride) mc[x] = (pfx[last][x] - pfx[first][x]) * up;
+                  match = (pfx[last][stride] - pfx[first][stride]) * up;
+                  mismatch = (double)enmers - match;
+                  for (uint32_t i = first; i < last; ++i) rho = fmax(rho, s.rho[sel_se[i]]);
+                } else
                 for (uint32_t i = first; i < nsel; ++i) { // ascending leaf se: the order Minfo::add is applied in
                   const uint32_t se = sel_se[i];
                   if (se > g) break;

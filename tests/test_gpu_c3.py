@@ -85,6 +85,30 @@ def test_c3_place_all_stages_vs_oracle(c3, handles, monkeypatch):
     assert st["placements"] > N_STAGE  # most reads are placed, several candidate edges each
 
 
+def test_c3_place_exact_mode_equals_ordered_sums_bit_for_bit(c3, handles, monkeypatch):
+    """Placement accumulates a node's histogram as a difference of prefix sums when every weight is a power of two (this binary
+    tree): the result must have the same bits as the reference's leaf-by-leaf sums (KREPP_PLACE_ORDERED=1 keeps those)."""
+    import krepp_b200
+    monkeypatch.delenv("KREPP_PIPELINE", raising=False)
+    reads = _reads(c3, 2 * N_STAGE, N_STAGE)
+    out = []
+    for ordered in (False, True):
+        if ordered:
+            monkeypatch.setenv("KREPP_PLACE_ORDERED", "1")
+        b = krepp_b200.IBatch(handles["gpu"], reads, place=True, no_filter=False)
+        b.submit()
+        r = b.wait()
+        out.append({k: np.array(r[k], copy=True) for k in ("reads", "placements")})
+        b.close()
+    a, c = out
+    assert np.array_equal(a["reads"]["place_count"], c["reads"]["place_count"]) and int(a["reads"]["place_count"].sum()) > N_STAGE
+    for i in range(len(reads)):
+        ab, cb, n = int(a["reads"]["place_begin"][i]), int(c["reads"]["place_begin"][i]), int(a["reads"]["place_count"][i])
+        for name in a["placements"].dtype.names:
+            if name != "read":
+                assert np.array_equal(a["placements"][name][ab:ab + n], c["placements"][name][cb:cb + n], equal_nan=True), (i, name)
+
+
 def test_c3_small_batches_grow_and_rerun(c3, handles, monkeypatch):
     """Result buffers that overflow are grown to the demand and the batch re-runs (18.6 records per read against the initial
     4 per read): a slot that has already grown and a fresh one give the same per-read rows bit for bit."""
