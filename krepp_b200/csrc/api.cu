@@ -587,8 +587,6 @@ static int alloc_sorted(krepp_batch* b)
   CU(cudaMalloc(&so.sc, 32));
   CU(cudaMallocHost(&b->h_sc, 4ull * (16 + 2 * (KREPP_MAX_SHARDS + 1))));
   if (const char* env = getenv("KREPP_SORT_WIDE")) so.extra_rank_bits = (uint32_t)std::min(24, std::max(0, atoi(env)));
-  if (const char* env = getenv("KREPP_RESOLVE")) so.resolve_sort = !strcmp(env, "sort") ? 1u : 0u;
-  if (so.extra_rank_bits) so.resolve_sort = 1u; // (that knob is about the sort keys)
   if (int rc = alloc_keys(b, 8192)) return rc;
   if (b->max_bases >= (1ull << 31)) return fail(KREPP_ERR_CAPACITY, "the bucket-sorted chain counts a batch's lookups in 32 bits: at most 2^31 - 1 bases per batch");
   // every base starts at most one window = two lookups, of which (r+1)/m are eligible on average; grown on demand

@@ -98,7 +98,6 @@ struct SortArgs {
   uint32_t* bin_cursor;   // [nbins] tuples appended to every bin
   uint32_t nbins, bin_cap, bin_shift;
   uint32_t res_ctas;      // CTAs of the resolve kernel (keys_g holds res_ctas * warps per CTA regions); 0 = the default grid
-  uint32_t resolve_sort;    // test knob (KREPP_RESOLVE=sort): every read goes through the sorting form of the resolve kernel
   uint32_t extra_rank_bits; // test knob (KREPP_SORT_WIDE): widens the leaf field of the sort keys so that the 64-bit key path runs
 };
 

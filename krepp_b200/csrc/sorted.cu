@@ -39,7 +39,7 @@ constexpr uint32_t kRowClaim = 32;     // bucket rows claimed per atomic: one pe
 constexpr int kJoinChunk = 128;        // index entries held in registers per pass: four per lane
 constexpr int kHitQ = 128;             // per-warp queue of hit entries; flushed once fewer than 32 slots (one ballot's worth) are free
 constexpr int kResWarps = 8;
-constexpr int kResKeys = 2048;         // 32-bit words per warp in shared memory: sort keys (half as many 64-bit keys), or the hash path's tables
+constexpr int kResKeys = 1024;         // 32-bit sort keys per warp in shared memory (half as many 64-bit keys)
 constexpr uint32_t kResClaim = 4;
 constexpr uint32_t kMaxLoc = 1u << 26; // local lookup indices must fit bits 5..30 of the hit word
 
@@ -216,6 +216,7 @@ constexpr int kLpBinsMax = 512;
 constexpr int kLpLine = 4;             // tuples per line sent to a bin (64 bytes)
 constexpr int kBsThreads = 1024;       // one CTA per SM, bins one after the other: few bins are open at a time, so the partly
                                        // written sectors at the tail of every row stay in L2 until their second half arrives
+constexpr uint32_t kBsRowsMax = 8192;  // rows per bin the bin sort's shared-memory counters hold
 
 struct LpShared {
   WarpSmemLite w[kLpWarps];
@@ -738,148 +739,9 @@ __device__ __forceinline__ ResolveOut resolve_read(const DevIndex& ix, const Mat
   return emit_sorted<K>(ix, a, keys, T, seg_shift, rank_bits, read, g0, g1, small_counts);
 }
 
-// ---- the sort-free form of one read's resolve, for the common case (a few hundred leaf hits on an index of a few thousand
-// references): everything lives in the warp's 8 KB of shared memory.
-//   bitmap   one bit per (strand, leaf rank): the pairs the read hits.  Its popcount prefix numbers them ("segments") in
-//            (strand, leaf) order -- the order the records must come out in -- without sorting anything.
-//   table    open-addressing hash set of (segment, lookup) -> smallest distance: a key is segment | lookup | hd, inserted with
-//            compare-and-swap; a second hit of the same lookup on the same leaf (two index entries of one bucket whose colours
-//            share a leaf) meets its twin and the two settle on the smaller distance with atomicMin, which is
-//            Minfo::update_match's per-position minimum (ref src/query.hpp:153-176).
-//   hist     per segment eight 8-bit counters (every count is below 256 here): one increment per occupied table slot.
-// Then the hdist_filt gate and the records exactly as emit_sorted writes them.
-__device__ __forceinline__ uint32_t hash_words(uint32_t T, uint32_t W, uint32_t& H)
-{
-  H = 32;
-  while (H < 2 * T) H <<= 1;
-  return 2 * W + (T + 1) / 2 + 2 * T + H;
-}
-
-template <class F>
-__device__ __forceinline__ void for_each_leaf_hit(const DevIndex& ix, const SortArgs& s, uint32_t hb, uint32_t nh, F&& f)
-{ // f(slot = strand * nleaves + leaf rank, lookup << 5 | hd) for every (hit entry, leaf of its colour) of the read
-  const uint32_t lane = threadIdx.x & 31;
-  for (uint32_t c = 0; c < nh; c += 32) {
-    const uint32_t i = c + lane;
-    uint4 h = make_uint4(0u, 0u, 0u, 0u);
-    if (i < nh) h = s.hits[hb + i];
-    const uint32_t cnt = h.y, sbase = (h.z >> 31) * ix.nleaves, low = h.z & 0x7FFFFFFFu;
-    if (cnt <= 8u) { // all leaf loads of the lane in flight before the first one is used
-      uint32_t lf[8];
-#pragma unroll
-      for (uint32_t j = 0; j < 8u; ++j) lf[j] = j < cnt ? __ldg(&ix.cleaf[h.x + j]) : 0u;
-#pragma unroll
-      for (uint32_t j = 0; j < 8u; ++j) if (j < cnt) f(sbase + lf[j], low);
-    }
-    uint32_t big = __ballot_sync(0xFFFFFFFFu, cnt > 8u); // long leaf lists: all lanes together
-    while (big) {
-      const int src = __ffs(big) - 1;
-      big &= big - 1;
-      const uint32_t bx = __shfl_sync(0xFFFFFFFFu, h.x, src), bn = __shfl_sync(0xFFFFFFFFu, cnt, src);
-      const uint32_t bs = __shfl_sync(0xFFFFFFFFu, sbase, src), bl = __shfl_sync(0xFFFFFFFFu, low, src);
-      for (uint32_t j = lane; j < bn; j += 32) f(bs + __ldg(&ix.cleaf[bx + j]), bl);
-    }
-  }
-}
-
-__device__ __forceinline__ ResolveOut resolve_hash(const DevIndex& ix, const MatchArgs& a, const SortArgs& s, uint32_t* buf, uint32_t hb, uint32_t nh, uint32_t T,
-                                                   uint32_t W, uint32_t loc_bits, uint32_t read, uint32_t g0, uint32_t g1)
-{
-  const uint32_t lane = threadIdx.x & 31, lt_mask = (1u << lane) - 1u, stride = a.th + 1;
-  uint32_t H;
-  hash_words(T, W, H);
-  uint32_t* bitmap = buf;
-  uint32_t* prefix = buf + W;
-  uint16_t* segslot = reinterpret_cast<uint16_t*>(buf + 2 * W);
-  uint32_t* hist = buf + 2 * W + (T + 1) / 2;
-  uint32_t* table = hist + 2 * T;
-  const uint32_t shift = loc_bits + 5u, hbits = 32u - (uint32_t)__ffs(H) + 1u; // H = 2^(32 - hbits)
-  for (uint32_t i = lane; i < W; i += 32) bitmap[i] = 0u;
-  for (uint32_t i = lane; i < H; i += 32) table[i] = 0xFFFFFFFFu;
-  __syncwarp();
-  for_each_leaf_hit(ix, s, hb, nh, [&](uint32_t slot, uint32_t) { atomicOr(&bitmap[slot >> 5], 1u << (slot & 31u)); });
-  __syncwarp();
-  uint32_t nseg = 0;
-  for (uint32_t base = 0; base < W; base += 32) {
-    const uint32_t w = base + lane;
-    uint32_t bits = w < W ? bitmap[w] : 0u;
-    const uint32_t pc = __popc(bits);
-    uint32_t incl = pc;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += t; }
-    uint32_t at = nseg + incl - pc;
-    if (w < W) prefix[w] = at;
-    while (bits) { const uint32_t bit = (uint32_t)__ffs(bits) - 1u; bits &= bits - 1u; segslot[at++] = (uint16_t)(32u * w + bit); }
-    nseg += __shfl_sync(0xFFFFFFFFu, incl, 31);
-  }
-  for (uint32_t i = lane; i < 2 * nseg; i += 32) hist[i] = 0u;
-  __syncwarp();
-  for_each_leaf_hit(ix, s, hb, nh, [&](uint32_t slot, uint32_t low) {
-    const uint32_t w = slot >> 5, seg = prefix[w] + __popc(bitmap[w] & ((1u << (slot & 31u)) - 1u));
-    const uint32_t key = seg << shift | low; // segment | lookup << 5 | hd
-    uint32_t idx = ((key >> 5) * 0x9E3779B1u) >> hbits;
-    for (;;) {
-      const uint32_t old = atomicCAS(&table[idx], 0xFFFFFFFFu, key);
-      if (old == 0xFFFFFFFFu) break;
-      if (((old ^ key) >> 5) == 0u) { atomicMin(&table[idx], key); break; } // the same lookup on the same leaf: the smaller distance stays
-      idx = (idx + 1u) & (H - 1u);
-    }
-  });
-  __syncwarp();
-  for (uint32_t i = lane; i < H; i += 32) {
-    const uint32_t key = table[i];
-    if (key != 0xFFFFFFFFu) { const uint32_t hd = key & 31u; atomicAdd(&hist[2u * (key >> shift) + (hd >> 2)], 1u << (8u * (hd & 3u))); }
-  }
-  __syncwarp();
-  // gate (ref src/query.cpp:101-106,116-119), then the records in segment order
-  ResolveOut out;
-  out.total = 0; out.rbegin = 0; out.fits = true;
-  uint32_t total = 0;
-  for (uint32_t c = 0; c < nseg; c += 32) {
-    const uint32_t sg = c + lane;
-    bool pass = false;
-    if (sg < nseg) {
-      const uint32_t lo = hist[2 * sg], hi = hist[2 * sg + 1];
-      const uint32_t hdmin = lo ? ((uint32_t)__ffs(lo) - 1u) >> 3 : 4u + (((uint32_t)__ffs(hi) - 1u) >> 3);
-      pass = a.keep_all || !(hdmin > ((uint32_t)segslot[sg] >= ix.nleaves ? g1 : g0));
-    }
-    total += __popc(__ballot_sync(0xFFFFFFFFu, pass));
-  }
-  out.total = total;
-  if (!total) return out;
-  uint32_t rbegin = 0;
-  if (lane == 0) rbegin = atomicAdd(a.counters, total);
-  rbegin = __shfl_sync(0xFFFFFFFFu, rbegin, 0);
-  const bool fits = (uint64_t)rbegin + total <= a.rec_cap;
-  if (!fits && lane == 0) atomicOr(a.counters + 2, kErrRecOverflow);
-  out.rbegin = rbegin; out.fits = fits;
-  uint32_t done = 0;
-  for (uint32_t c = 0; c < nseg; c += 32) {
-    const uint32_t sg = c + lane;
-    bool pass = false;
-    uint32_t lo = 0, hi = 0, slot = 0;
-    if (sg < nseg) {
-      lo = hist[2 * sg]; hi = hist[2 * sg + 1]; slot = segslot[sg];
-      const uint32_t hdmin = lo ? ((uint32_t)__ffs(lo) - 1u) >> 3 : 4u + (((uint32_t)__ffs(hi) - 1u) >> 3);
-      pass = a.keep_all || !(hdmin > (slot >= ix.nleaves ? g1 : g0));
-    }
-    const uint32_t pm = __ballot_sync(0xFFFFFFFFu, pass);
-    if (pass && fits) {
-      const uint32_t at = rbegin + done + __popc(pm & lt_mask), strand = slot >= ix.nleaves ? 1u : 0u;
-      a.rec_read[at] = read;
-      a.rec_slot[at] = strand << 31 | __ldg(&ix.leaf_se[slot - strand * ix.nleaves]);
-#pragma unroll
-      for (uint32_t x = 0; x < 8u; ++x) if (x < stride) a.rec_hist[(size_t)at * stride + x] = ((x < 4u ? lo >> (8u * x) : hi >> (8u * (x - 4u))) & 0xFFu);
-    }
-    done += __popc(pm);
-  }
-  return out;
-}
-
 __global__ void __launch_bounds__(kResWarps * 32) resolve_kernel(const DevIndex ix, const MatchArgs a, const SortArgs s, uint32_t rank_bits)
 {
-  extern __shared__ __align__(16) uint32_t res_smem[]; // kResWarps x kResKeys words
-  uint32_t (*skeys)[kResKeys] = reinterpret_cast<uint32_t (*)[kResKeys]>(res_smem);
+  __shared__ __align__(16) uint32_t skeys[kResWarps][kResKeys];
   if (a.counters[2] & kErrRedo) return;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t gwarp = blockIdx.x * kResWarps + warp;
@@ -916,11 +778,7 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_kernel(const DevIndex 
       const uint32_t loc_bits = nlk <= 1u ? 0u : 32u - __clz(nlk - 1u);
       const bool narrow = 1u + rank_bits + loc_bits + 5u <= 32u;
       const bool small_counts = nlk < 256u && a.th < 8u;
-      const uint32_t W = (2u * ix.nleaves + 31u) >> 5;
-      uint32_t Hh;
       if (T64 == 0) { /* only colours without leaves: no records */ }
-      else if (small_counts && !s.resolve_sort && 2u * ix.nleaves <= 65536u && T64 <= 1024ull && hash_words((uint32_t)T64, W, Hh) <= (uint32_t)kResKeys)
-        out = resolve_hash(ix, a, s, skeys[warp], hb, nh, (uint32_t)T64, W, loc_bits, read, g0, g1);
       else if (narrow && T64 <= (unsigned long long)kResKeys)
         out = resolve_read<uint32_t>(ix, a, s, skeys[warp], hb, nh, (uint32_t)T64, rank_bits, loc_bits, read, g0, g1, small_counts);
       else if (!narrow && T64 <= (unsigned long long)(kResKeys / 2))
@@ -946,7 +804,7 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_kernel(const DevIndex 
 
 static size_t lookup_smem(uint32_t k) { return lut_chunks(k) * 256 * sizeof(uint4) + kLkWarps * sizeof(WarpSmem); }
 
-int sorted_resolve_warps(int sms) { return sms * 3 * kResWarps; } // grid of the resolve kernel: three CTAs of 64 KB shared memory per SM (sizes SortArgs::keys_g)
+int sorted_resolve_warps(int sms) { return sms * 6 * kResWarps; } // grid of the resolve kernel (sizes SortArgs::keys_g)
 
 // CTAs per SM of the scatter pass (KREPP_SCATTER_CTAS = 1 or 2, default 2).  Measured on B200 (r06, config 3): the pass takes
 // the same 4.6 ms per 1M reads with one CTA per SM as with two -- it is bound by the SM's limit on outstanding returning
@@ -969,7 +827,7 @@ static int scatter_ctas_per_sm()
 
 static int resolve_grid(const SortArgs& s, int sms)
 { // keys_g holds one region per warp of the grid it was sized for (api.cu grow_keys shrinks the grid when the regions get large)
-  const int dflt = std::min(sorted_resolve_warps(sms) / kResWarps, sms * env_int("KREPP_RESOLVE_CTAS", 3));
+  const int dflt = std::min(sorted_resolve_warps(sms) / kResWarps, sms * env_int("KREPP_RESOLVE_CTAS", 6));
   return s.res_ctas ? std::min<int>((int)s.res_ctas, dflt) : dflt;
 }
 int sorted_resolve_warps_per_cta() { return kResWarps; }
@@ -1047,8 +905,7 @@ cudaError_t launch_match_sorted(const DevIndex& ix, const MatchArgs& a, const So
   uint32_t rank_bits = 0;
   while ((1ull << rank_bits) < ix.nleaves) ++rank_bits;
   rank_bits += s.extra_rank_bits;
-  if ((e = cudaFuncSetAttribute(resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kResWarps * kResKeys * 4)) != cudaSuccess) return e;
-  resolve_kernel<<<resolve_grid(s, sms), kResWarps * 32, kResWarps * kResKeys * 4, stream>>>(ix, a, s, rank_bits);
+  resolve_kernel<<<resolve_grid(s, sms), kResWarps * 32, 0, stream>>>(ix, a, s, rank_bits);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   if (clk) clk->tick("resolve_kernel", stream);
   if (launches) *launches += 6;
@@ -1096,8 +953,7 @@ cudaError_t launch_shard_finish(const DevIndex& ix, const MatchArgs& a, const So
   uint32_t rank_bits = 0;
   while ((1ull << rank_bits) < ix.nleaves) ++rank_bits;
   rank_bits += s.extra_rank_bits;
-  if ((e = cudaFuncSetAttribute(resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kResWarps * kResKeys * 4)) != cudaSuccess) return e;
-  resolve_kernel<<<resolve_grid(s, sms), kResWarps * 32, kResWarps * kResKeys * 4, stream>>>(ix, a, s, rank_bits);
+  resolve_kernel<<<resolve_grid(s, sms), kResWarps * 32, 0, stream>>>(ix, a, s, rank_bits);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   if (clk) clk->tick("resolve_kernel", stream);
   return cudaSuccess;

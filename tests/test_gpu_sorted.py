@@ -106,15 +106,11 @@ def test_sorted_place(env, sorted_pipeline):
 
 
 @needs_ref
-@pytest.mark.parametrize("resolve", ["hash", "sort"])
-def test_sorted_equals_fused_bit_for_bit(env, monkeypatch, resolve):
+def test_sorted_equals_fused_bit_for_bit(env, monkeypatch):
     """Both pipelines must return the same per-read summaries and, read by read, the same records (order included),
-    histograms and solved values; grown buffers (tiny initial capacity: one read per slot re-submitted with many) too.
-    Both forms of the resolve kernel: the sort-free one (shared-memory bitmap + hash set, the default where it fits) and the
-    sorting one (KREPP_RESOLVE=sort)."""
+    histograms and solved values; grown buffers (tiny initial capacity: one read per slot re-submitted with many) too."""
     import krepp_b200
     import synth
-    monkeypatch.setenv("KREPP_RESOLVE", resolve)
     seq, offs = synth.load_packed(os.path.join(TOY_DIR, "genomes.npz"))
     m = synth.sample_reads(seq, offs, 30000, seed=91)
     out = {}
