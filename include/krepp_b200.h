@@ -314,6 +314,10 @@ typedef struct krepp_reader krepp_reader_t;
 /* Replaces the QSeq constructor (src/rqseq.cpp:161-178): opens a FASTA/FASTQ file, plain or gzip (zlib gzopen). */
 int krepp_reader_open(const char* path, krepp_reader_t** out);
 void krepp_reader_close(krepp_reader_t* r);
+/* Worker threads krepp_reader_next may use (default 1).  With more than one, batches of plain (not gzip) four-line FASTQ are
+ * framed chunk-parallel from the mapped file; every record and the record order are those of the sequential reader (anything
+ * the chunks cannot prove -- FASTA, wrapped lines, a truncated tail -- is left to it), only batch boundaries may differ. */
+int krepp_reader_set_threads(krepp_reader_t* r, uint32_t threads);
 /* Replaces QSeq::read_next_batch (src/rqseq.cpp:180-197) over kseq_read (src/kseq.h:177-216) with the same record
  * framing: a record starts at '>' or '@'; the name is the header up to the first whitespace; sequence characters are
  * all printable non-space bytes up to the next '>', '@' or '+'; after '+' the rest of that line is skipped and as many

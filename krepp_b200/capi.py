@@ -170,6 +170,7 @@ def load_library():
     L.krepp_extract_mers.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.krepp_reader_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
     L.krepp_reader_close.argtypes = [C.c_void_p]
+    L.krepp_reader_set_threads.argtypes = [C.c_void_p, C.c_uint32]
     L.krepp_reader_next.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p,
                                     C.POINTER(C.c_uint32), C.POINTER(C.c_int)]
     for f in ("krepp_format_header", "krepp_format_dist", "krepp_format_place", "krepp_format_footer"):
@@ -470,9 +471,11 @@ class IBatch:
 class Reader:
     """FASTA/FASTQ batch reader with kseq framing (replaces QSeq, src/rqseq.cpp:161-197)."""
 
-    def __init__(self, path: str):
+    def __init__(self, path: str, threads: int = 1):
         self._h = C.c_void_p()
         _check(load_library().krepp_reader_open(os.fsencode(path), C.byref(self._h)))
+        if threads > 1:
+            _check(load_library().krepp_reader_set_threads(self._h, threads))
 
     def close(self):
         if getattr(self, "_h", None):

@@ -20,8 +20,11 @@
 #include <limits>
 #include <mutex>
 #include <string>
+#include <atomic>
+#include <fcntl.h>
 #include <sys/stat.h>
 #include <thread>
+#include <unistd.h>
 #include <vector>
 
 namespace {
@@ -404,14 +407,20 @@ int main(int argc, char** argv)
   uint64_t total_queries = 0;
   std::vector<double> wcount(info.nnodes + 1, 0.0);
 
-  // The text of a batch is formatted by --num-threads workers into one of two buffer sets and written by a writer thread of its
-  // own, so that the next batch is formatted (and its slot handed back to the reader) while this one goes to the file.
+  // The text of a batch is formatted by --num-threads workers, each into its own buffer.  When the output is a regular file the
+  // workers also write: once all of them know their lengths, every worker pwrite()s its part at its own offset, so neither the
+  // formatting nor the copy into the page cache is serial.  Otherwise (a pipe, a terminal) the parts go to a writer thread of
+  // their own through one of two buffer sets, so that the next batch is formatted while this one is written.
   struct TextSet { std::vector<std::vector<char>> part; std::vector<size_t> len; };
   const uint32_t T = o.num_threads;
   std::vector<TextSet> sets(2);
   Channel<TextSet*> sets_free, sets_full;
   for (TextSet& ts : sets) { ts.part.assign(T, std::vector<char>(1 << 20)); ts.len.assign(T, 0); sets_free.push(&ts); }
   const bool jplace = place && !o.tabular && !p.summarize;
+  bool direct = false;
+  off_t file_off = 0;
+  { struct stat st; fflush(out); direct = fstat(fileno(out), &st) == 0 && S_ISREG(st.st_mode) && !(fcntl(fileno(out), F_GETFL) & O_APPEND); if (direct) file_off = lseek(fileno(out), 0, SEEK_CUR); if (file_off < 0) direct = false; }
+  int wrote_any = 0; // (direct mode) a placement was already written: the next one is preceded by ",\n" (ref src/krepp.cpp:476-481)
 
   std::thread writer([&] {
     int has_previous = 0;
@@ -435,6 +444,8 @@ int main(int argc, char** argv)
       check(krepp_batch_wait(s->batch, &res));
       TextSet* ts = nullptr;
       sets_free.pop(ts);
+      std::atomic<uint32_t> formatted{0};
+      std::atomic<int> failed{0};
       // split the batch's reads over T workers; every worker formats its range into its own buffer
       auto work = [&](uint32_t t) {
         const uint32_t lo = (uint32_t)((uint64_t)res.n_reads * t / T), hi = (uint32_t)((uint64_t)res.n_reads * (t + 1) / T);
@@ -453,12 +464,31 @@ int main(int argc, char** argv)
           buf.resize(n + n / 4);
           if (w) part_w[t].assign(info.nnodes + 1, 0.0);
         }
+        if (!direct || p.summarize) return;
+        // direct mode: wait until every part's length is known, then write this one at its offset
+        formatted.fetch_add(1, std::memory_order_release);
+        while (formatted.load(std::memory_order_acquire) < T) std::this_thread::yield();
+        off_t at = file_off;
+        int before = wrote_any;
+        for (uint32_t u = 0; u < t; ++u) if (ts->len[u]) { at += (off_t)ts->len[u] + ((jplace && before) ? 2 : 0); before = 1; }
+        if (!ts->len[t]) return;
+        if (jplace && before) { if (pwrite(fileno(out), ",\n", 2, at) != 2) failed = 1; at += 2; }
+        size_t done = 0;
+        while (done < ts->len[t]) {
+          const ssize_t k = pwrite(fileno(out), buf.data() + done, ts->len[t] - done, at + (off_t)done);
+          if (k <= 0) { failed = 1; break; }
+          done += (size_t)k;
+        }
       };
       if (T == 1) work(0);
-      else { std::vector<std::thread> th; for (uint32_t t = 0; t < T; ++t) th.emplace_back(work, t); for (auto& x : th) x.join(); }
+      else { std::vector<std::thread> th; for (uint32_t t = 1; t < T; ++t) th.emplace_back(work, t); work(0); for (auto& x : th) x.join(); }
+      if (failed) error_exit("Failed to write the output");
       free_q.push(s); // results and names are no longer needed: the reader may fill the slot again
       if (p.summarize) {
         for (uint32_t t = 0; t < T; ++t) { for (uint32_t se = 0; se <= info.nnodes; ++se) wcount[se] += part_w[t][se]; ts->len[t] = 0; }
+        sets_free.push(ts);
+      } else if (direct) {
+        for (uint32_t t = 0; t < T; ++t) if (ts->len[t]) { file_off += (off_t)ts->len[t] + ((jplace && wrote_any) ? 2 : 0); wrote_any = 1; ts->len[t] = 0; }
         sets_free.push(ts);
       } else sets_full.push(ts);
     }
@@ -467,6 +497,7 @@ int main(int argc, char** argv)
 
   krepp_reader_t* reader = nullptr;
   check(krepp_reader_open(o.query.c_str(), &reader));
+  check(krepp_reader_set_threads(reader, o.num_threads)); // plain four-line FASTQ is framed chunk-parallel
   for (;;) {
     Slot* s = nullptr;
     free_q.pop(s);
@@ -484,6 +515,7 @@ int main(int argc, char** argv)
   consumer.join();
   writer.join();
 
+  if (direct) fseeko(out, file_off, SEEK_SET); // the batches were written behind stdio's back
   { // --summarize table / end_jplace
     size_t n = krepp_format_footer(index[0], &p, o.tabular, wcount.data(), total_queries, invocation.c_str(), text.data(), text.size());
     if (n > text.size()) { text.resize(n); n = krepp_format_footer(index[0], &p, o.tabular, wcount.data(), total_queries, invocation.c_str(), text.data(), text.size()); }

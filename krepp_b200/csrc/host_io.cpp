@@ -12,6 +12,7 @@
 #include <zlib.h>
 
 #include <fcntl.h>
+#include <sys/stat.h>
 #include <unistd.h>
 
 #include <cmath>
@@ -19,6 +20,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <chrono>
+#include <thread>
 #include <vector>
 
 using namespace krepp;
@@ -63,6 +66,12 @@ struct krepp_reader {
   bool have_pending = false; // a complete record that did not fit the previous batch
   bool fast = true;          // four-line FASTQ fast path (KREPP_READER_FAST=0 leaves every record to the state machine)
   std::string pend_name, pend_seq;
+  // plain regular files are read with pread at explicit offsets, and with several threads (krepp_reader_set_threads) whole
+  // batches of four-line FASTQ are framed chunk-parallel from a window the threads pread together (parallel_fastq below)
+  bool regular = false;
+  size_t file_len = 0, file_at = 0; // file_at: file offset of the first byte not yet handed to buf
+  std::vector<unsigned char> win;   // the parallel path's window of the file
+  uint32_t threads = 1;
 };
 
 namespace {
@@ -73,7 +82,8 @@ size_t read_input(krepp_reader* r, unsigned char* dst, size_t want)
   size_t got = 0;
   while (got < want) {
     long n;
-    if (r->fd >= 0) n = (long)read(r->fd, dst + got, want - got);
+    if (r->regular) { n = (long)pread(r->fd, dst + got, want - got, (off_t)r->file_at); if (n > 0) r->file_at += (size_t)n; }
+    else if (r->fd >= 0) n = (long)read(r->fd, dst + got, want - got);
     else n = gzread(r->f, dst + got, (unsigned)(want - got));
     if (n <= 0) break;
     got += (size_t)n;
@@ -240,6 +250,174 @@ bool fast_fastq(krepp_reader* r, char* bases, uint64_t max_bases, uint64_t& nb, 
 
 } // namespace
 
+namespace {
+
+struct FqRec { uint32_t name_len, len; uint64_t name_off, seq_off; };
+
+// The conditions of fast_fastq on raw pointers: a four-line FASTQ record starting at p ('@'), lying whole in [p, e) together with
+// the byte that follows its last quality character.  Returns the position after that byte, or nullptr.
+inline const unsigned char* probe_fastq(const unsigned char* base, const unsigned char* p, const unsigned char* e, FqRec* rec)
+{
+  if (p >= e || *p != '@') return nullptr;
+  const unsigned char* nl1 = static_cast<const unsigned char*>(memchr(p + 1, '\n', e - (p + 1)));
+  if (!nl1) return nullptr;
+  const unsigned char* ne = p + 1;
+  while (!kClass.space[*ne]) ++ne;
+  const size_t name_len = ne - (p + 1);
+  if (name_len == 0) return nullptr;
+  const unsigned char* sq = nl1 + 1;
+  const unsigned char* nl2 = static_cast<const unsigned char*>(memchr(sq, '\n', e - sq));
+  if (!nl2 || nl2 + 1 >= e || nl2[1] != '+') return nullptr;
+  const size_t len = nl2 - sq;
+  if (len > 0xFFFFFFFFull || name_len > 0xFFFFFFFFull || !all_seq_chars(sq, len)) return nullptr;
+  const unsigned char* nl3 = static_cast<const unsigned char*>(memchr(nl2 + 1, '\n', e - (nl2 + 1)));
+  if (!nl3) return nullptr;
+  const unsigned char* q = nl3 + 1;
+  if ((size_t)(e - q) < len + 1 || !all_qual_chars(q, len)) return nullptr;
+  rec->name_len = (uint32_t)name_len; rec->len = (uint32_t)len; rec->name_off = (uint64_t)(p + 1 - base); rec->seq_off = (uint64_t)(sq - base);
+  return q + len + 1;
+}
+
+// Chunk-parallel framing of one batch from the mapped file.  The parser stands in state Seek at file offset `pos`.  The window
+// that should hold the batch is cut into one chunk per thread; every thread but the first looks for a record start in its chunk
+// (a line starting with '@' from which probe_fastq succeeds: in four-line FASTQ a quality line that starts with '@' is followed
+// by a header line, which is no sequence line, so it cannot be mistaken) and frames records up to the next thread's start.  The
+// result is accepted as far as the chunks stitch: thread t must end exactly where thread t + 1 began, which by induction from
+// the true boundary `pos` makes every start a true boundary -- the records are then the ones the sequential state machine walks,
+// because probe_fastq's conditions are those under which it walks a record as Name -> Seq -> Plus -> Qual -> QualTail -> Seek.
+// Returns the number of records taken (0: nothing usable here, leave the batch to the sequential path).
+uint32_t parallel_fastq(krepp_reader* r, size_t pos, char* bases, uint64_t max_bases, uint64_t* offsets, uint32_t max_reads, char* names,
+                        uint64_t max_name_bytes, uint64_t* name_offsets, size_t* new_pos)
+{
+  // the first record (from a small read) sizes the window; then the threads pread the window together.  Offsets below are
+  // relative to the window: `base` is file offset `pos`.
+  if (pos >= r->file_len) return 0;
+  unsigned char head[4096];
+  const size_t hn = (size_t)std::max<ssize_t>(0, pread(r->fd, head, std::min<size_t>(sizeof head, r->file_len - pos), (off_t)pos));
+  FqRec first;
+  const unsigned char* after = probe_fastq(head, head, head + hn, &first);
+  if (!after) return 0;
+  const size_t rec_bytes = (size_t)(after - head);
+  uint64_t want = max_reads;
+  if (first.len) want = std::min<uint64_t>(want, max_bases / first.len);
+  want = std::min<uint64_t>(want, max_name_bytes / (first.name_len + 1ull));
+  if (want < 1024) return 0; // small batches: not worth the threads
+  // a little more than the batch should need, so that its last record (and the byte after it) lies inside the window
+  const size_t window = (size_t)std::min<uint64_t>((uint64_t)r->file_len - pos, want * rec_bytes + (1u << 16));
+  const uint32_t T = (uint32_t)std::max<size_t>(1, std::min<size_t>(r->threads, window >> 18));
+  static const bool dbg = getenv("KREPP_READER_DEBUG") != nullptr;
+  const auto t0 = std::chrono::steady_clock::now();
+  if (r->win.size() < window) r->win.resize(window);
+  {
+    auto fill = [&](uint32_t t) {
+      size_t lo = window / T * t, hi = t + 1 == T ? window : window / T * (t + 1);
+      while (lo < hi) { const ssize_t got = pread(r->fd, r->win.data() + lo, hi - lo, (off_t)(pos + lo)); if (got <= 0) break; lo += (size_t)got; }
+    };
+    std::vector<std::thread> th;
+    for (uint32_t t = 1; t < T; ++t) th.emplace_back(fill, t);
+    fill(0);
+    for (auto& x : th) x.join();
+  }
+  const auto t1 = std::chrono::steady_clock::now();
+  const unsigned char* base = r->win.data();
+  const unsigned char* const fe = base + window;
+  pos = 0; // window-relative from here on
+  std::vector<size_t> start(T, 0), stop(T, 0);
+  std::vector<std::vector<FqRec>> recs(T);
+  std::vector<uint64_t> tb(T, 0), tn(T, 0);
+  // every thread but the first finds the first record start after its chunk's nominal boundary, then frames records while they
+  // start at or before the next chunk's nominal boundary -- so it ends on the start the next thread finds, if both are right
+  auto frame = [&](uint32_t t) {
+    size_t at = window / T * t;
+    const size_t lim = t + 1 == T ? window : window / T * (t + 1);
+    FqRec rec;
+    if (t) {
+      for (;;) {
+        const unsigned char* nl = static_cast<const unsigned char*>(memchr(base + at, '\n', (size_t)(fe - (base + at))));
+        if (!nl || nl + 1 >= fe) { at = window; break; }
+        at = (size_t)(nl + 1 - base);
+        if (base[at] == '@' && probe_fastq(base, base + at, fe, &rec)) break;
+      }
+    }
+    start[t] = at;
+    std::vector<FqRec>& v = recs[t];
+    v.reserve((lim > at ? lim - at : 0) / std::max<size_t>(rec_bytes, 1) + 16);
+    uint64_t b = 0, nn = 0;
+    while (at <= lim && at < window) {
+      const unsigned char* nx = probe_fastq(base, base + at, fe, &rec);
+      if (!nx) break;
+      v.push_back(rec);
+      b += rec.len; nn += rec.name_len + 1ull;
+      at = (size_t)(nx - base);
+    }
+    stop[t] = at; tb[t] = b; tn[t] = nn;
+  };
+  {
+    std::vector<std::thread> th;
+    for (uint32_t t = 1; t < T; ++t) th.emplace_back(frame, t);
+    frame(0);
+    for (auto& x : th) x.join();
+  }
+  const auto t2 = std::chrono::steady_clock::now();
+  // 3. how far the chunks stitch, and how many records the batch limits admit
+  std::vector<uint64_t> keep(T, 0), rbase(T, 0), bbase(T, 0), nbase(T, 0);
+  uint64_t nr = 0, nb = 0, nn = 0;
+  size_t endpos = pos;
+  for (uint32_t t = 0; t < T; ++t) {
+    if (t && stop[t - 1] != start[t]) break; // the previous chunk did not end on this chunk's start: what follows is not proven
+    rbase[t] = nr; bbase[t] = nb; nbase[t] = nn;
+    uint64_t k = recs[t].size();
+    if (nr + k > max_reads || nb + tb[t] > max_bases || nn + tn[t] > max_name_bytes) { // the cut falls inside this chunk
+      k = 0;
+      uint64_t b = nb, m = nn;
+      while (k < recs[t].size() && nr + k < max_reads && b + recs[t][k].len <= max_bases && m + recs[t][k].name_len + 1ull <= max_name_bytes) {
+        b += recs[t][k].len; m += recs[t][k].name_len + 1ull; ++k;
+      }
+      keep[t] = k; nr += k; nb = b; nn = m;
+      endpos = k < recs[t].size() ? (size_t)recs[t][k].name_off - 1 : stop[t];
+      break;
+    }
+    keep[t] = k; nr += k; nb += tb[t]; nn += tn[t];
+    endpos = stop[t];
+  }
+  if (!nr) return 0;
+  auto copy = [&](uint32_t t) { // 4. into the batch arrays
+    uint64_t b = bbase[t], m = nbase[t], i = rbase[t];
+    for (uint64_t k = 0; k < keep[t]; ++k, ++i) {
+      const FqRec& rc = recs[t][k];
+      memcpy(bases + b, base + rc.seq_off, rc.len);
+      b += rc.len;
+      name_offsets[i] = m;
+      memcpy(names + m, base + rc.name_off, rc.name_len);
+      names[m + rc.name_len] = 0;
+      m += rc.name_len + 1ull;
+      offsets[i + 1] = b;
+    }
+  };
+  {
+    std::vector<std::thread> th;
+    for (uint32_t t = 1; t < T; ++t) if (keep[t]) th.emplace_back(copy, t);
+    copy(0);
+    for (auto& x : th) x.join();
+  }
+  if (dbg) {
+    const auto t3 = std::chrono::steady_clock::now();
+    auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    fprintf(stderr, "[reader] %u threads, window %zu B: pread %.2f ms, frame %.2f ms, stitch+copy %.2f ms, %llu reads\n", T, window, ms(t0, t1), ms(t1, t2), ms(t2, t3), (unsigned long long)nr);
+  }
+  *new_pos = endpos; // window-relative
+  return (uint32_t)nr;
+}
+
+} // namespace
+
+extern "C" int krepp_reader_set_threads(krepp_reader_t* r, uint32_t threads)
+{
+  if (!r) return set_error(KREPP_ERR_ARG, "krepp_reader_set_threads: null reader");
+  r->threads = threads ? threads : 1;
+  return KREPP_OK;
+}
+
 extern "C" int krepp_reader_open(const char* path, krepp_reader_t** out)
 {
   if (!path || !out) return set_error(KREPP_ERR_ARG, "krepp_reader_open: null argument");
@@ -259,6 +437,10 @@ extern "C" int krepp_reader_open(const char* path, krepp_reader_t** out)
   auto* r = new krepp_reader;
   r->f = f; r->fd = fd;
   r->buf.resize(4 << 20);
+  if (fd >= 0) { // plain input: a regular file is read with pread (a pipe keeps read(2))
+    struct stat st;
+    if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode)) { r->regular = true; r->file_len = (size_t)st.st_size; }
+  }
   if (const char* env = getenv("KREPP_READER_FAST")) r->fast = strcmp(env, "0") != 0;
   *out = r;
   return KREPP_OK;
@@ -296,6 +478,16 @@ extern "C" int krepp_reader_next(krepp_reader_t* r, char* bases, uint64_t max_ba
       return set_error(KREPP_ERR_CAPACITY, "a single sequence of %zu bases (name of %zu bytes) does not fit the batch buffers", r->pend_seq.size(), r->pend_name.size());
     put(r->pend_name, r->pend_seq);
     r->have_pending = false;
+  }
+  if (r->regular && r->threads > 1 && r->fast && n == 0 && r->st == St::Seek) { // whole batch chunk-parallel
+    const size_t pos = r->file_at - (r->end - r->at);
+    size_t rel = 0;
+    const uint32_t got = parallel_fastq(r, pos, bases, max_bases, offsets, max_reads, names, max_name_bytes, name_offsets, &rel);
+    if (got) {
+      r->file_at = pos + rel; r->at = r->end = 0; r->eof = false; // the buffer's read-ahead is dropped: the next bytes are read at file_at
+      *n_reads = got;
+      return KREPP_OK; // (the end of the input is reported by the next call, which finds nothing left)
+    }
   }
   for (;;) {
     if (n >= max_reads) break;

@@ -319,3 +319,39 @@ def test_reader_fast_path_equals_state_machine(K, tmp_path, monkeypatch):
             f.write(b"@q%d\n" % i + seq(150) + b"\n+\n" + qual(150) + b"\n" if i % 50 else record(i))
     a, b = parse(big, True), parse(big, False)
     assert a == b and len(a[0]) > 29000
+
+
+def test_reader_chunk_parallel_equals_sequential(K, tmp_path, monkeypatch):
+    """krepp_reader_set_threads: batches framed chunk-parallel from the mapped file hold exactly the records (and order) of the
+    sequential reader -- clean four-line FASTQ with '@'-leading quality lines (the false record starts a chunk could land on),
+    variable read lengths, a malformed stretch in the middle (wrapped records, FASTA) that only the state machine can walk, a
+    truncated last record, and every batch limit (reads, bases, name bytes) cutting the batches."""
+    import random
+    rng = random.Random(11)
+
+    def seq(n):
+        return bytes(rng.choice(b"ACGTN") for _ in range(n))
+
+    def qual(n):
+        return bytes(rng.choice(b"@@@IIIIFFF#5:<+>") for _ in range(n))
+
+    path = tmp_path / "par.fq"
+    with open(path, "wb") as f:
+        for i in range(120000):
+            n = rng.choice([150, 150, 150, 151, 100, 27, 250])
+            if 60000 <= i < 60040:   # a stretch the fast path cannot frame
+                h = n // 2
+                s, q = seq(n), qual(n)
+                f.write(b"@w%d\n" % i + s[:h] + b"\n" + s[h:] + b"\n+\n" + q[:h] + b"\n" + q[h:] + b"\n" if i % 2 else b">fa%d\n" % i + seq(n) + b"\n")
+            else:
+                f.write(b"@r%d c\n" % i + seq(n) + b"\n+\n" + qual(n) + b"\n")
+        f.write(b"@last\nACGTACGT\n+\nIIII")   # truncated quality: no record
+    monkeypatch.setenv("KREPP_READER_FAST", "0")
+    want = K.Reader(str(path)).read_all(max_reads=1 << 17, max_bases=1 << 25)
+    monkeypatch.setenv("KREPP_READER_FAST", "1")
+    assert len(want[0]) == 120000
+    for threads in (2, 5, 8):
+        for kw in (dict(max_reads=1 << 16, max_bases=1 << 24), dict(max_reads=40000, max_bases=3_000_000), dict(max_reads=1 << 16, max_bases=1 << 24, max_name_bytes=300_000),
+                   dict(max_reads=3000, max_bases=1 << 22)):
+            got = K.Reader(str(path), threads=threads).read_all(**kw)
+            assert got == want, (threads, kw, len(got[0]))
