@@ -420,6 +420,9 @@ int main(int argc, char** argv)
   bool direct = false;
   off_t file_off = 0;
   { struct stat st; fflush(out); direct = fstat(fileno(out), &st) == 0 && S_ISREG(st.st_mode) && !(fcntl(fileno(out), F_GETFL) & O_APPEND); if (direct) file_off = lseek(fileno(out), 0, SEEK_CUR); if (file_off < 0) direct = false; }
+  double t_read = 0, t_wait = 0, t_format = 0, t_submit = 0; // --verbose: seconds the reader / consumer spent in each stage
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
   int wrote_any = 0; // (direct mode) a placement was already written: the next one is preceded by ",\n" (ref src/krepp.cpp:476-481)
 
   std::thread writer([&] {
@@ -441,7 +444,10 @@ int main(int argc, char** argv)
     Slot* s = nullptr;
     while (busy_q.pop(s)) {
       krepp_results_t res;
+      const auto tw0 = now();
       check(krepp_batch_wait(s->batch, &res));
+      const auto tw1 = now();
+      t_wait += secs(tw0, tw1);
       TextSet* ts = nullptr;
       sets_free.pop(ts);
       std::atomic<uint32_t> formatted{0};
@@ -483,6 +489,7 @@ int main(int argc, char** argv)
       if (T == 1) work(0);
       else { std::vector<std::thread> th; for (uint32_t t = 1; t < T; ++t) th.emplace_back(work, t); work(0); for (auto& x : th) x.join(); }
       if (failed) error_exit("Failed to write the output");
+      t_format += secs(tw1, now());
       free_q.push(s); // results and names are no longer needed: the reader may fill the slot again
       if (p.summarize) {
         for (uint32_t t = 0; t < T; ++t) { for (uint32_t se = 0; se <= info.nnodes; ++se) wcount[se] += part_w[t][se]; ts->len[t] = 0; }
@@ -502,10 +509,14 @@ int main(int argc, char** argv)
     Slot* s = nullptr;
     free_q.pop(s);
     int eof = 0;
+    const auto tr0 = now();
     check(krepp_reader_next(reader, s->bases, o.batch_bases, s->offsets, o.batch_reads, s->names.data(), s->names.size(), s->name_off.data(), &s->n, &eof));
+    const auto tr1 = now();
+    t_read += secs(tr0, tr1);
     if (s->n) {
       total_queries += s->n;
       check(krepp_batch_submit(s->batch, s->bases, s->offsets, s->n));
+      t_submit += secs(tr1, now());
       busy_q.push(s);
     } else free_q.push(s);
     if (eof) break;
@@ -526,6 +537,8 @@ int main(int argc, char** argv)
   const std::chrono::duration<float> es = std::chrono::system_clock::now() - tquery;
   fprintf(stderr, place ? "Done placing queries, elapsed: %g sec\n" : "Done estimating distances, elapsed: %g sec\n", es.count());
   fprintf(stderr, "Total number of sequences queried: %llu\n", (unsigned long long)total_queries);
+  if (o.verbose) fprintf(stderr, "[stages] reader %.3f s, submit %.3f s (producer thread); waiting for the GPU %.3f s, formatting + writing %.3f s (consumer thread)%s\n",
+                         t_read, t_submit, t_wait, t_format, direct ? "; output written by the formatter threads (pwrite)" : "");
   for (Slot& s : slots) krepp_batch_destroy(s.batch);
   for (krepp_index_t* ix : index) krepp_index_close(ix);
   { std::time_t t = std::chrono::system_clock::to_time_t(std::chrono::system_clock::now()); fprintf(stderr, "%s", std::ctime(&t)); }

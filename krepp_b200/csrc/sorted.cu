@@ -664,7 +664,7 @@ struct ResolveOut { uint32_t total, rbegin; bool fits; };
 // bits of lookup + hd; every lane returns the same ResolveOut.
 template <typename K>
 __device__ __forceinline__ ResolveOut emit_sorted(const DevIndex& ix, const MatchArgs& a, const K* keys, uint32_t T, uint32_t seg_shift, uint32_t rank_bits,
-                                                  uint32_t read, uint32_t g0, uint32_t g1)
+                                                  uint32_t read, uint32_t g0, uint32_t g1, bool small_counts)
 {
   const uint32_t lane = threadIdx.x & 31, lt_mask = (1u << lane) - 1u, stride = a.th + 1;
   // pass A: (strand, leaf) segments that pass the hdist_filt gate
@@ -707,16 +707,29 @@ __device__ __forceinline__ ResolveOut emit_sorted(const DevIndex& ix, const Matc
       const K sg = kk >> seg_shift;
       if (i == 0 || (keys[i - 1] >> seg_shift) != sg) {
         uint32_t hdmin = 0xFFFFFFFFu;
-        K prev_lk = ~(K)0;
-        for (uint32_t j = i; j < T; ++j) {
-          const K kj = keys[j];
-          if ((kj >> seg_shift) != sg) break;
-          const K lk = kj >> 5;
-          if (lk != prev_lk) {
-            const uint32_t hd = (uint32_t)kj & 31u;
+        if (small_counts) { // every count < 256 and th < 8: eight 8-bit counters in one word
+          unsigned long long packed = 0;
+          K prev_lk = ~(K)0;
+          for (uint32_t j = i; j < T; ++j) {
+            const K kj = keys[j];
+            if ((kj >> seg_shift) != sg) break;
+            const K lk = kj >> 5;
+            if (lk != prev_lk) { const uint32_t hd = (uint32_t)kj & 31u; packed += 1ull << (8u * hd); hdmin = min(hdmin, hd); prev_lk = lk; }
+          }
 #pragma unroll
-            for (int x = 0; x <= kMaxTh; ++x) hv[x] += (hd == (uint32_t)x);
-            hdmin = min(hdmin, hd); prev_lk = lk;
+          for (int x = 0; x < 8; ++x) hv[x] = (uint32_t)(packed >> (8 * x)) & 0xFFu;
+        } else {
+          K prev_lk = ~(K)0;
+          for (uint32_t j = i; j < T; ++j) {
+            const K kj = keys[j];
+            if ((kj >> seg_shift) != sg) break;
+            const K lk = kj >> 5;
+            if (lk != prev_lk) {
+              const uint32_t hd = (uint32_t)kj & 31u;
+#pragma unroll
+              for (int x = 0; x <= kMaxTh; ++x) hv[x] += (hd == (uint32_t)x);
+              hdmin = min(hdmin, hd); prev_lk = lk;
+            }
           }
         }
         strand = (uint32_t)(sg >> rank_bits);
@@ -733,72 +746,6 @@ __device__ __forceinline__ ResolveOut emit_sorted(const DevIndex& ix, const Matc
       for (int x = 0; x <= kMaxTh; ++x) if ((uint32_t)x < stride) a.rec_hist[(size_t)at * stride + x] = hv[x];
     }
     done += __popc(pm);
-  }
-  return out;
-}
-
-// The same records for a read whose counts fit eight 8-bit counters (fewer than 256 lookups, th < 8 -- every short read): one
-// segmented scan per 32 keys instead of a lane walking each segment.  A key counts when it is the first of its lookup (its
-// smallest distance); the scan adds those counts, packed by distance, along each (strand, leaf) segment, so the key that ends
-// a segment holds the segment's histogram.  Two sweeps as above: count the segments that pass the gate, reserve, write.
-template <typename K>
-__device__ __forceinline__ ResolveOut emit_sorted_scan(const DevIndex& ix, const MatchArgs& a, const K* keys, uint32_t T, uint32_t seg_shift, uint32_t rank_bits,
-                                                       uint32_t read, uint32_t g0, uint32_t g1)
-{
-  const uint32_t lane = threadIdx.x & 31, lt_mask = (1u << lane) - 1u, stride = a.th + 1;
-  ResolveOut out;
-  out.total = 0; out.rbegin = 0; out.fits = true;
-  uint32_t rbegin = 0, done = 0;
-  bool fits = true;
-  for (int sweep = 0; sweep < 2; ++sweep) {
-    unsigned long long carry = 0; // histogram so far of the segment that runs into this chunk
-    uint32_t total = 0;
-    for (uint32_t c = 0; c < T; c += 32) {
-      const uint32_t i = c + lane;
-      const bool in = i < T;
-      const K kk = in ? keys[i] : (K)0;
-      K kp = __shfl_up_sync(0xFFFFFFFFu, kk, 1), kn = __shfl_down_sync(0xFFFFFFFFu, kk, 1);
-      if (lane == 0 && i > 0 && in) kp = keys[i - 1];
-      if (lane == 31 && i + 1 < T) kn = keys[i + 1];
-      const K sg = kk >> seg_shift;
-      const bool head = in && (i == 0 || (kp >> seg_shift) != sg);
-      const bool first = head || (kp >> 5) != (kk >> 5);
-      const bool tail = in && (i + 1 == T || (kn >> seg_shift) != sg);
-      unsigned long long v = (in && first) ? 1ull << (8u * ((uint32_t)kk & 7u)) : 0ull;
-      bool f = head;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const unsigned long long vu = __shfl_up_sync(0xFFFFFFFFu, v, o);
-        const int fu = __shfl_up_sync(0xFFFFFFFFu, (int)f, o);
-        if (lane >= (uint32_t)o && !f) { v += vu; f = fu != 0; }
-      }
-      if (!f) v += carry; // no segment starts at or before this lane in the chunk: it began in an earlier one
-      const unsigned long long v31 = __shfl_sync(0xFFFFFFFFu, v, 31);
-      carry = __shfl_sync(0xFFFFFFFFu, (int)tail, 31) ? 0ull : v31;
-      const uint32_t strand = (uint32_t)(sg >> rank_bits), hdmin = ((uint32_t)__ffsll((long long)v) - 1u) >> 3;
-      const bool pass = tail && (a.keep_all || !(hdmin > (strand ? g1 : g0)));
-      const uint32_t pm = __ballot_sync(0xFFFFFFFFu, pass);
-      if (sweep == 0) total += __popc(pm);
-      else {
-        if (pass && fits) {
-          const uint32_t at = rbegin + done + __popc(pm & lt_mask), rank = (uint32_t)sg & ((1u << rank_bits) - 1u);
-          a.rec_read[at] = read;
-          a.rec_slot[at] = strand << 31 | __ldg(&ix.leaf_se[rank]);
-#pragma unroll
-          for (uint32_t x = 0; x < 8u; ++x) if (x < stride) a.rec_hist[(size_t)at * stride + x] = (uint32_t)(v >> (8u * x)) & 0xFFu;
-        }
-        done += __popc(pm);
-      }
-    }
-    if (sweep == 0) {
-      out.total = total;
-      if (!total) return out;
-      if (lane == 0) rbegin = atomicAdd(a.counters, total);
-      rbegin = __shfl_sync(0xFFFFFFFFu, rbegin, 0);
-      fits = (uint64_t)rbegin + total <= a.rec_cap;
-      if (!fits && lane == 0) atomicOr(a.counters + 2, kErrRecOverflow);
-      out.rbegin = rbegin; out.fits = fits;
-    }
   }
   return out;
 }
@@ -849,11 +796,10 @@ __device__ __forceinline__ ResolveOut resolve_read(const DevIndex& ix, const Mat
   else if (n == 256 && sizeof(K) == 4) bitonic_sort_regs<K, (sizeof(K) == 4 ? 8 : 4)>(keys);
   else bitonic_sort_blocks<K>(keys, n);
   __syncwarp();
-  if (small_counts) return emit_sorted_scan<K>(ix, a, keys, T, seg_shift, rank_bits, read, g0, g1);
-  return emit_sorted<K>(ix, a, keys, T, seg_shift, rank_bits, read, g0, g1);
+  return emit_sorted<K>(ix, a, keys, T, seg_shift, rank_bits, read, g0, g1, small_counts);
 }
 
-__global__ void __launch_bounds__(kResWarps * 32, 3) resolve_kernel(const DevIndex ix, const MatchArgs a, const SortArgs s, uint32_t rank_bits)
+__global__ void __launch_bounds__(kResWarps * 32, 4) resolve_kernel(const DevIndex ix, const MatchArgs a, const SortArgs s, uint32_t rank_bits)
 {
   __shared__ __align__(16) uint32_t skeys[kResWarps][kResKeys];
   if (a.counters[2] & kErrRedo) return;
