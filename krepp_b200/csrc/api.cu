@@ -348,7 +348,7 @@ int krepp_index_open_shard(const char* index_dir, int device, uint32_t shard, ui
   d.nkmers = h.nkmers; d.nrows = h.nrows; d.row0 = h.row0; d.nrows_local = h.row1 - h.row0; d.nsubsets = h.nsubsets; d.nnodes = h.tree.nnodes; d.nleaves = h.tree.nleaves;
   d.k = h.k; d.h = h.h; d.m = h.m;
   d.m_shift = (h.m & (h.m - 1)) == 0 ? (uint32_t)__builtin_ctz(h.m) : 0xFFFFFFFFu;
-  for (uint32_t i = 0; i < (uint32_t)kMaxResidues; ++i) d.res_numer[i] = i < h.m ? h.res_numer[i] : 0;
+  for (uint32_t i = 0; i < (uint32_t)kMaxResidues; ++i) { d.res_numer[i] = i < h.m ? h.res_numer[i] : 0; d.res_base[i] = i < h.m ? h.res_base[i] : 0; }
   d.local_expand = h.max_expand_depth + 2 <= 32 ? 1u : 0u;
   { // scan strategy (match.cu phase B).  Small buckets: every lane scans whole buckets on its own with 128-bit loads.
     // Once a typical hit bucket spans several 128-byte lines, buckets are streamed through shared memory by bulk copies.

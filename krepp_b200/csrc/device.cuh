@@ -38,6 +38,7 @@ struct DevIndex {
   const uint32_t* cbeg;     // [nsubsets + 1] flattened colours: the leaves colour id se expands to (the walk of
   const uint32_t* cleaf;    //   ref src/query.cpp:369-387 done once at load) are cleaf[cbeg[se] .. cbeg[se+1]), as leaf ranks
   int32_t res_numer[kMaxResidues];
+  uint32_t res_base[kMaxResidues];  // first row of the partial library holding the residue (several partial libraries in one directory)
 };
 
 // Per-slot buffers for one batch.

@@ -273,6 +273,95 @@ uint64_t HostIndex::shard_table_device_bytes(uint32_t n) const
   return worst;
 }
 
+namespace {
+
+// One partial library of the directory: the files of one suffix "-m{m}r{r}-{frac|no_frac}" (ref src/krepp.cpp:72-91).
+struct Partial {
+  std::string sfx;
+  uint32_t k = 0, w = 0, h = 0, m = 0, r = 0, frac = 0, nrows = 0;
+  std::vector<uint8_t> ppos, npos;
+  uint64_t nkmers = 0;
+  std::vector<uint64_t> inc, pse;
+  std::vector<double> rho;
+  uint32_t cr_nnodes = 0, nsubsets = 0;
+  bool wbackbone = true;
+  std::string newick;
+  uint32_t row_base = 0, cshift = 0; // where its rows start in the merged table; what its colour ids above the tree nodes are shifted by
+  uint64_t ent_base = 0;             // where its entries start in the merged table
+};
+
+std::string read_partial(const std::string& dir, Partial& q)
+{
+  std::string buf;
+  const std::string& sfx = q.sfx;
+  if (!slurp(dir + "/metadata" + sfx, buf)) return "Failed to open " + dir + "/metadata" + sfx;
+  if (buf.size() < 16) return "Failed to read the metadata of a partial skecth!";
+  const unsigned char* md = reinterpret_cast<const unsigned char*>(buf.data());
+  q.k = md[0]; q.w = md[1]; q.h = md[2];
+  std::memcpy(&q.m, md + 3, 4); std::memcpy(&q.r, md + 7, 4); q.frac = md[11]; std::memcpy(&q.nrows, md + 12, 4);
+  if (q.k == 0 || q.k > 32 || q.h == 0 || q.h >= q.k || q.k - q.h > 16 || q.m == 0 || buf.size() < 16 + (size_t)q.k) return "Failed to read the metadata of a partial skecth!";
+  q.ppos.assign(md + 16, md + 16 + q.h);
+  q.npos.assign(md + 16 + q.h, md + 16 + q.k);
+  // ---- tree: the backbone tree file, else the balanced tree the reference generates over reflist-* (ref src/index.cpp:3-27,
+  //      Node::generate_tree src/phytree.cpp:217-253), written as Newick so that the same parser numbers it
+  q.wbackbone = slurp(dir + "/tree" + sfx, q.newick);
+  if (!q.wbackbone) {
+    std::string rl;
+    if (!slurp(dir + "/reflist" + sfx, rl)) return "Unable to open reference list file for an index without a tree.";
+    std::vector<std::string> names;
+    for (size_t at = 0; at < rl.size();) { // std::getline: one name per line, a last line without newline counts
+      size_t e = rl.find('\n', at);
+      if (e == std::string::npos) e = rl.size();
+      names.push_back(rl.substr(at, e - at));
+      at = e + 1;
+    }
+    if (names.empty()) return "Unable to open reference list file for an index without a tree.";
+    q.newick.clear();
+    struct Gen {
+      const std::vector<std::string>& nm; std::string& out;
+      void run(size_t lo, size_t hi)
+      { // a range of one name is a leaf; a longer one gets the SECOND half as its first child; every branch length is 1
+        if (hi - lo == 1) { out += '\''; for (char c : nm[lo]) { if (c == '\'') out += '\''; out += c; } out += '\''; }
+        else { const size_t half = lo + (hi - lo) / 2; out += '('; run(half, hi); out += ','; run(lo, half); out += ')'; }
+        out += ":1";
+      }
+    } gen{names, q.newick};
+    gen.run(0, names.size());
+    q.newick += ';';
+  }
+  { // ---- inc, and the size of cmer
+    std::ifstream f(dir + "/inc" + sfx, std::ios::binary);
+    if (!f.is_open()) return "Failed to open " + dir + "/inc" + sfx;
+    uint32_t nr = 0;
+    f.read(reinterpret_cast<char*>(&nr), 4);
+    if (!f.good()) return "Failed to read the offset array of a partial index!";
+    q.nrows = nr;
+    q.inc.resize(q.nrows);
+    f.read(reinterpret_cast<char*>(q.inc.data()), (std::streamsize)((uint64_t)q.nrows * 8));
+    if (!f.good() && q.nrows) return "Failed to read the offset array of a partial index!";
+  }
+  {
+    std::ifstream f(dir + "/cmer" + sfx, std::ios::binary);
+    if (!f.is_open()) return "Failed to open " + dir + "/cmer" + sfx;
+    f.read(reinterpret_cast<char*>(&q.nkmers), 8);
+    if (!f.good()) return "Failed to read the k-mer vector of a partial index!";
+    uint64_t prev = 0;
+    for (uint64_t v : q.inc) { if (v < prev || v > q.nkmers) return "Failed to read the offset array of a partial index!"; prev = v; }
+  }
+  // ---- crecord
+  if (!slurp(dir + "/crecord" + sfx, buf)) return "Failed to open " + dir + "/crecord" + sfx;
+  if (buf.size() < 8) return "Failed to read the color array of a partial index!";
+  std::memcpy(&q.cr_nnodes, buf.data(), 4); std::memcpy(&q.nsubsets, buf.data() + 4, 4);
+  if (buf.size() < 8 + 8ull * q.nsubsets + 8ull * q.cr_nnodes) return "Failed to read the color array of a partial index!";
+  q.pse.resize(q.nsubsets);
+  std::memcpy(q.pse.data(), buf.data() + 8, 8ull * q.nsubsets);
+  q.rho.resize(q.cr_nnodes);
+  std::memcpy(q.rho.data(), buf.data() + 8 + 8ull * q.nsubsets, 8ull * q.cr_nnodes);
+  return "";
+}
+
+} // namespace
+
 std::string HostIndex::load(const std::string& dir, uint32_t shard_id, uint32_t shard_count, bool with_table)
 {
   if (!shard_count || shard_id >= shard_count) return "Bad shard arguments for the index!";
@@ -287,21 +376,31 @@ std::string HostIndex::load(const std::string& dir, uint32_t shard_id, uint32_t 
   }
   closedir(d);
   if (suffixes.empty()) return "There is no partial index in " + dir;
-  if (suffixes.size() > 1)
-    return "directories holding several partial libraries are not supported by the GPU path yet (found " +
-           std::to_string(suffixes.size()) + " suffixes)";
-  const std::string sfx = suffixes[0];
-  std::string buf;
+  std::sort(suffixes.begin(), suffixes.end());
 
-  // ---- metadata
-  if (!slurp(dir + "/metadata" + sfx, buf)) return "Failed to open " + dir + "/metadata" + sfx;
-  if (buf.size() < 16) return "Failed to read the metadata of a partial skecth!";
-  const unsigned char* md = reinterpret_cast<const unsigned char*>(buf.data());
-  k = md[0]; w = md[1]; h = md[2];
-  std::memcpy(&m, md + 3, 4); std::memcpy(&r, md + 7, 4); frac = md[11]; std::memcpy(&nrows, md + 12, 4);
-  if (k == 0 || k > 32 || h == 0 || h >= k || k - h > 16 || m == 0 || buf.size() < 16 + (size_t)k) return "Failed to read the metadata of a partial skecth!";
-  ppos.assign(md + 16, md + 16 + h);
-  npos.assign(md + 16 + h, md + 16 + k);
+  // ---- every partial library of the directory (ref src/krepp.cpp:92-106).  Several of them -- separate `krepp index` runs over
+  //      disjoint hash residues into one directory -- become ONE image: their tables are laid one after the other (a residue's
+  //      rows start at its partial's row base), colour ids above the tree nodes are shifted per partial so that they stay
+  //      distinct, and the colour records are appended in the same order.  What the reference keeps per partial and the image
+  //      cannot: a rho array of its own -- partials built from the same genomes carry the same whole-genome estimates, and a
+  //      directory whose partials disagree is refused rather than approximated.
+  std::vector<Partial> parts(suffixes.size());
+  for (size_t i = 0; i < parts.size(); ++i) {
+    parts[i].sfx = suffixes[i];
+    if (std::string err = read_partial(dir, parts[i]); !err.empty()) return err;
+  }
+  const Partial& p0 = parts[0];
+  k = p0.k; w = p0.w; h = p0.h; m = p0.m; r = p0.r; frac = p0.frac;
+  ppos = p0.ppos; npos = p0.npos;
+  wbackbone = p0.wbackbone;
+  if (std::string err = tree.parse(p0.newick); !err.empty()) return err;
+  for (size_t i = 1; i < parts.size(); ++i) {
+    const Partial& q = parts[i];
+    if (q.k != k || q.h != h || q.m != m || q.ppos != ppos || q.npos != npos) return "Partial indexes are incompatible, not built using the same LSH function!"; // ref src/lshf.cpp:159-180
+    HostTree t2;
+    if (std::string err = t2.parse(q.newick); !err.empty()) return err;
+    if (t2.nnodes != tree.nnodes || t2.name != tree.name || q.wbackbone != wbackbone) return "Partial indexes are incompatible, not built on the same backbone tree!"; // ref src/phytree.cpp:10-36
+  }
   // masks (ref src/lshf.cpp:39-52)
   mask_hash_bp = mask_drop_lr = mask_drop_bp = 0;
   for (uint8_t p : npos) { if (p >= k) return "Failed to read the metadata of a partial skecth!"; mask_drop_lr += 0x0000000100000001ull << p; mask_drop_bp += 3ull << (2 * p); }
@@ -310,85 +409,88 @@ std::string HostIndex::load(const std::string& dir, uint32_t shard_id, uint32_t 
   if ((mask_hash_bp & mask_drop_bp) || __builtin_popcountll(mask_hash_bp | mask_drop_bp) != 2 * (int)k) return "Failed to read the metadata of a partial skecth!";
   hash_runs = runs_of(mask_hash_bp);
   drop_runs = runs_of(mask_drop_bp);
+  // residues -> numerator and row base (ref src/index.cpp:144-157 r_to_flatht / r_to_numerator, :160-168 bucket_indices)
   res_numer.assign(m, 0);
-  if (frac) { for (uint32_t i = 0; i <= r && i < m; ++i) res_numer[i] = (int32_t)(r + 1); }
-  else if (r < m) res_numer[r] = 1;
-
-  // ---- tree: the backbone tree file, else the balanced tree the reference generates over reflist-* (ref src/index.cpp:3-27,
-  //      Node::generate_tree src/phytree.cpp:217-253), written as Newick so that the same parser numbers it
-  wbackbone = slurp(dir + "/tree" + sfx, buf);
-  if (!wbackbone) {
-    std::string rl;
-    if (!slurp(dir + "/reflist" + sfx, rl)) return "Unable to open reference list file for an index without a tree.";
-    std::vector<std::string> names;
-    for (size_t at = 0; at < rl.size();) { // std::getline: one name per line, a last line without newline counts
-      size_t e = rl.find('\n', at);
-      if (e == std::string::npos) e = rl.size();
-      names.push_back(rl.substr(at, e - at));
-      at = e + 1;
-    }
-    if (names.empty()) return "Unable to open reference list file for an index without a tree.";
-    buf.clear();
-    struct Gen {
-      const std::vector<std::string>& nm; std::string& out;
-      void run(size_t lo, size_t hi)
-      { // a range of one name is a leaf; a longer one gets the SECOND half as its first child; every branch length is 1
-        if (hi - lo == 1) { out += '\''; for (char c : nm[lo]) { if (c == '\'') out += '\''; out += c; } out += '\''; }
-        else { const size_t half = lo + (hi - lo) / 2; out += '('; run(half, hi); out += ','; run(lo, half); out += ')'; }
-        out += ":1";
+  res_base.assign(m, 0);
+  {
+    uint64_t rows = 0, ents = 0;
+    uint32_t extra = 0;
+    const uint64_t hash_size = 1ull << (2 * h);
+    for (Partial& q : parts) {
+      if (q.cr_nnodes != tree.nnodes + 1 || q.nsubsets < q.cr_nnodes) return "The colour record does not match the backbone tree of the index!";
+      q.row_base = (uint32_t)rows; q.ent_base = ents; q.cshift = extra;
+      for (uint32_t res = 0; res < m; ++res) {
+        const bool mine = q.frac ? res <= q.r : res == q.r;
+        if (!mine) continue;
+        if (res_numer[res]) return "Partial indexes of " + dir + " overlap: residue " + std::to_string(res) + " is held by two of them";
+        res_numer[res] = q.frac ? (int32_t)(q.r + 1) : 1;
+        res_base[res] = q.row_base;
+        // every rix the hash can produce must address a row of the partial (ref src/krepp.cpp:5-16 set_nrows)
+        if (res < hash_size) {
+          const uint64_t max_rix = (hash_size - 1 - res) / m * m + res;
+          const uint64_t off = res_numer[res] > 1 ? (max_rix / m) * res_numer[res] + res : max_rix / m;
+          if (off + 1 > q.nrows) return "Failed to read the offset array of a partial index!";
+        }
       }
-    } gen{names, buf};
-    gen.run(0, names.size());
-    buf += ';';
-  }
-  if (std::string err = tree.parse(buf); !err.empty()) return err;
-
-  // ---- inc, then the shard's slice of cmer
-  {
-    std::ifstream f(dir + "/inc" + sfx, std::ios::binary);
-    if (!f.is_open()) return "Failed to open " + dir + "/inc" + sfx;
-    uint32_t nr = 0;
-    f.read(reinterpret_cast<char*>(&nr), 4);
-    if (!f.good()) return "Failed to read the offset array of a partial index!";
-    nrows = nr;
-    inc.resize(nrows);
-    f.read(reinterpret_cast<char*>(inc.data()), (std::streamsize)((uint64_t)nrows * 8));
-    if (!f.good() && nrows) return "Failed to read the offset array of a partial index!";
-  }
-  {
-    std::ifstream f(dir + "/cmer" + sfx, std::ios::binary);
-    if (!f.is_open()) return "Failed to open " + dir + "/cmer" + sfx;
-    f.read(reinterpret_cast<char*>(&nkmers), 8);
-    if (!f.good()) return "Failed to read the k-mer vector of a partial index!";
-    uint64_t prev = 0;
-    double s1 = 0, s2 = 0;
-    for (uint64_t v : inc) {
-      if (v < prev || v > nkmers) return "Failed to read the offset array of a partial index!";
-      const double len = (double)(v - prev);
-      s1 += len; s2 += len * len; prev = v;
+      rows += q.nrows; ents += q.nkmers; extra += q.nsubsets - q.cr_nnodes;
+      if (rows > 0xFFFFFFFFull) return "The partial indexes of " + dir + " have more than 2^32 rows together";
     }
+    nrows = (uint32_t)rows; nkmers = ents;
+    cr_nnodes = tree.nnodes + 1;
+    if ((uint64_t)cr_nnodes + extra > 0xFFFFFFFFull) return "The colour records of " + dir + " do not fit 32-bit ids";
+    nsubsets = cr_nnodes + extra;
+  }
+  // merged offsets, colour records and rho
+  inc.clear(); inc.reserve(nrows);
+  for (const Partial& q : parts) for (uint64_t v : q.inc) inc.push_back(v + q.ent_base);
+  pse.assign(nsubsets, 0);
+  rho = p0.rho;
+  for (const Partial& q : parts) {
+    auto remap = [&](uint32_t c) { return c >= cr_nnodes ? c + q.cshift : c; };
+    for (uint32_t se = 0; se < q.nsubsets; ++se) {
+      const uint64_t v = (uint64_t)remap((uint32_t)q.pse[se]) | (uint64_t)remap((uint32_t)(q.pse[se] >> 32)) << 32;
+      if (se < cr_nnodes) { if (&q != &p0 && v != pse[se]) return "Partial indexes are incompatible, their colour records disagree on the backbone tree!"; pse[se] = v; }
+      else pse[se + q.cshift] = v;
+    }
+    if (q.rho != rho)
+      return "The partial libraries of " + dir + " carry different rho estimates; the GPU path keeps one rho per reference and does not load such a directory";
+  }
+  {
+    double s1 = 0, s2 = 0;
+    uint64_t prev = 0;
+    for (uint64_t v : inc) { const double len = (double)(v - prev); s1 += len; s2 += len * len; prev = v; }
     mean_bucket = nrows ? s1 / nrows : 0;
     size_biased_bucket = s1 > 0 ? s2 / s1 : 0;
+  }
+  // ---- the shard's slice of the (merged) table
+  {
     row_splits = split_rows(inc, nkmers, nrows, nshards);
     row0 = row_splits[shard]; row1 = row_splits[shard + 1];
     ent0 = row0 ? inc[row0 - 1] : 0;
     const uint64_t ent1 = row1 ? inc[row1 - 1] : 0;
     cmer.resize(with_table ? ent1 - ent0 : 0);
-    if (with_table) { // the table is most of the index (1.6 GB for 1,000 genomes): read it with several threads, each pread()ing its own range
-      const int fd = open((dir + "/cmer" + sfx).c_str(), O_RDONLY);
-      if (fd < 0) return "Failed to open " + dir + "/cmer" + sfx;
-      const size_t bytes = cmer.size() * 8, nth = std::max<size_t>(1, std::min<size_t>(8, bytes >> 24));
+    for (const Partial& q : parts) { // every partial's entries that fall into [ent0, ent1), read by several threads, each pread()ing its own range
+      if (!with_table) break;
+      const uint64_t lo_e = std::max<uint64_t>(ent0, q.ent_base), hi_e = std::min<uint64_t>(ent1, q.ent_base + q.nkmers);
+      if (lo_e >= hi_e) continue;
+      const int fd = open((dir + "/cmer" + q.sfx).c_str(), O_RDONLY);
+      if (fd < 0) return "Failed to open " + dir + "/cmer" + q.sfx;
+      const size_t bytes = (size_t)(hi_e - lo_e) * 8, nth = std::max<size_t>(1, std::min<size_t>(8, bytes >> 24));
       std::vector<char> ok(nth, 1);
       std::vector<std::thread> th;
       auto work = [&](size_t t) {
         size_t lo = bytes * t / nth / 8 * 8, hi = bytes * (t + 1) / nth / 8 * 8;
         if (t + 1 == nth) hi = bytes;
-        char* dst = reinterpret_cast<char*>(cmer.data());
+        char* dst = reinterpret_cast<char*>(cmer.data() + (lo_e - ent0));
+        const size_t first = lo;
         while (lo < hi) {
-          const ssize_t got = pread(fd, dst + lo, hi - lo, (off_t)(8 + 8 * ent0 + lo));
+          const ssize_t got = pread(fd, dst + lo, hi - lo, (off_t)(8 + 8 * (lo_e - q.ent_base) + lo));
           if (got <= 0) { ok[t] = 0; return; }
           lo += (size_t)got;
         }
+        if (q.cshift) // this partial's colour ids above the tree nodes move up
+          for (uint64_t* e = reinterpret_cast<uint64_t*>(dst + first), *end = reinterpret_cast<uint64_t*>(dst + hi); e < end; ++e)
+            if ((uint32_t)(*e >> 32) >= cr_nnodes) *e += (uint64_t)q.cshift << 32;
       };
       for (size_t t = 1; t < nth; ++t) th.emplace_back(work, t);
       work(0);
@@ -398,29 +500,6 @@ std::string HostIndex::load(const std::string& dir, uint32_t shard_id, uint32_t 
     }
     if (ent1 - ent0 < (1ull << 32)) { inc32.resize(row1 - row0); for (uint32_t i = row0; i < row1; ++i) inc32[i - row0] = (uint32_t)(inc[i] - ent0); }
   }
-  // every rix the hash can produce must address a row below nrows (ref src/krepp.cpp:5-16 set_nrows)
-  {
-    const uint64_t hash_size = 1ull << (2 * h);
-    uint64_t need = 0;
-    for (uint32_t res = 0; res < m; ++res) {
-      if (!res_numer[res] || res >= hash_size) continue;
-      const uint64_t max_rix = (hash_size - 1 - res) / m * m + res;
-      const uint64_t off = res_numer[res] > 1 ? (max_rix / m) * res_numer[res] + res : max_rix / m;
-      need = std::max(need, off + 1);
-    }
-    if (need > nrows) return "Failed to read the offset array of a partial index!";
-  }
-
-  // ---- crecord
-  if (!slurp(dir + "/crecord" + sfx, buf)) return "Failed to open " + dir + "/crecord" + sfx;
-  if (buf.size() < 8) return "Failed to read the color array of a partial index!";
-  std::memcpy(&cr_nnodes, buf.data(), 4); std::memcpy(&nsubsets, buf.data() + 4, 4);
-  if (buf.size() < 8 + 8ull * nsubsets + 8ull * cr_nnodes) return "Failed to read the color array of a partial index!";
-  pse.resize(nsubsets);
-  std::memcpy(pse.data(), buf.data() + 8, 8ull * nsubsets);
-  rho.resize(cr_nnodes);
-  std::memcpy(rho.data(), buf.data() + 8 + 8ull * nsubsets, 8ull * cr_nnodes);
-  if (cr_nnodes != tree.nnodes + 1 || nsubsets < cr_nnodes) return "The colour record does not match the backbone tree of the index!";
   // make_rho_partial: rho *= (#residues present)/m (ref src/index.cpp:188-201, src/record.cpp:304-309)
   {
     uint32_t present = 0;

@@ -62,6 +62,7 @@ struct HostIndex {
   uint64_t mask_hash_bp = 0, mask_drop_lr = 0, mask_drop_bp = 0;
   std::vector<BitRun> hash_runs, drop_runs;   // pext plans over the 2-bit (bp) k-mer word
   std::vector<int32_t> res_numer;             // [m]: 0 = residue absent, else numerator (ref src/index.cpp:144-157)
+  std::vector<uint32_t> res_base;             // [m]: first row of the partial library that holds the residue (0 with one partial)
   std::vector<uint64_t, NoInitAlloc<uint64_t>> cmer; // nkmers x (enc | se<<32)
   std::vector<uint64_t> inc;                  // nrows
   std::vector<uint32_t> inc32;                // nrows, present when nkmers < 2^32 (what the device scans with)

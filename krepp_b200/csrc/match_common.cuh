@@ -142,7 +142,7 @@ __device__ __forceinline__ uint32_t tile_lookups(const DevIndex& ix, const Match
       else { quo = rix / ix.m; res = rix - quo * ix.m; }
       const int32_t numer = ix.res_numer[res];
       const bool elig = valid && numer != 0;
-      const uint32_t offset = numer > 1 ? quo * (uint32_t)numer + res : quo;
+      const uint32_t offset = (numer > 1 ? quo * (uint32_t)numer + res : quo) + ix.res_base[res];
       const uint32_t em = __ballot_sync(0xFFFFFFFFu, elig);
       if (elig) {
         const uint32_t idx = nl + __popc(em & lt_mask);

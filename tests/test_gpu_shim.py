@@ -66,3 +66,45 @@ def test_shim_summarize_tables_agree():
     b = run(EXE, "dist", "-i", idx, "-q", q, "--summarize").splitlines()[2:]
     key = lambda l: l.split("\t")[0]
     assert sorted(a, key=key) == sorted(b, key=key) and len(a) > 3
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/krepp not built")
+def test_cli_modes_equal_the_reference_cli_on_untied_reads(tmp_path):
+    """--no-multi, --filter, --dist-max, --summarize (dist) and --no-multi / --tabular (place) against the stock reference binary.
+    These modes consult the closest reference, which the reference picks in hash-map order when several leaves tie (SURVEY.md
+    section 0 fact 6), so the comparison runs on the reads whose closest reference is unique -- there every line must agree."""
+    import oracle_lib as O
+    idx, q = os.path.join(SMALL, "index"), os.path.join(SMALL, "reads.fq")
+    o = O.OracleIndex(idx)
+    sub = tmp_path / "untied.fq"
+    kept = 0
+    with open(q) as f, open(sub, "w") as g:
+        while True:
+            rec = [f.readline() for _ in range(4)]
+            if not rec[0]:
+                break
+            sel = o.query(rec[1].strip().encode(), O.default_params(no_filter=0))["sel"]
+            if sel:
+                dmin = min(x["d"] for x in sel)
+                if sum(1 for x in sel if x["d"] == dmin) != 1:
+                    continue
+            g.writelines(rec)
+            kept += 1
+    assert kept > 100
+    for args in (["dist", "--no-multi"], ["dist", "--filter"], ["dist", "--dist-max", "0.05"], ["dist", "--filter", "--dist-max", "0.08", "--no-multi"],
+                 ["dist", "--hdist-th", "2"], ["place", "--tabular"], ["place", "--tabular", "--no-multi"], ["place", "--tabular", "--no-filter"]):
+        a = sorted(run(EXE, *args, "-i", idx, "-q", str(sub)).splitlines()[2:])
+        b = sorted(run(REF, *args, "-i", idx, "-q", str(sub)).splitlines()[2:])
+        assert a == b and len(a) >= 50, (args, len(a), len(b), [x for x in a if x not in set(b)][:3], [x for x in b if x not in set(a)][:3])
+    for args in (["dist", "--summarize"], ["dist", "--summarize", "--dist-max", "0.1"], ["place", "--summarize"]):
+        def table(exe):
+            out = {}
+            for l in run(exe, *args, "-i", idx, "-q", str(sub)).splitlines():
+                t = l.split("\t")
+                if l and not l.startswith("#") and len(t) >= 3 and t[-1][:1].isdigit():
+                    out[tuple(t[:-2])] = [float(x) for x in t[-2:]]
+            return out
+        a, b = table(EXE), table(REF)
+        assert a.keys() == b.keys() and len(a) > 3, (args, sorted(set(a) ^ set(b))[:5])
+        for k in a:
+            assert all(abs(x - y) <= 2e-5 for x, y in zip(a[k], b[k])), (args, k, a[k], b[k])

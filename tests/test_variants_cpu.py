@@ -61,27 +61,38 @@ def test_treeless_index_dist_equals_reference(tmp_path_factory):
     assert place.returncode != 0 and "lacks a tree" in place.stderr   # what krepp_batch_create answers for place on this handle
 
 
-def test_partial_library_directory_oracle_pinned_loader_refuses(tmp_path_factory):
+def test_partial_library_directory_oracle_pinned_loader_merges(tmp_path_factory):
     """A directory holding several partial libraries (three `krepp index --no-frac` runs with r = 0, 2, 3 of m = 4 into one
     -o directory; every partial has its own table, colour record and rho).  The oracle restates the per-residue dispatch
-    (ref src/index.cpp:144-168) and is pinned here against the reference's `dist`; the GPU path does not model this form yet
-     and must say so instead of loading one of the partials."""
-    import shutil
+    (ref src/index.cpp:144-168) and is pinned here against the reference's `dist`; the C++ loader merges the partials into one
+    image (tables one after the other, colour ids shifted per partial), checked here for its sizes and on the GPU against the
+    oracle (tests/test_gpu_variants.py)."""
+    import numpy as np
     import krepp_b200
-    from krepp_b200.capi import KreppError
-    work = os.path.join(str(tmp_path_factory.getbasetemp()), "partials")
-    os.makedirs(work, exist_ok=True)
-    for item in ("genomes", "input_map.tsv", "tree.nwk"):
-        src, dst = os.path.join(SMALL, item), os.path.join(work, item)
-        if not os.path.exists(dst):
-            (shutil.copytree if os.path.isdir(src) else shutil.copy)(src, dst)
-    for r in ("0", "2", "3"):
-        subprocess.run([os.path.join(REF_DIR, "krepp"), "index", "-k", "21", "-w", "25", "-h", "7", "-m", "4", "-r", r, "--no-frac", "-o", "index",
-                        "-i", "input_map.tsv", "-t", "tree.nwk"], cwd=work, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-    idx, fq = os.path.join(work, "index"), os.path.join(SMALL, "reads.fq")
+    from variants import build_partials
+    idx, fq = build_partials(tmp_path_factory.getbasetemp()), os.path.join(SMALL, "reads.fq")
     ref = subprocess.run([os.path.join(REF_DIR, "krepp"), "dist", "-i", idx, "-q", fq], capture_output=True, text=True, check=True).stdout.splitlines()[2:]
     ora = subprocess.run([os.path.join(os.path.dirname(REF_DIR), "_build", "krepp_oracle"), "dist", idx, fq], capture_output=True, text=True,
                          check=True).stdout.splitlines()[1:]
     assert len(ref) > 1000 and sorted(ref) == sorted(ora)
-    with pytest.raises(KreppError, match="several partial libraries"):
-        krepp_b200.Index(idx, device=-1)
+    ix = krepp_b200.Index(idx, device=-1)
+    sizes = {}
+    for sfx in ("-m4r0-no_frac", "-m4r2-no_frac", "-m4r3-no_frac"):
+        nk = int(np.fromfile(os.path.join(idx, "cmer" + sfx), dtype="<u8", count=1)[0])
+        nr = int(np.fromfile(os.path.join(idx, "inc" + sfx), dtype="<u4", count=1)[0])
+        ns = int(np.fromfile(os.path.join(idx, "crecord" + sfx), dtype="<u4", count=2)[1])
+        sizes[sfx] = (nk, nr, ns)
+    assert ix.info.nkmers == sum(v[0] for v in sizes.values()) and ix.info.nrows == sum(v[1] for v in sizes.values())
+    assert ix.info.nsubsets == (ix.info.nnodes + 1) + sum(v[2] - (ix.info.nnodes + 1) for v in sizes.values())
+    cs = ix.host_checksums()   # sum of the bucket ends: every partial's ends, moved up by the entries of the partials before it
+    want, base = 0, 0
+    for sfx in sorted(sizes):
+        inc = np.fromfile(os.path.join(idx, "inc" + sfx), dtype="<u8", offset=4)
+        want += int(inc.sum()) + base * len(inc)
+        base += sizes[sfx][0]
+    assert cs[1] == want % (1 << 64)
+    # overlapping partials (two runs that both hold residue 0) are refused
+    from krepp_b200.capi import KreppError
+    both = build_partials(tmp_path_factory.getbasetemp(), rs=("0", "1"), frac=True)
+    with pytest.raises(KreppError, match="overlap"):
+        krepp_b200.Index(both, device=-1)

@@ -38,3 +38,19 @@ def build(label, args, tmp_root, with_tree=True):
         subprocess.run([os.path.join(REF_DIR, "krepp"), "index", *args, "-o", "index", "-i", "input_map.tsv", *(["-t", "tree.nwk"] if with_tree else [])],
                        cwd=work, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     return os.path.join(work, "index")
+
+
+def build_partials(tmp_root, rs=("0", "2", "3"), frac=False):
+    """A directory holding several partial libraries: separate `krepp index` runs (m = 4, one residue each, or with --frac the
+    residues 0..r) into ONE -o directory; every partial has its own table, colour record and rho (ref src/krepp.cpp:66-108)."""
+    work = os.path.join(str(tmp_root), "partials_" + "_".join(rs) + ("_frac" if frac else ""))
+    if not os.path.isdir(os.path.join(work, "index")):
+        os.makedirs(work, exist_ok=True)
+        for item in ("genomes", "input_map.tsv", "tree.nwk"):
+            src, dst = os.path.join(SMALL, item), os.path.join(work, item)
+            if not os.path.exists(dst):
+                (shutil.copytree if os.path.isdir(src) else shutil.copy)(src, dst)
+        for r in rs:
+            subprocess.run([os.path.join(REF_DIR, "krepp"), "index", "-k", "21", "-w", "25", "-h", "7", "-m", "4", "-r", r, *([] if frac else ["--no-frac"]), "-o", "index",
+                            "-i", "input_map.tsv", "-t", "tree.nwk"], cwd=work, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return os.path.join(work, "index")
