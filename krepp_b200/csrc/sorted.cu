@@ -630,7 +630,7 @@ __device__ __forceinline__ void bitonic_merge_regs(K* keys)
 // steps run in shared memory while the partners are a block or more apart and in registers (bitonic_merge_regs) below that -- so of
 // the 45 steps a 512-key network has, one touches shared memory.
 template <typename K>
-__device__ __noinline__ void bitonic_sort_blocks(K* keys, uint32_t n)
+__device__ __forceinline__ void bitonic_sort_blocks(K* keys, uint32_t n)
 {
   const uint32_t lane = threadIdx.x & 31;
   constexpr int E = sizeof(K) == 4 ? 8 : 4;   // keys per lane held in registers: 32-bit keys in blocks of 256, 64-bit keys of 128
@@ -656,6 +656,19 @@ __device__ __noinline__ void bitonic_sort_blocks(K* keys, uint32_t n)
     for (uint32_t b = 0; b < n; b += B) bitonic_merge_regs<K, E>(keys + b);
     __syncwarp();
   }
+}
+
+// One copy of every network per key width: the unrolled networks are thousands of instructions, and the resolve kernel, which
+// expands a read in three places (32-bit keys in shared memory, 64-bit keys in shared memory, 64-bit keys in HBM scratch), ran
+// out of instruction cache when each place carried its own (r07l: a fifth of the issue slots lost to instruction fetch).
+template <typename K>
+__device__ __noinline__ void sort_keys(K* keys, uint32_t n) // n: a power of two >= 32; ascending
+{
+  if (n == 32) bitonic_sort_regs<K, 1>(keys);
+  else if (n == 64) bitonic_sort_regs<K, 2>(keys);
+  else if (n == 128) bitonic_sort_regs<K, 4>(keys);
+  else if (n == 256 && sizeof(K) == 4) bitonic_sort_regs<K, (sizeof(K) == 4 ? 8 : 4)>(keys);
+  else bitonic_sort_blocks<K>(keys, n);
 }
 
 struct ResolveOut { uint32_t total, rbegin; bool fits; };
@@ -790,11 +803,7 @@ __device__ __forceinline__ ResolveOut resolve_read(const DevIndex& ix, const Mat
   while (n < T) n <<= 1;
   for (uint32_t i = T + lane; i < n; i += 32) keys[i] = ~(K)0; // never a real key: hd <= 16 < 31
   __syncwarp();
-  if (n == 32) bitonic_sort_regs<K, 1>(keys);
-  else if (n == 64) bitonic_sort_regs<K, 2>(keys);
-  else if (n == 128) bitonic_sort_regs<K, 4>(keys);
-  else if (n == 256 && sizeof(K) == 4) bitonic_sort_regs<K, (sizeof(K) == 4 ? 8 : 4)>(keys);
-  else bitonic_sort_blocks<K>(keys, n);
+  sort_keys<K>(keys, n);
   __syncwarp();
   return emit_sorted<K>(ix, a, keys, T, seg_shift, rank_bits, read, g0, g1, small_counts);
 }
