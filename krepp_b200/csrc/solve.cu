@@ -328,10 +328,10 @@ __global__ void __launch_bounds__(128) place_collect_kernel(const PlaceArgs a)
           //      the additions cannot matter and a node's histogram is a difference of prefix sums over the leaves below it --
           //      O(1) per node instead of one step per leaf below -- with the same bits as the reference's ordered sum.
           bool exact = nsel <= kPfxCap && enmers < 65536u && a.logw != nullptr;
-          {
+          if (exact) {
             bool bad = false;
             for (uint32_t i = lane; i < nsel; i += 32) bad = bad || a.logw[sel_se[i]] > 30u;
-            exact = exact && !__any_sync(0xFFFFFFFFu, bad);
+            exact = !__any_sync(0xFFFFFFFFu, bad);
           }
           if (exact) {
             if (lane <= stride && lane <= (uint32_t)N) { // lane x: component x of the histogram, lane `stride`: the match count
