@@ -598,79 +598,6 @@ __device__ __forceinline__ void bitonic_sort_regs(K* keys)
   for (int e = 0; e < E; ++e) keys[lane * E + e] = v[e];
 }
 
-// The last stage of that network alone: a block of 32 * E keys that is a bitonic sequence becomes ascending.
-template <typename K, int E>
-__device__ __forceinline__ void bitonic_merge_regs(K* keys)
-{
-  const uint32_t lane = threadIdx.x & 31;
-  K v[E];
-#pragma unroll
-  for (int e = 0; e < E; ++e) v[e] = keys[lane * E + e];
-#pragma unroll
-  for (int j = 16 * E; j > 0; j >>= 1) {
-    if (j >= E) {
-      const bool lower = (lane & (uint32_t)(j / E)) == 0;
-#pragma unroll
-      for (int e = 0; e < E; ++e) {
-        const K o = __shfl_xor_sync(0xFFFFFFFFu, v[e], j / E);
-        v[e] = lower ? (v[e] < o ? v[e] : o) : (v[e] < o ? o : v[e]);
-      }
-    } else {
-#pragma unroll
-      for (int e = 0; e < E; ++e)
-        if ((e & j) == 0) { const K x = v[e], y = v[e | j]; if (x > y) { v[e] = y; v[e | j] = x; } }
-    }
-  }
-#pragma unroll
-  for (int e = 0; e < E; ++e) keys[lane * E + e] = v[e];
-}
-
-// Larger n: blocks of 256 keys (128 when they are 64-bit) are sorted in registers, then merged pairwise.  Merging two ascending runs starts with
-// the mirrored compare-exchange (key t against key size-1-t of the pair), which leaves two bitonic halves; their half-cleaner
-// steps run in shared memory while the partners are a block or more apart and in registers (bitonic_merge_regs) below that -- so of
-// the 45 steps a 512-key network has, one touches shared memory.
-template <typename K>
-__device__ __forceinline__ void bitonic_sort_blocks(K* keys, uint32_t n)
-{
-  const uint32_t lane = threadIdx.x & 31;
-  constexpr int E = sizeof(K) == 4 ? 8 : 4;   // keys per lane held in registers: 32-bit keys in blocks of 256, 64-bit keys of 128
-  constexpr uint32_t B = 32 * E;
-  for (uint32_t b = 0; b < n; b += B) bitonic_sort_regs<K, E>(keys + b);
-  __syncwarp();
-  for (uint32_t size = 2 * B; size <= n; size <<= 1) {
-    const uint32_t half = size >> 1;
-    for (uint32_t t = lane; t < (n >> 1); t += 32) {
-      const uint32_t blk = t / half, o = t - blk * half, i = blk * size + o, l = blk * size + size - 1u - o;
-      const K x = keys[i], y = keys[l];
-      if (x > y) { keys[i] = y; keys[l] = x; }
-    }
-    __syncwarp();
-    for (uint32_t j = size >> 2; j >= B; j >>= 1) {
-      for (uint32_t t = lane; t < (n >> 1); t += 32) {
-        const uint32_t i = ((t & ~(j - 1u)) << 1) | (t & (j - 1u)), l = i | j;
-        const K x = keys[i], y = keys[l];
-        if (x > y) { keys[i] = y; keys[l] = x; }
-      }
-      __syncwarp();
-    }
-    for (uint32_t b = 0; b < n; b += B) bitonic_merge_regs<K, E>(keys + b);
-    __syncwarp();
-  }
-}
-
-// One copy of every network per key width: the unrolled networks are thousands of instructions, and the resolve kernel, which
-// expands a read in three places (32-bit keys in shared memory, 64-bit keys in shared memory, 64-bit keys in HBM scratch), ran
-// out of instruction cache when each place carried its own (r07l: a fifth of the issue slots lost to instruction fetch).
-template <typename K>
-__device__ __noinline__ void sort_keys(K* keys, uint32_t n) // n: a power of two >= 32; ascending
-{
-  if (n == 32) bitonic_sort_regs<K, 1>(keys);
-  else if (n == 64) bitonic_sort_regs<K, 2>(keys);
-  else if (n == 128) bitonic_sort_regs<K, 4>(keys);
-  else if (n == 256 && sizeof(K) == 4) bitonic_sort_regs<K, (sizeof(K) == 4 ? 8 : 4)>(keys);
-  else bitonic_sort_blocks<K>(keys, n);
-}
-
 struct ResolveOut { uint32_t total, rbegin; bool fits; };
 
 // One read's leaf hits, as sorted keys strand | leaf rank | lookup | hd, to its records (see the header).  seg_shift =
@@ -803,12 +730,16 @@ __device__ __forceinline__ ResolveOut resolve_read(const DevIndex& ix, const Mat
   while (n < T) n <<= 1;
   for (uint32_t i = T + lane; i < n; i += 32) keys[i] = ~(K)0; // never a real key: hd <= 16 < 31
   __syncwarp();
-  sort_keys<K>(keys, n);
+  if (n == 32) bitonic_sort_regs<K, 1>(keys);
+  else if (n == 64) bitonic_sort_regs<K, 2>(keys);
+  else if (n == 128) bitonic_sort_regs<K, 4>(keys);
+  else if (n == 256 && sizeof(K) == 4) bitonic_sort_regs<K, (sizeof(K) == 4 ? 8 : 4)>(keys);
+  else bitonic_sort(keys, n);
   __syncwarp();
   return emit_sorted<K>(ix, a, keys, T, seg_shift, rank_bits, read, g0, g1, small_counts);
 }
 
-__global__ void __launch_bounds__(kResWarps * 32, 4) resolve_kernel(const DevIndex ix, const MatchArgs a, const SortArgs s, uint32_t rank_bits)
+__global__ void __launch_bounds__(kResWarps * 32) resolve_kernel(const DevIndex ix, const MatchArgs a, const SortArgs s, uint32_t rank_bits)
 {
   __shared__ __align__(16) uint32_t skeys[kResWarps][kResKeys];
   if (a.counters[2] & kErrRedo) return;
