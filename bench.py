@@ -280,7 +280,7 @@ def hot_arm(env: Env, index, wl: Workload, mode: str, n: int, batch: int, steps:
         if mode == "dist":
             s.set_output(records=False, hist=False, placements=False, summaries=False, dist=True)
         else:
-            s.set_output(hist=False)
+            s.set_output(records=False, hist=False)  # placement rows + 44-byte read summaries
 
     # ---- device-resident arm (value): one slot, all reads of the step already in HBM, processed in batches
     slot = krepp_b200.IBatch(index, reads[:batch], **mode_kw)
@@ -376,7 +376,7 @@ def hot_arm(env: Env, index, wl: Workload, mode: str, n: int, batch: int, steps:
         e2e = world * n * steps / t_e2e
         rows_how = ("4 bytes per read (row offsets + the NA flag) and 4 bytes per printed TSV row (reference << 16 | distance as the integer its five printed decimals show): "
                     "the rows `krepp dist` prints are selected, ordered and rounded by a kernel (KREPP_OUT_DIST), nothing else leaves the device"
-                    if mode == "dist" else "the 40-byte read summaries, the full record rows and the placement rows (what the jplace writer reads); the Hamming histograms stay in HBM")
+                    if mode == "dist" else "the 44-byte read summaries and the 56-byte placement rows (all the jplace writer reads); records and Hamming histograms stay in HBM")
         e2e_out = {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "records_per_step": nrec_e2e, "output_rows_per_step": nrow_e2e,
                    "d2h_bytes_per_read": d2h / n, "h2d_bytes_per_read": h2d / n,
                    "how": f"krepp_batch_submit from page-locked host memory + krepp_batch_wait with the output the command line asks for (krepp_batch_set_output): {rows_how}; "

@@ -119,6 +119,8 @@ typedef struct {
   uint32_t rec_begin, rec_count;     /* this read's records[]: forward leaves by ascending se, then reverse */
   uint32_t place_begin, place_count; /* this read's placements[] by ascending se */
   int32_t closest;                   /* index into records[] of mi_closest, -1 when node_to_minfo is empty */
+  uint32_t n_selected;               /* entries of IBatch::node_to_minfo: references that keep a record after summarize_matches
+                                        (src/query.cpp:114,127-137); report_placement's single-reference shortcut tests it (:231) */
 } krepp_read_summary_t;
 
 /* The 16-byte form of a record, for front ends that only print distances (`krepp dist`): what report_distances
@@ -207,14 +209,14 @@ int krepp_batch_wait(krepp_batch_t* b, krepp_results_t* out);
                               krepp_format_dist reads them when `records` is NULL. */
 #define KREPP_OUT_DIST 16u /* the printed rows of `krepp dist` (see krepp_results_t): 4 bytes per read + 4 or 8 per printed row.
                               Not part of KREPP_OUT_ALL; krepp_format_dist prefers them when present. */
-#define KREPP_OUT_SUMMARIES 32u /* the 40-byte krepp_read_summary_t rows; a front end that asks for KREPP_OUT_DIST alone does without */
+#define KREPP_OUT_SUMMARIES 32u /* the 44-byte krepp_read_summary_t rows; a front end that asks for KREPP_OUT_DIST alone does without */
 #define KREPP_OUT_ALL 39u
 /* Must be called while no batch is pending on the slot (before krepp_batch_submit, or after the krepp_batch_wait that follows
  * it): the kernels that assemble the rows run as part of the submit.  KREPP_ERR_ARG otherwise. */
 int krepp_batch_set_output(krepp_batch_t* b, uint32_t rows);
 
 /* The same wait (including the grow-and-rerun of a batch whose result buffers were too small) without copying the record,
- * histogram and placement rows to the host: `reads` (40 bytes per read) and the counts are valid, the three row pointers
+ * histogram and placement rows to the host: `reads` (44 bytes per read) and the counts are valid, the three row pointers
  * are NULL and the rows stay in HBM.  For callers that only need the per-read summaries, and for timing the kernels
  * without the PCIe transfer of the rows.  (The summaries are copied here even if KREPP_OUT_SUMMARIES was not asked for.) */
 int krepp_batch_wait_device(krepp_batch_t* b, krepp_results_t* out);

@@ -66,7 +66,7 @@ class Results(C.Structure):
 RECORD_DTYPE = np.dtype([("read", "<u4"), ("leaf_se", "<u4"), ("strand", "<u4"), ("match_count", "<u4"), ("hdist_min", "<u4"),
                          ("flags", "<u4"), ("rho", "<f8"), ("d_llh", "<f8"), ("v_llh", "<f8"), ("chisq", "<f8")])
 READ_DTYPE = np.dtype([("onmers", "<u4"), ("wn", "<u4", (2,)), ("hdist_filt", "<u4", (2,)), ("rec_begin", "<u4"),
-                       ("rec_count", "<u4"), ("place_begin", "<u4"), ("place_count", "<u4"), ("closest", "<i4")])
+                       ("rec_count", "<u4"), ("place_begin", "<u4"), ("place_count", "<u4"), ("closest", "<i4"), ("n_selected", "<u4")])
 PLACEMENT_DTYPE = np.dtype([("read", "<u4"), ("se", "<u4"), ("pendant", "<f8"), ("distal", "<f8"), ("loglik", "<f8"),
                             ("lwr", "<f8"), ("d_llh", "<f8"), ("chisq", "<f8")])
 BRIEF_DTYPE = np.dtype([("read", "<u4"), ("ref", "<u4"), ("d_llh", "<f8")])  # krepp_brief_t

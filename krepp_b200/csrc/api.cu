@@ -122,6 +122,7 @@ __global__ void __launch_bounds__(128) finalize_kernel(const SolveArgs a, krepp_
     s.rec_begin = a.rec_begin[i]; s.rec_count = a.rec_count[i];
     s.place_begin = place_begin ? place_begin[i] : 0; s.place_count = place_count ? place_count[i] : 0;
     s.closest = a.closest[i];
+    s.n_selected = a.nsel ? a.nsel[i] : 0u;
     out_read[i] = s;
   }
 }
@@ -235,7 +236,7 @@ struct krepp_batch {
   char* d_bases = nullptr; uint64_t* d_offsets = nullptr;
   // device state
   uint32_t *d_onmers = nullptr, *d_wn = nullptr, *d_hdfilt = nullptr, *d_rec_begin = nullptr, *d_rec_count = nullptr;
-  int32_t* d_closest = nullptr;
+  int32_t* d_closest = nullptr; uint32_t* d_nsel = nullptr;
   uint32_t *d_rec_read = nullptr, *d_rec_slot = nullptr, *d_rec_hist = nullptr, *d_rec_flags = nullptr, *d_rec_match = nullptr, *d_rec_hdmin = nullptr, *d_rec_work = nullptr;
   double *d_rec_d = nullptr, *d_rec_v = nullptr, *d_rec_chisq = nullptr;
   uint32_t* d_rec_alias = nullptr; unsigned long long* d_memo_key = nullptr; uint32_t* d_memo_owner = nullptr; uint32_t memo_mask = 0, memo_bits = 0;
@@ -638,7 +639,7 @@ int krepp_batch_create(krepp_index_t* ix, const krepp_params_t* p, uint32_t max_
   CU(cudaMallocHost(&b->h_bases, max_bases + 64)); CU(cudaMallocHost(&b->h_offsets, 8ull * (max_reads + 1)));
   CU(cudaMalloc(&b->d_bases, max_bases + 64)); CU(cudaMalloc(&b->d_offsets, 8ull * (max_reads + 1)));
   CU(cudaMalloc(&b->d_onmers, 4ull * max_reads)); CU(cudaMalloc(&b->d_wn, 8ull * max_reads)); CU(cudaMalloc(&b->d_hdfilt, 8ull * max_reads));
-  CU(cudaMalloc(&b->d_rec_begin, 4ull * max_reads)); CU(cudaMalloc(&b->d_rec_count, 4ull * max_reads)); CU(cudaMalloc(&b->d_closest, 4ull * max_reads));
+  CU(cudaMalloc(&b->d_rec_begin, 4ull * max_reads)); CU(cudaMalloc(&b->d_rec_count, 4ull * max_reads)); CU(cudaMalloc(&b->d_closest, 4ull * max_reads)); CU(cudaMalloc(&b->d_nsel, 4ull * max_reads));
   CU(cudaMalloc(&b->d_counters, 32)); CU(cudaMalloc(&b->d_stats, 64)); // stats: [0..3] live, [4..7] snapshot taken before a mode B finish
   CU(cudaMallocHost(&b->h_counters, 32)); CU(cudaMallocHost(&b->h_stats, 32));
   CU(cudaMalloc(&b->d_out_read, sizeof(krepp_read_summary_t) * (size_t)max_reads));
@@ -695,7 +696,7 @@ void krepp_batch_destroy(krepp_batch_t* b)
   for (void* p : {(void*)b->d_dist_cnt, (void*)b->d_dist_begin, (void*)b->d_dist_out_begin, (void*)b->d_dist_partials}) if (p) cudaFree(p);
   if (b->h_dist_begin) cudaFreeHost(b->h_dist_begin);
   for (void* p : {(void*)b->d_bases, (void*)b->d_offsets, (void*)b->d_onmers, (void*)b->d_wn, (void*)b->d_hdfilt, (void*)b->d_rec_begin,
-                  (void*)b->d_rec_count, (void*)b->d_closest, (void*)b->d_memo_key, (void*)b->d_memo_owner, (void*)b->d_counters, (void*)b->d_stats, (void*)b->d_acc, (void*)b->d_bitmap,
+                  (void*)b->d_rec_count, (void*)b->d_closest, (void*)b->d_nsel, (void*)b->d_memo_key, (void*)b->d_memo_owner, (void*)b->d_counters, (void*)b->d_stats, (void*)b->d_acc, (void*)b->d_bitmap,
                   (void*)b->d_marker, (void*)b->d_stack, (void*)b->d_tagctr, (void*)b->d_out_read, (void*)b->d_tap, (void*)b->d_tap_count, (void*)b->d_place_begin,
                   (void*)b->d_place_count, (void*)b->d_node_bitmap, (void*)b->d_node_list, (void*)b->d_node_order, (void*)b->d_sel, (void*)b->d_chain, (void*)b->d_pn_begin, (void*)b->d_pn_count, (void*)b->d_pn_read,
                   (void*)b->d_pn_se, (void*)b->d_pn_flags, (void*)b->d_pn_work, (void*)b->d_pn_mc, (void*)b->d_pn_uc, (void*)b->d_pn_rho, (void*)b->d_pn_d,
@@ -767,7 +768,7 @@ static int enqueue(krepp_batch* b)
   sa.onmers = b->d_onmers; sa.hdfilt = b->d_hdfilt; sa.rec_begin = b->d_rec_begin; sa.rec_count = b->d_rec_count;
   sa.rec_read = b->d_rec_read; sa.rec_slot = b->d_rec_slot; sa.rec_hist = b->d_rec_hist; sa.rho = ix->dev.rho;
   sa.rec_d = b->d_rec_d; sa.rec_v = b->d_rec_v; sa.rec_chisq = b->d_rec_chisq; sa.rec_flags = b->d_rec_flags; sa.rec_match = b->d_rec_match;
-  sa.rec_hdmin = b->d_rec_hdmin; sa.closest = b->d_closest;
+  sa.rec_hdmin = b->d_rec_hdmin; sa.closest = b->d_closest; sa.nsel = b->d_nsel;
   sa.memo_key = b->d_memo_key; sa.memo_owner = b->d_memo_owner; sa.memo_mask = b->memo_mask; sa.memo_bits = b->memo_bits; sa.rec_alias = b->d_rec_alias;
   sa.want_chisq = (!b->p.no_filter || b->p.summarize || b->p.place) ? 1 : 0;
   CU(launch_solve(sa, b->tab, ix->sms, s, &b->clk));
@@ -983,7 +984,7 @@ static int wait_impl(krepp_batch_t* b, krepp_results_t* out, uint32_t rows)
     if (!(b->out_rows & KREPP_OUT_SUMMARIES)) { // they were not assembled by the submit: do it now
       SolveArgs sa{};
       sa.n_reads = b->n_reads; sa.n_records = 0; sa.counters = b->d_counters; sa.onmers = b->d_onmers; sa.hdfilt = b->d_hdfilt;
-      sa.rec_begin = b->d_rec_begin; sa.rec_count = b->d_rec_count; sa.closest = b->d_closest;
+      sa.rec_begin = b->d_rec_begin; sa.rec_count = b->d_rec_count; sa.closest = b->d_closest; sa.nsel = b->d_nsel;
       finalize_kernel<<<b->ix->sms * 4, 128, 0, b->stream>>>(sa, nullptr, b->d_out_read, b->d_wn, b->d_place_begin, b->d_place_count, nullptr, b->p.chisq);
       CU(cudaGetLastError());
     }

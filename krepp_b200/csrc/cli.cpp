@@ -214,7 +214,7 @@ static int run_sharded(const Options& o, const krepp_params_t& p, bool place, co
     ShardDev& d = D[g];
     d.row0 = splits[g]; d.row1 = splits[g + 1];
     check(krepp_batch_create(d.ix, &p, o.batch_reads, o.batch_bases, &d.slot));
-    check(krepp_batch_set_output(d.slot, place ? (KREPP_OUT_RECORDS | KREPP_OUT_PLACEMENTS | KREPP_OUT_SUMMARIES) : KREPP_OUT_DIST));
+    check(krepp_batch_set_output(d.slot, place ? (KREPP_OUT_PLACEMENTS | KREPP_OUT_SUMMARIES) : KREPP_OUT_DIST));
     check(krepp_batch_host_buffers(d.slot, &d.h_bases, &d.h_offsets));
     d.names.resize(64ull * o.batch_reads); d.name_off.resize(o.batch_reads);
     check(krepp_device_alloc(d.dev, o.batch_bases + 64, &d.d_bases));
@@ -387,7 +387,7 @@ int main(int argc, char** argv)
     s.gpu = (int)(i % o.devices.size());
     check(krepp_batch_create(index[s.gpu], &p, o.batch_reads, o.batch_bases, &s.batch));
     // the writers never read the histograms, and `dist` needs only the rows it prints, which the device selects and rounds
-    check(krepp_batch_set_output(s.batch, place ? (KREPP_OUT_RECORDS | KREPP_OUT_PLACEMENTS | KREPP_OUT_SUMMARIES) : KREPP_OUT_DIST));
+    check(krepp_batch_set_output(s.batch, place ? (KREPP_OUT_PLACEMENTS | KREPP_OUT_SUMMARIES) : KREPP_OUT_DIST));
     check(krepp_batch_host_buffers(s.batch, &s.bases, &s.offsets));
     { // result buffers sized once, before the clock starts: a large-bucket index (many genomes) gives ~19 records, ~56 hit entries
       // and, when placing, ~100 tree nodes per 150 bp read; the buffers still grow if a batch needs more

@@ -123,6 +123,7 @@ struct SolveArgs {
   // outputs
   double* rec_d; double* rec_v; double* rec_chisq; uint32_t* rec_flags; uint32_t* rec_match; uint32_t* rec_hdmin;
   int32_t* closest;                  // [n_reads] record index or -1
+  uint32_t* nsel;                    // [n_reads] selected references (entries of node_to_minfo, ref src/query.cpp:114,127-137)
   int want_chisq;
   // Identical problems are solved once per batch: the objective of a record is a function of (histogram, onmers - matches,
   // rho of the leaf) alone, and on a large index most records are weak matches that share those (about nine in ten of the

@@ -717,8 +717,7 @@ extern "C" size_t krepp_format_place(const krepp_index_t* ix, const krepp_params
     if (!s.place_count) continue; // report_placement returned false (ref src/query.cpp:220-222)
     const char* id = name_of(names, name_offsets, r);
     const krepp_placement_t* q = res->placements + s.place_begin;
-    uint32_t nsel = 0;
-    for_selected(res, s, [&](const krepp_record_t&) { ++nsel; });
+    const uint32_t nsel = s.n_selected; // (the records themselves are not needed here: place front ends leave them in HBM)
     const bool text = !tabular && !p->summarize;
     if (text) {
       if (prev) o.put(",\n");

@@ -158,29 +158,31 @@ __global__ void __launch_bounds__(128) merge_kernel(const SolveArgs a)
       if ((a.rec_flags[g] & 1u) && a.rec_d[g] <= best) { best = a.rec_d[g]; cl = (int32_t)g; }
     }
     // two-pointer walk over forward [b, b+nf) and reverse [b+nf, b+n), both ascending in se
-    uint32_t i = b, j = b + nf;
+    uint32_t i = b, j = b + nf, nsel = 0;
     const uint32_t ie = b + nf, je = b + n;
     while (i < ie || j < je) {
       const uint32_t si = i < ie ? (a.rec_slot[i] & 0x7FFFFFFFu) : 0xFFFFFFFFu;
       const uint32_t sj = j < je ? (a.rec_slot[j] & 0x7FFFFFFFu) : 0xFFFFFFFFu;
-      if (si < sj) { if (a.rec_flags[i] & 1u) a.rec_flags[i] |= 2u; ++i; }
-      else if (sj < si) { if (a.rec_flags[j] & 1u) a.rec_flags[j] |= 2u; ++j; }
+      if (si < sj) { if (a.rec_flags[i] & 1u) { a.rec_flags[i] |= 2u; ++nsel; } ++i; }
+      else if (sj < si) { if (a.rec_flags[j] & 1u) { a.rec_flags[j] |= 2u; ++nsel; } ++j; }
       else {
         const bool fs = a.rec_flags[i] & 1u, rs = a.rec_flags[j] & 1u;
         if (rs) {
           const double dr = a.rec_d[j], df = a.rec_d[i];
           const bool fwd_wins = (dr > df) || ((dr == df) && (a.rec_match[j] < a.rec_match[i]));
           if (fwd_wins) a.rec_flags[i] |= 2u; else a.rec_flags[j] |= 2u;
-        } else if (fs) a.rec_flags[i] |= 2u;
+          ++nsel;
+        } else if (fs) { a.rec_flags[i] |= 2u; ++nsel; }
         ++i; ++j;
       }
     }
-    if (cl >= 0) { // node_to_minfo[nd_closest] = mi_closest (ref src/query.cpp:136-138)
+    if (cl >= 0) { // node_to_minfo[nd_closest] = mi_closest (ref src/query.cpp:136-138): the leaf keeps one entry
       const uint32_t se = a.rec_slot[cl] & 0x7FFFFFFFu;
       for (uint32_t q = b; q < b + n; ++q)
         if ((a.rec_slot[q] & 0x7FFFFFFFu) == se) a.rec_flags[q] &= ~2u;
       a.rec_flags[cl] |= 2u | 4u;
     }
+    if (a.nsel) a.nsel[r] = nsel;
     a.closest[r] = cl;
   }
 }

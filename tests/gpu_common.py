@@ -42,6 +42,7 @@ def gpu_stage_dicts(batch: "krepp_b200.IBatch", res: dict, tap: np.ndarray | Non
                 sel.append(dict(leaf_se=int(r["leaf_se"]), strand=int(r["strand"]), is_closest=int(bool(r["flags"] & 4)),
                                 d=float(r["d_llh"]), v=float(r["v_llh"]), chisq=float(r["chisq"])))
         sel.sort(key=lambda e: e["leaf_se"])
+        assert int(s["n_selected"]) == len(sel), (i, "n_selected", int(s["n_selected"]), len(sel))
         pb, pn = int(s["place_begin"]), int(s["place_count"])
         place = [dict(se=int(q["se"]), edge=int(q["se"]) - 1, d=float(q["d_llh"]), v=-float(q["loglik"]), chisq=float(q["chisq"]),
                       lwr=float(q["lwr"]), pendant=float(q["pendant"]), distal=float(q["distal"])) for q in res["placements"][pb:pb + pn]]

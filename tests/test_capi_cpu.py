@@ -33,7 +33,7 @@ def test_header_is_plain_c(tmp_path):
     """The boundary header compiles as C11 with no C++ or torch types in the signatures."""
     import subprocess
     src = tmp_path / "t.c"
-    src.write_text('#include "krepp_b200.h"\nint main(void){ krepp_params_t p; (void)p; return sizeof(krepp_record_t) == 56 && sizeof(krepp_read_summary_t) == 40 && sizeof(krepp_placement_t) == 56 ? 0 : 1; }\n')
+    src.write_text('#include "krepp_b200.h"\nint main(void){ krepp_params_t p; (void)p; return sizeof(krepp_record_t) == 56 && sizeof(krepp_read_summary_t) == 44 && sizeof(krepp_placement_t) == 56 ? 0 : 1; }\n')
     exe = tmp_path / "t"
     subprocess.run(["/usr/bin/gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     assert subprocess.run([str(exe)]).returncode == 0
@@ -41,7 +41,7 @@ def test_header_is_plain_c(tmp_path):
 
 def test_struct_layouts_match_numpy_views():
     from krepp_b200 import capi
-    assert capi.RECORD_DTYPE.itemsize == 56 and capi.READ_DTYPE.itemsize == 40 and capi.PLACEMENT_DTYPE.itemsize == 56
+    assert capi.RECORD_DTYPE.itemsize == 56 and capi.READ_DTYPE.itemsize == 44 and capi.PLACEMENT_DTYPE.itemsize == 56
 
 
 def test_host_index_matches_oracle(lib):

@@ -141,7 +141,7 @@ def results_from_oracle(K, outs, th=4):
                     reads[i]["closest"] = at
             hist[at] = m["hist"]
             at += 1
-        reads[i]["place_begin"], reads[i]["place_count"] = pat, len(o["place"])
+        reads[i]["place_begin"], reads[i]["place_count"], reads[i]["n_selected"] = pat, len(o["place"]), len(o["sel"])
         for q in o["place"]:
             pls[pat] = (i, q["se"], q["pendant"], q["distal"], -q["v"], q["lwr"], q["d"], q["chisq"])
             pat += 1
