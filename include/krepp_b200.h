@@ -55,6 +55,13 @@ typedef struct {
  * flat image to `device`.  Round-1 scope: one partial suffix per directory, with a backbone tree file. */
 #define KREPP_DEVICE_NONE (-1) /* parse + validate only (metadata, tree, names); batches cannot be created on it */
 int krepp_index_open(const char* index_dir, int device, krepp_index_t** out);
+/* The same with `place -t NWK` (TargetIndex::ensure_backbone src/krepp.cpp:48-64, Tree::map_to_qtree / compute_eff_nchildren
+ * src/phytree.cpp:421-473): the Newick tree of nwk_path replaces the index's own backbone for everything after the colour
+ * expansion.  References are matched to its leaves by name; references it does not have are dropped (null nodes,
+ * src/query.cpp:373-376); a node weighs its children by how many of them have an indexed reference below and is a placement
+ * candidate only when all of them do (src/query.cpp:250-271).  Node numbers in records, placements and the jplace tree are
+ * the query tree's.  nwk_path NULL = the index's own tree; shard / nshards as for krepp_index_open_shard. */
+int krepp_index_open_tree(const char* index_dir, int device, uint32_t shard, uint32_t nshards, const char* nwk_path, krepp_index_t** out);
 void krepp_index_close(krepp_index_t* ix);
 int krepp_index_info(const krepp_index_t* ix, krepp_index_info_t* out);
 /* Wrapping 64-bit sums over the arrays of the host image this handle holds, for checking a loader (or a shard's slice) without

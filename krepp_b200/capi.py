@@ -163,6 +163,7 @@ def load_library():
     L.krepp_batch_algorithmic_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.krepp_batch_stage_times.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_char_p), C.POINTER(C.c_uint32)]
     L.krepp_index_open_shard.argtypes = [C.c_char_p, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]
+    L.krepp_index_open_tree.argtypes = [C.c_char_p, C.c_int, C.c_uint32, C.c_uint32, C.c_char_p, C.POINTER(C.c_void_p)]
     L.krepp_index_shard_info.argtypes = [C.c_void_p, C.POINTER(ShardInfo), C.c_void_p, C.c_uint32]
     L.krepp_index_plan_shards.argtypes = [C.c_char_p, C.c_int, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.krepp_shard_lookup.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
@@ -200,11 +201,12 @@ def _view(ptr, dtype, n):
 class Index:
     """Index image resident on one GPU (replaces Index + TargetIndex::load_index, src/krepp.cpp:66-108)."""
 
-    def __init__(self, index_dir: str, device: int = 0, shard: int = 0, nshards: int = 1):
-        """nshards > 1: this handle holds bucket-range shard `shard` of the table only (SURVEY.md 8e mode B)."""
+    def __init__(self, index_dir: str, device: int = 0, shard: int = 0, nshards: int = 1, nwk: str | None = None):
+        """nshards > 1: this handle holds bucket-range shard `shard` of the table only (SURVEY.md 8e mode B).
+        nwk: `place -t` -- a Newick file whose tree replaces the index's backbone (krepp_index_open_tree)."""
         L = load_library()
         self._h = C.c_void_p()
-        _check(L.krepp_index_open_shard(os.fsencode(index_dir), device, shard, nshards, C.byref(self._h)))
+        _check(L.krepp_index_open_tree(os.fsencode(index_dir), device, shard, nshards, os.fsencode(nwk) if nwk else None, C.byref(self._h)))
         self.info = IndexInfo()
         _check(L.krepp_index_info(self._h, C.byref(self.info)))
         self.shard = ShardInfo()

@@ -284,9 +284,10 @@ void krepp_params_default(krepp_params_t* p, int place)
   p->no_filter = place ? 0 : 1; p->multi = 1; p->summarize = 0; p->place = place ? 1 : 0;
 }
 
-int krepp_index_open(const char* index_dir, int device, krepp_index_t** out) { return krepp_index_open_shard(index_dir, device, 0, 1, out); }
+int krepp_index_open(const char* index_dir, int device, krepp_index_t** out) { return krepp_index_open_tree(index_dir, device, 0, 1, nullptr, out); }
+int krepp_index_open_shard(const char* index_dir, int device, uint32_t shard, uint32_t nshards, krepp_index_t** out) { return krepp_index_open_tree(index_dir, device, shard, nshards, nullptr, out); }
 
-int krepp_index_open_shard(const char* index_dir, int device, uint32_t shard, uint32_t nshards, krepp_index_t** out)
+int krepp_index_open_tree(const char* index_dir, int device, uint32_t shard, uint32_t nshards, const char* nwk_path, krepp_index_t** out)
 {
   if (!index_dir || !out) return fail(KREPP_ERR_ARG, "krepp_index_open: null argument");
   *out = nullptr;
@@ -297,7 +298,7 @@ int krepp_index_open_shard(const char* index_dir, int device, uint32_t shard, ui
     if (device < 0 || device >= ndev) return fail(KREPP_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
   }
   auto* ix = new krepp_index;
-  std::string err = ix->host.load(index_dir, shard, nshards);
+  std::string err = ix->host.load(index_dir, shard, nshards, true, nwk_path ? nwk_path : "");
   if (!err.empty()) { delete ix; return fail(KREPP_ERR_IO, "%s", err.c_str()); }
   const HostIndex& h = ix->host;
   if (device == KREPP_DEVICE_NONE) { ix->device = device; *out = ix; return KREPP_OK; } // metadata / tree only, no queries
@@ -319,7 +320,7 @@ int krepp_index_open_shard(const char* index_dir, int device, uint32_t shard, ui
   {
     std::vector<uint2> cnode(h.kind.size(), make_uint2(0u, 0u));
     for (size_t se = 0; se < cnode.size(); ++se) {
-      if (h.kind[se] == 1) cnode[se] = make_uint2(0x80000000u | h.tree.leaf_rank[se], 0u);
+      if (h.kind[se] == 1) cnode[se] = make_uint2(0x80000000u | h.col_rank[se], 0u);
       else if (h.kind[se] == 2) cnode[se] = make_uint2(0x40000000u | (uint32_t)h.pse[se], (uint32_t)(h.pse[se] >> 32));
     }
     if (h.nsubsets >= (1u << 30)) e = cudaErrorInvalidValue; // colour ids must leave the two flag bits free
@@ -330,6 +331,7 @@ int krepp_index_open_shard(const char* index_dir, int device, uint32_t shard, ui
   if (e == cudaSuccess) e = upload(h.tree.leaf_se, &d.leaf_se, ix->allocs, ix->device_bytes);
   if (e == cudaSuccess) e = upload(h.tree.parent, &d.parent, ix->allocs, ix->device_bytes);
   if (e == cudaSuccess) e = upload(h.tree.nchildren, &d.nchildren, ix->allocs, ix->device_bytes);
+  if (e == cudaSuccess) e = upload(h.tree.eff_nchildren, &d.eff_nchildren, ix->allocs, ix->device_bytes);
   if (e == cudaSuccess) e = upload(h.tree.blen, &d.blen, ix->allocs, ix->device_bytes);
   if (e == cudaSuccess) e = upload(build_lut(h), &d.lut, ix->allocs, ix->device_bytes);
   if (e == cudaSuccess) e = upload(h.tree.subtree, &d.subtree, ix->allocs, ix->device_bytes);
@@ -776,7 +778,7 @@ static int enqueue(krepp_batch* b)
   if (b->p.place) {
     PlaceArgs pa{};
     pa.s = sa; pa.offsets = b->in_offsets; pa.tau = b->p.tau; pa.no_filter = b->p.no_filter; pa.chisq_value = b->p.chisq;
-    pa.parent = ix->dev.parent; pa.nchildren = ix->dev.nchildren; pa.subtree = ix->dev.subtree; pa.depth = ix->dev.depth; pa.logw = getenv("KREPP_PLACE_ORDERED") ? nullptr : ix->dev.logw; pa.blen = ix->dev.blen; pa.leaf_rank = ix->dev.leaf_rank;
+    pa.parent = ix->dev.parent; pa.nchildren = ix->dev.nchildren; pa.eff = ix->dev.eff_nchildren; pa.subtree = ix->dev.subtree; pa.depth = ix->dev.depth; pa.logw = getenv("KREPP_PLACE_ORDERED") ? nullptr : ix->dev.logw; pa.blen = ix->dev.blen; pa.leaf_rank = ix->dev.leaf_rank;
     pa.nnodes = h.tree.nnodes; pa.nleaves = h.tree.nleaves; pa.sel = b->d_sel; pa.chain = b->d_chain; pa.chain_cap = b->chain_cap;
     pa.node_bitmap = b->d_node_bitmap; pa.node_list = b->d_node_list; pa.node_order = b->d_node_order;
     pa.node_cap = b->node_cap; pa.pn_read = b->d_pn_read; pa.pn_se = b->d_pn_se; pa.pn_flags = b->d_pn_flags; pa.pn_work = b->d_pn_work;

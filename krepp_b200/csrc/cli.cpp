@@ -54,7 +54,7 @@ const char* kUsage =
   "           --summarize/--no-summarize [false]\n"
   "  dist:    --dist-max X   --multi/--no-multi [true]   --filter/--no-filter [false]\n"
   "  place:   --tau N [2]   --multi/--no-multi [true]   --filter/--no-filter [true]   --tabular/--no-tabular [false]\n"
-  "           -t,--nwk-file / -l,--lineage-file (not supported by the GPU path yet)\n"
+  "           -t,--nwk-file PATH  place on this tree instead of the index's backbone   (-l,--lineage-file: not supported yet)\n"
   "  GPU:     --num-gpus N [1] | --devices 0,1,..   --batch-reads N [262144]   --batch-bases N [67108864]   --slots N [3]\n"
   "           --shard-index   split the index by LSH bucket range over the devices instead of replicating it (for an index\n"
   "                           larger than one GPU's memory; lookups and hits travel between the GPUs by peer copies)\n";
@@ -120,7 +120,8 @@ Options parse(int argc, char** argv)
   if (!exists(o.index_dir, true)) error_exit("--index-dir: Directory does not exist: " + o.index_dir);
   if (o.sub == "place" && !filter_set) o.filter = true; // ref src/krepp.cpp:614
   if (o.sub == "dist" && (o.tabular || !o.nwk_path.empty() || !o.lineage_path.empty())) error_exit("The following argument was not expected for dist");
-  if (!o.nwk_path.empty() || !o.lineage_path.empty()) error_exit("-t/--nwk-file and -l/--lineage-file are not supported by the GPU path yet (placement uses the index's backbone tree)");
+  if (!o.lineage_path.empty()) error_exit("-l/--lineage-file is not supported by the GPU path yet (use the index's backbone tree, or -t/--nwk-file)");
+  if (!o.nwk_path.empty() && !exists(o.nwk_path, false)) error_exit("--nwk-file: File does not exist: " + o.nwk_path);
   if (o.devices.empty()) for (int d = 0; d < (num_gpus > 0 ? num_gpus : 1); ++d) o.devices.push_back(d);
   if (!o.num_threads) o.num_threads = 1;
   if (!o.batch_reads || !o.batch_bases || !o.slots_per_gpu) error_exit("--batch-reads, --batch-bases and --slots must be positive");
@@ -205,7 +206,7 @@ static int run_sharded(const Options& o, const krepp_params_t& p, bool place, co
 {
   const size_t N = o.devices.size();
   std::vector<ShardDev> D(N);
-  each_device(N, [&](size_t g) { D[g].dev = o.devices[g]; check(krepp_index_open_shard(o.index_dir.c_str(), D[g].dev, (uint32_t)g, (uint32_t)N, &D[g].ix)); });
+  each_device(N, [&](size_t g) { D[g].dev = o.devices[g]; check(krepp_index_open_tree(o.index_dir.c_str(), D[g].dev, (uint32_t)g, (uint32_t)N, o.nwk_path.empty() ? nullptr : o.nwk_path.c_str(), &D[g].ix)); });
   krepp_index_info_t info;
   check(krepp_index_info(D[0].ix, &info));
   std::vector<uint32_t> splits(N + 1);
@@ -368,7 +369,7 @@ int main(int argc, char** argv)
     std::vector<std::thread> th;
     std::vector<std::string> err(o.devices.size());
     for (size_t g = 0; g < o.devices.size(); ++g)
-      th.emplace_back([&, g] { if (krepp_index_open(o.index_dir.c_str(), o.devices[g], &index[g]) != KREPP_OK) err[g] = krepp_last_error(); });
+      th.emplace_back([&, g] { if (krepp_index_open_tree(o.index_dir.c_str(), o.devices[g], 0, 1, o.nwk_path.empty() ? nullptr : o.nwk_path.c_str(), &index[g]) != KREPP_OK) err[g] = krepp_last_error(); });
     for (auto& t : th) t.join();
     for (auto& e : err) if (!e.empty()) error_exit(e);
   }

@@ -25,6 +25,7 @@ struct DevIndex {
   const uint32_t* leaf_se;  // by rank
   const uint32_t* parent;   // by se (0 for root)                  ref Node::parent
   const uint32_t* nchildren;// by se
+  const uint32_t* eff_nchildren; // by se: children with an indexed reference below (= nchildren unless place -t replaced the tree)
   const double* blen;       // by se
   const uint32_t* depth;    // by se: number of ancestors
   const uint32_t* logw;     // by se: log2 of the product of the ancestors' child counts when they are all powers of two (HostTree::logw)
@@ -142,7 +143,7 @@ struct PlaceArgs {
   const uint64_t* offsets;     // read offsets (enmers = len - k + 1, ref src/query.cpp:345-349)
   uint32_t tau; int no_filter; double chisq_value;
   // flattened tree (by se)
-  const uint32_t* parent; const uint32_t* nchildren; const uint32_t* subtree; const uint32_t* depth; const uint32_t* logw; const double* blen; const uint32_t* leaf_rank;
+  const uint32_t* parent; const uint32_t* nchildren; const uint32_t* eff; const uint32_t* subtree; const uint32_t* depth; const uint32_t* logw; const double* blen; const uint32_t* leaf_rank;
   uint32_t nnodes, nleaves;
   // per-warp scratch of the collect kernel
   uint32_t* node_bitmap;       // [warps][ceil((nnodes+1)/32)]

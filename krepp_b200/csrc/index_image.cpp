@@ -10,6 +10,7 @@
 #include <fcntl.h>
 #include <thread>
 #include <unistd.h>
+#include <unordered_map>
 #include <fstream>
 #include <limits>
 #include <sstream>
@@ -167,14 +168,20 @@ std::string HostTree::parse(const std::string& newick)
   for (uint32_t se = 1; se <= nnodes; ++se) shown[se] = name[se].empty() ? std::to_string(se - 1) : name[se];
   depth.assign(N, 0);
   for (uint32_t se = nnodes; se >= 1; --se) if (parent[se]) depth[se] = depth[parent[se]] + 1;  // parents have the larger se
+  eff_nchildren = nchildren;
+  compute_logw();
+  return "";
+}
+
+void HostTree::compute_logw()
+{
   logw.assign(nnodes + 1, 0);
-  for (uint32_t se = nnodes; se >= 1; --se) {
+  for (uint32_t se = nnodes; se >= 1; --se) { // parents have the larger se
     const uint32_t p = parent[se];
     if (!p) continue;
-    const uint32_t nc = nchildren[p];
+    const uint32_t nc = eff_nchildren[p];
     logw[se] = (logw[p] == 0xFFFFFFFFu || nc == 0 || (nc & (nc - 1))) ? 0xFFFFFFFFu : logw[p] + (uint32_t)__builtin_ctz(nc);
   }
-  return "";
 }
 
 std::string HostTree::node_name(uint32_t se, bool return_na) const
@@ -258,7 +265,7 @@ static std::vector<uint32_t> split_rows(const std::vector<uint64_t>& inc, uint64
 uint64_t HostIndex::replicated_device_bytes() const
 { // what krepp_index_open_shard uploads besides cmer / inc32 (api.cu)
   const uint64_t nn = (uint64_t)tree.nnodes + 1;
-  return 8ull * pse.size() + kind.size() + 8ull * kind.size() + 8ull * rho.size() + 4ull * nn * 6 + 8ull * nn + 4ull * tree.leaf_se.size() + 8ull * 256 * 16 +
+  return 8ull * pse.size() + kind.size() + 8ull * kind.size() + 8ull * rho.size() + 4ull * nn * 7 + 8ull * nn + 4ull * tree.leaf_se.size() + 8ull * 256 * 16 +
          4ull * cbeg.size() + 4ull * (cleaf.size() + 1);
 }
 
@@ -362,7 +369,7 @@ std::string read_partial(const std::string& dir, Partial& q)
 
 } // namespace
 
-std::string HostIndex::load(const std::string& dir, uint32_t shard_id, uint32_t shard_count, bool with_table)
+std::string HostIndex::load(const std::string& dir, uint32_t shard_id, uint32_t shard_count, bool with_table, const std::string& qtree_path)
 {
   if (!shard_count || shard_id >= shard_count) return "Bad shard arguments for the index!";
   shard = shard_id; nshards = shard_count;
@@ -500,6 +507,37 @@ std::string HostIndex::load(const std::string& dir, uint32_t shard_id, uint32_t 
     }
     if (ent1 - ent0 < (1ull << 32)) { inc32.resize(row1 - row0); for (uint32_t i = row0; i < row1; ++i) inc32[i - row0] = (uint32_t)(inc[i] - ent0); }
   }
+  // ---- which reference (leaf of `tree`) a colour id below cr_nnodes stands for; with a query tree (place -t) the index's own
+  //      tree is only the numbering of the colour ids, and everything downstream lives on the query tree
+  //      (ref src/phytree.cpp:421-448 map_to_qtree: leaves matched by name, unmatched index leaves become null nodes)
+  std::vector<uint8_t> idx_is_leaf(tree.is_leaf.begin(), tree.is_leaf.end());
+  col_rank.assign(cr_nnodes, 0xFFFFFFFFu);
+  if (qtree_path.empty()) {
+    for (uint32_t se = 1; se < cr_nnodes; ++se) if (tree.is_leaf[se]) col_rank[se] = tree.leaf_rank[se];
+  } else {
+    std::string text;
+    if (!slurp(qtree_path, text)) return "Error opening " + qtree_path;
+    HostTree qt;
+    if (std::string err = qt.parse(text); !err.empty()) return err;
+    std::unordered_map<std::string, uint32_t> name_to_se;
+    for (uint32_t se = 1; se < cr_nnodes; ++se) if (tree.is_leaf[se]) name_to_se[tree.name[se]] = se;
+    std::vector<double> qrho(qt.nnodes + 1, 0.0);
+    std::vector<uint8_t> covered(qt.nnodes + 1, 0);
+    for (uint32_t q = 1; q <= qt.nnodes; ++q) {
+      if (!qt.is_leaf[q] || qt.name[q].empty()) continue;
+      auto it = name_to_se.find(qt.name[q]);
+      if (it == name_to_se.end()) continue;
+      col_rank[it->second] = qt.leaf_rank[q];
+      qrho[q] = rho[it->second];
+      for (uint32_t a = q; a && !covered[a]; a = qt.parent[a]) covered[a] = 1; // ref src/phytree.cpp:450-473 compute_eff_nchildren
+    }
+    qt.eff_nchildren.assign(qt.nnodes + 1, 0);
+    for (uint32_t q = 1; q <= qt.nnodes; ++q) if (covered[q] && qt.parent[q]) ++qt.eff_nchildren[qt.parent[q]];
+    qt.compute_logw();
+    tree = std::move(qt);
+    rho.swap(qrho);
+    wbackbone = true;
+  }
   // make_rho_partial: rho *= (#residues present)/m (ref src/index.cpp:188-201, src/record.cpp:304-309)
   {
     uint32_t present = 0;
@@ -510,7 +548,7 @@ std::string HostIndex::load(const std::string& dir, uint32_t shard_id, uint32_t 
   // classify colour ids the way add_matching_mer walks them (ref src/query.cpp:369-387)
   kind.assign(nsubsets, 2);
   kind[0] = 0;
-  for (uint32_t se = 1; se <= tree.nnodes; ++se) kind[se] = tree.is_leaf[se] ? 1 : 2;
+  for (uint32_t se = 1; se < cr_nnodes; ++se) kind[se] = idx_is_leaf[se] ? (col_rank[se] != 0xFFFFFFFFu ? 1 : 0) : 2;
   { // every entry's colour id must exist (several threads: the table is most of the index)
     const size_t n = cmer.size(), nth = n < (1u << 22) ? 1 : 8;
     std::vector<char> bad(nth, 0);
@@ -574,7 +612,7 @@ std::string HostIndex::load(const std::string& dir, uint32_t shard_id, uint32_t 
         for (uint32_t i = lo; i < hi; ++i) {
           const uint32_t se = bylevel[i];
           uint32_t* out = flat.data() + start[se];
-          if (kind[se] == 1) { out[0] = tree.leaf_rank[se]; len[se] = 1; }
+          if (kind[se] == 1) { out[0] = col_rank[se]; len[se] = 1; }
           else if (kind[se] == 2) { // sorted union of the two children's lists
             const uint32_t ca = (uint32_t)pse[se], cb = (uint32_t)(pse[se] >> 32);
             const uint32_t *pa = flat.data() + start[ca], *ea = pa + len[ca], *pb = flat.data() + start[cb], *eb = pb + len[cb];

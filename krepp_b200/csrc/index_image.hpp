@@ -38,6 +38,9 @@ struct BitRun { uint8_t src, width, dst; }; // ((x >> src) & ((1<<width)-1)) << 
 struct HostTree {
   uint32_t nnodes = 0, root = 0, nleaves = 0;
   std::vector<uint32_t> parent, nchildren, card, first_child, next_sibling; // [nnodes+1], by se
+  std::vector<uint32_t> eff_nchildren;   // children with an indexed reference below (ref Tree::compute_eff_nchildren src/phytree.cpp:450-473); = nchildren
+                                         // unless a query tree replaced the index's own (place -t)
+  void compute_logw();                   // from eff_nchildren
   std::vector<uint32_t> depth;           // ancestors of se (0 for the root)
   std::vector<uint32_t> logw;            // sum of log2(nchildren) over the proper ancestors of se when every one of them has a power-of-two
                                          // number of children (a leaf's weight at an ancestor g is then exactly 2^-(logw[leaf] - logw[g])), else 0xffffffff
@@ -70,6 +73,7 @@ struct HostIndex {
   std::vector<uint64_t> pse;                  // nsubsets x (first | second<<32)
   std::vector<double> rho;                    // cr_nnodes, already scaled by make_rho_partial (ref src/index.cpp:188-201)
   std::vector<uint8_t> kind;                  // [nsubsets]: 0 drop (null node), 1 leaf, 2 expand through pse
+  std::vector<uint32_t> col_rank;             // [cr_nnodes]: leaf rank (in `tree`) of the reference whose colour id this is, 0xffffffff otherwise
   uint32_t max_expand_depth = 0;              // deepest colour DAG expansion (bounds the device stack)
   uint32_t max_colour_leaves = 0;
   // Flattened colours for the bucket-sorted pipeline: colour id se expands (the walk of ref src/query.cpp:369-387, null
@@ -87,7 +91,10 @@ struct HostIndex {
   std::vector<uint32_t> row_splits;           // [nshards + 1] first row of every shard; equal cmer bytes per shard
   // Returns "" on success, else an error message (the reference's wording where it has one).
   // with_table = false: everything but the k-mer table itself (cmer stays empty) -- enough to plan a sharding (plan_shards).
-  std::string load(const std::string& dir, uint32_t shard = 0, uint32_t nshards = 1, bool with_table = true);
+  // qtree_path (place -t, ref src/krepp.cpp:48-64 ensure_backbone, src/phytree.cpp:421-448 map_to_qtree): a Newick file whose tree
+  // replaces the index's own for everything after the colour expansion -- references are matched by leaf name, references the
+  // query tree does not have are dropped, and every node number (records, placements, jplace tree) is the query tree's.
+  std::string load(const std::string& dir, uint32_t shard = 0, uint32_t nshards = 1, bool with_table = true, const std::string& qtree_path = "");
   // Device bytes of the parts every shard replicates (colour record, flattened colour lists, tree, hash tables), and of the
   // largest shard's slice of the table when it is split into n bucket-range shards (the split rule of load()).
   uint64_t replicated_device_bytes() const;

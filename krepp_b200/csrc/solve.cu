@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(128) place_collect_kernel(const PlaceArgs a)
             for (uint32_t i = lane; i < nsel; i += 32) {
               double denom = 1.0;
               uint32_t at = sel_off[i];
-              for (uint32_t node = a.parent[sel_se[i]]; node; node = a.parent[node]) { denom /= (double)a.nchildren[node]; chain[at++] = denom; }
+              for (uint32_t node = a.parent[sel_se[i]]; node; node = a.parent[node]) { denom /= (double)a.eff[node]; chain[at++] = denom; }
             }
           __syncwarp();
           // 3b. one lane per marked node: a selected leaf brings its own record, an internal node accumulates the leaves below it
@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(128) place_collect_kernel(const PlaceArgs a)
                   const uint32_t rec = sel_rec[i];
                   double denom = 1.0;
                   if (chained) denom = chain[sel_off[i] + a.depth[se] - gdep - 1];
-                  else for (uint32_t node = a.parent[se];; node = a.parent[node]) { denom /= (double)a.nchildren[node]; if (node == g) break; }
+                  else for (uint32_t node = a.parent[se];; node = a.parent[node]) { denom /= (double)a.eff[node]; if (node == g) break; }
                   const double m = (double)s.rec_match[rec];
                   mismatch = nmers != 0 ? mismatch : (double)enmers;      // Minfo::add (ref src/query.hpp:139-152)
                   match += m * denom;
@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(128) place_collect_kernel(const PlaceArgs a)
                   a.pn_uc[e] = mismatch; a.pn_rho[e] = rho;
                 }
               }
-              const bool eligible = a.nchildren[g] != 1 && (a.no_filter || leq > 1.0);
+              const bool eligible = a.nchildren[g] == a.eff[g] && a.nchildren[g] != 1 && (a.no_filter || leq > 1.0); // ref src/query.cpp:269-271
               a.pn_read[e] = r; a.pn_se[e] = g; a.pn_flags[e] = (solve ? kPnSolve : 0u) | (eligible ? kPnEligible : 0u);
               a.pn_d[e] = d; a.pn_v[e] = v; a.pn_chisq[e] = nan("");
             }
