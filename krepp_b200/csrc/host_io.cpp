@@ -70,7 +70,8 @@ struct krepp_reader {
   // batches of four-line FASTQ are framed chunk-parallel from a window the threads pread together (parallel_fastq below)
   bool regular = false;
   size_t file_len = 0, file_at = 0; // file_at: file offset of the first byte not yet handed to buf
-  std::vector<unsigned char> win;   // the parallel path's window of the file
+  unsigned char* win = nullptr;     // the parallel path's window of the file (malloc'd: no zero fill, first touched by the pread threads)
+  size_t win_cap = 0;
   uint32_t threads = 1;
 };
 
@@ -307,11 +308,16 @@ uint32_t parallel_fastq(krepp_reader* r, size_t pos, char* bases, uint64_t max_b
   const uint32_t T = (uint32_t)std::max<size_t>(1, std::min<size_t>(r->threads, window >> 18));
   static const bool dbg = getenv("KREPP_READER_DEBUG") != nullptr;
   const auto t0 = std::chrono::steady_clock::now();
-  if (r->win.size() < window) r->win.resize(window);
+  if (r->win_cap < window) { // sized with some room so that later windows (slightly different record sizes) fit without a new allocation
+    free(r->win);
+    r->win_cap = window + window / 8 + (1u << 20);
+    r->win = static_cast<unsigned char*>(malloc(r->win_cap));
+    if (!r->win) { r->win_cap = 0; return 0; }
+  }
   {
     auto fill = [&](uint32_t t) {
       size_t lo = window / T * t, hi = t + 1 == T ? window : window / T * (t + 1);
-      while (lo < hi) { const ssize_t got = pread(r->fd, r->win.data() + lo, hi - lo, (off_t)(pos + lo)); if (got <= 0) break; lo += (size_t)got; }
+      while (lo < hi) { const ssize_t got = pread(r->fd, r->win + lo, hi - lo, (off_t)(pos + lo)); if (got <= 0) break; lo += (size_t)got; }
     };
     std::vector<std::thread> th;
     for (uint32_t t = 1; t < T; ++t) th.emplace_back(fill, t);
@@ -319,7 +325,7 @@ uint32_t parallel_fastq(krepp_reader* r, size_t pos, char* bases, uint64_t max_b
     for (auto& x : th) x.join();
   }
   const auto t1 = std::chrono::steady_clock::now();
-  const unsigned char* base = r->win.data();
+  const unsigned char* base = r->win;
   const unsigned char* const fe = base + window;
   pos = 0; // window-relative from here on
   std::vector<size_t> start(T, 0), stop(T, 0);
@@ -451,6 +457,7 @@ extern "C" void krepp_reader_close(krepp_reader_t* r)
   if (!r) return;
   if (r->f) gzclose(r->f);
   if (r->fd >= 0) close(r->fd);
+  free(r->win);
   delete r;
 }
 
@@ -651,6 +658,30 @@ size_t format_dist_compact(const krepp_index_t* ix, const krepp_params_t* p, con
     const char* id = name_of(names, name_offsets, r);
     const size_t id_len = strlen(id);
     if (KREPP_DIST_NA(w0)) { o.put(id, id_len); o.put("\tNA\tNaN\n"); continue; }
+    // every row is id, tab, reference name, tab, d.ddddd, newline: when the read's rows certainly fit, they are written through a
+    // bare pointer (one capacity check per read instead of one per piece)
+    const size_t per_row = id_len + t.max_shown + 11;
+    if (o.len + (size_t)(e - b) * per_row <= o.cap) {
+      char* p = o.buf + o.len;
+      for (uint32_t i = b; i < e; ++i) {
+        uint32_t units;
+        if constexpr (sizeof(Row) == 4) units = rows[i] & 0xFFFFu; else units = (uint32_t)(rows[i] >> 32);
+        const std::string& nm = t.shown[se_of(rows[i])];
+        memcpy(p, id, id_len); p += id_len;
+        *p++ = '\t';
+        memcpy(p, nm.data(), nm.size()); p += nm.size();
+        *p++ = '\t';
+        uint32_t ip = units / 100000u, x = units - ip * 100000u;
+        if (ip < 10) *p++ = (char)('0' + ip);
+        else { char tmp[12]; int n = 0; do { tmp[n++] = (char)('0' + ip % 10); ip /= 10; } while (ip); while (n) *p++ = tmp[--n]; }
+        *p++ = '.';
+        p[4] = (char)('0' + x % 10); x /= 10; p[3] = (char)('0' + x % 10); x /= 10; p[2] = (char)('0' + x % 10); x /= 10; p[1] = (char)('0' + x % 10); x /= 10; p[0] = (char)('0' + x);
+        p += 5;
+        *p++ = '\n';
+      }
+      o.len = (size_t)(p - o.buf);
+      continue;
+    }
     for (uint32_t i = b; i < e; ++i) {
       uint32_t units;
       if constexpr (sizeof(Row) == 4) units = rows[i] & 0xFFFFu; else units = (uint32_t)(rows[i] >> 32);

@@ -165,7 +165,8 @@ std::string HostTree::parse(const std::string& newick)
   subtree.assign(N, 1); subtree[0] = 0;
   for (uint32_t se = 1; se <= nnodes; ++se) if (parent[se]) subtree[parent[se]] += subtree[se]; // children precede parents
   shown.assign(N, "");
-  for (uint32_t se = 1; se <= nnodes; ++se) shown[se] = name[se].empty() ? std::to_string(se - 1) : name[se];
+  max_shown = 0;
+  for (uint32_t se = 1; se <= nnodes; ++se) { shown[se] = name[se].empty() ? std::to_string(se - 1) : name[se]; max_shown = std::max(max_shown, shown[se].size()); }
   depth.assign(N, 0);
   for (uint32_t se = nnodes; se >= 1; --se) if (parent[se]) depth[se] = depth[parent[se]] + 1;  // parents have the larger se
   eff_nchildren = nchildren;

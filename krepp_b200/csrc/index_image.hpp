@@ -49,6 +49,7 @@ struct HostTree {
   std::vector<double> blen;              // NaN when absent
   std::vector<std::string> name;         // "" when unlabeled
   std::vector<std::string> shown;        // node_name(se, false) of every node, built once (the writers print one per output row)
+  size_t max_shown = 0;                  // longest of them
   std::vector<uint32_t> leaf_rank;       // se -> 0-based rank among leaves by ascending se (0xffffffff for non-leaves)
   std::vector<uint32_t> leaf_se;         // rank -> se
   // Parses Newick text with the reference's conventions (ref src/phytree.cpp:84-215): post-order, 1-based se.

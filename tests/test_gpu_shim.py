@@ -108,3 +108,49 @@ def test_cli_modes_equal_the_reference_cli_on_untied_reads(tmp_path):
         assert a.keys() == b.keys() and len(a) > 3, (args, sorted(set(a) ^ set(b))[:5])
         for k in a:
             assert all(abs(x - y) <= 2e-5 for x, y in zip(a[k], b[k])), (args, k, a[k], b[k])
+
+
+ALT_TREE = ("((G000000:0.01,G000002:0.02):0.03,((G000003:0.01,G000001:0.02):0.01,(G000004:0.05,(G000005:0.02,GXXXXXX:0.01):0.02):0.03):0.02,"
+            "G000006:0.08)root;")
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/krepp not built")
+def test_place_on_a_query_tree_equals_the_reference(tmp_path):
+    """`place -t NWK` (ref src/krepp.cpp:48-64, src/phytree.cpp:421-473): a tree with another topology, a multifurcating root, a
+    leaf the index does not have (its parent is then no placement candidate and weighs its one covered child by 1) and without
+    one indexed reference (dropped at colour expansion).  Against the reference CLI, on the reads whose closest reference -- among
+    the references the tree keeps -- is unique; with the index's own tree as -t the output must not change at all."""
+    import oracle_lib as O
+    idx, q = os.path.join(SMALL, "index"), os.path.join(SMALL, "reads.fq")
+    own = run(EXE, "place", "--tabular", "-i", idx, "-q", q).splitlines()[3:]
+    same = run(EXE, "place", "--tabular", "-i", idx, "-q", q, "-t", os.path.join(SMALL, "tree.nwk")).splitlines()[3:]
+    assert own == same and len(own) == 408
+    alt = tmp_path / "alt.nwk"
+    alt.write_text(ALT_TREE + "\n")
+    kept = {"G000000", "G000001", "G000002", "G000003", "G000004", "G000005", "G000006"}
+    o = O.OracleIndex(idx)
+    sub = tmp_path / "untied.fq"
+    n = 0
+    with open(q) as f, open(sub, "w") as g:
+        while True:
+            rec = [f.readline() for _ in range(4)]
+            if not rec[0]:
+                break
+            sel = [x for x in o.query(rec[1].strip().encode(), O.default_params(no_filter=0))["sel"] if o.name(x["leaf_se"]) in kept]
+            if sel:
+                dmin = min(x["d"] for x in sel)
+                if sum(1 for x in sel if x["d"] == dmin) != 1:
+                    continue
+            g.writelines(rec)
+            n += 1
+    assert n > 100
+    for extra in ([], ["--no-filter"], ["--no-multi"]):
+        a = run(EXE, "place", "--tabular", "-i", idx, "-q", str(sub), "-t", str(alt), *extra).splitlines()
+        b = run(REF, "place", "--tabular", "-i", idx, "-q", str(sub), "-t", str(alt), *extra).splitlines()
+        assert a[1] == b[1] and "GXXXXXX" in a[1]                      # the edge-numbered query tree
+        assert sorted(a[3:]) == sorted(b[3:]) and len(a) > 100, (extra, [x for x in a[3:] if x not in set(b)][:4], [x for x in b[3:] if x not in set(a)][:4])
+    ja = rows(run(EXE, "place", "-i", idx, "-q", str(sub), "-t", str(alt)))
+    jb = rows(run(REF, "place", "-i", idx, "-q", str(sub), "-t", str(alt)))
+    assert ja == jb and len(ja) > 100
+    d = run(EXE, "dist", "-i", idx, "-q", q).splitlines()[2:]          # dist takes no tree
+    assert len(d) > 500
