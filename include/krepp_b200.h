@@ -62,6 +62,12 @@ int krepp_index_open(const char* index_dir, int device, krepp_index_t** out);
  * candidate only when all of them do (src/query.cpp:250-271).  Node numbers in records, placements and the jplace tree are
  * the query tree's.  nwk_path NULL = the index's own tree; shard / nshards as for krepp_index_open_shard. */
 int krepp_index_open_tree(const char* index_dir, int device, uint32_t shard, uint32_t nshards, const char* nwk_path, krepp_index_t** out);
+/* The same with `place -l FILE` (TargetIndex::read_lineages src/krepp.cpp:37-46, Tree::parse_lineages src/phytree.cpp:320-370):
+ * the tree is built from a Greengenes/GTDB style lineage file ("NAME<tab>d__A; p__B; ..."), the references hang below the
+ * last taxon of their line, there are no branch lengths (pendant and distal lengths print as 0) and nodes with one child are
+ * kept but are no placement candidates.  Works on an index without a backbone tree too (the reference skips
+ * ensure_backbone with -l). */
+int krepp_index_open_lineages(const char* index_dir, int device, uint32_t shard, uint32_t nshards, const char* lineage_path, krepp_index_t** out);
 void krepp_index_close(krepp_index_t* ix);
 int krepp_index_info(const krepp_index_t* ix, krepp_index_info_t* out);
 /* Wrapping 64-bit sums over the arrays of the host image this handle holds, for checking a loader (or a shard's slice) without

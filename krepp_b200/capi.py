@@ -65,6 +65,7 @@ class Results(C.Structure):
 
 RECORD_DTYPE = np.dtype([("read", "<u4"), ("leaf_se", "<u4"), ("strand", "<u4"), ("match_count", "<u4"), ("hdist_min", "<u4"),
                          ("flags", "<u4"), ("rho", "<f8"), ("d_llh", "<f8"), ("v_llh", "<f8"), ("chisq", "<f8")])
+DEVICE_NONE = -1  # KREPP_DEVICE_NONE: parse + validate only
 READ_DTYPE = np.dtype([("onmers", "<u4"), ("wn", "<u4", (2,)), ("hdist_filt", "<u4", (2,)), ("rec_begin", "<u4"),
                        ("rec_count", "<u4"), ("place_begin", "<u4"), ("place_count", "<u4"), ("closest", "<i4"), ("n_selected", "<u4")])
 PLACEMENT_DTYPE = np.dtype([("read", "<u4"), ("se", "<u4"), ("pendant", "<f8"), ("distal", "<f8"), ("loglik", "<f8"),
@@ -164,6 +165,7 @@ def load_library():
     L.krepp_batch_stage_times.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_char_p), C.POINTER(C.c_uint32)]
     L.krepp_index_open_shard.argtypes = [C.c_char_p, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]
     L.krepp_index_open_tree.argtypes = [C.c_char_p, C.c_int, C.c_uint32, C.c_uint32, C.c_char_p, C.POINTER(C.c_void_p)]
+    L.krepp_index_open_lineages.argtypes = [C.c_char_p, C.c_int, C.c_uint32, C.c_uint32, C.c_char_p, C.POINTER(C.c_void_p)]
     L.krepp_index_shard_info.argtypes = [C.c_void_p, C.POINTER(ShardInfo), C.c_void_p, C.c_uint32]
     L.krepp_index_plan_shards.argtypes = [C.c_char_p, C.c_int, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.krepp_shard_lookup.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
@@ -201,12 +203,16 @@ def _view(ptr, dtype, n):
 class Index:
     """Index image resident on one GPU (replaces Index + TargetIndex::load_index, src/krepp.cpp:66-108)."""
 
-    def __init__(self, index_dir: str, device: int = 0, shard: int = 0, nshards: int = 1, nwk: str | None = None):
+    def __init__(self, index_dir: str, device: int = 0, shard: int = 0, nshards: int = 1, nwk: str | None = None, lineages: str | None = None):
         """nshards > 1: this handle holds bucket-range shard `shard` of the table only (SURVEY.md 8e mode B).
-        nwk: `place -t` -- a Newick file whose tree replaces the index's backbone (krepp_index_open_tree)."""
+        nwk: `place -t` -- a Newick file whose tree replaces the index's backbone (krepp_index_open_tree).
+        lineages: `place -l` -- a Greengenes/GTDB style lineage file whose taxonomy does (krepp_index_open_lineages; wins over nwk)."""
         L = load_library()
         self._h = C.c_void_p()
-        _check(L.krepp_index_open_tree(os.fsencode(index_dir), device, shard, nshards, os.fsencode(nwk) if nwk else None, C.byref(self._h)))
+        if lineages:
+            _check(L.krepp_index_open_lineages(os.fsencode(index_dir), device, shard, nshards, os.fsencode(lineages), C.byref(self._h)))
+        else:
+            _check(L.krepp_index_open_tree(os.fsencode(index_dir), device, shard, nshards, os.fsencode(nwk) if nwk else None, C.byref(self._h)))
         self.info = IndexInfo()
         _check(L.krepp_index_info(self._h, C.byref(self.info)))
         self.shard = ShardInfo()

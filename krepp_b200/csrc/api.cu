@@ -287,7 +287,15 @@ void krepp_params_default(krepp_params_t* p, int place)
 int krepp_index_open(const char* index_dir, int device, krepp_index_t** out) { return krepp_index_open_tree(index_dir, device, 0, 1, nullptr, out); }
 int krepp_index_open_shard(const char* index_dir, int device, uint32_t shard, uint32_t nshards, krepp_index_t** out) { return krepp_index_open_tree(index_dir, device, shard, nshards, nullptr, out); }
 
-int krepp_index_open_tree(const char* index_dir, int device, uint32_t shard, uint32_t nshards, const char* nwk_path, krepp_index_t** out)
+static int open_index(const char* index_dir, int device, uint32_t shard, uint32_t nshards, const char* nwk_path, bool lineages, krepp_index_t** out);
+int krepp_index_open_tree(const char* index_dir, int device, uint32_t shard, uint32_t nshards, const char* nwk_path, krepp_index_t** out) { return open_index(index_dir, device, shard, nshards, nwk_path, false, out); }
+int krepp_index_open_lineages(const char* index_dir, int device, uint32_t shard, uint32_t nshards, const char* lineage_path, krepp_index_t** out)
+{
+  if (!lineage_path) return fail(KREPP_ERR_ARG, "krepp_index_open_lineages: null lineage file");
+  return open_index(index_dir, device, shard, nshards, lineage_path, true, out);
+}
+
+static int open_index(const char* index_dir, int device, uint32_t shard, uint32_t nshards, const char* nwk_path, bool lineages, krepp_index_t** out)
 {
   if (!index_dir || !out) return fail(KREPP_ERR_ARG, "krepp_index_open: null argument");
   *out = nullptr;
@@ -298,7 +306,7 @@ int krepp_index_open_tree(const char* index_dir, int device, uint32_t shard, uin
     if (device < 0 || device >= ndev) return fail(KREPP_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
   }
   auto* ix = new krepp_index;
-  std::string err = ix->host.load(index_dir, shard, nshards, true, nwk_path ? nwk_path : "");
+  std::string err = ix->host.load(index_dir, shard, nshards, true, nwk_path ? nwk_path : "", lineages);
   if (!err.empty()) { delete ix; return fail(KREPP_ERR_IO, "%s", err.c_str()); }
   const HostIndex& h = ix->host;
   if (device == KREPP_DEVICE_NONE) { ix->device = device; *out = ix; return KREPP_OK; } // metadata / tree only, no queries

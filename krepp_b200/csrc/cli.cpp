@@ -54,7 +54,8 @@ const char* kUsage =
   "           --summarize/--no-summarize [false]\n"
   "  dist:    --dist-max X   --multi/--no-multi [true]   --filter/--no-filter [false]\n"
   "  place:   --tau N [2]   --multi/--no-multi [true]   --filter/--no-filter [true]   --tabular/--no-tabular [false]\n"
-  "           -t,--nwk-file PATH  place on this tree instead of the index's backbone   (-l,--lineage-file: not supported yet)\n"
+  "           -t,--nwk-file PATH  place on this tree instead of the index's backbone\n"
+  "           -l,--lineage-file PATH  place on the taxonomy of a Greengenes/GTDB style lineage file (wins over -t)\n"
   "  GPU:     --num-gpus N [1] | --devices 0,1,..   --batch-reads N [262144]   --batch-bases N [67108864]   --slots N [3]\n"
   "           --shard-index   split the index by LSH bucket range over the devices instead of replicating it (for an index\n"
   "                           larger than one GPU's memory; lookups and hits travel between the GPUs by peer copies)\n";
@@ -120,7 +121,7 @@ Options parse(int argc, char** argv)
   if (!exists(o.index_dir, true)) error_exit("--index-dir: Directory does not exist: " + o.index_dir);
   if (o.sub == "place" && !filter_set) o.filter = true; // ref src/krepp.cpp:614
   if (o.sub == "dist" && (o.tabular || !o.nwk_path.empty() || !o.lineage_path.empty())) error_exit("The following argument was not expected for dist");
-  if (!o.lineage_path.empty()) error_exit("-l/--lineage-file is not supported by the GPU path yet (use the index's backbone tree, or -t/--nwk-file)");
+  if (!o.lineage_path.empty() && !exists(o.lineage_path, false)) error_exit("--lineage-file: File does not exist: " + o.lineage_path);
   if (!o.nwk_path.empty() && !exists(o.nwk_path, false)) error_exit("--nwk-file: File does not exist: " + o.nwk_path);
   if (o.devices.empty()) for (int d = 0; d < (num_gpus > 0 ? num_gpus : 1); ++d) o.devices.push_back(d);
   if (!o.num_threads) o.num_threads = 1;
@@ -202,11 +203,18 @@ static void grow(int dev, void*& p, uint64_t& cap, uint64_t want_items)
   check(krepp_device_alloc(dev, 16 * cap, &p));
 }
 
+// the index with the tree the command line asks for: -l (lineages) wins over -t, as in the reference (src/krepp.cpp:742-748)
+static int open_for(const Options& o, int dev, uint32_t shard, uint32_t nshards, krepp_index_t** out)
+{
+  if (!o.lineage_path.empty()) return krepp_index_open_lineages(o.index_dir.c_str(), dev, shard, nshards, o.lineage_path.c_str(), out);
+  return krepp_index_open_tree(o.index_dir.c_str(), dev, shard, nshards, o.nwk_path.empty() ? nullptr : o.nwk_path.c_str(), out);
+}
+
 static int run_sharded(const Options& o, const krepp_params_t& p, bool place, const std::string& invocation, FILE* out)
 {
   const size_t N = o.devices.size();
   std::vector<ShardDev> D(N);
-  each_device(N, [&](size_t g) { D[g].dev = o.devices[g]; check(krepp_index_open_tree(o.index_dir.c_str(), D[g].dev, (uint32_t)g, (uint32_t)N, o.nwk_path.empty() ? nullptr : o.nwk_path.c_str(), &D[g].ix)); });
+  each_device(N, [&](size_t g) { D[g].dev = o.devices[g]; check(open_for(o, D[g].dev, (uint32_t)g, (uint32_t)N, &D[g].ix)); });
   krepp_index_info_t info;
   check(krepp_index_info(D[0].ix, &info));
   std::vector<uint32_t> splits(N + 1);
@@ -369,7 +377,7 @@ int main(int argc, char** argv)
     std::vector<std::thread> th;
     std::vector<std::string> err(o.devices.size());
     for (size_t g = 0; g < o.devices.size(); ++g)
-      th.emplace_back([&, g] { if (krepp_index_open_tree(o.index_dir.c_str(), o.devices[g], 0, 1, o.nwk_path.empty() ? nullptr : o.nwk_path.c_str(), &index[g]) != KREPP_OK) err[g] = krepp_last_error(); });
+      th.emplace_back([&, g] { if (open_for(o, o.devices[g], 0, 1, &index[g]) != KREPP_OK) err[g] = krepp_last_error(); });
     for (auto& t : th) t.join();
     for (auto& e : err) if (!e.empty()) error_exit(e);
   }
@@ -408,7 +416,7 @@ int main(int argc, char** argv)
     check(krepp_batch_wait(s.batch, &res));
   }
 
-  fprintf(stderr, place ? "Placing given sequences on the backbone tree...\n" : "Estimating distances between given sequences and references...\n");
+  fprintf(stderr, place ? (o.lineage_path.empty() ? "Placing given sequences on the backbone tree...\n" : "Placing given sequences on the taxonomic lineage...\n") : "Estimating distances between given sequences and references...\n");
   const auto tquery = std::chrono::system_clock::now();
   std::vector<char> text(1 << 20);
   auto emit = [&](size_t n) { if (n && fwrite(text.data(), 1, n, out) != n) error_exit("Failed to write the output"); };

@@ -80,7 +80,7 @@ struct TreeBuilder {
   HostTree& t;
   std::string error;
   // temporary per-node storage in creation order; se is handed out when a node closes (post-order)
-  struct Tmp { uint32_t se = 0, parent_tmp = 0xffffffffu, nch = 0, card = 0; bool leaf = true; double blen = 0; std::string name; std::vector<uint32_t> kids; };
+  using Tmp = TreeNodeTmp;
   std::vector<Tmp> tmp;
   uint32_t next_se = 0;
 
@@ -142,23 +142,29 @@ std::string HostTree::parse(const std::string& newick)
   TreeBuilder tb(sc.items, *this);
   const uint32_t root_tmp = tb.subtree();
   if (!tb.error.empty()) return tb.error;
-  nnodes = tb.next_se;
+  adopt(tb.tmp, root_tmp, tb.next_se);
+  return "";
+}
+
+void HostTree::adopt(const std::vector<TreeNodeTmp>& tmp, uint32_t root_tmp, uint32_t next_se)
+{
+  nnodes = next_se;
   const size_t N = nnodes + 1;
   parent.assign(N, 0); nchildren.assign(N, 0); card.assign(N, 0); first_child.assign(N, 0); next_sibling.assign(N, 0);
   is_leaf.assign(N, 0); blen.assign(N, std::numeric_limits<double>::quiet_NaN()); name.assign(N, "");
   leaf_rank.assign(N, 0xffffffffu); leaf_se.clear();
-  for (const auto& nd : tb.tmp) {
+  for (const auto& nd : tmp) {
     if (!nd.se) continue;
-    parent[nd.se] = nd.parent_tmp == 0xffffffffu ? 0 : tb.tmp[nd.parent_tmp].se;
+    parent[nd.se] = nd.parent_tmp == 0xffffffffu ? 0 : tmp[nd.parent_tmp].se;
     nchildren[nd.se] = (uint32_t)nd.kids.size();
     card[nd.se] = nd.card; is_leaf[nd.se] = nd.leaf; blen[nd.se] = nd.blen; name[nd.se] = nd.name;
     for (size_t i = 0; i < nd.kids.size(); ++i) {
-      const uint32_t c = tb.tmp[nd.kids[i]].se;
+      const uint32_t c = tmp[nd.kids[i]].se;
       if (i == 0) first_child[nd.se] = c;
-      if (i + 1 < nd.kids.size()) next_sibling[c] = tb.tmp[nd.kids[i + 1]].se;
+      if (i + 1 < nd.kids.size()) next_sibling[c] = tmp[nd.kids[i + 1]].se;
     }
   }
-  root = tb.tmp[root_tmp].se;
+  root = tmp[root_tmp].se;
   for (uint32_t se = 1; se <= nnodes; ++se)
     if (is_leaf[se]) { leaf_rank[se] = (uint32_t)leaf_se.size(); leaf_se.push_back(se); }
   nleaves = (uint32_t)leaf_se.size();
@@ -171,6 +177,72 @@ std::string HostTree::parse(const std::string& newick)
   for (uint32_t se = nnodes; se >= 1; --se) if (parent[se]) depth[se] = depth[parent[se]] + 1;  // parents have the larger se
   eff_nchildren = nchildren;
   compute_logw();
+}
+
+std::string HostTree::parse_lineages(const std::string& text)
+{
+  // ref src/phytree.cpp:320-370 Tree::parse_lineages.  One reference per line, "NAME<tab>d__A; p__B; ...[<tab>ignored]": every
+  // "; " becomes ";", a taxon loses each "<any character>__" it holds (the rank prefix) and is skipped when nothing remains,
+  // taxa are keyed by what remains alone (the same word at two ranks is one node, its parent the first one seen), the
+  // reference hangs below the last taxon of its line.  No branch lengths (NaN), unifurcations stay; numbering is post-order
+  // from a node named "root".  Nodes without a parent hang below the root in the order they first appear: the reference
+  // walks a hash map there, so with more than one top-level taxon its numbering is whatever that map's order is.
+  using Tmp = TreeNodeTmp;
+  std::vector<Tmp> tmp(1);
+  const double nan = std::numeric_limits<double>::quiet_NaN();
+  tmp[0].name = "root"; tmp[0].leaf = false; tmp[0].blen = nan;
+  std::unordered_map<std::string, uint32_t> by_name;
+  auto hang = [&](uint32_t child, uint32_t par) { tmp[child].parent_tmp = par; tmp[par].kids.push_back(child); tmp[par].leaf = false; };
+  auto node = [&](const std::string& nm, bool leaf, uint32_t par) {
+    const uint32_t id = (uint32_t)tmp.size();
+    tmp.emplace_back();
+    tmp[id].name = nm; tmp[id].leaf = leaf; tmp[id].blen = nan;
+    if (par != 0xffffffffu) hang(id, par);
+    by_name.emplace(nm, id);
+    return id;
+  };
+  for (size_t at = 0, n = text.size(); at < n;) {
+    size_t eol = text.find('\n', at);
+    if (eol == std::string::npos) eol = n;
+    std::string line;
+    line.reserve(eol - at);
+    for (size_t i = at; i < eol; ++i) { line += text[i]; if (text[i] == ';' && i + 1 < eol && text[i + 1] == ' ') ++i; }
+    at = eol + 1;
+    const size_t tab = line.find('\t');
+    if (tab == std::string::npos || tab + 1 >= line.size()) return "Failed to reference to lineage mapping!";
+    const std::string ref_name = line.substr(0, tab);
+    const size_t tab2 = line.find('\t', tab + 1);
+    const std::string lineage = line.substr(tab + 1, tab2 == std::string::npos ? std::string::npos : tab2 - tab - 1);
+    uint32_t par = 0xffffffffu;
+    for (size_t p = 0; p < lineage.size();) {
+      size_t e = lineage.find(';', p);
+      if (e == std::string::npos) e = lineage.size();
+      std::string taxon;
+      for (size_t i = p; i < e;) {
+        if (i + 2 < e && lineage[i + 1] == '_' && lineage[i + 2] == '_' && lineage[i] != '\r') i += 3; else taxon += lineage[i++];
+      }
+      p = e + 1;
+      if (taxon.empty()) continue;
+      auto it = by_name.find(taxon);
+      par = it == by_name.end() ? node(taxon, false, par) : it->second;
+    }
+    if (by_name.count(ref_name)) return "The same reference appears more than once in the lineage file.";
+    node(ref_name, true, par);
+  }
+  for (uint32_t id = 1; id < tmp.size(); ++id) if (tmp[id].parent_tmp == 0xffffffffu) hang(id, 0);
+  if (tmp.size() == 1) tmp[0].leaf = true;
+  // post-order numbering, children in the order they were hung; cardinalities bottom-up
+  uint32_t next_se = 0;
+  std::vector<std::pair<uint32_t, uint32_t>> st{{0u, 0u}};
+  while (!st.empty()) {
+    const uint32_t id = st.back().first, k = st.back().second;
+    if (k < tmp[id].kids.size()) { ++st.back().second; st.push_back({tmp[id].kids[k], 0u}); continue; }
+    tmp[id].se = ++next_se;
+    tmp[id].card = tmp[id].leaf ? 1 : 0;
+    for (uint32_t c : tmp[id].kids) tmp[id].card += tmp[c].card;
+    st.pop_back();
+  }
+  adopt(tmp, 0, next_se);
   return "";
 }
 
@@ -370,7 +442,7 @@ std::string read_partial(const std::string& dir, Partial& q)
 
 } // namespace
 
-std::string HostIndex::load(const std::string& dir, uint32_t shard_id, uint32_t shard_count, bool with_table, const std::string& qtree_path)
+std::string HostIndex::load(const std::string& dir, uint32_t shard_id, uint32_t shard_count, bool with_table, const std::string& qtree_path, bool lineages)
 {
   if (!shard_count || shard_id >= shard_count) return "Bad shard arguments for the index!";
   shard = shard_id; nshards = shard_count;
@@ -519,7 +591,7 @@ std::string HostIndex::load(const std::string& dir, uint32_t shard_id, uint32_t 
     std::string text;
     if (!slurp(qtree_path, text)) return "Error opening " + qtree_path;
     HostTree qt;
-    if (std::string err = qt.parse(text); !err.empty()) return err;
+    if (std::string err = lineages ? qt.parse_lineages(text) : qt.parse(text); !err.empty()) return err;
     std::unordered_map<std::string, uint32_t> name_to_se;
     for (uint32_t se = 1; se < cr_nnodes; ++se) if (tree.is_leaf[se]) name_to_se[tree.name[se]] = se;
     std::vector<double> qrho(qt.nnodes + 1, 0.0);

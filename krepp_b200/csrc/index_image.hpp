@@ -35,6 +35,9 @@ struct NoInitAlloc {
 
 struct BitRun { uint8_t src, width, dst; }; // ((x >> src) & ((1<<width)-1)) << dst
 
+// a node while a tree is being built (creation order; se is handed out when the node closes, post-order)
+struct TreeNodeTmp { uint32_t se = 0, parent_tmp = 0xffffffffu, nch = 0, card = 0; bool leaf = true; double blen = 0; std::string name; std::vector<uint32_t> kids; };
+
 struct HostTree {
   uint32_t nnodes = 0, root = 0, nleaves = 0;
   std::vector<uint32_t> parent, nchildren, card, first_child, next_sibling; // [nnodes+1], by se
@@ -55,6 +58,9 @@ struct HostTree {
   // Parses Newick text with the reference's conventions (ref src/phytree.cpp:84-215): post-order, 1-based se.
   // Returns an empty string on success, else the error message.
   std::string parse(const std::string& newick);
+  // Builds the tree of a Greengenes/GTDB style lineage file, `place -l` (ref src/phytree.cpp:320-370).
+  std::string parse_lineages(const std::string& text);
+  void adopt(const std::vector<TreeNodeTmp>& tmp, uint32_t root_tmp, uint32_t next_se);
   std::string node_name(uint32_t se, bool return_na) const; // ref src/phytree.hpp:133-144
   std::string jplace_newick() const;                         // ref src/phytree.cpp:47-64
 };
@@ -95,7 +101,7 @@ struct HostIndex {
   // qtree_path (place -t, ref src/krepp.cpp:48-64 ensure_backbone, src/phytree.cpp:421-448 map_to_qtree): a Newick file whose tree
   // replaces the index's own for everything after the colour expansion -- references are matched by leaf name, references the
   // query tree does not have are dropped, and every node number (records, placements, jplace tree) is the query tree's.
-  std::string load(const std::string& dir, uint32_t shard = 0, uint32_t nshards = 1, bool with_table = true, const std::string& qtree_path = "");
+  std::string load(const std::string& dir, uint32_t shard = 0, uint32_t nshards = 1, bool with_table = true, const std::string& qtree_path = "", bool lineages = false);
   // Device bytes of the parts every shard replicates (colour record, flattened colour lists, tree, hash tables), and of the
   // largest shard's slice of the table when it is split into n bucket-range shards (the split rule of load()).
   uint64_t replicated_device_bytes() const;

@@ -935,3 +935,83 @@ void ko_extract_mers(const ko_index_t* g, const char* seq, uint64_t len, uint32_
   }
   free(win);
 }
+
+/* ------------------------------------------------------------------------------------------------ seek (a sketch of one genome) */
+
+struct ko_sketch {
+  ko_index_t geom;  /* k, w, h, m, positions and masks; no tables */
+  uint32_t r, frac, nrows;
+  uint64_t nkmers;
+  uint32_t* enc;    /* nkmers residual encodings (ref src/table.hpp SFlatHT::enc_v) */
+  uint64_t* inc;    /* nrows cumulative ends */
+  double rho;       /* after make_rho_partial */
+};
+
+/* ref src/sketch.cpp:3-23 Sketch::load_full_sketch (SFlatHT::load src/table.cpp:23-33, then the metadata, then rho) and
+ * :25-32 make_rho_partial */
+ko_sketch_t* ko_sketch_load(const char* path, char* err, size_t errlen)
+{
+  FILE* f = fopen(path, "rb");
+  if (!f) { seterr(err, errlen, "Failed to open %s", path); return NULL; }
+  ko_sketch_t* s = (ko_sketch_t*)calloc(1, sizeof *s);
+  int ok = fread(&s->nkmers, 8, 1, f) == 1;
+  if (ok) { s->enc = (uint32_t*)malloc((s->nkmers ? s->nkmers : 1) * 4); ok = fread(s->enc, 4, s->nkmers, f) == s->nkmers; }
+  uint32_t nrows = 0;
+  ok = ok && fread(&nrows, 4, 1, f) == 1;
+  if (ok) { s->inc = (uint64_t*)malloc((nrows ? nrows : 1) * 8ull); ok = fread(s->inc, 8, nrows, f) == nrows; }
+  uint8_t k = 0, w = 0, h = 0, frac = 0;
+  uint32_t m = 0, r = 0, nrows2 = 0;
+  ok = ok && fread(&k, 1, 1, f) == 1 && fread(&w, 1, 1, f) == 1 && fread(&h, 1, 1, f) == 1 && fread(&m, 4, 1, f) == 1 && fread(&r, 4, 1, f) == 1 &&
+       fread(&frac, 1, 1, f) == 1 && fread(&nrows2, 4, 1, f) == 1;
+  ok = ok && k && k <= 32 && h && h < k && m;
+  if (ok) ok = fread(s->geom.ppos, 1, h, f) == h && fread(s->geom.npos, 1, (size_t)(k - h), f) == (size_t)(k - h) && fread(&s->rho, 8, 1, f) == 1;
+  fclose(f);
+  if (!ok) { seterr(err, errlen, "Failed to read the sketch file!"); ko_sketch_free(s); return NULL; }
+  s->geom.k = k; s->geom.w = w; s->geom.h = h; s->geom.m = m;
+  s->r = r; s->frac = frac; s->nrows = nrows;
+  set_masks(&s->geom);
+  s->rho *= frac ? ((double)r + 1.0) / (double)m : 1.0 / (double)m;
+  return s;
+}
+
+void ko_sketch_free(ko_sketch_t* s) { if (s) { free(s->enc); free(s->inc); free(s); } }
+uint32_t ko_sketch_k(const ko_sketch_t* s) { return s->geom.k; }
+double ko_sketch_rho(const ko_sketch_t* s) { return s->rho; }
+
+/* ref src/seek.cpp:22-53 seek_sequences (one sequence), :55-101 search_mers (non-CANONICAL), :103-120 add_matching_mer,
+ * :121-127 optimize_likelihood; bucket addressing src/sketch.cpp:34-39, residue test src/sketch.hpp:18-22 */
+void ko_seek_read(const ko_sketch_t* s, uint32_t th, const char* seq, uint64_t len, ko_seek_t* out)
+{
+  const ko_index_t* g = &s->geom;
+  const uint32_t k = g->k;
+  memset(out, 0, sizeof *out);
+  out->dist = NAN; out->d[0] = out->d[1] = NAN; out->v[0] = out->v[1] = NAN;
+  uint64_t i, l, onmers = 0;
+  uint64_t bp = 0, lr = 0, rcbp;
+  for (i = l = 0; i < len;) {
+    unsigned c = nt4((unsigned char)seq[i]);
+    if (c >= 4) { l = 0; i++; continue; }
+    l++; i++;
+    bp = (bp << 2) + c; lr = ((lr << 1) & 0xFFFFFFFEFFFFFFFEull) + (c & 1) + ((uint64_t)(c >> 1) << 32);
+    if (l < k) continue;
+    bp &= g->mask_bp; lr &= g->mask_lr;
+    rcbp = ko_revcomp_bp64(bp, k);
+    onmers++;
+    for (uint32_t st = 0; st < 2; ++st) {
+      const uint64_t ebp = st ? rcbp : bp, elr = st ? ko_conv_bp64_lr64(rcbp) : lr;
+      const uint32_t rix = (uint32_t)ko_pext64(ebp, g->mask_hash_bp), res = rix % g->m;
+      if (!((s->frac && res <= s->r) || res == s->r)) continue;
+      const uint32_t enc = (uint32_t)ko_pext64(elr, g->mask_drop_lr);
+      const uint64_t off = s->frac ? (uint64_t)(rix / g->m) * (s->r + 1) + res : rix / g->m;
+      if (off >= s->nrows) continue; /* the reference would read past inc_v here; a valid sketch has the row */
+      uint32_t hmin = th + 1;
+      for (uint64_t e = off ? s->inc[off - 1] : 0; e < s->inc[off]; ++e) { const uint32_t hd = ko_popcount_lr32(s->enc[e] ^ enc); if (hd < hmin) hmin = hd; }
+      if (hmin <= th) { out->match[st] += 1; out->hist[st][hmin] += 1; }
+    }
+  }
+  out->onmers = onmers;
+  if (out->match[0] + out->match[1] == 0) return;
+  out->found = 1;
+  for (uint32_t st = 0; st < 2; ++st) ko_brent(g->h, k, th, out->hist[st], (double)onmers - out->match[st], s->rho, &out->d[st], &out->v[st], NULL);
+  out->dist = out->d[0] < out->d[1] ? out->d[0] : out->d[1];
+}

@@ -43,6 +43,11 @@ class Read(C.Structure):
                 ("sel", C.POINTER(Sel)), ("place", C.POINTER(Place))]
 
 
+class Seek(C.Structure):
+    _fields_ = [("onmers", C.c_uint64), ("hist", (C.c_double * 8) * 2), ("match", C.c_double * 2), ("d", C.c_double * 2), ("v", C.c_double * 2),
+                ("dist", C.c_double), ("found", C.c_int)]
+
+
 def build() -> str:
     subprocess.run(["make", "-s", "-C", ORACLE_DIR, "port"], check=True)
     return LIB_PATH
@@ -96,6 +101,14 @@ def lib():
         L.ko_geom_new.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_char_p]
         L.ko_extract_mers.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint32, C.POINTER(C.POINTER(C.c_uint64)),
                                       C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.ko_sketch_load.restype = C.c_void_p
+        L.ko_sketch_load.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t]
+        L.ko_sketch_free.argtypes = [C.c_void_p]
+        L.ko_sketch_k.restype = C.c_uint32
+        L.ko_sketch_k.argtypes = [C.c_void_p]
+        L.ko_sketch_rho.restype = C.c_double
+        L.ko_sketch_rho.argtypes = [C.c_void_p]
+        L.ko_seek_read.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.c_uint64, C.POINTER(Seek)]
         _lib = L
     return _lib
 
@@ -105,6 +118,32 @@ def default_params(**kw) -> Params:
     for k, v in kw.items():
         setattr(p, k, v)
     return p
+
+
+class OracleSketch:
+    """The sketch of one genome (`krepp sketch`) and `krepp seek` on it."""
+
+    def __init__(self, path: str):
+        err = C.create_string_buffer(512)
+        self.h = lib().ko_sketch_load(path.encode(), err, 512)
+        if not self.h:
+            raise RuntimeError(err.value.decode())
+        self.k, self.rho = lib().ko_sketch_k(self.h), lib().ko_sketch_rho(self.h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().ko_sketch_free(self.h)
+            self.h = None
+
+    def seek(self, seq: bytes, th: int = 4) -> dict:
+        r = Seek()
+        lib().ko_seek_read(self.h, th, seq, len(seq), C.byref(r))
+        return {"onmers": r.onmers, "hist": [[int(r.hist[s][x]) for x in range(th + 1)] for s in range(2)], "match": [int(r.match[0]), int(r.match[1])],
+                "d": [r.d[0], r.d[1]], "v": [r.v[0], r.v[1]], "dist": r.dist, "found": bool(r.found)}
+
+    def tsv_row(self, name: str, seq: bytes, th: int = 4) -> str:
+        r = self.seek(seq, th)
+        return f"{name}\t{r['dist']:.5f}" if r["found"] else f"{name}\tNaN"
 
 
 class OracleIndex:

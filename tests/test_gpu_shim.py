@@ -114,20 +114,11 @@ ALT_TREE = ("((G000000:0.01,G000002:0.02):0.03,((G000003:0.01,G000001:0.02):0.01
             "G000006:0.08)root;")
 
 
-@pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/krepp not built")
-def test_place_on_a_query_tree_equals_the_reference(tmp_path):
-    """`place -t NWK` (ref src/krepp.cpp:48-64, src/phytree.cpp:421-473): a tree with another topology, a multifurcating root, a
-    leaf the index does not have (its parent is then no placement candidate and weighs its one covered child by 1) and without
-    one indexed reference (dropped at colour expansion).  Against the reference CLI, on the reads whose closest reference -- among
-    the references the tree keeps -- is unique; with the index's own tree as -t the output must not change at all."""
+def untied_subset(tmp_path, kept):
+    """The golden reads whose closest reference, among the references `kept`, is unique (ties are broken by container order in
+    the reference), as a FASTQ file."""
     import oracle_lib as O
     idx, q = os.path.join(SMALL, "index"), os.path.join(SMALL, "reads.fq")
-    own = run(EXE, "place", "--tabular", "-i", idx, "-q", q).splitlines()[3:]
-    same = run(EXE, "place", "--tabular", "-i", idx, "-q", q, "-t", os.path.join(SMALL, "tree.nwk")).splitlines()[3:]
-    assert own == same and len(own) == 408
-    alt = tmp_path / "alt.nwk"
-    alt.write_text(ALT_TREE + "\n")
-    kept = {"G000000", "G000001", "G000002", "G000003", "G000004", "G000005", "G000006"}
     o = O.OracleIndex(idx)
     sub = tmp_path / "untied.fq"
     n = 0
@@ -144,6 +135,23 @@ def test_place_on_a_query_tree_equals_the_reference(tmp_path):
             g.writelines(rec)
             n += 1
     assert n > 100
+    return sub
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/krepp not built")
+def test_place_on_a_query_tree_equals_the_reference(tmp_path):
+    """`place -t NWK` (ref src/krepp.cpp:48-64, src/phytree.cpp:421-473): a tree with another topology, a multifurcating root, a
+    leaf the index does not have (its parent is then no placement candidate and weighs its one covered child by 1) and without
+    one indexed reference (dropped at colour expansion).  Against the reference CLI, on the reads whose closest reference -- among
+    the references the tree keeps -- is unique; with the index's own tree as -t the output must not change at all."""
+    idx, q = os.path.join(SMALL, "index"), os.path.join(SMALL, "reads.fq")
+    own = run(EXE, "place", "--tabular", "-i", idx, "-q", q).splitlines()[3:]
+    same = run(EXE, "place", "--tabular", "-i", idx, "-q", q, "-t", os.path.join(SMALL, "tree.nwk")).splitlines()[3:]
+    assert own == same and len(own) == 408
+    alt = tmp_path / "alt.nwk"
+    alt.write_text(ALT_TREE + "\n")
+    kept = {"G000000", "G000001", "G000002", "G000003", "G000004", "G000005", "G000006"}
+    sub = untied_subset(tmp_path, kept)
     for extra in ([], ["--no-filter"], ["--no-multi"]):
         a = run(EXE, "place", "--tabular", "-i", idx, "-q", str(sub), "-t", str(alt), *extra).splitlines()
         b = run(REF, "place", "--tabular", "-i", idx, "-q", str(sub), "-t", str(alt), *extra).splitlines()
@@ -154,3 +162,27 @@ def test_place_on_a_query_tree_equals_the_reference(tmp_path):
     assert ja == jb and len(ja) > 100
     d = run(EXE, "dist", "-i", idx, "-q", q).splitlines()[2:]          # dist takes no tree
     assert len(d) > 500
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/krepp not built")
+def test_place_on_lineages_equals_the_reference(tmp_path):
+    """`place -l FILE` (ref src/krepp.cpp:37-46,742-744, src/phytree.cpp:320-370): the taxonomy of a lineage file as the placement
+    tree -- chains of one-child nodes (never candidates), no branch lengths (pendant and distal print as 0), a reference the
+    index lacks, an indexed reference left out.  Against the reference CLI in every output form; -l wins over -t."""
+    from lineages import KEPT, LINEAGES
+    idx = os.path.join(SMALL, "index")
+    lin = tmp_path / "lin.tsv"
+    lin.write_text(LINEAGES)
+    sub = untied_subset(tmp_path, KEPT)
+    for extra in ([], ["--no-filter"], ["--no-multi"], ["-t", os.path.join(SMALL, "tree.nwk")]):
+        a = run(EXE, "place", "--tabular", "-i", idx, "-q", str(sub), "-l", str(lin), *extra).splitlines()
+        b = run(REF, "place", "--tabular", "-i", idx, "-q", str(sub), "-l", str(lin), *extra).splitlines()
+        assert a[1] == b[1] and "Bacteria{30})root{31};" in a[1]
+        assert sorted(a[3:]) == sorted(b[3:]) and len(a) > 100, (extra, [x for x in a[3:] if x not in set(b)][:4], [x for x in b[3:] if x not in set(a)][:4])
+        assert any("\tGd\t19\t" in x or "\tPb\t29\t" in x for x in a[3:])    # placements on taxa
+    ja = rows(run(EXE, "place", "-i", idx, "-q", str(sub), "-l", str(lin)))
+    jb = rows(run(REF, "place", "-i", idx, "-q", str(sub), "-l", str(lin)))
+    assert ja == jb and len(ja) > 100
+    sa = run(EXE, "place", "--summarize", "-i", idx, "-q", str(sub), "-l", str(lin)).splitlines()
+    sb = run(REF, "place", "--summarize", "-i", idx, "-q", str(sub), "-l", str(lin)).splitlines()
+    assert sa[1] == sb[1] and len(sa) == len(sb)
