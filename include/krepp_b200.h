@@ -67,6 +67,12 @@ int krepp_index_open_tree(const char* index_dir, int device, uint32_t shard, uin
  * last taxon of their line, there are no branch lengths (pendant and distal lengths print as 0) and nodes with one child are
  * kept but are no placement candidates.  Works on an index without a backbone tree too (the reference skips
  * ensure_backbone with -l). */
+/* `krepp seek -i SKETCH` (TargetSketch::load_sketch src/krepp.cpp:31-35, Sketch::load_full_sketch / make_rho_partial
+ * src/sketch.cpp:3-32): the sketch file of ONE genome written by `krepp sketch` -- a table of 4-byte residual encodings without
+ * colours, its LSH geometry and the genome's rho.  It is held as an index whose tree is a single leaf named after the file, so
+ * krepp_index_info and the batch calls work on it unchanged; a batch on it gives at most one record per strand, and
+ * KREPP_OUT_SEEK the distance SBatch::seek_sequences prints (src/seek.cpp:22-53).  `place` is refused. */
+int krepp_sketch_open(const char* sketch_path, int device, krepp_index_t** out);
 int krepp_index_open_lineages(const char* index_dir, int device, uint32_t shard, uint32_t nshards, const char* lineage_path, krepp_index_t** out);
 void krepp_index_close(krepp_index_t* ix);
 int krepp_index_info(const krepp_index_t* ix, krepp_index_info_t* out);
@@ -174,6 +180,8 @@ typedef struct {
   const void* dist_rows;              /* [n_dist_rows] rows of dist_row_bytes bytes */
   uint64_t n_dist_rows;
   uint32_t dist_row_bytes;            /* 4 or 8 */
+  const double* seek_dist;            /* [n_reads] when KREPP_OUT_SEEK was asked for, else NULL: SBatch::seek_sequences' distance (src/seek.cpp:22-53),
+                                         the smaller of the two strands' estimates; NaN = no k-mer of the read matched the sketch */
 } krepp_results_t;
 
 /* -------------------------------------------------------------------------------------------------- batches */
@@ -223,6 +231,7 @@ int krepp_batch_wait(krepp_batch_t* b, krepp_results_t* out);
 #define KREPP_OUT_DIST 16u /* the printed rows of `krepp dist` (see krepp_results_t): 4 bytes per read + 4 or 8 per printed row.
                               Not part of KREPP_OUT_ALL; krepp_format_dist prefers them when present. */
 #define KREPP_OUT_SUMMARIES 32u /* the 44-byte krepp_read_summary_t rows; a front end that asks for KREPP_OUT_DIST alone does without */
+#define KREPP_OUT_SEEK 64u /* sketch handles (krepp_sketch_open) only: one double per read, what `krepp seek` prints (seek_dist) */
 #define KREPP_OUT_ALL 39u
 /* Must be called while no batch is pending on the slot (before krepp_batch_submit, or after the krepp_batch_wait that follows
  * it): the kernels that assemble the rows run as part of the submit.  KREPP_ERR_ARG otherwise. */
@@ -371,6 +380,10 @@ size_t krepp_format_dist(const krepp_index_t* ix, const krepp_params_t* p, const
 size_t krepp_format_place(const krepp_index_t* ix, const krepp_params_t* p, const krepp_results_t* res,
                           const char* names, const uint64_t* name_offsets, int tabular, int* has_previous, double* wcount,
                           char* buf, size_t cap);
+/* SBatch::seek_sequences' rows for a batch on a sketch handle (src/seek.cpp:41-49): "<id>\t<distance>", "<id>\tNaN" for a read
+ * without a matching k-mer; needs res->seek_dist (KREPP_OUT_SEEK).  `krepp seek` writes no header line (the reference builds one,
+ * src/krepp.cpp:305-309, and never sends it to the output). */
+size_t krepp_format_seek(const krepp_results_t* res, const char* names, const uint64_t* name_offsets, char* buf, size_t cap);
 /* Tail of the output: the --summarize table (src/krepp.cpp:385-392,492-497) or end_jplace (src/krepp.cpp:410-424). */
 size_t krepp_format_footer(const krepp_index_t* ix, const krepp_params_t* p, int tabular, const double* wcount,
                            uint64_t total_queries, const char* invocation, char* buf, size_t cap);

@@ -60,7 +60,8 @@ class Results(C.Structure):
     _fields_ = [("n_reads", C.c_uint32), ("hist_stride", C.c_uint32), ("n_records", C.c_uint64), ("n_placements", C.c_uint64),
                 ("reads", C.c_void_p), ("records", C.c_void_p), ("hist", C.c_void_p), ("placements", C.c_void_p),
                 ("gpu_ms", C.c_float), ("match_ms", C.c_float), ("gpu_launches", C.c_uint32), ("brief", C.c_void_p),
-                ("dist_begin", C.c_void_p), ("dist_rows", C.c_void_p), ("n_dist_rows", C.c_uint64), ("dist_row_bytes", C.c_uint32)]
+                ("dist_begin", C.c_void_p), ("dist_rows", C.c_void_p), ("n_dist_rows", C.c_uint64), ("dist_row_bytes", C.c_uint32),
+                ("seek_dist", C.c_void_p)]
 
 
 RECORD_DTYPE = np.dtype([("read", "<u4"), ("leaf_se", "<u4"), ("strand", "<u4"), ("match_count", "<u4"), ("hdist_min", "<u4"),
@@ -165,6 +166,7 @@ def load_library():
     L.krepp_batch_stage_times.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_char_p), C.POINTER(C.c_uint32)]
     L.krepp_index_open_shard.argtypes = [C.c_char_p, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]
     L.krepp_index_open_tree.argtypes = [C.c_char_p, C.c_int, C.c_uint32, C.c_uint32, C.c_char_p, C.POINTER(C.c_void_p)]
+    L.krepp_sketch_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
     L.krepp_index_open_lineages.argtypes = [C.c_char_p, C.c_int, C.c_uint32, C.c_uint32, C.c_char_p, C.POINTER(C.c_void_p)]
     L.krepp_index_shard_info.argtypes = [C.c_void_p, C.POINTER(ShardInfo), C.c_void_p, C.c_uint32]
     L.krepp_index_plan_shards.argtypes = [C.c_char_p, C.c_int, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
@@ -179,6 +181,8 @@ def load_library():
                                     C.POINTER(C.c_uint32), C.POINTER(C.c_int)]
     for f in ("krepp_format_header", "krepp_format_dist", "krepp_format_place", "krepp_format_footer"):
         getattr(L, f).restype = C.c_size_t
+    L.krepp_format_seek.restype = C.c_size_t
+    L.krepp_format_seek.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_size_t]
     L.krepp_format_header.argtypes = [C.c_void_p, C.POINTER(Params), C.c_int, C.c_char_p, C.c_void_p, C.c_size_t]
     L.krepp_format_dist.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Results), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
     L.krepp_format_place.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Results), C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int),
@@ -209,7 +213,9 @@ class Index:
         lineages: `place -l` -- a Greengenes/GTDB style lineage file whose taxonomy does (krepp_index_open_lineages; wins over nwk)."""
         L = load_library()
         self._h = C.c_void_p()
-        if lineages:
+        if os.path.isfile(index_dir):  # the sketch of one genome (`krepp sketch`), queried by `krepp seek`
+            _check(L.krepp_sketch_open(os.fsencode(index_dir), device, C.byref(self._h)))
+        elif lineages:
             _check(L.krepp_index_open_lineages(os.fsencode(index_dir), device, shard, nshards, os.fsencode(lineages), C.byref(self._h)))
         else:
             _check(L.krepp_index_open_tree(os.fsencode(index_dir), device, shard, nshards, os.fsencode(nwk) if nwk else None, C.byref(self._h)))
@@ -378,14 +384,24 @@ class IBatch:
             placements=_view(r.placements, PLACEMENT_DTYPE, int(r.n_placements)), brief=_view(r.brief, BRIEF_DTYPE, nrec),
             dist_begin=_view(r.dist_begin, np.dtype("<u4"), r.n_reads + 1 if r.dist_begin else 0),
             dist_rows=_view(r.dist_rows, np.dtype("<u4" if r.dist_row_bytes == 4 else "<u8"), int(r.n_dist_rows) if r.dist_begin else 0),
+            seek_dist=_view(r.seek_dist, np.dtype("<f8"), r.n_reads if r.seek_dist else 0),
             n_records=nrec, gpu_ms=float(r.gpu_ms), match_ms=float(r.match_ms), gpu_launches=int(r.gpu_launches))
         return self._res
 
     def set_output(self, records: bool = True, hist: bool = True, placements: bool = True, brief: bool = False, dist: bool = False,
-                   summaries: bool = True):
+                   summaries: bool = True, seek: bool = False):
         """krepp_batch_set_output: which row arrays wait() copies to the host (the others come back empty)."""
         _check(load_library().krepp_batch_set_output(self._h, int(records) | 2 * int(hist) | 4 * int(placements) | 8 * int(brief) | 16 * int(dist)
-                                                     | 32 * int(summaries)))
+                                                     | 32 * int(summaries) | 64 * int(seek)))
+
+    def seek_sequences(self) -> str:
+        """Rows of `krepp seek` for this batch on a sketch handle (SBatch::seek_sequences, src/seek.cpp:22-53): "<id>\t<distance>",
+        "<id>\tNaN" when no k-mer matched."""
+        if self._res is None:
+            self.set_output(seek=True)
+        d = self.results()["seek_dist"]
+        names = self.names if self.names is not None else [f"r{i}" for i in range(self.n_reads)]
+        return "".join(f"{n}\tNaN\n" if math.isnan(x) else f"{n}\t{x:.5f}\n" for n, x in zip(names, d))
 
     def reserve(self, records: int = 0, hits: int = 0, nodes: int = 0, placements: int = 0):
         """krepp_batch_reserve: pre-size the result buffers (per batch) instead of letting the first batches grow them."""
@@ -574,6 +590,16 @@ def format_dist(index: Index, params: Params, res: Results, names, wcount: np.nd
         L.krepp_format_dist(index._h, C.byref(params), C.byref(res), nb.ctypes.data, no.ctypes.data, w, None, 0)
         return ""
     return _format(lambda b, c: L.krepp_format_dist(index._h, C.byref(params), C.byref(res), nb.ctypes.data, no.ctypes.data, None, b, c))
+
+
+def format_seek(seek_dist: np.ndarray, names) -> str:
+    """krepp_format_seek over a caller-owned array of distances (NaN = no match)."""
+    L = load_library()
+    nb, no = pack_names(names)
+    d = np.ascontiguousarray(seek_dist, dtype=np.float64)
+    r = Results()
+    r.n_reads, r.seek_dist = len(d), d.ctypes.data
+    return _format(lambda b, c: L.krepp_format_seek(C.byref(r), nb.ctypes.data, no.ctypes.data, b, c))
 
 
 def format_place(index: Index, params: Params, res: Results, names, tabular: bool = False, wcount: np.ndarray | None = None) -> str:

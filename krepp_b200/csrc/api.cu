@@ -17,6 +17,7 @@
 #include <cstring>
 #include <limits>
 #include <string>
+#include <sys/stat.h>
 #include <vector>
 
 using namespace krepp;
@@ -246,6 +247,7 @@ struct krepp_batch {
   krepp_record_t* d_out_rec = nullptr; krepp_read_summary_t* d_out_read = nullptr;
   krepp_brief_t *d_out_brief = nullptr, *h_brief = nullptr;
   // KREPP_OUT_DIST: printed rows per read, their exclusive prefix, the rows (4 or 8 bytes each; at most one per record)
+  double *d_seek = nullptr, *h_seek = nullptr; // KREPP_OUT_SEEK: one distance per read (sketch handles)
   uint32_t *d_dist_cnt = nullptr, *d_dist_begin = nullptr, *d_dist_out_begin = nullptr, *d_dist_partials = nullptr, *h_dist_begin = nullptr;
   void *d_dist_rows = nullptr, *h_dist_rows = nullptr;
   uint32_t dist_row_bytes = 4;
@@ -293,6 +295,14 @@ int krepp_index_open_lineages(const char* index_dir, int device, uint32_t shard,
 {
   if (!lineage_path) return fail(KREPP_ERR_ARG, "krepp_index_open_lineages: null lineage file");
   return open_index(index_dir, device, shard, nshards, lineage_path, true, out);
+}
+
+int krepp_sketch_open(const char* sketch_path, int device, krepp_index_t** out)
+{
+  if (!sketch_path || !out) return fail(KREPP_ERR_ARG, "krepp_sketch_open: null argument");
+  struct stat st;
+  if (stat(sketch_path, &st) != 0 || !S_ISREG(st.st_mode)) return fail(KREPP_ERR_IO, "Failed to open %s", sketch_path);
+  return open_index(sketch_path, device, 0, 1, nullptr, false, out);
 }
 
 static int open_index(const char* index_dir, int device, uint32_t shard, uint32_t nshards, const char* nwk_path, bool lineages, krepp_index_t** out)
@@ -705,6 +715,8 @@ void krepp_batch_destroy(krepp_batch_t* b)
   free_records(b);
   for (void* p : {(void*)b->d_dist_cnt, (void*)b->d_dist_begin, (void*)b->d_dist_out_begin, (void*)b->d_dist_partials}) if (p) cudaFree(p);
   if (b->h_dist_begin) cudaFreeHost(b->h_dist_begin);
+  if (b->d_seek) cudaFree(b->d_seek);
+  if (b->h_seek) cudaFreeHost(b->h_seek);
   for (void* p : {(void*)b->d_bases, (void*)b->d_offsets, (void*)b->d_onmers, (void*)b->d_wn, (void*)b->d_hdfilt, (void*)b->d_rec_begin,
                   (void*)b->d_rec_count, (void*)b->d_closest, (void*)b->d_nsel, (void*)b->d_memo_key, (void*)b->d_memo_owner, (void*)b->d_counters, (void*)b->d_stats, (void*)b->d_acc, (void*)b->d_bitmap,
                   (void*)b->d_marker, (void*)b->d_stack, (void*)b->d_tagctr, (void*)b->d_out_read, (void*)b->d_tap, (void*)b->d_tap_count, (void*)b->d_place_begin,
@@ -823,6 +835,11 @@ static int enqueue(krepp_batch* b)
       b->launches += 5;
     }
   }
+  const bool want_seek = (b->out_rows & KREPP_OUT_SEEK) != 0;
+  if (want_seek && b->n_reads) {
+    CU(launch_seek(sa, b->tab, b->d_seek, ix->sms, s));
+    ++b->launches;
+  }
   b->clk.tick("finalize_kernel / dist rows", s);
   CU(cudaEventRecord(b->ev1, s)); // kernels only: [ev0, ev1] excludes the host<->device copies on both sides
   CU(cudaMemcpyAsync(b->h_counters, b->d_counters, 32, cudaMemcpyDeviceToHost, s));
@@ -830,6 +847,7 @@ static int enqueue(krepp_batch* b)
   b->summaries_copied = want_sum;
   if (want_sum) CU(cudaMemcpyAsync(b->h_read, b->d_out_read, sizeof(krepp_read_summary_t) * (size_t)b->n_reads, cudaMemcpyDeviceToHost, s));
   if (want_dist && b->n_reads) CU(cudaMemcpyAsync(b->h_dist_begin, b->d_dist_out_begin, 4ull * (b->n_reads + 1ull), cudaMemcpyDeviceToHost, s));
+  if (want_seek && b->n_reads) CU(cudaMemcpyAsync(b->h_seek, b->d_seek, 8ull * b->n_reads, cudaMemcpyDeviceToHost, s));
   return KREPP_OK;
 }
 
@@ -906,7 +924,8 @@ static int host_rows(krepp_batch* b, uint32_t rows)
 
 int krepp_batch_set_output(krepp_batch_t* b, uint32_t rows)
 {
-  if (!b || (rows & ~(uint32_t)(KREPP_OUT_ALL | KREPP_OUT_BRIEF | KREPP_OUT_DIST))) return fail(KREPP_ERR_ARG, "krepp_batch_set_output: bad argument");
+  if (!b || (rows & ~(uint32_t)(KREPP_OUT_ALL | KREPP_OUT_BRIEF | KREPP_OUT_DIST | KREPP_OUT_SEEK))) return fail(KREPP_ERR_ARG, "krepp_batch_set_output: bad argument");
+  if ((rows & KREPP_OUT_SEEK) && !b->ix->host.is_sketch) return fail(KREPP_ERR_ARG, "krepp_batch_set_output: KREPP_OUT_SEEK needs a sketch handle (krepp_sketch_open)");
   if (b->pending) return fail(KREPP_ERR_ARG, "krepp_batch_set_output: a batch is pending on this slot (the rows are assembled by the submit); call it before krepp_batch_submit or after krepp_batch_wait");
   if ((rows & KREPP_OUT_DIST) && b->p.place) return fail(KREPP_ERR_ARG, "krepp_batch_set_output: KREPP_OUT_DIST rows are those of `dist`; this slot runs `place`");
   if (cudaSetDevice(b->device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice failed");
@@ -914,6 +933,7 @@ int krepp_batch_set_output(krepp_batch_t* b, uint32_t rows)
   b->out_rows = rows;
   if ((rows & KREPP_OUT_BRIEF) && !b->d_out_brief) CU(cudaMalloc(&b->d_out_brief, sizeof(krepp_brief_t) * (size_t)b->rec_cap));
   if ((rows & KREPP_OUT_DIST) && !b->d_dist_rows) CU(cudaMalloc(&b->d_dist_rows, (size_t)b->dist_row_bytes * b->rec_cap));
+  if ((rows & KREPP_OUT_SEEK) && !b->d_seek) { CU(cudaMalloc(&b->d_seek, 8ull * (b->max_reads + 1ull))); CU(cudaMallocHost(&b->h_seek, 8ull * (b->max_reads + 1ull))); }
   return KREPP_OK;
 }
 
@@ -1009,6 +1029,7 @@ static int wait_impl(krepp_batch_t* b, krepp_results_t* out, uint32_t rows)
   out->records = (rows & KREPP_OUT_RECORDS) ? b->h_rec : nullptr; out->hist = (rows & KREPP_OUT_HIST) ? b->h_hist : nullptr;
   out->placements = nplace && (rows & KREPP_OUT_PLACEMENTS) ? b->h_place : nullptr;
   out->brief = (rows & KREPP_OUT_BRIEF) ? b->h_brief : nullptr;
+  out->seek_dist = ((rows & KREPP_OUT_SEEK) && (b->out_rows & KREPP_OUT_SEEK)) ? b->h_seek : nullptr;
   out->dist_begin = have_dist ? b->h_dist_begin : nullptr; out->dist_rows = have_dist ? b->h_dist_rows : nullptr;
   out->n_dist_rows = ndist; out->dist_row_bytes = b->dist_row_bytes;
   float mms = 0;

@@ -50,6 +50,7 @@ struct Options {
 const char* kUsage =
   "krepp_b200: B200-native query path of krepp (k-mer-based distance estimation & phylogenetic placement).\n"
   "Usage: krepp_b200 [--num-threads N] [--seed S] [--verbose] {dist|place} -i INDEX_DIR -q QUERY [options]\n"
+  "       krepp_b200 [--num-threads N] seek -i,--sketch-path SKETCH_FILE -q QUERY [-o PATH] [--hdist-th N]\n"
   "  common:  -q,--query PATH   -i,--index-dir DIR   -o,--output-path PATH   --hdist-th N [4]   --chisq X [2.706]\n"
   "           --summarize/--no-summarize [false]\n"
   "  dist:    --dist-max X   --multi/--no-multi [true]   --filter/--no-filter [false]\n"
@@ -82,15 +83,15 @@ Options parse(int argc, char** argv)
   for (size_t i = 0; i < a.size(); ++i) {
     std::string k = a[i];
     if (k.rfind("--", 0) == 0 && k.find('=') != std::string::npos) k = k.substr(0, k.find('='));
-    if (k == "dist" || k == "place") { if (!o.sub.empty()) error_exit("Only one subcommand may be given."); o.sub = k; }
-    else if (k == "index" || k == "inspect" || k == "sketch" || k == "seek") error_exit("Subcommand '" + k + "' is not part of the GPU query path; use the reference krepp binary for it.");
+    if (k == "dist" || k == "place" || k == "seek") { if (!o.sub.empty()) error_exit("Only one subcommand may be given."); o.sub = k; }
+    else if (k == "index" || k == "inspect" || k == "sketch") error_exit("Subcommand '" + k + "' is not part of the GPU query path; use the reference krepp binary for it.");
     else if (k == "--help") { fputs(kUsage, stdout); exit(0); }
     else if (k == "--verbose") o.verbose = true;
     else if (k == "--no-verbose") o.verbose = false;
     else if (k == "--seed") o.seed = (uint32_t)strtoul(need(i, k).c_str(), nullptr, 10);
     else if (k == "--num-threads") o.num_threads = (uint32_t)strtoul(need(i, k).c_str(), nullptr, 10);
     else if (k == "-q" || k == "--query") o.query = need(i, k);
-    else if (k == "-i" || k == "--index-dir") o.index_dir = need(i, k);
+    else if (k == "-i" || k == "--index-dir" || k == "--sketch-path") o.index_dir = need(i, k);
     else if (k == "-o" || k == "--output-path") o.output_path = need(i, k);
     else if (k == "--hdist-th") { const std::string v = need(i, k); if (v.empty() || v[0] == '-') error_exit("--hdist-th: Number less than 0"); o.hdist_th = (uint32_t)strtoul(v.c_str(), nullptr, 10); }
     else if (k == "--chisq") { o.chisq = atof(need(i, k).c_str()); if (!(o.chisq > 0)) error_exit("--chisq: Number less or equal to 0"); }
@@ -116,9 +117,12 @@ Options parse(int argc, char** argv)
   }
   if (o.sub.empty()) { fputs(kUsage, stderr); error_exit("A subcommand is required"); }
   if (o.query.empty()) error_exit("--query is required");
-  if (o.index_dir.empty()) error_exit("--index-dir is required");
+  if (o.index_dir.empty()) error_exit(o.sub == "seek" ? "--sketch-path is required" : "--index-dir is required");
   if (!exists(o.query, false)) error_exit("--query: File does not exist: " + o.query);
-  if (!exists(o.index_dir, true)) error_exit("--index-dir: Directory does not exist: " + o.index_dir);
+  if (o.sub == "seek") { // ref src/krepp.cpp:543-559: -q, -i, -o, --hdist-th and nothing else
+    if (!exists(o.index_dir, false)) error_exit("--sketch-path: File does not exist: " + o.index_dir);
+    if (o.tabular || o.summarize || filter_set || o.shard_index || !o.nwk_path.empty() || !o.lineage_path.empty()) error_exit("The following argument was not expected for seek");
+  } else if (!exists(o.index_dir, true)) error_exit("--index-dir: Directory does not exist: " + o.index_dir);
   if (o.sub == "place" && !filter_set) o.filter = true; // ref src/krepp.cpp:614
   if (o.sub == "dist" && (o.tabular || !o.nwk_path.empty() || !o.lineage_path.empty())) error_exit("The following argument was not expected for dist");
   if (!o.lineage_path.empty() && !exists(o.lineage_path, false)) error_exit("--lineage-file: File does not exist: " + o.lineage_path);
@@ -351,7 +355,7 @@ int main(int argc, char** argv)
   const auto tstart = std::chrono::system_clock::now();
   { std::time_t t = std::chrono::system_clock::to_time_t(tstart); fprintf(stderr, "Invocation: %s\n%s", invocation.c_str(), std::ctime(&t)); }
 
-  const bool place = o.sub == "place";
+  const bool place = o.sub == "place", seek = o.sub == "seek";
   krepp_params_t p;
   krepp_params_default(&p, place ? 1 : 0);
   p.hdist_th = o.hdist_th; p.chisq = o.chisq; p.dist_max = o.dist_max; p.tau = o.tau;
@@ -361,7 +365,7 @@ int main(int argc, char** argv)
     error_exit("Invalid configuration!");
   }
 
-  fprintf(stderr, place ? "Loading the index and the backbone tree...\n" : "Loading the index and initializing...\n");
+  fprintf(stderr, seek ? "Loading the sketch...\n" : place ? "Loading the index and the backbone tree...\n" : "Loading the index and initializing...\n");
   if (o.shard_index) {
     FILE* sout = stdout;
     if (!o.output_path.empty()) { sout = fopen(o.output_path.c_str(), "wb"); if (!sout) error_exit("Failed to open the output file at " + o.output_path); }
@@ -377,7 +381,7 @@ int main(int argc, char** argv)
     std::vector<std::thread> th;
     std::vector<std::string> err(o.devices.size());
     for (size_t g = 0; g < o.devices.size(); ++g)
-      th.emplace_back([&, g] { if (open_for(o, o.devices[g], 0, 1, &index[g]) != KREPP_OK) err[g] = krepp_last_error(); });
+      th.emplace_back([&, g] { if ((seek ? krepp_sketch_open(o.index_dir.c_str(), o.devices[g], &index[g]) : open_for(o, o.devices[g], 0, 1, &index[g])) != KREPP_OK) err[g] = krepp_last_error(); });
     for (auto& t : th) t.join();
     for (auto& e : err) if (!e.empty()) error_exit(e);
   }
@@ -396,7 +400,7 @@ int main(int argc, char** argv)
     s.gpu = (int)(i % o.devices.size());
     check(krepp_batch_create(index[s.gpu], &p, o.batch_reads, o.batch_bases, &s.batch));
     // the writers never read the histograms, and `dist` needs only the rows it prints, which the device selects and rounds
-    check(krepp_batch_set_output(s.batch, place ? (KREPP_OUT_PLACEMENTS | KREPP_OUT_SUMMARIES) : KREPP_OUT_DIST));
+    check(krepp_batch_set_output(s.batch, seek ? KREPP_OUT_SEEK : place ? (KREPP_OUT_PLACEMENTS | KREPP_OUT_SUMMARIES) : KREPP_OUT_DIST));
     check(krepp_batch_host_buffers(s.batch, &s.bases, &s.offsets));
     { // result buffers sized once, before the clock starts: a large-bucket index (many genomes) gives ~19 records, ~56 hit entries
       // and, when placing, ~100 tree nodes per 150 bp read; the buffers still grow if a batch needs more
@@ -416,11 +420,11 @@ int main(int argc, char** argv)
     check(krepp_batch_wait(s.batch, &res));
   }
 
-  fprintf(stderr, place ? (o.lineage_path.empty() ? "Placing given sequences on the backbone tree...\n" : "Placing given sequences on the taxonomic lineage...\n") : "Estimating distances between given sequences and references...\n");
+  fprintf(stderr, seek ? "Seeking query sequences in the sktech...\n" : place ? (o.lineage_path.empty() ? "Placing given sequences on the backbone tree...\n" : "Placing given sequences on the taxonomic lineage...\n") : "Estimating distances between given sequences and references...\n");
   const auto tquery = std::chrono::system_clock::now();
   std::vector<char> text(1 << 20);
   auto emit = [&](size_t n) { if (n && fwrite(text.data(), 1, n, out) != n) error_exit("Failed to write the output"); };
-  { // header / begin_jplace
+  if (!seek) { // header / begin_jplace (`seek` prints rows only: the reference never writes the header it builds, src/krepp.cpp:321-324)
     size_t n = krepp_format_header(index[0], &p, o.tabular, invocation.c_str(), text.data(), text.size());
     if (n > text.size()) { text.resize(n); n = krepp_format_header(index[0], &p, o.tabular, invocation.c_str(), text.data(), text.size()); }
     emit(n);
@@ -480,13 +484,15 @@ int main(int argc, char** argv)
         krepp_results_t sub = res;
         if (res.reads) sub.reads = res.reads + lo;
         if (res.dist_begin) sub.dist_begin = res.dist_begin + lo;
+        if (res.seek_dist) sub.seek_dist = res.seek_dist + lo;
         sub.n_reads = hi - lo;
         double* w = nullptr;
         if (p.summarize) { part_w[t].assign(info.nnodes + 1, 0.0); w = part_w[t].data(); }
         std::vector<char>& buf = ts->part[t];
         for (;;) {
           int prev = 0;
-          const size_t n = place ? krepp_format_place(index[0], &p, &sub, s->names.data(), s->name_off.data() + lo, o.tabular, &prev, w, buf.data(), buf.size())
+          const size_t n = seek ? krepp_format_seek(&sub, s->names.data(), s->name_off.data() + lo, buf.data(), buf.size())
+                           : place ? krepp_format_place(index[0], &p, &sub, s->names.data(), s->name_off.data() + lo, o.tabular, &prev, w, buf.data(), buf.size())
                                  : krepp_format_dist(index[0], &p, &sub, s->names.data(), s->name_off.data() + lo, w, buf.data(), buf.size());
           if (n <= buf.size()) { ts->len[t] = n; break; }
           buf.resize(n + n / 4);
@@ -549,7 +555,7 @@ int main(int argc, char** argv)
   writer.join();
 
   if (direct) fseeko(out, file_off, SEEK_SET); // the batches were written behind stdio's back
-  { // --summarize table / end_jplace
+  if (!seek) { // --summarize table / end_jplace
     size_t n = krepp_format_footer(index[0], &p, o.tabular, wcount.data(), total_queries, invocation.c_str(), text.data(), text.size());
     if (n > text.size()) { text.resize(n); n = krepp_format_footer(index[0], &p, o.tabular, wcount.data(), total_queries, invocation.c_str(), text.data(), text.size()); }
     emit(n);
@@ -557,7 +563,7 @@ int main(int argc, char** argv)
   fflush(out);
   if (out != stdout) fclose(out);
   const std::chrono::duration<float> es = std::chrono::system_clock::now() - tquery;
-  fprintf(stderr, place ? "Done placing queries, elapsed: %g sec\n" : "Done estimating distances, elapsed: %g sec\n", es.count());
+  fprintf(stderr, seek ? "Done seeking sequences, elapsed: %g sec\n" : place ? "Done placing queries, elapsed: %g sec\n" : "Done estimating distances, elapsed: %g sec\n", es.count());
   fprintf(stderr, "Total number of sequences queried: %llu\n", (unsigned long long)total_queries);
   if (o.verbose) fprintf(stderr, "[stages] reader %.3f s, submit %.3f s (producer thread); waiting for the GPU %.3f s, formatting + writing %.3f s (consumer thread)%s\n",
                          t_read, t_submit, t_wait, t_format, direct ? "; output written by the formatter threads (pwrite)" : "");

@@ -729,6 +729,19 @@ extern "C" size_t krepp_format_dist(const krepp_index_t* ix, const krepp_params_
   return format_dist_rows(ix, p, res, res->brief, names, name_offsets, wcount, buf, cap);
 }
 
+extern "C" size_t krepp_format_seek(const krepp_results_t* res, const char* names, const uint64_t* name_offsets, char* buf, size_t cap)
+{ // SBatch::seek_sequences' rows (ref src/seek.cpp:41-49): "<id>\t<distance>" at std::fixed precision 5, "<id>\tNaN" when nothing matched
+  if (!res || !names || !name_offsets || !res->seek_dist) return 0;
+  Out o(buf, cap);
+  for (uint32_t r = 0; r < res->n_reads; ++r) {
+    o.put(name_of(names, name_offsets, r)); o.ch('\t');
+    const double d = res->seek_dist[r];
+    if (d != d) o.put("NaN"); else o.fixed5(d);
+    o.ch('\n');
+  }
+  return o.len;
+}
+
 extern "C" size_t krepp_format_place(const krepp_index_t* ix, const krepp_params_t* p, const krepp_results_t* res, const char* names,
                                      const uint64_t* name_offsets, int tabular, int* has_previous, double* wcount, char* buf, size_t cap)
 {

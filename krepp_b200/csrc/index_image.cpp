@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <dirent.h>
+#include <sys/stat.h>
 #include <fcntl.h>
 #include <thread>
 #include <unistd.h>
@@ -368,7 +369,52 @@ struct Partial {
   std::string newick;
   uint32_t row_base = 0, cshift = 0; // where its rows start in the merged table; what its colour ids above the tree nodes are shifted by
   uint64_t ent_base = 0;             // where its entries start in the merged table
+  bool sketch = false;               // the one "partial" of a sketch file: 4-byte entries at byte 8 of `sfx` (the file's path)
 };
+
+// The sketch of one genome (`krepp sketch`, ref src/sketch.cpp:3-23 Sketch::load_full_sketch; table part SFlatHT::load
+// src/table.cpp:23-33) as a partial library with ONE reference: u64 nkmers, nkmers x u32 enc, u32 nrows, nrows x u64 inc, then the
+// metadata record of an index (k, w, h, m, r, frac, nrows, ppos, npos) and the genome's rho.  The colour of every entry is 1,
+// the only leaf of a one-node tree, so the same match / resolve / solve chain produces the two per-strand histograms of
+// SBatch::search_mers (ref src/seek.cpp:55-120) as its records.
+std::string read_sketch(const std::string& path, Partial& q)
+{
+  q.sfx = path; q.sketch = true;
+  std::ifstream f(path, std::ios::binary);
+  if (!f.is_open()) return "Failed to open " + path;
+  f.read(reinterpret_cast<char*>(&q.nkmers), 8);
+  if (!f.good() || q.nkmers > (1ull << 40)) return "Failed to read the sketch file!";
+  f.seekg((std::streamoff)(8 + 4 * q.nkmers));
+  uint32_t nr = 0;
+  f.read(reinterpret_cast<char*>(&nr), 4);
+  if (!f.good()) return "Failed to read the sketch file!";
+  q.inc.resize(nr);
+  f.read(reinterpret_cast<char*>(q.inc.data()), (std::streamsize)(8ull * nr));
+  unsigned char md[16];
+  f.read(reinterpret_cast<char*>(md), 16);
+  if (!f.good()) return "Failed to read the sketch file!";
+  q.k = md[0]; q.w = md[1]; q.h = md[2];
+  std::memcpy(&q.m, md + 3, 4); std::memcpy(&q.r, md + 7, 4); q.frac = md[11]; std::memcpy(&q.nrows, md + 12, 4);
+  if (q.k == 0 || q.k > 32 || q.h == 0 || q.h >= q.k || q.k - q.h > 16 || q.m == 0) return "Failed to read the sketch file!";
+  q.nrows = nr;
+  q.ppos.resize(q.h); q.npos.resize(q.k - q.h);
+  f.read(reinterpret_cast<char*>(q.ppos.data()), q.h);
+  f.read(reinterpret_cast<char*>(q.npos.data()), q.k - q.h);
+  double rho = 0;
+  f.read(reinterpret_cast<char*>(&rho), 8);
+  if (!f.good()) return "Failed to read the sketch file!";
+  uint64_t prev = 0;
+  for (uint64_t v : q.inc) { if (v < prev || v > q.nkmers) return "Failed to read the sketch file!"; prev = v; }
+  std::string stem = path.substr(path.find_last_of('/') == std::string::npos ? 0 : path.find_last_of('/') + 1);
+  q.newick = "'";
+  for (char c : stem) { if (c == '\'') q.newick += '\''; q.newick += c; }
+  q.newick += "';";
+  q.wbackbone = false;
+  q.cr_nnodes = 2; q.nsubsets = 2;
+  q.pse = {0ull, 1ull << 32}; // a leaf's record is (0, itself) (ref src/record.cpp: leaves)
+  q.rho = {0.0, rho};
+  return "";
+}
 
 std::string read_partial(const std::string& dir, Partial& q)
 {
@@ -446,28 +492,36 @@ std::string HostIndex::load(const std::string& dir, uint32_t shard_id, uint32_t 
 {
   if (!shard_count || shard_id >= shard_count) return "Bad shard arguments for the index!";
   shard = shard_id; nshards = shard_count;
-  // group files by suffix the way TargetIndex::load_index does (ref src/krepp.cpp:72-91)
-  std::vector<std::string> suffixes;
-  DIR* d = opendir(dir.c_str());
-  if (!d) return "Failed to open " + dir;
-  while (dirent* e = readdir(d)) {
-    std::string fn = e->d_name;
-    if (fn.rfind("metadata-", 0) == 0 && fn.find('.') == std::string::npos) suffixes.push_back(fn.substr(8));
-  }
-  closedir(d);
-  if (suffixes.empty()) return "There is no partial index in " + dir;
-  std::sort(suffixes.begin(), suffixes.end());
+  struct stat dst;
+  is_sketch = stat(dir.c_str(), &dst) == 0 && S_ISREG(dst.st_mode);
+  std::vector<Partial> parts;
+  if (is_sketch) {
+    parts.resize(1);
+    if (std::string err = read_sketch(dir, parts[0]); !err.empty()) return err;
+  } else {
+    // group files by suffix the way TargetIndex::load_index does (ref src/krepp.cpp:72-91)
+    std::vector<std::string> suffixes;
+    DIR* d = opendir(dir.c_str());
+    if (!d) return "Failed to open " + dir;
+    while (dirent* e = readdir(d)) {
+      std::string fn = e->d_name;
+      if (fn.rfind("metadata-", 0) == 0 && fn.find('.') == std::string::npos) suffixes.push_back(fn.substr(8));
+    }
+    closedir(d);
+    if (suffixes.empty()) return "There is no partial index in " + dir;
+    std::sort(suffixes.begin(), suffixes.end());
 
-  // ---- every partial library of the directory (ref src/krepp.cpp:92-106).  Several of them -- separate `krepp index` runs over
-  //      disjoint hash residues into one directory -- become ONE image: their tables are laid one after the other (a residue's
-  //      rows start at its partial's row base), colour ids above the tree nodes are shifted per partial so that they stay
-  //      distinct, and the colour records are appended in the same order.  What the reference keeps per partial and the image
-  //      cannot: a rho array of its own -- partials built from the same genomes carry the same whole-genome estimates, and a
-  //      directory whose partials disagree is refused rather than approximated.
-  std::vector<Partial> parts(suffixes.size());
-  for (size_t i = 0; i < parts.size(); ++i) {
-    parts[i].sfx = suffixes[i];
-    if (std::string err = read_partial(dir, parts[i]); !err.empty()) return err;
+    // ---- every partial library of the directory (ref src/krepp.cpp:92-106).  Several of them -- separate `krepp index` runs over
+    //      disjoint hash residues into one directory -- become ONE image: their tables are laid one after the other (a residue's
+    //      rows start at its partial's row base), colour ids above the tree nodes are shifted per partial so that they stay
+    //      distinct, and the colour records are appended in the same order.  What the reference keeps per partial and the image
+    //      cannot: a rho array of its own -- partials built from the same genomes carry the same whole-genome estimates, and a
+    //      directory whose partials disagree is refused rather than approximated.
+    parts.resize(suffixes.size());
+    for (size_t i = 0; i < parts.size(); ++i) {
+      parts[i].sfx = suffixes[i];
+      if (std::string err = read_partial(dir, parts[i]); !err.empty()) return err;
+    }
   }
   const Partial& p0 = parts[0];
   k = p0.k; w = p0.w; h = p0.h; m = p0.m; r = p0.r; frac = p0.frac;
@@ -553,6 +607,21 @@ std::string HostIndex::load(const std::string& dir, uint32_t shard_id, uint32_t 
       if (!with_table) break;
       const uint64_t lo_e = std::max<uint64_t>(ent0, q.ent_base), hi_e = std::min<uint64_t>(ent1, q.ent_base + q.nkmers);
       if (lo_e >= hi_e) continue;
+      if (q.sketch) { // 4-byte entries widened with the colour of the sketch's one reference
+        const int fd = open(q.sfx.c_str(), O_RDONLY);
+        if (fd < 0) return "Failed to open " + q.sfx;
+        std::vector<uint32_t> enc(hi_e - lo_e);
+        size_t done = 0;
+        const size_t bytes = enc.size() * 4;
+        while (done < bytes) {
+          const ssize_t got = pread(fd, reinterpret_cast<char*>(enc.data()) + done, bytes - done, (off_t)(8 + 4 * (lo_e - q.ent_base) + done));
+          if (got <= 0) { close(fd); return "Failed to read the sketch file!"; }
+          done += (size_t)got;
+        }
+        close(fd);
+        for (size_t i = 0; i < enc.size(); ++i) cmer[lo_e - ent0 + i] = (uint64_t)enc[i] | 1ull << 32;
+        continue;
+      }
       const int fd = open((dir + "/cmer" + q.sfx).c_str(), O_RDONLY);
       if (fd < 0) return "Failed to open " + dir + "/cmer" + q.sfx;
       const size_t bytes = (size_t)(hi_e - lo_e) * 8, nth = std::max<size_t>(1, std::min<size_t>(8, bytes >> 24));

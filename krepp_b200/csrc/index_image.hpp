@@ -90,6 +90,7 @@ struct HostIndex {
   static constexpr uint64_t kMaxFlatLeaves = 1ull << 30;
   double mean_bucket = 0, size_biased_bucket = 0;
   HostTree tree;
+  bool is_sketch = false;                     // loaded from the sketch file of one genome (`krepp sketch`): one reference, one leaf; queried by `krepp seek`
   bool wbackbone = true;                      // false: no tree-* file, the tree was generated from reflist-* (dist only; ref src/krepp.cpp:59-63)
   // Bucket-range shard held by this image (SURVEY.md 8e mode B): rows [row0, row1) of the table, entries [ent0, ent0 +
   // cmer.size()) of cmer-*; `inc32` then holds row1 - row0 ends relative to ent0.  One shard = the whole table.

@@ -576,6 +576,54 @@ cudaError_t launch_place(const PlaceArgs& a, const LlhTables& tab, int grid, int
   return cudaGetLastError();
 }
 
+// `krepp seek` (SBatch::seek_sequences ref src/seek.cpp:22-53) on a sketch handle, whose one reference makes a read's records
+// its two per-strand summaries: one thread per read prints the smaller of the two strands' distances.  Both strands are
+// solved as soon as either matched anything (:36-41), so a strand without a record gets the histogram of zeros (every k-mer a
+// mismatch) solved here; NaN when neither strand has a record.
+template <int N>
+__global__ void __launch_bounds__(128) seek_kernel(const SolveArgs a, const LlhTables tab, double* out)
+{
+  __shared__ double su[4];
+  __shared__ DTerms st[4];
+  if (a.counters[2] & kErrRedo) return;
+  if (threadIdx.x < 4) {
+    double u[4];
+    brent_first_points(u);
+    const double ut = threadIdx.x == 0 ? u[0] : threadIdx.x == 1 ? u[1] : threadIdx.x == 2 ? u[2] : u[3];
+    su[threadIdx.x] = ut;
+    st[threadIdx.x] = d_terms(tab, ut, a.k);
+  }
+  __syncthreads();
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < a.n_reads; r += gridDim.x * blockDim.x) {
+    const uint32_t b = a.rec_begin[r], c = a.rec_count[r];
+    double res = nan("");
+    if (c) {
+      double d[2] = {0.0, 0.0};
+      bool have[2] = {false, false};
+      uint32_t se = 1;
+      for (uint32_t j = 0; j < c && j < 2; ++j) { const uint32_t slot = a.rec_slot[b + j], sd = slot >> 31; se = slot & 0x7FFFFFFFu; d[sd] = a.rec_d[b + j]; have[sd] = true; }
+      for (int sd = 0; sd < 2; ++sd) {
+        if (have[sd]) continue;
+        Objective<N> f;
+#pragma unroll
+        for (int x = 0; x < N; ++x) f.mc[x] = 0.0;
+        f.uc = (double)a.onmers[r]; f.rho = a.rho[se]; f.k = a.k; f.th = a.th;
+        double v;
+        brent_minimum(MemoEval<N>{&f, &tab, su, st}, d[sd], v);
+      }
+      res = d[0] < d[1] ? d[0] : d[1];
+    }
+    out[r] = res;
+  }
+}
+
+cudaError_t launch_seek(const SolveArgs& a, const LlhTables& tab, double* out, int sms, cudaStream_t stream)
+{
+  if (a.th + 1 <= 5) seek_kernel<5><<<sms * 8, 128, 0, stream>>>(a, tab, out);
+  else seek_kernel<kMaxTh + 1><<<sms * 8, 128, 0, stream>>>(a, tab, out);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_solve(const SolveArgs& a, const LlhTables& tab, int sms, cudaStream_t stream, StageClock* clk)
 {
   const int grid = sms * 8;

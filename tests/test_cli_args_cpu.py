@@ -39,13 +39,17 @@ def test_argument_errors(args, msg):
 
 
 def test_subcommands_outside_the_query_path_are_refused_by_name():
-    for sub in ("index", "sketch", "seek", "inspect"):
+    for sub in ("index", "sketch", "inspect"):
         r = subprocess.run([CLI, sub, "-i", "x"], capture_output=True, text=True, timeout=60)
         assert r.returncode != 0 and f"Subcommand '{sub}' is not part of the GPU query path" in r.stderr
     r = subprocess.run([CLI, "place", "-i", IDX, "-q", FQ, "-l", os.path.join(S, "no_such_lineages.tsv")], capture_output=True, text=True, timeout=60)
     assert r.returncode != 0 and "--lineage-file: File does not exist" in r.stderr
     r = subprocess.run([CLI, "place", "-i", IDX, "-q", FQ, "-t", os.path.join(S, "no_such_tree.nwk")], capture_output=True, text=True, timeout=60)
     assert r.returncode != 0 and "--nwk-file: File does not exist" in r.stderr
+    r = subprocess.run([CLI, "seek", "-i", IDX, "-q", FQ], capture_output=True, text=True, timeout=60)   # seek takes a sketch FILE
+    assert r.returncode != 0 and "--sketch-path: File does not exist" in r.stderr
+    r = subprocess.run([CLI, "seek", "-q", FQ], capture_output=True, text=True, timeout=60)
+    assert r.returncode != 0 and "--sketch-path is required" in r.stderr
     r = subprocess.run([CLI, "--help"], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0 and "--shard-index" in r.stdout and "--num-gpus" in r.stdout
 

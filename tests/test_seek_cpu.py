@@ -24,3 +24,26 @@ def test_oracle_seek_equals_the_reference(label, genome, args, tmp_path_factory)
         assert sorted(mine) == sorted(ref), (label, th)
         found = sum(1 for x in mine if not x.endswith("NaN"))
         assert found > 10 and found < len(mine), (label, found)
+
+
+def test_sketch_loads_as_a_one_reference_image_and_rows_format(tmp_path_factory):
+    """Host side without a GPU: the sketch file as an index image (geometry, one leaf named after the file, bucket statistics),
+    a truncated file refused, and the row formatter (std::fixed precision 5, NaN for a read without a match)."""
+    import numpy as np
+    import krepp_b200
+    import oracle_lib as O
+    from krepp_b200 import capi
+    label, genome, args = SKETCHES[2]
+    path = build_sketch(label, genome, args, tmp_path_factory.getbasetemp())
+    ix = krepp_b200.Index(path, capi.DEVICE_NONE)
+    assert (ix.info.k, ix.info.w, ix.info.h, ix.info.m, ix.info.r, ix.info.frac) == (21, 21, 7, 3, 1, 1)
+    assert ix.info.nleaves == 1 and ix.info.nnodes == 1 and ix.info.nsubsets == 2 and ix.info.nkmers > 1000
+    assert ix.jplace_tree() == os.path.basename(path) + "{0};" and O.OracleSketch(path).k == 21
+    ix.close()
+    cut = os.path.join(os.path.dirname(path), "cut.skc")
+    with open(path, "rb") as f, open(cut, "wb") as g:
+        g.write(f.read()[:-9])
+    with pytest.raises(capi.KreppError, match="Failed to read the sketch file!"):
+        krepp_b200.Index(cut, capi.DEVICE_NONE)
+    txt = capi.format_seek(np.array([0.015994, float("nan"), 0.5, 1e-10, 0.123455]), ["a", "b", "c d", "e", "f"])
+    assert txt == "a\t0.01599\nb\tNaN\nc d\t0.50000\ne\t0.00000\nf\t" + "%.5f" % 0.123455 + "\n"
