@@ -193,11 +193,14 @@ std::string HostTree::parse_lineages(const std::string& text)
   const double nan = std::numeric_limits<double>::quiet_NaN();
   tmp[0].name = "root"; tmp[0].leaf = false; tmp[0].blen = nan;
   std::unordered_map<std::string, uint32_t> by_name;
-  auto hang = [&](uint32_t child, uint32_t par) { tmp[child].parent_tmp = par; tmp[par].kids.push_back(child); tmp[par].leaf = false; };
+  // Node::add_children (ref src/phytree.hpp:104-113) adds the child's cardinality AS IT IS when the child is hung: a taxon is hung
+  // when it is created, before anything is below it, so a node's card ends up as the number of references directly below it
+  // (plus, for the root, what its late-hung children had gathered) -- `--no-multi` ranks candidates by it (src/query.cpp:311-330)
+  auto hang = [&](uint32_t child, uint32_t par) { tmp[child].parent_tmp = par; tmp[par].kids.push_back(child); tmp[par].leaf = false; tmp[par].card += tmp[child].card; };
   auto node = [&](const std::string& nm, bool leaf, uint32_t par) {
     const uint32_t id = (uint32_t)tmp.size();
     tmp.emplace_back();
-    tmp[id].name = nm; tmp[id].leaf = leaf; tmp[id].blen = nan;
+    tmp[id].name = nm; tmp[id].leaf = leaf; tmp[id].blen = nan; tmp[id].card = leaf ? 1 : 0;
     if (par != 0xffffffffu) hang(id, par);
     by_name.emplace(nm, id);
     return id;
@@ -232,15 +235,13 @@ std::string HostTree::parse_lineages(const std::string& text)
   }
   for (uint32_t id = 1; id < tmp.size(); ++id) if (tmp[id].parent_tmp == 0xffffffffu) hang(id, 0);
   if (tmp.size() == 1) tmp[0].leaf = true;
-  // post-order numbering, children in the order they were hung; cardinalities bottom-up
+  // post-order numbering, children in the order they were hung
   uint32_t next_se = 0;
   std::vector<std::pair<uint32_t, uint32_t>> st{{0u, 0u}};
   while (!st.empty()) {
     const uint32_t id = st.back().first, k = st.back().second;
     if (k < tmp[id].kids.size()) { ++st.back().second; st.push_back({tmp[id].kids[k], 0u}); continue; }
     tmp[id].se = ++next_se;
-    tmp[id].card = tmp[id].leaf ? 1 : 0;
-    for (uint32_t c : tmp[id].kids) tmp[id].card += tmp[c].card;
     st.pop_back();
   }
   adopt(tmp, 0, next_se);
