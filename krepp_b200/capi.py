@@ -210,7 +210,7 @@ class Index:
     def __init__(self, index_dir: str, device: int = 0, shard: int = 0, nshards: int = 1, nwk: str | None = None, lineages: str | None = None):
         """nshards > 1: this handle holds bucket-range shard `shard` of the table only (SURVEY.md 8e mode B).
         nwk: `place -t` -- a Newick file whose tree replaces the index's backbone (krepp_index_open_tree).
-        lineages: `place -l` -- a Greengenes/GTDB style lineage file whose taxonomy does (krepp_index_open_lineages; wins over nwk)."""
+        lineages: `place -l` -- a Greengenes/GTDB style lineage file whose taxonomy does (krepp_index_open_lineages; not together with nwk)."""
         L = load_library()
         self._h = C.c_void_p()
         if os.path.isfile(index_dir):  # the sketch of one genome (`krepp sketch`), queried by `krepp seek`

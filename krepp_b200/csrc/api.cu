@@ -263,6 +263,16 @@ struct krepp_batch {
   uint32_t *d_pn_read = nullptr, *d_pn_se = nullptr, *d_pn_flags = nullptr, *d_pn_work = nullptr, *d_pn_begin = nullptr, *d_pn_count = nullptr;
   double *d_pn_mc = nullptr, *d_pn_uc = nullptr, *d_pn_rho = nullptr, *d_pn_d = nullptr, *d_pn_v = nullptr, *d_pn_chisq = nullptr;
   krepp_placement_t *d_place = nullptr, *h_place = nullptr;
+  // long reads cut into segments (SegArgs, device.cuh): decided per batch by krepp_batch_submit from the host offsets
+  uint32_t seg_windows = 0;   // windows per segment (0: never cut); a read is cut when it has more than twice as many
+  uint32_t cap_vreads = 0;    // most segments a batch can have: max_reads + max_bases / seg_windows + 1
+  uint32_t seg_nv = 0;        // segments of the pending batch, 0 when none of its reads was cut
+  uint64_t* h_voff = nullptr; uint32_t* h_vbegin = nullptr;   // pinned: (begin, end) of every segment; first segment of every read
+  uint64_t* d_voff = nullptr; uint32_t* d_vbegin = nullptr;
+  uint32_t *v_onmers = nullptr, *v_wn = nullptr, *v_hdfilt = nullptr, *v_rec_begin = nullptr, *v_rec_count = nullptr; // per segment
+  uint32_t *v_rec_read = nullptr, *v_rec_slot = nullptr, *v_rec_hist = nullptr; // the segments' records (rec_cap rows)
+  uint32_t *d_vcounters = nullptr, *d_seg_scratch = nullptr, *d_seg_claim = nullptr;
+  int seg_ctas = 0;
   // bucket-sorted pipeline (sorted.cu)
   bool sorted = false, fused_once = false;
   bool bins_off = false;      // a batch overflowed a coarse bin of the two-level lookup sort: this slot keeps to the two-pass sort
@@ -484,6 +494,8 @@ static void free_records(krepp_batch* b)
   for (void* p : {(void*)b->d_rec_alias, (void*)b->d_rec_work, (void*)b->d_rec_read, (void*)b->d_rec_slot, (void*)b->d_rec_hist, (void*)b->d_rec_flags, (void*)b->d_rec_match,
                   (void*)b->d_rec_hdmin, (void*)b->d_rec_d, (void*)b->d_rec_v, (void*)b->d_rec_chisq, (void*)b->d_out_rec})
     if (p) cudaFree(p);
+  for (void* p : {(void*)b->v_rec_read, (void*)b->v_rec_slot, (void*)b->v_rec_hist}) if (p) cudaFree(p);
+  b->v_rec_read = b->v_rec_slot = b->v_rec_hist = nullptr;
   if (b->h_rec) cudaFreeHost(b->h_rec);
   if (b->h_hist) cudaFreeHost(b->h_hist);
   if (b->d_out_brief) cudaFree(b->d_out_brief);
@@ -534,7 +546,56 @@ static int alloc_records(krepp_batch* b, uint32_t cap)
   CU(cudaMalloc(&b->d_out_rec, sizeof(krepp_record_t) * (size_t)cap));
   if (b->out_rows & KREPP_OUT_BRIEF) CU(cudaMalloc(&b->d_out_brief, sizeof(krepp_brief_t) * (size_t)cap));
   if (b->out_rows & KREPP_OUT_DIST) CU(cudaMalloc(&b->d_dist_rows, (size_t)b->dist_row_bytes * cap));
-  (void)stride; // the page-locked host copies are sized when a wait first needs them (host_rows): page-locking is slow and most callers want one form only
+  if (b->d_voff) { CU(cudaMalloc(&b->v_rec_read, 4ull * cap)); CU(cudaMalloc(&b->v_rec_slot, 4ull * cap)); CU(cudaMalloc(&b->v_rec_hist, 4ull * cap * stride)); } // segments' rows
+  // the page-locked host copies are sized when a wait first needs them (host_rows): page-locking is slow and most callers want one form only
+  return KREPP_OK;
+}
+
+// Buffers of the segmented path, allocated by the first batch that holds a long read.
+static int alloc_segments(krepp_batch* b)
+{
+  if (b->d_voff) return KREPP_OK;
+  const HostIndex& h = b->ix->host;
+  const size_t nv = b->cap_vreads, stride = b->p.hdist_th + 1;
+  CU(cudaMallocHost(&b->h_voff, 16ull * nv)); CU(cudaMallocHost(&b->h_vbegin, 4ull * (b->max_reads + 1ull)));
+  CU(cudaMalloc(&b->d_voff, 16ull * nv)); CU(cudaMalloc(&b->d_vbegin, 4ull * (b->max_reads + 1ull)));
+  CU(cudaMalloc(&b->v_onmers, 4ull * nv)); CU(cudaMalloc(&b->v_wn, 8ull * nv)); CU(cudaMalloc(&b->v_hdfilt, 8ull * nv));
+  CU(cudaMalloc(&b->v_rec_begin, 4ull * nv)); CU(cudaMalloc(&b->v_rec_count, 4ull * nv));
+  CU(cudaMalloc(&b->v_rec_read, 4ull * b->rec_cap)); CU(cudaMalloc(&b->v_rec_slot, 4ull * b->rec_cap)); CU(cudaMalloc(&b->v_rec_hist, 4ull * b->rec_cap * stride));
+  CU(cudaMalloc(&b->d_vcounters, 32)); CU(cudaMalloc(&b->d_seg_claim, 4));
+  // one dense table of 2 * nleaves histograms per warp of segment_combine_kernel, at most 256 MB of them
+  const size_t per_warp = 4ull * 2ull * std::max<uint32_t>(h.tree.nleaves, 1) * stride;
+  b->seg_ctas = (int)std::max<size_t>(1, std::min<size_t>((size_t)b->ix->sms * 4, (256ull << 20) / (per_warp * 8)));
+  CU(cudaMalloc(&b->d_seg_scratch, per_warp * 8 * (size_t)b->seg_ctas));
+  CU(cudaMemsetAsync(b->d_seg_scratch, 0, per_warp * 8 * (size_t)b->seg_ctas, b->stream));
+  return KREPP_OK;
+}
+
+// Cuts the batch's long reads into segments (host offsets, already relative to the first base).  Sets seg_nv.
+static int plan_segments(krepp_batch* b, const uint64_t* off, uint32_t n_reads)
+{
+  b->seg_nv = 0;
+  const uint64_t S = b->seg_windows, k = b->ix->host.k;
+  if (!S || b->ix->host.nshards > 1 || b->d_tap) return KREPP_OK; // (the parity tap names lookups by read and position: whole reads only)
+  bool any = false;
+  for (uint32_t r = 0; r < n_reads && !any; ++r) any = off[r + 1] - off[r] >= 2 * S + k;
+  if (!any) return KREPP_OK;
+  if (int rc = alloc_segments(b)) return rc;
+  uint64_t nv = 0;
+  for (uint32_t r = 0; r < n_reads; ++r) {
+    b->h_vbegin[r] = (uint32_t)nv;
+    const uint64_t len = off[r + 1] - off[r], W = len >= k ? len - k + 1 : 0, nseg = W > 2 * S ? (W + S - 1) / S : 1;
+    if (nv + nseg > b->cap_vreads) return fail(KREPP_ERR_CAPACITY, "batch has more read segments than the slot was sized for");
+    for (uint64_t j = 0; j < nseg; ++j) { // windows [j * S, (j + 1) * S) of the read: S + k - 1 bases
+      b->h_voff[2 * nv] = off[r] + j * S;
+      b->h_voff[2 * nv + 1] = j + 1 < nseg ? off[r] + (j + 1) * S + k - 1 : off[r + 1];
+      ++nv;
+    }
+  }
+  b->h_vbegin[n_reads] = (uint32_t)nv;
+  b->seg_nv = (uint32_t)nv;
+  CU(cudaMemcpyAsync(b->d_voff, b->h_voff, 16ull * nv, cudaMemcpyHostToDevice, b->stream));
+  CU(cudaMemcpyAsync(b->d_vbegin, b->h_vbegin, 4ull * (n_reads + 1ull), cudaMemcpyHostToDevice, b->stream));
   return KREPP_OK;
 }
 
@@ -602,8 +663,8 @@ static int alloc_sorted(krepp_batch* b)
   SortArgs& so = b->so;
   so.nrows = h.nrows;
   CU(cudaMalloc(&so.row_count, 4ull * h.nrows)); CU(cudaMalloc(&so.row_begin, 4ull * (h.nrows + 1))); CU(cudaMalloc(&so.row_cursor, 4ull * h.nrows));
-  CU(cudaMalloc(&so.hit_count, 4ull * b->max_reads)); CU(cudaMalloc(&so.hit_begin, 4ull * (b->max_reads + 1ull))); CU(cudaMalloc(&so.hit_cursor, 4ull * b->max_reads));
-  const uint64_t nmax = std::max<uint64_t>(h.nrows, b->max_reads);
+  CU(cudaMalloc(&so.hit_count, 4ull * b->cap_vreads)); CU(cudaMalloc(&so.hit_begin, 4ull * (b->cap_vreads + 1ull))); CU(cudaMalloc(&so.hit_cursor, 4ull * b->cap_vreads));
+  const uint64_t nmax = std::max<uint64_t>(h.nrows, b->cap_vreads);
   CU(cudaMalloc(&so.partials, 4ull * (nmax / 4096 + 2)));
   CU(cudaMalloc(&so.sc, 32));
   CU(cudaMallocHost(&b->h_sc, 4ull * (16 + 2 * (KREPP_MAX_SHARDS + 1))));
@@ -652,6 +713,14 @@ int krepp_batch_create(krepp_index_t* ix, const krepp_params_t* p, uint32_t max_
   b->ix = ix; b->device = ix->device; b->p = *p; b->max_reads = max_reads; b->max_bases = max_bases;
   const HostIndex& h = ix->host;
   b->dist_row_bytes = h.tree.nleaves <= 65536u ? 4u : 8u;
+  { // long reads are cut into segments of this many k-mer windows (KREPP_SEGMENT_WINDOWS; 0 = never)
+    const char* env = getenv("KREPP_SEGMENT_WINDOWS");
+    b->seg_windows = env ? (uint32_t)std::max(0, atoi(env)) : 1024u;
+    if (b->seg_windows && b->seg_windows < 32) b->seg_windows = 32;
+    const uint64_t nv = (uint64_t)max_reads + (b->seg_windows ? max_bases / b->seg_windows : 0) + 1;
+    if (nv > (1ull << 30)) b->seg_windows = 0;
+    b->cap_vreads = b->seg_windows ? (uint32_t)nv : max_reads;
+  }
   llh_tables(b->tab, h.k, h.h, p->hdist_th); // HDistHistLLH tables (ref src/hdhistllh.hpp:51-69), exact integer arithmetic then converted
   CU(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
   CU(cudaEventCreate(&b->ev0)); CU(cudaEventCreate(&b->ev1)); CU(cudaEventCreate(&b->evm0)); CU(cudaEventCreate(&b->evm1));
@@ -717,6 +786,11 @@ void krepp_batch_destroy(krepp_batch_t* b)
   if (b->h_dist_begin) cudaFreeHost(b->h_dist_begin);
   if (b->d_seek) cudaFree(b->d_seek);
   if (b->h_seek) cudaFreeHost(b->h_seek);
+  for (void* p : {(void*)b->d_voff, (void*)b->d_vbegin, (void*)b->v_onmers, (void*)b->v_wn, (void*)b->v_hdfilt, (void*)b->v_rec_begin, (void*)b->v_rec_count, (void*)b->d_vcounters,
+                  (void*)b->d_seg_scratch, (void*)b->d_seg_claim})
+    if (p) cudaFree(p);
+  if (b->h_voff) cudaFreeHost(b->h_voff);
+  if (b->h_vbegin) cudaFreeHost(b->h_vbegin);
   for (void* p : {(void*)b->d_bases, (void*)b->d_offsets, (void*)b->d_onmers, (void*)b->d_wn, (void*)b->d_hdfilt, (void*)b->d_rec_begin,
                   (void*)b->d_rec_count, (void*)b->d_closest, (void*)b->d_nsel, (void*)b->d_memo_key, (void*)b->d_memo_owner, (void*)b->d_counters, (void*)b->d_stats, (void*)b->d_acc, (void*)b->d_bitmap,
                   (void*)b->d_marker, (void*)b->d_stack, (void*)b->d_tagctr, (void*)b->d_out_read, (void*)b->d_tap, (void*)b->d_tap_count, (void*)b->d_place_begin,
@@ -747,6 +821,11 @@ static MatchArgs match_args(krepp_batch* b)
   m.rec_read = b->d_rec_read; m.rec_slot = b->d_rec_slot; m.rec_hist = b->d_rec_hist; m.rec_cap = b->rec_cap; m.counters = b->d_counters;
   m.acc = b->d_acc; m.bitmap = b->d_bitmap; m.marker = b->d_marker; m.stack = b->d_stack; m.stack_cap = b->stack_cap; m.tagctr = b->d_tagctr; m.stats = b->d_stats;
   m.tap = b->d_tap; m.tap_count = b->d_tap_count; m.tap_cap = b->tap_cap;
+  if (b->seg_nv) { // the match step sees the segments as its reads and writes their rows to the staging arrays (segment_combine_kernel follows)
+    m.offsets = b->d_voff; m.off_pairs = 1; m.n_reads = b->seg_nv; m.keep_all = 1u; // (the gate needs the whole read: segment_combine_kernel applies it)
+    m.onmers = b->v_onmers; m.wn = b->v_wn; m.hdfilt = b->v_hdfilt; m.rec_begin = b->v_rec_begin; m.rec_count = b->v_rec_count;
+    m.rec_read = b->v_rec_read; m.rec_slot = b->v_rec_slot; m.rec_hist = b->v_rec_hist; m.counters = b->d_vcounters;
+  }
   return m;
 }
 
@@ -758,6 +837,7 @@ static int enqueue(krepp_batch* b)
   const HostIndex& h = ix->host;
   cudaStream_t s = b->stream;
   CU(cudaMemsetAsync(b->d_counters, 0, 32, s));
+  if (b->seg_nv) { CU(cudaMemsetAsync(b->d_vcounters, 0, 32, s)); CU(cudaMemsetAsync(b->d_seg_claim, 0, 4, s)); }
   if (b->shard_hits) CU(cudaMemcpyAsync(b->d_stats, b->d_stats + 4, 32, cudaMemcpyDeviceToDevice, s)); // the lookup / join phases' counts
   else CU(cudaMemsetAsync(b->d_stats, 0, 32, s));
   if (b->d_tap_count && !b->shard_hits) CU(cudaMemsetAsync(b->d_tap_count, 0, 8, s));
@@ -783,6 +863,19 @@ static int enqueue(krepp_batch* b)
     CU(launch_match(ix->dev, m, ix->resident_warps, ix->staged, b->d_tap != nullptr, s));
     b->clk.tick("match_kernel", s);
     (void)fused;
+  }
+  if (b->seg_nv) {
+    SegArgs g{};
+    g.n_reads = b->n_reads; g.vbegin = b->d_vbegin;
+    g.v_onmers = b->v_onmers; g.v_wn = b->v_wn; g.v_hdfilt = b->v_hdfilt; g.v_rec_begin = b->v_rec_begin; g.v_rec_count = b->v_rec_count;
+    g.v_rec_slot = b->v_rec_slot; g.v_rec_hist = b->v_rec_hist; g.v_counters = b->d_vcounters;
+    g.onmers = b->d_onmers; g.wn = b->d_wn; g.hdfilt = b->d_hdfilt; g.rec_begin = b->d_rec_begin; g.rec_count = b->d_rec_count;
+    g.rec_read = b->d_rec_read; g.rec_slot = b->d_rec_slot; g.rec_hist = b->d_rec_hist; g.counters = b->d_counters;
+    g.rec_cap = b->rec_cap; g.th = b->p.hdist_th; g.keep_all = b->keep_all ? 1u : 0u; g.nleaves = h.tree.nleaves;
+    g.leaf_rank = ix->dev.leaf_rank; g.leaf_se = ix->dev.leaf_se; g.scratch = b->d_seg_scratch; g.claim = b->d_seg_claim;
+    CU(launch_segment_combine(g, b->seg_ctas, s));
+    b->clk.tick("segment_combine_kernel", s);
+    ++match_launches;
   }
   CU(cudaEventRecord(b->evm1, s));
   SolveArgs sa{};
@@ -882,6 +975,7 @@ int krepp_batch_submit(krepp_batch_t* b, const char* bases, const uint64_t* offs
   }
   b->n_reads = n_reads; b->n_bases = nb; b->device_input = false; b->fused_once = false; b->shard_hits = nullptr;
   b->in_bases = b->d_bases; b->in_offsets = b->d_offsets;
+  if (int rc = plan_segments(b, b->h_offsets, n_reads)) return rc;
   CU(cudaMemcpyAsync(b->d_bases, src, nb, cudaMemcpyHostToDevice, b->stream));
   CU(cudaMemcpyAsync(b->d_offsets, b->h_offsets, 8ull * (n_reads + 1), cudaMemcpyHostToDevice, b->stream));
   CU(cudaEventRecord(b->ev0, b->stream));
@@ -900,6 +994,7 @@ int krepp_batch_submit_device(krepp_batch_t* b, const char* d_bases, const uint6
   CU(cudaStreamSynchronize(b->stream));
   b->n_reads = n_reads; b->n_bases = n_bases; b->device_input = true; b->fused_once = false; b->shard_hits = nullptr;
   b->in_bases = d_bases; b->in_offsets = d_offsets;
+  b->seg_nv = 0; // the offsets live on the device: such batches are not cut (their callers cut long sequences themselves)
   CU(cudaEventRecord(b->ev0, b->stream));
   if (int rc = enqueue(b)) return rc;
   b->submitted = true; b->pending = true;
@@ -1052,7 +1147,7 @@ int krepp_shard_lookup(krepp_batch_t* b, const char* d_bases, const uint64_t* d_
   const HostIndex& h = b->ix->host;
   cudaStream_t s = b->stream;
   CU(cudaStreamSynchronize(s));
-  b->n_reads = n_reads; b->n_bases = n_bases; b->device_input = true; b->fused_once = false; b->shard_hits = nullptr; b->submitted = false;
+  b->n_reads = n_reads; b->n_bases = n_bases; b->device_input = true; b->fused_once = false; b->shard_hits = nullptr; b->submitted = false; b->seg_nv = 0;
   b->in_bases = d_bases; b->in_offsets = d_offsets;
   CU(cudaMemsetAsync(b->d_counters, 0, 32, s));
   CU(cudaMemsetAsync(b->d_stats, 0, 32, s));

@@ -22,6 +22,7 @@
 #include <string>
 #include <atomic>
 #include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <thread>
 #include <unistd.h>
@@ -56,7 +57,7 @@ const char* kUsage =
   "  dist:    --dist-max X   --multi/--no-multi [true]   --filter/--no-filter [false]\n"
   "  place:   --tau N [2]   --multi/--no-multi [true]   --filter/--no-filter [true]   --tabular/--no-tabular [false]\n"
   "           -t,--nwk-file PATH  place on this tree instead of the index's backbone\n"
-  "           -l,--lineage-file PATH  place on the taxonomy of a Greengenes/GTDB style lineage file (wins over -t)\n"
+  "           -l,--lineage-file PATH  place on the taxonomy of a Greengenes/GTDB style lineage file (not together with -t)\n"
   "  GPU:     --num-gpus N [1] | --devices 0,1,..   --batch-reads N [262144]   --batch-bases N [67108864]   --slots N [3]\n"
   "           --shard-index   split the index by LSH bucket range over the devices instead of replicating it (for an index\n"
   "                           larger than one GPU's memory; lookups and hits travel between the GPUs by peer copies)\n";
@@ -125,6 +126,7 @@ Options parse(int argc, char** argv)
   } else if (!exists(o.index_dir, true)) error_exit("--index-dir: Directory does not exist: " + o.index_dir);
   if (o.sub == "place" && !filter_set) o.filter = true; // ref src/krepp.cpp:614
   if (o.sub == "dist" && (o.tabular || !o.nwk_path.empty() || !o.lineage_path.empty())) error_exit("The following argument was not expected for dist");
+  if (!o.lineage_path.empty() && !o.nwk_path.empty()) error_exit("--nwk-file excludes --lineage-file"); // ref src/krepp.cpp:598-603 (CLI11 excludes)
   if (!o.lineage_path.empty() && !exists(o.lineage_path, false)) error_exit("--lineage-file: File does not exist: " + o.lineage_path);
   if (!o.nwk_path.empty() && !exists(o.nwk_path, false)) error_exit("--nwk-file: File does not exist: " + o.nwk_path);
   if (o.devices.empty()) for (int d = 0; d < (num_gpus > 0 ? num_gpus : 1); ++d) o.devices.push_back(d);
@@ -207,7 +209,7 @@ static void grow(int dev, void*& p, uint64_t& cap, uint64_t want_items)
   check(krepp_device_alloc(dev, 16 * cap, &p));
 }
 
-// the index with the tree the command line asks for: -l (lineages) wins over -t, as in the reference (src/krepp.cpp:742-748)
+// the index with the tree the command line asks for: -l (lineages) or -t (ref src/krepp.cpp:742-748)
 static int open_for(const Options& o, int dev, uint32_t shard, uint32_t nshards, krepp_index_t** out)
 {
   if (!o.lineage_path.empty()) return krepp_index_open_lineages(o.index_dir.c_str(), dev, shard, nshards, o.lineage_path.c_str(), out);
@@ -389,7 +391,7 @@ int main(int argc, char** argv)
   check(krepp_index_info(index[0], &info));
 
   FILE* out = stdout;
-  if (!o.output_path.empty()) { out = fopen(o.output_path.c_str(), "wb"); if (!out) error_exit("Failed to open the output file at " + o.output_path); }
+  if (!o.output_path.empty()) { out = fopen(o.output_path.c_str(), "w+b"); if (!out) error_exit("Failed to open the output file at " + o.output_path); } // (readable: the formatters map it)
   std::vector<char> obuf(8 << 20);
   setvbuf(out, obuf.data(), _IOFBF, obuf.size());
 
@@ -449,6 +451,7 @@ int main(int argc, char** argv)
   double t_read = 0, t_wait = 0, t_format = 0, t_submit = 0; // --verbose: seconds the reader / consumer spent in each stage
   auto now = [] { return std::chrono::steady_clock::now(); };
   auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+  std::atomic<bool> use_map{getenv("KREPP_OUT_MMAP") ? atoi(getenv("KREPP_OUT_MMAP")) != 0 : true}; // (direct mode) parts are copied through a mapping of the file
   int wrote_any = 0; // (direct mode) a placement was already written: the next one is preceded by ",\n" (ref src/krepp.cpp:476-481)
 
   std::thread writer([&] {
@@ -476,7 +479,8 @@ int main(int argc, char** argv)
       t_wait += secs(tw0, tw1);
       TextSet* ts = nullptr;
       sets_free.pop(ts);
-      std::atomic<uint32_t> formatted{0};
+      std::atomic<uint32_t> formatted{0}, copied{0};
+      std::atomic<char*> map_ptr{nullptr};
       std::atomic<int> failed{0};
       // split the batch's reads over T workers; every worker formats its range into its own buffer
       auto work = [&](uint32_t t) {
@@ -499,19 +503,46 @@ int main(int argc, char** argv)
           if (w) part_w[t].assign(info.nnodes + 1, 0.0);
         }
         if (!direct || p.summarize) return;
-        // direct mode: wait until every part's length is known, then write this one at its offset
+        // direct mode: wait until every part's length is known, then put this one at its offset.  Buffered writes to one file take
+        // the inode lock one at a time, so the parts are copied through a shared mapping of the batch's byte range instead (the
+        // file is grown first); pwrite remains for outputs that cannot be mapped (a file the shell opened write-only).
         formatted.fetch_add(1, std::memory_order_release);
         while (formatted.load(std::memory_order_acquire) < T) std::this_thread::yield();
-        off_t at = file_off;
+        off_t at = file_off, end = file_off;
         int before = wrote_any;
-        for (uint32_t u = 0; u < t; ++u) if (ts->len[u]) { at += (off_t)ts->len[u] + ((jplace && before) ? 2 : 0); before = 1; }
-        if (!ts->len[t]) return;
-        if (jplace && before) { if (pwrite(fileno(out), ",\n", 2, at) != 2) failed = 1; at += 2; }
-        size_t done = 0;
-        while (done < ts->len[t]) {
-          const ssize_t k = pwrite(fileno(out), buf.data() + done, ts->len[t] - done, at + (off_t)done);
-          if (k <= 0) { failed = 1; break; }
-          done += (size_t)k;
+        for (uint32_t u = 0; u < T; ++u) if (ts->len[u]) { const off_t sep = (jplace && before) ? 2 : 0; if (u < t) at += (off_t)ts->len[u] + sep; end += (off_t)ts->len[u] + sep; before = 1; }
+        before = wrote_any;
+        for (uint32_t u = 0; u < t; ++u) if (ts->len[u]) before = 1;
+        char* map = nullptr;
+        const off_t map_off = file_off & ~(off_t)4095;
+        if (use_map.load(std::memory_order_relaxed) && end > file_off) {
+          if (t == 0) {
+            void* m = MAP_FAILED;
+            if (ftruncate(fileno(out), end) == 0) m = mmap(nullptr, (size_t)(end - map_off), PROT_READ | PROT_WRITE, MAP_SHARED, fileno(out), map_off);
+            if (m == MAP_FAILED) use_map.store(false, std::memory_order_relaxed);
+            map_ptr.store(m == MAP_FAILED ? reinterpret_cast<char*>(1) : static_cast<char*>(m), std::memory_order_release);
+          }
+          while (!(map = map_ptr.load(std::memory_order_acquire))) std::this_thread::yield();
+          if (map == reinterpret_cast<char*>(1)) map = nullptr;
+        }
+        if (ts->len[t]) {
+          if (map) {
+            char* dst = map + (at - map_off);
+            if (jplace && before) { dst[0] = ','; dst[1] = '\n'; dst += 2; }
+            memcpy(dst, buf.data(), ts->len[t]);
+          } else {
+            if (jplace && before) { if (pwrite(fileno(out), ",\n", 2, at) != 2) failed = 1; at += 2; }
+            size_t done = 0;
+            while (done < ts->len[t]) {
+              const ssize_t k = pwrite(fileno(out), buf.data() + done, ts->len[t] - done, at + (off_t)done);
+              if (k <= 0) { failed = 1; break; }
+              done += (size_t)k;
+            }
+          }
+        }
+        if (map) {
+          copied.fetch_add(1, std::memory_order_release);
+          if (t == 0) { while (copied.load(std::memory_order_acquire) < T) std::this_thread::yield(); munmap(map, (size_t)(end - map_off)); }
         }
       };
       if (T == 1) work(0);

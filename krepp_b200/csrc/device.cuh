@@ -45,9 +45,10 @@ struct DevIndex {
 // Per-slot buffers for one batch.
 struct MatchArgs {
   const char* bases;          // concatenated ASCII reads
-  const uint64_t* offsets;    // n_reads + 1
+  const uint64_t* offsets;    // n_reads + 1; with off_pairs 2 * n_reads: read i spans [offsets[2i], offsets[2i + 1]) (segments of long reads overlap)
   uint64_t n_bases;           // bytes readable at `bases`
   uint32_t n_reads, th;
+  uint32_t off_pairs;
   uint32_t keep_all;          // 1: emit every (strand, leaf) pair with a hit (parity tap 2); 0: only those passing the hdist_filt gate
   // per-read outputs
   uint32_t* onmers;           // [n]
@@ -73,6 +74,28 @@ struct MatchArgs {
   uint4* tap;
   unsigned long long* tap_count;
   unsigned long long tap_cap;
+};
+
+__device__ __forceinline__ void read_span(const MatchArgs& a, uint32_t read, uint64_t& off, uint64_t& len)
+{
+  if (a.off_pairs) { off = a.offsets[2ull * read]; len = a.offsets[2ull * read + 1] - off; }
+  else { off = a.offsets[read]; len = a.offsets[read + 1] - off; }
+}
+
+// Long reads (contigs, long-read sequencing) are cut into segments of seg_windows k-mer windows, overlapping by k - 1 bases so
+// that every window belongs to exactly one segment; the segments go through the match step as reads of their own and
+// segment_combine_kernel (solve.cu) adds their per-(strand, reference) histograms up again -- a lookup is counted once, at its
+// own smallest distance, so the sums are the histograms of the whole read -- before anything is gated or solved.
+struct SegArgs {
+  uint32_t n_reads;
+  const uint32_t* vbegin;       // [n_reads + 1] first segment of every read
+  const uint32_t *v_onmers, *v_wn, *v_hdfilt, *v_rec_begin, *v_rec_count, *v_rec_slot, *v_rec_hist, *v_counters; // what the match step wrote per segment
+  uint32_t *onmers, *wn, *hdfilt, *rec_begin, *rec_count, *rec_read, *rec_slot, *rec_hist, *counters;            // the read's own
+  uint32_t rec_cap, th, keep_all, nleaves;
+  const uint32_t* leaf_rank;    // se -> rank among the leaves
+  const uint32_t* leaf_se;      // rank -> se
+  uint32_t* scratch;            // [warps][2 * nleaves * (th + 1)], zero between reads
+  uint32_t* claim;              // next read to claim
 };
 
 // Bucket-sorted pipeline (sorted.cu): per-slot buffers between its kernels.

@@ -463,8 +463,8 @@ __global__ void __launch_bounds__(warps_per_cta(STAGED) * 32, STAGED ? 1 : 4) ma
       if (claim >= a.n_reads) break;
     }
     const uint32_t read = claim++;
-    const uint64_t off = a.offsets[read];
-    const uint64_t len = a.offsets[read + 1] - off;
+    uint64_t off, len;
+    read_span(a, read, off, len);
     uint32_t onmers = 0, wn0 = 0, wn1 = 0, filt0 = 0xFFFFFFFFu, filt1 = 0xFFFFFFFFu;
     st_bytes += (lane == 0) ? len : 0;
 

@@ -576,6 +576,134 @@ cudaError_t launch_place(const PlaceArgs& a, const LlhTables& tab, int grid, int
   return cudaGetLastError();
 }
 
+// Segments of long reads back to reads (SegArgs, device.cuh): one warp per read.  A read that was not cut takes its one segment's
+// rows as they are.  A cut read's segments are summed in a dense per-warp table of 2 * nleaves histograms (atomics: two
+// segments' rows may hit one slot in the same step), the read's hdist_filt is the minimum over its segments, and the rows are
+// written in the order the match step itself uses -- forward references by ascending se, then reverse -- under the gate of
+// summarize_matches (ref src/query.cpp:101-106) taken against the READ's hdist_filt.  The match step runs with keep_all on a cut
+// batch: a pair that passes for the read may sit beyond a segment's own gate in that segment (its nearest hit there is farther
+// than the pair's nearest over the read), and its lookups there still count.  The table is zeroed again on the way out.
+__global__ void __launch_bounds__(256) segment_combine_kernel(const SegArgs g)
+{
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, lt_mask = (1u << lane) - 1u, stride = g.th + 1;
+  if (g.v_counters[2] & kErrRedo) { // the match step ran out of room: hand its demand and flags to the host, which grows and reruns
+    if (blockIdx.x == 0 && threadIdx.x == 0) { atomicMax(g.counters, g.v_counters[0]); atomicOr(g.counters + 2, g.v_counters[2]); }
+    return;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && g.v_counters[2]) atomicOr(g.counters + 2, g.v_counters[2]);
+  uint32_t* acc = g.scratch + (size_t)(blockIdx.x * (blockDim.x >> 5) + warp) * 2u * g.nleaves * stride;
+  const uint32_t nslots = 2u * g.nleaves;
+  for (;;) {
+    uint32_t r = 0;
+    if (lane == 0) r = atomicAdd(g.claim, 1u);
+    r = __shfl_sync(0xFFFFFFFFu, r, 0);
+    if (r >= g.n_reads) break;
+    const uint32_t v0 = g.vbegin[r], v1 = g.vbegin[r + 1];
+    if (v1 - v0 == 1) { // not cut: its rows as they are, minus those the gate drops (the match step kept all of them, see below)
+      const uint32_t cnt = g.v_rec_count[v0], vb = g.v_rec_begin[v0];
+      const uint32_t f0 = g.v_hdfilt[2 * v0], f1 = g.v_hdfilt[2 * v0 + 1], g0 = 2u * f0 + 1u, g1 = 2u * f1 + 1u;
+      auto passes = [&](uint32_t i) {
+        if (g.keep_all) return true;
+        uint32_t hdmin = 0xFFFFFFFFu;
+        for (uint32_t x = 0; x < stride; ++x) if (g.v_rec_hist[(size_t)(vb + i) * stride + x] && hdmin == 0xFFFFFFFFu) hdmin = x;
+        return !(hdmin > ((g.v_rec_slot[vb + i] >> 31) ? g1 : g0));
+      };
+      uint32_t total = 0;
+      for (uint32_t c = 0; c < cnt; c += 32) total += __popc(__ballot_sync(0xFFFFFFFFu, c + lane < cnt && passes(c + lane)));
+      uint32_t rb = 0;
+      if (lane == 0 && total) rb = atomicAdd(g.counters, total);
+      rb = __shfl_sync(0xFFFFFFFFu, rb, 0);
+      const bool fits = (uint64_t)rb + total <= g.rec_cap;
+      if (lane == 0) {
+        if (!fits) atomicOr(g.counters + 2, kErrRecOverflow);
+        g.onmers[r] = g.v_onmers[v0]; g.wn[2 * r] = g.v_wn[2 * v0]; g.wn[2 * r + 1] = g.v_wn[2 * v0 + 1];
+        g.hdfilt[2 * r] = f0; g.hdfilt[2 * r + 1] = f1;
+        g.rec_begin[r] = fits ? rb : 0; g.rec_count[r] = fits ? total : 0;
+      }
+      uint32_t done = 0;
+      for (uint32_t c = 0; c < cnt && fits; c += 32) {
+        const uint32_t i = c + lane;
+        const bool pass = i < cnt && passes(i);
+        const uint32_t pm = __ballot_sync(0xFFFFFFFFu, pass);
+        if (pass) {
+          const uint32_t at = rb + done + __popc(pm & lt_mask);
+          g.rec_read[at] = r; g.rec_slot[at] = g.v_rec_slot[vb + i];
+          for (uint32_t x = 0; x < stride; ++x) g.rec_hist[(size_t)at * stride + x] = g.v_rec_hist[(size_t)(vb + i) * stride + x];
+        }
+        done += __popc(pm);
+      }
+      continue;
+    }
+    uint32_t onm = 0, w0 = 0, w1 = 0, f0 = 0xFFFFFFFFu, f1 = 0xFFFFFFFFu;
+    for (uint32_t v = v0 + lane; v < v1; v += 32) {
+      onm += g.v_onmers[v]; w0 += g.v_wn[2 * v]; w1 += g.v_wn[2 * v + 1];
+      f0 = min(f0, g.v_hdfilt[2 * v]); f1 = min(f1, g.v_hdfilt[2 * v + 1]);
+    }
+    for (int o = 16; o; o >>= 1) {
+      onm += __shfl_xor_sync(0xFFFFFFFFu, onm, o); w0 += __shfl_xor_sync(0xFFFFFFFFu, w0, o); w1 += __shfl_xor_sync(0xFFFFFFFFu, w1, o);
+      f0 = min(f0, __shfl_xor_sync(0xFFFFFFFFu, f0, o)); f1 = min(f1, __shfl_xor_sync(0xFFFFFFFFu, f1, o));
+    }
+    const uint32_t g0 = 2u * f0 + 1u, g1 = 2u * f1 + 1u; // uint32 wrap kept, as in the reference
+    for (uint32_t v = v0; v < v1; ++v) {
+      const uint32_t cnt = g.v_rec_count[v], vb = g.v_rec_begin[v];
+      for (uint32_t i = lane; i < cnt; i += 32) {
+        const uint32_t slot = g.v_rec_slot[vb + i];
+        uint32_t* dst = acc + ((size_t)(slot >> 31) * g.nleaves + g.leaf_rank[slot & 0x7FFFFFFFu]) * stride;
+        for (uint32_t x = 0; x < stride; ++x) { const uint32_t c = g.v_rec_hist[(size_t)(vb + i) * stride + x]; if (c) atomicAdd(dst + x, c); }
+      }
+    }
+    __syncwarp();
+    uint32_t total = 0;
+    for (uint32_t c = 0; c < nslots; c += 32) {
+      const uint32_t j = c + lane;
+      bool pass = false;
+      if (j < nslots) {
+        uint32_t hdmin = 0xFFFFFFFFu;
+        for (uint32_t x = 0; x < stride; ++x) if (__ldcg(acc + (size_t)j * stride + x) && hdmin == 0xFFFFFFFFu) hdmin = x;
+        pass = hdmin != 0xFFFFFFFFu && (g.keep_all || !(hdmin > (j >= g.nleaves ? g1 : g0)));
+      }
+      total += __popc(__ballot_sync(0xFFFFFFFFu, pass));
+    }
+    uint32_t rb = 0;
+    if (lane == 0 && total) rb = atomicAdd(g.counters, total);
+    rb = __shfl_sync(0xFFFFFFFFu, rb, 0);
+    const bool fits = (uint64_t)rb + total <= g.rec_cap;
+    uint32_t done = 0;
+    for (uint32_t c = 0; c < nslots; c += 32) {
+      const uint32_t j = c + lane;
+      bool pass = false, any = false;
+      uint32_t hv[kMaxTh + 1];
+      if (j < nslots) {
+        uint32_t hdmin = 0xFFFFFFFFu;
+        for (uint32_t x = 0; x < stride; ++x) { hv[x] = __ldcg(acc + (size_t)j * stride + x); if (hv[x] && hdmin == 0xFFFFFFFFu) hdmin = x; }
+        any = hdmin != 0xFFFFFFFFu;
+        pass = any && (g.keep_all || !(hdmin > (j >= g.nleaves ? g1 : g0)));
+      }
+      const uint32_t pm = __ballot_sync(0xFFFFFFFFu, pass);
+      if (pass && fits) {
+        const uint32_t at = rb + done + __popc(pm & lt_mask);
+        g.rec_read[at] = r;
+        g.rec_slot[at] = (j >= g.nleaves ? 0x80000000u : 0u) | g.leaf_se[j >= g.nleaves ? j - g.nleaves : j];
+        for (uint32_t x = 0; x < stride; ++x) g.rec_hist[(size_t)at * stride + x] = hv[x];
+      }
+      if (any) for (uint32_t x = 0; x < stride; ++x) acc[(size_t)j * stride + x] = 0u;
+      done += __popc(pm);
+    }
+    if (lane == 0) {
+      if (!fits) atomicOr(g.counters + 2, kErrRecOverflow);
+      g.onmers[r] = onm; g.wn[2 * r] = w0; g.wn[2 * r + 1] = w1; g.hdfilt[2 * r] = f0; g.hdfilt[2 * r + 1] = f1;
+      g.rec_begin[r] = fits ? rb : 0; g.rec_count[r] = fits ? total : 0;
+    }
+    __syncwarp();
+  }
+}
+
+cudaError_t launch_segment_combine(const SegArgs& g, int ctas, cudaStream_t stream)
+{
+  segment_combine_kernel<<<ctas, 256, 0, stream>>>(g);
+  return cudaGetLastError();
+}
+
 // `krepp seek` (SBatch::seek_sequences ref src/seek.cpp:22-53) on a sketch handle, whose one reference makes a read's records
 // its two per-strand summaries: one thread per read prints the smaller of the two strands' distances.  Both strands are
 // solved as soon as either matched anything (:36-41), so a strand without a record gets the histogram of zeros (every k-mer a

@@ -27,6 +27,7 @@ cudaError_t launch_shard_lookup(const DevIndex& ix, const MatchArgs& a, const So
 cudaError_t launch_shard_join(const DevIndex& ix, const SortArgs& s, uint32_t th, uint32_t* counters, unsigned long long* stats, int sms, cudaStream_t stream);
 cudaError_t launch_shard_finish(const DevIndex& ix, const MatchArgs& a, const SortArgs& s, int sms, cudaStream_t stream, StageClock* clk = nullptr);
 cudaError_t launch_solve(const SolveArgs& a, const LlhTables& tab, int sms, cudaStream_t stream, StageClock* clk = nullptr);
+cudaError_t launch_segment_combine(const SegArgs& g, int ctas, cudaStream_t stream); // ctas * 8 warps, each with its own slice of g.scratch
 cudaError_t launch_seek(const SolveArgs& a, const LlhTables& tab, double* out, int sms, cudaStream_t stream); // after launch_solve, sketch handles only
 constexpr int kPlaceWarpsPerCta = 4;
 cudaError_t launch_place(const PlaceArgs& a, const LlhTables& tab, int grid, int sms, cudaStream_t stream, StageClock* clk = nullptr);

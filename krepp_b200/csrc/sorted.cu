@@ -72,8 +72,8 @@ __global__ void __launch_bounds__(kLkWarps * 32, 2) lookup_kernel(const DevIndex
       if (claim >= a.n_reads) break;
     }
     const uint32_t read = claim++;
-    const uint64_t off = a.offsets[read];
-    const uint64_t len = a.offsets[read + 1] - off;
+    uint64_t off, len;
+    read_span(a, read, off, len);
     uint32_t onmers = 0, wn0 = 0, wn1 = 0, loc = 0;
     for (uint64_t t0 = 0; t0 + k <= len; t0 += kTileWindows) {
       const uint32_t nl = tile_lookups<TAP && !SCATTER>(ix, a, sm, lut, wide, read, off, len, t0, onmers, wn0, wn1);
@@ -257,8 +257,7 @@ __global__ void __launch_bounds__(kLpWarps * 32, 2) lookup_partition_kernel(cons
         if (claim >= a.n_reads) { exhausted = true; break; }
       }
       read = claim++;
-      off = a.offsets[read];
-      len = a.offsets[read + 1] - off;
+      read_span(a, read, off, len);
       onmers = wn0 = wn1 = loc = 0; t0 = 0;
       if (len >= k) have = true;
       else if (lane == 0) { a.onmers[read] = 0; a.wn[2 * read] = 0; a.wn[2 * read + 1] = 0; st_bytes += len; }

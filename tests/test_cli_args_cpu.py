@@ -20,6 +20,7 @@ CASES = [
     (["place", "-i", IDX, "-q", FQ, "--tau", "9"], "The threshold tau must be less than HD threshold --hdist-th!"),
     (["dist", "-i", IDX, "-q", FQ, "--dist-max", "0.9"], "not in range [1e-08 - 0.33]"),
     (["dist", "-i", IDX, "-q", FQ, "--bogus"], "The following argument was not expected: --bogus"),
+    (["place", "-i", IDX, "-q", FQ, "-t", os.path.join(S, "tree.nwk"), "-l", os.path.join(S, "input_map.tsv")], "--nwk-file excludes --lineage-file"),
 ]
 
 
