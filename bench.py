@@ -461,33 +461,40 @@ def shard_arm(env: Env, wl: Workload, n: int, batch: int, steps: int, warmup: in
     budget = int(whole - table + table / world * 1.03) if world > 1 else whole
     plan = capi.plan_shards(wl.index, budget, local)
     assert plan["nshards"] == world, (plan, world, budget)
-    me = kd.ShardRank(wl.index, local, rank, world, batch, batch * READ_LEN + 64)
+    me = kd.ShardRank(wl.index, local, rank, world, batch, batch * READ_LEN + 64, lanes=2)  # two batches in flight: one's tail under the next one's head
     job = kd.ShardedJob([me])
     h_reads = torch.from_numpy(reads.reshape(-1)).pin_memory()
     d_bases = torch.empty(n * READ_LEN + 64, dtype=torch.uint8, device="cuda")
     d_bases[:n * READ_LEN].copy_(h_reads)
     d_offs = (torch.arange(batch + 1, dtype=torch.int64, device="cuda") * READ_LEN)
-    stage = torch.empty(batch * READ_LEN + 64, dtype=torch.uint8, device="cuda")
+    stage = [torch.empty(batch * READ_LEN + 64, dtype=torch.uint8, device="cuda") for _ in me.lanes]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     chunks = [(i, min(batch, n - i)) for i in range(0, n, batch)]
 
     def step(from_host: bool):
-        nrec = d2h = 0
+        tot = dict(nrec=0, d2h=0)
         alg = dict(bytes=0, lookups=0, entries=0)
-        for first, cnt in chunks:
+
+        def batches():
+            for j, (first, cnt) in enumerate(chunks):
+                if from_host:
+                    src = stage[j % len(stage)]
+                    src[:cnt * READ_LEN].copy_(h_reads[first * READ_LEN:(first + cnt) * READ_LEN], non_blocking=True)
+                else:
+                    src = d_bases[first * READ_LEN:]
+                yield [(src[:cnt * READ_LEN + 64], d_offs, cnt)]
+
+        def consume(i, res, lane):
+            r = res[0]
+            tot["nrec"] += r["n_records"]
             if from_host:
-                stage[:cnt * READ_LEN].copy_(h_reads[first * READ_LEN:(first + cnt) * READ_LEN], non_blocking=True)
-                src = stage
-            else:
-                src = d_bases[first * READ_LEN:]
-            r = job.run([(src[:cnt * READ_LEN + 64], d_offs, cnt)], rows=from_host)[0]
-            nrec += r["n_records"]
-            if from_host:
-                d2h += r["dist_begin"].nbytes + r["dist_rows"].nbytes
-            ab = me.slot.algorithmic_bytes()
+                tot["d2h"] += r["dist_begin"].nbytes + r["dist_rows"].nbytes
+            ab = me.lanes[lane].slot.algorithmic_bytes()
             for k in alg:
                 alg[k] += ab[k]
-        return nrec, d2h, alg
+
+        job.run_stream(batches(), rows=from_host, consume=consume)
+        return tot["nrec"], tot["d2h"], alg
 
     def timed(from_host: bool):
         for _ in range(warmup):
@@ -508,7 +515,8 @@ def shard_arm(env: Env, wl: Workload, n: int, batch: int, steps: int, warmup: in
 
     sampler = ClockSampler(local)
     sampler.start()
-    me.slot.set_output(records=False, hist=False, placements=False, summaries=False, dist=True)  # what the dist front end asks for
+    for ln in me.lanes:
+        ln.slot.set_output(records=False, hist=False, placements=False, summaries=False, dist=True)  # what the dist front end asks for
     t_dev, _, (nrec, _, alg), xbytes = timed(False)
     clocks = sampler.stop()
     stages = dict(me.slot.stage_times())
@@ -565,7 +573,7 @@ def main() -> None:
     ap.add_argument("--no-place", action="store_true", help="leave out the `place` object (configs[3]) of the default line")
     ap.add_argument("--no-mode-b", action="store_true", help="leave out the `mode_b` object (configs[4], N > 1) of the default line")
     ap.add_argument("--place-reads", type=int, default=2_000_000)
-    ap.add_argument("--mode-b-reads", type=int, default=2_000_000)
+    ap.add_argument("--mode-b-reads", type=int, default=4_000_000)
     args = ap.parse_args()
     if args.impl == "reference":
         if args.workload == "c5":
@@ -601,7 +609,7 @@ def main() -> None:
         if args.mode == "dist" and args.workload == "c3" and env.world > 1 and not args.no_mode_b:
             # configs[4] beside the headline: the same table split by bucket range over the ranks under a memory budget it exceeds
             bn = min(args.mode_b_reads, n)
-            mb = shard_arm(env, wl, bn, min(1_000_000, bn), args.steps, args.warmup, not args.no_e2e, t_wl, min(cpu_sample, 50_000))
+            mb = shard_arm(env, wl, bn, min(500_000, bn), args.steps, args.warmup, not args.no_e2e, t_wl, min(cpu_sample, 50_000))
             if out is not None:
                 out["mode_b"] = mb
     if env.rank == 0 and out is not None:

@@ -22,7 +22,6 @@
 #include <string>
 #include <atomic>
 #include <fcntl.h>
-#include <sys/mman.h>
 #include <sys/stat.h>
 #include <thread>
 #include <unistd.h>
@@ -391,7 +390,7 @@ int main(int argc, char** argv)
   check(krepp_index_info(index[0], &info));
 
   FILE* out = stdout;
-  if (!o.output_path.empty()) { out = fopen(o.output_path.c_str(), "w+b"); if (!out) error_exit("Failed to open the output file at " + o.output_path); } // (readable: the formatters map it)
+  if (!o.output_path.empty()) { out = fopen(o.output_path.c_str(), "wb"); if (!out) error_exit("Failed to open the output file at " + o.output_path); }
   std::vector<char> obuf(8 << 20);
   setvbuf(out, obuf.data(), _IOFBF, obuf.size());
 
@@ -447,11 +446,10 @@ int main(int argc, char** argv)
   const bool jplace = place && !o.tabular && !p.summarize;
   bool direct = false;
   off_t file_off = 0;
-  { struct stat st; fflush(out); direct = fstat(fileno(out), &st) == 0 && S_ISREG(st.st_mode) && !(fcntl(fileno(out), F_GETFL) & O_APPEND); if (direct) file_off = lseek(fileno(out), 0, SEEK_CUR); if (file_off < 0) direct = false; }
+  { struct stat st; fflush(out); direct = !(getenv("KREPP_OUT_DIRECT") && !atoi(getenv("KREPP_OUT_DIRECT"))) && fstat(fileno(out), &st) == 0 && S_ISREG(st.st_mode) && !(fcntl(fileno(out), F_GETFL) & O_APPEND); if (direct) file_off = lseek(fileno(out), 0, SEEK_CUR); if (file_off < 0) direct = false; }
   double t_read = 0, t_wait = 0, t_format = 0, t_submit = 0; // --verbose: seconds the reader / consumer spent in each stage
   auto now = [] { return std::chrono::steady_clock::now(); };
   auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
-  std::atomic<bool> use_map{getenv("KREPP_OUT_MMAP") ? atoi(getenv("KREPP_OUT_MMAP")) != 0 : true}; // (direct mode) parts are copied through a mapping of the file
   int wrote_any = 0; // (direct mode) a placement was already written: the next one is preceded by ",\n" (ref src/krepp.cpp:476-481)
 
   std::thread writer([&] {
@@ -479,8 +477,7 @@ int main(int argc, char** argv)
       t_wait += secs(tw0, tw1);
       TextSet* ts = nullptr;
       sets_free.pop(ts);
-      std::atomic<uint32_t> formatted{0}, copied{0};
-      std::atomic<char*> map_ptr{nullptr};
+      std::atomic<uint32_t> formatted{0};
       std::atomic<int> failed{0};
       // split the batch's reads over T workers; every worker formats its range into its own buffer
       auto work = [&](uint32_t t) {
@@ -503,46 +500,19 @@ int main(int argc, char** argv)
           if (w) part_w[t].assign(info.nnodes + 1, 0.0);
         }
         if (!direct || p.summarize) return;
-        // direct mode: wait until every part's length is known, then put this one at its offset.  Buffered writes to one file take
-        // the inode lock one at a time, so the parts are copied through a shared mapping of the batch's byte range instead (the
-        // file is grown first); pwrite remains for outputs that cannot be mapped (a file the shell opened write-only).
+        // direct mode: wait until every part's length is known, then write this one at its offset
         formatted.fetch_add(1, std::memory_order_release);
         while (formatted.load(std::memory_order_acquire) < T) std::this_thread::yield();
-        off_t at = file_off, end = file_off;
+        off_t at = file_off;
         int before = wrote_any;
-        for (uint32_t u = 0; u < T; ++u) if (ts->len[u]) { const off_t sep = (jplace && before) ? 2 : 0; if (u < t) at += (off_t)ts->len[u] + sep; end += (off_t)ts->len[u] + sep; before = 1; }
-        before = wrote_any;
-        for (uint32_t u = 0; u < t; ++u) if (ts->len[u]) before = 1;
-        char* map = nullptr;
-        const off_t map_off = file_off & ~(off_t)4095;
-        if (use_map.load(std::memory_order_relaxed) && end > file_off) {
-          if (t == 0) {
-            void* m = MAP_FAILED;
-            if (ftruncate(fileno(out), end) == 0) m = mmap(nullptr, (size_t)(end - map_off), PROT_READ | PROT_WRITE, MAP_SHARED, fileno(out), map_off);
-            if (m == MAP_FAILED) use_map.store(false, std::memory_order_relaxed);
-            map_ptr.store(m == MAP_FAILED ? reinterpret_cast<char*>(1) : static_cast<char*>(m), std::memory_order_release);
-          }
-          while (!(map = map_ptr.load(std::memory_order_acquire))) std::this_thread::yield();
-          if (map == reinterpret_cast<char*>(1)) map = nullptr;
-        }
-        if (ts->len[t]) {
-          if (map) {
-            char* dst = map + (at - map_off);
-            if (jplace && before) { dst[0] = ','; dst[1] = '\n'; dst += 2; }
-            memcpy(dst, buf.data(), ts->len[t]);
-          } else {
-            if (jplace && before) { if (pwrite(fileno(out), ",\n", 2, at) != 2) failed = 1; at += 2; }
-            size_t done = 0;
-            while (done < ts->len[t]) {
-              const ssize_t k = pwrite(fileno(out), buf.data() + done, ts->len[t] - done, at + (off_t)done);
-              if (k <= 0) { failed = 1; break; }
-              done += (size_t)k;
-            }
-          }
-        }
-        if (map) {
-          copied.fetch_add(1, std::memory_order_release);
-          if (t == 0) { while (copied.load(std::memory_order_acquire) < T) std::this_thread::yield(); munmap(map, (size_t)(end - map_off)); }
+        for (uint32_t u = 0; u < t; ++u) if (ts->len[u]) { at += (off_t)ts->len[u] + ((jplace && before) ? 2 : 0); before = 1; }
+        if (!ts->len[t]) return;
+        if (jplace && before) { if (pwrite(fileno(out), ",\n", 2, at) != 2) failed = 1; at += 2; }
+        size_t done = 0;
+        while (done < ts->len[t]) {
+          const ssize_t k = pwrite(fileno(out), buf.data() + done, ts->len[t] - done, at + (off_t)done);
+          if (k <= 0) { failed = 1; break; }
+          done += (size_t)k;
         }
       };
       if (T == 1) work(0);

@@ -76,52 +76,65 @@ def exchange_v(send, send_counts, group=None):
     return recv, recv_counts
 
 
-class ShardRank:
-    """One rank of a mode-B job: its shard of the index on its GPU, one batch slot, and the device buffers of the two
-    exchanges.  The three phases below are the library's; `ShardedJob` strings them together with the exchanges."""
+class _Lane:
+    """One batch in flight on a rank: a batch slot (its own CUDA stream and result buffers) and the exchange buffers."""
 
-    def __init__(self, index_dir: str, device: int, rank: int, world: int, max_reads: int, max_bases: int, **batch_kw):
+    def __init__(self, rank: "ShardRank", max_reads: int, max_bases: int, batch_kw: dict):
         import numpy as np
         import torch
-        from .capi import Index, IBatch
+        from .capi import IBatch
+        info = rank.index.info
+        self.slot = IBatch(rank.index, np.zeros((0, 1), np.uint8), capacity=(max_reads, max_bases), **batch_kw)
+        self.row_begin = torch.empty(rank.nrows + 1, dtype=torch.int32, device=rank.dev)
+        # 2 strands x one window per base, of which (r+1)/m are eligible on average
+        frac = (info.r + 1) / info.m if info.frac else 1.0 / info.m
+        self.tuples = torch.empty((int(max_bases * 2 * frac * 1.1) + 4096, TUPLE_WORDS), dtype=torch.int32, device=rank.dev)
+        self.hits = torch.empty((max(96 * max_reads, 65536), TUPLE_WORDS), dtype=torch.int32, device=rank.dev)
+        self.keep = None
+
+
+class ShardRank:
+    """One rank of a mode-B job: its shard of the index on its GPU and `lanes` batches in flight (each a batch slot plus the
+    device buffers of the two exchanges).  The three phases below are the library's; `ShardedJob` strings them together with
+    the exchanges.  With two lanes the tail of batch i (regrouping, resolve, solve: enqueued, not waited for) runs while the
+    host drives batch i + 1 through its lookups and exchanges."""
+
+    def __init__(self, index_dir: str, device: int, rank: int, world: int, max_reads: int, max_bases: int, lanes: int = 1, **batch_kw):
+        import torch
+        from .capi import Index
         self.torch, self.rank, self.world = torch, rank, world
         self.dev = torch.device("cuda", device)
         with torch.cuda.device(self.dev):
             self.index = Index(index_dir, device, shard=rank, nshards=world)
-            self.slot = IBatch(self.index, np.zeros((0, 1), np.uint8), capacity=(max_reads, max_bases), **batch_kw)
             self.nrows = int(self.index.info.nrows)
             self.splits = [int(x) for x in self.index.row_splits]
-            self.row_begin = torch.empty(self.nrows + 1, dtype=torch.int32, device=self.dev)
-            # 2 strands x one window per base, of which (r+1)/m are eligible on average
-            frac = (self.index.info.r + 1) / self.index.info.m if self.index.info.frac else 1.0 / self.index.info.m
-            self.tuples = torch.empty((int(max_bases * 2 * frac * 1.1) + 4096, TUPLE_WORDS), dtype=torch.int32, device=self.dev)
-            self.hits = torch.empty((max(96 * max_reads, 65536), TUPLE_WORDS), dtype=torch.int32, device=self.dev)
-        self._keep = None
+            self.lanes = [_Lane(self, max_reads, max_bases, batch_kw) for _ in range(max(1, lanes))]
+        self.slot = self.lanes[0].slot
 
     # phase 1 (home): reads -> tuples grouped by row; what goes to every owner
-    def lookup(self, d_bases, d_offsets, n_reads: int):
+    def lookup(self, d_bases, d_offsets, n_reads: int, lane: int = 0):
         from .capi import CapacityError
-        torch = self.torch
+        torch, ln = self.torch, self.lanes[lane]
         with torch.cuda.device(self.dev):
             torch.cuda.current_stream().synchronize()  # the reads may still be on their way (torch's stream); the library has its own
             while True:
                 try:
-                    so = self.slot.shard_lookup(d_bases.data_ptr(), d_offsets.data_ptr(), n_reads, d_bases.numel(), self.tuples.data_ptr(),
-                                                self.tuples.shape[0], self.row_begin.data_ptr())
+                    so = ln.slot.shard_lookup(d_bases.data_ptr(), d_offsets.data_ptr(), n_reads, d_bases.numel(), ln.tuples.data_ptr(),
+                                              ln.tuples.shape[0], ln.row_begin.data_ptr())
                     break
                 except CapacityError as e:
-                    self.tuples = torch.empty((e.demand + e.demand // 10 + 4096, TUPLE_WORDS), dtype=torch.int32, device=self.dev)
+                    ln.tuples = torch.empty((e.demand + e.demand // 10 + 4096, TUPLE_WORDS), dtype=torch.int32, device=self.dev)
             counts = [int(so[g + 1] - so[g]) for g in range(self.world)]
             # owner g needs row_begin[splits[g] .. splits[g+1]] inclusive: neighbouring slices share one word, so they are
             # laid out one after the other for the all-to-all
-            rb = torch.cat([self.row_begin[self.splits[g]:self.splits[g + 1] + 1] for g in range(self.world)])
+            rb = torch.cat([ln.row_begin[self.splits[g]:self.splits[g + 1] + 1] for g in range(self.world)])
             rb_counts = [self.splits[g + 1] - self.splits[g] + 1 for g in range(self.world)]
-        return self.tuples, counts, rb, rb_counts
+        return ln.tuples, counts, rb, rb_counts
 
     # phase 2 (owner): every sender's tuples against this shard -> hit entries, sender by sender
-    def join(self, recv_tuples, recv_counts, recv_rb):
+    def join(self, recv_tuples, recv_counts, recv_rb, lane: int = 0):
         from .capi import CapacityError
-        torch = self.torch
+        torch, ln = self.torch, self.lanes[lane]
         nloc = self.splits[self.rank + 1] - self.splits[self.rank] + 1
         tp, rp, at = [], [], 0
         for s in range(self.world):
@@ -132,27 +145,29 @@ class ShardRank:
             torch.cuda.current_stream().synchronize()  # the exchange ran on torch's stream, the library has its own
             while True:
                 try:
-                    ho = self.slot.shard_join(tp, rp, self.hits.data_ptr(), self.hits.shape[0])
+                    ho = ln.slot.shard_join(tp, rp, ln.hits.data_ptr(), ln.hits.shape[0])
                     break
                 except CapacityError as e:
-                    self.hits = torch.empty((e.demand + e.demand // 8 + 4096, TUPLE_WORDS), dtype=torch.int32, device=self.dev)
-        return self.hits, [int(ho[s + 1] - ho[s]) for s in range(self.world)]
+                    ln.hits = torch.empty((e.demand + e.demand // 8 + 4096, TUPLE_WORDS), dtype=torch.int32, device=self.dev)
+        return ln.hits, [int(ho[s + 1] - ho[s]) for s in range(self.world)]
 
     # phase 3 (home): the batch's hit entries from all owners -> records (enqueued; results() waits)
-    def finish(self, recv_hits):
-        self._keep = recv_hits  # must stay alive until the wait
+    def finish(self, recv_hits, lane: int = 0):
+        self.lanes[lane].keep = recv_hits  # must stay alive until the wait
         with self.torch.cuda.device(self.dev):
             self.torch.cuda.current_stream().synchronize()
-            self.slot.shard_finish(recv_hits.data_ptr(), recv_hits.shape[0])
+            self.lanes[lane].slot.shard_finish(recv_hits.data_ptr(), recv_hits.shape[0])
 
-    def results(self, rows: bool = True) -> dict:
+    def results(self, rows: bool = True, lane: int = 0) -> dict:
+        ln = self.lanes[lane]
         with self.torch.cuda.device(self.dev):
-            r = self.slot.wait() if rows else self.slot.wait_device()
-        self._keep = None
+            r = ln.slot.wait() if rows else ln.slot.wait_device()
+        ln.keep = None
         return r
 
     def close(self):
-        self.slot.close()
+        for ln in self.lanes:
+            ln.slot.close()
         self.index.close()
 
 
@@ -188,14 +203,42 @@ class ShardedJob:
             out.append((recv, rc))
         return out
 
+    def start(self, batches, lane: int = 0):
+        """Phases 1-3 of one batch on `lane`, up to the enqueue of its last phase (no wait)."""
+        p1 = [r.lookup(*b, lane=lane) for r, b in zip(self.ranks, batches)]
+        tup = self._exchange([(t, c) for t, c, _, _ in p1])
+        rbs = self._exchange([(rb.view(-1, 1), rc) for _, _, rb, rc in p1])
+        p2 = [r.join(t, c, rb.view(-1), lane=lane) for r, (t, c), (rb, _) in zip(self.ranks, tup, rbs)]
+        back = self._exchange(p2)
+        for r, (h, _) in zip(self.ranks, back):
+            r.finish(h, lane=lane)
+
     def run(self, batches, rows: bool = True):
         """batches[i] = (d_bases uint8 tensor, d_offsets int64 tensor, n_reads) of in-process rank i.  Returns the result
         dicts (krepp_batch_wait; krepp_batch_wait_device when rows is False) in the same order."""
-        p1 = [r.lookup(*b) for r, b in zip(self.ranks, batches)]
-        tup = self._exchange([(t, c) for t, c, _, _ in p1])
-        rbs = self._exchange([(rb.view(-1, 1), rc) for _, _, rb, rc in p1])
-        p2 = [r.join(t, c, rb.view(-1)) for r, (t, c), (rb, _) in zip(self.ranks, tup, rbs)]
-        back = self._exchange(p2)
-        for r, (h, _) in zip(self.ranks, back):
-            r.finish(h)
+        self.start(batches)
         return [r.results(rows) for r in self.ranks]
+
+    def run_stream(self, stream, rows: bool = True, consume=None):
+        """A sequence of batches (each as for run()) through the ranks' lanes: batch i + 1 is started while batch i's last
+        phase still runs, and a batch is waited for only when its lane is needed again.  Every rank of the job must pass the
+        same number of batches (the exchanges are collectives).  consume(i, results, lane) is called for every batch in order,
+        while its result buffers are still valid (they are reused by the batch that takes the lane next); returns the number of batches."""
+        nl = min(len(r.lanes) for r in self.ranks)
+        pending = []  # (batch number, lane)
+        n = 0
+        for batches in stream:
+            lane = n % nl
+            if len(pending) == nl:
+                i, l = pending.pop(0)
+                res = [r.results(rows, lane=l) for r in self.ranks]
+                if consume:
+                    consume(i, res, l)
+            self.start(batches, lane=lane)
+            pending.append((n, lane))
+            n += 1
+        for i, l in pending:
+            res = [r.results(rows, lane=l) for r in self.ranks]
+            if consume:
+                consume(i, res, l)
+        return n

@@ -10,9 +10,9 @@ for mode in dist place; do
     ( TIMEFORMAT="wall %R s"; time krepp_b200/_build/krepp_b200 --verbose --num-threads $T $mode -i $D/index -q $D/reads.fq -o /tmp/gpu_$mode.out ) 2>&1 | grep -E "stages|elapsed|wall" | sed "s/^/$mode run $rep: /"
   done
 done | tee $O/cli_stages.txt
-for v in "KREPP_OUT_MMAP=0 -o /tmp/gpu_dist_pw.out" "KREPP_OUT_MMAP=1 -o /dev/null"; do
+for v in "KREPP_OUT_DIRECT=0 -o /tmp/gpu_dist_pw.out" "KREPP_OUT_DIRECT=1 -o /dev/null"; do
   set -- $v
   ( TIMEFORMAT="wall %R s"; time env $1 krepp_b200/_build/krepp_b200 --verbose --num-threads $T dist -i $D/index -q $D/reads.fq $2 $3 ) 2>&1 | grep -E "stages|elapsed|wall" | sed "s|^|dist ($v): |"
 done | tee -a $O/cli_stages.txt
-cmp /tmp/gpu_dist.out /tmp/gpu_dist_pw.out && echo "mapped output == pwrite output" | tee -a $O/cli_stages.txt
+cmp <(tail -n +2 /tmp/gpu_dist.out) <(tail -n +2 /tmp/gpu_dist_pw.out) && echo "writer-thread output == pwrite output" | tee -a $O/cli_stages.txt
 ( KREPP_READER_DEBUG=1 krepp_b200/_build/krepp_b200 --num-threads $T dist -i $D/index -q $D/reads.fq -o /tmp/gpu_dist.out ) 2>&1 | grep "\[reader\]" | tee -a $O/cli_stages.txt
