@@ -423,7 +423,7 @@ def hot_arm(env: Env, index, wl: Workload, mode: str, n: int, batch: int, steps:
         "metric": METRIC if mode == "dist" else METRIC.replace("dist", "place"), "value": value, "unit": "reads/s", "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": t_dev * 1e3 / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32/f64", "data": "synthetic",
-        "config": {"workload": workload_name, "reads_per_gpu": n, "read_len": READ_LEN, "batch_reads": batch, **wl.info,
+        "config": {"workload": workload_name, "reads_per_gpu": n, "read_len": READ_LEN, "batch_reads": batch, "batches_in_flight": lanes, **wl.info,
                    "l2": "inputs larger than L2 (index image %.2f GB, reads %.2f GB per step) and a 256 MiB memset between steps" % (index.info.device_bytes / 1e9, n * READ_LEN / 1e9),
                    "index": "replicated per GPU", "records_per_step": last["records"], "placements_per_step": last["placements"], "wall_s_device_arm": wall_device,
                    "workload_setup_s": round(t_wl, 1)},
@@ -445,7 +445,7 @@ def hot_arm(env: Env, index, wl: Workload, mode: str, n: int, batch: int, steps:
     return out
 
 
-def shard_arm(env: Env, wl: Workload, n: int, batch: int, steps: int, warmup: int, want_e2e: bool, t_wl: float, cpu_sample: int) -> dict | None:
+def shard_arm(env: Env, wl: Workload, n: int, batch: int, steps: int, warmup: int, want_e2e: bool, t_wl: float, cpu_sample: int, lanes: int = 2) -> dict | None:
     """Mode B (BASELINE configs[4]): the index does not fit the per-GPU memory budget, so every rank holds one
     bucket-range shard of the table and its own reads; a step = every rank's reads through lookup -> all-to-all -> join on the
     owning shard -> all-to-all -> resolve / solve, batch by batch.  The budget is set so that the index needs exactly `world`
@@ -461,7 +461,7 @@ def shard_arm(env: Env, wl: Workload, n: int, batch: int, steps: int, warmup: in
     budget = int(whole - table + table / world * 1.03) if world > 1 else whole
     plan = capi.plan_shards(wl.index, budget, local)
     assert plan["nshards"] == world, (plan, world, budget)
-    me = kd.ShardRank(wl.index, local, rank, world, batch, batch * READ_LEN + 64, lanes=2)  # two batches in flight: one's tail under the next one's head
+    me = kd.ShardRank(wl.index, local, rank, world, batch, batch * READ_LEN + 64, lanes=lanes)  # two batches in flight: one's tail under the next one's head
     job = kd.ShardedJob([me])
     h_reads = torch.from_numpy(reads.reshape(-1)).pin_memory()
     d_bases = torch.empty(n * READ_LEN + 64, dtype=torch.uint8, device="cuda")
@@ -534,7 +534,7 @@ def shard_arm(env: Env, wl: Workload, n: int, batch: int, steps: int, warmup: in
         out = {
             "metric": METRIC, "value": world * n * steps / t_dev, "unit": "reads/s", "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": t_dev * 1e3 / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32/f64", "data": "synthetic",
-            "config": {"workload": WORKLOADS["c5"], "reads_per_gpu": n, "read_len": READ_LEN, "batch_reads": batch, **wl.info,
+            "config": {"workload": WORKLOADS["c5"], "reads_per_gpu": n, "read_len": READ_LEN, "batch_reads": batch, "batches_in_flight": lanes, **wl.info,
                        "budget": f"per-GPU image budget {budget / 1e9:.3f} GB: the whole image is {whole / 1e9:.3f} GB and needs {plan['nshards']} bucket-range shards to fit "
                                  f"(krepp_index_plan_shards); shard image {image / 1e9:.3f} GB",
                        "index": f"sharded by bucket range, {world} shards; rank 0 holds rows [{sh.row0}, {sh.row1}) = {sh.n_entries} of {me.index.info.nkmers} entries",
@@ -574,6 +574,7 @@ def main() -> None:
     ap.add_argument("--no-mode-b", action="store_true", help="leave out the `mode_b` object (configs[4], N > 1) of the default line")
     ap.add_argument("--place-reads", type=int, default=2_000_000)
     ap.add_argument("--mode-b-reads", type=int, default=4_000_000)
+    ap.add_argument("--lanes", type=int, default=2, help="mode B: batches in flight per rank")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.workload == "c5":
@@ -591,7 +592,7 @@ def main() -> None:
     cpu_sample = 0 if args.no_cpu_baseline else (args.cpu_sample or 200_000)
 
     if args.workload == "c5":  # mode B as the main line
-        out = shard_arm(env, wl, n, batch, args.steps, args.warmup, not args.no_e2e, t_wl, cpu_sample)
+        out = shard_arm(env, wl, n, batch, args.steps, args.warmup, not args.no_e2e, t_wl, cpu_sample, args.lanes)
     else:
         index = krepp_b200.Index(wl.index, env.local)
         wname = WORKLOADS[args.workload]
@@ -609,7 +610,7 @@ def main() -> None:
         if args.mode == "dist" and args.workload == "c3" and env.world > 1 and not args.no_mode_b:
             # configs[4] beside the headline: the same table split by bucket range over the ranks under a memory budget it exceeds
             bn = min(args.mode_b_reads, n)
-            mb = shard_arm(env, wl, bn, min(500_000, bn), args.steps, args.warmup, not args.no_e2e, t_wl, min(cpu_sample, 50_000))
+            mb = shard_arm(env, wl, bn, min(1_000_000, bn), args.steps, args.warmup, not args.no_e2e, t_wl, min(cpu_sample, 50_000), args.lanes)
             if out is not None:
                 out["mode_b"] = mb
     if env.rank == 0 and out is not None:

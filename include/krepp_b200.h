@@ -67,6 +67,12 @@ int krepp_index_open_tree(const char* index_dir, int device, uint32_t shard, uin
  * last taxon of their line, there are no branch lengths (pendant and distal lengths print as 0) and nodes with one child are
  * kept but are no placement candidates.  Works on an index without a backbone tree too (the reference skips
  * ensure_backbone with -l). */
+/* The LSH geometry of a library still to be built (BaseLSH set_nrows / set_lshf src/krepp.cpp:3-16, LSHF::get_random_positions
+ * src/lshf.cpp:125-147, validate_configuration src/krepp.hpp:59-85): k, w, h, m, r, frac and the h hash positions the reference
+ * draws from its global std::mt19937 (default-constructed; seed >= 0 is `--seed`, a negative seed means the option was not
+ * given).  The handle serves the index-side calls (krepp_extract_mers, krepp_sketch_write) and krepp_index_info; it has no table
+ * and cannot be queried. */
+int krepp_geometry_open(uint32_t k, uint32_t w, uint32_t h, uint32_t m, uint32_t r, int frac, int64_t seed, int device, krepp_index_t** out);
 /* `krepp seek -i SKETCH` (TargetSketch::load_sketch src/krepp.cpp:31-35, Sketch::load_full_sketch / make_rho_partial
  * src/sketch.cpp:3-32): the sketch file of ONE genome written by `krepp sketch` -- a table of 4-byte residual encodings without
  * colours, its LSH geometry and the genome's rho.  It is held as an index whose tree is a single leaf named after the file, so
@@ -335,6 +341,18 @@ int krepp_device_copy(int dst_device, void* dst, int src_device, const void* src
  * KREPP_ERR_CAPACITY when cap is too small (cap = 0 just counts). */
 int krepp_extract_mers(const krepp_index_t* ix, const char* bases, const uint64_t* offsets, uint32_t n_seqs, uint64_t* keys,
                        uint64_t cap, uint64_t* n_keys);
+
+/* The subsampling rate of a genome as `krepp index` / `krepp sketch` estimate it (RSeq::extract_mers + compute_rho, src/rqseq.cpp:63-64,
+ * 107-108,117,142-143, src/rqseq.hpp:79; hll::HyperLogLog src/hyperloglog.hpp:58-140, 12 bits): per sequence one HyperLogLog over
+ * the hashes of all valid k-mers and one over the window minimizers (registers filled by the minimizer kernel), the estimates
+ * summed over the sequences; rho = *n_minimizers_est / *n_kmers_est. */
+int krepp_sequence_rho(const krepp_index_t* ix, const char* bases, const uint64_t* offsets, uint32_t n_seqs, double* n_kmers_est,
+                       double* n_minimizers_est);
+/* `krepp sketch` (SketchSingle::create_sketch / save_sketch src/krepp.cpp:110-128): the sequences' minimizers through
+ * krepp_extract_mers, the table (SFlatHT::save src/table.cpp:35-41), the configuration (src/krepp.cpp:18-29) and rho, written
+ * to out_path -- the file `krepp seek` / krepp_sketch_open read.  ix: a geometry handle (krepp_geometry_open) on a GPU. */
+int krepp_sketch_write(const krepp_index_t* ix, const char* bases, const uint64_t* offsets, uint32_t n_seqs, const char* out_path,
+                       uint64_t* n_kmers, double* rho);
 
 /* -------------------------------------------------------------------------------------------------- host I/O layer
  * The steps immediately either side of the GPU path.  Pure host code: usable

@@ -166,6 +166,9 @@ def load_library():
     L.krepp_batch_stage_times.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_char_p), C.POINTER(C.c_uint32)]
     L.krepp_index_open_shard.argtypes = [C.c_char_p, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]
     L.krepp_index_open_tree.argtypes = [C.c_char_p, C.c_int, C.c_uint32, C.c_uint32, C.c_char_p, C.POINTER(C.c_void_p)]
+    L.krepp_geometry_open.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_void_p)]
+    L.krepp_sequence_rho.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.krepp_sketch_write.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_char_p, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
     L.krepp_sketch_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
     L.krepp_index_open_lineages.argtypes = [C.c_char_p, C.c_int, C.c_uint32, C.c_uint32, C.c_char_p, C.POINTER(C.c_void_p)]
     L.krepp_index_shard_info.argtypes = [C.c_void_p, C.POINTER(ShardInfo), C.c_void_p, C.c_uint32]

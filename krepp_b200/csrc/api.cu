@@ -307,6 +307,35 @@ int krepp_index_open_lineages(const char* index_dir, int device, uint32_t shard,
   return open_index(index_dir, device, shard, nshards, lineage_path, true, out);
 }
 
+int krepp_geometry_open(uint32_t k, uint32_t w, uint32_t h, uint32_t m, uint32_t r, int frac, int64_t seed, int device, krepp_index_t** out)
+{
+  if (!out) return fail(KREPP_ERR_ARG, "krepp_geometry_open: null argument");
+  *out = nullptr;
+  int ndev = 0;
+  if (device != KREPP_DEVICE_NONE) {
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(KREPP_ERR_CUDA, "no CUDA device is available (the krepp_b200 kernels have no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(KREPP_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
+  }
+  if (k > 32 || h >= k) return fail(KREPP_ERR_ARG, "Invalid configuration!");
+  std::vector<uint8_t> ppos, npos;
+  lsh_positions(k, h, seed >= 0, (uint32_t)seed, ppos, npos);
+  auto* ix = new krepp_index;
+  std::string err = ix->host.set_geometry(k, w, h, m, r, frac != 0, ppos, npos);
+  if (!err.empty()) { delete ix; return fail(KREPP_ERR_ARG, "%s", err.c_str()); }
+  ix->device = device;
+  if (device == KREPP_DEVICE_NONE) { *out = ix; return KREPP_OK; }
+  const HostIndex& hh = ix->host;
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ix->sms, cudaDevAttrMultiProcessorCount, device);
+  DevIndex& d = ix->dev;
+  if (e == cudaSuccess) e = upload(build_lut(hh), &d.lut, ix->allocs, ix->device_bytes);
+  if (e != cudaSuccess) { for (void* p : ix->allocs) cudaFree(p); delete ix; return fail(KREPP_ERR_CUDA, "uploading the hash tables failed: %s", cudaGetErrorString(e)); }
+  d.k = hh.k; d.h = hh.h; d.m = hh.m; d.nrows = hh.nrows;
+  d.m_shift = (hh.m & (hh.m - 1)) == 0 ? (uint32_t)__builtin_ctz(hh.m) : 0xFFFFFFFFu;
+  *out = ix;
+  return KREPP_OK;
+}
+
 int krepp_sketch_open(const char* sketch_path, int device, krepp_index_t** out)
 {
   if (!sketch_path || !out) return fail(KREPP_ERR_ARG, "krepp_sketch_open: null argument");
@@ -706,6 +735,7 @@ int krepp_batch_create(krepp_index_t* ix, const krepp_params_t* p, uint32_t max_
   if (p->hdist_th > (uint32_t)kMaxTh) return fail(KREPP_ERR_ARG, "--hdist-th %u exceeds %d", p->hdist_th, kMaxTh);
   if (p->place && p->hdist_th < p->tau) return fail(KREPP_ERR_ARG, "The threshold tau must be less than HD threshold --hdist-th!");
   if (p->place && !ix->host.wbackbone) return fail(KREPP_ERR_ARG, "Given index lacks a tree and no backbone tree is provided..."); // ref src/krepp.cpp:61-63
+  if (ix->host.is_geometry) return fail(KREPP_ERR_ARG, "this handle carries an LSH geometry only (krepp_geometry_open): there is nothing to query");
   if (ix->device == KREPP_DEVICE_NONE) return fail(KREPP_ERR_CUDA, "this index handle was opened without a device (KREPP_DEVICE_NONE); queries need a GPU");
   if (cudaSetDevice(ix->device) != cudaSuccess) return fail(KREPP_ERR_CUDA, "cudaSetDevice(%d) failed", ix->device);
   auto* b = new krepp_batch;

@@ -11,6 +11,7 @@
 #include <fcntl.h>
 #include <thread>
 #include <unistd.h>
+#include <random>
 #include <unordered_map>
 #include <fstream>
 #include <limits>
@@ -489,6 +490,64 @@ std::string read_partial(const std::string& dir, Partial& q)
 
 } // namespace
 
+std::string HostIndex::set_masks()
+{ // ref src/lshf.cpp:39-52
+  mask_hash_bp = mask_drop_lr = mask_drop_bp = 0;
+  for (uint8_t p : npos) { if (p >= k) return "Failed to read the metadata of a partial skecth!"; mask_drop_lr += 0x0000000100000001ull << p; mask_drop_bp += 3ull << (2 * p); }
+  for (uint32_t i = 0; i < 16 - (k - h); ++i) mask_drop_lr += 1ull << (i + k);
+  for (uint8_t p : ppos) { if (p >= k) return "Failed to read the metadata of a partial skecth!"; mask_hash_bp += 3ull << (2 * p); }
+  if ((mask_hash_bp & mask_drop_bp) || __builtin_popcountll(mask_hash_bp | mask_drop_bp) != 2 * (int)k) return "Failed to read the metadata of a partial skecth!";
+  hash_runs = runs_of(mask_hash_bp);
+  drop_runs = runs_of(mask_drop_bp);
+  return "";
+}
+
+void lsh_positions(uint32_t k, uint32_t h, bool seeded, uint32_t seed, std::vector<uint8_t>& ppos, std::vector<uint8_t>& npos)
+{
+  // ref src/lshf.cpp:125-147 LSHF::get_random_positions over the global std::mt19937 `gen` (src/common.cpp:7: default-constructed,
+  // re-seeded only by --seed, src/krepp.cpp:688-692).  std::uniform_int_distribution<uint8_t>(0, k - 1) over a 32-bit engine is,
+  // in libstdc++ (bits/uniform_int_dist.h, _S_nd), Lemire's multiply-and-reject: the high word of draw * k, redrawn while the low
+  // word falls below 2^32 mod k.
+  std::mt19937 gen;
+  if (seeded) gen.seed(seed);
+  auto draw = [&]() {
+    uint64_t product = (uint64_t)(uint32_t)gen() * k;
+    uint32_t low = (uint32_t)product;
+    if (low < k) { const uint32_t threshold = (0u - k) % k; while (low < threshold) { product = (uint64_t)(uint32_t)gen() * k; low = (uint32_t)product; } }
+    return (uint8_t)(product >> 32);
+  };
+  ppos.clear(); npos.clear();
+  while (ppos.size() < h) { const uint8_t n = draw(); if (!std::count(ppos.begin(), ppos.end(), n)) ppos.push_back(n); }
+  std::sort(ppos.begin(), ppos.end());
+  for (uint32_t i = 0, at = 0; i < k; ++i) { if (at < h && i == ppos[at]) ++at; else npos.push_back((uint8_t)i); }
+  std::sort(ppos.begin(), ppos.end(), std::greater<uint8_t>());
+}
+
+std::string HostIndex::set_geometry(uint32_t k_, uint32_t w_, uint32_t h_, uint32_t m_, uint32_t r_, bool frac_, const std::vector<uint8_t>& ppos_, const std::vector<uint8_t>& npos_)
+{
+  // validate_configuration (ref src/krepp.hpp:59-85), its messages
+  if (w_ < k_) return "The minimum minimizer window size (-w) is k (-k).";
+  if (h_ < 3) return "The minimum number of LSH positions (-h) is 3.";
+  if (h_ > 15) return "The maximum number of LSH positions (-h) is 15.";
+  if (k_ > 31) return "The maximum allowed k-mer length (-k) is 31.";
+  if (k_ < 19) return "The minimum allowed k-mer length (-k) is 19.";
+  if (k_ - h_ > 16) return "For compact k-mer encodings, h must be >= k-16.";
+  if (!m_ || ppos_.size() != h_ || npos_.size() != k_ - h_) return "Invalid configuration!";
+  k = k_; w = w_; h = h_; m = m_; r = r_; frac = frac_ ? 1 : 0; ppos = ppos_; npos = npos_;
+  if (std::string err = set_masks(); !err.empty()) return err;
+  { // BaseLSH::set_nrows (ref src/krepp.cpp:5-16)
+    const uint32_t hash_size = 1u << (2 * h), full_residue = hash_size % m;
+    if (frac) { nrows = (hash_size / m) * (r + 1); nrows = full_residue > r ? nrows + (r + 1) : nrows + full_residue; }
+    else { nrows = hash_size / m; nrows = full_residue > r ? nrows + 1 : nrows; }
+  }
+  res_numer.assign(m, 0); res_base.assign(m, 0);
+  for (uint32_t res = 0; res < m; ++res) if (frac ? res <= r : res == r) res_numer[res] = frac ? (int32_t)(r + 1) : 1;
+  is_geometry = true;
+  nkmers = 0; cr_nnodes = 1; nsubsets = 1;
+  row0 = 0; row1 = 0; shard = 0; nshards = 1;
+  return "";
+}
+
 std::string HostIndex::load(const std::string& dir, uint32_t shard_id, uint32_t shard_count, bool with_table, const std::string& qtree_path, bool lineages)
 {
   if (!shard_count || shard_id >= shard_count) return "Bad shard arguments for the index!";
@@ -536,14 +595,7 @@ std::string HostIndex::load(const std::string& dir, uint32_t shard_id, uint32_t 
     if (std::string err = t2.parse(q.newick); !err.empty()) return err;
     if (t2.nnodes != tree.nnodes || t2.name != tree.name || q.wbackbone != wbackbone) return "Partial indexes are incompatible, not built on the same backbone tree!"; // ref src/phytree.cpp:10-36
   }
-  // masks (ref src/lshf.cpp:39-52)
-  mask_hash_bp = mask_drop_lr = mask_drop_bp = 0;
-  for (uint8_t p : npos) { if (p >= k) return "Failed to read the metadata of a partial skecth!"; mask_drop_lr += 0x0000000100000001ull << p; mask_drop_bp += 3ull << (2 * p); }
-  for (uint32_t i = 0; i < 16 - (k - h); ++i) mask_drop_lr += 1ull << (i + k);
-  for (uint8_t p : ppos) { if (p >= k) return "Failed to read the metadata of a partial skecth!"; mask_hash_bp += 3ull << (2 * p); }
-  if ((mask_hash_bp & mask_drop_bp) || __builtin_popcountll(mask_hash_bp | mask_drop_bp) != 2 * (int)k) return "Failed to read the metadata of a partial skecth!";
-  hash_runs = runs_of(mask_hash_bp);
-  drop_runs = runs_of(mask_drop_bp);
+  if (std::string err = set_masks(); !err.empty()) return err;
   // residues -> numerator and row base (ref src/index.cpp:144-157 r_to_flatht / r_to_numerator, :160-168 bucket_indices)
   res_numer.assign(m, 0);
   res_base.assign(m, 0);

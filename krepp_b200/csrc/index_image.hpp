@@ -65,6 +65,10 @@ struct HostTree {
   std::string jplace_newick() const;                         // ref src/phytree.cpp:47-64
 };
 
+// The h hash positions (descending) and the k - h kept positions (ascending) `krepp index` / `krepp sketch` draw for a new
+// library (ref LSHF::get_random_positions src/lshf.cpp:125-147); seeded = --seed was given.
+void lsh_positions(uint32_t k, uint32_t h, bool seeded, uint32_t seed, std::vector<uint8_t>& ppos, std::vector<uint8_t>& npos);
+
 struct HostIndex {
   uint32_t k = 0, w = 0, h = 0, m = 0, r = 0, frac = 0, nrows = 0;
   uint64_t nkmers = 0;
@@ -90,6 +94,7 @@ struct HostIndex {
   static constexpr uint64_t kMaxFlatLeaves = 1ull << 30;
   double mean_bucket = 0, size_biased_bucket = 0;
   HostTree tree;
+  bool is_geometry = false;                   // LSH geometry only (krepp_geometry_open): what the index-side kernels need, no table and no tree
   bool is_sketch = false;                     // loaded from the sketch file of one genome (`krepp sketch`): one reference, one leaf; queried by `krepp seek`
   bool wbackbone = true;                      // false: no tree-* file, the tree was generated from reflist-* (dist only; ref src/krepp.cpp:59-63)
   // Bucket-range shard held by this image (SURVEY.md 8e mode B): rows [row0, row1) of the table, entries [ent0, ent0 +
@@ -97,6 +102,9 @@ struct HostIndex {
   uint32_t shard = 0, nshards = 1, row0 = 0, row1 = 0;
   uint64_t ent0 = 0;
   std::vector<uint32_t> row_splits;           // [nshards + 1] first row of every shard; equal cmer bytes per shard
+  std::string set_masks();                    // masks and pext plans from k, h, ppos, npos
+  // A handle that carries only the LSH geometry of an index or sketch still to be built (ref BaseLSH src/krepp.hpp:28-98).
+  std::string set_geometry(uint32_t k, uint32_t w, uint32_t h, uint32_t m, uint32_t r, bool frac, const std::vector<uint8_t>& ppos, const std::vector<uint8_t>& npos);
   // Returns "" on success, else an error message (the reference's wording where it has one).
   // with_table = false: everything but the k-mer table itself (cmer stays empty) -- enough to plan a sharding (plan_shards).
   // qtree_path (place -t, ref src/krepp.cpp:48-64 ensure_backbone, src/phytree.cpp:421-448 map_to_qtree): a Newick file whose tree

@@ -46,7 +46,40 @@ struct MzArgs {
   uint64_t n_bases, n_tiles;
   uint32_t n_seqs, k, w, m, r, frac, m_shift;
   unsigned long long* keys; unsigned long long cap; unsigned long long* counters; // [0] next tile, [1] keys appended
+  unsigned char* hll;  // optional [n_seqs][2][4096]: HyperLogLog registers of every sequence's valid k-mers and of its minimizers (rho)
 };
+
+constexpr uint32_t kHllBits = 12, kHllRegs = 1u << kHllBits;
+
+// hll::HyperLogLog::add (ref src/hyperloglog.hpp:103-110) with b = 12 on the low 32 bits of the k-mer's hash: register = top 12
+// bits, rank = leading zeros of the rest (capped at 20) + 1.  The registers are bytes; a byte-wide maximum is a CAS on its word,
+// tried only when the register would grow (after the first few thousand k-mers almost never).
+__host__ __device__ __forceinline__ uint32_t hll_rank(uint32_t hash, uint32_t& index)
+{
+  index = hash >> (32 - kHllBits);
+  const uint32_t x = hash << kHllBits;
+#ifdef __CUDA_ARCH__
+  const uint32_t lz = (uint32_t)__clz((int)x);
+#else
+  const uint32_t lz = x ? (uint32_t)__builtin_clz(x) : 32u; // (the reference's __builtin_clz(0) is undefined; 32 is what lzcnt gives)
+#endif
+  return (lz < 32 - kHllBits ? lz : 32 - kHllBits) + 1;
+}
+
+__device__ __forceinline__ void hll_add(unsigned char* regs, uint32_t hash)
+{
+  uint32_t index;
+  const uint32_t rank = hll_rank(hash, index);
+  if (__ldcg(regs + index) >= rank) return;
+  uint32_t* word = reinterpret_cast<uint32_t*>(regs + (index & ~3u));
+  const uint32_t sh = 8 * (index & 3u);
+  uint32_t old = __ldcg(word);
+  while (((old >> sh) & 0xFFu) < rank) {
+    const uint32_t seen = atomicCAS(word, old, (old & ~(0xFFu << sh)) | rank << sh);
+    if (seen == old) break;
+    old = seen;
+  }
+}
 
 __device__ __forceinline__ unsigned long long xur64(unsigned long long h)
 { // ref src/common.hpp:147-155
@@ -132,6 +165,7 @@ __global__ void __launch_bounds__(kMzWarps * 32) minimizer_kernel(const uint4* _
       }
       vk[j] = __ballot_sync(0xFFFFFFFFu, ok);
       sm.z[p] = z; sm.rq[p] = rq;
+      if (a.hll && ok) hll_add(a.hll + (size_t)lo * 2 * kHllRegs, (uint32_t)z); // c1: every valid k-mer (ref src/rqseq.cpp:107-108); k-mers two tiles share are added twice, which a maximum does not see
     }
     __syncwarp();
     // ---- window ends: the w-k+1 k-mers i .. i + ldiff - 1 of the tile must all be valid (a valid run of >= w bases)
@@ -146,6 +180,7 @@ __global__ void __launch_bounds__(kMzWarps * 32) minimizer_kernel(const uint4* _
         uint32_t at = i;
         for (uint32_t d = 1; d < ldiff; ++d) { const unsigned long long z = sm.z[i + d]; if (z < best) { best = z; at = i + d; } } // equal hashes are equal k-mers
         const uint2 rq = sm.rq[at];
+        if (a.hll) hll_add(a.hll + ((size_t)lo * 2 + 1) * kHllRegs, (uint32_t)best); // c2: every window's minimizer, before the residue test (ref :117)
         uint32_t quo, res;
         if (a.m_shift != 0xFFFFFFFFu) { quo = rq.x >> a.m_shift; res = rq.x & (a.m - 1); } else { quo = rq.x / a.m; res = rq.x - quo * a.m; }
         if (a.frac ? res <= a.r : res == a.r) { // ref src/rqseq.cpp:123-126
@@ -184,7 +219,7 @@ inline uint64_t host_pext(uint64_t x, uint64_t mask) { uint64_t r = 0; int b = 0
 
 // The end-of-sequence emit of ref src/rqseq.cpp:112-116 when the last valid run has k <= l < w bases: the ring holds the last
 // w-k+1 valid k-mers of the sequence (pushed in order, never reset), zero-initialised slots where there were fewer.
-bool end_quirk_key(const HostIndex& h, const char* s, uint64_t len, uint64_t* key)
+bool end_quirk_key(const HostIndex& h, const char* s, uint64_t len, uint64_t* key, bool* kept, uint64_t* zmin)
 {
   const uint32_t k = h.k, w = h.w, ldiff = w - k + 1;
   uint64_t l = 0;
@@ -211,8 +246,10 @@ bool end_quirk_key(const HostIndex& h, const char* s, uint64_t len, uint64_t* ke
   uint64_t best_z = 0, best_x = 0;
   if (ring.size() < ldiff) { have = true; best_z = 0; best_x = 0; } // a zero slot: hash 0 beats everything (or ties with poly-A, the same key)
   for (uint64_t x : ring) { const uint64_t z = host_xur64(x); if (!have || z < best_z) { have = true; best_z = z; best_x = x; } }
+  *zmin = best_z; // the emit happens (and counts towards rho) whether or not the k-mer belongs to this library
   const uint32_t rix = (uint32_t)host_pext(best_x, h.mask_hash_bp), res = rix % h.m;
-  if (!(h.frac ? res <= h.r : res == h.r)) return false;
+  *kept = h.frac ? res <= h.r : res == h.r;
+  if (!*kept) return true;
   const uint32_t row = h.frac ? rix / h.m * (h.r + 1) + res : rix / h.m;
   // bp -> lr (ref src/common.hpp:188-197,223): low 32 = bit 0 of every base, high 32 = bit 1; position 0 = last base
   uint64_t lr = 0;
@@ -223,11 +260,15 @@ bool end_quirk_key(const HostIndex& h, const char* s, uint64_t len, uint64_t* ke
 
 } // namespace
 
-extern "C" int krepp_extract_mers(const krepp_index_t* ix, const char* bases, const uint64_t* offsets, uint32_t n_seqs, uint64_t* keys, uint64_t cap,
-                                  uint64_t* n_keys)
+namespace {
+
+// Shared body of krepp_extract_mers / krepp_sketch_write: the sorted unique keys (row << 32 | encoding) of the sequences, and,
+// when `est` is given, the two HyperLogLog estimates of RSeq::extract_mers summed over the sequences in order (n1: distinct
+// valid k-mers, n2: distinct minimizers; ref src/rqseq.cpp:63-64,107-108,117,142-143), whose ratio is rho (src/rqseq.hpp:79).
+int extract_impl(const krepp_index_t* ix, const char* bases, const uint64_t* offsets, uint32_t n_seqs, uint64_t* keys, uint64_t cap, uint64_t* n_keys,
+                 std::vector<uint64_t>* keys_vec, double* est)
 {
-  if (!ix || !bases || !offsets || !n_keys || (cap && !keys)) return set_error(KREPP_ERR_ARG, "krepp_extract_mers: null argument");
-  if (ix->device == KREPP_DEVICE_NONE) return set_error(KREPP_ERR_CUDA, "krepp_extract_mers needs an index handle opened on a GPU (there is no CPU fallback)");
+  if (ix->device == KREPP_DEVICE_NONE) return set_error(KREPP_ERR_CUDA, "the index-side kernels need a handle opened on a GPU (there is no CPU fallback)");
   const HostIndex& h = ix->host;
   if (h.w < h.k || h.w - h.k + 1 > 32) return set_error(KREPP_ERR_UNSUPPORTED, "window of %u with k = %u: at most 32 k-mers per window are supported", h.w, h.k);
   if (cudaSetDevice(ix->device) != cudaSuccess) return set_error(KREPP_ERR_CUDA, "cudaSetDevice(%d) failed", ix->device);
@@ -235,6 +276,7 @@ extern "C" int krepp_extract_mers(const krepp_index_t* ix, const char* bases, co
   int rc = KREPP_OK;
   const uint64_t nb = n_seqs ? offsets[n_seqs] - offsets[0] : 0;
   std::vector<uint64_t> rel(n_seqs + 1), tile_begin(n_seqs + 1, 0), quirk;
+  std::vector<std::pair<uint32_t, uint64_t>> quirk_z; // (sequence, hash of the end-of-sequence emit)
   uint64_t windows = 0;
   for (uint32_t s = 0; s <= n_seqs; ++s) rel[s] = offsets[s] - offsets[0];
   for (uint32_t s = 0; s < n_seqs; ++s) {
@@ -244,13 +286,15 @@ extern "C" int krepp_extract_mers(const krepp_index_t* ix, const char* bases, co
       const uint64_t nwin = len - h.w + 1;
       tiles = (nwin + adv - 1) / adv;
       windows += nwin;
-      uint64_t key;
-      if (end_quirk_key(h, bases + offsets[s], len, &key)) quirk.push_back(key);
+      uint64_t key = 0, z = 0;
+      bool kept = false;
+      if (end_quirk_key(h, bases + offsets[s], len, &key, &kept, &z)) { quirk_z.emplace_back(s, z); if (kept) quirk.push_back(key); }
     }
     tile_begin[s + 1] = tile_begin[s] + tiles;
   }
   char* d_bases = nullptr; uint64_t *d_off = nullptr, *d_tb = nullptr;
   unsigned long long *d_keys = nullptr, *d_sorted = nullptr, *d_uniq = nullptr, *d_cnt = nullptr, *d_nsel = nullptr;
+  unsigned char* d_hll = nullptr;
   void* d_tmp = nullptr;
   size_t tmp1 = 0, tmp2 = 0;
   unsigned long long h_cnt[2] = {0, 0}, nsel = 0;
@@ -260,13 +304,14 @@ extern "C" int krepp_extract_mers(const krepp_index_t* ix, const char* bases, co
     MZ_CU(cudaMalloc(&d_bases, nb + 64)); MZ_CU(cudaMalloc(&d_off, 8ull * (n_seqs + 1))); MZ_CU(cudaMalloc(&d_tb, 8ull * (n_seqs + 1)));
     MZ_CU(cudaMalloc(&d_keys, 8ull * kcap)); MZ_CU(cudaMalloc(&d_sorted, 8ull * kcap)); MZ_CU(cudaMalloc(&d_uniq, 8ull * kcap));
     MZ_CU(cudaMalloc(&d_cnt, 16)); MZ_CU(cudaMalloc(&d_nsel, 8));
+    if (est) { MZ_CU(cudaMalloc(&d_hll, 2ull * kHllRegs * std::max<uint32_t>(n_seqs, 1))); MZ_CU(cudaMemset(d_hll, 0, 2ull * kHllRegs * std::max<uint32_t>(n_seqs, 1))); }
     MZ_CU(cudaMemcpy(d_bases, bases + offsets[0], nb, cudaMemcpyHostToDevice));
     MZ_CU(cudaMemcpy(d_off, rel.data(), 8ull * (n_seqs + 1), cudaMemcpyHostToDevice));
     MZ_CU(cudaMemcpy(d_tb, tile_begin.data(), 8ull * (n_seqs + 1), cudaMemcpyHostToDevice));
     MZ_CU(cudaMemset(d_cnt, 0, 16));
     a.bases = d_bases; a.offsets = d_off; a.tile_begin = d_tb; a.n_bases = nb; a.n_tiles = tile_begin[n_seqs]; a.n_seqs = n_seqs;
     a.k = h.k; a.w = h.w; a.m = h.m; a.r = h.r; a.frac = h.frac; a.m_shift = ix->dev.m_shift;
-    a.keys = d_keys; a.cap = kcap; a.counters = d_cnt;
+    a.keys = d_keys; a.cap = kcap; a.counters = d_cnt; a.hll = d_hll;
     if (a.n_tiles) {
       const size_t smem = lut_chunks(h.k) * 256 * sizeof(uint4) + kMzWarps * sizeof(MzWarpSmem);
       MZ_CU(cudaFuncSetAttribute(minimizer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -289,11 +334,95 @@ extern "C" int krepp_extract_mers(const krepp_index_t* ix, const char* bases, co
       MZ_CU(cudaMemcpy(&nsel, d_nsel, 8, cudaMemcpyDeviceToHost));
       nsel &= 0xFFFFFFFFull; // DeviceSelect writes an int
     }
+    if (est) { // hll::HyperLogLog::estimate per sequence (ref src/hyperloglog.hpp:117-140), summed in sequence order
+      std::vector<unsigned char> regs(2ull * kHllRegs * std::max<uint32_t>(n_seqs, 1));
+      MZ_CU(cudaMemcpy(regs.data(), d_hll, regs.size(), cudaMemcpyDeviceToHost));
+      for (const auto& qz : quirk_z) { // the end-of-sequence emit is the host's: its minimizer joins c2
+        uint32_t index;
+        const uint32_t rank = hll_rank((uint32_t)qz.second, index);
+        unsigned char& reg = regs[((size_t)qz.first * 2 + 1) * kHllRegs + index];
+        if (rank > reg) reg = (unsigned char)rank;
+      }
+      const double mm = (double)kHllRegs, alpha_mm = (0.7213 / (1.0 + 1.079 / mm)) * mm * mm;
+      est[0] = est[1] = 0.0;
+      for (uint32_t s = 0; s < n_seqs; ++s) {
+        if (rel[s + 1] - rel[s] < h.w) continue; // no extract_mers call for it
+        for (int c = 0; c < 2; ++c) {
+          const unsigned char* M = regs.data() + ((size_t)s * 2 + c) * kHllRegs;
+          double sum = 0.0;
+          for (uint32_t i = 0; i < kHllRegs; ++i) sum += 1.0 / (double)(1 << M[i]);
+          double e = alpha_mm / sum;
+          if (e <= 2.5 * mm) {
+            uint32_t zeros = 0;
+            for (uint32_t i = 0; i < kHllRegs; ++i) zeros += M[i] == 0;
+            if (zeros) e = mm * std::log(mm / (double)zeros);
+          } else if (e > (1.0 / 30.0) * 4294967296.0) e = -4294967296.0 * std::log(1.0 - e / 4294967296.0);
+          est[c] += e;
+        }
+      }
+    }
     *n_keys = nsel;
+    if (keys_vec) { keys_vec->resize(nsel); if (nsel) MZ_CU(cudaMemcpy(keys_vec->data(), d_uniq, 8ull * nsel, cudaMemcpyDeviceToHost)); goto done; }
     if (nsel > cap) { rc = cap ? set_error(KREPP_ERR_CAPACITY, "krepp_extract_mers: %llu keys but room for %llu", (unsigned long long)nsel, (unsigned long long)cap) : KREPP_OK; goto done; }
     if (nsel) MZ_CU(cudaMemcpy(keys, d_uniq, 8ull * nsel, cudaMemcpyDeviceToHost));
   }
 done:
-  for (void* p : {(void*)d_bases, (void*)d_off, (void*)d_tb, (void*)d_keys, (void*)d_sorted, (void*)d_uniq, (void*)d_cnt, (void*)d_nsel, d_tmp}) if (p) cudaFree(p);
+  for (void* p : {(void*)d_bases, (void*)d_off, (void*)d_tb, (void*)d_keys, (void*)d_sorted, (void*)d_uniq, (void*)d_cnt, (void*)d_nsel, (void*)d_hll, d_tmp}) if (p) cudaFree(p);
   return rc;
+}
+
+} // namespace
+
+extern "C" int krepp_extract_mers(const krepp_index_t* ix, const char* bases, const uint64_t* offsets, uint32_t n_seqs, uint64_t* keys, uint64_t cap,
+                                  uint64_t* n_keys)
+{
+  if (!ix || !bases || !offsets || !n_keys || (cap && !keys)) return set_error(KREPP_ERR_ARG, "krepp_extract_mers: null argument");
+  return extract_impl(ix, bases, offsets, n_seqs, keys, cap, n_keys, nullptr, nullptr);
+}
+
+extern "C" int krepp_sequence_rho(const krepp_index_t* ix, const char* bases, const uint64_t* offsets, uint32_t n_seqs, double* n_kmers_est, double* n_minimizers_est)
+{
+  if (!ix || !bases || !offsets || !n_kmers_est || !n_minimizers_est) return set_error(KREPP_ERR_ARG, "krepp_sequence_rho: null argument");
+  double est[2] = {0, 0};
+  uint64_t n = 0;
+  std::vector<uint64_t> keys;
+  if (int rc = extract_impl(ix, bases, offsets, n_seqs, nullptr, 0, &n, &keys, est)) return rc;
+  *n_kmers_est = est[0]; *n_minimizers_est = est[1];
+  return KREPP_OK;
+}
+
+extern "C" int krepp_sketch_write(const krepp_index_t* ix, const char* bases, const uint64_t* offsets, uint32_t n_seqs, const char* out_path, uint64_t* n_kmers,
+                                  double* rho_out)
+{
+  // SketchSingle::create_sketch / save_sketch (ref src/krepp.cpp:110-128): SDynHT::fill_table (extract_mers of every sequence,
+  // sort and unique per row; src/table.cpp:236-246), SFlatHT (src/table.cpp:3-21) and its save (:35-41), save_configuration
+  // (src/krepp.cpp:18-29), then rho = n2 / n1
+  if (!ix || !bases || !offsets || !out_path) return set_error(KREPP_ERR_ARG, "krepp_sketch_write: null argument");
+  const HostIndex& h = ix->host;
+  double est[2] = {0, 0};
+  uint64_t n = 0;
+  std::vector<uint64_t> keys;
+  if (int rc = extract_impl(ix, bases, offsets, n_seqs, nullptr, 0, &n, &keys, est)) return rc;
+  const double rho = est[1] / est[0];
+  std::vector<uint32_t> enc(n);
+  std::vector<uint64_t> inc(h.nrows, 0);
+  for (uint64_t i = 0; i < n; ++i) {
+    enc[i] = (uint32_t)keys[i];
+    const uint64_t row = keys[i] >> 32;
+    if (row >= h.nrows) return set_error(KREPP_ERR_CUDA, "a minimizer fell outside the table (row %llu of %u)", (unsigned long long)row, h.nrows);
+    ++inc[row];
+  }
+  for (uint32_t r = 1; r < h.nrows; ++r) inc[r] += inc[r - 1];
+  FILE* f = fopen(out_path, "wb");
+  if (!f) return set_error(KREPP_ERR_IO, "Failed to write the sketch!");
+  const uint8_t k8 = (uint8_t)h.k, w8 = (uint8_t)h.w, h8 = (uint8_t)h.h, frac8 = h.frac ? 1 : 0;
+  bool ok = fwrite(&n, 8, 1, f) == 1 && (!n || fwrite(enc.data(), 4, n, f) == n) && fwrite(&h.nrows, 4, 1, f) == 1 && (!h.nrows || fwrite(inc.data(), 8, h.nrows, f) == h.nrows);
+  ok = ok && fwrite(&k8, 1, 1, f) == 1 && fwrite(&w8, 1, 1, f) == 1 && fwrite(&h8, 1, 1, f) == 1 && fwrite(&h.m, 4, 1, f) == 1 && fwrite(&h.r, 4, 1, f) == 1 &&
+       fwrite(&frac8, 1, 1, f) == 1 && fwrite(&h.nrows, 4, 1, f) == 1 && fwrite(h.ppos.data(), 1, h.ppos.size(), f) == h.ppos.size() &&
+       fwrite(h.npos.data(), 1, h.npos.size(), f) == h.npos.size() && fwrite(&rho, 8, 1, f) == 1;
+  ok = (fclose(f) == 0) && ok;
+  if (!ok) return set_error(KREPP_ERR_IO, "Failed to write the sketch!");
+  if (n_kmers) *n_kmers = n;
+  if (rho_out) *rho_out = rho;
+  return KREPP_OK;
 }

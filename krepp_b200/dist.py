@@ -60,16 +60,18 @@ def gather_text(text: str) -> list[str]:
 TUPLE_WORDS = 4  # a lookup tuple and a hit entry are both 4 x u32
 
 
-def exchange_v(send, send_counts, group=None):
+def exchange_v(send, send_counts, group=None, recv_counts=None):
     """All-to-all-v of the rows of `send` (a [n, w] tensor, rank g's rows contiguous, send_counts[g] of them).
-    Returns (recv, recv_counts): the rows every rank sent here, in rank order."""
+    Returns (recv, recv_counts): the rows every rank sent here, in rank order.  recv_counts, when the caller knows them (the
+    row-boundary slices have the same sizes every batch), saves the exchange of the counts and its host round trip."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    sc = torch.as_tensor([int(c) for c in send_counts], dtype=torch.int64, device=send.device)
-    rc = torch.empty(world, dtype=torch.int64, device=send.device)
-    dist.all_to_all_single(rc, sc, group=group)
-    recv_counts = [int(x) for x in rc.tolist()]
+    if recv_counts is None:
+        sc = torch.as_tensor([int(c) for c in send_counts], dtype=torch.int64, device=send.device)
+        rc = torch.empty(world, dtype=torch.int64, device=send.device)
+        dist.all_to_all_single(rc, sc, group=group)
+        recv_counts = [int(x) for x in rc.tolist()]
     recv = torch.empty((sum(recv_counts),) + tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
     dist.all_to_all_single(recv, send[:sum(int(c) for c in send_counts)], output_split_sizes=recv_counts,
                            input_split_sizes=[int(c) for c in send_counts], group=group)
@@ -183,12 +185,12 @@ class ShardedJob:
             assert [r.rank for r in ranks] == list(range(ranks[0].world)), "an in-process job holds every rank"
         self.bytes_exchanged = 0
 
-    def _exchange(self, sends):
+    def _exchange(self, sends, recv_counts=None):
         """sends[i] = (tensor, counts) of in-process rank i -> [(recv tensor, recv counts)] per in-process rank."""
         import torch
         if not self.local:
             t, c = sends[0]
-            recv, rc = exchange_v(t, c, self.group)
+            recv, rc = exchange_v(t, c, self.group, recv_counts)
             self.bytes_exchanged += recv.numel() * recv.element_size()
             return [(recv, rc)]
         out = []
@@ -207,7 +209,8 @@ class ShardedJob:
         """Phases 1-3 of one batch on `lane`, up to the enqueue of its last phase (no wait)."""
         p1 = [r.lookup(*b, lane=lane) for r, b in zip(self.ranks, batches)]
         tup = self._exchange([(t, c) for t, c, _, _ in p1])
-        rbs = self._exchange([(rb.view(-1, 1), rc) for _, _, rb, rc in p1])
+        r0 = self.ranks[0]  # every sender sends this rank its own slice of row boundaries: the sizes are known
+        rbs = self._exchange([(rb.view(-1, 1), rc) for _, _, rb, rc in p1], None if self.local else [r0.splits[r0.rank + 1] - r0.splits[r0.rank] + 1] * r0.world)
         p2 = [r.join(t, c, rb.view(-1), lane=lane) for r, (t, c), (rb, _) in zip(self.ranks, tup, rbs)]
         back = self._exchange(p2)
         for r, (h, _) in zip(self.ranks, back):
