@@ -210,6 +210,39 @@ def _view(ptr, dtype, n):
 class Index:
     """Index image resident on one GPU (replaces Index + TargetIndex::load_index, src/krepp.cpp:66-108)."""
 
+    @classmethod
+    def geometry(cls, k: int = 26, w: int | None = None, h: int | None = None, m: int = 4, r: int = 1, frac: bool = True, seed: int | None = None,
+                 device: int = 0) -> "Index":
+        """krepp_geometry_open: the LSH geometry of a library still to be built (what `krepp sketch` / `krepp index` set up before
+        reading a genome); serves extract_mers, sequence_rho and sketch_write."""
+        self = cls.__new__(cls)
+        L = load_library()
+        self._h = C.c_void_p()
+        w = k + 6 if w is None else w
+        h = k - 16 if h is None else h
+        _check(L.krepp_geometry_open(k, w, h, m, r, int(frac), -1 if seed is None else seed, device, C.byref(self._h)))
+        self.info = IndexInfo()
+        _check(L.krepp_index_info(self._h, C.byref(self.info)))
+        self.device = device
+        return self
+
+    def sequence_rho(self, seqs) -> tuple[float, float]:
+        """krepp_sequence_rho: (HyperLogLog estimate of the distinct valid k-mers, of the distinct window minimizers), summed over
+        the sequences; their ratio is the genome's rho."""
+        bases, offs = pack_reads(list(seqs))
+        bases = np.ascontiguousarray(bases) if len(bases) else np.zeros(1, np.uint8)
+        a, b = C.c_double(), C.c_double()
+        _check(load_library().krepp_sequence_rho(self._h, bases.ctypes.data, offs.ctypes.data, len(offs) - 1, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def sketch_write(self, seqs, path: str) -> tuple[int, float]:
+        """krepp_sketch_write: `krepp sketch` of the sequences into `path`; returns (k-mers in the sketch, rho)."""
+        bases, offs = pack_reads(list(seqs))
+        bases = np.ascontiguousarray(bases) if len(bases) else np.zeros(1, np.uint8)
+        n, rho = C.c_uint64(), C.c_double()
+        _check(load_library().krepp_sketch_write(self._h, bases.ctypes.data, offs.ctypes.data, len(offs) - 1, os.fsencode(path), C.byref(n), C.byref(rho)))
+        return n.value, rho.value
+
     def __init__(self, index_dir: str, device: int = 0, shard: int = 0, nshards: int = 1, nwk: str | None = None, lineages: str | None = None):
         """nshards > 1: this handle holds bucket-range shard `shard` of the table only (SURVEY.md 8e mode B).
         nwk: `place -t` -- a Newick file whose tree replaces the index's backbone (krepp_index_open_tree).

@@ -311,17 +311,18 @@ int krepp_geometry_open(uint32_t k, uint32_t w, uint32_t h, uint32_t m, uint32_t
 {
   if (!out) return fail(KREPP_ERR_ARG, "krepp_geometry_open: null argument");
   *out = nullptr;
+  auto* ix = new krepp_index;
+  { // the configuration is judged before any device is looked for, as the reference judges it before reading anything
+    std::vector<uint8_t> ppos, npos;
+    if (k >= 19 && k <= 31 && h >= 3 && h <= 15 && h < k) lsh_positions(k, h, seed >= 0, (uint32_t)seed, ppos, npos);
+    std::string err = ix->host.set_geometry(k, w, h, m, r, frac != 0, ppos, npos);
+    if (!err.empty()) { delete ix; return fail(KREPP_ERR_ARG, "%s", err.c_str()); }
+  }
   int ndev = 0;
   if (device != KREPP_DEVICE_NONE) {
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(KREPP_ERR_CUDA, "no CUDA device is available (the krepp_b200 kernels have no CPU fallback)");
-    if (device < 0 || device >= ndev) return fail(KREPP_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { delete ix; return fail(KREPP_ERR_CUDA, "no CUDA device is available (the krepp_b200 kernels have no CPU fallback)"); }
+    if (device < 0 || device >= ndev) { delete ix; return fail(KREPP_ERR_ARG, "device %d out of range (%d devices)", device, ndev); }
   }
-  if (k > 32 || h >= k) return fail(KREPP_ERR_ARG, "Invalid configuration!");
-  std::vector<uint8_t> ppos, npos;
-  lsh_positions(k, h, seed >= 0, (uint32_t)seed, ppos, npos);
-  auto* ix = new krepp_index;
-  std::string err = ix->host.set_geometry(k, w, h, m, r, frac != 0, ppos, npos);
-  if (!err.empty()) { delete ix; return fail(KREPP_ERR_ARG, "%s", err.c_str()); }
   ix->device = device;
   if (device == KREPP_DEVICE_NONE) { *out = ix; return KREPP_OK; }
   const HostIndex& hh = ix->host;

@@ -39,7 +39,10 @@ struct Options {
   std::string sub, query, index_dir, output_path, nwk_path, lineage_path;
   uint32_t hdist_th = 4, tau = 2, num_threads = 1, seed = 0;
   double chisq = 2.706, dist_max = std::numeric_limits<double>::quiet_NaN();
-  bool multi = true, filter = false, summarize = false, tabular = false, verbose = false;
+  bool multi = true, filter = false, summarize = false, tabular = false, verbose = false, seed_set = false;
+  // sketch (ref src/krepp.hpp:35-46 set_sketch_defaults, src/krepp.cpp:516-540)
+  uint32_t sk_k = 26, sk_w = 32, sk_h = 10, sk_m = 4, sk_r = 1, sdust_t = 0, sdust_w = 0;
+  bool sk_frac = true, sk_w_set = false;
   // additions of this implementation
   std::vector<int> devices;
   bool shard_index = false; // --shard-index: every device holds one bucket-range shard of the table (SURVEY.md 8e mode B)
@@ -51,6 +54,7 @@ const char* kUsage =
   "krepp_b200: B200-native query path of krepp (k-mer-based distance estimation & phylogenetic placement).\n"
   "Usage: krepp_b200 [--num-threads N] [--seed S] [--verbose] {dist|place} -i INDEX_DIR -q QUERY [options]\n"
   "       krepp_b200 [--num-threads N] seek -i,--sketch-path SKETCH_FILE -q QUERY [-o PATH] [--hdist-th N]\n"
+  "       krepp_b200 [--seed S] sketch -i,--input-file FASTA -o,--output-path SKETCH_FILE [-k 26] [-w k+6] [-h k-16] [-m 4] [-r 1] [--frac/--no-frac]\n"
   "  common:  -q,--query PATH   -i,--index-dir DIR   -o,--output-path PATH   --hdist-th N [4]   --chisq X [2.706]\n"
   "           --summarize/--no-summarize [false]\n"
   "  dist:    --dist-max X   --multi/--no-multi [true]   --filter/--no-filter [false]\n"
@@ -83,12 +87,22 @@ Options parse(int argc, char** argv)
   for (size_t i = 0; i < a.size(); ++i) {
     std::string k = a[i];
     if (k.rfind("--", 0) == 0 && k.find('=') != std::string::npos) k = k.substr(0, k.find('='));
-    if (k == "dist" || k == "place" || k == "seek") { if (!o.sub.empty()) error_exit("Only one subcommand may be given."); o.sub = k; }
-    else if (k == "index" || k == "inspect" || k == "sketch") error_exit("Subcommand '" + k + "' is not part of the GPU query path; use the reference krepp binary for it.");
+    if (k == "dist" || k == "place" || k == "seek" || k == "sketch") { if (!o.sub.empty()) error_exit("Only one subcommand may be given."); o.sub = k; }
+    else if (k == "index" || k == "inspect") error_exit("Subcommand '" + k + "' is not part of the GPU query path; use the reference krepp binary for it.");
     else if (k == "--help") { fputs(kUsage, stdout); exit(0); }
     else if (k == "--verbose") o.verbose = true;
     else if (k == "--no-verbose") o.verbose = false;
-    else if (k == "--seed") o.seed = (uint32_t)strtoul(need(i, k).c_str(), nullptr, 10);
+    else if (k == "--seed") { o.seed = (uint32_t)strtoul(need(i, k).c_str(), nullptr, 10); o.seed_set = true; }
+    else if (o.sub == "sketch" && (k == "-i" || k == "--input-file")) o.index_dir = need(i, k);
+    else if (o.sub == "sketch" && (k == "-k" || k == "--kmer-len")) { o.sk_k = (uint32_t)atoi(need(i, k).c_str()); if (o.sk_k < 19 || o.sk_k > 31) error_exit("--kmer-len: Value " + std::to_string(o.sk_k) + " not in range [19 - 31]"); }
+    else if (o.sub == "sketch" && (k == "-w" || k == "--win-len")) { o.sk_w = (uint32_t)atoi(need(i, k).c_str()); o.sk_w_set = true; }
+    else if (o.sub == "sketch" && (k == "-h" || k == "--num-positions")) o.sk_h = (uint32_t)atoi(need(i, k).c_str());
+    else if (o.sub == "sketch" && (k == "-m" || k == "--modulo-lsh")) { o.sk_m = (uint32_t)atoi(need(i, k).c_str()); if (!o.sk_m) error_exit("--modulo-lsh: Number less or equal to 0"); }
+    else if (o.sub == "sketch" && (k == "-r" || k == "--residue-lsh")) o.sk_r = (uint32_t)atoi(need(i, k).c_str());
+    else if (o.sub == "sketch" && k == "--frac") o.sk_frac = true;
+    else if (o.sub == "sketch" && k == "--no-frac") o.sk_frac = false;
+    else if (o.sub == "sketch" && k == "--sdust-t") o.sdust_t = (uint32_t)atoi(need(i, k).c_str());
+    else if (o.sub == "sketch" && k == "--sdust-w") o.sdust_w = (uint32_t)atoi(need(i, k).c_str());
     else if (k == "--num-threads") o.num_threads = (uint32_t)strtoul(need(i, k).c_str(), nullptr, 10);
     else if (k == "-q" || k == "--query") o.query = need(i, k);
     else if (k == "-i" || k == "--index-dir" || k == "--sketch-path") o.index_dir = need(i, k);
@@ -116,6 +130,15 @@ Options parse(int argc, char** argv)
     else error_exit("The following argument was not expected: " + a[i]);
   }
   if (o.sub.empty()) { fputs(kUsage, stderr); error_exit("A subcommand is required"); }
+  if (o.sub == "sketch") { // ref src/krepp.cpp:516-540
+    if (o.index_dir.empty()) error_exit("--input-file is required");
+    if (o.output_path.empty()) error_exit("--output-path is required");
+    if (!exists(o.index_dir, false)) error_exit("--input-file: File does not exist: " + o.index_dir);
+    if (!o.sk_w_set) { o.sk_w = o.sk_k + 6; o.sk_h = o.sk_k - 16; }
+    if (o.sdust_t && o.sdust_w) error_exit("--sdust-t / --sdust-w (dustmasker) are not part of the GPU path; build such a sketch with the reference binary");
+    if (o.devices.empty()) o.devices.push_back(0);
+    return o;
+  }
   if (o.query.empty()) error_exit("--query is required");
   if (o.index_dir.empty()) error_exit(o.sub == "seek" ? "--sketch-path is required" : "--index-dir is required");
   if (!exists(o.query, false)) error_exit("--query: File does not exist: " + o.query);
@@ -347,6 +370,48 @@ static int run_sharded(const Options& o, const krepp_params_t& p, bool place, co
   return 0;
 }
 
+// `krepp sketch` (ref src/krepp.cpp:110-128,773-782): one FASTA/FASTQ file -> the sketch file `seek` reads.
+static int run_sketch(const Options& o)
+{
+  fprintf(stderr, "Initializing the sketch...\n");
+  const auto t0 = std::chrono::system_clock::now();
+  krepp_index_t* geom = nullptr;
+  if (krepp_geometry_open(o.sk_k, o.sk_w, o.sk_h, o.sk_m, o.sk_r, o.sk_frac ? 1 : 0, o.seed_set ? (int64_t)o.seed : -1, o.devices[0], &geom) != KREPP_OK) {
+    const std::string msg = krepp_last_error();
+    if (msg.find("(-") != std::string::npos || msg.find("h must be") != std::string::npos) { fprintf(stderr, "%s\n", msg.c_str()); error_exit("Invalid configuration!"); } // ref src/krepp.hpp:59-85
+    error_exit(msg);
+  }
+  struct stat st;
+  stat(o.index_dir.c_str(), &st);
+  const bool gz = o.index_dir.size() > 3 && o.index_dir.compare(o.index_dir.size() - 3, 3, ".gz") == 0;
+  uint64_t cap_bases = (uint64_t)st.st_size * (gz ? 8 : 1) + (1u << 20);
+  uint32_t cap_seqs = 1u << 16;
+  std::vector<char> bases, names;
+  std::vector<uint64_t> offsets, name_off;
+  uint32_t n = 0;
+  for (;;) { // the whole file in one batch; a batch that ends before the input does is read again with more room
+    bases.resize(cap_bases + 64); offsets.resize((size_t)cap_seqs + 1); names.resize(64ull * cap_seqs); name_off.resize(cap_seqs);
+    krepp_reader_t* rd = nullptr;
+    check(krepp_reader_open(o.index_dir.c_str(), &rd));
+    int eof = 0;
+    const int rc = krepp_reader_next(rd, bases.data(), cap_bases, offsets.data(), cap_seqs, names.data(), names.size(), name_off.data(), &n, &eof);
+    krepp_reader_close(rd);
+    if (rc == KREPP_OK && eof) break;
+    if (rc != KREPP_OK && rc != KREPP_ERR_CAPACITY) error_exit(krepp_last_error());
+    if (cap_bases > (1ull << 40)) error_exit("the input does not fit in memory");
+    cap_bases *= 2; cap_seqs *= 2;
+  }
+  uint64_t nk = 0;
+  double rho = 0;
+  check(krepp_sketch_write(geom, bases.data(), offsets.data(), n, o.output_path.c_str(), &nk, &rho));
+  fprintf(stderr, "Total number of k-mers included in the sketch: %llu\n", (unsigned long long)nk);
+  fprintf(stderr, "Subsampling rate (rho) is: %g\n", rho);
+  const std::chrono::duration<float> es = std::chrono::system_clock::now() - t0;
+  fprintf(stderr, "Done sketching & saving, elapsed: %g sec\n", es.count());
+  krepp_index_close(geom);
+  return 0;
+}
+
 int main(int argc, char** argv)
 {
   fprintf(stderr, "krepp_b200 version: v0.8.3+b200\n");
@@ -356,6 +421,7 @@ int main(int argc, char** argv)
   const auto tstart = std::chrono::system_clock::now();
   { std::time_t t = std::chrono::system_clock::to_time_t(tstart); fprintf(stderr, "Invocation: %s\n%s", invocation.c_str(), std::ctime(&t)); }
 
+  if (o.sub == "sketch") return run_sketch(o);
   const bool place = o.sub == "place", seek = o.sub == "seek";
   krepp_params_t p;
   krepp_params_default(&p, place ? 1 : 0);

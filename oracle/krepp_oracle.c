@@ -905,12 +905,47 @@ static void mers_push(uint64_t** out, uint64_t* n, uint64_t* cap, uint64_t v)
 /* ref src/rqseq.cpp:51-144 (RSeq::extract_mers) with sdust off (its default): ring of w-k+1 slots, zero-initialised per
  * sequence, indexed by kix % ldiff and NOT reset by non-ACGT bases; an emit happens at every window end whose valid run
  * is >= w, and also at i == len (end-of-sequence quirk, :112-116).  set_curr_seq (src/rqseq.hpp:80-86) skips len < w. */
+/* hll::HyperLogLog with b = 12 (ref src/hyperloglog.hpp:58-140): add() on the low 32 bits of the hash, estimate() */
+#define KO_HLL_REGS 4096
+static void hll_add(uint8_t* M, uint64_t z)
+{
+  const uint32_t hash = (uint32_t)z, index = hash >> 20, x = hash << 12;
+  const uint32_t lz = x ? (uint32_t)__builtin_clz(x) : 32u; /* the reference's __builtin_clz(0) is undefined; 32 = lzcnt */
+  const uint8_t rank = (uint8_t)((lz < 20 ? lz : 20) + 1);
+  if (rank > M[index]) M[index] = rank;
+}
+static double hll_estimate(const uint8_t* M)
+{
+  const double m = (double)KO_HLL_REGS, alpha_mm = (0.7213 / (1.0 + 1.079 / m)) * m * m;
+  double sum = 0.0;
+  for (uint32_t i = 0; i < KO_HLL_REGS; ++i) sum += 1.0 / (double)(1 << M[i]);
+  double e = alpha_mm / sum;
+  if (e <= 2.5 * m) {
+    uint32_t zeros = 0;
+    for (uint32_t i = 0; i < KO_HLL_REGS; ++i) zeros += M[i] == 0;
+    if (zeros) e = m * log(m / (double)zeros);
+  } else if (e > (1.0 / 30.0) * 4294967296.0) e = -4294967296.0 * log(1.0 - e / 4294967296.0);
+  return e;
+}
+
+static void extract_mers_est(const ko_index_t* g, const char* seq, uint64_t len, uint32_t w, uint64_t** out, uint64_t* n, uint64_t* cap, double* est);
 void ko_extract_mers(const ko_index_t* g, const char* seq, uint64_t len, uint32_t w, uint64_t** out, uint64_t* n, uint64_t* cap)
 {
+  extract_mers_est(g, seq, len, w, out, n, cap, NULL);
+}
+/* the same walk with RSeq's two counters: est[0] += distinct valid k-mers, est[1] += distinct minimizers (ref src/rqseq.cpp:63-64,107-108,117,142-143) */
+void ko_extract_mers_rho(const ko_index_t* g, const char* seq, uint64_t len, uint32_t w, uint64_t** out, uint64_t* n, uint64_t* cap, double* est)
+{
+  extract_mers_est(g, seq, len, w, out, n, cap, est);
+}
+static void extract_mers_est(const ko_index_t* g, const char* seq, uint64_t len, uint32_t w, uint64_t** out, uint64_t* n, uint64_t* cap, double* est)
+{
+  uint8_t* c1 = est ? (uint8_t*)calloc(2 * KO_HLL_REGS, 1) : NULL;
+  uint8_t* c2 = c1 ? c1 + KO_HLL_REGS : NULL;
   uint32_t k = g->k, m = g->m, r = g->geom_r; int frac = (int)g->geom_frac;
   uint32_t ldiff;
   if (w > k) ldiff = w - k + 1; else { ldiff = 1; w = k; }
-  if (len < w) return;
+  if (len < w) { free(c1); return; }
   typedef struct { uint64_t x, y, z; } hm_t;
   hm_t* win = (hm_t*)calloc(ldiff, sizeof(hm_t));
   uint64_t kix = 0, bp = 0, lr = 0;
@@ -924,9 +959,11 @@ void ko_extract_mers(const ko_index_t* g, const char* seq, uint64_t len, uint32_
     uint64_t x = bp & g->mask_bp, y = lr & g->mask_lr;
     hm_t cur = {x, y, ko_xur64_hash(x)};
     win[kix % ldiff] = cur; kix++;
+    if (c1) hll_add(c1, cur.z);
     if ((l < w) && (i != len)) continue;
     hm_t mn = win[0];
     for (uint32_t j = 1; j < ldiff; ++j) if (win[j].z < mn.z) mn = win[j]; /* std::min_element: first minimum */
+    if (c2) hll_add(c2, mn.z);
     uint32_t rix = (uint32_t)ko_pext64(mn.x, g->mask_hash_bp), res = rix % m;
     if (frac ? res <= r : res == r) {
       rix = frac ? rix / m * (r + 1) + res : rix / m;
@@ -934,6 +971,8 @@ void ko_extract_mers(const ko_index_t* g, const char* seq, uint64_t len, uint32_
     }
   }
   free(win);
+  if (est) { est[0] += hll_estimate(c1); est[1] += hll_estimate(c2); }
+  free(c1);
 }
 
 /* ------------------------------------------------------------------------------------------------ seek (a sketch of one genome) */

@@ -101,6 +101,8 @@ def lib():
         L.ko_geom_new.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_char_p]
         L.ko_extract_mers.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint32, C.POINTER(C.POINTER(C.c_uint64)),
                                       C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.ko_extract_mers_rho.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint32, C.POINTER(C.POINTER(C.c_uint64)),
+                                          C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
         L.ko_sketch_load.restype = C.c_void_p
         L.ko_sketch_load.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t]
         L.ko_sketch_free.argtypes = [C.c_void_p]
@@ -118,6 +120,42 @@ def default_params(**kw) -> Params:
     for k, v in kw.items():
         setattr(p, k, v)
     return p
+
+
+def read_sketch_file(path: str) -> dict:
+    """The fields of a sketch file as `krepp sketch` writes them (ref src/table.cpp:35-41, src/krepp.cpp:18-29,121-128)."""
+    import numpy as np
+    import struct
+    with open(path, "rb") as f:
+        buf = f.read()
+    nk = struct.unpack_from("<Q", buf, 0)[0]
+    enc = np.frombuffer(buf, "<u4", nk, 8)
+    at = 8 + 4 * nk
+    nrows = struct.unpack_from("<I", buf, at)[0]
+    inc = np.frombuffer(buf, "<u8", nrows, at + 4)
+    at += 4 + 8 * nrows
+    k, w, h = buf[at], buf[at + 1], buf[at + 2]
+    m, r = struct.unpack_from("<II", buf, at + 3)
+    frac = buf[at + 11]
+    nrows2 = struct.unpack_from("<I", buf, at + 12)[0]
+    ppos = bytes(buf[at + 16:at + 16 + h])
+    npos = bytes(buf[at + 16 + h:at + 16 + k])
+    rho = struct.unpack_from("<d", buf, at + 16 + k)[0]
+    assert at + 16 + k + 8 == len(buf) and nrows2 == nrows
+    return dict(enc=enc, inc=inc, k=k, w=w, h=h, m=m, r=r, frac=frac, nrows=nrows, ppos=ppos, npos=npos, rho=rho)
+
+
+def oracle_sketch_table(meta: dict, seqs) -> tuple:
+    """(sorted unique row << 32 | enc keys, rho) of the sequences under a sketch's geometry, from the oracle's extract_mers walk."""
+    import numpy as np
+    L = lib()
+    geom = L.ko_geom_new(meta["k"], meta["h"], meta["m"], meta["r"], int(meta["frac"]), meta["ppos"])
+    out, n, cap = C.POINTER(C.c_uint64)(), C.c_uint64(0), C.c_uint64(0)
+    est = (C.c_double * 2)(0.0, 0.0)
+    for s in seqs:
+        L.ko_extract_mers_rho(geom, s, len(s), meta["w"], C.byref(out), C.byref(n), C.byref(cap), est)
+    keys = np.unique(np.ctypeslib.as_array(out, shape=(n.value,)).copy()) if n.value else np.zeros(0, np.uint64)
+    return keys, est[1] / est[0]
 
 
 class OracleSketch:

@@ -40,7 +40,7 @@ def test_argument_errors(args, msg):
 
 
 def test_subcommands_outside_the_query_path_are_refused_by_name():
-    for sub in ("index", "sketch", "inspect"):
+    for sub in ("index", "inspect"):
         r = subprocess.run([CLI, sub, "-i", "x"], capture_output=True, text=True, timeout=60)
         assert r.returncode != 0 and f"Subcommand '{sub}' is not part of the GPU query path" in r.stderr
     r = subprocess.run([CLI, "place", "-i", IDX, "-q", FQ, "-l", os.path.join(S, "no_such_lineages.tsv")], capture_output=True, text=True, timeout=60)
@@ -51,6 +51,10 @@ def test_subcommands_outside_the_query_path_are_refused_by_name():
     assert r.returncode != 0 and "--sketch-path: File does not exist" in r.stderr
     r = subprocess.run([CLI, "seek", "-q", FQ], capture_output=True, text=True, timeout=60)
     assert r.returncode != 0 and "--sketch-path is required" in r.stderr
+    r = subprocess.run([CLI, "sketch", "-i", FQ], capture_output=True, text=True, timeout=60)
+    assert r.returncode != 0 and "--output-path is required" in r.stderr
+    r = subprocess.run([CLI, "sketch", "-i", FQ, "-o", "/tmp/x.skc", "-k", "26", "-w", "20", "-h", "10"], capture_output=True, text=True, timeout=60)
+    assert r.returncode != 0 and "The minimum minimizer window size (-w) is k (-k)." in r.stderr
     r = subprocess.run([CLI, "--help"], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0 and "--shard-index" in r.stdout and "--num-gpus" in r.stdout
 

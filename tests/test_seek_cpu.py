@@ -47,3 +47,34 @@ def test_sketch_loads_as_a_one_reference_image_and_rows_format(tmp_path_factory)
         krepp_b200.Index(cut, capi.DEVICE_NONE)
     txt = capi.format_seek(np.array([0.015994, float("nan"), 0.5, 1e-10, 0.123455]), ["a", "b", "c d", "e", "f"])
     assert txt == "a\t0.01599\nb\tNaN\nc d\t0.50000\ne\t0.00000\nf\t" + "%.5f" % 0.123455 + "\n"
+
+
+def fasta_seqs(path):
+    seqs, cur = [], []
+    with open(path) as f:
+        for line in f:
+            if line.startswith(">"):
+                if cur:
+                    seqs.append("".join(cur).encode())
+                cur = []
+            else:
+                cur.append(line.strip())
+    if cur:
+        seqs.append("".join(cur).encode())
+    return seqs
+
+
+@pytest.mark.parametrize("label,genome,args", SKETCHES, ids=[s[0] for s in SKETCHES])
+def test_oracle_sketch_equals_the_reference_file(label, genome, args, tmp_path_factory):
+    """`krepp sketch` restated (extract_mers walk, per-row sort + unique, HyperLogLog rho) against the file the reference wrote:
+    the table entry for entry, rho bit for bit (ref src/krepp.cpp:110-128, src/rqseq.cpp:51-144, src/hyperloglog.hpp:58-140)."""
+    import numpy as np
+    import oracle_lib as O
+    path = build_sketch(label, genome, args, tmp_path_factory.getbasetemp())
+    meta = O.read_sketch_file(path)
+    keys, rho = O.oracle_sketch_table(meta, fasta_seqs(os.path.join(SMALL, "genomes", genome + ".fna")))
+    assert len(keys) == len(meta["enc"]) > 500
+    assert np.array_equal((keys & 0xFFFFFFFF).astype(np.uint32), meta["enc"])
+    inc = np.cumsum(np.bincount((keys >> 32).astype(np.int64), minlength=meta["nrows"])).astype(np.uint64)
+    assert np.array_equal(inc, meta["inc"])
+    assert rho == meta["rho"], (rho, meta["rho"])
