@@ -423,7 +423,7 @@ def hot_arm(env: Env, index, wl: Workload, mode: str, n: int, batch: int, steps:
         "metric": METRIC if mode == "dist" else METRIC.replace("dist", "place"), "value": value, "unit": "reads/s", "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": t_dev * 1e3 / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32/f64", "data": "synthetic",
-        "config": {"workload": workload_name, "reads_per_gpu": n, "read_len": READ_LEN, "batch_reads": batch, "batches_in_flight": lanes, **wl.info,
+        "config": {"workload": workload_name, "reads_per_gpu": n, "read_len": READ_LEN, "batch_reads": batch, **wl.info,
                    "l2": "inputs larger than L2 (index image %.2f GB, reads %.2f GB per step) and a 256 MiB memset between steps" % (index.info.device_bytes / 1e9, n * READ_LEN / 1e9),
                    "index": "replicated per GPU", "records_per_step": last["records"], "placements_per_step": last["placements"], "wall_s_device_arm": wall_device,
                    "workload_setup_s": round(t_wl, 1)},

@@ -42,10 +42,11 @@ def test_sorted_golden_small_index(sorted_pipeline):
 
 
 @needs_ref
-@pytest.mark.parametrize("lookup", ["binned", "two_pass"])
+@pytest.mark.parametrize("lookup", ["binned", "two_pass", "staged"])
 def test_sorted_toy_query_and_20k(env, sorted_pipeline, monkeypatch, lookup):
-    """Both forms of the lookup sort: the two-pass counting sort (the default) and the two-level one (lookup_partition_kernel +
-    bin_sort_kernel, KREPP_LOOKUP=binned)."""
+    """The forms of the lookup sort: the two-pass counting sort, the one that keeps the counting pass's lookups and scatters them by
+    a plain copy (scatter_staged_kernel, KREPP_LOOKUP=staged), and the two-level one (lookup_partition_kernel + bin_sort_kernel,
+    KREPP_LOOKUP=binned)."""
     import synth
     from gpu_common import run_and_compare
     monkeypatch.setenv("KREPP_LOOKUP", lookup)
@@ -66,6 +67,7 @@ def test_sorted_edge_cases_and_long_reads(env, sorted_pipeline, monkeypatch, wid
     import synth
     from gpu_common import run_and_compare
     monkeypatch.setenv("KREPP_SORT_WIDE", wide)
+    monkeypatch.setenv("KREPP_SEGMENT_WINDOWS", "0")  # whole reads: this test is about the one-warp-per-read paths (cut reads: test_gpu_segments.py)
     seq, offs = synth.load_packed(os.path.join(TOY_DIR, "genomes.npz"))
     rng = np.random.default_rng(5)
     base = [r.tobytes() for r in synth.sample_reads(seq, offs, 64, read_len=300, max_sub=0.05, seed=3)]
