@@ -635,9 +635,6 @@ static int alloc_tuples(krepp_batch* b, uint64_t cap)
   if (b->so.tuples) cudaFree(b->so.tuples);
   b->so.tuples = nullptr; b->so.cap_lookups = (uint32_t)cap;
   CU(cudaMalloc(&b->so.tuples, 16ull * cap));
-  if (b->so.staged) cudaFree(b->so.staged);
-  b->so.staged = nullptr;
-  if (const char* lk = getenv("KREPP_LOOKUP")) { if (!strcmp(lk, "staged")) CU(cudaMalloc(&b->so.staged, 16ull * cap)); }
   // coarse bins of the two-level lookup sort (sorted.cu lookup_partition_kernel): at most 512 bins of a power-of-two number of
   // rows, each with room for a quarter more than an even share of the lookups.  Opt-in (KREPP_LOOKUP=binned): measured on B200
   // (r07e/f, config 3) it only ties the two-pass sort -- 28.0 + 32.3 ms against 14.0 + 47.1 ms per 10 M reads: the partition's
@@ -832,7 +829,7 @@ void krepp_batch_destroy(krepp_batch_t* b)
                   (void*)b->d_pn_se, (void*)b->d_pn_flags, (void*)b->d_pn_work, (void*)b->d_pn_mc, (void*)b->d_pn_uc, (void*)b->d_pn_rho, (void*)b->d_pn_d,
                   (void*)b->d_pn_v, (void*)b->d_pn_chisq, (void*)b->d_place})
     if (p) cudaFree(p);
-  for (void* p : {(void*)b->so.staged, (void*)b->so.binned, (void*)b->so.bin_cursor, (void*)b->so.row_count, (void*)b->so.row_begin, (void*)b->so.row_cursor, (void*)b->so.tuples, (void*)b->so.hits_tmp, (void*)b->so.hits,
+  for (void* p : {(void*)b->so.binned, (void*)b->so.bin_cursor, (void*)b->so.row_count, (void*)b->so.row_begin, (void*)b->so.row_cursor, (void*)b->so.tuples, (void*)b->so.hits_tmp, (void*)b->so.hits,
                   (void*)b->so.hit_count, (void*)b->so.hit_begin, (void*)b->so.hit_cursor, (void*)b->so.partials, (void*)b->so.sc, (void*)b->so.keys_g})
     if (p) cudaFree(p);
   if (b->h_sc) cudaFreeHost(b->h_sc);

@@ -114,7 +114,7 @@ struct SortArgs {
   uint32_t* hit_cursor;   // [n_reads]
   uint32_t* partials;     // scan scratch
   uint32_t* sc;           // [0] hit entries appended, [1] next row to claim, [2] next read to claim (lookup pass 1), [3] (pass 2), [4] (resolve),
-                          // [5] most leaf hits of one read that did not fit keys_g (the host grows it to that), [6] next bin to claim (bin sort), [7] staged tuples
+                          // [5] most leaf hits of one read that did not fit keys_g (the host grows it to that), [6] next bin to claim (bin sort)
   uint64_t* keys_g;       // [warps][cap_keys_g] per-warp sort scratch in HBM for reads whose leaf hits exceed shared memory
   uint32_t cap_keys_g;
   // two-level sort of the lookups (lookup_partition_kernel -> bin_sort_kernel): coarse bins of 2^bin_shift rows, each with room
@@ -122,9 +122,6 @@ struct SortArgs {
   uint4* binned;          // [nbins * bin_cap]
   uint32_t* bin_cursor;   // [nbins] tuples appended to every bin
   uint32_t nbins, bin_cap, bin_shift;
-  // lookups kept from the counting pass (KREPP_LOOKUP=staged): {q, read, local lookup index | strand << 31, row} in the order the
-  // warps produced them, so that the scatter pass is a plain copy through the row cursors instead of a second walk over the reads
-  uint4* staged;          // [cap_lookups] or null; sc[7] = tuples appended
   uint32_t res_ctas;      // CTAs of the resolve kernel (keys_g holds res_ctas * warps per CTA regions); 0 = the default grid
   uint32_t extra_rank_bits; // test knob (KREPP_SORT_WIDE): widens the leaf field of the sort keys so that the 64-bit key path runs
 };

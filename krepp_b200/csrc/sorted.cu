@@ -80,13 +80,6 @@ __global__ void __launch_bounds__(kLkWarps * 32, 2) lookup_kernel(const DevIndex
       if (loc + nl >= kMaxLoc) { if (lane == 0) atomicOr(a.counters + 2, kErrSortFallback); break; }
       if (!SCATTER) {
         for (uint32_t i = lane; i < nl; i += 32) atomicAdd(&s.row_count[sm.lk_a[i] & 0x7FFFFFFFu], 1u);
-        if (s.staged && nl) { // keep the lookups: one cursor bump per tile, 16-byte stores side by side
-          uint32_t base = 0;
-          if (lane == 0) base = atomicAdd(s.sc + 7, nl);
-          base = __shfl_sync(0xFFFFFFFFu, base, 0);
-          if ((uint64_t)base + nl <= s.cap_lookups)
-            for (uint32_t i = lane; i < nl; i += 32) { const uint32_t ob = sm.lk_a[i]; s.staged[base + i] = make_uint4(sm.lk_q[i], read, (loc + i) | (ob & 0x80000000u), ob & 0x7FFFFFFFu); }
-        }
       } else {
         // the cursor atomics return positions: four are kept in flight per lane before the stores that need them
         for (uint32_t i0 = lane; i0 < nl; i0 += 128) {
@@ -113,28 +106,6 @@ __global__ void __launch_bounds__(kLkWarps * 32, 2) lookup_kernel(const DevIndex
     }
   }
   if (!SCATTER && lane == 0 && (st_bytes | st_lookups)) { atomicAdd(a.stats, st_bytes + 16ull * st_lookups); atomicAdd(a.stats + 1, st_lookups); }
-}
-
-// L2 when the counting pass kept its lookups (SortArgs::staged): every staged tuple goes to the next free place of its row.
-// Four tuples per thread and trip: the loads, then the four cursor atomics, then the stores.
-__global__ void __launch_bounds__(256) scatter_staged_kernel(const SortArgs s, uint32_t* counters)
-{
-  const uint32_t n = s.row_begin[s.nrows];
-  if (n > s.cap_lookups) { // the lookup list does not fit (the counting pass dropped what it could not keep): the host grows it and runs the batch again
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(counters + 2, kErrLookupOverflow);
-    return;
-  }
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride) {
-    uint4 t[4];
-    uint32_t pos[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) { const uint32_t i = i0 + u * stride; if (i < n) t[u] = __ldcs(s.staged + i); }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) { const uint32_t i = i0 + u * stride; pos[u] = i < n ? atomicAdd(&s.row_cursor[t[u].w], 1u) : 0u; }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) { const uint32_t i = i0 + u * stride; if (i < n) s.tuples[pos[u]] = make_uint4(t[u].x, t[u].y, t[u].z, 0u); }
-  }
 }
 
 // ---------------------------------------------------------------------------------------------------- S1 / S2: exclusive scan
@@ -907,13 +878,6 @@ static cudaError_t launch_lookup_sort(const DevIndex& ix, const MatchArgs& a, co
   if (clk) clk->tick("lookup_kernel<count>", stream);
   if ((e = exclusive_scan(s.row_count, s.nrows, s.partials, s.row_begin, s.row_cursor, stream)) != cudaSuccess) return e;
   if (clk) clk->tick("scan(rows)", stream);
-  if (s.staged) {
-    scatter_staged_kernel<<<sms * 8, 256, 0, stream>>>(s, a.counters);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    if (clk) clk->tick("scatter_staged_kernel", stream);
-    if (launches) *launches += 5;
-    return cudaSuccess;
-  }
   if ((e = launch_lookup<true>(ix, a, s, sms, false, stream)) != cudaSuccess) return e;
   if (clk) clk->tick("lookup_kernel<scatter>", stream);
   if (launches) *launches += 5;

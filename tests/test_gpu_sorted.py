@@ -42,11 +42,10 @@ def test_sorted_golden_small_index(sorted_pipeline):
 
 
 @needs_ref
-@pytest.mark.parametrize("lookup", ["binned", "two_pass", "staged"])
+@pytest.mark.parametrize("lookup", ["binned", "two_pass"])
 def test_sorted_toy_query_and_20k(env, sorted_pipeline, monkeypatch, lookup):
-    """The forms of the lookup sort: the two-pass counting sort, the one that keeps the counting pass's lookups and scatters them by
-    a plain copy (scatter_staged_kernel, KREPP_LOOKUP=staged), and the two-level one (lookup_partition_kernel + bin_sort_kernel,
-    KREPP_LOOKUP=binned)."""
+    """Both forms of the lookup sort: the two-pass counting sort (the default) and the two-level one (lookup_partition_kernel +
+    bin_sort_kernel, KREPP_LOOKUP=binned)."""
     import synth
     from gpu_common import run_and_compare
     monkeypatch.setenv("KREPP_LOOKUP", lookup)
