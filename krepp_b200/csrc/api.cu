@@ -793,7 +793,7 @@ int krepp_batch_create(krepp_index_t* ix, const krepp_params_t* p, uint32_t max_
   if (b->sorted) { if (int rc = alloc_sorted(b)) return rc; }
   if (p->place) {
     const size_t nn = h.tree.nnodes, nbm_nodes = (nn + 32) / 32;
-    b->place_warps = (uint32_t)ix->sms * 8u * (uint32_t)kPlaceWarpsPerCta; // 32 resident warps per SM: the collect kernel is latency-bound
+    b->place_warps = (uint32_t)ix->sms * 8u * (uint32_t)kPlaceWarpsPerCta; // 32 resident warps per SM (64 registers; 40 at 48 registers spill and lose): the collect kernel is latency-bound
     const size_t pw = b->place_warps;
     CU(cudaMalloc(&b->d_place_begin, 4ull * max_reads)); CU(cudaMalloc(&b->d_place_count, 4ull * max_reads));
     CU(cudaMalloc(&b->d_node_bitmap, 4 * pw * nbm_nodes)); CU(cudaMemset(b->d_node_bitmap, 0, 4 * pw * nbm_nodes));

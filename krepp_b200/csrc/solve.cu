@@ -228,7 +228,7 @@ __device__ __forceinline__ double jukes_cantor(double d) { return -0.75 * log(1 
 //   place_chisq_kernel    thread per node entry: likelihood-ratio test against the closest reference
 //   place_emit_kernel     warp per read: candidates in ascending se, lwr, placement rows
 template <int N> // N = histogram bins kept in registers (th + 1 <= N)
-__global__ void __launch_bounds__(128) place_collect_kernel(const PlaceArgs a)
+__global__ void __launch_bounds__(128, 8) place_collect_kernel(const PlaceArgs a)
 {
   const SolveArgs& s = a.s;
   if (s.counters[2] & kErrRedo) return;
@@ -242,7 +242,9 @@ __global__ void __launch_bounds__(128) place_collect_kernel(const PlaceArgs a)
   // exact mode (see 3a'): prefix sums over the read's selected references of their scaled histograms (+ match count)
   constexpr uint32_t kPfxCap = 64;
   __shared__ double spfx[kPlaceWarpsPerCta][kPfxCap + 1][N + 1];
+  __shared__ double srho[kPlaceWarpsPerCta][kPfxCap];  // exact mode: rho of the selected references, by rank
   double (*pfx)[N + 1] = spfx[threadIdx.x >> 5];
+  double* sel_rho = srho[threadIdx.x >> 5];
   uint32_t* bm = a.node_bitmap + (size_t)gwarp * nbm;
   if (nbm <= kSmemBm) {
     bm = sbm[threadIdx.x >> 5];
@@ -315,6 +317,15 @@ __global__ void __launch_bounds__(128) place_collect_kernel(const PlaceArgs a)
           uint32_t* sel_se = sel_rec + a.nleaves;
           uint32_t* sel_off = sel_se + a.nleaves;
           double* chain = a.chain + (size_t)gwarp * a.chain_cap;
+          if (n <= 32) { // one record per lane: a selected record's rank = selected records with a smaller se, counted over shuffles
+            const bool have = lane < n;
+            const uint32_t se = have ? (s.rec_slot[b + lane] & 0x7FFFFFFFu) : 0xFFFFFFFFu;
+            const bool picked = have && (s.rec_flags[b + lane] & 2u);
+            const uint32_t pm = __ballot_sync(0xFFFFFFFFu, picked);
+            uint32_t rank = 0;
+            for (uint32_t q = 0; q < n; ++q) { const uint32_t sq = __shfl_sync(0xFFFFFFFFu, se, q); rank += ((pm >> q) & 1u) && sq < se; }
+            if (picked) { sel_rec[rank] = b + lane; sel_se[rank] = se; }
+          } else
           for (uint32_t i = lane; i < n; i += 32) {
             if (!(s.rec_flags[b + i] & 2u)) continue;
             const uint32_t se = s.rec_slot[b + i] & 0x7FFFFFFFu;
@@ -336,16 +347,20 @@ __global__ void __launch_bounds__(128) place_collect_kernel(const PlaceArgs a)
             exact = !__any_sync(0xFFFFFFFFu, bad);
           }
           if (exact) {
-            if (lane <= stride && lane <= (uint32_t)N) { // lane x: component x of the histogram, lane `stride`: the match count
+            // every reference's scaled histogram (+ match count) and rho into shared memory, one reference per lane and trip ...
+            for (uint32_t i = lane; i < nsel; i += 32) {
+              const uint32_t rec = sel_rec[i], se = sel_se[i];
+              const double scale = __hiloint2double((int)((1023u - a.logw[se]) << 20), 0); // 2^-logw
+              for (uint32_t x = 0; x < stride; ++x) pfx[i + 1][x] = (double)s.rec_hist[(size_t)rec * stride + x] * scale;
+              pfx[i + 1][stride] = (double)s.rec_match[rec] * scale;
+              sel_rho[i] = s.rho[se];
+            }
+            __syncwarp();
+            // ... then the running sums, lane x = component x (lane `stride`: the match count)
+            if (lane <= stride && lane <= (uint32_t)N) {
               double run = 0;
               pfx[0][lane] = 0;
-              for (uint32_t i = 0; i < nsel; ++i) {
-                const uint32_t rec = sel_rec[i];
-                const double scale = __hiloint2double((int)((1023u - a.logw[sel_se[i]]) << 20), 0); // 2^-logw
-                const double val = lane < stride ? (double)s.rec_hist[(size_t)rec * stride + lane] : (double)s.rec_match[rec];
-                run = run + val * scale;
-                pfx[i + 1][lane] = run;
-              }
+              for (uint32_t i = 0; i < nsel; ++i) { run = run + pfx[i + 1][lane]; pfx[i + 1][lane] = run; }
             }
             __syncwarp();
           }
@@ -422,7 +437,7 @@ __global__ void __launch_bounds__(128) place_collect_kernel(const PlaceArgs a)
                   for (int x = 0; x < N; ++x) if ((uint32_t)x < stride) mc[x] = (pfx[last][x] - pfx[first][x]) * up;
                   match = (pfx[last][stride] - pfx[first][stride]) * up;
                   mismatch = (double)enmers - match;
-                  for (uint32_t i = first; i < last; ++i) rho = fmax(rho, s.rho[sel_se[i]]);
+                  for (uint32_t i = first; i < last; ++i) rho = fmax(rho, sel_rho[i]);
                 } else
                 for (uint32_t i = first; i < nsel; ++i) { // ascending leaf se: the order Minfo::add is applied in
                   const uint32_t se = sel_se[i];
