@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(256) alias_kernel(const SolveArgs a)
 
 // One thread per work item: Brent on the record's histogram.  N = histogram bins kept in registers (th + 1 <= N).
 template <int N>
-__global__ void __launch_bounds__(128) solve_kernel(const SolveArgs a, const LlhTables tab)
+__global__ void __launch_bounds__(128, 8) solve_kernel(const SolveArgs a, const LlhTables tab)
 {
   __shared__ double su[4];
   __shared__ DTerms st[4];
@@ -482,7 +482,7 @@ __global__ void __launch_bounds__(128, 8) place_collect_kernel(const PlaceArgs a
 }
 
 template <int N>
-__global__ void __launch_bounds__(128) place_solve_kernel(const PlaceArgs a, const LlhTables tab)
+__global__ void __launch_bounds__(128, 8) place_solve_kernel(const PlaceArgs a, const LlhTables tab)
 {
   __shared__ double su[4];
   __shared__ DTerms st[4];
