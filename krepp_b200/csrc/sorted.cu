@@ -738,7 +738,7 @@ __device__ __forceinline__ ResolveOut resolve_read(const DevIndex& ix, const Mat
   return emit_sorted<K>(ix, a, keys, T, seg_shift, rank_bits, read, g0, g1, small_counts);
 }
 
-__global__ void __launch_bounds__(kResWarps * 32, 4) resolve_kernel(const DevIndex ix, const MatchArgs a, const SortArgs s, uint32_t rank_bits)
+__global__ void __launch_bounds__(kResWarps * 32) resolve_kernel(const DevIndex ix, const MatchArgs a, const SortArgs s, uint32_t rank_bits)
 {
   __shared__ __align__(16) uint32_t skeys[kResWarps][kResKeys];
   if (a.counters[2] & kErrRedo) return;
