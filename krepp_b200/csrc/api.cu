@@ -177,73 +177,30 @@ __device__ __forceinline__ bool dist_rows_of(const DistOut& a, uint32_t r, F&& e
   return false;
 }
 
-// A warp per read, a record per lane (reads with more than 32 records go through dist_rows_of on lane 0).  Returns what the read
-// prints: `keep` says whether this lane's record is a printed row, `rank` its place among the read's rows (rows are printed by
-// ascending se, and the kept records of a read have distinct se), the return value the number of rows, 0xFFFFFFFF for "NA".
-__device__ __forceinline__ uint32_t dist_rows_warp(const DistOut& a, uint32_t b, uint32_t n, int32_t cl, uint32_t lane, bool& keep, uint32_t& rank, uint32_t& slot, double& d)
-{
-  const bool have = lane < n;
-  slot = have ? a.rec_slot[b + lane] : 0xFFFFFFFFu;
-  const uint32_t flags = have ? a.rec_flags[b + lane] : 0u;
-  d = have ? a.rec_d[b + lane] : 0.0;
-  keep = false; rank = 0;
-  if (!a.summarize) {
-    const double dcl = __shfl_sync(0xFFFFFFFFu, d, cl >= 0 ? (int)((uint32_t)cl - b) & 31 : 0);
-    if (cl < 0 || (a.has_max && dcl > a.dist_max)) return 0xFFFFFFFFu;
-    if (!a.multi) { keep = have && b + lane == (uint32_t)cl; return 1u; }
-  }
-  keep = have && (flags & KREPP_REC_SELECTED) && (!a.has_max || d < a.dist_max);
-  if (keep && (a.summarize || !a.no_filter)) keep = a.rec_chisq[b + lane] < a.chisq_value; // NaN never passes
-  const uint32_t km = __ballot_sync(0xFFFFFFFFu, keep);
-  const uint32_t se = slot & 0x7FFFFFFFu;
-  for (uint32_t q = 0; q < n; ++q) { const uint32_t sq = __shfl_sync(0xFFFFFFFFu, se, q); rank += ((km >> q) & 1u) && sq < se; }
-  return __popc(km);
-}
-
-__global__ void __launch_bounds__(256) dist_count_kernel(const DistOut a)
+__global__ void __launch_bounds__(128) dist_count_kernel(const DistOut a)
 {
   if (a.counters[2] & kErrRedo) return;
-  const uint32_t lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t r = warp; r < a.n_reads; r += nwarps) {
-    const uint32_t b = a.rec_begin[r], n = a.rec_count[r];
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < a.n_reads; r += gridDim.x * blockDim.x) {
     uint32_t c = 0;
-    if (n <= 32) {
-      bool keep; uint32_t rank, slot; double d;
-      c = dist_rows_warp(a, b, n, a.closest[r], lane, keep, rank, slot, d);
-      if (c == 0xFFFFFFFFu) c = 0;
-    } else if (lane == 0) dist_rows_of(a, r, [&](uint32_t) { ++c; });
-    if (lane == 0) a.cnt[r] = c;
+    dist_rows_of(a, r, [&](uint32_t) { ++c; });
+    a.cnt[r] = c;
   }
 }
 
-__global__ void __launch_bounds__(256) dist_emit_kernel(const DistOut a)
+__global__ void __launch_bounds__(128) dist_emit_kernel(const DistOut a)
 {
   if (a.counters[2] & kErrRedo) return;
-  const uint32_t lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-  auto put = [&](uint32_t at, uint32_t slot, double d) {
-    const uint32_t se = slot & 0x7FFFFFFFu, units = fixed5_units(d);
-    if (a.row_bytes == 4) static_cast<uint32_t*>(a.rows)[at] = a.leaf_rank[se] << 16 | (units < 0xFFFFu ? units : 0xFFFFu);
-    else static_cast<uint2*>(a.rows)[at] = make_uint2(se, units);
-  };
-  for (uint32_t r = warp; r < a.n_reads; r += nwarps) {
-    const uint32_t b = a.rec_begin[r], n = a.rec_count[r], first = a.begin[r];
-    uint32_t rows = 0;
-    bool na = false;
-    if (n <= 32) {
-      bool keep; uint32_t rank, slot; double d;
-      rows = dist_rows_warp(a, b, n, a.closest[r], lane, keep, rank, slot, d);
-      na = rows == 0xFFFFFFFFu;
-      if (na) rows = 0;
-      if (keep) put(first + rank, slot, d);
-    } else if (lane == 0) {
-      uint32_t at = first;
-      na = dist_rows_of(a, r, [&](uint32_t i) { put(at, a.rec_slot[i], a.rec_d[i]); ++at; });
-      rows = at - first;
-    }
-    if (lane == 0) {
-      a.out_begin[r] = first | (na ? 0x80000000u : 0u);
-      if (r == a.n_reads - 1) a.out_begin[a.n_reads] = first + rows;
-    }
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < a.n_reads; r += gridDim.x * blockDim.x) {
+    uint32_t at = a.begin[r];
+    const uint32_t first = at;
+    const bool na = dist_rows_of(a, r, [&](uint32_t i) {
+      const uint32_t se = a.rec_slot[i] & 0x7FFFFFFFu, units = fixed5_units(a.rec_d[i]);
+      if (a.row_bytes == 4) static_cast<uint32_t*>(a.rows)[at] = a.leaf_rank[se] << 16 | (units < 0xFFFFu ? units : 0xFFFFu);
+      else static_cast<uint2*>(a.rows)[at] = make_uint2(se, units);
+      ++at;
+    });
+    a.out_begin[r] = first | (na ? 0x80000000u : 0u);
+    if (r == a.n_reads - 1) a.out_begin[a.n_reads] = at;
   }
 }
 
@@ -994,10 +951,10 @@ static int enqueue(krepp_batch* b)
     d.dist_max = b->p.dist_max; d.chisq_value = b->p.chisq;
     d.cnt = b->d_dist_cnt; d.begin = b->d_dist_begin; d.out_begin = b->d_dist_out_begin; d.rows = b->d_dist_rows; d.row_bytes = b->dist_row_bytes;
     if (b->n_reads) {
-      dist_count_kernel<<<ix->sms * 8, 256, 0, s>>>(d);
+      dist_count_kernel<<<ix->sms * 8, 128, 0, s>>>(d);
       CU(cudaGetLastError());
       CU(exclusive_scan(b->d_dist_cnt, b->n_reads, b->d_dist_partials, b->d_dist_begin, nullptr, s));
-      dist_emit_kernel<<<ix->sms * 8, 256, 0, s>>>(d);
+      dist_emit_kernel<<<ix->sms * 8, 128, 0, s>>>(d);
       CU(cudaGetLastError());
       b->launches += 5;
     }

@@ -144,9 +144,10 @@ __global__ void __launch_bounds__(128, 8) solve_kernel(const SolveArgs a, const 
 
 // One thread per read: closest + per-leaf strand choice, in the fixed visiting order (forward leaves by ascending se,
 // then reverse leaves by ascending se; `<=` kept so the last tied entry wins -- SURVEY.md section 0 fact 6).
-__device__ void merge_read_serial(const SolveArgs& a, uint32_t r)
+__global__ void __launch_bounds__(128) merge_kernel(const SolveArgs a)
 {
-  {
+  if (a.counters[2] & kErrRedo) return; // the host grows the buffers and runs the batch again
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < a.n_reads; r += gridDim.x * blockDim.x) {
     const uint32_t b = a.rec_begin[r], n = a.rec_count[r];
     int32_t cl = -1;
     double best = DBL_MAX;
@@ -183,55 +184,6 @@ __device__ void merge_read_serial(const SolveArgs& a, uint32_t r)
     }
     if (a.nsel) a.nsel[r] = nsel;
     a.closest[r] = cl;
-  }
-}
-
-// A warp per read, a record per lane (reads with more than 32 records: the serial walk above on lane 0).  The closest is the
-// solved record with the smallest distance, the LAST of them in visiting order when tied (`<=` in the walk); a reference both
-// strands hit keeps the reverse record unless the forward one is strictly better (or as good with more matches); the closest's
-// reference keeps the closest.
-__global__ void __launch_bounds__(256) merge_kernel(const SolveArgs a)
-{
-  if (a.counters[2] & kErrRedo) return; // the host grows the buffers and runs the batch again
-  const uint32_t lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t r = warp; r < a.n_reads; r += nwarps) {
-    const uint32_t b = a.rec_begin[r], n = a.rec_count[r];
-    if (n > 32) { if (lane == 0) merge_read_serial(a, r); continue; }
-    const bool have = lane < n;
-    const uint32_t slot = have ? a.rec_slot[b + lane] : 0xFFFFFFFFu, se = slot & 0x7FFFFFFFu;
-    uint32_t flags = have ? a.rec_flags[b + lane] : 0u;
-    const bool solved = have && (flags & 1u);
-    const double d = have ? a.rec_d[b + lane] : DBL_MAX;
-    const uint32_t match = have ? a.rec_match[b + lane] : 0u;
-    // closest
-    double best = solved ? d : DBL_MAX;
-    for (int o = 16; o; o >>= 1) best = fmin(best, __shfl_xor_sync(0xFFFFFFFFu, best, o));
-    const uint32_t tie = __ballot_sync(0xFFFFFFFFu, solved && d <= best);
-    const int32_t cl = tie ? (int32_t)(b + 31u - __clz(tie)) : -1;
-    // per reference: the lane's partner is the record of the other strand with the same se, if any
-    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, se) & ~(1u << lane);
-    const int partner = (have && peers) ? __ffs(peers) - 1 : (int)lane;
-    const double dp = __shfl_sync(0xFFFFFFFFu, d, partner);
-    const uint32_t mp = __shfl_sync(0xFFFFFFFFu, match, partner);
-    const bool sp = __shfl_sync(0xFFFFFFFFu, (int)solved, partner) != 0;
-    bool sel;
-    if (!have) sel = false;
-    else if (partner == (int)lane) sel = solved;
-    else if (!(slot >> 31)) { // forward record i, reverse partner j (ref: fwd_wins = dr > df || (dr == df && match_j < match_i))
-      sel = sp ? ((dp > d) || (dp == d && mp < match)) : solved;
-    } else {                  // reverse record j, forward partner i
-      sel = solved && !((d > dp) || (d == dp && match < mp));
-    }
-    const uint32_t nsel = __popc(__ballot_sync(0xFFFFFFFFu, sel)); // one selected record per reference
-    uint32_t nf = flags;
-    if (sel) nf |= 2u;
-    if (cl >= 0) {
-      const uint32_t se_cl = __shfl_sync(0xFFFFFFFFu, se, (int)((uint32_t)cl - b));
-      if (have && se == se_cl) nf &= ~2u;
-      if (b + lane == (uint32_t)cl) nf |= 2u | 4u;
-    }
-    if (have && nf != flags) a.rec_flags[b + lane] = nf;
-    if (lane == 0) { if (a.nsel) a.nsel[r] = nsel; a.closest[r] = cl; }
   }
 }
 
@@ -825,7 +777,7 @@ cudaError_t launch_solve(const SolveArgs& a, const LlhTables& tab, int sms, cuda
   else solve_kernel<kMaxTh + 1><<<grid, 128, 0, stream>>>(a, tab);
   if (clk) clk->tick("solve_kernel", stream);
   if (a.memo_mask) alias_kernel<<<sms * 8, 256, 0, stream>>>(a);
-  merge_kernel<<<sms * 8, 256, 0, stream>>>(a);
+  merge_kernel<<<sms * 16, 128, 0, stream>>>(a);
   if (a.want_chisq) chisq_kernel<<<sms * 16, 128, 0, stream>>>(a, tab);
   if (clk) clk->tick(a.want_chisq ? "alias_kernel+merge_kernel+chisq_kernel" : "alias_kernel+merge_kernel", stream);
   return cudaGetLastError();
