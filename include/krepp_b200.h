@@ -354,6 +354,46 @@ int krepp_sequence_rho(const krepp_index_t* ix, const char* bases, const uint64_
 int krepp_sketch_write(const krepp_index_t* ix, const char* bases, const uint64_t* offsets, uint32_t n_seqs, const char* out_path,
                        uint64_t* n_kmers, double* rho);
 
+/* `krepp index` (IndexMultiple::build_index / build_for_subtree / save_index, src/krepp.cpp:164-309): a whole library from
+ * its reference genomes.  The reference builds a leaf table per genome and unions the tables up the guide tree, giving every
+ * k-mer a colour -- the set of references that hold it -- as a DAG of pairs over the tree's nodes (DynHT::union_row
+ * src/table.cpp:214-234, Record::add_subset src/record.cpp:82-113, CRecord src/record.cpp:156-175).  Here:
+ *   krepp_builder_add_genome   GPU: the genome's leaf table (krepp_extract_mers) stays in HBM; its rho (krepp_sequence_rho).
+ *   krepp_builder_union        GPU: every (k-mer, reference) pair of the library in one array, one stable radix sort by
+ *                              (row, encoding); a run of equal keys is one k-mer with its references in leaf order; runs are
+ *                              hashed and grouped into the DISTINCT reference sets (verified element by element, never trusted
+ *                              to the hash).  Leaves the host with: per k-mer its key and the id of its set; per set its leaves.
+ *   krepp_builder_write        host: each distinct set is decomposed along the guide tree (a set that is a whole subtree is the
+ *                              tree node itself, as in the reference; otherwise pairs, shared between sets), colour ids are
+ *                              numbered, and the seven files of src/krepp.cpp:206-246 are written in the reference's format.
+ * The result is the reference's library up to the numbering of colours above the tree nodes (which the reference itself does
+ * not fix from run to run): metadata-*, inc-*, the encoding column of cmer-*, reflist-*, tree-* and
+ * rho are the reference's bytes, and every k-mer's colour expands to the same references.
+ * geom: a geometry handle (krepp_geometry_open); on a GPU for add_genome / union, any for set_union / write.
+ * nwk_text: the guide tree (-t), written to tree-* verbatim; NULL = no tree: the balanced tree the reference generates over
+ * the names (Node::generate_tree src/phytree.cpp:217-253) and no tree-* file.  names: the reference ids of input_map.tsv in
+ * file order (reflist-*).  A name the tree lacks is never visited and a leaf without a genome stays empty, as in the reference. */
+typedef struct krepp_builder krepp_builder_t;
+int krepp_builder_create(const krepp_index_t* geom, const char* nwk_text, const char* const* names, uint32_t n_names, krepp_builder_t** out);
+void krepp_builder_destroy(krepp_builder_t* b);
+/* 1 when `name` is a leaf of the build tree (its genome will be used), 0 when not (the reference skips it), < 0 on error */
+int krepp_builder_has_leaf(const krepp_builder_t* b, const char* name);
+int krepp_builder_add_genome(krepp_builder_t* b, const char* name, const char* bases, const uint64_t* offsets, uint32_t n_seqs,
+                             uint64_t* n_keys, double* rho);
+int krepp_builder_union(krepp_builder_t* b, uint64_t* n_kmers, uint64_t* n_sets);
+/* The union handed in by the caller instead (host arrays, copied): n_kmers keys (row << 32 | encoding, ascending, distinct),
+ * the set id of each, and the sets as CSR over leaf RANKS (leaves of the build tree in ascending post-order number, ascending
+ * within a set); rho per leaf rank (0 where a leaf has no genome).  What krepp_builder_union leaves behind, for callers that
+ * computed the union elsewhere and for the host-side tests. */
+int krepp_builder_set_union(krepp_builder_t* b, uint64_t n_kmers, const uint64_t* keys, const uint32_t* set_of, uint64_t n_sets,
+                            const uint64_t* set_begin, const uint32_t* set_leaves, const double* leaf_rho);
+/* Leaf rank of a reference in the build tree (0xffffffff when the tree lacks it) and the number of leaves. */
+uint32_t krepp_builder_leaf_rank(const krepp_builder_t* b, const char* name);
+uint32_t krepp_builder_nleaves(const krepp_builder_t* b);
+/* Writes the library into index_dir (created when missing) with the suffix -m{m}r{r}-{frac|no_frac} (src/krepp.cpp:586-589).
+ * seed: what metadata-*.txt reports (src/krepp.cpp:192).  *n_subsets: colour ids incl. the null id (crecord's nsubsets). */
+int krepp_builder_write(krepp_builder_t* b, const char* index_dir, uint32_t seed, uint64_t* n_kmers, uint32_t* n_subsets);
+
 /* -------------------------------------------------------------------------------------------------- host I/O layer
  * The steps immediately either side of the GPU path.  Pure host code: usable
  * without a device (the index handle may have been opened with KREPP_DEVICE_NONE). */

@@ -177,6 +177,18 @@ def load_library():
     L.krepp_shard_join.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
     L.krepp_shard_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
     L.krepp_extract_mers.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.krepp_builder_create.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_char_p), C.c_uint32, C.POINTER(C.c_void_p)]
+    L.krepp_builder_destroy.argtypes = [C.c_void_p]
+    L.krepp_builder_destroy.restype = None
+    L.krepp_builder_has_leaf.argtypes = [C.c_void_p, C.c_char_p]
+    L.krepp_builder_leaf_rank.argtypes = [C.c_void_p, C.c_char_p]
+    L.krepp_builder_leaf_rank.restype = C.c_uint32
+    L.krepp_builder_nleaves.argtypes = [C.c_void_p]
+    L.krepp_builder_nleaves.restype = C.c_uint32
+    L.krepp_builder_add_genome.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
+    L.krepp_builder_union.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.krepp_builder_set_union.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.krepp_builder_write.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
     L.krepp_reader_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
     L.krepp_reader_close.argtypes = [C.c_void_p]
     L.krepp_reader_set_threads.argtypes = [C.c_void_p, C.c_uint32]
@@ -303,6 +315,64 @@ class Index:
         buf = C.create_string_buffer(n + 1)
         L.krepp_index_jplace_tree(self._h, buf, n + 1)
         return buf.value.decode()
+
+
+class LibraryBuilder:
+    """krepp_builder_*: `krepp index` (IndexMultiple::build_index / save_index, ref src/krepp.cpp:164-309).  geometry: an
+    Index.geometry handle (on a GPU for add_genome / union); nwk: the guide tree text or None (the reference's generated tree
+    over `names`); names: reference ids in input_map.tsv order."""
+
+    def __init__(self, geometry: "Index", nwk: str | None, names):
+        L = load_library()
+        self._h = C.c_void_p()
+        self._geometry = geometry  # the builder borrows the handle
+        enc = [n.encode() for n in names]
+        arr = (C.c_char_p * max(len(enc), 1))(*enc)
+        _check(L.krepp_builder_create(geometry._h, None if nwk is None else nwk.encode(), arr, len(enc), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().krepp_builder_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    @property
+    def nleaves(self) -> int:
+        return load_library().krepp_builder_nleaves(self._h)
+
+    def leaf_rank(self, name: str) -> int | None:
+        r = load_library().krepp_builder_leaf_rank(self._h, name.encode())
+        return None if r == 0xFFFFFFFF else r
+
+    def add_genome(self, name: str, seqs) -> tuple[int, float]:
+        """GPU: the genome's leaf table (kept in HBM) and rho; returns (keys in the table, rho)."""
+        bases, offs = pack_reads(list(seqs))
+        bases = np.ascontiguousarray(bases) if len(bases) else np.zeros(1, np.uint8)
+        n, rho = C.c_uint64(), C.c_double()
+        _check(load_library().krepp_builder_add_genome(self._h, name.encode(), bases.ctypes.data, offs.ctypes.data, len(offs) - 1, C.byref(n), C.byref(rho)))
+        return n.value, rho.value
+
+    def union(self) -> tuple[int, int]:
+        """GPU: the union of the leaf tables; returns (distinct k-mers, distinct reference sets)."""
+        n, s = C.c_uint64(), C.c_uint64()
+        _check(load_library().krepp_builder_union(self._h, C.byref(n), C.byref(s)))
+        return n.value, s.value
+
+    def set_union(self, keys: np.ndarray, set_of: np.ndarray, set_begin: np.ndarray, set_leaves: np.ndarray, leaf_rho: np.ndarray | None = None):
+        """krepp_builder_set_union: a union computed by the caller (host arrays)."""
+        keys = np.ascontiguousarray(keys, np.uint64); set_of = np.ascontiguousarray(set_of, np.uint32)
+        set_begin = np.ascontiguousarray(set_begin, np.uint64); set_leaves = np.ascontiguousarray(set_leaves, np.uint32)
+        rho = None if leaf_rho is None else np.ascontiguousarray(leaf_rho, np.float64)
+        assert rho is None or len(rho) == self.nleaves
+        _check(load_library().krepp_builder_set_union(self._h, len(keys), keys.ctypes.data, set_of.ctypes.data, len(set_begin) - 1, set_begin.ctypes.data,
+                                                      set_leaves.ctypes.data if len(set_leaves) else None, None if rho is None else rho.ctypes.data))
+
+    def write(self, index_dir: str, seed: int = 0) -> tuple[int, int]:
+        """Host: colours along the tree and the library files; returns (k-mers, colour ids incl. the null id)."""
+        n, s = C.c_uint64(), C.c_uint32()
+        _check(load_library().krepp_builder_write(self._h, os.fsencode(index_dir), seed, C.byref(n), C.byref(s)))
+        return n.value, s.value
 
 
 def plan_shards(index_dir: str, budget_bytes: int, device: int = 0) -> dict:

@@ -325,6 +325,23 @@ std::vector<BitRun> runs_of(uint64_t mask)
 
 } // namespace
 
+std::string generated_newick(const std::vector<std::string>& names)
+{
+  std::string out;
+  struct Gen {
+    const std::vector<std::string>& nm; std::string& out;
+    void run(size_t lo, size_t hi)
+    { // a range of one name is a leaf; a longer one gets the SECOND half as its first child; every branch length is 1
+      if (hi - lo == 1) { out += '\''; for (char c : nm[lo]) { if (c == '\'') out += '\''; out += c; } out += '\''; }
+      else { const size_t half = lo + (hi - lo) / 2; out += '('; run(half, hi); out += ','; run(lo, half); out += ')'; }
+      out += ":1";
+    }
+  } gen{names, out};
+  if (!names.empty()) gen.run(0, names.size());
+  out += ';';
+  return out;
+}
+
 static std::vector<uint32_t> split_rows(const std::vector<uint64_t>& inc, uint64_t nkmers, uint32_t nrows, uint32_t nshards)
 { // shard g starts at the first row whose bucket ends beyond g/nshards of the entries: contiguous row ranges of (nearly) equal
   // cmer bytes, the same on every rank because they depend on inc-* alone
@@ -444,18 +461,7 @@ std::string read_partial(const std::string& dir, Partial& q)
       at = e + 1;
     }
     if (names.empty()) return "Unable to open reference list file for an index without a tree.";
-    q.newick.clear();
-    struct Gen {
-      const std::vector<std::string>& nm; std::string& out;
-      void run(size_t lo, size_t hi)
-      { // a range of one name is a leaf; a longer one gets the SECOND half as its first child; every branch length is 1
-        if (hi - lo == 1) { out += '\''; for (char c : nm[lo]) { if (c == '\'') out += '\''; out += c; } out += '\''; }
-        else { const size_t half = lo + (hi - lo) / 2; out += '('; run(half, hi); out += ','; run(lo, half); out += ')'; }
-        out += ":1";
-      }
-    } gen{names, q.newick};
-    gen.run(0, names.size());
-    q.newick += ';';
+    q.newick = generated_newick(names);
   }
   { // ---- inc, and the size of cmer
     std::ifstream f(dir + "/inc" + sfx, std::ios::binary);

@@ -69,6 +69,10 @@ struct HostTree {
 // library (ref LSHF::get_random_positions src/lshf.cpp:125-147); seeded = --seed was given.
 void lsh_positions(uint32_t k, uint32_t h, bool seeded, uint32_t seed, std::vector<uint8_t>& ppos, std::vector<uint8_t>& npos);
 
+// The balanced tree the reference generates over a list of reference ids when a library has no guide tree (Node::generate_tree
+// ref src/phytree.cpp:217-253: halves, the SECOND half first, every branch length 1), as Newick for HostTree::parse.
+std::string generated_newick(const std::vector<std::string>& names);
+
 struct HostIndex {
   uint32_t k = 0, w = 0, h = 0, m = 0, r = 0, frac = 0, nrows = 0;
   uint64_t nkmers = 0;

@@ -20,6 +20,7 @@
 #include "../../include/krepp_b200.h"
 
 #include "device.cuh"
+#include "builder.hpp"
 #include "handles.hpp"
 #include "match_common.cuh"
 
@@ -266,7 +267,7 @@ namespace {
 // when `est` is given, the two HyperLogLog estimates of RSeq::extract_mers summed over the sequences in order (n1: distinct
 // valid k-mers, n2: distinct minimizers; ref src/rqseq.cpp:63-64,107-108,117,142-143), whose ratio is rho (src/rqseq.hpp:79).
 int extract_impl(const krepp_index_t* ix, const char* bases, const uint64_t* offsets, uint32_t n_seqs, uint64_t* keys, uint64_t cap, uint64_t* n_keys,
-                 std::vector<uint64_t>* keys_vec, double* est)
+                 std::vector<uint64_t>* keys_vec, double* est, unsigned long long** keep_dev = nullptr)
 {
   if (ix->device == KREPP_DEVICE_NONE) return set_error(KREPP_ERR_CUDA, "the index-side kernels need a handle opened on a GPU (there is no CPU fallback)");
   const HostIndex& h = ix->host;
@@ -362,6 +363,11 @@ int extract_impl(const krepp_index_t* ix, const char* bases, const uint64_t* off
       }
     }
     *n_keys = nsel;
+    if (keep_dev) { // the table stays on the device for the library builder (builder.cu), in an allocation of its own size
+      *keep_dev = nullptr;
+      if (nsel) { MZ_CU(cudaMalloc(keep_dev, 8ull * nsel)); MZ_CU(cudaMemcpy(*keep_dev, d_uniq, 8ull * nsel, cudaMemcpyDeviceToDevice)); }
+      goto done;
+    }
     if (keys_vec) { keys_vec->resize(nsel); if (nsel) MZ_CU(cudaMemcpy(keys_vec->data(), d_uniq, 8ull * nsel, cudaMemcpyDeviceToHost)); goto done; }
     if (nsel > cap) { rc = cap ? set_error(KREPP_ERR_CAPACITY, "krepp_extract_mers: %llu keys but room for %llu", (unsigned long long)nsel, (unsigned long long)cap) : KREPP_OK; goto done; }
     if (nsel) MZ_CU(cudaMemcpy(keys, d_uniq, 8ull * nsel, cudaMemcpyDeviceToHost));
@@ -372,6 +378,13 @@ done:
 }
 
 } // namespace
+
+namespace krepp {
+int extract_to_device(const krepp_index* ix, const char* bases, const uint64_t* offsets, uint32_t n_seqs, unsigned long long** d_keys, uint64_t* n_keys, double est[2])
+{
+  return extract_impl(ix, bases, offsets, n_seqs, nullptr, 0, n_keys, nullptr, est, d_keys);
+}
+} // namespace krepp
 
 extern "C" int krepp_extract_mers(const krepp_index_t* ix, const char* bases, const uint64_t* offsets, uint32_t n_seqs, uint64_t* keys, uint64_t cap,
                                   uint64_t* n_keys)

@@ -1,0 +1,157 @@
+"""CPU: the host stage of `krepp index` -- krepp_builder_set_union / krepp_builder_write: reference sets ->
+colours along the guide tree -> the library files -- against libraries built by the UNMODIFIED reference (`oracle/_ref/krepp
+index`) from the same genomes.  The union handed in is computed here from the oracle's leaf tables (test plumbing; on the GPU box
+krepp_builder_add_genome / krepp_builder_union compute it, tests/test_gpu_index_build.py).  The library written must be the
+reference's up to the numbering of the colours above the tree nodes, and the reference's own `krepp dist` must print the same
+lines from either."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import conftest
+import krepp_b200
+import oracle_lib as O
+from conftest import needs_ref
+from libraries import assert_same_library, colour_leaves, numpy_union, read_library
+from test_seek_cpu import fasta_seqs
+from variants import SMALL, TREELESS, VARIANTS, build
+
+REF = os.path.join(conftest.REF_DIR, "krepp")
+NONE = -1  # KREPP_DEVICE_NONE
+
+
+def names_and_paths():
+    rows = [l.rstrip("\n").split("\t") for l in open(os.path.join(SMALL, "input_map.tsv")) if l.strip()]
+    return [r[0] for r in rows], {r[0]: os.path.join(SMALL, r[1]) for r in rows}
+
+
+def host_build(ref_lib: dict, out_dir: str, nwk: str | None, names, paths, seed=None):
+    """The library of the golden genomes under the geometry of `ref_lib`, written by krepp_builder_write from a numpy union of
+    the oracle's leaf tables."""
+    g = krepp_b200.Index.geometry(ref_lib["k"], ref_lib["w"], ref_lib["h"], ref_lib["m"], ref_lib["r"], bool(ref_lib["frac"]), seed=seed, device=NONE)
+    b = krepp_b200.LibraryBuilder(g, nwk, names)
+    tables, rho = {}, np.zeros(b.nleaves)
+    for nm in names:
+        rank = b.leaf_rank(nm)
+        if rank is None:
+            continue
+        keys, rh = O.oracle_sketch_table(ref_lib, fasta_seqs(paths[nm]))
+        tables[rank], rho[rank] = keys, rh
+    keys, set_of, set_begin, set_leaves = numpy_union(tables)
+    b.set_union(keys, set_of, set_begin, set_leaves, rho)
+    nk, nsub = b.write(out_dir)
+    b.close()
+    g.close()
+    return nk, nsub
+
+
+def ref_dist(index_dir, extra=()):
+    out = subprocess.run([REF, "dist", "-i", index_dir, "-q", os.path.join(SMALL, "reads.fq"), *extra], capture_output=True, text=True, check=True).stdout
+    return sorted(l for l in out.splitlines() if not l.startswith("#"))
+
+
+@needs_ref
+@pytest.mark.parametrize("label,args", [("default_k21", ["-k", "21", "-w", "25", "-h", "7"])] + VARIANTS[:3], ids=lambda v: v if isinstance(v, str) else "")
+def test_written_library_equals_the_reference(label, args, tmp_path_factory, tmp_path):
+    ref_dir = build("lib_" + label, args, tmp_path_factory.getbasetemp())
+    ref = read_library(ref_dir)
+    names, paths = names_and_paths()
+    nwk = open(os.path.join(SMALL, "tree.nwk")).read()
+    mine_dir = str(tmp_path / "index")
+    nk, nsub = host_build(ref, mine_dir, nwk, names, paths)
+    mine = read_library(mine_dir)
+    assert nk == ref["nkmers"] and nsub == mine["nsubsets"]
+    n_mine, n_ref = assert_same_library(mine, ref)
+    assert n_mine <= n_ref  # pairs are shared between sets; the reference's record may hold sets only met on the way up
+    txt = open(os.path.join(mine_dir, "metadata" + mine["sfx"] + ".txt")).read()
+    assert f"total_num_kmers: {nk}\n" in txt and f"nrows: {ref['nrows']}\n" in txt
+    # the reference reads it and answers as it does from its own
+    assert ref_dist(mine_dir) == ref_dist(ref_dir)
+    assert ref_dist(mine_dir, ["--hdist-th", "3"]) == ref_dist(ref_dir, ["--hdist-th", "3"])  # (no --filter: its test is against a tie-dependent closest)
+    # and so does this implementation's loader (host image only)
+    a, b = krepp_b200.Index(mine_dir, device=NONE), krepp_b200.Index(ref_dir, device=NONE)
+    assert a.info.nkmers == b.info.nkmers and a.info.nnodes == b.info.nnodes
+    ca, cb = a.host_checksums(), b.host_checksums()
+    assert ca[1] == cb[1]  # the offsets; the other sums weigh colour ids, which are numbered differently above the tree nodes
+    a.close(); b.close()
+
+
+@needs_ref
+def test_written_library_without_a_guide_tree(tmp_path_factory, tmp_path):
+    label, args = TREELESS
+    ref_dir = build("lib_" + label, args, tmp_path_factory.getbasetemp(), with_tree=False)
+    ref = read_library(ref_dir)
+    assert ref["tree"] is None
+    names, paths = names_and_paths()
+    mine_dir = str(tmp_path / "index")
+    host_build(ref, mine_dir, None, names, paths)
+    mine = read_library(mine_dir)
+    assert_same_library(mine, ref)
+    assert ref_dist(mine_dir) == ref_dist(ref_dir)
+
+
+def random_sets(rng, nleaves, n_sets):
+    sets = {tuple(range(nleaves))}
+    while len(sets) < n_sets:
+        k = int(rng.integers(1, nleaves + 1))
+        sets.add(tuple(sorted(int(x) for x in rng.choice(nleaves, k, replace=False))))
+    return sorted(sets)
+
+
+@pytest.mark.parametrize("nwk", ["((A:1,B:1,C:1,D:1)x:1,(E:1,(F:1,G:1,H:1):1):1,I:1);", "(A,(B,(C,(D,(E,(F,(G,(H,I))))))));",
+                                 "(((A,B),(C,D)),((E,F),(G,(H,I))));"], ids=["multifurcating", "caterpillar", "balanced"])
+def test_colours_expand_to_their_sets_on_any_tree(nwk, tmp_path):
+    """Every distinct reference set gets a colour that expands to exactly that set; a whole subtree is the tree node itself; pairs
+    are shared.  (The reference cannot pin multifurcating trees: it drops references there, see library_writer.cpp.)"""
+    rng = np.random.default_rng(5)
+    names = list("ABCDEFGHI")
+    g = krepp_b200.Index.geometry(21, 25, 7, 4, 1, True, device=NONE)
+    b = krepp_b200.LibraryBuilder(g, nwk, names)
+    assert b.nleaves == 9 and b.leaf_rank("nope") is None
+    sets = random_sets(rng, 9, 150)
+    set_begin = np.zeros(len(sets) + 1, np.uint64)
+    set_begin[1:] = np.cumsum([len(s) for s in sets])
+    set_leaves = np.array([x for s in sets for x in s], np.uint32)
+    keys = (np.arange(len(sets), dtype=np.uint64) * 7 + 3) << np.uint64(20)  # ascending, spread over rows
+    b.set_union(keys, np.arange(len(sets), dtype=np.uint32), set_begin, set_leaves, np.linspace(0.1, 0.2, 9))
+    out = str(tmp_path / "index")
+    nk, nsub = b.write(out)
+    lib = read_library(out)
+    assert nk == len(sets) and nsub == lib["nsubsets"]
+    exp = colour_leaves(lib)
+    ix = krepp_b200.Index(out, device=NONE)  # leaf rank -> node number through this implementation's own tree
+    leaf_se = [se for se in range(1, ix.info.nnodes + 1) if ix.node_name(se) in names]
+    rank_of = {nm: b.leaf_rank(nm) for nm in names}
+    se_of_rank = {rank_of[ix.node_name(se)]: se for se in leaf_se}
+    for s, colour in zip(sets, lib["se"]):
+        assert exp[int(colour)] == frozenset(se_of_rank[r] for r in s), s
+    assert exp[ix.info.root_se] == frozenset(leaf_se)                    # the set of all references is the root
+    assert int(lib["se"][sets.index(tuple(range(9)))]) == ix.info.root_se
+    assert lib["rho"][se_of_rank[0]] == 0.1 and lib["rho"][0] == 0.0
+    # shared pairs: far fewer colours than the sum of the set sizes
+    assert lib["nsubsets"] < ix.info.nnodes + 1 + sum(len(s) - 1 for s in sets)
+    ix.close(); b.close(); g.close()
+
+
+def test_builder_argument_errors(tmp_path):
+    g = krepp_b200.Index.geometry(21, 25, 7, 4, 1, True, device=NONE)
+    with pytest.raises(krepp_b200.KreppError, match="two leaves named"):
+        krepp_b200.LibraryBuilder(g, "((A,B),A);", ["A", "B"])
+    with pytest.raises(krepp_b200.KreppError):
+        krepp_b200.LibraryBuilder(g, "((A,B);", ["A", "B"])
+    b = krepp_b200.LibraryBuilder(g, "((A,B),C);", ["A", "B", "C"])
+    with pytest.raises(krepp_b200.KreppError, match="no union yet"):
+        b.write(str(tmp_path / "x"))
+    with pytest.raises(krepp_b200.KreppError, match="GPU"):  # no CPU fallback for the device stage
+        b.add_genome("A", [b"ACGT" * 50])
+    with pytest.raises(krepp_b200.KreppError, match="GPU"):
+        b.union()
+    b.set_union(np.array([5, 4], np.uint64), np.zeros(2, np.uint32), np.array([0, 1], np.uint64), np.array([0], np.uint32))
+    with pytest.raises(krepp_b200.KreppError, match="ascending"):
+        b.write(str(tmp_path / "x"))
+    b.set_union(np.array([4, 5], np.uint64), np.zeros(2, np.uint32), np.array([0, 2], np.uint64), np.array([1, 0], np.uint32))
+    with pytest.raises(krepp_b200.KreppError, match="ascending list of leaf ranks"):
+        b.write(str(tmp_path / "x"))
+    b.close(); g.close()
