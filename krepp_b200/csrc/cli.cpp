@@ -42,7 +42,7 @@ struct Options {
   bool multi = true, filter = false, summarize = false, tabular = false, verbose = false, seed_set = false;
   // sketch (ref src/krepp.hpp:35-46 set_sketch_defaults, src/krepp.cpp:516-540)
   uint32_t sk_k = 26, sk_w = 32, sk_h = 10, sk_m = 4, sk_r = 1, sdust_t = 0, sdust_w = 0;
-  bool sk_frac = true, sk_w_set = false;
+  bool sk_frac = true, sk_w_set = false, sk_k_set = false, sk_h_set = false;
   // additions of this implementation
   std::vector<int> devices;
   bool shard_index = false; // --shard-index: every device holds one bucket-range shard of the table (SURVEY.md 8e mode B)
@@ -55,6 +55,7 @@ const char* kUsage =
   "Usage: krepp_b200 [--num-threads N] [--seed S] [--verbose] {dist|place} -i INDEX_DIR -q QUERY [options]\n"
   "       krepp_b200 [--num-threads N] seek -i,--sketch-path SKETCH_FILE -q QUERY [-o PATH] [--hdist-th N]\n"
   "       krepp_b200 [--seed S] sketch -i,--input-file FASTA -o,--output-path SKETCH_FILE [-k 26] [-w k+6] [-h k-16] [-m 4] [-r 1] [--frac/--no-frac]\n"
+  "       krepp_b200 [--num-threads N] [--seed S] index -i,--input-file MAP.tsv -o,--index-dir DIR [-t,--nwk-file NWK] [-k 29] [-w k+6] [-h k-16] [-m 4] [-r 1] [--frac/--no-frac]\n"
   "  common:  -q,--query PATH   -i,--index-dir DIR   -o,--output-path PATH   --hdist-th N [4]   --chisq X [2.706]\n"
   "           --summarize/--no-summarize [false]\n"
   "  dist:    --dist-max X   --multi/--no-multi [true]   --filter/--no-filter [false]\n"
@@ -87,22 +88,24 @@ Options parse(int argc, char** argv)
   for (size_t i = 0; i < a.size(); ++i) {
     std::string k = a[i];
     if (k.rfind("--", 0) == 0 && k.find('=') != std::string::npos) k = k.substr(0, k.find('='));
-    if (k == "dist" || k == "place" || k == "seek" || k == "sketch") { if (!o.sub.empty()) error_exit("Only one subcommand may be given."); o.sub = k; }
-    else if (k == "index" || k == "inspect") error_exit("Subcommand '" + k + "' is not part of the GPU query path; use the reference krepp binary for it.");
+    const bool build_sub = o.sub == "sketch" || o.sub == "index"; // the subcommands that set up a new LSH geometry
+    if (k == "dist" || k == "place" || k == "seek" || k == "sketch" || k == "index") { if (!o.sub.empty()) error_exit("Only one subcommand may be given."); o.sub = k; }
+    else if (k == "inspect") error_exit("Subcommand '" + k + "' is not part of the GPU query path; use the reference krepp binary for it.");
     else if (k == "--help") { fputs(kUsage, stdout); exit(0); }
     else if (k == "--verbose") o.verbose = true;
     else if (k == "--no-verbose") o.verbose = false;
     else if (k == "--seed") { o.seed = (uint32_t)strtoul(need(i, k).c_str(), nullptr, 10); o.seed_set = true; }
-    else if (o.sub == "sketch" && (k == "-i" || k == "--input-file")) o.index_dir = need(i, k);
-    else if (o.sub == "sketch" && (k == "-k" || k == "--kmer-len")) { o.sk_k = (uint32_t)atoi(need(i, k).c_str()); if (o.sk_k < 19 || o.sk_k > 31) error_exit("--kmer-len: Value " + std::to_string(o.sk_k) + " not in range [19 - 31]"); }
-    else if (o.sub == "sketch" && (k == "-w" || k == "--win-len")) { o.sk_w = (uint32_t)atoi(need(i, k).c_str()); o.sk_w_set = true; }
-    else if (o.sub == "sketch" && (k == "-h" || k == "--num-positions")) o.sk_h = (uint32_t)atoi(need(i, k).c_str());
-    else if (o.sub == "sketch" && (k == "-m" || k == "--modulo-lsh")) { o.sk_m = (uint32_t)atoi(need(i, k).c_str()); if (!o.sk_m) error_exit("--modulo-lsh: Number less or equal to 0"); }
-    else if (o.sub == "sketch" && (k == "-r" || k == "--residue-lsh")) o.sk_r = (uint32_t)atoi(need(i, k).c_str());
-    else if (o.sub == "sketch" && k == "--frac") o.sk_frac = true;
-    else if (o.sub == "sketch" && k == "--no-frac") o.sk_frac = false;
-    else if (o.sub == "sketch" && k == "--sdust-t") o.sdust_t = (uint32_t)atoi(need(i, k).c_str());
-    else if (o.sub == "sketch" && k == "--sdust-w") o.sdust_w = (uint32_t)atoi(need(i, k).c_str());
+    else if (build_sub && (k == "-i" || k == "--input-file")) o.index_dir = need(i, k);
+    else if (o.sub == "index" && (k == "-o" || k == "--index-dir")) o.output_path = need(i, k);
+    else if (build_sub && (k == "-k" || k == "--kmer-len")) { o.sk_k = (uint32_t)atoi(need(i, k).c_str()); o.sk_k_set = true; if (o.sk_k < 19 || o.sk_k > 31) error_exit("--kmer-len: Value " + std::to_string(o.sk_k) + " not in range [19 - 31]"); }
+    else if (build_sub && (k == "-w" || k == "--win-len")) { o.sk_w = (uint32_t)atoi(need(i, k).c_str()); o.sk_w_set = true; }
+    else if (build_sub && (k == "-h" || k == "--num-positions")) { o.sk_h = (uint32_t)atoi(need(i, k).c_str()); o.sk_h_set = true; }
+    else if (build_sub && (k == "-m" || k == "--modulo-lsh")) { o.sk_m = (uint32_t)atoi(need(i, k).c_str()); if (!o.sk_m) error_exit("--modulo-lsh: Number less or equal to 0"); }
+    else if (build_sub && (k == "-r" || k == "--residue-lsh")) o.sk_r = (uint32_t)atoi(need(i, k).c_str());
+    else if (build_sub && k == "--frac") o.sk_frac = true;
+    else if (build_sub && k == "--no-frac") o.sk_frac = false;
+    else if (build_sub && k == "--sdust-t") o.sdust_t = (uint32_t)atoi(need(i, k).c_str());
+    else if (build_sub && k == "--sdust-w") o.sdust_w = (uint32_t)atoi(need(i, k).c_str());
     else if (k == "--num-threads") o.num_threads = (uint32_t)strtoul(need(i, k).c_str(), nullptr, 10);
     else if (k == "-q" || k == "--query") o.query = need(i, k);
     else if (k == "-i" || k == "--index-dir" || k == "--sketch-path") o.index_dir = need(i, k);
@@ -130,6 +133,19 @@ Options parse(int argc, char** argv)
     else error_exit("The following argument was not expected: " + a[i]);
   }
   if (o.sub.empty()) { fputs(kUsage, stderr); error_exit("A subcommand is required"); }
+  if (o.sub == "index") { // ref src/krepp.cpp:560-591 (defaults: set_index_defaults src/krepp.hpp:47-58)
+    if (o.index_dir.empty()) error_exit("--input-file is required");
+    if (o.output_path.empty()) error_exit("--index-dir is required");
+    if (!exists(o.index_dir, false)) error_exit("--input-file: File does not exist: " + o.index_dir);
+    if (!o.nwk_path.empty() && !exists(o.nwk_path, false)) error_exit("--nwk-file: File does not exist: " + o.nwk_path);
+    if (!o.sk_k_set) o.sk_k = 29;
+    if (!o.sk_h_set) o.sk_h = 13;
+    if (!o.sk_w_set) { o.sk_w = o.sk_k + 6; o.sk_h = o.sk_k - 16; }
+    if (o.sdust_t && o.sdust_w) error_exit("--sdust-t / --sdust-w (dustmasker) are not part of the GPU path; build such a library with the reference binary");
+    if (!o.lineage_path.empty() || !o.query.empty()) error_exit("The following argument was not expected for index");
+    if (o.devices.empty()) o.devices.push_back(0);
+    return o;
+  }
   if (o.sub == "sketch") { // ref src/krepp.cpp:516-540
     if (o.index_dir.empty()) error_exit("--input-file is required");
     if (o.output_path.empty()) error_exit("--output-path is required");
@@ -370,29 +386,22 @@ static int run_sharded(const Options& o, const krepp_params_t& p, bool place, co
   return 0;
 }
 
-// `krepp sketch` (ref src/krepp.cpp:110-128,773-782): one FASTA/FASTQ file -> the sketch file `seek` reads.
-static int run_sketch(const Options& o)
+// Every sequence of a FASTA/FASTQ file (plain or gzip) in one batch: what RSeq hands extract_mers sequence by sequence
+// (ref src/rqseq.cpp:39-49).  A batch that ends before the input does is read again with more room.
+static uint32_t read_whole_file(const std::string& path, std::vector<char>& bases, std::vector<uint64_t>& offsets)
 {
-  fprintf(stderr, "Initializing the sketch...\n");
-  const auto t0 = std::chrono::system_clock::now();
-  krepp_index_t* geom = nullptr;
-  if (krepp_geometry_open(o.sk_k, o.sk_w, o.sk_h, o.sk_m, o.sk_r, o.sk_frac ? 1 : 0, o.seed_set ? (int64_t)o.seed : -1, o.devices[0], &geom) != KREPP_OK) {
-    const std::string msg = krepp_last_error();
-    if (msg.find("(-") != std::string::npos || msg.find("h must be") != std::string::npos) { fprintf(stderr, "%s\n", msg.c_str()); error_exit("Invalid configuration!"); } // ref src/krepp.hpp:59-85
-    error_exit(msg);
-  }
   struct stat st;
-  stat(o.index_dir.c_str(), &st);
-  const bool gz = o.index_dir.size() > 3 && o.index_dir.compare(o.index_dir.size() - 3, 3, ".gz") == 0;
+  if (stat(path.c_str(), &st) != 0) error_exit("Failed to open the file at " + path); // ref src/rqseq.cpp:36-38
+  const bool gz = path.size() > 3 && path.compare(path.size() - 3, 3, ".gz") == 0;
   uint64_t cap_bases = (uint64_t)st.st_size * (gz ? 8 : 1) + (1u << 20);
   uint32_t cap_seqs = 1u << 16;
-  std::vector<char> bases, names;
-  std::vector<uint64_t> offsets, name_off;
+  std::vector<char> names;
+  std::vector<uint64_t> name_off;
   uint32_t n = 0;
-  for (;;) { // the whole file in one batch; a batch that ends before the input does is read again with more room
+  for (;;) {
     bases.resize(cap_bases + 64); offsets.resize((size_t)cap_seqs + 1); names.resize(64ull * cap_seqs); name_off.resize(cap_seqs);
     krepp_reader_t* rd = nullptr;
-    check(krepp_reader_open(o.index_dir.c_str(), &rd));
+    if (krepp_reader_open(path.c_str(), &rd) != KREPP_OK) error_exit("Failed to open the file at " + path);
     int eof = 0;
     const int rc = krepp_reader_next(rd, bases.data(), cap_bases, offsets.data(), cap_seqs, names.data(), names.size(), name_off.data(), &n, &eof);
     krepp_reader_close(rd);
@@ -401,6 +410,119 @@ static int run_sketch(const Options& o)
     if (cap_bases > (1ull << 40)) error_exit("the input does not fit in memory");
     cap_bases *= 2; cap_seqs *= 2;
   }
+  return n;
+}
+
+static krepp_index_t* open_geometry(const Options& o)
+{
+  krepp_index_t* geom = nullptr;
+  if (krepp_geometry_open(o.sk_k, o.sk_w, o.sk_h, o.sk_m, o.sk_r, o.sk_frac ? 1 : 0, o.seed_set ? (int64_t)o.seed : -1, o.devices[0], &geom) != KREPP_OK) {
+    const std::string msg = krepp_last_error();
+    if (msg.find("(-") != std::string::npos || msg.find("h must be") != std::string::npos) { fprintf(stderr, "%s\n", msg.c_str()); error_exit("Invalid configuration!"); } // ref src/krepp.hpp:59-85
+    error_exit(msg);
+  }
+  return geom;
+}
+
+// `krepp index` (ref src/krepp.cpp:131-309,723-736): reference genomes + guide tree -> a library directory.  Host threads read
+// (and inflate) the genomes; each genome's leaf table and rho are computed on the GPU and stay there; the union over the tree is
+// one sort on the GPU; the colour record and the files are written by the host (krepp_builder_*, include/krepp_b200.h).
+static int run_index(const Options& o)
+{
+  fprintf(stderr, "Reading the tree and initializing the index...\n");
+  const auto t0 = std::chrono::system_clock::now();
+  krepp_index_t* geom = open_geometry(o);
+  std::vector<std::string> names;
+  std::vector<std::pair<std::string, std::string>> todo; // (name, path), one per distinct name: a later line overrides (ref src/krepp.cpp:157-158)
+  { // IndexMultiple::read_input_file ref src/krepp.cpp:147-162
+    FILE* f = fopen(o.index_dir.c_str(), "r");
+    if (!f) error_exit("Error opening " + o.index_dir);
+    std::string text;
+    char buf[1 << 16];
+    size_t got;
+    while ((got = fread(buf, 1, sizeof buf, f)) > 0) text.append(buf, got);
+    fclose(f);
+    for (size_t at = 0; at < text.size();) {
+      size_t e = text.find('\n', at);
+      if (e == std::string::npos) e = text.size();
+      const std::string line = text.substr(at, e - at);
+      at = e + 1;
+      const size_t tab = line.find('\t');
+      if (tab == std::string::npos) error_exit("Failed to read the reference name to path/URL mapping!");
+      const size_t tab2 = line.find('\t', tab + 1);
+      const std::string name = line.substr(0, tab), path = line.substr(tab + 1, tab2 == std::string::npos ? std::string::npos : tab2 - tab - 1);
+      if (path.empty()) error_exit("Failed to read the reference name to path/URL mapping!");
+      names.push_back(name);
+      bool seen = false;
+      for (auto& np : todo) if (np.first == name) { np.second = path; seen = true; }
+      if (!seen) todo.emplace_back(name, path);
+    }
+  }
+  std::string nwk;
+  if (o.nwk_path.empty()) fprintf(stderr, "No tree has given as a guide, the color index could be suboptimal.\n");
+  else {
+    FILE* f = fopen(o.nwk_path.c_str(), "r");
+    if (!f) error_exit("Error opening " + o.nwk_path);
+    char buf[1 << 16];
+    size_t got;
+    while ((got = fread(buf, 1, sizeof buf, f)) > 0) nwk.append(buf, got);
+    fclose(f);
+  }
+  std::vector<const char*> name_ptrs;
+  for (const auto& nm : names) name_ptrs.push_back(nm.c_str());
+  krepp_builder_t* b = nullptr;
+  check(krepp_builder_create(geom, o.nwk_path.empty() ? nullptr : nwk.c_str(), name_ptrs.data(), (uint32_t)name_ptrs.size(), &b));
+  fprintf(stderr, "Building the index...\n");
+  { // readers in parallel, one genome on the GPU at a time
+    std::atomic<size_t> next{0};
+    std::mutex gpu;
+    uint32_t done = 0;
+    auto work = [&] {
+      std::vector<char> bases;
+      std::vector<uint64_t> offsets;
+      for (;;) {
+        const size_t i = next.fetch_add(1);
+        if (i >= todo.size()) return;
+        if (krepp_builder_has_leaf(b, todo[i].first.c_str()) != 1) continue; // not on the tree: never visited (ref src/krepp.cpp:248-252)
+        const uint32_t n = read_whole_file(todo[i].second, bases, offsets);
+        std::lock_guard<std::mutex> lock(gpu);
+        uint64_t nk = 0;
+        double rho = 0;
+        check(krepp_builder_add_genome(b, todo[i].first.c_str(), bases.data(), offsets.data(), n, &nk, &rho));
+        ++done;
+        if (o.verbose) fprintf(stderr, "Leaf node: %s\tsize: %llu\trho: %g\tprogress: %u/%u\n", todo[i].first.c_str(), (unsigned long long)nk, rho, done, krepp_builder_nleaves(b));
+      }
+    };
+    std::vector<std::thread> th;
+    const uint32_t nt = (uint32_t)std::max<size_t>(1, std::min<size_t>(o.num_threads, todo.size()));
+    for (uint32_t t = 1; t < nt; ++t) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+  }
+  uint64_t nk = 0, nsets = 0;
+  check(krepp_builder_union(b, &nk, &nsets));
+  const std::chrono::duration<float> es_b = std::chrono::system_clock::now() - t0;
+  fprintf(stderr, "\nFinished indexing, elapsed: %g sec\n", es_b.count());
+  uint32_t nsub = 0;
+  check(krepp_builder_write(b, o.output_path.c_str(), o.seed_set ? o.seed : 0, &nk, &nsub));
+  if (o.nwk_path.empty()) fprintf(stderr, "Skipped saving a backbone for the index!\n");
+  if (o.verbose) fprintf(stderr, "k-mers: %llu, distinct reference sets: %llu, colours: %u\n", (unsigned long long)nk, (unsigned long long)nsets, nsub);
+  const std::chrono::duration<float> es_s = std::chrono::system_clock::now() - t0 - es_b;
+  fprintf(stderr, "Done converting & saving, elapsed: %g sec\n", es_s.count());
+  krepp_builder_destroy(b);
+  krepp_index_close(geom);
+  return 0;
+}
+
+// `krepp sketch` (ref src/krepp.cpp:110-128,773-782): one FASTA/FASTQ file -> the sketch file `seek` reads.
+static int run_sketch(const Options& o)
+{
+  fprintf(stderr, "Initializing the sketch...\n");
+  const auto t0 = std::chrono::system_clock::now();
+  krepp_index_t* geom = open_geometry(o);
+  std::vector<char> bases;
+  std::vector<uint64_t> offsets;
+  const uint32_t n = read_whole_file(o.index_dir, bases, offsets);
   uint64_t nk = 0;
   double rho = 0;
   check(krepp_sketch_write(geom, bases.data(), offsets.data(), n, o.output_path.c_str(), &nk, &rho));
@@ -422,6 +544,7 @@ int main(int argc, char** argv)
   { std::time_t t = std::chrono::system_clock::to_time_t(tstart); fprintf(stderr, "Invocation: %s\n%s", invocation.c_str(), std::ctime(&t)); }
 
   if (o.sub == "sketch") return run_sketch(o);
+  if (o.sub == "index") return run_index(o);
   const bool place = o.sub == "place", seek = o.sub == "seek";
   krepp_params_t p;
   krepp_params_default(&p, place ? 1 : 0);

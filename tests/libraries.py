@@ -76,8 +76,6 @@ def assert_same_library(mine: dict, ref: dict):
     assert a[:n] == b[:n]
     sa, sb = mine["se"], ref["se"]
     assert all(a[int(x)] == b[int(y)] for x, y in zip(sa, sb))
-    # and no colour is wasted: every id above the nodes is reachable from some k-mer (as in the reference, whose record only
-    # holds sets that were met), except the tails of nodes with more than two children
     return len(mine["pse"]), len(ref["pse"])
 
 
@@ -104,3 +102,14 @@ def numpy_union(tables: dict) -> tuple:
     set_begin[1:] = np.cumsum([len(t) for t in sets])
     set_leaves = np.array([x for t in sets for x in t], np.uint32)
     return keys[starts].copy(), set_of, set_begin, set_leaves
+
+
+def same_colours_vectorised(mine: dict, ref: dict) -> bool:
+    """assert_same_library's per-k-mer colour check for libraries of millions of k-mers: colour ids of both libraries are mapped
+    to one shared numbering of their expansions, then the two columns are compared as arrays."""
+    shared = {}
+    canon = []
+    for lib in (mine, ref):
+        exp = colour_leaves(lib)
+        canon.append(np.array([shared.setdefault(s, len(shared)) for s in exp], np.int64))
+    return bool((canon[0][mine["se"]] == canon[1][ref["se"]]).all())

@@ -92,6 +92,33 @@ def test_written_library_without_a_guide_tree(tmp_path_factory, tmp_path):
     assert ref_dist(mine_dir) == ref_dist(ref_dir)
 
 
+@needs_ref
+def test_written_library_of_draft_assemblies(tmp_path):
+    """Contigs with runs of N, short contigs and the end-of-sequence emit; a leaf of the tree without a genome (an empty table, rho
+    0) and a reference id the tree does not have (listed in reflist-*, never indexed) -- as the reference treats them."""
+    import shutil
+    from test_gpu_sketch import contigs_fasta
+    w = str(tmp_path / "w")
+    os.makedirs(w)
+    shutil.copytree(os.path.join(SMALL, "genomes"), os.path.join(w, "genomes"))
+    shutil.copy(os.path.join(SMALL, "tree.nwk"), w)
+    contigs_fasta(os.path.join(w, "genomes", "G000001.fna"))
+    names, paths = names_and_paths()
+    names = ["GXXXXXX" if n == "G000005" else n for n in names]
+    with open(os.path.join(w, "input_map.tsv"), "w") as f:
+        for n in names:
+            f.write(n + "\t./genomes/" + ("G000005" if n == "GXXXXXX" else n) + ".fna\n")
+    subprocess.run([REF, "index", "-k", "21", "-w", "25", "-h", "7", "-o", "ref_index", "-i", "input_map.tsv", "-t", "tree.nwk"], cwd=w, check=True, capture_output=True)
+    ref = read_library(os.path.join(w, "ref_index"))
+    paths = {n: os.path.join(w, "genomes", ("G000005" if n == "GXXXXXX" else n) + ".fna") for n in names}
+    mine_dir = os.path.join(w, "my_index")
+    host_build(ref, mine_dir, open(os.path.join(w, "tree.nwk")).read(), names, paths)
+    mine = read_library(mine_dir)
+    assert_same_library(mine, ref)
+    assert b"GXXXXXX\n" in mine["reflist"] and (mine["rho"] == 0).sum() == (ref["rho"] == 0).sum()
+    assert ref_dist(mine_dir) == ref_dist(os.path.join(w, "ref_index"))
+
+
 def random_sets(rng, nleaves, n_sets):
     sets = {tuple(range(nleaves))}
     while len(sets) < n_sets:
