@@ -117,9 +117,11 @@ __global__ void set_gather_kernel(const uint32_t* __restrict__ rep, const unsign
 
 void free_tables(krepp_builder* b)
 {
-  if (!b->tables.empty() && b->geom->device != KREPP_DEVICE_NONE) cudaSetDevice(b->geom->device);
+  if (b->geom->device == KREPP_DEVICE_NONE) return;
+  cudaSetDevice(b->geom->device);
   for (auto& t : b->tables) if (t.keys) cudaFree(t.keys);
   b->tables.clear();
+  b->scratch.release();
 }
 
 } // namespace
@@ -178,7 +180,7 @@ extern "C" int krepp_builder_add_genome(krepp_builder_t* b, const char* name, co
   krepp_builder::DevTable t;
   t.leaf = it->second;
   double est[2] = {0, 0};
-  if (int rc = extract_to_device(b->geom, bases, offsets, n_seqs, &t.keys, &t.n, est)) return rc;
+  if (int rc = extract_to_device(b->geom, bases, offsets, n_seqs, &t.keys, &t.n, est, &b->scratch)) return rc;
   b->leaf_added[t.leaf] = 1;
   b->leaf_rho[t.leaf] = est[1] / est[0]; // RSeq::compute_rho ref src/rqseq.hpp:79 (0/0 = NaN for a genome without a single window, as there)
   b->tables.push_back(t);

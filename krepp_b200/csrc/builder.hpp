@@ -9,8 +9,20 @@
 #include <unordered_map>
 #include <vector>
 
+namespace krepp {
+// Device buffers of the minimizer pass kept between the genomes of one build (a genome's pass is a few milliseconds; allocating
+// and freeing its ten buffers every time costs as much again).
+struct MzScratch {
+  static constexpr int kSlots = 10;
+  void* p[kSlots] = {};
+  size_t cap[kSlots] = {};
+  void release();
+};
+} // namespace krepp
+
 struct krepp_builder {
   const krepp_index* geom = nullptr;
+  krepp::MzScratch scratch;
   krepp::HostTree tree;              // the build tree: the guide tree, or the balanced tree generated over the names
   std::string nwk_text;              // guide tree text as given (written to tree-* verbatim); unused without one
   bool with_tree = false;
@@ -33,7 +45,7 @@ namespace krepp {
 // minimizer.cu: one genome's leaf table left on the device (exact-size allocation owned by the caller) and the two HyperLogLog
 // estimates whose ratio is rho.
 int extract_to_device(const krepp_index* ix, const char* bases, const uint64_t* offsets, uint32_t n_seqs, unsigned long long** d_keys, uint64_t* n_keys,
-                      double est[2]);
+                      double est[2], MzScratch* scratch);
 
 // The colour record of a library: ids 1..tree.nnodes are the tree's nodes, the ids above them the reference sets that are not
 // whole subtrees; pse[id] = the two ids a colour splits into (first | second << 32), (0, self) for a leaf.

@@ -472,6 +472,7 @@ static int run_index(const Options& o)
   for (const auto& nm : names) name_ptrs.push_back(nm.c_str());
   krepp_builder_t* b = nullptr;
   check(krepp_builder_create(geom, o.nwk_path.empty() ? nullptr : nwk.c_str(), name_ptrs.data(), (uint32_t)name_ptrs.size(), &b));
+  const auto t1 = std::chrono::system_clock::now();
   fprintf(stderr, "Building the index...\n");
   { // readers in parallel, one genome on the GPU at a time
     std::atomic<size_t> next{0};
@@ -500,7 +501,13 @@ static int run_index(const Options& o)
     for (auto& t : th) t.join();
   }
   uint64_t nk = 0, nsets = 0;
+  const auto t2 = std::chrono::system_clock::now();
   check(krepp_builder_union(b, &nk, &nsets));
+  const auto t3 = std::chrono::system_clock::now();
+  if (o.verbose) {
+    const std::chrono::duration<float> a = t1 - t0, g = t2 - t1, u = t3 - t2;
+    fprintf(stderr, "\n[stages] set-up (device, tree) %.3f s, genomes (read + leaf tables on the GPU) %.3f s, union on the GPU %.3f s", a.count(), g.count(), u.count());
+  }
   const std::chrono::duration<float> es_b = std::chrono::system_clock::now() - t0;
   fprintf(stderr, "\nFinished indexing, elapsed: %g sec\n", es_b.count());
   uint32_t nsub = 0;

@@ -267,8 +267,21 @@ namespace {
 // when `est` is given, the two HyperLogLog estimates of RSeq::extract_mers summed over the sequences in order (n1: distinct
 // valid k-mers, n2: distinct minimizers; ref src/rqseq.cpp:63-64,107-108,117,142-143), whose ratio is rho (src/rqseq.hpp:79).
 int extract_impl(const krepp_index_t* ix, const char* bases, const uint64_t* offsets, uint32_t n_seqs, uint64_t* keys, uint64_t cap, uint64_t* n_keys,
-                 std::vector<uint64_t>* keys_vec, double* est, unsigned long long** keep_dev = nullptr)
+                 std::vector<uint64_t>* keys_vec, double* est, unsigned long long** keep_dev = nullptr, MzScratch* scratch = nullptr)
 {
+  // device buffer `slot` of at least `bytes`: from the caller's scratch (grown when too small, kept between calls) or fresh
+  auto buffer = [&](int slot, void** out, size_t bytes) -> cudaError_t {
+    if (!scratch) return cudaMalloc(out, bytes);
+    if (scratch->cap[slot] < bytes) {
+      if (scratch->p[slot]) cudaFree(scratch->p[slot]);
+      scratch->p[slot] = nullptr; scratch->cap[slot] = 0;
+      const cudaError_t e = cudaMalloc(&scratch->p[slot], bytes + bytes / 4);
+      if (e != cudaSuccess) return e;
+      scratch->cap[slot] = bytes + bytes / 4;
+    }
+    *out = scratch->p[slot];
+    return cudaSuccess;
+  };
   if (ix->device == KREPP_DEVICE_NONE) return set_error(KREPP_ERR_CUDA, "the index-side kernels need a handle opened on a GPU (there is no CPU fallback)");
   const HostIndex& h = ix->host;
   if (h.w < h.k || h.w - h.k + 1 > 32) return set_error(KREPP_ERR_UNSUPPORTED, "window of %u with k = %u: at most 32 k-mers per window are supported", h.w, h.k);
@@ -302,10 +315,10 @@ int extract_impl(const krepp_index_t* ix, const char* bases, const uint64_t* off
   const uint64_t kcap = windows + quirk.size() + 1;
   MzArgs a{};
   {
-    MZ_CU(cudaMalloc(&d_bases, nb + 64)); MZ_CU(cudaMalloc(&d_off, 8ull * (n_seqs + 1))); MZ_CU(cudaMalloc(&d_tb, 8ull * (n_seqs + 1)));
-    MZ_CU(cudaMalloc(&d_keys, 8ull * kcap)); MZ_CU(cudaMalloc(&d_sorted, 8ull * kcap)); MZ_CU(cudaMalloc(&d_uniq, 8ull * kcap));
-    MZ_CU(cudaMalloc(&d_cnt, 16)); MZ_CU(cudaMalloc(&d_nsel, 8));
-    if (est) { MZ_CU(cudaMalloc(&d_hll, 2ull * kHllRegs * std::max<uint32_t>(n_seqs, 1))); MZ_CU(cudaMemset(d_hll, 0, 2ull * kHllRegs * std::max<uint32_t>(n_seqs, 1))); }
+    MZ_CU(buffer(0, (void**)&d_bases, nb + 64)); MZ_CU(buffer(1, (void**)&d_off, 8ull * (n_seqs + 1))); MZ_CU(buffer(2, (void**)&d_tb, 8ull * (n_seqs + 1)));
+    MZ_CU(buffer(3, (void**)&d_keys, 8ull * kcap)); MZ_CU(buffer(4, (void**)&d_sorted, 8ull * kcap)); MZ_CU(buffer(5, (void**)&d_uniq, 8ull * kcap));
+    MZ_CU(buffer(6, (void**)&d_cnt, 16)); MZ_CU(buffer(7, (void**)&d_nsel, 8));
+    if (est) { MZ_CU(buffer(8, (void**)&d_hll, 2ull * kHllRegs * std::max<uint32_t>(n_seqs, 1))); MZ_CU(cudaMemset(d_hll, 0, 2ull * kHllRegs * std::max<uint32_t>(n_seqs, 1))); }
     MZ_CU(cudaMemcpy(d_bases, bases + offsets[0], nb, cudaMemcpyHostToDevice));
     MZ_CU(cudaMemcpy(d_off, rel.data(), 8ull * (n_seqs + 1), cudaMemcpyHostToDevice));
     MZ_CU(cudaMemcpy(d_tb, tile_begin.data(), 8ull * (n_seqs + 1), cudaMemcpyHostToDevice));
@@ -328,7 +341,7 @@ int extract_impl(const krepp_index_t* ix, const char* bases, const uint64_t* off
       while ((1ull << row_bits) < h.nrows) ++row_bits;
       MZ_CU(cub::DeviceRadixSort::SortKeys(nullptr, tmp1, d_keys, d_sorted, (int)n, 0, 32 + (int)row_bits));
       MZ_CU(cub::DeviceSelect::Unique(nullptr, tmp2, d_sorted, d_uniq, d_nsel, (int)n));
-      MZ_CU(cudaMalloc(&d_tmp, std::max(tmp1, tmp2)));
+      MZ_CU(buffer(9, &d_tmp, std::max(tmp1, tmp2)));
       if (n > 0x7FFFFFFFull) { rc = set_error(KREPP_ERR_CAPACITY, "more than 2^31 minimizers in one call: pass fewer sequences"); goto done; }
       MZ_CU(cub::DeviceRadixSort::SortKeys(d_tmp, tmp1, d_keys, d_sorted, (int)n, 0, 32 + (int)row_bits));
       MZ_CU(cub::DeviceSelect::Unique(d_tmp, tmp2, d_sorted, d_uniq, d_nsel, (int)n));
@@ -373,16 +386,21 @@ int extract_impl(const krepp_index_t* ix, const char* bases, const uint64_t* off
     if (nsel) MZ_CU(cudaMemcpy(keys, d_uniq, 8ull * nsel, cudaMemcpyDeviceToHost));
   }
 done:
-  for (void* p : {(void*)d_bases, (void*)d_off, (void*)d_tb, (void*)d_keys, (void*)d_sorted, (void*)d_uniq, (void*)d_cnt, (void*)d_nsel, (void*)d_hll, d_tmp}) if (p) cudaFree(p);
+  if (!scratch) for (void* p : {(void*)d_bases, (void*)d_off, (void*)d_tb, (void*)d_keys, (void*)d_sorted, (void*)d_uniq, (void*)d_cnt, (void*)d_nsel, (void*)d_hll, d_tmp}) if (p) cudaFree(p);
   return rc;
 }
 
 } // namespace
 
 namespace krepp {
-int extract_to_device(const krepp_index* ix, const char* bases, const uint64_t* offsets, uint32_t n_seqs, unsigned long long** d_keys, uint64_t* n_keys, double est[2])
+int extract_to_device(const krepp_index* ix, const char* bases, const uint64_t* offsets, uint32_t n_seqs, unsigned long long** d_keys, uint64_t* n_keys, double est[2],
+                      MzScratch* scratch)
 {
-  return extract_impl(ix, bases, offsets, n_seqs, nullptr, 0, n_keys, nullptr, est, d_keys);
+  return extract_impl(ix, bases, offsets, n_seqs, nullptr, 0, n_keys, nullptr, est, d_keys, scratch);
+}
+void MzScratch::release()
+{
+  for (int i = 0; i < kSlots; ++i) { if (p[i]) cudaFree(p[i]); p[i] = nullptr; cap[i] = 0; }
 }
 } // namespace krepp
 
