@@ -113,3 +113,38 @@ def same_colours_vectorised(mine: dict, ref: dict) -> bool:
         exp = colour_leaves(lib)
         canon.append(np.array([shared.setdefault(s, len(shared)) for s in exp], np.int64))
     return bool((canon[0][mine["se"]] == canon[1][ref["se"]]).all())
+
+
+def sampled_colour_check(mine: dict, ref: dict, n: int = 200_000, seed: int = 1) -> tuple:
+    """For libraries too large to expand every colour in Python: n random k-mers, their colours expanded on demand in both
+    libraries.  Returns (k-mers checked, k-mers whose two colours expand to different references)."""
+    rng = np.random.default_rng(seed)
+    at = rng.integers(0, len(mine["se"]), min(n, len(mine["se"])))
+
+    def expander(lib):
+        pse, nnodes, memo = lib["pse"], lib["nnodes"], {0: frozenset()}
+
+        def expand(c):
+            stack = [c]
+            while stack:
+                x = stack[-1]
+                if x in memo:
+                    stack.pop()
+                    continue
+                a, b = int(pse[x][0]), int(pse[x][1])
+                if x < nnodes and a == 0 and b == x:
+                    memo[x] = frozenset([x])
+                    stack.pop()
+                    continue
+                todo = [y for y in (a, b) if y not in memo]
+                if todo:
+                    stack.extend(todo)
+                    continue
+                memo[x] = memo[a] | memo[b]
+                stack.pop()
+            return memo[c]
+        return expand
+
+    ea, eb = expander(mine), expander(ref)
+    bad = sum(1 for i in at if ea(int(mine["se"][i])) != eb(int(ref["se"][i])))
+    return len(at), bad
