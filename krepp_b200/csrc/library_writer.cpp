@@ -21,49 +21,53 @@
 #include "builder.hpp"
 
 #include <cerrno>
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <ctime>
 #include <sys/stat.h>
+#include <thread>
+#include <algorithm>
 
 namespace krepp {
 
 namespace {
 
-struct PairTable { // (first, second) -> colour id, open addressing; the ids index ColourRecord::pse
-  std::vector<uint64_t> key;
-  std::vector<uint32_t> val;
+struct PairTable { // (first, second) -> colour id, open addressing; the ids index ColourRecord::pse.  Key and id share a 16-byte
+                   // slot: a probe is one cache miss, and the interning of 2.5 M sets is little else than its misses
+  struct Slot { uint64_t key; uint32_t val, pad; };
+  std::vector<Slot> slot;
   uint64_t mask = 0, used = 0;
   explicit PairTable(uint64_t expect)
   {
     uint64_t cap = 1024;
     while (cap < 2 * expect) cap <<= 1;
-    key.assign(cap, 0); val.assign(cap, 0); mask = cap - 1;
+    slot.assign(cap, Slot{0, 0, 0}); mask = cap - 1;
   }
   static uint64_t mix(uint64_t x) { x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33; return x; }
   void grow()
   {
-    std::vector<uint64_t> k2(key.size() * 2, 0);
-    std::vector<uint32_t> v2(key.size() * 2, 0);
-    const uint64_t m2 = k2.size() - 1;
-    for (size_t i = 0; i < key.size(); ++i) {
-      if (!val[i]) continue;
-      uint64_t at = mix(key[i]) & m2;
-      while (v2[at]) at = (at + 1) & m2;
-      k2[at] = key[i]; v2[at] = val[i];
+    std::vector<Slot> s2(slot.size() * 2, Slot{0, 0, 0});
+    const uint64_t m2 = s2.size() - 1;
+    for (const Slot& e : slot) {
+      if (!e.val) continue;
+      uint64_t at = mix(e.key) & m2;
+      while (s2[at].val) at = (at + 1) & m2;
+      s2[at] = e;
     }
-    key.swap(k2); val.swap(v2); mask = m2;
+    slot.swap(s2); mask = m2;
   }
   // the id of the pair, `fresh` when it is new (the caller then appends it under that id)
   uint32_t intern(uint64_t pair, uint32_t fresh, bool* is_new)
   {
-    if (2 * (used + 1) > key.size()) grow();
+    if (2 * (used + 1) > slot.size()) grow();
     uint64_t at = mix(pair) & mask;
-    while (val[at]) {
-      if (key[at] == pair) { *is_new = false; return val[at]; }
+    while (slot[at].val) {
+      if (slot[at].key == pair) { *is_new = false; return slot[at].val; }
       at = (at + 1) & mask;
     }
-    key[at] = pair; val[at] = fresh; ++used; *is_new = true;
+    slot[at] = Slot{pair, fresh, 0}; ++used; *is_new = true;
     return fresh;
   }
 };
@@ -98,9 +102,10 @@ std::string colour_sets(const HostTree& t, uint64_t n_sets, const uint64_t* set_
     pse[g] = (uint64_t)kids[0] | (uint64_t)acc << 32;
   }
   out->set_colour.assign(n_sets, 0);
-  struct Frame { uint32_t lo, hi, g, at; size_t base; };
+  struct Frame { uint32_t lo, hi, g, at, child; size_t base; };
   std::vector<Frame> stack;
   std::vector<uint32_t> vals;
+  auto leaves_below = [&](uint32_t g) { return upto[g] - upto[g - t.subtree[g]]; };
   for (uint64_t s = 0; s < n_sets; ++s) {
     const uint32_t* lv = set_leaves + set_begin[s];
     const uint64_t n64 = set_begin[s + 1] - set_begin[s];
@@ -108,27 +113,32 @@ std::string colour_sets(const HostTree& t, uint64_t n_sets, const uint64_t* set_
     const uint32_t n = (uint32_t)n64;
     for (uint32_t i = 0; i < n; ++i) if (lv[i] >= t.nleaves || (i && lv[i] <= lv[i - 1])) return "a reference set is not an ascending list of leaf ranks";
     stack.clear(); vals.clear();
-    // enter(lo, hi): a leaf or a whole subtree is its own colour; anything else opens a frame at the lowest node above the segment
-    auto enter = [&](uint32_t lo, uint32_t hi) {
-      const uint32_t a = t.leaf_se[lv[lo]], b = t.leaf_se[lv[hi - 1]];
-      if (hi - lo == 1) { vals.push_back(a); return; }
-      uint32_t g = a;
-      while (g < b) g = t.parent[g]; // ancestors have larger numbers; the first one at or past b holds b too
-      if (hi - lo == upto[g] - upto[g - t.subtree[g]]) { vals.push_back(g); return; }
-      stack.push_back(Frame{lo, hi, g, lo, vals.size()});
+    // enter(x, lo, hi): the segment lies below x.  Walks down while one child holds all of it; a node (or leaf) whose every leaf
+    // is in the segment is its own colour; otherwise a frame opens at the lowest node above the segment.  Children are numbered
+    // in ascending order (post-order), so the child that holds a leaf is the first one numbered at or past it.
+    auto enter = [&](uint32_t x, uint32_t lo, uint32_t hi) {
+      const uint32_t first = t.leaf_se[lv[lo]], last = t.leaf_se[lv[hi - 1]];
+      for (;;) {
+        if (hi - lo == leaves_below(x)) { vals.push_back(x); return; }
+        uint32_t d = t.first_child[x];
+        while (first > d) d = t.next_sibling[d];
+        if (last <= d) { x = d; continue; }
+        stack.push_back(Frame{lo, hi, x, lo, d, vals.size()});
+        return;
+      }
     };
-    enter(0, n);
+    enter(t.root, 0, n);
     while (!stack.empty()) {
       Frame& f = stack.back();
       if (f.at < f.hi) { // the next child of f.g that the segment touches
-        uint32_t c = t.leaf_se[lv[f.at]];
-        while (t.parent[c] != f.g) c = t.parent[c];
-        const uint32_t end_rank = upto[c];
+        uint32_t d = f.child;
+        while (t.leaf_se[lv[f.at]] > d) d = t.next_sibling[d];
+        const uint32_t end_rank = upto[d];
         uint32_t j = f.at + 1;
         while (j < f.hi && lv[j] < end_rank) ++j;
         const uint32_t i = f.at;
-        f.at = j; // (f may dangle after enter)
-        enter(i, j);
+        f.at = j; f.child = d; // (f may dangle after enter)
+        enter(d, i, j);
       } else { // all parts are in vals[base..): right fold
         const size_t base = f.base;
         uint32_t acc = vals.back();
@@ -171,19 +181,45 @@ std::string write_library(const krepp_builder& b, const std::string& dir, uint32
   if (!n) return "No k-mers to index!"; // ref src/krepp.cpp:183
   ColourRecord cr;
   const uint64_t n_sets = b.set_begin.empty() ? 0 : b.set_begin.size() - 1;
+  const bool debug = getenv("KREPP_BUILD_DEBUG") && atoi(getenv("KREPP_BUILD_DEBUG"));
+  auto clk = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    const auto now = std::chrono::steady_clock::now();
+    if (debug) fprintf(stderr, "[library writer] %s %.3f s\n", what, std::chrono::duration<double>(now - clk).count());
+    clk = now;
+  };
   { std::string err = colour_sets(b.tree, n_sets, b.set_begin.data(), b.set_leaves.data(), &cr); if (!err.empty()) return err; }
+  lap("colour record");
   // FlatHT (ref src/table.cpp:43-63): entries row by row, ascending encoding within a row, and the cumulative row ends
   std::vector<uint64_t, NoInitAlloc<uint64_t>> cmer(n);
   std::vector<uint64_t> inc(h.nrows, 0);
-  for (uint64_t i = 0; i < n; ++i) {
-    const uint64_t key = b.keys[i], row = key >> 32;
-    if (row >= h.nrows) return "a k-mer fell outside the table";
-    if (i && key <= b.keys[i - 1]) return "the union is not ascending by (row, encoding)";
-    if (b.set_of[i] >= n_sets) return "a k-mer names a reference set that does not exist";
-    cmer[i] = (key & 0xFFFFFFFFull) | (uint64_t)cr.set_colour[b.set_of[i]] << 32;
-    ++inc[row];
+  { // in parallel over ranges of k-mers: entry i is the last of its row when the next key has another row, and is then the
+    // cumulative end (i + 1) of its row and of every empty row up to the next key's
+    const uint32_t nt = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(std::min<unsigned>(std::thread::hardware_concurrency(), 32u), n / (1u << 20)));
+    std::vector<int> bad(nt, 0);
+    auto work = [&](uint32_t t) {
+      const uint64_t lo = n * t / nt, hi = n * (t + 1) / nt;
+      for (uint64_t i = lo; i < hi; ++i) {
+        const uint64_t key = b.keys[i], row = key >> 32;
+        if (row >= h.nrows) { bad[t] = 1; return; }
+        if (i && key <= b.keys[i - 1]) { bad[t] = 2; return; }
+        if (b.set_of[i] >= n_sets) { bad[t] = 3; return; }
+        cmer[i] = (key & 0xFFFFFFFFull) | (uint64_t)cr.set_colour[b.set_of[i]] << 32;
+        const uint64_t next_row = i + 1 < n ? std::min<uint64_t>(b.keys[i + 1] >> 32, h.nrows) : h.nrows;
+        for (uint64_t q = row; q < next_row; ++q) inc[q] = i + 1;
+      }
+    };
+    std::vector<std::thread> th;
+    for (uint32_t t = 1; t < nt; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+    for (int e : bad) {
+      if (e == 1) return "a k-mer fell outside the table";
+      if (e == 2) return "the union is not ascending by (row, encoding)";
+      if (e == 3) return "a k-mer names a reference set that does not exist";
+    }
   }
-  for (uint32_t r = 1; r < h.nrows; ++r) inc[r] += inc[r - 1];
+  lap("table");
   // CRecord (ref src/record.cpp:156-175,213-219): nnodes = tree nodes + 1, rho by node number (leaves only)
   const uint32_t nnodes = b.tree.nnodes + 1, nsubsets = (uint32_t)cr.pse.size();
   std::vector<double> rho(nnodes, 0.0);
@@ -213,6 +249,7 @@ std::string write_library(const krepp_builder& b, const std::string& dir, uint32
                        "\nnpos_v: " + pos_list(h.npos) + "\nnrows: " + std::to_string(h.nrows) + "\ntotal_num_kmers: " + std::to_string(n) + "\nsdust-t: 0\nsdust-w: 0\n";
     if (!write_all(dir + "/metadata" + sfx + ".txt", {{info.data(), info.size()}})) return "Failed to write the text metadata of the index!";
   }
+  lap("files");
   if (n_kmers) *n_kmers = n;
   if (n_subsets) *n_subsets = nsubsets;
   return "";
