@@ -516,8 +516,10 @@ static int run_index(const Options& o)
   if (o.verbose) fprintf(stderr, "k-mers: %llu, distinct reference sets: %llu, colours: %u\n", (unsigned long long)nk, (unsigned long long)nsets, nsub);
   const std::chrono::duration<float> es_s = std::chrono::system_clock::now() - t0 - es_b;
   fprintf(stderr, "Done converting & saving, elapsed: %g sec\n", es_s.count());
+  const auto t4 = std::chrono::system_clock::now();
   krepp_builder_destroy(b);
   krepp_index_close(geom);
+  if (o.verbose) { const std::chrono::duration<float> d = std::chrono::system_clock::now() - t4; fprintf(stderr, "[stages] releasing the builder %.3f s\n", d.count()); }
   return 0;
 }
 
@@ -551,7 +553,14 @@ int main(int argc, char** argv)
   { std::time_t t = std::chrono::system_clock::to_time_t(tstart); fprintf(stderr, "Invocation: %s\n%s", invocation.c_str(), std::ctime(&t)); }
 
   if (o.sub == "sketch") return run_sketch(o);
-  if (o.sub == "index") return run_index(o);
+  if (o.sub == "index") {
+    const int rc = run_index(o);
+    const auto tend = std::chrono::system_clock::now();
+    if (o.verbose) { const std::chrono::duration<float> d = tend - tstart; fprintf(stderr, "[stages] main() %.3f s\n", d.count()); }
+    std::time_t t = std::chrono::system_clock::to_time_t(tend);
+    fprintf(stderr, "%s", std::ctime(&t)); // ref src/krepp.cpp:795-797
+    return rc;
+  }
   const bool place = o.sub == "place", seek = o.sub == "seek";
   krepp_params_t p;
   krepp_params_default(&p, place ? 1 : 0);
