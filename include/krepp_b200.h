@@ -62,23 +62,27 @@ int krepp_index_open(const char* index_dir, int device, krepp_index_t** out);
  * candidate only when all of them do (src/query.cpp:250-271).  Node numbers in records, placements and the jplace tree are
  * the query tree's.  nwk_path NULL = the index's own tree; shard / nshards as for krepp_index_open_shard. */
 int krepp_index_open_tree(const char* index_dir, int device, uint32_t shard, uint32_t nshards, const char* nwk_path, krepp_index_t** out);
-/* The same with `place -l FILE` (TargetIndex::read_lineages src/krepp.cpp:37-46, Tree::parse_lineages src/phytree.cpp:320-370):
- * the tree is built from a Greengenes/GTDB style lineage file ("NAME<tab>d__A; p__B; ..."), the references hang below the
- * last taxon of their line, there are no branch lengths (pendant and distal lengths print as 0) and nodes with one child are
- * kept but are no placement candidates.  Works on an index without a backbone tree too (the reference skips
- * ensure_backbone with -l). */
 /* The LSH geometry of a library still to be built (BaseLSH set_nrows / set_lshf src/krepp.cpp:3-16, LSHF::get_random_positions
  * src/lshf.cpp:125-147, validate_configuration src/krepp.hpp:59-85): k, w, h, m, r, frac and the h hash positions the reference
  * draws from its global std::mt19937 (default-constructed; seed >= 0 is `--seed`, a negative seed means the option was not
  * given).  The handle serves the index-side calls (krepp_extract_mers, krepp_sketch_write) and krepp_index_info; it has no table
  * and cannot be queried. */
 int krepp_geometry_open(uint32_t k, uint32_t w, uint32_t h, uint32_t m, uint32_t r, int frac, int64_t seed, int device, krepp_index_t** out);
+/* The same with the h hash positions given by the caller (any order; the reference keeps them descending and the other k - h
+ * positions ascending, src/lshf.cpp:125-147): for a binding that sits beside the reference's own LSHF (LSHF::get_ppos,
+ * src/lshf.hpp:17), and for adding a partial library to a directory whose positions are already fixed. */
+int krepp_geometry_open_positions(uint32_t k, uint32_t w, uint32_t h, uint32_t m, uint32_t r, int frac, const uint8_t* ppos, int device, krepp_index_t** out);
 /* `krepp seek -i SKETCH` (TargetSketch::load_sketch src/krepp.cpp:31-35, Sketch::load_full_sketch / make_rho_partial
  * src/sketch.cpp:3-32): the sketch file of ONE genome written by `krepp sketch` -- a table of 4-byte residual encodings without
  * colours, its LSH geometry and the genome's rho.  It is held as an index whose tree is a single leaf named after the file, so
  * krepp_index_info and the batch calls work on it unchanged; a batch on it gives at most one record per strand, and
  * KREPP_OUT_SEEK the distance SBatch::seek_sequences prints (src/seek.cpp:22-53).  `place` is refused. */
 int krepp_sketch_open(const char* sketch_path, int device, krepp_index_t** out);
+/* krepp_index_open_tree with `place -l FILE` in place of `-t` (TargetIndex::read_lineages src/krepp.cpp:37-46, Tree::parse_lineages src/phytree.cpp:320-370):
+ * the tree is built from a Greengenes/GTDB style lineage file ("NAME<tab>d__A; p__B; ..."), the references hang below the
+ * last taxon of their line, there are no branch lengths (pendant and distal lengths print as 0) and nodes with one child are
+ * kept but are no placement candidates.  Works on an index without a backbone tree too (the reference skips
+ * ensure_backbone with -l). */
 int krepp_index_open_lineages(const char* index_dir, int device, uint32_t shard, uint32_t nshards, const char* lineage_path, krepp_index_t** out);
 void krepp_index_close(krepp_index_t* ix);
 int krepp_index_info(const krepp_index_t* ix, krepp_index_info_t* out);

@@ -167,6 +167,7 @@ def load_library():
     L.krepp_index_open_shard.argtypes = [C.c_char_p, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]
     L.krepp_index_open_tree.argtypes = [C.c_char_p, C.c_int, C.c_uint32, C.c_uint32, C.c_char_p, C.POINTER(C.c_void_p)]
     L.krepp_geometry_open.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_void_p)]
+    L.krepp_geometry_open_positions.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
     L.krepp_sequence_rho.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.krepp_sketch_write.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_char_p, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
     L.krepp_sketch_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
@@ -224,7 +225,7 @@ class Index:
 
     @classmethod
     def geometry(cls, k: int = 26, w: int | None = None, h: int | None = None, m: int = 4, r: int = 1, frac: bool = True, seed: int | None = None,
-                 device: int = 0) -> "Index":
+                 device: int = 0, ppos: bytes | None = None) -> "Index":
         """krepp_geometry_open: the LSH geometry of a library still to be built (what `krepp sketch` / `krepp index` set up before
         reading a genome); serves extract_mers, sequence_rho and sketch_write."""
         self = cls.__new__(cls)
@@ -232,7 +233,11 @@ class Index:
         self._h = C.c_void_p()
         w = k + 6 if w is None else w
         h = k - 16 if h is None else h
-        _check(L.krepp_geometry_open(k, w, h, m, r, int(frac), -1 if seed is None else seed, device, C.byref(self._h)))
+        if ppos is not None:  # krepp_geometry_open_positions: the caller's hash positions instead of a draw
+            assert len(ppos) == h
+            _check(L.krepp_geometry_open_positions(k, w, h, m, r, int(frac), bytes(ppos), device, C.byref(self._h)))
+        else:
+            _check(L.krepp_geometry_open(k, w, h, m, r, int(frac), -1 if seed is None else seed, device, C.byref(self._h)))
         self.info = IndexInfo()
         _check(L.krepp_index_info(self._h, C.byref(self.info)))
         self.device = device

@@ -307,13 +307,35 @@ int krepp_index_open_lineages(const char* index_dir, int device, uint32_t shard,
   return open_index(index_dir, device, shard, nshards, lineage_path, true, out);
 }
 
+static int geometry_open(uint32_t k, uint32_t w, uint32_t h, uint32_t m, uint32_t r, int frac, int64_t seed, const uint8_t* given_ppos, int device, krepp_index_t** out);
+
 int krepp_geometry_open(uint32_t k, uint32_t w, uint32_t h, uint32_t m, uint32_t r, int frac, int64_t seed, int device, krepp_index_t** out)
+{
+  return geometry_open(k, w, h, m, r, frac, seed, nullptr, device, out);
+}
+
+int krepp_geometry_open_positions(uint32_t k, uint32_t w, uint32_t h, uint32_t m, uint32_t r, int frac, const uint8_t* ppos, int device, krepp_index_t** out)
+{
+  if (!ppos) return fail(KREPP_ERR_ARG, "krepp_geometry_open_positions: null argument");
+  return geometry_open(k, w, h, m, r, frac, -1, ppos, device, out);
+}
+
+static int geometry_open(uint32_t k, uint32_t w, uint32_t h, uint32_t m, uint32_t r, int frac, int64_t seed, const uint8_t* given_ppos, int device, krepp_index_t** out)
 {
   if (!out) return fail(KREPP_ERR_ARG, "krepp_geometry_open: null argument");
   *out = nullptr;
   auto* ix = new krepp_index;
   { // the configuration is judged before any device is looked for, as the reference judges it before reading anything
     std::vector<uint8_t> ppos, npos;
+    if (given_ppos && k >= 19 && k <= 31 && h >= 3 && h <= 15 && h < k) { // the caller's hash positions: distinct, below k; the kept positions are the others, ascending
+      std::vector<uint8_t> taken(k, 0);
+      for (uint32_t i = 0; i < h; ++i) {
+        if (given_ppos[i] >= k || taken[given_ppos[i]]) { delete ix; return fail(KREPP_ERR_ARG, "krepp_geometry_open_positions: the %u hash positions must be distinct and below k", h); }
+        taken[given_ppos[i]] = 1;
+      }
+      for (uint32_t p = k; p-- > 0;) if (taken[p]) ppos.push_back((uint8_t)p);  // descending (ref src/lshf.cpp:143)
+      for (uint32_t p = 0; p < k; ++p) if (!taken[p]) npos.push_back((uint8_t)p); // ascending (ref src/lshf.cpp:144)
+    } else
     if (k >= 19 && k <= 31 && h >= 3 && h <= 15 && h < k) lsh_positions(k, h, seed >= 0, (uint32_t)seed, ppos, npos);
     std::string err = ix->host.set_geometry(k, w, h, m, r, frac != 0, ppos, npos);
     if (!err.empty()) { delete ix; return fail(KREPP_ERR_ARG, "%s", err.c_str()); }

@@ -186,3 +186,28 @@ def test_place_on_lineages_equals_the_reference(tmp_path):
     sa = run(EXE, "place", "--summarize", "-i", idx, "-q", str(sub), "-l", str(lin)).splitlines()
     sb = run(REF, "place", "--summarize", "-i", idx, "-q", str(sub), "-l", str(lin)).splitlines()
     assert sa[1] == sb[1] and len(sa) == len(sb)
+
+
+@needs_shim
+@pytest.mark.parametrize("with_tree,pre", [(True, ()), (False, ("--seed", "5"))], ids=["guide_tree", "no_tree_seeded"])
+def test_shim_index_equals_the_reference_library(with_tree, pre, tmp_path):
+    """`krepp_gpu index`: the reference's own driver (CLI11, LSH position draw, input map, guide tree, RSeq / kseq reader) with
+    build_index / save_index redirected to the library builder (oracle/shim/gpubuilder.hpp).  The library must be the stock
+    binary's up to the numbering of colours above the tree nodes, and the stock `krepp dist` must answer alike from either."""
+    import shutil
+    from libraries import assert_same_library, read_library
+    if not os.path.exists(REF):
+        pytest.skip("oracle/_ref/krepp not built")
+    w = str(tmp_path)
+    shutil.copytree(os.path.join(SMALL, "genomes"), os.path.join(w, "genomes"))
+    for f in ("input_map.tsv", "tree.nwk"):
+        shutil.copy(os.path.join(SMALL, f), w)
+    args = ["-k", "23", "-w", "29", "-h", "8", "-m", "3", "-r", "1", "-i", "input_map.tsv", *(["-t", "tree.nwk"] if with_tree else [])]
+    for exe, out in ((SHIM, "gpu_index"), (REF, "ref_index")):
+        r = subprocess.run([exe, *pre, "index", *args, "-o", out], cwd=w, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+    assert_same_library(read_library(os.path.join(w, "gpu_index")), read_library(os.path.join(w, "ref_index")))
+    q = os.path.join(SMALL, "reads.fq")
+    a = sorted(run(REF, "dist", "-i", os.path.join(w, "gpu_index"), "-q", q).splitlines()[2:])
+    b = sorted(run(REF, "dist", "-i", os.path.join(w, "ref_index"), "-q", q).splitlines()[2:])
+    assert a == b and len(a) > 100

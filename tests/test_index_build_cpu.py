@@ -182,3 +182,20 @@ def test_builder_argument_errors(tmp_path):
     with pytest.raises(krepp_b200.KreppError, match="ascending list of leaf ranks"):
         b.write(str(tmp_path / "x"))
     b.close(); g.close()
+
+
+def test_geometry_with_given_positions():
+    """krepp_geometry_open_positions: the masks of a drawn geometry come back when its positions are handed in (any order), and
+    bad positions are refused."""
+    drawn = krepp_b200.Index.geometry(27, 35, 11, 4, 1, True, device=NONE)
+    ppos = [p for p in range(31, -1, -1) if (drawn.info.mask_hash_bp >> (2 * p)) & 3]
+    assert ppos == [26, 24, 22, 21, 17, 14, 8, 7, 5, 3, 2]  # the reference's default draw (SURVEY.md 8 a4)
+    given = krepp_b200.Index.geometry(27, 35, 11, 4, 1, True, device=NONE, ppos=bytes(reversed(ppos)))
+    assert (given.info.mask_hash_bp, given.info.mask_drop_lr, given.info.nrows) == (drawn.info.mask_hash_bp, drawn.info.mask_drop_lr, drawn.info.nrows)
+    other = krepp_b200.Index.geometry(27, 35, 11, 4, 1, True, device=NONE, ppos=bytes(range(11)))
+    assert other.info.mask_hash_bp == (1 << 22) - 1
+    for bad in (bytes([3] * 11), bytes(list(range(10)) + [27])):
+        with pytest.raises(krepp_b200.KreppError, match="distinct and below k"):
+            krepp_b200.Index.geometry(27, 35, 11, 4, 1, True, device=NONE, ppos=bad)
+    for g in (drawn, given, other):
+        g.close()
