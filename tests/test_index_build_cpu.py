@@ -199,3 +199,70 @@ def test_geometry_with_given_positions():
             krepp_b200.Index.geometry(27, 35, 11, 4, 1, True, device=NONE, ppos=bad)
     for g in (drawn, given, other):
         g.close()
+
+
+def random_newick(rng, names, max_children=4):
+    """A random rooted tree over the names: leaves are joined in random groups of 2..max_children until one node is left."""
+    nodes = list(names)
+    rng.shuffle(nodes)
+    while len(nodes) > 1:
+        k = int(min(len(nodes), rng.integers(2, max_children + 1)))
+        at = int(rng.integers(0, len(nodes) - k + 1))
+        nodes[at:at + k] = ["(" + ",".join(nodes[at:at + k]) + ")"]
+    return nodes[0] + ";"
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_colours_on_random_trees(seed, tmp_path):
+    """Random trees with up to four children per node and random reference sets: every colour expands to exactly its set, the
+    colour of a whole subtree is the subtree's node, equal sets share one id, and the record holds no colour that nothing reaches."""
+    rng = np.random.default_rng(100 + seed)
+    n = int(rng.integers(5, 60))
+    names = [f"L{i:02d}" for i in range(n)]
+    nwk = random_newick(rng, names, max_children=2 if seed % 2 else 4)
+    g = krepp_b200.Index.geometry(21, 25, 7, 4, 1, True, device=NONE)
+    b = krepp_b200.LibraryBuilder(g, nwk, names)
+    sets = random_sets(rng, n, 400)
+    # clustered sets too (runs of neighbouring leaves: whole subtrees and near-subtrees), as real libraries have
+    for _ in range(200):
+        a = int(rng.integers(0, n)); z = int(rng.integers(a + 1, n + 1))
+        s = set(range(a, z))
+        if rng.random() < 0.5 and len(s) > 1:
+            s.discard(int(rng.integers(a, z)))
+        sets.append(tuple(sorted(s)))
+    sets = sorted(set(sets))
+    set_begin = np.zeros(len(sets) + 1, np.uint64)
+    set_begin[1:] = np.cumsum([len(s) for s in sets])
+    keys = np.arange(1, 2 * len(sets) + 1, dtype=np.uint64) << np.uint64(18)
+    set_of = np.concatenate([np.arange(len(sets)), np.arange(len(sets))[::-1]]).astype(np.uint32)  # every set used by two k-mers
+    b.set_union(keys, set_of, set_begin, np.array([x for s in sets for x in s], np.uint32), np.full(n, 0.2))
+    out = str(tmp_path / "index")
+    b.write(out)
+    lib = read_library(out)
+    exp = colour_leaves(lib)
+    ix = krepp_b200.Index(out, device=NONE)
+    se_of_rank = {b.leaf_rank(ix.node_name(se)): se for se in range(1, ix.info.nnodes + 1) if ix.node_name(se) in set(names)}
+    assert len(se_of_rank) == n
+    colour_of_set = {}
+    for i, colour in zip(set_of, lib["se"]):
+        want = frozenset(se_of_rank[r] for r in sets[int(i)])
+        assert exp[int(colour)] == want
+        assert colour_of_set.setdefault(int(i), int(colour)) == int(colour)
+    # a set that is everything below a node is that node
+    below = {exp[se]: se for se in range(1, ix.info.nnodes + 1)}
+    for i, colour in colour_of_set.items():
+        want = frozenset(se_of_rank[r] for r in sets[i])
+        if want in below:
+            assert colour == below[want]
+    # every colour above the tree nodes is reachable from a k-mer's colour or from a node with more than two children
+    reach, todo = set(), [int(c) for c in lib["se"]] + list(range(1, ix.info.nnodes + 1))
+    while todo:
+        c = todo.pop()
+        if c in reach or c == 0:
+            continue
+        reach.add(c)
+        a, z = int(lib["pse"][c][0]), int(lib["pse"][c][1])
+        if not (a == 0 and z == c):
+            todo += [a, z]
+    assert reach == set(range(1, lib["nsubsets"]))
+    ix.close(); b.close(); g.close()
