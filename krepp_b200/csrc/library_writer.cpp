@@ -12,9 +12,10 @@
 //     colour(S) at the lowest tree node g above S:  g itself when S is every leaf below g; else the colours of S restricted to
 //     each child of g that S touches, folded from the right into pairs  (p1, (p2, (... , pn))).
 // A node with more than two children gets the same right fold over its children as its own pair, so the tails are shared.
-// (The reference writes (first child, 0) for such a node -- the sum of the other children is no colour it knows, ref
-// src/record.cpp:172-174 -- and loses their references at query time; SURVEY.md calls it the multifurcation quirk.  Guide trees
-// are binary in every configuration of the benchmark; on a multifurcating tree this writer keeps all references.)
+// (The reference gives such a node the pair (first child, sum of the others), ref src/record.cpp:172-174, which is the null id
+// unless some k-mer's set is exactly the other children -- SURVEY.md 7.7, the multifurcation quirk -- and a k-mer held by every
+// child gets a separate colour there, the node itself here.  The k-mers expand alike: tests/test_index_build_cpu.py checks all
+// 6.9 M of the reference's own toy library, whose guide tree has multifurcations.)
 // Ids: 0 = null, 1..nnodes = the tree's nodes in post-order (Record::make_compact ref src/record.cpp:132-154 numbers them
 // first too), then the interned pairs in order of creation.  The reference's numbering above the nodes follows a hash map's
 // iteration order and differs from run to run; nothing reads more into an id than its expansion.

@@ -131,7 +131,7 @@ def random_sets(rng, nleaves, n_sets):
                                  "(((A,B),(C,D)),((E,F),(G,(H,I))));"], ids=["multifurcating", "caterpillar", "balanced"])
 def test_colours_expand_to_their_sets_on_any_tree(nwk, tmp_path):
     """Every distinct reference set gets a colour that expands to exactly that set; a whole subtree is the tree node itself; pairs
-    are shared.  (The reference cannot pin multifurcating trees: it drops references there, see library_writer.cpp.)"""
+    are shared.  (Synthetic sets; the reference's own multifurcating fixture is test_toy_library_equals_the_reference.)"""
     rng = np.random.default_rng(5)
     names = list("ABCDEFGHI")
     g = krepp_b200.Index.geometry(21, 25, 7, 4, 1, True, device=NONE)
@@ -266,3 +266,34 @@ def test_colours_on_random_trees(seed, tmp_path):
             todo += [a, z]
     assert reach == set(range(1, lib["nsubsets"]))
     ix.close(); b.close(); g.close()
+
+
+TOY_TARBALL = "/root/reference/test/references_toy.tar.gz"
+
+
+@needs_ref
+@pytest.mark.skipif(not os.path.exists(TOY_TARBALL), reason="the reference's toy genomes are only in this container")
+def test_toy_library_equals_the_reference(tmp_path):
+    """Configuration 1, the reference's own fixture: 25 genomes (71 Mbp, draft assemblies of thousands of contigs) on a guide tree
+    with multifurcations.  The library written from the oracle's leaf tables has the reference-built toy index's metadata, offsets,
+    encodings and rho byte for byte, and each of its 6.9 M k-mers expands to the same references.  (The reference's colours of the
+    multifurcating nodes themselves expand to their first child only -- SURVEY.md 7.7 -- but no k-mer of its index carries them: a
+    k-mer held by every child gets a separate colour there, the node itself here.)"""
+    from libraries import same_colours_vectorised
+    toy = conftest.TOY_DIR
+    subprocess.run(["tar", "-C", str(tmp_path), "-xzf", TOY_TARBALL], check=True)
+    subprocess.run("xz -d -f " + str(tmp_path / "references_toy") + "/*.xz", shell=True, check=True)
+    ref = read_library(os.path.join(toy, "index_toy"))
+    rows = [l.rstrip("\n").split("\t") for l in open(os.path.join(toy, "input_map.tsv")) if l.strip()]
+    names, paths = [r[0] for r in rows], {r[0]: str(tmp_path / r[1]) for r in rows}
+    mine_dir = str(tmp_path / "index")
+    nk, nsub = host_build(ref, mine_dir, open(os.path.join(toy, "tree_toy.nwk")).read(), names, paths)
+    mine = read_library(mine_dir)
+    for f in ("metadata", "inc_bytes", "reflist", "tree"):
+        assert mine[f] == ref[f], f
+    assert nk == ref["nkmers"] == 6934548 and (mine["enc"] == ref["enc"]).all() and mine["rho"].tobytes() == ref["rho"].tobytes()
+    assert same_colours_vectorised(mine, ref)
+    a, b = colour_leaves(mine), colour_leaves(ref)
+    leaves = [se for se in range(1, ref["nnodes"]) if a[se] == frozenset([se])]
+    assert len(leaves) == 25 and a[ref["nnodes"] - 1] == frozenset(leaves)     # here the root is every reference ...
+    assert b[ref["nnodes"] - 1] < frozenset(leaves)                             # ... in the reference's record it is not
