@@ -141,7 +141,11 @@ extern "C" int krepp_builder_create(const krepp_index_t* geom, const char* nwk_t
   if (!err.empty()) { delete b; return set_error(KREPP_ERR_IO, "%s", err.c_str()); }
   for (uint32_t rank = 0; rank < b->tree.nleaves; ++rank) {
     const std::string& nm = b->tree.name[b->tree.leaf_se[rank]];
-    if (!b->leaf_by_name.emplace(nm, rank).second) { delete b; return set_error(KREPP_ERR_UNSUPPORTED, "the guide tree has two leaves named %s", nm.c_str()); }
+    if (!b->leaf_by_name.emplace(nm, rank).second) {
+      const int rc = set_error(KREPP_ERR_UNSUPPORTED, "the guide tree has two leaves named %s", nm.c_str()); // (nm lives in *b: the message first)
+      delete b;
+      return rc;
+    }
   }
   b->leaf_rho.assign(b->tree.nleaves, 0.0);
   b->leaf_added.assign(b->tree.nleaves, 0);
