@@ -1,7 +1,8 @@
 """Host threads under ThreadSanitizer.  (1) The host reader's chunk-parallel FASTQ framing (krepp_reader_set_threads; row a1 / f1) under ThreadSanitizer: host_io.cpp and
 index_image.cpp compiled with -fsanitize=thread into a small driver (tests/native/reader_tsan.cpp) that reads a FASTQ file with
 one and with eight threads and compares the records.  (2) The index loader (threads pread the k-mer table and flatten the colour
-lists level by level): the golden index whole and as three bucket-range shards.  A data race makes the driver exit non-zero
+lists level by level): the golden index whole and as three bucket-range shards.  (3) The library writer's table stage (threads
+over ranges of k-mers, each writing the offsets of the rows that end in its range).  A data race makes the driver exit non-zero
 (TSAN_OPTIONS=halt_on_error)."""
 import os
 import subprocess
@@ -19,7 +20,7 @@ OUT = os.path.join(ROOT, "oracle", "_build", "reader_tsan")
 def driver():
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     r = subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-I/usr/local/cuda/include", "-o", OUT, SRC,
-                        os.path.join(CSRC, "host_io.cpp"), os.path.join(CSRC, "index_image.cpp"), "-lz", "-lpthread"], capture_output=True, text=True)
+                        os.path.join(CSRC, "host_io.cpp"), os.path.join(CSRC, "index_image.cpp"), os.path.join(CSRC, "library_writer.cpp"), "-lz", "-lpthread"], capture_output=True, text=True)
     if r.returncode != 0:
         pytest.skip("ThreadSanitizer build failed here: " + r.stderr[-300:])
     return OUT
@@ -58,3 +59,10 @@ def test_index_loader_has_no_data_race(driver):
     if os.path.isdir(toy):  # 6.9 M entries: the table is read by several threads
         r = subprocess.run([driver, "--load", toy], capture_output=True, text=True, env=env, timeout=600)
         assert r.returncode == 0 and "1 shard(s) hold 6934548 entries" in r.stdout, (r.stdout + r.stderr)[-3000:]
+
+
+def test_library_writer_has_no_data_race(driver, tmp_path):
+    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=1:exitcode=66")
+    r = subprocess.run([driver, "--write", str(tmp_path / "index"), str(6 << 20)], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+    assert "6291456 k-mers written, 16 colour ids, offsets as counted sequentially" in r.stdout
