@@ -25,6 +25,7 @@
 #include <sys/stat.h>
 #include <thread>
 #include <unistd.h>
+#include <unordered_map>
 #include <vector>
 
 namespace {
@@ -434,6 +435,7 @@ static int run_index(const Options& o)
   krepp_index_t* geom = open_geometry(o);
   std::vector<std::string> names;
   std::vector<std::pair<std::string, std::string>> todo; // (name, path), one per distinct name: a later line overrides (ref src/krepp.cpp:157-158)
+  std::unordered_map<std::string, size_t> todo_at;
   { // IndexMultiple::read_input_file ref src/krepp.cpp:147-162
     FILE* f = fopen(o.index_dir.c_str(), "r");
     if (!f) error_exit("Error opening " + o.index_dir);
@@ -453,9 +455,9 @@ static int run_index(const Options& o)
       const std::string name = line.substr(0, tab), path = line.substr(tab + 1, tab2 == std::string::npos ? std::string::npos : tab2 - tab - 1);
       if (path.empty()) error_exit("Failed to read the reference name to path/URL mapping!");
       names.push_back(name);
-      bool seen = false;
-      for (auto& np : todo) if (np.first == name) { np.second = path; seen = true; }
-      if (!seen) todo.emplace_back(name, path);
+      const auto known = todo_at.find(name);
+      if (known != todo_at.end()) todo[known->second].second = path;
+      else { todo_at.emplace(name, todo.size()); todo.emplace_back(name, path); }
     }
   }
   std::string nwk;
