@@ -297,3 +297,27 @@ def test_toy_library_equals_the_reference(tmp_path):
     leaves = [se for se in range(1, ref["nnodes"]) if a[se] == frozenset([se])]
     assert len(leaves) == 25 and a[ref["nnodes"] - 1] == frozenset(leaves)     # here the root is every reference ...
     assert b[ref["nnodes"] - 1] < frozenset(leaves)                             # ... in the reference's record it is not
+
+
+@needs_ref
+def test_partial_libraries_written_into_one_directory(tmp_path_factory, tmp_path):
+    """Three builds with one LSH residue each (m = 4, r = 0, 2, 3, --no-frac) into ONE directory, as `krepp index` is run for a
+    library split by residue (ref src/krepp.cpp:66-108): every partial equals the reference's, the reference's `dist` reads the
+    directory alike, and this implementation's loader merges it to the same image as the reference-built directory."""
+    from variants import build_partials
+    ref_dir = build_partials(tmp_path_factory.getbasetemp(), rs=("0", "2", "3"), frac=False)
+    names, paths = names_and_paths()
+    nwk = open(os.path.join(SMALL, "tree.nwk")).read()
+    mine_dir = str(tmp_path / "index")
+    for r in (0, 2, 3):
+        sfx = f"-m4r{r}-no_frac"
+        md = open(os.path.join(ref_dir, "metadata" + sfx), "rb").read()
+        geom = dict(k=md[0], w=md[1], h=md[2], m=4, r=r, frac=0, ppos=bytes(md[16:16 + md[2]]))
+        host_build(geom, mine_dir, nwk, names, paths)
+        for f in ("metadata", "inc", "reflist", "tree"):
+            assert open(os.path.join(mine_dir, f + sfx), "rb").read() == open(os.path.join(ref_dir, f + sfx), "rb").read(), (f, r)
+    assert sorted(os.listdir(mine_dir)) == sorted(os.listdir(ref_dir))
+    assert ref_dist(mine_dir) == ref_dist(ref_dir)
+    a, b = krepp_b200.Index(mine_dir, device=NONE), krepp_b200.Index(ref_dir, device=NONE)
+    assert a.info.nkmers == b.info.nkmers and a.info.nrows == b.info.nrows and a.host_checksums()[1] == b.host_checksums()[1]
+    a.close(); b.close()
